@@ -1,0 +1,184 @@
+/*
+ * pnec_b200.h — C-ABI of the B200-native PNEC frame-pair solver.
+ *
+ * This is the drop-in boundary for the reference's Ceres-backed refinement
+ * (tum-vision/pnec).  Every entry point names the reference interface it
+ * replaces (paths relative to the reference tree).  Plain pointers and sizes
+ * only: no C++/torch/Eigen types cross this boundary.
+ *
+ * Data layout (identical to what the reference already holds in memory):
+ *   bearing vectors   double[n][3]   == std::vector<Eigen::Vector3d>::data()
+ *   covariances       double[n][9]   == std::vector<Eigen::Matrix3d>::data()
+ *                                       (column-major 3x3; the path only ever
+ *                                       forms x^T S x, so only the symmetric
+ *                                       part of S matters)
+ *   pose              double[7]      qx qy qz qw tx ty tz
+ *                                       == Sophus::SE3d memory order
+ * A batch is the concatenation of B independent frame pairs; problem b owns
+ * correspondences [offsets[b], offsets[b+1]).  `offsets == NULL` means a
+ * uniform batch of `n_per_problem` correspondences each.
+ */
+#ifndef PNEC_B200_H_
+#define PNEC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PNEC_B200_VERSION_MAJOR 0
+#define PNEC_B200_VERSION_MINOR 1
+
+/* Residual variants.
+ *   NEC        include/optimization/nec_residual.h:47-69
+ *   TARGET     include/optimization/pnec_residual.h:81-111  (PNEC::CeresSolver default)
+ *   HOST       include/optimization/pnec_residual.h:50-79
+ *   SYMMETRIC  include/optimization/pnec_residual.h:113-150 (pypnec.pyceres)
+ */
+typedef enum pnec_variant {
+  PNEC_VARIANT_NEC = 0,
+  PNEC_VARIANT_TARGET = 1,
+  PNEC_VARIANT_HOST = 2,
+  PNEC_VARIANT_SYMMETRIC = 3
+} pnec_variant;
+
+/* Where the batch pointers live. */
+typedef enum pnec_memspace {
+  PNEC_MEM_HOST = 0,  /* library stages H2D / D2H itself and synchronises   */
+  PNEC_MEM_DEVICE = 1 /* all pointers are device pointers, call is async     */
+} pnec_memspace;
+
+/* Return codes of the entry points (0 == success). */
+typedef enum pnec_error {
+  PNEC_OK = 0,
+  PNEC_ERR_INVALID_ARGUMENT = -1,
+  PNEC_ERR_CUDA = -2,
+  PNEC_ERR_NO_DEVICE = -3,
+  PNEC_ERR_UNSUPPORTED = -4,
+  PNEC_ERR_ALLOC = -5
+} pnec_error;
+
+/* Per-problem termination status — the information the reference keeps in
+ * ceres::Solver::Summary (include/optimization/pnec_ceres.h:88) and never
+ * exposes. */
+typedef enum pnec_status {
+  PNEC_STATUS_CONVERGED_FUNCTION = 0,  /* |dcost| <= function_tolerance*cost  */
+  PNEC_STATUS_CONVERGED_PARAMETER = 1, /* |dx| <= parameter_tolerance*(|x|+tol) */
+  PNEC_STATUS_CONVERGED_GRADIENT = 2,  /* max|g| <= gradient_tolerance        */
+  PNEC_STATUS_CONVERGED_RADIUS = 3,    /* trust region radius <= min          */
+  PNEC_STATUS_MAX_ITERATIONS = 4,      /* NO_CONVERGENCE in Ceres terms       */
+  PNEC_STATUS_FAILURE = 5,             /* too many consecutive invalid steps  */
+  PNEC_STATUS_NONFINITE = 6,           /* non-finite cost at the start point  */
+  PNEC_STATUS_EMPTY = 7                /* zero correspondences: pose unchanged */
+} pnec_status;
+
+/* Solver options.  Field names and defaults are those of
+ * ceres::Solver::Options as the reference uses it: always default-constructed
+ * (src/optimization/pnec_ceres.cc:43-48, src/rel_pose_estimation/pnec.cc:355).
+ * `regularization` is Options::regularization_
+ * (include/rel_pose_estimation/pnec_config.h:50). */
+typedef struct pnec_solver_opts {
+  int32_t variant;                           /* pnec_variant                  */
+  int32_t max_num_iterations;                /* 50                            */
+  int32_t max_num_consecutive_invalid_steps; /* 5                             */
+  int32_t jacobi_scaling;                    /* 1                             */
+  double regularization;                     /* 1e-13                         */
+  double function_tolerance;                 /* 1e-6                          */
+  double gradient_tolerance;                 /* 1e-10                         */
+  double parameter_tolerance;                /* 1e-8                          */
+  double initial_trust_region_radius;        /* 1e4                           */
+  double max_trust_region_radius;            /* 1e16                          */
+  double min_trust_region_radius;            /* 1e-32                         */
+  double min_relative_decrease;              /* 1e-3                          */
+  double min_lm_diagonal;                    /* 1e-6                          */
+  double max_lm_diagonal;                    /* 1e32                          */
+} pnec_solver_opts;
+
+/* A batch of independent frame pairs. */
+typedef struct pnec_batch {
+  int64_t num_problems;      /* B                                             */
+  int64_t n_per_problem;     /* uniform N when offsets == NULL                */
+  const int64_t *offsets;    /* B+1 entries, HOST pointer always, or NULL     */
+  int32_t memspace;          /* pnec_memspace of every pointer below          */
+  int32_t reserved;
+  const double *bvs_host;    /* [total][3]  f1, frame-1 ("host") bearings     */
+  const double *bvs_target;  /* [total][3]  f2, frame-2 ("target") bearings   */
+  const double *covs_target; /* [total][9]  TARGET, SYMMETRIC; HOST uses it too
+                                (PNECCeres::Optimize(..., covs, reg, Host))  */
+  const double *covs_host;   /* [total][9]  SYMMETRIC only, else NULL         */
+  const double *poses;       /* [B][7]      start pose (solve) / eval pose    */
+} pnec_batch;
+
+/* Outputs of a batched solve.  Any pointer except `poses` may be NULL. */
+typedef struct pnec_solve_out {
+  double *poses;       /* [B][7] unit quaternion (x,y,z,w) + unit translation
+                          == PNECCeres::Result(), src/optimization/pnec_ceres.cc:201-206 */
+  int32_t *status;     /* [B] pnec_status                                     */
+  int32_t *iterations; /* [B] LM iterations taken (Summary::iterations.size()-1) */
+  double *cost;        /* [B] final cost 1/2 sum r^2 at the returned pose     */
+  double *initial_cost;/* [B] cost at the start pose                          */
+} pnec_solve_out;
+
+/* Outputs of one fused evaluation (residual + Jacobian + J^T J reduction) at a
+ * fixed pose per problem.  Tangent order (theta, phi, d1, d2, d3) follows the
+ * parameter-block order of problem.AddResidualBlock(cf, nullptr, &theta_,
+ * &phi_, q) + EigenQuaternionManifold, src/optimization/pnec_ceres.cc:99-106. */
+typedef struct pnec_eval_out {
+  double *cost;     /* [B]      1/2 sum r^2                                   */
+  double *gradient; /* [B][5]   J^T r                                         */
+  double *jtj;      /* [B][15]  upper triangle of J^T J, row-major packed     */
+} pnec_eval_out;
+
+typedef struct pnec_handle pnec_handle;
+
+/* Library / error plumbing. */
+int pnec_version(void);              /* major*1000 + minor                    */
+const char *pnec_last_error(void);   /* thread-local message of the last failure */
+const char *pnec_status_string(int32_t status);
+
+/* ceres::Solver::Options() defaults + Options::regularization_ = 1e-13, variant TARGET. */
+void pnec_solver_opts_default(pnec_solver_opts *opts);
+
+/* A handle owns the device scratch and a stream-ordered staging area; it is
+ * the analogue of one `PNECCeres optimizer;` local
+ * (src/rel_pose_estimation/pnec.cc:355) and is re-entrant per handle. */
+int pnec_create(int device, pnec_handle **out);
+void pnec_destroy(pnec_handle *h);
+
+/* Batched LM refinement, all iterations on device.
+ * Replaces PNECCeres::Optimize (both overloads, src/optimization/pnec_ceres.cc:70-168)
+ * and NECCeres::Optimize (src/optimization/nec_ceres.cc:73-101), i.e. the
+ * bodies of PNEC::CeresSolver / CeresSolverFull / NECCeresSolver
+ * (src/rel_pose_estimation/pnec.cc:350-411) and pypnec.pyceres / pyceresnec
+ * (python/pypnec.cpp:50-82), for B frame pairs at once.
+ * `cuda_stream` is a cudaStream_t (NULL = default stream).
+ * HOST memspace: returns after results are in the caller's buffers.
+ * DEVICE memspace: enqueues on the stream and returns. */
+int pnec_solve_batch(pnec_handle *h, const pnec_batch *batch,
+                     const pnec_solver_opts *opts, const pnec_solve_out *out,
+                     void *cuda_stream);
+
+/* One fused residual + analytic 5-DoF Jacobian + J^T J / J^T r / cost pass.
+ * Replaces one ceres::Problem evaluation, i.e. N x
+ * NumericDiffCostFunction<..., CENTRAL, 1,1,1,4>::Evaluate
+ * (src/optimization/pnec_ceres.cc:92-101) plus the normal-equation assembly
+ * inside ceres::Solve (:110). */
+int pnec_eval_batch(pnec_handle *h, const pnec_batch *batch, int32_t variant,
+                    double regularization, const pnec_eval_out *out,
+                    void *cuda_stream);
+
+/* Mean PNEC energy without regularisation at the given poses — the parity
+ * metric pnec::common::CostFunction, src/common/common.cc:237-259. */
+int pnec_cost_function_batch(pnec_handle *h, const pnec_batch *batch,
+                             double *out_mean_energy /* [B] */,
+                             void *cuda_stream);
+
+/* Number of kernels this handle has launched so far (bench bookkeeping). */
+int64_t pnec_launch_count(const pnec_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* PNEC_B200_H_ */

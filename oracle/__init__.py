@@ -1,0 +1,263 @@
+"""ctypes front-end of the CPU oracle (oracle/pnec_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py.  The product package
+(pnec_b200/) never imports this module.
+
+Parity status: residual functors pinned against the reference's numpy energies
+(tests/golden/); the Ceres LM loop is restated from upstream behaviour and is
+PARITY UNPINNED (Ceres is neither vendored by the reference nor installed here).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libpnec_oracle.so")
+
+NEC, TARGET, HOST, SYMMETRIC = 0, 1, 2, 3
+JAC_NUMERIC_CENTRAL, JAC_ANALYTIC = 0, 1
+
+STATUS_NAMES = (
+    "converged_function",
+    "converged_parameter",
+    "converged_gradient",
+    "converged_radius",
+    "max_iterations",
+    "failure",
+    "nonfinite",
+    "empty",
+)
+
+
+class OracleOpts(ctypes.Structure):
+    _fields_ = [
+        ("variant", ctypes.c_int32),
+        ("max_num_iterations", ctypes.c_int32),
+        ("max_num_consecutive_invalid_steps", ctypes.c_int32),
+        ("jacobi_scaling", ctypes.c_int32),
+        ("regularization", ctypes.c_double),
+        ("function_tolerance", ctypes.c_double),
+        ("gradient_tolerance", ctypes.c_double),
+        ("parameter_tolerance", ctypes.c_double),
+        ("initial_trust_region_radius", ctypes.c_double),
+        ("max_trust_region_radius", ctypes.c_double),
+        ("min_trust_region_radius", ctypes.c_double),
+        ("min_relative_decrease", ctypes.c_double),
+        ("min_lm_diagonal", ctypes.c_double),
+        ("max_lm_diagonal", ctypes.c_double),
+        ("jacobian_mode", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+    ]
+
+
+class OracleInfo(ctypes.Structure):
+    _fields_ = [
+        ("status", ctypes.c_int32),
+        ("iterations", ctypes.c_int32),
+        ("num_successful_steps", ctypes.c_int32),
+        ("num_unsuccessful_steps", ctypes.c_int32),
+        ("initial_cost", ctypes.c_double),
+        ("final_cost", ctypes.c_double),
+        ("final_radius", ctypes.c_double),
+        ("final_gradient_max_norm", ctypes.c_double),
+    ]
+
+
+INFO_DTYPE = np.dtype(
+    [
+        ("status", np.int32),
+        ("iterations", np.int32),
+        ("num_successful_steps", np.int32),
+        ("num_unsuccessful_steps", np.int32),
+        ("initial_cost", np.float64),
+        ("final_cost", np.float64),
+        ("final_radius", np.float64),
+        ("final_gradient_max_norm", np.float64),
+    ]
+)
+
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle/pnec_oracle.c (gcc) into oracle/_build/; returns the path."""
+    if force or not os.path.exists(_LIB_PATH) or (
+        os.path.exists(os.path.join(_HERE, "pnec_oracle.c"))
+        and os.path.getmtime(os.path.join(_HERE, "pnec_oracle.c")) > os.path.getmtime(_LIB_PATH)
+    ):
+        subprocess.run(["make", "-C", _HERE, "-s"] + (["-B"] if force else []), check=True)
+    return _LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        L = ctypes.CDLL(_LIB_PATH)
+        dp = ctypes.POINTER(ctypes.c_double)
+        L.oracle_opts_default.argtypes = [ctypes.POINTER(OracleOpts)]
+        L.oracle_opts_default.restype = None
+        L.oracle_eval.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int64, dp, dp, dp, dp,
+                                  ctypes.c_double, dp, dp, dp, dp]
+        L.oracle_eval.restype = ctypes.c_int
+        L.oracle_solve.argtypes = [ctypes.POINTER(OracleOpts), ctypes.c_int64, dp, dp, dp, dp, dp,
+                                   dp, ctypes.POINTER(OracleInfo)]
+        L.oracle_solve.restype = ctypes.c_int
+        L.oracle_solve_batch.argtypes = [ctypes.POINTER(OracleOpts), ctypes.c_int64,
+                                         ctypes.c_int64, ctypes.POINTER(ctypes.c_int64), dp, dp,
+                                         dp, dp, dp, dp, ctypes.c_void_p, ctypes.c_int]
+        L.oracle_solve_batch.restype = ctypes.c_int
+        L.oracle_max_threads.restype = ctypes.c_int
+        L.oracle_angles_from_vec.argtypes = [dp, dp, dp]
+        L.oracle_angles_from_vec.restype = None
+        L.oracle_rotational_difference_deg.argtypes = [dp, dp]
+        L.oracle_rotational_difference_deg.restype = ctypes.c_double
+        L.oracle_translational_difference_deg.argtypes = [dp, dp, ctypes.c_int]
+        L.oracle_translational_difference_deg.restype = ctypes.c_double
+        L.oracle_cost_function.argtypes = [ctypes.c_int64, dp, dp, dp, dp]
+        L.oracle_cost_function.restype = ctypes.c_double
+        L.oracle_energy.argtypes = [ctypes.c_int, ctypes.c_int64, dp, dp, dp, dp,
+                                    ctypes.c_double, dp, dp]
+        L.oracle_energy.restype = ctypes.c_double
+        _lib = L
+    return _lib
+
+
+def _dp(a):
+    if a is None:
+        return None
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def _c(a, shape_tail=None):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape_tail is not None:
+        a = a.reshape((-1,) + tuple(shape_tail))
+    return a
+
+
+def default_opts(variant: int = TARGET, regularization: float = 1e-13,
+                 jacobian_mode: int = JAC_NUMERIC_CENTRAL, **overrides) -> OracleOpts:
+    o = OracleOpts()
+    lib().oracle_opts_default(ctypes.byref(o))
+    o.variant = variant
+    o.regularization = regularization
+    o.jacobian_mode = jacobian_mode
+    for k, v in overrides.items():
+        if not hasattr(o, k):
+            raise AttributeError(k)
+        setattr(o, k, v)
+    return o
+
+
+@dataclass
+class EvalResult:
+    cost: float
+    gradient: np.ndarray  # (5,)
+    jtj: np.ndarray  # (15,) upper triangle, row-major packed
+
+
+def covs_to_abi(covs):
+    """(n,3,3) row-indexed numpy matrices -> the ABI's column-major double[n][9]."""
+    if covs is None:
+        return None
+    covs = np.asarray(covs, dtype=np.float64).reshape(-1, 3, 3)
+    return np.ascontiguousarray(covs.transpose(0, 2, 1)).reshape(-1, 9)
+
+
+def evaluate(variant, f1, f2, cov_t, cov_h, reg, pose7, jacobian_mode=JAC_NUMERIC_CENTRAL):
+    """cov_* are in the ABI layout: [n][9] column-major."""
+    f1, f2 = _c(f1, (3,)), _c(f2, (3,))
+    cov_t, cov_h = _c(cov_t, (9,)), _c(cov_h, (9,))
+    pose7 = _c(pose7)
+    cost = ctypes.c_double()
+    g = np.zeros(5)
+    H = np.zeros(15)
+    rc = lib().oracle_eval(variant, jacobian_mode, f1.shape[0], _dp(f1), _dp(f2), _dp(cov_t),
+                           _dp(cov_h), reg, _dp(pose7), ctypes.byref(cost), _dp(g), _dp(H))
+    if rc != 0:
+        raise RuntimeError("oracle_eval failed")
+    return EvalResult(cost.value, g, H)
+
+
+def solve(f1, f2, cov_t, cov_h, init_pose7, opts: OracleOpts):
+    f1, f2 = _c(f1, (3,)), _c(f2, (3,))
+    cov_t, cov_h = _c(cov_t, (9,)), _c(cov_h, (9,))
+    init_pose7 = _c(init_pose7)
+    out = np.zeros(7)
+    info = OracleInfo()
+    rc = lib().oracle_solve(ctypes.byref(opts), f1.shape[0], _dp(f1), _dp(f2), _dp(cov_t),
+                            _dp(cov_h), _dp(init_pose7), _dp(out), ctypes.byref(info))
+    if rc != 0:
+        raise RuntimeError("oracle_solve failed")
+    return out, info
+
+
+def solve_batch(f1, f2, cov_t, cov_h, init_poses, opts: OracleOpts, offsets=None,
+                n_per_problem=None, num_threads: int = 1):
+    """Returns (poses [B,7], info structured array [B])."""
+    f1, f2 = _c(f1, (3,)), _c(f2, (3,))
+    cov_t, cov_h = _c(cov_t, (9,)), _c(cov_h, (9,))
+    init_poses = _c(init_poses, (7,))
+    B = init_poses.shape[0]
+    if offsets is not None:
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        assert offsets.shape[0] == B + 1
+        op = offsets.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))
+        n_per_problem = 0
+    else:
+        op = None
+        if n_per_problem is None:
+            n_per_problem = f1.shape[0] // max(B, 1)
+    out = np.zeros((B, 7))
+    infos = np.zeros(B, dtype=INFO_DTYPE)
+    assert INFO_DTYPE.itemsize == ctypes.sizeof(OracleInfo)
+    rc = lib().oracle_solve_batch(ctypes.byref(opts), B, n_per_problem, op, _dp(f1), _dp(f2),
+                                  _dp(cov_t), _dp(cov_h), _dp(init_poses), _dp(out),
+                                  infos.ctypes.data_as(ctypes.c_void_p), num_threads)
+    if rc != 0:
+        raise RuntimeError("oracle_solve_batch failed")
+    return out, infos
+
+
+def max_threads() -> int:
+    return int(lib().oracle_max_threads())
+
+
+def angles_from_vec(v):
+    v = _c(v)
+    th, ph = ctypes.c_double(), ctypes.c_double()
+    lib().oracle_angles_from_vec(_dp(v), ctypes.byref(th), ctypes.byref(ph))
+    return th.value, ph.value
+
+
+def rotational_difference_deg(pose_a, pose_b) -> float:
+    a, b = _c(pose_a), _c(pose_b)
+    return float(lib().oracle_rotational_difference_deg(_dp(a), _dp(b)))
+
+
+def translational_difference_deg(t1, t2, both_directions=True) -> float:
+    a, b = _c(t1), _c(t2)
+    return float(lib().oracle_translational_difference_deg(_dp(a), _dp(b), int(both_directions)))
+
+
+def cost_function(f1, f2, cov, pose7) -> float:
+    f1, f2, cov, pose7 = _c(f1, (3,)), _c(f2, (3,)), _c(cov, (9,)), _c(pose7)
+    return float(lib().oracle_cost_function(f1.shape[0], _dp(f1), _dp(f2), _dp(cov), _dp(pose7)))
+
+
+def energy(variant, f1, f2, cov_t, cov_h, reg, q_xyzw, t) -> float:
+    f1, f2 = _c(f1, (3,)), _c(f2, (3,))
+    cov_t, cov_h = _c(cov_t, (9,)), _c(cov_h, (9,))
+    q, t = _c(q_xyzw), _c(t)
+    return float(lib().oracle_energy(variant, f1.shape[0], _dp(f1), _dp(f2), _dp(cov_t),
+                                     _dp(cov_h), reg, _dp(q), _dp(t)))
