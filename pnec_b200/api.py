@@ -1,0 +1,372 @@
+"""Host-side binding of the C-ABI (include/pnec_b200.h) — ctypes, no torch types
+cross the boundary: tensors are passed as raw device pointers + the current CUDA
+stream handle.  There is NO CPU fallback: if libpnec_b200.so is missing or no
+Blackwell GPU is visible, every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libpnec_b200.so")
+
+NEC, TARGET, HOST, SYMMETRIC = 0, 1, 2, 3
+VARIANT_NAMES = {"nec": NEC, "target": TARGET, "host": HOST, "symmetric": SYMMETRIC}
+MEM_HOST, MEM_DEVICE = 0, 1
+
+STATUS_NAMES = (
+    "converged_function",
+    "converged_parameter",
+    "converged_gradient",
+    "converged_radius",
+    "max_iterations",
+    "failure",
+    "nonfinite",
+    "empty",
+)
+
+# every symbol include/pnec_b200.h declares
+EXPORTED_SYMBOLS = (
+    "pnec_version",
+    "pnec_last_error",
+    "pnec_status_string",
+    "pnec_solver_opts_default",
+    "pnec_create",
+    "pnec_destroy",
+    "pnec_solve_batch",
+    "pnec_eval_batch",
+    "pnec_cost_function_batch",
+    "pnec_launch_count",
+)
+
+
+class PnecError(RuntimeError):
+    pass
+
+
+class SolverOpts(ctypes.Structure):
+    """pnec_solver_opts == ceres::Solver::Options defaults the reference runs with
+    (src/optimization/pnec_ceres.cc:43-48) + Options::regularization_
+    (include/rel_pose_estimation/pnec_config.h:50)."""
+
+    _fields_ = [
+        ("variant", ctypes.c_int32),
+        ("max_num_iterations", ctypes.c_int32),
+        ("max_num_consecutive_invalid_steps", ctypes.c_int32),
+        ("jacobi_scaling", ctypes.c_int32),
+        ("regularization", ctypes.c_double),
+        ("function_tolerance", ctypes.c_double),
+        ("gradient_tolerance", ctypes.c_double),
+        ("parameter_tolerance", ctypes.c_double),
+        ("initial_trust_region_radius", ctypes.c_double),
+        ("max_trust_region_radius", ctypes.c_double),
+        ("min_trust_region_radius", ctypes.c_double),
+        ("min_relative_decrease", ctypes.c_double),
+        ("min_lm_diagonal", ctypes.c_double),
+        ("max_lm_diagonal", ctypes.c_double),
+    ]
+
+
+class _Batch(ctypes.Structure):
+    _fields_ = [
+        ("num_problems", ctypes.c_int64),
+        ("n_per_problem", ctypes.c_int64),
+        ("offsets", ctypes.c_void_p),
+        ("memspace", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+        ("bvs_host", ctypes.c_void_p),
+        ("bvs_target", ctypes.c_void_p),
+        ("covs_target", ctypes.c_void_p),
+        ("covs_host", ctypes.c_void_p),
+        ("poses", ctypes.c_void_p),
+    ]
+
+
+class _SolveOut(ctypes.Structure):
+    _fields_ = [
+        ("poses", ctypes.c_void_p),
+        ("status", ctypes.c_void_p),
+        ("iterations", ctypes.c_void_p),
+        ("cost", ctypes.c_void_p),
+        ("initial_cost", ctypes.c_void_p),
+    ]
+
+
+class _EvalOut(ctypes.Structure):
+    _fields_ = [
+        ("cost", ctypes.c_void_p),
+        ("gradient", ctypes.c_void_p),
+        ("jtj", ctypes.c_void_p),
+    ]
+
+
+_lib = None
+
+
+def load_library() -> ctypes.CDLL:
+    """Loads libpnec_b200.so (built in-tree by __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PnecError(
+            f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  pnec_b200 has no CPU fallback."
+        )
+    L = ctypes.CDLL(LIB_PATH)
+    L.pnec_version.restype = ctypes.c_int
+    L.pnec_last_error.restype = ctypes.c_char_p
+    L.pnec_status_string.restype = ctypes.c_char_p
+    L.pnec_status_string.argtypes = [ctypes.c_int32]
+    L.pnec_solver_opts_default.argtypes = [ctypes.POINTER(SolverOpts)]
+    L.pnec_solver_opts_default.restype = None
+    L.pnec_create.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+    L.pnec_create.restype = ctypes.c_int
+    L.pnec_destroy.argtypes = [ctypes.c_void_p]
+    L.pnec_destroy.restype = None
+    L.pnec_solve_batch.argtypes = [ctypes.c_void_p, ctypes.POINTER(_Batch),
+                                   ctypes.POINTER(SolverOpts), ctypes.POINTER(_SolveOut),
+                                   ctypes.c_void_p]
+    L.pnec_solve_batch.restype = ctypes.c_int
+    L.pnec_eval_batch.argtypes = [ctypes.c_void_p, ctypes.POINTER(_Batch), ctypes.c_int32,
+                                  ctypes.c_double, ctypes.POINTER(_EvalOut), ctypes.c_void_p]
+    L.pnec_eval_batch.restype = ctypes.c_int
+    L.pnec_cost_function_batch.argtypes = [ctypes.c_void_p, ctypes.POINTER(_Batch),
+                                           ctypes.c_void_p, ctypes.c_void_p]
+    L.pnec_cost_function_batch.restype = ctypes.c_int
+    L.pnec_launch_count.argtypes = [ctypes.c_void_p]
+    L.pnec_launch_count.restype = ctypes.c_int64
+    _lib = L
+    return L
+
+
+def default_opts(variant: int = TARGET, regularization: float = 1e-13, **overrides) -> SolverOpts:
+    o = SolverOpts()
+    load_library().pnec_solver_opts_default(ctypes.byref(o))
+    o.variant = int(variant)
+    o.regularization = float(regularization)
+    for k, v in overrides.items():
+        if not hasattr(o, k):
+            raise AttributeError(f"pnec_solver_opts has no field {k!r}")
+        setattr(o, k, v)
+    return o
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+@dataclass
+class SolveResult:
+    poses: object  # (B,7) numpy (host call) or torch.cuda tensor (device call)
+    status: object  # (B,) int32
+    iterations: object  # (B,) int32
+    cost: object  # (B,) final 1/2 sum r^2
+    initial_cost: object  # (B,)
+
+
+@dataclass
+class EvalResult:
+    cost: object  # (B,)
+    gradient: object  # (B,5)
+    jtj: object  # (B,15) packed upper triangle
+
+
+class Handle:
+    """pnec_handle wrapper.  One per device/stream user; re-entrant per handle."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load_library()
+        self._h = ctypes.c_void_p()
+        rc = self._lib.pnec_create(int(device), ctypes.byref(self._h))
+        if rc != 0:
+            raise PnecError(f"pnec_create failed ({rc}): {self._lib.pnec_last_error().decode()}")
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.pnec_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.pnec_launch_count(self._h))
+
+    # ------------------------------------------------------------ plumbing
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise PnecError(f"{what} failed ({rc}): {self._lib.pnec_last_error().decode()}")
+
+    @staticmethod
+    def _prep_host(a, tail):
+        if a is None:
+            return None
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        return a.reshape((-1,) + tail)
+
+    def _batch(self, f1, f2, ct, ch, poses, offsets, n_per_problem, keep):
+        device = _is_torch(f1)
+        b = _Batch()
+        if device:
+            import torch
+
+            def dev(t, tail):
+                if t is None:
+                    return None
+                if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()):
+                    raise PnecError("device batches need contiguous float64 CUDA tensors")
+                if t.device.index != self.device:
+                    raise PnecError("tensor is on a different device than the handle")
+                return t
+
+            f1, f2, ct, ch, poses = (dev(x, None) for x in (f1, f2, ct, ch, poses))
+            ptr = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+            total = f1.numel() // 3
+            B = poses.numel() // 7
+            b.memspace = MEM_DEVICE
+        else:
+            f1 = self._prep_host(f1, (3,))
+            f2 = self._prep_host(f2, (3,))
+            ct = self._prep_host(ct, (9,))
+            ch = self._prep_host(ch, (9,))
+            poses = self._prep_host(poses, (7,))
+            ptr = lambda a: None if a is None else ctypes.c_void_p(a.ctypes.data)
+            total = f1.shape[0]
+            B = poses.shape[0]
+            b.memspace = MEM_HOST
+        keep.extend([f1, f2, ct, ch, poses])
+        if f2 is not None and (f2.numel() if device else f2.size) != total * 3:
+            raise PnecError("bvs_host and bvs_target differ in size")
+        b.num_problems = B
+        if offsets is not None:
+            offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+            if offsets.shape != (B + 1,):
+                raise PnecError("offsets must have num_problems + 1 entries")
+            if int(offsets[-1]) > total:
+                raise PnecError("offsets run past the end of the correspondence arrays")
+            keep.append(offsets)
+            b.offsets = ctypes.c_void_p(offsets.ctypes.data)
+            b.n_per_problem = 0
+        else:
+            if n_per_problem is None:
+                n_per_problem = total // B if B else 0
+            if n_per_problem * B > total:
+                raise PnecError("n_per_problem * num_problems exceeds the correspondence arrays")
+            b.offsets = None
+            b.n_per_problem = int(n_per_problem)
+        b.bvs_host, b.bvs_target = ptr(f1), ptr(f2)
+        b.covs_target, b.covs_host, b.poses = ptr(ct), ptr(ch), ptr(poses)
+        return b, device, B
+
+    def _stream(self, device: bool):
+        if not device:
+            return None
+        import torch
+
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ----------------------------------------------------------------- API
+    def solve_batch(self, bvs_host, bvs_target, covs_target, covs_host, init_poses,
+                    opts: Optional[SolverOpts] = None, *, offsets=None, n_per_problem=None,
+                    out: Optional[SolveResult] = None) -> SolveResult:
+        """Batched on-device LM refinement (pnec_solve_batch).
+
+        numpy inputs -> HOST call (copies inside, synchronous); torch CUDA tensors ->
+        DEVICE call, enqueued on torch's current stream, results are CUDA tensors.
+        """
+        opts = opts or default_opts()
+        keep = []
+        b, device, B = self._batch(bvs_host, bvs_target, covs_target, covs_host, init_poses,
+                                   offsets, n_per_problem, keep)
+        o = _SolveOut()
+        if device:
+            import torch
+
+            dev = torch.device("cuda", self.device)
+            if out is None:
+                out = SolveResult(
+                    torch.empty((B, 7), dtype=torch.float64, device=dev),
+                    torch.empty((B,), dtype=torch.int32, device=dev),
+                    torch.empty((B,), dtype=torch.int32, device=dev),
+                    torch.empty((B,), dtype=torch.float64, device=dev),
+                    torch.empty((B,), dtype=torch.float64, device=dev),
+                )
+            o.poses, o.status = out.poses.data_ptr(), out.status.data_ptr()
+            o.iterations, o.cost = out.iterations.data_ptr(), out.cost.data_ptr()
+            o.initial_cost = out.initial_cost.data_ptr()
+        else:
+            if out is None:
+                out = SolveResult(np.empty((B, 7)), np.empty(B, np.int32), np.empty(B, np.int32),
+                                  np.empty(B), np.empty(B))
+            o.poses, o.status = out.poses.ctypes.data, out.status.ctypes.data
+            o.iterations, o.cost = out.iterations.ctypes.data, out.cost.ctypes.data
+            o.initial_cost = out.initial_cost.ctypes.data
+        rc = self._lib.pnec_solve_batch(self._h, ctypes.byref(b), ctypes.byref(opts),
+                                        ctypes.byref(o), self._stream(device))
+        self._check(rc, "pnec_solve_batch")
+        return out
+
+    def eval_batch(self, bvs_host, bvs_target, covs_target, covs_host, poses, variant=TARGET,
+                   regularization=1e-13, *, offsets=None, n_per_problem=None,
+                   out: Optional[EvalResult] = None) -> EvalResult:
+        """One fused residual + Jacobian + JtJ/Jtr/cost pass per problem (pnec_eval_batch)."""
+        keep = []
+        b, device, B = self._batch(bvs_host, bvs_target, covs_target, covs_host, poses, offsets,
+                                   n_per_problem, keep)
+        o = _EvalOut()
+        if device:
+            import torch
+
+            dev = torch.device("cuda", self.device)
+            if out is None:
+                out = EvalResult(torch.empty((B,), dtype=torch.float64, device=dev),
+                                 torch.empty((B, 5), dtype=torch.float64, device=dev),
+                                 torch.empty((B, 15), dtype=torch.float64, device=dev))
+            o.cost, o.gradient, o.jtj = out.cost.data_ptr(), out.gradient.data_ptr(), out.jtj.data_ptr()
+        else:
+            if out is None:
+                out = EvalResult(np.empty(B), np.empty((B, 5)), np.empty((B, 15)))
+            o.cost, o.gradient, o.jtj = out.cost.ctypes.data, out.gradient.ctypes.data, out.jtj.ctypes.data
+        rc = self._lib.pnec_eval_batch(self._h, ctypes.byref(b), int(variant), float(regularization),
+                                       ctypes.byref(o), self._stream(device))
+        self._check(rc, "pnec_eval_batch")
+        return out
+
+    def cost_function_batch(self, bvs_host, bvs_target, covs_target, poses, *, offsets=None,
+                            n_per_problem=None):
+        """pnec::common::CostFunction (src/common/common.cc:237-259) per problem."""
+        keep = []
+        b, device, B = self._batch(bvs_host, bvs_target, covs_target, None, poses, offsets,
+                                   n_per_problem, keep)
+        if device:
+            import torch
+
+            out = torch.empty((B,), dtype=torch.float64, device=torch.device("cuda", self.device))
+            p = ctypes.c_void_p(out.data_ptr())
+        else:
+            out = np.empty(B)
+            p = ctypes.c_void_p(out.ctypes.data)
+        rc = self._lib.pnec_cost_function_batch(self._h, ctypes.byref(b), p, self._stream(device))
+        self._check(rc, "pnec_cost_function_batch")
+        return out
+
+
+_default_handles = {}
+
+
+def default_handle(device: int = 0) -> Handle:
+    h = _default_handles.get(device)
+    if h is None:
+        h = _default_handles[device] = Handle(device)
+    return h

@@ -1,0 +1,920 @@
+// pnec_kernels.cu — sm_100a kernels and the C-ABI of the PNEC frame-pair solver.
+//
+//   solve_kernel   one CTA per frame pair.  The pair's correspondences are pulled
+//                  from HBM ONCE into shared memory with 1-D bulk async copies (TMA
+//                  engine, mbarrier complete_tx), then every LM iteration — fused
+//                  residual + analytic Jacobian + J^T J / J^T r reduction, 5x5
+//                  damped Cholesky, SO(3) x S^2 retraction, accept/reject — runs
+//                  out of shared memory with no host round trip.
+//   eval_kernel    the fused residual + Jacobian + J^T J pass alone (K1), streaming
+//                  tiles through an S-stage bulk-copy ring: the HBM-roofline kernel.
+//   cost_kernel    pnec::common::CostFunction (parity metric).
+//
+// Replaces (reference, file:line): PNECCeres::Optimize src/optimization/pnec_ceres.cc:70-168,
+// NECCeres::Optimize src/optimization/nec_ceres.cc:73-101, and under them
+// ceres::Solve + N x NumericDiffCostFunction<F, CENTRAL, 1,1,1,4>.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "pnec_device.cuh"
+
+namespace pnec {
+
+struct BatchView {
+  const double *f1, *f2, *ct, *ch;
+  const long long *offsets;  // device, B+1, or nullptr for uniform
+  long long n_uniform, num_problems, total;
+  const double *poses;  // [B][7]
+};
+
+__device__ __forceinline__ void problem_range(const BatchView &bv, long long b, long long &s,
+                                              long long &e) {
+  if (bv.offsets) {
+    s = bv.offsets[b];
+    e = bv.offsets[b + 1];
+  } else {
+    s = b * bv.n_uniform;
+    e = s + bv.n_uniform;
+  }
+}
+
+template <int V>
+struct VariantTraits {
+  static constexpr bool kHasCt = (V != PNEC_VARIANT_NEC);
+  static constexpr bool kHasCh = (V == PNEC_VARIANT_SYMMETRIC);
+  // doubles per correspondence as laid out in HBM (the algorithmic bytes / 8)
+  static constexpr int kDoubles = 6 + (kHasCt ? 9 : 0) + (kHasCh ? 9 : 0);
+};
+
+// One correspondence from (f1, f2, ct, ch) arrays at element index i.
+template <int V>
+__device__ __forceinline__ void load_corr(const double *f1, const double *f2, const double *ct,
+                                          const double *ch, long long i, double a1[3],
+                                          double a2[3], double c1[9], double c2[9]) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k) a1[k] = f1[3 * i + k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) a2[k] = f2[3 * i + k];
+  if (VariantTraits<V>::kHasCt) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) c1[k] = ct[9 * i + k];
+  }
+  if (VariantTraits<V>::kHasCh) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) c2[k] = ch[9 * i + k];
+  }
+}
+
+template <int V, int NT>
+__device__ __forceinline__ void eval_pass(const PoseConst &pc, double reg, const double *f1,
+                                          const double *f2, const double *ct, const double *ch,
+                                          int begin, int end, int tid, double acc[kNumAcc]) {
+  for (int i = begin + tid; i < end; i += NT) {
+    double a1[3], a2[3], c1[9], c2[9], r, row[5];
+    load_corr<V>(f1, f2, ct, ch, i, a1, a2, c1, c2);
+    residual_row<V>(pc, reg, a1, a2, c1, c2, r, row);
+    accumulate(acc, r, row);
+  }
+}
+
+// Block reduction of the 21 partial sums.  After it, in warp 0, tot[j] (all lanes)
+// holds the scaled block total of value j.  Contains one __syncthreads().
+template <int NW>
+__device__ __forceinline__ void block_reduce(const double acc[kNumAcc],
+                                             double (*s_part)[kAccPad], int warp, int lane,
+                                             double tot[kNumAcc]) {
+  const double v = warp_transpose_reduce(acc, lane);
+  const int idx = warp_reduce_owner_index(lane);
+  if (idx >= 0 && idx < kNumAcc) s_part[warp][idx] = v;
+  __syncthreads();
+  if (warp == 0) {
+    double mine = 0.0;
+    if (lane < kNumAcc) {
+#pragma unroll
+      for (int w = 0; w < NW; ++w) mine += s_part[w][lane];
+      mine *= acc_scale(lane);
+    }
+#pragma unroll
+    for (int j = 0; j < kNumAcc; ++j) tot[j] = __shfl_sync(0xffffffffu, mine, j);
+  }
+}
+
+__device__ __forceinline__ void load_pose_const(const PoseConst &src, PoseConst &dst) {
+#pragma unroll
+  for (int i = 0; i < 9; ++i) dst.R[i] = src.R[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    dst.t[i] = src.t[i];
+    dst.tth[i] = src.tth[i];
+    dst.tph[i] = src.tph[i];
+  }
+}
+
+// Issues the bulk copies of `cnt` correspondences starting at global element
+// `first` (even) into the arrays at sf1/sf2/sct/sch, completing on `bar`.
+// Called by ONE thread.  Sizes are rounded up to an even element count (16-byte
+// granularity of cp.async.bulk); if that would run past the end of the batch the
+// last element is copied with plain loads instead.
+template <int V>
+__device__ __forceinline__ void issue_bulk(const BatchView &bv, long long first, int cnt,
+                                           double *sf1, double *sf2, double *sct, double *sch,
+                                           uint64_t *bar) {
+  int cb = cnt + (cnt & 1);
+  if (first + cb > bv.total) {
+    cb = cnt - 1;  // cnt is odd here
+    const long long g = first + cb;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) sf1[3 * cb + k] = bv.f1[3 * g + k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) sf2[3 * cb + k] = bv.f2[3 * g + k];
+    if (VariantTraits<V>::kHasCt) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) sct[9 * cb + k] = bv.ct[9 * g + k];
+    }
+    if (VariantTraits<V>::kHasCh) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) sch[9 * cb + k] = bv.ch[9 * g + k];
+    }
+  }
+  const uint32_t bytes = static_cast<uint32_t>(cb) * 8u * VariantTraits<V>::kDoubles;
+  mbar_arrive_expect_tx(bar, bytes);
+  if (cb > 0) {
+    bulk_g2s(sf1, bv.f1 + 3 * first, cb * 24u, bar);
+    bulk_g2s(sf2, bv.f2 + 3 * first, cb * 24u, bar);
+    if (VariantTraits<V>::kHasCt) bulk_g2s(sct, bv.ct + 9 * first, cb * 72u, bar);
+    if (VariantTraits<V>::kHasCh) bulk_g2s(sch, bv.ch + 9 * first, cb * 72u, bar);
+  }
+}
+
+// Same region, plain cooperative loads (unaligned base pointers).
+template <int V, int NT>
+__device__ __forceinline__ void copy_plain(const BatchView &bv, long long first, int cnt,
+                                           double *sf1, double *sf2, double *sct, double *sch,
+                                           int tid) {
+  for (int j = tid; j < cnt * 3; j += NT) {
+    sf1[j] = bv.f1[3 * first + j];
+    sf2[j] = bv.f2[3 * first + j];
+  }
+  if (VariantTraits<V>::kHasCt)
+    for (int j = tid; j < cnt * 9; j += NT) sct[j] = bv.ct[9 * first + j];
+  if (VariantTraits<V>::kHasCh)
+    for (int j = tid; j < cnt * 9; j += NT) sch[j] = bv.ch[9 * first + j];
+}
+
+// --------------------------------------------------------------- solve kernel
+
+struct SolveArgs {
+  BatchView bv;
+  pnec_solver_opts o;
+  double *out_poses;
+  int *out_status;
+  int *out_iters;
+  double *out_cost;
+  double *out_init_cost;
+  int cap_elems;  // resident capacity of the dynamic smem, in correspondences (even)
+  int use_bulk;   // all base pointers 16-byte aligned
+};
+
+extern __shared__ __align__(16) double dyn_smem[];
+
+template <int V, int NW, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB) solve_kernel(const __grid_constant__ SolveArgs args) {
+  constexpr int NT = NW * 32;
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ PoseConst s_pc;
+  __shared__ LMState s_lm;
+  __shared__ double s_part[NW][kAccPad];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long b = blockIdx.x;
+  long long s, e;
+  problem_range(args.bv, b, s, e);
+  const int n = static_cast<int>(e - s);
+  const long long g0 = s & ~1LL;  // even => 16-byte aligned in every array
+  const int head = static_cast<int>(s - g0);
+  const int span = n + head;
+  const bool resident = (span + (span & 1)) <= args.cap_elems;
+  const pnec_solver_opts &o = args.o;
+
+  double *sf1 = dyn_smem;
+  double *sf2 = sf1 + 3 * args.cap_elems;
+  double *sct = sf2 + 3 * args.cap_elems;
+  double *sch = sct + (VariantTraits<V>::kHasCt ? 9 * args.cap_elems : 0);
+
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    fence_mbar_init();
+    // PNECCeres::InitValues(orientation, translation), pnec_ceres.cc:188-192
+    const double *p = args.bv.poses + 7 * b;
+    LMState &st = s_lm;
+    angles_from_vec(p + 4, st.x[0], st.x[1]);
+    st.x[2] = p[0]; st.x[3] = p[1]; st.x[4] = p[2]; st.x[5] = p[3];
+    double xn = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      st.cand[i] = st.x[i];
+      xn += st.x[i] * st.x[i];
+    }
+    st.x_norm = sqrt(xn);
+    st.radius = o.initial_trust_region_radius;
+    st.decrease_factor = 2.0;
+    st.model_cost_change = 0.0;
+    st.gmax = 0.0;
+    st.x_cost = 0.0;
+    st.initial_cost = 0.0;
+    st.iteration = 0;
+    st.num_invalid = 0;
+    st.reuse_diagonal = 0;
+    st.step_successful = 1;
+    st.status = (n <= 0) ? PNEC_STATUS_EMPTY : PNEC_STATUS_MAX_ITERATIONS;
+    st.done = (n <= 0) ? 1 : 0;
+    PoseConst pc0;
+    make_pose_const(st.x, pc0);
+    s_pc = pc0;
+  }
+  __syncthreads();
+
+  if (n > 0) {
+    if (resident) {
+      if (args.use_bulk) {
+        if (tid == 0) issue_bulk<V>(args.bv, g0, span, sf1, sf2, sct, sch, &s_bar);
+        mbar_wait(&s_bar, 0);
+      } else {
+        copy_plain<V, NT>(args.bv, g0, span, sf1, sf2, sct, sch, tid);
+        __syncthreads();
+      }
+    }
+    bool first = true;
+    for (;;) {
+      PoseConst pc;
+      load_pose_const(s_pc, pc);
+      double acc[kNumAcc];
+#pragma unroll
+      for (int i = 0; i < kNumAcc; ++i) acc[i] = 0.0;
+      if (resident) {
+        eval_pass<V, NT>(pc, o.regularization, sf1, sf2, sct, sch, head, span, tid, acc);
+      } else {
+        // problem larger than the resident capacity: stream it from L2/HBM
+        eval_pass<V, NT>(pc, o.regularization, args.bv.f1 + 3 * s, args.bv.f2 + 3 * s,
+                         VariantTraits<V>::kHasCt ? args.bv.ct + 9 * s : nullptr,
+                         VariantTraits<V>::kHasCh ? args.bv.ch + 9 * s : nullptr, 0, n, tid, acc);
+      }
+      double tot[kNumAcc];
+      block_reduce<NW>(acc, s_part, warp, lane, tot);
+      if (warp == 0) {
+        LMState st = s_lm;
+        if (first) lm_begin(st, tot, o);
+        else lm_judge(st, tot, o);
+        if (!st.done) lm_propose(st, o);
+        if (lane == 0) {
+          s_lm = st;
+          if (!st.done) {
+            PoseConst pcn;
+            make_pose_const(st.cand, pcn);
+            s_pc = pcn;
+          }
+        }
+      }
+      __syncthreads();
+      if (s_lm.done) break;
+      first = false;
+    }
+  }
+
+  if (tid == 0) {
+    // PNECCeres::Result(): q.normalized(), t(theta, phi); pnec_ceres.cc:201-206
+    const LMState &st = s_lm;
+    const double qn = sqrt(st.x[2] * st.x[2] + st.x[3] * st.x[3] + st.x[4] * st.x[4] + st.x[5] * st.x[5]);
+    const double iq = qn > 0.0 ? 1.0 / qn : 1.0;
+    double *op = args.out_poses + 7 * b;
+    op[0] = st.x[2] * iq; op[1] = st.x[3] * iq; op[2] = st.x[4] * iq; op[3] = st.x[5] * iq;
+    double sth, cth, sph, cph;
+    sincos(st.x[0], &sth, &cth);
+    sincos(st.x[1], &sph, &cph);
+    op[4] = sth * cph; op[5] = sth * sph; op[6] = cth;
+    if (args.out_status) args.out_status[b] = st.status;
+    if (args.out_iters) args.out_iters[b] = st.iteration;
+    if (args.out_cost) args.out_cost[b] = st.x_cost;
+    if (args.out_init_cost) args.out_init_cost[b] = st.initial_cost;
+  }
+}
+
+// ---------------------------------------------------------------- eval kernel
+
+struct EvalArgs {
+  BatchView bv;
+  double reg;
+  double *out_cost, *out_grad, *out_jtj;
+  int use_bulk;
+};
+
+template <int V, int NW, int S, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(const __grid_constant__ EvalArgs args) {
+  constexpr int NT = NW * 32;
+  constexpr int T = NT;  // correspondences per tile: one per thread
+  constexpr int kStageDoubles = T * VariantTraits<V>::kDoubles;
+  __shared__ __align__(8) uint64_t s_full[S];
+  __shared__ PoseConst s_pc;
+  __shared__ double s_part[NW][kAccPad];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long b = blockIdx.x;
+  long long s, e;
+  problem_range(args.bv, b, s, e);
+  const int n = static_cast<int>(e - s);
+  const long long g0 = s & ~1LL;
+  const int head = static_cast<int>(s - g0);
+  const int span = n + head;
+  const int ntiles = (n > 0) ? (span + T - 1) / T : 0;
+
+  auto stage_f1 = [&](int st) { return dyn_smem + st * kStageDoubles; };
+  auto stage_f2 = [&](int st) { return dyn_smem + st * kStageDoubles + 3 * T; };
+  auto stage_ct = [&](int st) { return dyn_smem + st * kStageDoubles + 6 * T; };
+  auto stage_ch = [&](int st) { return dyn_smem + st * kStageDoubles + 15 * T; };
+  auto issue_tile = [&](int k) {
+    const int st = k % S;
+    const int cnt = min(T, span - k * T);
+    issue_bulk<V>(args.bv, g0 + static_cast<long long>(k) * T, cnt, stage_f1(st), stage_f2(st),
+                  stage_ct(st), stage_ch(st), &s_full[st]);
+  };
+
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < S; ++i) mbar_init(&s_full[i], 1);
+    fence_mbar_init();
+    const double *p = args.bv.poses + 7 * b;
+    double x[6];
+    angles_from_vec(p + 4, x[0], x[1]);
+    x[2] = p[0]; x[3] = p[1]; x[4] = p[2]; x[5] = p[3];
+    PoseConst pc0;
+    make_pose_const(x, pc0);
+    s_pc = pc0;
+  }
+  __syncthreads();
+  if (tid == 0 && args.use_bulk) {
+    for (int k = 0; k < min(S, ntiles); ++k) issue_tile(k);
+  }
+  PoseConst pc;
+  load_pose_const(s_pc, pc);
+  double acc[kNumAcc];
+#pragma unroll
+  for (int i = 0; i < kNumAcc; ++i) acc[i] = 0.0;
+
+  for (int k = 0; k < ntiles; ++k) {
+    const int st = k % S;
+    if (args.use_bulk) {
+      mbar_wait(&s_full[st], (k / S) & 1);
+    } else {
+      copy_plain<V, NT>(args.bv, g0 + static_cast<long long>(k) * T, min(T, span - k * T),
+                        stage_f1(st), stage_f2(st), stage_ct(st), stage_ch(st), tid);
+      __syncthreads();
+    }
+    const int i = k * T + tid;
+    const bool valid = (i >= head) && (i < span);
+    double a1[3], a2[3], c1[9], c2[9];
+    if (valid) load_corr<V>(stage_f1(st), stage_f2(st), stage_ct(st), stage_ch(st), tid, a1, a2, c1, c2);
+    __syncthreads();  // every thread holds its correspondence: the stage may be refilled
+    if (tid == 0 && args.use_bulk && k + S < ntiles) issue_tile(k + S);
+    if (valid) {
+      double r, row[5];
+      residual_row<V>(pc, args.reg, a1, a2, c1, c2, r, row);
+      accumulate(acc, r, row);
+    }
+  }
+  double tot[kNumAcc];
+  block_reduce<NW>(acc, s_part, warp, lane, tot);
+  if (warp == 0) {
+    // lane j writes value j
+    double mine = 0.0;
+#pragma unroll
+    for (int j = 0; j < kNumAcc; ++j) mine = (lane == j) ? tot[j] : mine;
+    if (lane < 15) {
+      if (args.out_jtj) args.out_jtj[15 * b + lane] = mine;
+    } else if (lane < 20) {
+      if (args.out_grad) args.out_grad[5 * b + (lane - 15)] = mine;
+    } else if (lane == 20) {
+      if (args.out_cost) args.out_cost[b] = mine;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- cost kernel
+// pnec::common::CostFunction, src/common/common.cc:237-259: mean of
+// (t^T (f1 x R f2))^2 / (b^T S b), no regularisation.  pose: unit quaternion taken
+// from the normalised stored quaternion, translation as stored.
+__global__ void __launch_bounds__(128) cost_kernel(BatchView bv, double *out) {
+  __shared__ double s_red[4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long b = blockIdx.x;
+  long long s, e;
+  problem_range(bv, b, s, e);
+  const double *p = bv.poses + 7 * b;
+  const double qn = sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2] + p[3] * p[3]);
+  double x[6] = {0.0, 0.0, p[0] / qn, p[1] / qn, p[2] / qn, p[3] / qn};
+  PoseConst pc;
+  make_pose_const(x, pc);
+  const double t[3] = {p[4], p[5], p[6]};
+  double sum = 0.0;
+  for (long long i = s + tid; i < e; i += 128) {
+    double f1[3], f2[3], c[9], g[3], a[3], bb[3], Sb[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { f1[k] = bv.f1[3 * i + k]; f2[k] = bv.f2[3 * i + k]; }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) c[k] = bv.ct[9 * i + k];
+    rot(pc.R, f2, g);
+    cross3(t, f1, a);
+    const double num = dot3(a, g);
+    rot_t(pc.R, a, bb);
+    sym_mul(c, bb, Sb);
+    sum += num * num / dot3(bb, Sb);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) s_red[warp] = sum;
+  __syncthreads();
+  if (tid == 0) out[b] = (s_red[0] + s_red[1] + s_red[2] + s_red[3]) / static_cast<double>(e - s);
+}
+
+}  // namespace pnec
+
+// =================================================================== host side
+
+using namespace pnec;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string &msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define PNEC_CUDA(call)                                                                      \
+  do {                                                                                       \
+    cudaError_t err__ = (call);                                                              \
+    if (err__ != cudaSuccess)                                                                \
+      return fail(PNEC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(err__));     \
+  } while (0)
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int env_int(const char *name, int dflt) {
+  const char *v = std::getenv(name);
+  return (v && *v) ? std::atoi(v) : dflt;
+}
+
+}  // namespace
+
+struct pnec_handle {
+  int device = 0;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  int64_t launches = 0;
+  // staging for HOST-memspace calls and for the device copy of offsets
+  DevBuf d_f1, d_f2, d_ct, d_ch, d_off, d_poses;
+  DevBuf d_out_poses, d_out_status, d_out_iters, d_out_cost, d_out_init, d_out_grad, d_out_jtj;
+  std::mutex mu;
+};
+
+namespace {
+
+struct Staged {
+  BatchView bv;
+  long long max_n = 0;
+};
+
+int validate_batch(const pnec_batch *b, int variant, bool need_poses) {
+  if (!b) return fail(PNEC_ERR_INVALID_ARGUMENT, "batch is NULL");
+  if (b->num_problems < 0) return fail(PNEC_ERR_INVALID_ARGUMENT, "num_problems < 0");
+  if (!b->offsets && b->n_per_problem < 0)
+    return fail(PNEC_ERR_INVALID_ARGUMENT, "n_per_problem < 0");
+  if (b->memspace != PNEC_MEM_HOST && b->memspace != PNEC_MEM_DEVICE)
+    return fail(PNEC_ERR_INVALID_ARGUMENT, "unknown memspace");
+  if (variant < PNEC_VARIANT_NEC || variant > PNEC_VARIANT_SYMMETRIC)
+    return fail(PNEC_ERR_INVALID_ARGUMENT, "unknown residual variant");
+  long long total = 0;
+  if (b->offsets) {
+    if (b->offsets[0] < 0) return fail(PNEC_ERR_INVALID_ARGUMENT, "offsets[0] < 0");
+    for (int64_t i = 0; i < b->num_problems; ++i)
+      if (b->offsets[i + 1] < b->offsets[i])
+        return fail(PNEC_ERR_INVALID_ARGUMENT, "offsets must be non-decreasing");
+    total = b->offsets[b->num_problems];
+  } else {
+    total = b->num_problems * b->n_per_problem;
+  }
+  if (total > 0) {
+    if (!b->bvs_host || !b->bvs_target)
+      return fail(PNEC_ERR_INVALID_ARGUMENT, "bearing vector arrays are NULL");
+    if (variant != PNEC_VARIANT_NEC && !b->covs_target)
+      return fail(PNEC_ERR_INVALID_ARGUMENT, "covs_target is NULL for a PNEC variant");
+    if (variant == PNEC_VARIANT_SYMMETRIC && !b->covs_host)
+      return fail(PNEC_ERR_INVALID_ARGUMENT, "covs_host is NULL for the SYMMETRIC variant");
+  }
+  if (need_poses && b->num_problems > 0 && !b->poses)
+    return fail(PNEC_ERR_INVALID_ARGUMENT, "poses is NULL");
+  return PNEC_OK;
+}
+
+// Builds the device view of a batch: copies H2D for HOST batches, always copies
+// the (host) offsets.  Everything is enqueued on `stream`.
+int stage_batch(pnec_handle *h, const pnec_batch *b, int variant, cudaStream_t stream,
+                Staged *out) {
+  const long long B = b->num_problems;
+  long long total, max_n = 0;
+  if (b->offsets) {
+    total = b->offsets[B];
+    for (long long i = 0; i < B; ++i) max_n = std::max<long long>(max_n, b->offsets[i + 1] - b->offsets[i]);
+  } else {
+    total = B * b->n_per_problem;
+    max_n = b->n_per_problem;
+  }
+  BatchView bv{};
+  bv.num_problems = B;
+  bv.total = b->offsets ? b->offsets[B] : total;
+  bv.n_uniform = b->offsets ? 0 : b->n_per_problem;
+  const long long base = b->offsets ? b->offsets[0] : 0;
+  (void)base;
+  if (b->offsets) {
+    PNEC_CUDA(h->d_off.ensure(sizeof(long long) * (B + 1)));
+    PNEC_CUDA(cudaMemcpyAsync(h->d_off.p, b->offsets, sizeof(long long) * (B + 1),
+                              cudaMemcpyHostToDevice, stream));
+    bv.offsets = static_cast<const long long *>(h->d_off.p);
+  }
+  const bool need_ct = variant != PNEC_VARIANT_NEC;
+  const bool need_ch = variant == PNEC_VARIANT_SYMMETRIC;
+  if (b->memspace == PNEC_MEM_HOST) {
+    const size_t nel = static_cast<size_t>(bv.total);
+    PNEC_CUDA(h->d_f1.ensure(nel * 24));
+    PNEC_CUDA(h->d_f2.ensure(nel * 24));
+    PNEC_CUDA(h->d_poses.ensure(static_cast<size_t>(B) * 56));
+    if (nel) {
+      PNEC_CUDA(cudaMemcpyAsync(h->d_f1.p, b->bvs_host, nel * 24, cudaMemcpyHostToDevice, stream));
+      PNEC_CUDA(cudaMemcpyAsync(h->d_f2.p, b->bvs_target, nel * 24, cudaMemcpyHostToDevice, stream));
+    }
+    if (need_ct) {
+      PNEC_CUDA(h->d_ct.ensure(nel * 72));
+      if (nel)
+        PNEC_CUDA(cudaMemcpyAsync(h->d_ct.p, b->covs_target, nel * 72, cudaMemcpyHostToDevice, stream));
+    }
+    if (need_ch) {
+      PNEC_CUDA(h->d_ch.ensure(nel * 72));
+      if (nel)
+        PNEC_CUDA(cudaMemcpyAsync(h->d_ch.p, b->covs_host, nel * 72, cudaMemcpyHostToDevice, stream));
+    }
+    if (B && b->poses)
+      PNEC_CUDA(cudaMemcpyAsync(h->d_poses.p, b->poses, static_cast<size_t>(B) * 56,
+                                cudaMemcpyHostToDevice, stream));
+    bv.f1 = static_cast<const double *>(h->d_f1.p);
+    bv.f2 = static_cast<const double *>(h->d_f2.p);
+    bv.ct = need_ct ? static_cast<const double *>(h->d_ct.p) : nullptr;
+    bv.ch = need_ch ? static_cast<const double *>(h->d_ch.p) : nullptr;
+    bv.poses = static_cast<const double *>(h->d_poses.p);
+  } else {
+    bv.f1 = b->bvs_host;
+    bv.f2 = b->bvs_target;
+    bv.ct = need_ct ? b->covs_target : nullptr;
+    bv.ch = need_ch ? b->covs_host : nullptr;
+    bv.poses = b->poses;
+  }
+  out->bv = bv;
+  out->max_n = max_n;
+  return PNEC_OK;
+}
+
+bool bulk_ok(const BatchView &bv) {
+  return aligned16(bv.f1) && aligned16(bv.f2) && (!bv.ct || aligned16(bv.ct)) &&
+         (!bv.ch || aligned16(bv.ch));
+}
+
+int bytes_per_corr(int variant) {
+  switch (variant) {
+    case PNEC_VARIANT_NEC: return 48;
+    case PNEC_VARIANT_SYMMETRIC: return 192;
+    default: return 120;
+  }
+}
+
+// ------------------------------------------------------------ kernel launchers
+
+constexpr size_t kStaticSmemReserve = 3072;  // static __shared__ of the kernels + slack
+
+template <int V, int NW, int MINB>
+int launch_solve_t(pnec_handle *h, const SolveArgs &a, size_t dyn, cudaStream_t stream) {
+  auto kern = solve_kernel<V, NW, MINB>;
+  PNEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(dyn)));
+  kern<<<static_cast<unsigned>(a.bv.num_problems), NW * 32, dyn, stream>>>(a);
+  PNEC_CUDA(cudaGetLastError());
+  h->launches++;
+  return PNEC_OK;
+}
+
+template <int V>
+int launch_solve_v(pnec_handle *h, const SolveArgs &a, int nw, size_t dyn, cudaStream_t stream) {
+  switch (nw) {
+    case 1: return launch_solve_t<V, 1, 8>(h, a, dyn, stream);
+    case 2: return launch_solve_t<V, 2, 4>(h, a, dyn, stream);
+    case 4: return launch_solve_t<V, 4, 3>(h, a, dyn, stream);
+    case 8: return launch_solve_t<V, 8, 1>(h, a, dyn, stream);
+    default: return fail(PNEC_ERR_INVALID_ARGUMENT, "unsupported warps per problem");
+  }
+}
+
+int launch_solve(pnec_handle *h, const SolveArgs &a0, int variant, long long max_n,
+                 cudaStream_t stream) {
+  SolveArgs a = a0;
+  if (a.bv.num_problems == 0) return PNEC_OK;
+  int nw = env_int("PNEC_B200_SOLVE_WARPS", 0);
+  if (nw == 0) nw = max_n <= 64 ? 1 : max_n <= 192 ? 2 : max_n <= 1024 ? 4 : 8;
+  const int bpc = bytes_per_corr(variant);
+  const size_t cap_bytes = h->smem_optin - kStaticSmemReserve;
+  const long long want_elems = ((max_n + 1) + 1) & ~1LL;  // head element + round up to even
+  long long cap_elems = std::min<long long>(want_elems, static_cast<long long>(cap_bytes / bpc) & ~1LL);
+  if (cap_elems < 2) cap_elems = 2;
+  a.cap_elems = static_cast<int>(cap_elems);
+  a.use_bulk = bulk_ok(a.bv) ? 1 : 0;
+  if (env_int("PNEC_B200_NO_BULK", 0)) a.use_bulk = 0;
+  const size_t dyn = static_cast<size_t>(cap_elems) * bpc;
+  switch (variant) {
+    case PNEC_VARIANT_NEC: return launch_solve_v<PNEC_VARIANT_NEC>(h, a, nw, dyn, stream);
+    case PNEC_VARIANT_TARGET: return launch_solve_v<PNEC_VARIANT_TARGET>(h, a, nw, dyn, stream);
+    case PNEC_VARIANT_HOST: return launch_solve_v<PNEC_VARIANT_HOST>(h, a, nw, dyn, stream);
+    default: return launch_solve_v<PNEC_VARIANT_SYMMETRIC>(h, a, nw, dyn, stream);
+  }
+}
+
+template <int V, int NW, int S, int MINB>
+int launch_eval_t(pnec_handle *h, const EvalArgs &a, cudaStream_t stream) {
+  auto kern = eval_kernel<V, NW, S, MINB>;
+  const size_t dyn = static_cast<size_t>(S) * NW * 32 * VariantTraits<V>::kDoubles * 8;
+  PNEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(dyn)));
+  kern<<<static_cast<unsigned>(a.bv.num_problems), NW * 32, dyn, stream>>>(a);
+  PNEC_CUDA(cudaGetLastError());
+  h->launches++;
+  return PNEC_OK;
+}
+
+template <int V>
+int launch_eval_v(pnec_handle *h, const EvalArgs &a, long long max_n, cudaStream_t stream) {
+  int cfg = env_int("PNEC_B200_EVAL_CFG", 0);
+  if (cfg == 0) cfg = max_n <= 96 ? 1 : 2;
+  switch (cfg) {
+    case 1: return launch_eval_t<V, 2, 2, 8>(h, a, stream);   // 64-wide tiles, small problems
+    case 2: return launch_eval_t<V, 4, 4, 3>(h, a, stream);   // 128-wide tiles, 4 stages
+    case 3: return launch_eval_t<V, 4, 2, 6>(h, a, stream);   // 128-wide tiles, 2 stages
+    case 4: return launch_eval_t<V, 8, 2, 3>(h, a, stream);   // 256-wide tiles, 2 stages
+    default: return fail(PNEC_ERR_INVALID_ARGUMENT, "unknown PNEC_B200_EVAL_CFG");
+  }
+}
+
+int launch_eval(pnec_handle *h, const EvalArgs &a0, int variant, long long max_n,
+                cudaStream_t stream) {
+  EvalArgs a = a0;
+  if (a.bv.num_problems == 0) return PNEC_OK;
+  a.use_bulk = bulk_ok(a.bv) ? 1 : 0;
+  if (env_int("PNEC_B200_NO_BULK", 0)) a.use_bulk = 0;
+  switch (variant) {
+    case PNEC_VARIANT_NEC: return launch_eval_v<PNEC_VARIANT_NEC>(h, a, max_n, stream);
+    case PNEC_VARIANT_TARGET: return launch_eval_v<PNEC_VARIANT_TARGET>(h, a, max_n, stream);
+    case PNEC_VARIANT_HOST: return launch_eval_v<PNEC_VARIANT_HOST>(h, a, max_n, stream);
+    default: return launch_eval_v<PNEC_VARIANT_SYMMETRIC>(h, a, max_n, stream);
+  }
+}
+
+}  // namespace
+
+// ===================================================================== C-ABI
+
+extern "C" {
+
+int pnec_version(void) { return PNEC_B200_VERSION_MAJOR * 1000 + PNEC_B200_VERSION_MINOR; }
+
+const char *pnec_last_error(void) { return g_last_error.c_str(); }
+
+const char *pnec_status_string(int32_t status) {
+  switch (status) {
+    case PNEC_STATUS_CONVERGED_FUNCTION: return "converged: function tolerance";
+    case PNEC_STATUS_CONVERGED_PARAMETER: return "converged: parameter tolerance";
+    case PNEC_STATUS_CONVERGED_GRADIENT: return "converged: gradient tolerance";
+    case PNEC_STATUS_CONVERGED_RADIUS: return "converged: minimum trust region radius";
+    case PNEC_STATUS_MAX_ITERATIONS: return "no convergence: maximum iterations";
+    case PNEC_STATUS_FAILURE: return "failure: consecutive invalid steps";
+    case PNEC_STATUS_NONFINITE: return "failure: non-finite cost at the start point";
+    case PNEC_STATUS_EMPTY: return "empty problem";
+    default: return "unknown";
+  }
+}
+
+void pnec_solver_opts_default(pnec_solver_opts *o) {
+  if (!o) return;
+  o->variant = PNEC_VARIANT_TARGET;
+  o->max_num_iterations = 50;
+  o->max_num_consecutive_invalid_steps = 5;
+  o->jacobi_scaling = 1;
+  o->regularization = 1.0e-13;
+  o->function_tolerance = 1e-6;
+  o->gradient_tolerance = 1e-10;
+  o->parameter_tolerance = 1e-8;
+  o->initial_trust_region_radius = 1e4;
+  o->max_trust_region_radius = 1e16;
+  o->min_trust_region_radius = 1e-32;
+  o->min_relative_decrease = 1e-3;
+  o->min_lm_diagonal = 1e-6;
+  o->max_lm_diagonal = 1e32;
+}
+
+int pnec_create(int device, pnec_handle **out) {
+  if (!out) return fail(PNEC_ERR_INVALID_ARGUMENT, "out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(PNEC_ERR_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail(PNEC_ERR_INVALID_ARGUMENT, "bad device index");
+  PNEC_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop{};
+  PNEC_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(PNEC_ERR_UNSUPPORTED, "pnec_b200 is built for sm_100a (Blackwell) only");
+  pnec_handle *h = new (std::nothrow) pnec_handle();
+  if (!h) return fail(PNEC_ERR_ALLOC, "out of host memory");
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  h->smem_optin = prop.sharedMemPerBlockOptin;
+  *out = h;
+  return PNEC_OK;
+}
+
+void pnec_destroy(pnec_handle *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  DevBuf *bufs[] = {&h->d_f1, &h->d_f2, &h->d_ct, &h->d_ch, &h->d_off, &h->d_poses,
+                    &h->d_out_poses, &h->d_out_status, &h->d_out_iters, &h->d_out_cost,
+                    &h->d_out_init, &h->d_out_grad, &h->d_out_jtj};
+  for (DevBuf *b : bufs) b->release();
+  delete h;
+}
+
+int64_t pnec_launch_count(const pnec_handle *h) { return h ? h->launches : 0; }
+
+int pnec_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_solver_opts *opts,
+                     const pnec_solve_out *out, void *cuda_stream) {
+  if (!h || !opts || !out) return fail(PNEC_ERR_INVALID_ARGUMENT, "NULL argument");
+  int rc = validate_batch(batch, opts->variant, true);
+  if (rc != PNEC_OK) return rc;
+  const long long B = batch->num_problems;
+  if (B > 0 && !out->poses) return fail(PNEC_ERR_INVALID_ARGUMENT, "out->poses is NULL");
+  if (B == 0) return PNEC_OK;
+  std::lock_guard<std::mutex> lock(h->mu);
+  PNEC_CUDA(cudaSetDevice(h->device));
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  Staged st;
+  rc = stage_batch(h, batch, opts->variant, stream, &st);
+  if (rc != PNEC_OK) return rc;
+  SolveArgs a{};
+  a.bv = st.bv;
+  a.o = *opts;
+  const bool host = batch->memspace == PNEC_MEM_HOST;
+  if (host) {
+    PNEC_CUDA(h->d_out_poses.ensure(static_cast<size_t>(B) * 56));
+    PNEC_CUDA(h->d_out_status.ensure(static_cast<size_t>(B) * 4));
+    PNEC_CUDA(h->d_out_iters.ensure(static_cast<size_t>(B) * 4));
+    PNEC_CUDA(h->d_out_cost.ensure(static_cast<size_t>(B) * 8));
+    PNEC_CUDA(h->d_out_init.ensure(static_cast<size_t>(B) * 8));
+    a.out_poses = static_cast<double *>(h->d_out_poses.p);
+    a.out_status = out->status ? static_cast<int *>(h->d_out_status.p) : nullptr;
+    a.out_iters = out->iterations ? static_cast<int *>(h->d_out_iters.p) : nullptr;
+    a.out_cost = out->cost ? static_cast<double *>(h->d_out_cost.p) : nullptr;
+    a.out_init_cost = out->initial_cost ? static_cast<double *>(h->d_out_init.p) : nullptr;
+  } else {
+    a.out_poses = out->poses;
+    a.out_status = out->status;
+    a.out_iters = out->iterations;
+    a.out_cost = out->cost;
+    a.out_init_cost = out->initial_cost;
+  }
+  rc = launch_solve(h, a, opts->variant, st.max_n, stream);
+  if (rc != PNEC_OK) return rc;
+  if (host) {
+    PNEC_CUDA(cudaMemcpyAsync(out->poses, a.out_poses, static_cast<size_t>(B) * 56,
+                              cudaMemcpyDeviceToHost, stream));
+    if (out->status)
+      PNEC_CUDA(cudaMemcpyAsync(out->status, a.out_status, static_cast<size_t>(B) * 4,
+                                cudaMemcpyDeviceToHost, stream));
+    if (out->iterations)
+      PNEC_CUDA(cudaMemcpyAsync(out->iterations, a.out_iters, static_cast<size_t>(B) * 4,
+                                cudaMemcpyDeviceToHost, stream));
+    if (out->cost)
+      PNEC_CUDA(cudaMemcpyAsync(out->cost, a.out_cost, static_cast<size_t>(B) * 8,
+                                cudaMemcpyDeviceToHost, stream));
+    if (out->initial_cost)
+      PNEC_CUDA(cudaMemcpyAsync(out->initial_cost, a.out_init_cost, static_cast<size_t>(B) * 8,
+                                cudaMemcpyDeviceToHost, stream));
+    PNEC_CUDA(cudaStreamSynchronize(stream));
+  }
+  return PNEC_OK;
+}
+
+int pnec_eval_batch(pnec_handle *h, const pnec_batch *batch, int32_t variant,
+                    double regularization, const pnec_eval_out *out, void *cuda_stream) {
+  if (!h || !out) return fail(PNEC_ERR_INVALID_ARGUMENT, "NULL argument");
+  int rc = validate_batch(batch, variant, true);
+  if (rc != PNEC_OK) return rc;
+  const long long B = batch->num_problems;
+  if (B == 0) return PNEC_OK;
+  std::lock_guard<std::mutex> lock(h->mu);
+  PNEC_CUDA(cudaSetDevice(h->device));
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  Staged st;
+  rc = stage_batch(h, batch, variant, stream, &st);
+  if (rc != PNEC_OK) return rc;
+  EvalArgs a{};
+  a.bv = st.bv;
+  a.reg = regularization;
+  const bool host = batch->memspace == PNEC_MEM_HOST;
+  if (host) {
+    PNEC_CUDA(h->d_out_cost.ensure(static_cast<size_t>(B) * 8));
+    PNEC_CUDA(h->d_out_grad.ensure(static_cast<size_t>(B) * 40));
+    PNEC_CUDA(h->d_out_jtj.ensure(static_cast<size_t>(B) * 120));
+    a.out_cost = out->cost ? static_cast<double *>(h->d_out_cost.p) : nullptr;
+    a.out_grad = out->gradient ? static_cast<double *>(h->d_out_grad.p) : nullptr;
+    a.out_jtj = out->jtj ? static_cast<double *>(h->d_out_jtj.p) : nullptr;
+  } else {
+    a.out_cost = out->cost;
+    a.out_grad = out->gradient;
+    a.out_jtj = out->jtj;
+  }
+  rc = launch_eval(h, a, variant, st.max_n, stream);
+  if (rc != PNEC_OK) return rc;
+  if (host) {
+    if (out->cost)
+      PNEC_CUDA(cudaMemcpyAsync(out->cost, a.out_cost, static_cast<size_t>(B) * 8,
+                                cudaMemcpyDeviceToHost, stream));
+    if (out->gradient)
+      PNEC_CUDA(cudaMemcpyAsync(out->gradient, a.out_grad, static_cast<size_t>(B) * 40,
+                                cudaMemcpyDeviceToHost, stream));
+    if (out->jtj)
+      PNEC_CUDA(cudaMemcpyAsync(out->jtj, a.out_jtj, static_cast<size_t>(B) * 120,
+                                cudaMemcpyDeviceToHost, stream));
+    PNEC_CUDA(cudaStreamSynchronize(stream));
+  }
+  return PNEC_OK;
+}
+
+int pnec_cost_function_batch(pnec_handle *h, const pnec_batch *batch, double *out_mean_energy,
+                             void *cuda_stream) {
+  if (!h || !out_mean_energy) return fail(PNEC_ERR_INVALID_ARGUMENT, "NULL argument");
+  int rc = validate_batch(batch, PNEC_VARIANT_TARGET, true);
+  if (rc != PNEC_OK) return rc;
+  const long long B = batch->num_problems;
+  if (B == 0) return PNEC_OK;
+  std::lock_guard<std::mutex> lock(h->mu);
+  PNEC_CUDA(cudaSetDevice(h->device));
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  Staged st;
+  rc = stage_batch(h, batch, PNEC_VARIANT_TARGET, stream, &st);
+  if (rc != PNEC_OK) return rc;
+  const bool host = batch->memspace == PNEC_MEM_HOST;
+  double *d_out = out_mean_energy;
+  if (host) {
+    PNEC_CUDA(h->d_out_cost.ensure(static_cast<size_t>(B) * 8));
+    d_out = static_cast<double *>(h->d_out_cost.p);
+  }
+  cost_kernel<<<static_cast<unsigned>(B), 128, 0, stream>>>(st.bv, d_out);
+  PNEC_CUDA(cudaGetLastError());
+  h->launches++;
+  if (host) {
+    PNEC_CUDA(cudaMemcpyAsync(out_mean_energy, d_out, static_cast<size_t>(B) * 8,
+                              cudaMemcpyDeviceToHost, stream));
+    PNEC_CUDA(cudaStreamSynchronize(stream));
+  }
+  return PNEC_OK;
+}
+
+}  // extern "C"
