@@ -402,6 +402,133 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(const __grid_consta
   }
 }
 
+// ----------------------------------------------------- eval kernel, warp-private
+//
+// K1 as a persistent, barrier-free stream.  Every warp owns its frame pairs
+// (problem gw, gw + W, gw + 2W, ...), its own S-stage ring of 32-correspondence
+// tiles in shared memory and its own mbarriers; lane 0 keeps the ring S tiles ahead
+// with bulk async copies and the ring runs across problem boundaries, so HBM
+// requests never drain between problems.  No __syncthreads anywhere: the only
+// cross-lane traffic is the transposing reduction once per problem.  Pose
+// constants (acos/atan2/sincos, the expensive scalar part) are prepared
+// lane-parallel for CHUNK problems at a time.
+template <int V, int WPC, int S, int CHUNK, int MINB>
+__global__ void __launch_bounds__(WPC * 32, MINB)
+eval_warp_kernel(const __grid_constant__ EvalArgs args) {
+  constexpr int T = 32;
+  constexpr int kStageDoubles = T * VariantTraits<V>::kDoubles;
+  __shared__ __align__(8) uint64_t s_full[WPC][S];
+  __shared__ PoseConst s_pcs[WPC][CHUNK];
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long W = static_cast<long long>(gridDim.x) * WPC;
+  const long long gw = static_cast<long long>(blockIdx.x) * WPC + warp;
+  const long long B = args.bv.num_problems;
+  const long long nmine = (B > gw) ? (B - gw + W - 1) / W : 0;
+  double *ring = dyn_smem + static_cast<size_t>(warp) * S * kStageDoubles;
+  uint64_t *full = s_full[warp];
+
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < S; ++i) mbar_init(&full[i], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+
+  // producer cursor (uniform across the warp; only lane 0 issues)
+  long long pj = 0, pg0 = 0;
+  int ptile = 0, pntiles = 0, pspan = 0;
+  auto producer_open = [&]() {  // position on the first tile of the next non-empty problem
+    while (pj < nmine) {
+      long long s, e;
+      problem_range(args.bv, gw + pj * W, s, e);
+      if (e > s) {
+        pg0 = s & ~1LL;
+        pspan = static_cast<int>(e - pg0);
+        pntiles = (pspan + T - 1) / T;
+        ptile = 0;
+        return;
+      }
+      ++pj;
+    }
+  };
+  long long issued = 0;
+  auto producer_issue = [&]() {  // issue the current producer tile, then advance
+    if (pj >= nmine) return;
+    const int st = static_cast<int>(issued % S);
+    double *base = ring + st * kStageDoubles;
+    if (lane == 0) {
+      issue_bulk<V>(args.bv, pg0 + static_cast<long long>(ptile) * T, min(T, pspan - ptile * T),
+                    base, base + 3 * T, base + 6 * T, base + 15 * T, &full[st]);
+    }
+    ++issued;
+    if (++ptile == pntiles) {
+      ++pj;
+      producer_open();
+    }
+  };
+  producer_open();
+#pragma unroll 1
+  for (int i = 0; i < S; ++i) producer_issue();
+
+  long long consumed = 0;
+  for (long long j = 0; j < nmine; ++j) {
+    if (j % CHUNK == 0) {
+      __syncwarp();
+      if (lane < CHUNK && j + lane < nmine) {
+        const double *p = args.bv.poses + 7 * (gw + (j + lane) * W);
+        double x[6];
+        angles_from_vec(p + 4, x[0], x[1]);
+        x[2] = p[0]; x[3] = p[1]; x[4] = p[2]; x[5] = p[3];
+        PoseConst pc0;
+        make_pose_const(x, pc0);
+        s_pcs[warp][lane] = pc0;
+      }
+      __syncwarp();
+    }
+    const long long prob = gw + j * W;
+    long long s, e;
+    problem_range(args.bv, prob, s, e);
+    const int head = static_cast<int>(s & 1LL);
+    const int span = static_cast<int>(e - s) + head;
+    const int ntiles = (e > s) ? (span + T - 1) / T : 0;
+    PoseConst pc;
+    load_pose_const(s_pcs[warp][j % CHUNK], pc);
+    double acc[kNumAcc];
+#pragma unroll
+    for (int i = 0; i < kNumAcc; ++i) acc[i] = 0.0;
+    for (int k = 0; k < ntiles; ++k) {
+      const int st = static_cast<int>(consumed % S);
+      mbar_wait(&full[st], static_cast<uint32_t>((consumed / S) & 1));
+      const double *base = ring + st * kStageDoubles;
+      const int i = k * T + lane;
+      const bool valid = (i >= head) && (i < span);
+      double a1[3], a2[3], c1[9], c2[9];
+      if (valid) load_corr<V>(base, base + 3 * T, base + 6 * T, base + 15 * T, lane, a1, a2, c1, c2);
+      __syncwarp();  // every lane holds its correspondence: the stage may be refilled
+      producer_issue();
+      ++consumed;
+      if (valid) {
+        double r, row[5];
+        residual_row<V>(pc, args.reg, a1, a2, c1, c2, r, row);
+        accumulate(acc, r, row);
+      }
+    }
+    const double v = warp_transpose_reduce(acc, lane);
+    const int idx = warp_reduce_owner_index(lane);
+    if (idx >= 0 && idx < kNumAcc) {
+      const double out = v * acc_scale(idx);
+      if (idx < 15) {
+        if (args.out_jtj) args.out_jtj[15 * prob + idx] = out;
+      } else if (idx < 20) {
+        if (args.out_grad) args.out_grad[5 * prob + (idx - 15)] = out;
+      } else {
+        if (args.out_cost) args.out_cost[prob] = out;
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- cost kernel
 // pnec::common::CostFunction, src/common/common.cc:237-259: mean of
 // (t^T (f1 x R f2))^2 / (b^T S b), no regularisation.  pose: unit quaternion taken
@@ -680,15 +807,32 @@ int launch_eval_t(pnec_handle *h, const EvalArgs &a, cudaStream_t stream) {
   return PNEC_OK;
 }
 
+template <int V, int WPC, int S, int CHUNK, int MINB>
+int launch_eval_warp_t(pnec_handle *h, const EvalArgs &a, cudaStream_t stream) {
+  auto kern = eval_warp_kernel<V, WPC, S, CHUNK, MINB>;
+  const size_t dyn = static_cast<size_t>(WPC) * S * 32 * VariantTraits<V>::kDoubles * 8;
+  PNEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(dyn)));
+  const long long want = (a.bv.num_problems + WPC - 1) / WPC;
+  const long long cap = static_cast<long long>(h->sm_count) * MINB;
+  const unsigned grid = static_cast<unsigned>(std::max<long long>(1, std::min(want, cap)));
+  kern<<<grid, WPC * 32, dyn, stream>>>(a);
+  PNEC_CUDA(cudaGetLastError());
+  h->launches++;
+  return PNEC_OK;
+}
+
 template <int V>
 int launch_eval_v(pnec_handle *h, const EvalArgs &a, long long max_n, cudaStream_t stream) {
+  (void)max_n;
   int cfg = env_int("PNEC_B200_EVAL_CFG", 0);
-  if (cfg == 0) cfg = max_n <= 96 ? 1 : 2;
+  if (cfg == 0) cfg = a.use_bulk ? 10 : 2;
   switch (cfg) {
-    case 1: return launch_eval_t<V, 2, 2, 8>(h, a, stream);   // 64-wide tiles, small problems
-    case 2: return launch_eval_t<V, 4, 4, 3>(h, a, stream);   // 128-wide tiles, 4 stages
-    case 3: return launch_eval_t<V, 4, 2, 6>(h, a, stream);   // 128-wide tiles, 2 stages
-    case 4: return launch_eval_t<V, 8, 2, 3>(h, a, stream);   // 256-wide tiles, 2 stages
+    case 2: return launch_eval_t<V, 4, 4, 3>(h, a, stream);    // CTA per problem, 128-wide tiles
+    case 10: return launch_eval_warp_t<V, 4, 4, 8, 3>(h, a, stream);  // warp-private, 4 stages
+    case 11: return launch_eval_warp_t<V, 4, 3, 8, 3>(h, a, stream);
+    case 12: return launch_eval_warp_t<V, 4, 6, 8, 2>(h, a, stream);
+    case 13: return launch_eval_warp_t<V, 8, 3, 8, 2>(h, a, stream);
     default: return fail(PNEC_ERR_INVALID_ARGUMENT, "unknown PNEC_B200_EVAL_CFG");
   }
 }

@@ -1,0 +1,60 @@
+"""CPU, world_size 2, gloo: the sharded solve + gather reproduces the single-process result.
+The per-shard solver here is the oracle (test infrastructure); on GPUs it is the CUDA handle."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, ragged, out_dir):
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    sys.path.insert(0, os.path.join(root, "tests"))
+    import oracle
+    from pnec_b200 import distributed
+    from pnec_b200 import synthetic as syn
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        B, N = 7, 40
+        counts = np.array([5, 40, 1, 0, 33, 64, 12]) if ragged else None
+        b = syn.make_batch(B, N, seed=21, counts=counts)
+
+        def solve_fn(f1, f2, ct, ch, poses, offsets=None, n_per_problem=None):
+            p, info = oracle.solve_batch(f1, f2, ct, ch, poses, oracle.default_opts(oracle.TARGET),
+                                         offsets=offsets, n_per_problem=n_per_problem)
+            return (torch.from_numpy(p), torch.from_numpy(info["status"].copy()),
+                    torch.from_numpy(info["iterations"].copy()))
+
+        poses, status, iters = distributed.solve_sharded(
+            solve_fn, B, N, b.offsets, b.bvs_host, b.bvs_target, b.covs_target, None, b.init_poses)
+        ref, info = oracle.solve_batch(b.bvs_host, b.bvs_target, b.covs_target, None, b.init_poses,
+                                       oracle.default_opts(oracle.TARGET), offsets=b.offsets,
+                                       n_per_problem=N)
+        assert np.array_equal(poses.numpy(), ref)
+        assert np.array_equal(status.numpy(), info["status"])
+        assert np.array_equal(iters.numpy(), info["iterations"])
+        open(os.path.join(out_dir, f"ok{rank}"), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+def test_sharded_solve_matches_single_process(tmp_path, ragged):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), ragged, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
