@@ -271,55 +271,158 @@ __device__ __forceinline__ double warp_transpose_reduce(const double acc[kNumAcc
 // State of ceres::TrustRegionMinimizer + LevenbergMarquardtStrategy for one
 // problem.  Lives in shared memory between evaluations so that it costs no
 // registers while the CTA streams correspondences.
+//
+// The per-iteration update is the serial part of a solve (one warp, the other
+// warps of the CTA wait), so it is written as straight-line, branch-free code:
+// Newton-refined MUFU reciprocals instead of IEEE division, LDL^T instead of
+// Cholesky (no square roots), small-angle polynomials + angle addition instead of
+// sin/cos calls.  All of it stays within a few ulp of the IEEE forms.
 struct LMState {
-  double x[6];     // accepted point (theta, phi, qx, qy, qz, qw)
-  double cand[6];  // candidate point being evaluated
-  double H[15];    // J^T J at x (unscaled, packed upper)
-  double g[5];     // J^T r at x
-  double scale[5]; // Jacobi column scaling, fixed at iteration 0
-  double diag[5];  // LM diagonal of the scaled Jacobian (reused on rejection)
-  double x_cost, x_norm, radius, decrease_factor, model_cost_change, gmax, initial_cost;
-  int iteration, num_invalid, reuse_diagonal, step_successful, status, done;
+  double x[6];      // accepted point (theta, phi, qx, qy, qz, qw)
+  double cand[6];   // candidate point being evaluated
+  double sc[4];     // sin/cos of theta, phi at x:    s_th, c_th, s_ph, c_ph
+  double scc[4];    // same at the candidate
+  double H[15];     // J^T J at x (unscaled, packed upper)
+  double g[5];      // J^T r at x
+  double scale[5];  // Jacobi column scaling, fixed at iteration 0
+  double diag[5];   // LM diagonal of the scaled Jacobian (reused on rejection)
+  double x_cost, x_norm, radius, decrease_factor, model_cost_change, initial_cost;
+  int iteration, num_invalid, reuse_diagonal, step_successful, grad_converged, status, done;
 };
 
 __host__ __device__ constexpr int tri(int a, int b) {  // a <= b
   return a * 5 - (a * (a - 1)) / 2 + (b - a);
 }
 
-// || x - Plus(x, -g) ||_inf.  Exact whenever it can matter (|g_d| < 1); for larger
-// quaternion gradients the theta/phi part or the chord 2|sin(|g_d|/2)| already
-// exceeds any sensible gradient_tolerance, and +inf is returned instead of
-// paying sin/cos of a huge argument.
-__device__ __forceinline__ double gradient_max_norm(const double x[6], const double g[5]) {
-  double m = fmax(fabs(g[0]), fabs(g[1]));
-  const double nd2 = g[2] * g[2] + g[3] * g[3] + g[4] * g[4];
-  if (nd2 >= 1.0) return CUDART_INF;
-  double ng[5] = {-g[0], -g[1], -g[2], -g[3], -g[4]}, xs[6];
-  state_plus(x, ng, xs);
-#pragma unroll
-  for (int i = 2; i < 6; ++i) m = fmax(m, fabs(x[i] - xs[i]));
-  return m;
+// 1/x: MUFU.RCP64H seed + Newton steps (each squares the relative error); no
+// special-case branches.  x must be a finite, non-zero normal number.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  return y;
+}
+// sqrt(x) for x >= 0 through rsqrt (no slow-path branch)
+__device__ __forceinline__ double fast_sqrt(double x) { return x > 0.0 ? x * rsqrt(x) : 0.0; }
+
+// sin(a)/a and cos(a) as polynomials in z = a^2, |a| <= 0.25 (truncation < 1e-19)
+__device__ __forceinline__ void small_sinc_cos(double z, double &sinc, double &cs) {
+  double p = -1.0 / 1307674368000.0;
+  p = fma(p, z, 1.0 / 6227020800.0);
+  p = fma(p, z, -1.0 / 39916800.0);
+  p = fma(p, z, 1.0 / 362880.0);
+  p = fma(p, z, -1.0 / 5040.0);
+  p = fma(p, z, 1.0 / 120.0);
+  p = fma(p, z, -1.0 / 6.0);
+  sinc = fma(p, z, 1.0);
+  double q = 1.0 / 20922789888000.0;
+  q = fma(q, z, -1.0 / 87178291200.0);
+  q = fma(q, z, 1.0 / 479001600.0);
+  q = fma(q, z, -1.0 / 3628800.0);
+  q = fma(q, z, 1.0 / 40320.0);
+  q = fma(q, z, -1.0 / 720.0);
+  q = fma(q, z, 1.0 / 24.0);
+  q = fma(q, z, -0.5);
+  cs = fma(q, z, 1.0);
+}
+constexpr double kSmallAngle2 = 0.0625;  // (0.25 rad)^2
+
+// (sin, cos)(a + d) from (sin, cos)(a); exact sincos when the step is large.
+__device__ __forceinline__ void advance_sincos(double a_new, double d, double s, double c,
+                                               double &s_new, double &c_new) {
+  const double z = d * d;
+  if (z <= kSmallAngle2) {
+    double sinc, cd;
+    small_sinc_cos(z, sinc, cd);
+    const double sd = d * sinc;
+    s_new = fma(s, cd, c * sd);
+    c_new = fma(c, cd, -s * sd);
+  } else {
+    sincos(a_new, &s_new, &c_new);
+  }
 }
 
-// 5x5 Cholesky solve A y = b; returns false if A is not positive definite or the
-// solution is not finite (== LINEAR_SOLVER_FAILURE, an invalid step).
-__device__ __forceinline__ bool chol_solve5(const double A[5][5], const double b[5], double y[5]) {
-  double L[5][5], inv[5];
+// ceres::EigenQuaternionManifold::Plus with the small-angle forms (no sqrt, no
+// division, no sin/cos call while |d| <= 0.25 rad).
+__device__ __forceinline__ void quat_plus_fast(const double x[4], const double d[3],
+                                               double out[4]) {
+  const double z = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+  double s, dw;
+  if (z <= kSmallAngle2) {
+    small_sinc_cos(z, s, dw);
+  } else {
+    const double nd = sqrt(z);
+    double sn;
+    sincos(nd, &sn, &dw);
+    s = sn / nd;
+  }
+  const double dx = s * d[0], dy = s * d[1], dz = s * d[2];
+  const double xx = x[0], xy = x[1], xz = x[2], xw = x[3];
+  out[3] = dw * xw - dx * xx - dy * xy - dz * xz;
+  out[0] = dw * xx + dx * xw + dy * xz - dz * xy;
+  out[1] = dw * xy - dx * xz + dy * xw + dz * xx;
+  out[2] = dw * xz + dx * xy - dy * xx + dz * xw;
+}
+
+// Pose constants from sin/cos of (theta, phi) and the quaternion.
+__device__ __forceinline__ void make_pose_const_sc(const double sc[4], const double q[4],
+                                                   PoseConst &pc) {
+  const double st = sc[0], ct = sc[1], sp = sc[2], cp = sc[3];
+  pc.t[0] = st * cp;  pc.t[1] = st * sp;  pc.t[2] = ct;
+  pc.tth[0] = ct * cp; pc.tth[1] = ct * sp; pc.tth[2] = -st;
+  pc.tph[0] = -st * sp; pc.tph[1] = st * cp; pc.tph[2] = 0.0;
+  const double qx = q[0], qy = q[1], qz = q[2], qw = q[3];
+  const double tx = 2.0 * qx, ty = 2.0 * qy, tz = 2.0 * qz;
+  const double twx = tx * qw, twy = ty * qw, twz = tz * qw;
+  const double txx = tx * qx, txy = ty * qx, txz = tz * qx;
+  const double tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
+  pc.R[0] = 1.0 - (tyy + tzz); pc.R[1] = txy - twz;         pc.R[2] = txz + twy;
+  pc.R[3] = txy + twz;         pc.R[4] = 1.0 - (txx + tzz); pc.R[5] = tyz - twx;
+  pc.R[6] = txz - twy;         pc.R[7] = tyz + twx;         pc.R[8] = 1.0 - (txx + tyy);
+}
+
+// gradient_max_norm <= tol, where gradient_max_norm = || x - Plus(x, -g) ||_inf
+// (TrustRegionMinimizer::EvaluateGradientAndJacobian).  The theta/phi part of
+// that norm is |g0|, |g1|; the quaternion part is only evaluated when those pass.
+__device__ __forceinline__ bool gradient_converged(const double x[6], const double g[5],
+                                                   double tol) {
+  if (!(fmax(fabs(g[0]), fabs(g[1])) <= tol)) return false;
+  const double nd2 = g[2] * g[2] + g[3] * g[3] + g[4] * g[4];
+  if (nd2 > kSmallAngle2) return false;  // chord 2 sin(|g|/2) is far above any tolerance
+  const double ng[3] = {-g[2], -g[3], -g[4]};
+  double qs[4];
+  quat_plus_fast(x + 2, ng, qs);
+  double m = 0.0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) m = fmax(m, fabs(x[2 + i] - qs[i]));
+  return m <= tol;
+}
+
+// 5x5 LDL^T solve of A y = b (A symmetric, upper part read).  Returns false if a
+// pivot is not positive (A not positive definite) or the solution is not finite:
+// LINEAR_SOLVER_FAILURE in Ceres terms, an invalid step.
+__device__ __forceinline__ bool ldlt_solve5(const double A[5][5], const double b[5], double y[5]) {
+  double L[5][5], d[5], id[5];
   bool ok = true;
 #pragma unroll
   for (int j = 0; j < 5; ++j) {
-    double d = A[j][j];
+    double dj = A[j][j];
 #pragma unroll
-    for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
-    ok = ok && (d > 0.0) && (d < CUDART_INF);
-    const double l = sqrt(d);
-    inv[j] = 1.0 / l;
+    for (int k = 0; k < j; ++k) dj = fma(-L[j][k] * L[j][k], d[k], dj);
+    d[j] = dj;
+    ok = ok && (dj > 0.0) && (dj < CUDART_INF);
+    id[j] = fast_rcp(dj);
 #pragma unroll
     for (int i = j + 1; i < 5; ++i) {
-      double s = A[i][j];
+      double s = A[j][i];
 #pragma unroll
-      for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
-      L[i][j] = s * inv[j];
+      for (int k = 0; k < j; ++k) s = fma(-L[i][k] * L[j][k], d[k], s);
+      L[i][j] = s * id[j];
     }
   }
   double z[5];
@@ -327,15 +430,15 @@ __device__ __forceinline__ bool chol_solve5(const double A[5][5], const double b
   for (int i = 0; i < 5; ++i) {
     double s = b[i];
 #pragma unroll
-    for (int k = 0; k < i; ++k) s -= L[i][k] * z[k];
-    z[i] = s * inv[i];
+    for (int k = 0; k < i; ++k) s = fma(-L[i][k], z[k], s);
+    z[i] = s;
   }
 #pragma unroll
   for (int i = 4; i >= 0; --i) {
-    double s = z[i];
+    double s = z[i] * id[i];
 #pragma unroll
-    for (int k = i + 1; k < 5; ++k) s -= L[k][i] * y[k];
-    y[i] = s * inv[i];
+    for (int k = i + 1; k < 5; ++k) s = fma(-L[k][i], y[k], s);
+    y[i] = s;
   }
 #pragma unroll
   for (int i = 0; i < 5; ++i) ok = ok && (fabs(y[i]) < CUDART_INF);
@@ -344,13 +447,13 @@ __device__ __forceinline__ bool chol_solve5(const double A[5][5], const double b
 
 // FinalizeIterationAndCheckIfMinimizerCanContinue + ComputeTrustRegionStep.
 // Loops over invalid steps (they need no new evaluation).  On return either
-// st.done is set, or st.cand holds the next point to evaluate.
+// st.done is set, or st.cand / st.scc hold the next point to evaluate.
 __device__ __forceinline__ void lm_propose(LMState &st, const pnec_solver_opts &o) {
   for (;;) {
     if (st.iteration >= o.max_num_iterations) {
       st.status = PNEC_STATUS_MAX_ITERATIONS; st.done = 1; return;
     }
-    if (st.step_successful && st.gmax <= o.gradient_tolerance) {
+    if (st.step_successful && st.grad_converged) {
       st.status = PNEC_STATUS_CONVERGED_GRADIENT; st.done = 1; return;
     }
     if (st.radius <= o.min_trust_region_radius) {
@@ -358,44 +461,37 @@ __device__ __forceinline__ void lm_propose(LMState &st, const pnec_solver_opts &
     }
     st.iteration++;
 
-    double M[5][5], A[5][5], rhs[5], y[5];
+    double A[5][5], rhs[5], y[5];
 #pragma unroll
     for (int a = 0; a < 5; ++a) {
       rhs[a] = st.g[a] * st.scale[a];
 #pragma unroll
       for (int b = a; b < 5; ++b) {
-        M[a][b] = st.H[tri(a, b)] * st.scale[a] * st.scale[b];
-        M[b][a] = M[a][b];
+        A[a][b] = st.H[tri(a, b)] * st.scale[a] * st.scale[b];
+        A[b][a] = A[a][b];
       }
     }
     if (!st.reuse_diagonal) {
 #pragma unroll
       for (int a = 0; a < 5; ++a)
-        st.diag[a] = fmin(fmax(M[a][a], o.min_lm_diagonal), o.max_lm_diagonal);
+        st.diag[a] = fmin(fmax(A[a][a], o.min_lm_diagonal), o.max_lm_diagonal);
     }
+    const double inv_radius = fast_rcp(st.radius);
+    double D[5];
 #pragma unroll
     for (int a = 0; a < 5; ++a) {
-#pragma unroll
-      for (int b = 0; b < 5; ++b) A[a][b] = M[a][b];
-      A[a][a] += st.diag[a] / st.radius;
+      D[a] = st.diag[a] * inv_radius;
+      A[a][a] += D[a];
     }
-    bool valid = chol_solve5(A, rhs, y);
+    bool valid = ldlt_solve5(A, rhs, y);
     st.reuse_diagonal = 1;
+    // step = -y.  model_cost_change = -(J s)^T (f + J s / 2) = y.rhs - y^T M y / 2 with
+    // M = A - D and A y = rhs, i.e. (y.rhs + y^T D y) / 2.
     double mcc = 0.0;
-    if (valid) {
-      // step = -y; model_cost_change = -(J s)^T (f + J s / 2) = -s.g - s^T M s / 2
-      double sg = 0.0, sMs = 0.0;
 #pragma unroll
-      for (int a = 0; a < 5; ++a) {
-        double Ms = 0.0;
-#pragma unroll
-        for (int b = 0; b < 5; ++b) Ms += M[a][b] * y[b];
-        sMs += y[a] * Ms;
-        sg += y[a] * rhs[a];
-      }
-      mcc = sg - 0.5 * sMs;
-      valid = (mcc > 0.0);
-    }
+    for (int a = 0; a < 5; ++a) mcc = fma(y[a], fma(D[a], y[a], rhs[a]), mcc);
+    mcc *= 0.5;
+    valid = valid && (mcc > 0.0);
     if (!valid) {
       if (++st.num_invalid >= o.max_num_consecutive_invalid_steps) {
         st.status = PNEC_STATUS_FAILURE; st.done = 1; return;
@@ -409,7 +505,11 @@ __device__ __forceinline__ void lm_propose(LMState &st, const pnec_solver_opts &
     double delta[5];
 #pragma unroll
     for (int a = 0; a < 5; ++a) delta[a] = -y[a] * st.scale[a];
-    state_plus(st.x, delta, st.cand);
+    st.cand[0] = st.x[0] + delta[0];
+    st.cand[1] = st.x[1] + delta[1];
+    advance_sincos(st.cand[0], delta[0], st.sc[0], st.sc[1], st.scc[0], st.scc[1]);
+    advance_sincos(st.cand[1], delta[1], st.sc[2], st.sc[3], st.scc[2], st.scc[3]);
+    quat_plus_fast(st.x + 2, delta + 2, st.cand + 2);
     return;
   }
 }
@@ -428,8 +528,8 @@ __device__ __forceinline__ void lm_begin(LMState &st, const double tot[kNumAcc],
   }
 #pragma unroll
   for (int a = 0; a < 5; ++a)
-    st.scale[a] = o.jacobi_scaling ? 1.0 / (1.0 + sqrt(st.H[tri(a, a)])) : 1.0;
-  st.gmax = gradient_max_norm(st.x, st.g);
+    st.scale[a] = o.jacobi_scaling ? fast_rcp(1.0 + fast_sqrt(st.H[tri(a, a)])) : 1.0;
+  st.grad_converged = gradient_converged(st.x, st.g, o.gradient_tolerance) ? 1 : 0;
   st.step_successful = 1;
 }
 
@@ -441,37 +541,42 @@ __device__ __forceinline__ void lm_judge(LMState &st, const double tot[kNumAcc],
   if (!(fabs(cand_cost) < CUDART_INF)) cand_cost = DBL_MAX;
   double sn = 0.0;
 #pragma unroll
-  for (int i = 0; i < 6; ++i) sn += (st.x[i] - st.cand[i]) * (st.x[i] - st.cand[i]);
-  if (sqrt(sn) <= o.parameter_tolerance * (st.x_norm + o.parameter_tolerance)) {
+  for (int i = 0; i < 6; ++i) sn = fma(st.x[i] - st.cand[i], st.x[i] - st.cand[i], sn);
+  const double ptol = o.parameter_tolerance * (st.x_norm + o.parameter_tolerance);
+  if (sn <= ptol * ptol) {  // step_norm <= tolerance, compared squared
     st.status = PNEC_STATUS_CONVERGED_PARAMETER; st.done = 1; return;
   }
   const double cost_change = st.x_cost - cand_cost;
   if (fabs(cost_change) <= o.function_tolerance * st.x_cost) {
     st.status = PNEC_STATUS_CONVERGED_FUNCTION; st.done = 1; return;
   }
-  const double rho = (cand_cost >= DBL_MAX) ? -DBL_MAX : cost_change / st.model_cost_change;
+  const double rho =
+      (cand_cost >= DBL_MAX) ? -DBL_MAX : cost_change * fast_rcp(st.model_cost_change);
   if (rho > o.min_relative_decrease) {
-#pragma unroll
-    for (int i = 0; i < 6; ++i) st.x[i] = st.cand[i];
     double xn = 0.0;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) xn += st.x[i] * st.x[i];
-    st.x_norm = sqrt(xn);
+    for (int i = 0; i < 6; ++i) {
+      st.x[i] = st.cand[i];
+      xn = fma(st.x[i], st.x[i], xn);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) st.sc[i] = st.scc[i];
+    st.x_norm = fast_sqrt(xn);
     st.x_cost = cand_cost;
 #pragma unroll
     for (int i = 0; i < 15; ++i) st.H[i] = tot[i];
 #pragma unroll
     for (int i = 0; i < 5; ++i) st.g[i] = tot[15 + i];
-    st.gmax = gradient_max_norm(st.x, st.g);
+    st.grad_converged = gradient_converged(st.x, st.g, o.gradient_tolerance) ? 1 : 0;
     st.step_successful = 1;
     const double c = 2.0 * rho - 1.0;
-    st.radius = st.radius / fmax(1.0 / 3.0, 1.0 - c * c * c);
+    st.radius = st.radius * fast_rcp(fmax(1.0 / 3.0, 1.0 - c * c * c));
     st.radius = fmin(o.max_trust_region_radius, st.radius);
     st.decrease_factor = 2.0;
     st.reuse_diagonal = 0;
   } else {
     st.step_successful = 0;
-    st.radius = st.radius / st.decrease_factor;
+    st.radius = st.radius * fast_rcp(st.decrease_factor);
     st.decrease_factor *= 2.0;
     st.reuse_diagonal = 1;
   }

@@ -208,32 +208,39 @@ __global__ void __launch_bounds__(NW * 32, MINB) solve_kernel(const __grid_const
   if (tid == 0) {
     mbar_init(&s_bar, 1);
     fence_mbar_init();
+    // get the HBM -> shared-memory copies going before the scalar set-up below
+    if (n > 0 && resident && args.use_bulk)
+      issue_bulk<V>(args.bv, g0, span, sf1, sf2, sct, sch, &s_bar);
     // PNECCeres::InitValues(orientation, translation), pnec_ceres.cc:188-192
     const double *p = args.bv.poses + 7 * b;
     LMState &st = s_lm;
     angles_from_vec(p + 4, st.x[0], st.x[1]);
     st.x[2] = p[0]; st.x[3] = p[1]; st.x[4] = p[2]; st.x[5] = p[3];
+    sincos(st.x[0], &st.sc[0], &st.sc[1]);
+    sincos(st.x[1], &st.sc[2], &st.sc[3]);
     double xn = 0.0;
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
       st.cand[i] = st.x[i];
       xn += st.x[i] * st.x[i];
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) st.scc[i] = st.sc[i];
     st.x_norm = sqrt(xn);
     st.radius = o.initial_trust_region_radius;
     st.decrease_factor = 2.0;
     st.model_cost_change = 0.0;
-    st.gmax = 0.0;
     st.x_cost = 0.0;
     st.initial_cost = 0.0;
     st.iteration = 0;
     st.num_invalid = 0;
     st.reuse_diagonal = 0;
     st.step_successful = 1;
+    st.grad_converged = 0;
     st.status = (n <= 0) ? PNEC_STATUS_EMPTY : PNEC_STATUS_MAX_ITERATIONS;
     st.done = (n <= 0) ? 1 : 0;
     PoseConst pc0;
-    make_pose_const(st.x, pc0);
+    make_pose_const_sc(st.sc, st.x + 2, pc0);
     s_pc = pc0;
   }
   __syncthreads();
@@ -241,7 +248,6 @@ __global__ void __launch_bounds__(NW * 32, MINB) solve_kernel(const __grid_const
   if (n > 0) {
     if (resident) {
       if (args.use_bulk) {
-        if (tid == 0) issue_bulk<V>(args.bv, g0, span, sf1, sf2, sct, sch, &s_bar);
         mbar_wait(&s_bar, 0);
       } else {
         copy_plain<V, NT>(args.bv, g0, span, sf1, sf2, sct, sch, tid);
@@ -274,7 +280,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) solve_kernel(const __grid_const
           s_lm = st;
           if (!st.done) {
             PoseConst pcn;
-            make_pose_const(st.cand, pcn);
+            make_pose_const_sc(st.scc, st.cand + 2, pcn);
             s_pc = pcn;
           }
         }
@@ -292,10 +298,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) solve_kernel(const __grid_const
     const double iq = qn > 0.0 ? 1.0 / qn : 1.0;
     double *op = args.out_poses + 7 * b;
     op[0] = st.x[2] * iq; op[1] = st.x[3] * iq; op[2] = st.x[4] * iq; op[3] = st.x[5] * iq;
-    double sth, cth, sph, cph;
-    sincos(st.x[0], &sth, &cth);
-    sincos(st.x[1], &sph, &cph);
-    op[4] = sth * cph; op[5] = sth * sph; op[6] = cth;
+    op[4] = st.sc[0] * st.sc[3]; op[5] = st.sc[0] * st.sc[2]; op[6] = st.sc[1];
     if (args.out_status) args.out_status[b] = st.status;
     if (args.out_iters) args.out_iters[b] = st.iteration;
     if (args.out_cost) args.out_cost[b] = st.x_cost;

@@ -1,0 +1,70 @@
+// Exercises the reference's C++ call shapes through include/pnec/pnec_compat.hpp.
+// Input (binary, from the Python test): int64 n, then f1[n*3], f2[n*3], cov_t[n*9],
+// cov_h[n*9], init pose7.  Output (text): one line per API with 7 pose numbers + status + iters.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "pnec/pnec_compat.hpp"
+
+using pnec::Mat3;
+using pnec::SE3;
+using pnec::Vec3;
+
+static void print_pose(const char *tag, const SE3 &p, int status, int iters) {
+  std::printf("%s %.17g %.17g %.17g %.17g %.17g %.17g %.17g %d %d\n", tag, p.q.c[0], p.q.c[1], p.q.c[2],
+              p.q.c[3], p.t[0], p.t[1], p.t[2], status, iters);
+}
+
+int main(int argc, char **argv) {
+  if (argc < 2) return 2;
+  FILE *f = std::fopen(argv[1], "rb");
+  if (!f) return 3;
+  long long n = 0;
+  if (std::fread(&n, sizeof(n), 1, f) != 1) return 4;
+  std::vector<Vec3> bvs1(n), bvs2(n);
+  std::vector<Mat3> covs_t(n), covs_h(n);
+  double init7[7];
+  bool ok = std::fread(bvs1.data(), sizeof(Vec3), n, f) == (size_t)n &&
+            std::fread(bvs2.data(), sizeof(Vec3), n, f) == (size_t)n &&
+            std::fread(covs_t.data(), sizeof(Mat3), n, f) == (size_t)n &&
+            std::fread(covs_h.data(), sizeof(Mat3), n, f) == (size_t)n &&
+            std::fread(init7, sizeof(double), 7, f) == 7;
+  std::fclose(f);
+  if (!ok) return 5;
+  const SE3 init(pnec::Quat(init7[3], init7[0], init7[1], init7[2]), Vec3(init7[4], init7[5], init7[6]));
+
+  // call shapes of src/run_simulation.cc:157-180 (Ablation) and src/rel_pose_estimation/pnec.cc:350-411
+  pnec::rel_pose_estimation::Options options;
+  options.use_ransac_ = false;
+  options.weighted_iterations_ = 0;
+  pnec::rel_pose_estimation::PNEC pnec(options);
+  SE3 a = pnec.CeresSolver(bvs1, bvs2, covs_t, init);
+  print_pose("CeresSolver", a, pnec.LastStatus(), pnec.LastIterations());
+  SE3 b = pnec.CeresSolverFull(bvs1, bvs2, covs_t, 1e-10, init);
+  print_pose("CeresSolverFull", b, pnec.LastStatus(), pnec.LastIterations());
+  SE3 c = pnec.NECCeresSolver(bvs1, bvs2, init);
+  print_pose("NECCeresSolver", c, pnec.LastStatus(), pnec.LastIterations());
+  SE3 d = pnec.Solve(bvs1, bvs2, covs_t, init);
+  print_pose("Solve", d, pnec.LastStatus(), pnec.LastIterations());
+
+  // lower level: include/optimization/pnec_ceres.h:50-81
+  pnec::optimization::PNECCeres opt;
+  opt.InitValues(pnec::Quat::FromRotationMatrix(init.rotationMatrix()), init.translation());
+  opt.Optimize(bvs1, bvs2, covs_t, 1e-13, pnec::common::Host);
+  print_pose("PNECCeresHost", opt.Result(), opt.Status(), opt.Iterations());
+  pnec::optimization::PNECCeres sym(init);
+  sym.Optimize(bvs1, bvs2, covs_h, covs_t, 1e-13);
+  print_pose("PNECCeresSymmetric", sym.Result(), sym.Status(), sym.Iterations());
+  std::printf("CostFunction %.17g\n", pnec::common::CostFunction(bvs1, bvs2, covs_t, a));
+
+  // unsupported orchestration must throw, not silently do something else
+  pnec::rel_pose_estimation::PNEC full((pnec::rel_pose_estimation::Options()));
+  try {
+    full.Solve(bvs1, bvs2, covs_t, init);
+    std::printf("SolveDefaultOptions no-throw\n");
+  } catch (const std::logic_error &) {
+    std::printf("SolveDefaultOptions throws\n");
+  }
+  return 0;
+}

@@ -1,0 +1,372 @@
+"""GPU (-m gpu): the CUDA path, called through the C-ABI, against the CPU oracle.
+
+Tolerances (BASELINE.json north_star): rotation within 1e-6 rad, translation direction
+within 1e-6 rad (modulo sign) of the Ceres-semantics oracle on identical inputs; the
+fused evaluation (cost, J^T r, J^T J) within 1e-9 relative of the oracle's closed form.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import direction_angle, max_pose_diff, rotation_angle
+from pnec_b200 import api
+from pnec_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROT_TOL = 1e-6  # rad
+DIR_TOL = 1e-6  # rad
+EVAL_RTOL = 1e-9
+
+VARIANTS = {"nec": api.NEC, "target": api.TARGET, "host": api.HOST, "symmetric": api.SYMMETRIC}
+CASES = ["c1_iso_omni_n100", "c2_aniso_omni_n512", "aniso_pinhole_n64", "aniso_omni_n10"]
+
+
+@pytest.fixture(scope="module")
+def handle():
+    import torch
+
+    assert torch.cuda.is_available(), "gpu tests need a B200"
+    return api.Handle(0)
+
+
+def dev(a):
+    import torch
+
+    return None if a is None else torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def covs_for(variant, ct, ch):
+    return (None if variant == api.NEC else ct), (ch if variant == api.SYMMETRIC else None)
+
+
+def oracle_solve(variant, f1, f2, ct, ch, init, **kw):
+    return oracle.solve_batch(f1, f2, ct, ch, init, oracle.default_opts(variant),
+                              num_threads=oracle.max_threads(), **kw)
+
+
+# ------------------------------------------------------------------ fixtures
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("vname", list(VARIANTS))
+def test_solve_matches_committed_oracle_solutions(handle, golden_solutions, name, vname):
+    g = golden_solutions
+    variant = VARIANTS[vname]
+    n = int(g[f"{name}/n"])
+    ct, ch = covs_for(variant, g[f"{name}/cov_t"], g[f"{name}/cov_h"])
+    res = handle.solve_batch(g[f"{name}/f1"], g[f"{name}/f2"], ct, ch, g[f"{name}/init"],
+                             api.default_opts(variant), n_per_problem=n)
+    r, t = max_pose_diff(res.poses, g[f"{name}/{vname}/poses"])
+    assert r <= ROT_TOL and t <= DIR_TOL, (r, t)
+    assert np.array_equal(res.iterations, g[f"{name}/{vname}/iterations"])
+    assert np.array_equal(res.status, g[f"{name}/{vname}/status"])
+    np.testing.assert_allclose(res.cost, g[f"{name}/{vname}/final_cost"], rtol=1e-9)
+    np.testing.assert_allclose(res.initial_cost, g[f"{name}/{vname}/initial_cost"], rtol=1e-11)
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("vname", list(VARIANTS))
+def test_eval_matches_committed_oracle_evaluations(handle, golden_solutions, name, vname):
+    g = golden_solutions
+    variant = VARIANTS[vname]
+    n = int(g[f"{name}/n"])
+    ct, ch = covs_for(variant, g[f"{name}/cov_t"], g[f"{name}/cov_h"])
+    ev = handle.eval_batch(g[f"{name}/f1"], g[f"{name}/f2"], ct, ch, g[f"{name}/init"], variant,
+                           1e-13, n_per_problem=n)
+    # committed evaluations use central differences (what Ceres does): ~1e-8 agreement
+    np.testing.assert_allclose(ev.cost, g[f"{name}/{vname}/eval_cost"], rtol=1e-12)
+    G, H = g[f"{name}/{vname}/eval_gradient"], g[f"{name}/{vname}/eval_jtj"]
+    for i in range(G.shape[0]):
+        np.testing.assert_allclose(ev.gradient[i], G[i], rtol=0, atol=5e-8 * np.abs(G[i]).max())
+        np.testing.assert_allclose(ev.jtj[i], H[i], rtol=0, atol=5e-8 * np.abs(H[i]).max())
+
+
+# ------------------------------------------------------- fresh seeded inputs
+
+
+@pytest.mark.parametrize("vname", list(VARIANTS))
+@pytest.mark.parametrize("B,N,camera", [(48, 100, syn.OMNIDIRECTIONAL), (12, 512, syn.OMNIDIRECTIONAL),
+                                        (40, 37, syn.PINHOLE)])
+def test_solve_and_eval_against_oracle(handle, vname, B, N, camera):
+    variant = VARIANTS[vname]
+    b = syn.with_host_covariances(syn.make_batch(B, N, seed=100 + N, camera=camera), camera=camera)
+    ct, ch = covs_for(variant, b.covs_target, b.covs_host)
+    res = handle.solve_batch(dev(b.bvs_host), dev(b.bvs_target), dev(ct), dev(ch), dev(b.init_poses),
+                             api.default_opts(variant), n_per_problem=N)
+    ref, info = oracle_solve(variant, b.bvs_host, b.bvs_target, ct, ch, b.init_poses, n_per_problem=N)
+    poses = res.poses.cpu().numpy()
+    r, t = max_pose_diff(poses, ref)
+    assert r <= ROT_TOL and t <= DIR_TOL, (r, t)
+    assert np.array_equal(res.iterations.cpu().numpy(), info["iterations"])
+    assert np.array_equal(res.status.cpu().numpy(), info["status"])
+    np.testing.assert_allclose(res.cost.cpu().numpy(), info["final_cost"], rtol=1e-9)
+    # fused evaluation vs the oracle's closed form
+    ev = handle.eval_batch(dev(b.bvs_host), dev(b.bvs_target), dev(ct), dev(ch), dev(b.init_poses),
+                           variant, 1e-13, n_per_problem=N)
+    for i in range(min(B, 6)):
+        s, e = b.range(i)
+        o = oracle.evaluate(variant, b.bvs_host[s:e], b.bvs_target[s:e], None if ct is None else ct[s:e],
+                            None if ch is None else ch[s:e], 1e-13, b.init_poses[i], oracle.JAC_ANALYTIC)
+        assert ev.cost[i].item() == pytest.approx(o.cost, rel=EVAL_RTOL)
+        np.testing.assert_allclose(ev.gradient[i].cpu().numpy(), o.gradient, rtol=0,
+                                   atol=EVAL_RTOL * np.abs(o.gradient).max())
+        np.testing.assert_allclose(ev.jtj[i].cpu().numpy(), o.jtj, rtol=0, atol=EVAL_RTOL * np.abs(o.jtj).max())
+
+
+def test_ragged_batch_with_edge_sizes(handle):
+    """Empty problems, single correspondences, odd offsets, sizes around tile and
+    resident-capacity boundaries, one problem larger than shared memory."""
+    counts = np.array([0, 1, 2, 3, 5, 0, 31, 32, 33, 63, 64, 65, 127, 128, 129, 255, 257, 511, 513,
+                       1000, 1023, 1887, 1889, 1890, 1891, 2500, 0, 77, 4100, 6])
+    B = len(counts)
+    b = syn.make_batch(B, 0, seed=77, counts=counts)
+    res = handle.solve_batch(dev(b.bvs_host), dev(b.bvs_target), dev(b.covs_target), None,
+                             dev(b.init_poses), api.default_opts(api.TARGET), offsets=b.offsets)
+    ref, info = oracle_solve(api.TARGET, b.bvs_host, b.bvs_target, b.covs_target, None, b.init_poses,
+                             offsets=b.offsets)
+    poses = res.poses.cpu().numpy()
+    status = res.status.cpu().numpy()
+    iters = res.iterations.cpu().numpy()
+    cost = res.cost.cpu().numpy()
+    assert (status[counts == 0] == 7).all() and (iters[counts == 0] == 0).all()
+    # fewer than 5 correspondences leave the 5-DoF problem rank deficient: the LM path is then
+    # decided by rounding noise, so only well-posed problems are compared step for step
+    well = counts >= 10
+    assert np.array_equal(status[well], info["status"][well])
+    assert np.array_equal(iters[well], info["iterations"][well])
+    r, t = max_pose_diff(poses[well], ref[well])
+    assert r <= ROT_TOL and t <= DIR_TOL, (r, t)
+    np.testing.assert_allclose(cost[well], info["final_cost"][well], rtol=1e-9)
+    ill = (counts > 0) & ~well
+    assert np.isfinite(poses[ill]).all() and (status[ill] <= 5).all()
+    assert (cost[ill] <= res.initial_cost.cpu().numpy()[ill]).all()
+    # empty problems return the start pose (normalised)
+    for i in np.nonzero(counts == 0)[0]:
+        assert rotation_angle(poses[i], b.init_poses[i]) < 1e-12
+        assert direction_angle(poses[i][4:], b.init_poses[i][4:], False) < 1e-7
+    ev = handle.eval_batch(dev(b.bvs_host), dev(b.bvs_target), dev(b.covs_target), None,
+                           dev(b.init_poses), api.TARGET, 1e-13, offsets=b.offsets)
+    cost = ev.cost.cpu().numpy()
+    np.testing.assert_allclose(cost[counts > 0], info["initial_cost"][counts > 0], rtol=1e-11)
+    assert (cost[counts == 0] == 0).all() and (ev.jtj.cpu().numpy()[counts == 0] == 0).all()
+
+
+def test_host_and_device_memspace_agree_bitwise(handle):
+    b = syn.make_batch(20, 96, seed=5)
+    o = api.default_opts(api.TARGET)
+    host = handle.solve_batch(b.bvs_host, b.bvs_target, b.covs_target, None, b.init_poses, o, n_per_problem=96)
+    devr = handle.solve_batch(dev(b.bvs_host), dev(b.bvs_target), dev(b.covs_target), None,
+                              dev(b.init_poses), o, n_per_problem=96)
+    assert np.array_equal(host.poses, devr.poses.cpu().numpy())
+    assert np.array_equal(host.iterations, devr.iterations.cpu().numpy())
+    again = handle.solve_batch(b.bvs_host, b.bvs_target, b.covs_target, None, b.init_poses, o, n_per_problem=96)
+    assert np.array_equal(host.poses, again.poses), "solve is not deterministic"
+
+
+def test_unaligned_device_pointers_take_the_plain_copy_path(handle):
+    """Base pointers that are 8- but not 16-byte aligned cannot use cp.async.bulk."""
+    import torch
+
+    b = syn.make_batch(6, 70, seed=6)
+
+    def shifted(a):
+        flat = torch.empty(a.size + 1, dtype=torch.float64, device="cuda")
+        view = flat[1:].view(a.shape)
+        view.copy_(torch.from_numpy(a))
+        assert view.data_ptr() % 16 == 8
+        return view
+
+    res = handle.solve_batch(shifted(b.bvs_host), shifted(b.bvs_target), shifted(b.covs_target), None,
+                             dev(b.init_poses), api.default_opts(api.TARGET), n_per_problem=70)
+    ref = handle.solve_batch(dev(b.bvs_host), dev(b.bvs_target), dev(b.covs_target), None,
+                             dev(b.init_poses), api.default_opts(api.TARGET), n_per_problem=70)
+    assert np.array_equal(res.poses.cpu().numpy(), ref.poses.cpu().numpy())
+    ev = handle.eval_batch(shifted(b.bvs_host), shifted(b.bvs_target), shifted(b.covs_target), None,
+                           dev(b.init_poses), api.TARGET, 1e-13, n_per_problem=70)
+    ev2 = handle.eval_batch(dev(b.bvs_host), dev(b.bvs_target), dev(b.covs_target), None,
+                            dev(b.init_poses), api.TARGET, 1e-13, n_per_problem=70)
+    np.testing.assert_allclose(ev.jtj.cpu().numpy(), ev2.jtj.cpu().numpy(), rtol=1e-13)
+
+
+def test_solver_options_are_honoured(handle):
+    b = syn.make_batch(16, 80, seed=8)
+    for kw in (dict(max_num_iterations=1), dict(function_tolerance=1e-12, max_num_iterations=8),
+               dict(initial_trust_region_radius=1e-2), dict(jacobi_scaling=0)):
+        res = handle.solve_batch(b.bvs_host, b.bvs_target, b.covs_target, None, b.init_poses,
+                                 api.default_opts(api.TARGET, **kw), n_per_problem=80)
+        ref, info = oracle.solve_batch(b.bvs_host, b.bvs_target, b.covs_target, None, b.init_poses,
+                                       oracle.default_opts(oracle.TARGET, **kw), n_per_problem=80)
+        r, t = max_pose_diff(res.poses, ref)
+        assert r <= ROT_TOL and t <= DIR_TOL, (kw, r, t)
+        assert np.array_equal(res.iterations, info["iterations"]), kw
+        assert np.array_equal(res.status, info["status"]), kw
+
+
+def test_argument_errors(handle):
+    b = syn.make_batch(2, 10, seed=1)
+    with pytest.raises(api.PnecError, match="covs_target"):
+        handle.solve_batch(b.bvs_host, b.bvs_target, None, None, b.init_poses, api.default_opts(api.TARGET),
+                           n_per_problem=10)
+    with pytest.raises(api.PnecError, match="covs_host"):
+        handle.solve_batch(b.bvs_host, b.bvs_target, b.covs_target, None, b.init_poses,
+                           api.default_opts(api.SYMMETRIC), n_per_problem=10)
+    with pytest.raises(api.PnecError, match="variant"):
+        handle.solve_batch(b.bvs_host, b.bvs_target, b.covs_target, None, b.init_poses,
+                           api.default_opts(9), n_per_problem=10)
+    with pytest.raises(api.PnecError, match="non-decreasing"):
+        handle.solve_batch(b.bvs_host, b.bvs_target, b.covs_target, None, b.init_poses,
+                           api.default_opts(api.TARGET), offsets=np.array([0, 12, 8]))
+
+
+def test_cost_function_metric(handle):
+    b = syn.make_batch(5, 60, seed=12)
+    got = handle.cost_function_batch(b.bvs_host, b.bvs_target, b.covs_target, b.gt_poses, n_per_problem=60)
+    for i in range(5):
+        f1, f2, ct, _ = b.problem(i)
+        assert got[i] == pytest.approx(oracle.cost_function(f1, f2, ct, b.gt_poses[i]), rel=1e-11)
+
+
+# -------------------------------------- BASELINE full size: structural properties
+
+
+@pytest.fixture(scope="module")
+def c2_batch():
+    """BASELINE config C2: 10 000 frame pairs x 512 correspondences, anisotropic."""
+    return syn.make_batch(10000, 512, seed=2024, noise_type="anisotropic_inhomogenous")
+
+
+def test_c2_full_size_properties(handle, c2_batch):
+    b = c2_batch
+    B, N = 10000, 512
+    f1, f2, ct, init = dev(b.bvs_host), dev(b.bvs_target), dev(b.covs_target), dev(b.init_poses)
+    o = api.default_opts(api.TARGET)
+    res = handle.solve_batch(f1, f2, ct, None, init, o, n_per_problem=N)
+    poses, status = res.poses.cpu().numpy(), res.status.cpu().numpy()
+    cost, cost0 = res.cost.cpu().numpy(), res.initial_cost.cpu().numpy()
+    # 1. every problem terminates, the cost never increases, output is a unit pose
+    assert (status <= 4).all() and (status <= 3).mean() > 0.999
+    assert (cost <= cost0 * (1 + 1e-12)).all()
+    np.testing.assert_allclose(np.linalg.norm(poses[:, :4], axis=1), 1.0, atol=1e-14)
+    np.testing.assert_allclose(np.linalg.norm(poses[:, 4:], axis=1), 1.0, atol=1e-14)
+    # 2. the returned cost is the cost of the returned pose (fused eval == solve bookkeeping)
+    ev = handle.eval_batch(f1, f2, ct, None, res.poses, api.TARGET, 1e-13, n_per_problem=N)
+    np.testing.assert_allclose(ev.cost.cpu().numpy(), cost, rtol=1e-9)
+    # 3. idempotence: restarting from the solution (almost always) returns it unchanged,
+    #    and never moves further than the early-stopping slack of function_tolerance
+    again = handle.solve_batch(f1, f2, ct, None, res.poses, o, n_per_problem=N)
+    p2 = again.poses.cpu().numpy()
+    rot = np.array([rotation_angle(a, c) for a, c in zip(p2, poses)])
+    tra = np.array([direction_angle(a[4:], c[4:]) for a, c in zip(p2, poses)])
+    assert np.percentile(rot, 90) < 1e-9 and rot.max() < 1e-4 and tra.max() < 1e-3
+    assert (again.cost.cpu().numpy() <= cost * (1 + 1e-12)).all()
+    # 4. gauge: the energy is even in t, the t-columns of the gradient are odd
+    import torch
+
+    flipped = res.poses.clone()
+    flipped[:, 4:] *= -1
+    evf = handle.eval_batch(f1, f2, ct, None, flipped, api.TARGET, 1e-13, n_per_problem=N)
+    np.testing.assert_allclose(evf.cost.cpu().numpy(), ev.cost.cpu().numpy(), rtol=1e-12)
+    np.testing.assert_allclose(evf.jtj.cpu().numpy()[:, 9:], ev.jtj.cpu().numpy()[:, 9:], rtol=1e-9, atol=1e-6)
+    # 5. additivity: JtJ of a problem == sum of JtJ over its two halves (same pose)
+    half = handle.eval_batch(f1, f2, ct, None, res.poses.repeat_interleave(2, dim=0), api.TARGET, 1e-13,
+                             n_per_problem=N // 2)
+    np.testing.assert_allclose(half.jtj.cpu().numpy().reshape(B, 2, 15).sum(1), ev.jtj.cpu().numpy(),
+                               rtol=1e-11, atol=1e-9)
+    np.testing.assert_allclose(half.cost.cpu().numpy().reshape(B, 2).sum(1), ev.cost.cpu().numpy(), rtol=1e-12)
+    # 6. accuracy: the refinement lands near the ground truth (statistical sanity)
+    gt = b.gt_poses
+    dq = np.abs(np.sum(poses[:, :4] * gt[:, :4], axis=1))
+    assert np.median(2 * np.arccos(np.clip(dq, -1, 1))) < 5e-4
+
+
+def test_c2_subsample_matches_oracle(handle, c2_batch):
+    b = c2_batch
+    N, K = 512, 256
+    sl = slice(0, K * N)
+    res = handle.solve_batch(dev(b.bvs_host[sl]), dev(b.bvs_target[sl]), dev(b.covs_target[sl]), None,
+                             dev(b.init_poses[:K]), api.default_opts(api.TARGET), n_per_problem=N)
+    ref, info = oracle_solve(api.TARGET, b.bvs_host[sl], b.bvs_target[sl], b.covs_target[sl], None,
+                             b.init_poses[:K], n_per_problem=N)
+    r, t = max_pose_diff(res.poses.cpu().numpy(), ref)
+    assert r <= ROT_TOL and t <= DIR_TOL, (r, t)
+    assert np.array_equal(res.iterations.cpu().numpy(), info["iterations"])
+
+
+# ------------------------------------------- reference-shaped host interfaces
+
+
+def test_pypnec_module_matches_oracle():
+    """pypnec.pyceres / pyceresnec with the reference's signatures (python/pypnec.cpp:50-82)."""
+    from pnec_b200 import pypnec
+
+    N = 90
+    b = syn.with_host_covariances(syn.make_batch(1, N, seed=31))
+    f1 = [v for v in b.bvs_host]
+    f2 = [v for v in b.bvs_target]
+    cov_h = [c.reshape(3, 3).T.copy() for c in b.covs_host]
+    cov_t = [c.reshape(3, 3).T.copy() for c in b.covs_target]
+    init = np.eye(4)
+    init[:3, :3] = syn.quaternion_to_matrix(b.init_poses[0][:4])
+    init[:3, 3] = b.init_poses[0][4:]
+    out = pypnec.pyceres(f1, f2, cov_h, cov_t, init, 1e-13)
+    assert out.shape == (4, 4) and np.allclose(out[3], [0, 0, 0, 1])
+    ref, _ = oracle.solve(b.bvs_host, b.bvs_target, b.covs_target, b.covs_host, b.init_poses[0],
+                          oracle.default_opts(oracle.SYMMETRIC))
+    got = np.concatenate([syn.matrix_to_quaternion(out[:3, :3]), out[:3, 3]])
+    assert rotation_angle(got, ref) <= ROT_TOL and direction_angle(got[4:], ref[4:]) <= DIR_TOL
+    assert np.linalg.norm(out[:3, 3]) == pytest.approx(1.0, abs=1e-14)
+    out_nec = pypnec.pyceresnec(np.asarray(f1), np.asarray(f2), init)
+    refn, _ = oracle.solve(b.bvs_host, b.bvs_target, None, None, b.init_poses[0], oracle.default_opts(oracle.NEC))
+    gotn = np.concatenate([syn.matrix_to_quaternion(out_nec[:3, :3]), out_nec[:3, 3]])
+    assert rotation_angle(gotn, refn) <= ROT_TOL and direction_angle(gotn[4:], refn[4:]) <= DIR_TOL
+    # batched extension
+    outs = pypnec.pyceres_target_batch(b.bvs_host.reshape(1, N, 3), b.bvs_target.reshape(1, N, 3),
+                                       np.asarray(cov_t).reshape(1, N, 3, 3), init[None], 1e-13)
+    reft, _ = oracle.solve(b.bvs_host, b.bvs_target, b.covs_target, None, b.init_poses[0],
+                           oracle.default_opts(oracle.TARGET))
+    gott = np.concatenate([syn.matrix_to_quaternion(outs[0, :3, :3]), outs[0, :3, 3]])
+    assert rotation_angle(gott, reft) <= ROT_TOL and direction_angle(gott[4:], reft[4:]) <= DIR_TOL
+    with pytest.raises(ValueError):
+        pypnec.pyceresnec(f1, f2[:-1], init)
+
+
+def test_cpp_compat_api_matches_oracle(tmp_path):
+    """The reference's C++ call shapes (PNEC::CeresSolver & co) through pnec_compat.hpp."""
+    exe = tmp_path / "compat_test"
+    lib = os.path.join(ROOT, "pnec_b200", "lib")
+    subprocess.run(["/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++", "-std=c++17", "-O1",
+                    "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "compat_test.cpp"),
+                    "-o", str(exe), "-L", lib, "-lpnec_b200", f"-Wl,-rpath,{lib}"], check=True)
+    N = 120
+    b = syn.with_host_covariances(syn.make_batch(1, N, seed=41))
+    blob = tmp_path / "in.bin"
+    with open(blob, "wb") as f:
+        f.write(np.int64(N).tobytes())
+        for a in (b.bvs_host, b.bvs_target, b.covs_target, b.covs_host, b.init_poses[0]):
+            f.write(np.ascontiguousarray(a, dtype=np.float64).tobytes())
+    out = subprocess.run([str(exe), str(blob)], check=True, capture_output=True, text=True).stdout
+    lines = {l.split()[0]: l.split()[1:] for l in out.strip().splitlines()}
+    init = b.init_poses[0]
+
+    def check(tag, variant, reg, ct, ch):
+        pose = np.array(lines[tag][:7], dtype=np.float64)
+        ref, info = oracle.solve(b.bvs_host, b.bvs_target, ct, ch, init, oracle.default_opts(variant, reg))
+        assert rotation_angle(pose, ref) <= ROT_TOL and direction_angle(pose[4:], ref[4:]) <= DIR_TOL, tag
+        assert int(lines[tag][7]) == info.status and int(lines[tag][8]) == info.iterations, tag
+        return pose
+
+    p = check("CeresSolver", oracle.TARGET, 1e-13, b.covs_target, None)
+    check("CeresSolverFull", oracle.TARGET, 1e-10, b.covs_target, None)
+    check("NECCeresSolver", oracle.NEC, 0.0, None, None)
+    check("Solve", oracle.TARGET, 1e-13, b.covs_target, None)
+    check("PNECCeresHost", oracle.HOST, 1e-13, b.covs_target, None)
+    check("PNECCeresSymmetric", oracle.SYMMETRIC, 1e-13, b.covs_target, b.covs_host)
+    assert float(lines["CostFunction"][0]) == pytest.approx(
+        oracle.cost_function(b.bvs_host, b.bvs_target, b.covs_target, p), rel=1e-10)
+    assert lines["SolveDefaultOptions"] == ["throws"]
