@@ -83,6 +83,14 @@ def ncu_traffic_bytes():
 # ------------------------------------------------------------------ CPU arms
 
 
+def host_threads():
+    """All host cores this process may use (torchrun pins OMP_NUM_THREADS=1: ignore that)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_oracle_rate(batch, n_problems, threads):
     """solves/s of the oracle (numeric-diff Jacobian + Ceres-style LM) on n_problems of batch."""
     import oracle
@@ -103,7 +111,7 @@ def run_reference(args):
     import oracle
 
     oracle.build()
-    threads = oracle.max_threads()
+    threads = host_threads()
     sample = min(args.problems, 2048)
     batch = make_workload(sample, args.corr, seed=1)
     for _ in range(max(args.warmup, 1)):
@@ -325,7 +333,7 @@ def run_b200(args):
     if world == 1:
         import oracle
 
-        threads = oracle.max_threads()
+        threads = host_threads()
         sample = min(B, 8192)
         rate_all = cpu_oracle_rate(batch, sample, threads)
         rate_one = cpu_oracle_rate(batch, min(B, 512), 1)
