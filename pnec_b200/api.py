@@ -13,7 +13,7 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpnec_b200.so")
+LIB_PATH = os.environ.get("PNEC_B200_LIB") or os.path.join(_HERE, "lib", "libpnec_b200.so")
 
 NEC, TARGET, HOST, SYMMETRIC = 0, 1, 2, 3
 VARIANT_NAMES = {"nec": NEC, "target": TARGET, "host": HOST, "symmetric": SYMMETRIC}

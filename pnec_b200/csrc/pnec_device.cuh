@@ -198,6 +198,37 @@ __device__ __forceinline__ void residual_row(const PoseConst &pc, double reg, co
   row[4] = drdw[2];
 }
 
+// Residual only (cost passes of the LM loop): same expressions as residual_row.
+template <int V>
+__device__ __forceinline__ double residual_only(const PoseConst &pc, double reg, const double f1[3],
+                                                const double f2[3], const double ct[9],
+                                                const double ch[9]) {
+  double g[3], a[3];
+  rot(pc.R, f2, g);
+  cross3(pc.t, f1, a);
+  const double e = dot3(a, g);
+  if (V == PNEC_VARIANT_NEC) return e;
+  double s2 = reg;
+  if (V == PNEC_VARIANT_TARGET || V == PNEC_VARIANT_SYMMETRIC) {
+    double b[3], Sb[3];
+    rot_t(pc.R, a, b);
+    sym_mul(ct, b, Sb);
+    s2 = dot3(b, Sb) + reg;
+  }
+  if (V == PNEC_VARIANT_HOST || V == PNEC_VARIANT_SYMMETRIC) {
+    double h[3], c[3], Sc[3];
+    if (V == PNEC_VARIANT_HOST) {
+      rot(pc.R, f1, h);
+    } else {
+      h[0] = g[0]; h[1] = g[1]; h[2] = g[2];
+    }
+    cross3(pc.t, h, c);
+    sym_mul(V == PNEC_VARIANT_HOST ? ct : ch, c, Sc);
+    s2 += dot3(c, Sc);
+  }
+  return e * rsqrt(s2);
+}
+
 // acc += (J^T J upper, J^T r, r^2)
 __device__ __forceinline__ void accumulate(double acc[kNumAcc], double r, const double row[5]) {
   int k = 0;
@@ -278,17 +309,23 @@ __device__ __forceinline__ double warp_transpose_reduce(const double acc[kNumAcc
 // Cholesky (no square roots), small-angle polynomials + angle addition instead of
 // sin/cos calls.  All of it stays within a few ulp of the IEEE forms.
 struct LMState {
-  double x[6];      // accepted point (theta, phi, qx, qy, qz, qw)
-  double cand[6];   // candidate point being evaluated
-  double sc[4];     // sin/cos of theta, phi at x:    s_th, c_th, s_ph, c_ph
-  double scc[4];    // same at the candidate
-  double H[15];     // J^T J at x (unscaled, packed upper)
-  double g[5];      // J^T r at x
-  double scale[5];  // Jacobi column scaling, fixed at iteration 0
-  double diag[5];   // LM diagonal of the scaled Jacobian (reused on rejection)
-  double x_cost, x_norm, radius, decrease_factor, model_cost_change, initial_cost;
+  // Points and totals are double-buffered so that accepting a step flips an index
+  // instead of copying: pts[xi] is the accepted point x, pts[xi ^ 1] the candidate;
+  // tot[ti] holds (J^T J, J^T r, cost) at x, tot[ti ^ 1] receives the next evaluation.
+  double pts[2][6];  // (theta, phi, qx, qy, qz, qw)
+  double scs[2][4];  // sin/cos of theta, phi of the same points: s_th, c_th, s_ph, c_ph
+  double tot[2][kAccPad];
+  double scale[5];   // Jacobi column scaling, fixed at iteration 0
+  double inv_scale2[5];  // 1 / scale^2
+  double diag[5];    // LM diagonal of the scaled Jacobian (reused on rejection)
+  double x_cost, inv_radius, decrease_factor, inv_model_cost_change, initial_cost;
+  int xi, ti;
   int iteration, num_invalid, reuse_diagonal, step_successful, grad_converged, status, done;
+  int pass_mode;     // what the CTA evaluates next: kPassFull or kPassCost
 };
+
+constexpr int kPassFull = 0;  // residual + Jacobian + JtJ/Jtr at the candidate
+constexpr int kPassCost = 1;  // cost only (the step is predicted to hit function_tolerance)
 
 __host__ __device__ constexpr int tri(int a, int b) {  // a <= b
   return a * 5 - (a * (a - 1)) / 2 + (b - a);
@@ -300,11 +337,10 @@ __device__ __forceinline__ double fast_rcp(double x) {
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
   double e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
+  e = fma(e, e, e);        // e + e^2
+  y = fma(y, e, y);        // y (1 + e + e^2): relative error eps^3
   e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
-  e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
+  y = fma(y, e, y);        // eps^6
   return y;
 }
 // sqrt(x) for x >= 0 through rsqrt (no slow-path branch)
@@ -445,140 +481,219 @@ __device__ __forceinline__ bool ldlt_solve5(const double A[5][5], const double b
   return ok;
 }
 
-// FinalizeIterationAndCheckIfMinimizerCanContinue + ComputeTrustRegionStep.
-// Loops over invalid steps (they need no new evaluation).  On return either
-// st.done is set, or st.cand / st.scc hold the next point to evaluate.
-__device__ __forceinline__ void lm_propose(LMState &st, const pnec_solver_opts &o) {
-  for (;;) {
-    if (st.iteration >= o.max_num_iterations) {
-      st.status = PNEC_STATUS_MAX_ITERATIONS; st.done = 1; return;
+// One trust-region solve attempt at the accepted point.  Ceres solves, in Jacobi-scaled
+// coordinates, (S H S + D) y = S g with D = diag / radius and takes delta = -S y.  With
+// d = S y this is (H + S^-1 D S^-1) d = g: the same system without the 45 scaling products,
+// and model_cost_change = (y.Sg + y^T D y) / 2 = sum d_a (g_a + L_a d_a) / 2, L = D / s^2.
+// Returns false for an invalid step (LINEAR_SOLVER_FAILURE or model_cost_change <= 0).
+__device__ __forceinline__ bool lm_trust_region_step(const double *Hg, const double scale[5],
+                                                     const double inv_scale2[5], double diag[5],
+                                                     bool reuse_diagonal, double inv_radius,
+                                                     const pnec_solver_opts &o, double delta[5],
+                                                     double &mcc) {
+  double A[5][5], lam[5], d[5];
+#pragma unroll
+  for (int a = 0; a < 5; ++a) {
+#pragma unroll
+    for (int b = a; b < 5; ++b) {
+      A[a][b] = Hg[tri(a, b)];
+      A[b][a] = A[a][b];
     }
-    if (st.step_successful && st.grad_converged) {
-      st.status = PNEC_STATUS_CONVERGED_GRADIENT; st.done = 1; return;
-    }
-    if (st.radius <= o.min_trust_region_radius) {
-      st.status = PNEC_STATUS_CONVERGED_RADIUS; st.done = 1; return;
-    }
-    st.iteration++;
-
-    double A[5][5], rhs[5], y[5];
-#pragma unroll
-    for (int a = 0; a < 5; ++a) {
-      rhs[a] = st.g[a] * st.scale[a];
-#pragma unroll
-      for (int b = a; b < 5; ++b) {
-        A[a][b] = st.H[tri(a, b)] * st.scale[a] * st.scale[b];
-        A[b][a] = A[a][b];
-      }
-    }
-    if (!st.reuse_diagonal) {
-#pragma unroll
-      for (int a = 0; a < 5; ++a)
-        st.diag[a] = fmin(fmax(A[a][a], o.min_lm_diagonal), o.max_lm_diagonal);
-    }
-    const double inv_radius = fast_rcp(st.radius);
-    double D[5];
-#pragma unroll
-    for (int a = 0; a < 5; ++a) {
-      D[a] = st.diag[a] * inv_radius;
-      A[a][a] += D[a];
-    }
-    bool valid = ldlt_solve5(A, rhs, y);
-    st.reuse_diagonal = 1;
-    // step = -y.  model_cost_change = -(J s)^T (f + J s / 2) = y.rhs - y^T M y / 2 with
-    // M = A - D and A y = rhs, i.e. (y.rhs + y^T D y) / 2.
-    double mcc = 0.0;
-#pragma unroll
-    for (int a = 0; a < 5; ++a) mcc = fma(y[a], fma(D[a], y[a], rhs[a]), mcc);
-    mcc *= 0.5;
-    valid = valid && (mcc > 0.0);
-    if (!valid) {
-      if (++st.num_invalid >= o.max_num_consecutive_invalid_steps) {
-        st.status = PNEC_STATUS_FAILURE; st.done = 1; return;
-      }
-      st.radius *= 0.5;
-      st.step_successful = 0;
-      continue;
-    }
-    st.num_invalid = 0;
-    st.model_cost_change = mcc;
-    double delta[5];
-#pragma unroll
-    for (int a = 0; a < 5; ++a) delta[a] = -y[a] * st.scale[a];
-    st.cand[0] = st.x[0] + delta[0];
-    st.cand[1] = st.x[1] + delta[1];
-    advance_sincos(st.cand[0], delta[0], st.sc[0], st.sc[1], st.scc[0], st.scc[1]);
-    advance_sincos(st.cand[1], delta[1], st.sc[2], st.sc[3], st.scc[2], st.scc[3]);
-    quat_plus_fast(st.x + 2, delta + 2, st.cand + 2);
-    return;
-  }
-}
-
-// IterationZero: totals = (H, g, cost) at the start point.
-__device__ __forceinline__ void lm_begin(LMState &st, const double tot[kNumAcc],
-                                         const pnec_solver_opts &o) {
-#pragma unroll
-  for (int i = 0; i < 15; ++i) st.H[i] = tot[i];
-#pragma unroll
-  for (int i = 0; i < 5; ++i) st.g[i] = tot[15 + i];
-  st.x_cost = tot[20];
-  st.initial_cost = tot[20];
-  if (!(fabs(st.x_cost) < CUDART_INF)) {
-    st.status = PNEC_STATUS_NONFINITE; st.done = 1; return;
   }
 #pragma unroll
-  for (int a = 0; a < 5; ++a)
-    st.scale[a] = o.jacobi_scaling ? fast_rcp(1.0 + fast_sqrt(st.H[tri(a, a)])) : 1.0;
-  st.grad_converged = gradient_converged(st.x, st.g, o.gradient_tolerance) ? 1 : 0;
-  st.step_successful = 1;
+  for (int a = 0; a < 5; ++a) {
+    if (!reuse_diagonal)  // squared column norm of the scaled Jacobian, clamped
+      diag[a] = fmin(fmax(A[a][a] * scale[a] * scale[a], o.min_lm_diagonal), o.max_lm_diagonal);
+    lam[a] = diag[a] * inv_radius * inv_scale2[a];
+    A[a][a] += lam[a];
+  }
+  bool valid = ldlt_solve5(A, Hg + 15, d);
+  mcc = 0.0;
+#pragma unroll
+  for (int a = 0; a < 5; ++a) mcc = fma(d[a], fma(lam[a], d[a], Hg[15 + a]), mcc);
+  mcc *= 0.5;
+#pragma unroll
+  for (int a = 0; a < 5; ++a) delta[a] = -d[a];
+  return valid && (mcc > 0.0);
 }
 
-// Everything after ComputeCandidatePointAndEvaluateCost: the two convergence
-// tests (made BEFORE acceptance, as Ceres does), then accept / reject.
-__device__ __forceinline__ void lm_judge(LMState &st, const double tot[kNumAcc],
-                                         const pnec_solver_opts &o) {
-  double cand_cost = tot[20];
+// The whole LM update between two evaluations, straight-line:
+//   (FIRST)  IterationZero bookkeeping,
+//   (!FIRST) FunctionToleranceReached, IsStepSuccessful, StepAccepted / StepRejected,
+//   then FinalizeIterationAndCheckIfMinimizerCanContinue, ComputeTrustRegionStep (invalid
+//   steps retried in place: they need no evaluation), candidate = Plus(x, delta),
+//   ParameterToleranceReached, choice of the next pass, pose constants of the candidate.
+// `st` is the shared-memory state; every lane of the calling warp executes this with
+// identical values, lane 0 stores.  New totals are in st.tot[st.ti ^ 1].
+#ifdef PNEC_PHASE_TIMING
+__device__ unsigned long long g_lm_probe[8];
+#define LM_PROBE(k) do { const long long t_now = clock64(); if (lane == 0) atomicAdd(&g_lm_probe[k], (unsigned long long)(t_now - t_prev)); t_prev = t_now; } while (0)
+#else
+#define LM_PROBE(k) do { } while (0)
+#endif
+
+template <bool FIRST>
+__device__ __forceinline__ void lm_step(LMState &st, const pnec_solver_opts &o, int lane,
+                                        PoseConst &s_pc) {
+#ifdef PNEC_PHASE_TIMING
+  long long t_prev = clock64();
+#endif
+  const int xi = st.xi, ti = st.ti;
+  const double *newtot = st.tot[ti ^ 1];
+  // The trust-region radius is carried as its inverse: every use is a division by it
+  // (D = diag / radius, radius /= factor), so the update chain needs no reciprocal.
+  double inv_radius = st.inv_radius, decrease_factor = st.decrease_factor, x_cost = st.x_cost;
+  int reuse_diagonal = st.reuse_diagonal;
+  bool accept = true;
+  double cand_cost = newtot[20];
   if (!(fabs(cand_cost) < CUDART_INF)) cand_cost = DBL_MAX;
-  double sn = 0.0;
-#pragma unroll
-  for (int i = 0; i < 6; ++i) sn = fma(st.x[i] - st.cand[i], st.x[i] - st.cand[i], sn);
-  const double ptol = o.parameter_tolerance * (st.x_norm + o.parameter_tolerance);
-  if (sn <= ptol * ptol) {  // step_norm <= tolerance, compared squared
-    st.status = PNEC_STATUS_CONVERGED_PARAMETER; st.done = 1; return;
+  if (FIRST) {
+    if (cand_cost >= DBL_MAX) {
+      if (lane == 0) { st.status = PNEC_STATUS_NONFINITE; st.done = 1; st.initial_cost = newtot[20]; st.x_cost = newtot[20]; }
+      return;
+    }
+    x_cost = cand_cost;
+  } else {
+    const double cost_change = x_cost - cand_cost;
+    if (fabs(cost_change) <= o.function_tolerance * x_cost) {  // before acceptance, like Ceres
+      if (lane == 0) { st.status = PNEC_STATUS_CONVERGED_FUNCTION; st.done = 1; }
+      return;
+    }
+    const double rho = (cand_cost >= DBL_MAX) ? -DBL_MAX : cost_change * st.inv_model_cost_change;
+    accept = rho > o.min_relative_decrease;
+    const double c = 2.0 * rho - 1.0;
+    // StepAccepted: radius /= max(1/3, 1 - (2 rho - 1)^3), capped; StepRejected: radius /= factor
+    inv_radius *= accept ? fmax(1.0 / 3.0, 1.0 - c * c * c) : decrease_factor;
+    if (accept) inv_radius = fmax(inv_radius, 1.0 / o.max_trust_region_radius);
+    decrease_factor = accept ? 2.0 : 2.0 * decrease_factor;
+    reuse_diagonal = accept ? 0 : 1;
+    x_cost = accept ? cand_cost : x_cost;
   }
-  const double cost_change = st.x_cost - cand_cost;
-  if (fabs(cost_change) <= o.function_tolerance * st.x_cost) {
-    st.status = PNEC_STATUS_CONVERGED_FUNCTION; st.done = 1; return;
-  }
-  const double rho =
-      (cand_cost >= DBL_MAX) ? -DBL_MAX : cost_change * fast_rcp(st.model_cost_change);
-  if (rho > o.min_relative_decrease) {
-    double xn = 0.0;
+  LM_PROBE(0);  // judge
+  const int nxi = accept ? (FIRST ? xi : xi ^ 1) : xi;  // index of the accepted point
+  const int nti = accept ? ti ^ 1 : ti;                 // index of its totals
+  const double *Hg = st.tot[nti];
+  const double *x = st.pts[nxi];
+  const double *sc = st.scs[nxi];
+
+  double scale[5], inv_scale2[5], diag[5];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      st.x[i] = st.cand[i];
-      xn = fma(st.x[i], st.x[i], xn);
+  for (int a = 0; a < 5; ++a) {
+    if (FIRST) {
+      const double one_plus = 1.0 + fast_sqrt(Hg[tri(a, a)]);  // scale = 1 / (1 + |J col|)
+      scale[a] = o.jacobi_scaling ? fast_rcp(one_plus) : 1.0;
+      inv_scale2[a] = o.jacobi_scaling ? one_plus * one_plus : 1.0;
+    } else {
+      scale[a] = st.scale[a];
+      inv_scale2[a] = st.inv_scale2[a];
+    }
+    diag[a] = FIRST ? 0.0 : st.diag[a];
+  }
+  // the gradient test of a newly accepted point (cheap unless |g| is already tiny)
+  int grad_conv = st.grad_converged;
+  if (accept) grad_conv = gradient_converged(x, Hg + 15, o.gradient_tolerance) ? 1 : 0;
+  LM_PROBE(1);  // scale, gradient test
+  int iteration = st.iteration, num_invalid = st.num_invalid, step_successful = accept ? 1 : 0;
+  int status = st.status, done = 0;
+  double delta[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, mcc = 0.0;
+  for (;;) {  // FinalizeIterationAndCheckIfMinimizerCanContinue
+    if (iteration >= o.max_num_iterations) { status = PNEC_STATUS_MAX_ITERATIONS; done = 1; break; }
+    if (step_successful && grad_conv) { status = PNEC_STATUS_CONVERGED_GRADIENT; done = 1; break; }
+    if (inv_radius * o.min_trust_region_radius >= 1.0) { status = PNEC_STATUS_CONVERGED_RADIUS; done = 1; break; }
+    ++iteration;
+    const bool valid = lm_trust_region_step(Hg, scale, inv_scale2, diag, reuse_diagonal != 0, inv_radius, o, delta, mcc);
+    reuse_diagonal = 1;
+    if (valid) { num_invalid = 0; break; }
+    if (++num_invalid >= o.max_num_consecutive_invalid_steps) { status = PNEC_STATUS_FAILURE; done = 1; break; }
+    inv_radius *= 2.0;  // StepIsInvalid: radius *= 0.5
+    step_successful = 0;
+  }
+
+  LM_PROBE(2);  // trust-region step
+  double cand[6], scc[4];
+  int pass_mode = kPassFull;
+  if (!done) {
+    cand[0] = x[0] + delta[0];
+    cand[1] = x[1] + delta[1];
+    advance_sincos(cand[0], delta[0], sc[0], sc[1], scc[0], scc[1]);
+    advance_sincos(cand[1], delta[1], sc[2], sc[3], scc[2], scc[3]);
+    quat_plus_fast(x + 2, delta + 2, cand + 2);
+    // ParameterToleranceReached depends on the step only.  Ceres evaluates the candidate's
+    // cost first and then returns without applying the step, so the evaluation cannot change
+    // the outcome: decide here and skip it.
+    double sn = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) sn = fma(x[i] - cand[i], x[i] - cand[i], sn);
+    // |x| <= |theta| + |phi| + |q| gives a cheap upper bound of the tolerance; the exact
+    // norm is only formed when the step is small enough for the test to possibly pass.
+    const double ptol_hi = o.parameter_tolerance * (fabs(x[0]) + fabs(x[1]) + 2.0 + o.parameter_tolerance);
+    if (sn <= ptol_hi * ptol_hi) {
+      double xn = 0.0;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) xn = fma(x[i], x[i], xn);
+      const double ptol = o.parameter_tolerance * (sqrt(xn) + o.parameter_tolerance);
+      if (sn <= ptol * ptol) {  // step_norm <= tolerance, compared squared
+        status = PNEC_STATUS_CONVERGED_PARAMETER;
+        done = 1;
+      }
+    }
+    // If the quadratic model already predicts |cost change| <= function_tolerance * cost the
+    // iteration will almost surely terminate there: evaluate the cost alone first.
+    pass_mode = (mcc <= 1.05 * o.function_tolerance * x_cost) ? kPassCost : kPassFull;
+  }
+  LM_PROBE(3);  // candidate
+  __syncwarp();  // every lane has read the state it needs; lane 0 may now overwrite it
+  if (lane == 0) {
+    if (!done) {
+      PoseConst pcn;
+      make_pose_const_sc(scc, cand + 2, pcn);
+      s_pc = pcn;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) st.pts[nxi ^ 1][i] = cand[i];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) st.scs[nxi ^ 1][i] = scc[i];
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) st.sc[i] = st.scc[i];
-    st.x_norm = fast_sqrt(xn);
-    st.x_cost = cand_cost;
-#pragma unroll
-    for (int i = 0; i < 15; ++i) st.H[i] = tot[i];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) st.g[i] = tot[15 + i];
-    st.grad_converged = gradient_converged(st.x, st.g, o.gradient_tolerance) ? 1 : 0;
-    st.step_successful = 1;
-    const double c = 2.0 * rho - 1.0;
-    st.radius = st.radius * fast_rcp(fmax(1.0 / 3.0, 1.0 - c * c * c));
-    st.radius = fmin(o.max_trust_region_radius, st.radius);
-    st.decrease_factor = 2.0;
-    st.reuse_diagonal = 0;
-  } else {
-    st.step_successful = 0;
-    st.radius = st.radius * fast_rcp(st.decrease_factor);
-    st.decrease_factor *= 2.0;
-    st.reuse_diagonal = 1;
+    for (int a = 0; a < 5; ++a) {
+      if (FIRST) {
+        st.scale[a] = scale[a];
+        st.inv_scale2[a] = inv_scale2[a];
+      }
+      st.diag[a] = diag[a];
+    }
+    st.xi = nxi;
+    st.ti = nti;
+    st.x_cost = x_cost;
+    if (FIRST) st.initial_cost = x_cost;
+    st.inv_radius = inv_radius;
+    st.decrease_factor = decrease_factor;
+    st.inv_model_cost_change = (mcc > 0.0) ? fast_rcp(mcc) : 0.0;  // off the critical path
+    st.iteration = iteration;
+    st.num_invalid = num_invalid;
+    st.reuse_diagonal = reuse_diagonal;
+    st.step_successful = step_successful;
+    st.grad_converged = grad_conv;
+    st.status = status;
+    st.done = done;
+    st.pass_mode = pass_mode;
+  }
+  LM_PROBE(4);  // pose constants + state store
+}
+
+// After a cost-only pass: FunctionToleranceReached, or fall through to a full pass at the
+// same candidate (nothing else is decided from a cost-only pass).
+__device__ __forceinline__ void lm_after_cost_pass(LMState &st, double cand_cost_in,
+                                                   const pnec_solver_opts &o, int lane) {
+  double cand_cost = cand_cost_in;
+  if (!(fabs(cand_cost) < CUDART_INF)) cand_cost = DBL_MAX;
+  const bool conv = fabs(st.x_cost - cand_cost) <= o.function_tolerance * st.x_cost;
+  if (lane == 0) {
+    if (conv) {
+      st.status = PNEC_STATUS_CONVERGED_FUNCTION;
+      st.done = 1;
+    } else {
+      st.pass_mode = kPassFull;
+    }
   }
 }
 

@@ -19,6 +19,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "pnec_device.cuh"
 
@@ -81,25 +82,55 @@ __device__ __forceinline__ void eval_pass(const PoseConst &pc, double reg, const
   }
 }
 
-// Block reduction of the 21 partial sums.  After it, in warp 0, tot[j] (all lanes)
-// holds the scaled block total of value j.  Contains one __syncthreads().
+template <int V, int NT>
+__device__ __forceinline__ double eval_pass_cost(const PoseConst &pc, double reg, const double *f1,
+                                                 const double *f2, const double *ct,
+                                                 const double *ch, int begin, int end, int tid) {
+  double sum = 0.0;
+  for (int i = begin + tid; i < end; i += NT) {
+    double a1[3], a2[3], c1[9], c2[9];
+    load_corr<V>(f1, f2, ct, ch, i, a1, a2, c1, c2);
+    const double r = residual_only<V>(pc, reg, a1, a2, c1, c2);
+    sum = fma(r, r, sum);
+  }
+  return sum;
+}
+
+// Block reduction of one value (cost passes); result valid in warp 0.  One __syncthreads().
+template <int NW>
+__device__ __forceinline__ double block_reduce_scalar(double v, double (*s_part)[kAccPad], int warp,
+                                                      int lane, int owner = 0) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) s_part[warp][kNumAcc - 1] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (warp == owner) {
+#pragma unroll
+    for (int w = 0; w < NW; ++w) t += s_part[w][kNumAcc - 1];
+    t *= 0.5;
+  }
+  return t;
+}
+
+// Block reduction of the 21 partial sums into dst[0..20] (shared memory), scaled; valid for
+// warp 0 after the call (other warps must pass a barrier first).  One __syncthreads().
 template <int NW>
 __device__ __forceinline__ void block_reduce(const double acc[kNumAcc],
                                              double (*s_part)[kAccPad], int warp, int lane,
-                                             double tot[kNumAcc]) {
+                                             double *dst, int owner = 0) {
   const double v = warp_transpose_reduce(acc, lane);
   const int idx = warp_reduce_owner_index(lane);
   if (idx >= 0 && idx < kNumAcc) s_part[warp][idx] = v;
   __syncthreads();
-  if (warp == 0) {
-    double mine = 0.0;
+  if (warp == owner) {
     if (lane < kNumAcc) {
+      double mine = 0.0;
 #pragma unroll
       for (int w = 0; w < NW; ++w) mine += s_part[w][lane];
-      mine *= acc_scale(lane);
+      dst[lane] = mine * acc_scale(lane);
     }
-#pragma unroll
-    for (int j = 0; j < kNumAcc; ++j) tot[j] = __shfl_sync(0xffffffffu, mine, j);
+    __syncwarp();
   }
 }
 
@@ -177,6 +208,7 @@ struct SolveArgs {
   double *out_init_cost;
   int cap_elems;  // resident capacity of the dynamic smem, in correspondences (even)
   int use_bulk;   // all base pointers 16-byte aligned
+  long long *dbg; // PNEC_PHASE_TIMING builds only: per-CTA cycle counters
 };
 
 extern __shared__ __align__(16) double dyn_smem[];
@@ -199,13 +231,18 @@ __global__ void __launch_bounds__(NW * 32, MINB) solve_kernel(const __grid_const
   const int span = n + head;
   const bool resident = (span + (span & 1)) <= args.cap_elems;
   const pnec_solver_opts &o = args.o;
+  // The warp that runs the serial part (set-up, LM update).  Warp w of every CTA sits on SM
+  // sub-partition w % 4, so a fixed choice would pile the serial fp64 work of all co-resident
+  // problems onto one sub-partition; rotate it per CTA instead.
+  const int lmw = (NW == 1) ? 0 : static_cast<int>((blockIdx.x + blockIdx.x / 148u) % NW);
+  const int lmt = lmw * 32;  // its lane 0
 
   double *sf1 = dyn_smem;
   double *sf2 = sf1 + 3 * args.cap_elems;
   double *sct = sf2 + 3 * args.cap_elems;
   double *sch = sct + (VariantTraits<V>::kHasCt ? 9 * args.cap_elems : 0);
 
-  if (tid == 0) {
+  if (tid == lmt) {
     mbar_init(&s_bar, 1);
     fence_mbar_init();
     // get the HBM -> shared-memory copies going before the scalar set-up below
@@ -214,24 +251,18 @@ __global__ void __launch_bounds__(NW * 32, MINB) solve_kernel(const __grid_const
     // PNECCeres::InitValues(orientation, translation), pnec_ceres.cc:188-192
     const double *p = args.bv.poses + 7 * b;
     LMState &st = s_lm;
-    angles_from_vec(p + 4, st.x[0], st.x[1]);
-    st.x[2] = p[0]; st.x[3] = p[1]; st.x[4] = p[2]; st.x[5] = p[3];
-    sincos(st.x[0], &st.sc[0], &st.sc[1]);
-    sincos(st.x[1], &st.sc[2], &st.sc[3]);
-    double xn = 0.0;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      st.cand[i] = st.x[i];
-      xn += st.x[i] * st.x[i];
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) st.scc[i] = st.sc[i];
-    st.x_norm = sqrt(xn);
-    st.radius = o.initial_trust_region_radius;
+    double *x = st.pts[0], *sc = st.scs[0];
+    angles_from_vec(p + 4, x[0], x[1]);
+    x[2] = p[0]; x[3] = p[1]; x[4] = p[2]; x[5] = p[3];
+    sincos(x[0], &sc[0], &sc[1]);
+    sincos(x[1], &sc[2], &sc[3]);
+    st.inv_radius = 1.0 / o.initial_trust_region_radius;
     st.decrease_factor = 2.0;
-    st.model_cost_change = 0.0;
+    st.inv_model_cost_change = 0.0;
     st.x_cost = 0.0;
     st.initial_cost = 0.0;
+    st.xi = 0;
+    st.ti = 0;
     st.iteration = 0;
     st.num_invalid = 0;
     st.reuse_diagonal = 0;
@@ -239,8 +270,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) solve_kernel(const __grid_const
     st.grad_converged = 0;
     st.status = (n <= 0) ? PNEC_STATUS_EMPTY : PNEC_STATUS_MAX_ITERATIONS;
     st.done = (n <= 0) ? 1 : 0;
+    st.pass_mode = kPassFull;
     PoseConst pc0;
-    make_pose_const_sc(st.sc, st.x + 2, pc0);
+    make_pose_const_sc(sc, x + 2, pc0);
     s_pc = pc0;
   }
   __syncthreads();
@@ -254,51 +286,77 @@ __global__ void __launch_bounds__(NW * 32, MINB) solve_kernel(const __grid_const
         __syncthreads();
       }
     }
+#ifdef PNEC_PHASE_TIMING
+    long long t_e = 0, t_l = 0, t_w = 0, n_pass = 0, t_start = clock64();
+#endif
     bool first = true;
     for (;;) {
+#ifdef PNEC_PHASE_TIMING
+      const long long t0 = clock64();
+#endif
       PoseConst pc;
       load_pose_const(s_pc, pc);
-      double acc[kNumAcc];
-#pragma unroll
-      for (int i = 0; i < kNumAcc; ++i) acc[i] = 0.0;
-      if (resident) {
-        eval_pass<V, NT>(pc, o.regularization, sf1, sf2, sct, sch, head, span, tid, acc);
+      const int mode = first ? kPassFull : s_lm.pass_mode;
+      const double *pf1 = resident ? sf1 : args.bv.f1 + 3 * s;
+      const double *pf2 = resident ? sf2 : args.bv.f2 + 3 * s;
+      const double *pct = resident ? sct : (VariantTraits<V>::kHasCt ? args.bv.ct + 9 * s : nullptr);
+      const double *pch = resident ? sch : (VariantTraits<V>::kHasCh ? args.bv.ch + 9 * s : nullptr);
+      const int lo = resident ? head : 0, hi = resident ? span : n;
+      if (mode == kPassCost) {
+        double sum;
+        if (resident) sum = eval_pass_cost<V, NT>(pc, o.regularization, sf1, sf2, sct, sch, lo, hi, tid);
+        else sum = eval_pass_cost<V, NT>(pc, o.regularization, pf1, pf2, pct, pch, lo, hi, tid);
+        const double cand_cost = block_reduce_scalar<NW>(sum, s_part, warp, lane, lmw);
+        if (warp == lmw) lm_after_cost_pass(s_lm, cand_cost, o, lane);
       } else {
-        // problem larger than the resident capacity: stream it from L2/HBM
-        eval_pass<V, NT>(pc, o.regularization, args.bv.f1 + 3 * s, args.bv.f2 + 3 * s,
-                         VariantTraits<V>::kHasCt ? args.bv.ct + 9 * s : nullptr,
-                         VariantTraits<V>::kHasCh ? args.bv.ch + 9 * s : nullptr, 0, n, tid, acc);
-      }
-      double tot[kNumAcc];
-      block_reduce<NW>(acc, s_part, warp, lane, tot);
-      if (warp == 0) {
-        LMState st = s_lm;
-        if (first) lm_begin(st, tot, o);
-        else lm_judge(st, tot, o);
-        if (!st.done) lm_propose(st, o);
-        if (lane == 0) {
-          s_lm = st;
-          if (!st.done) {
-            PoseConst pcn;
-            make_pose_const_sc(st.scc, st.cand + 2, pcn);
-            s_pc = pcn;
-          }
+        double acc[kNumAcc];
+#pragma unroll
+        for (int i = 0; i < kNumAcc; ++i) acc[i] = 0.0;
+        // two call sites so the resident one compiles to shared-memory loads
+        if (resident) eval_pass<V, NT>(pc, o.regularization, sf1, sf2, sct, sch, lo, hi, tid, acc);
+        else eval_pass<V, NT>(pc, o.regularization, pf1, pf2, pct, pch, lo, hi, tid, acc);
+        block_reduce<NW>(acc, s_part, warp, lane, s_lm.tot[s_lm.ti ^ 1], lmw);
+#ifdef PNEC_PHASE_TIMING
+        const long long t1 = clock64();
+        t_e += t1 - t0;
+#endif
+        if (warp == lmw) {
+          if (first) lm_step<true>(s_lm, o, lane, s_pc);
+          else lm_step<false>(s_lm, o, lane, s_pc);
         }
+#ifdef PNEC_PHASE_TIMING
+        const long long t2 = clock64();
+        t_l += t2 - t1;
+        ++n_pass;
+#endif
       }
+#ifdef PNEC_PHASE_TIMING
+      const long long t3 = clock64();
+#endif
       __syncthreads();
+#ifdef PNEC_PHASE_TIMING
+      t_w += clock64() - t3;
+#endif
       if (s_lm.done) break;
       first = false;
     }
+#ifdef PNEC_PHASE_TIMING
+    if (args.dbg && (tid == lmt || tid == ((lmw + 1) % NW) * 32)) {
+      long long *d = args.dbg + 12 * b + (tid != lmt ? 6 : 0);
+      d[0] = t_e; d[1] = t_l; d[2] = t_w; d[3] = n_pass; d[4] = clock64() - t_start; d[5] = t_start;
+    }
+#endif
   }
 
-  if (tid == 0) {
+  if (tid == lmt) {
     // PNECCeres::Result(): q.normalized(), t(theta, phi); pnec_ceres.cc:201-206
     const LMState &st = s_lm;
-    const double qn = sqrt(st.x[2] * st.x[2] + st.x[3] * st.x[3] + st.x[4] * st.x[4] + st.x[5] * st.x[5]);
+    const double *x = st.pts[st.xi], *sc = st.scs[st.xi];
+    const double qn = sqrt(x[2] * x[2] + x[3] * x[3] + x[4] * x[4] + x[5] * x[5]);
     const double iq = qn > 0.0 ? 1.0 / qn : 1.0;
     double *op = args.out_poses + 7 * b;
-    op[0] = st.x[2] * iq; op[1] = st.x[3] * iq; op[2] = st.x[4] * iq; op[3] = st.x[5] * iq;
-    op[4] = st.sc[0] * st.sc[3]; op[5] = st.sc[0] * st.sc[2]; op[6] = st.sc[1];
+    op[0] = x[2] * iq; op[1] = x[3] * iq; op[2] = x[4] * iq; op[3] = x[5] * iq;
+    op[4] = sc[0] * sc[3]; op[5] = sc[0] * sc[2]; op[6] = sc[1];
     if (args.out_status) args.out_status[b] = st.status;
     if (args.out_iters) args.out_iters[b] = st.iteration;
     if (args.out_cost) args.out_cost[b] = st.x_cost;
@@ -388,18 +446,15 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(const __grid_consta
       accumulate(acc, r, row);
     }
   }
-  double tot[kNumAcc];
-  block_reduce<NW>(acc, s_part, warp, lane, tot);
-  if (warp == 0) {
-    // lane j writes value j
-    double mine = 0.0;
-#pragma unroll
-    for (int j = 0; j < kNumAcc; ++j) mine = (lane == j) ? tot[j] : mine;
+  __shared__ double s_tot[kAccPad];
+  block_reduce<NW>(acc, s_part, warp, lane, s_tot);
+  if (warp == 0 && lane < kNumAcc) {
+    const double mine = s_tot[lane];  // lane j writes value j
     if (lane < 15) {
       if (args.out_jtj) args.out_jtj[15 * b + lane] = mine;
     } else if (lane < 20) {
       if (args.out_grad) args.out_grad[5 * b + (lane - 15)] = mine;
-    } else if (lane == 20) {
+    } else {
       if (args.out_cost) args.out_cost[b] = mine;
     }
   }
@@ -775,6 +830,27 @@ int launch_solve_v(pnec_handle *h, const SolveArgs &a, int nw, size_t dyn, cudaS
   }
 }
 
+#ifdef PNEC_PHASE_TIMING
+void dump_phase_timing(const SolveArgs &a) {
+  cudaDeviceSynchronize();
+  const long long B = a.bv.num_problems;
+  std::vector<long long> hbuf(12 * B);
+  cudaMemcpy(hbuf.data(), a.dbg, sizeof(long long) * 12 * B, cudaMemcpyDeviceToHost);
+  double s[12] = {0};
+  for (long long b = 0; b < B; ++b)
+    for (int k = 0; k < 12; ++k) s[k] += hbuf[12 * b + k];
+  unsigned long long probe[8];
+  cudaMemcpyFromSymbol(probe, g_lm_probe, sizeof(probe));
+  std::fprintf(stderr, "[lm_step probes, cycles per CTA] judge %.0f bookkeeping %.0f tr-step %.0f candidate %.0f store %.0f\n",
+               (double)probe[0] / B, (double)probe[1] / B, (double)probe[2] / B, (double)probe[3] / B, (double)probe[4] / B);
+  unsigned long long zero[8] = {0};
+  cudaMemcpyToSymbol(g_lm_probe, zero, sizeof(zero));
+  std::fprintf(stderr, "[phase timing, mean cycles per CTA] warp0: eval %.0f lm %.0f barrier %.0f full-passes %.2f "
+               "total %.0f | warp1: eval %.0f lm(idle) %.0f barrier %.0f\n",
+               s[0] / B, s[1] / B, s[2] / B, s[3] / B, s[4] / B, s[6] / B, s[7] / B, s[8] / B);
+}
+#endif
+
 int launch_solve(pnec_handle *h, const SolveArgs &a0, int variant, long long max_n,
                  cudaStream_t stream) {
   SolveArgs a = a0;
@@ -789,13 +865,24 @@ int launch_solve(pnec_handle *h, const SolveArgs &a0, int variant, long long max
   a.cap_elems = static_cast<int>(cap_elems);
   a.use_bulk = bulk_ok(a.bv) ? 1 : 0;
   if (env_int("PNEC_B200_NO_BULK", 0)) a.use_bulk = 0;
+  a.dbg = nullptr;
+#ifdef PNEC_PHASE_TIMING
+  static long long *dbg_buf = nullptr;
+  if (!dbg_buf) cudaMalloc(&dbg_buf, sizeof(long long) * 12 * 1000000);
+  a.dbg = dbg_buf;
+#endif
   const size_t dyn = static_cast<size_t>(cap_elems) * bpc;
+  int rc;
   switch (variant) {
-    case PNEC_VARIANT_NEC: return launch_solve_v<PNEC_VARIANT_NEC>(h, a, nw, dyn, stream);
-    case PNEC_VARIANT_TARGET: return launch_solve_v<PNEC_VARIANT_TARGET>(h, a, nw, dyn, stream);
-    case PNEC_VARIANT_HOST: return launch_solve_v<PNEC_VARIANT_HOST>(h, a, nw, dyn, stream);
-    default: return launch_solve_v<PNEC_VARIANT_SYMMETRIC>(h, a, nw, dyn, stream);
+    case PNEC_VARIANT_NEC: rc = launch_solve_v<PNEC_VARIANT_NEC>(h, a, nw, dyn, stream); break;
+    case PNEC_VARIANT_TARGET: rc = launch_solve_v<PNEC_VARIANT_TARGET>(h, a, nw, dyn, stream); break;
+    case PNEC_VARIANT_HOST: rc = launch_solve_v<PNEC_VARIANT_HOST>(h, a, nw, dyn, stream); break;
+    default: rc = launch_solve_v<PNEC_VARIANT_SYMMETRIC>(h, a, nw, dyn, stream); break;
   }
+#ifdef PNEC_PHASE_TIMING
+  if (rc == PNEC_OK && env_int("PNEC_B200_DUMP_TIMING", 0)) dump_phase_timing(a);
+#endif
+  return rc;
 }
 
 template <int V, int NW, int S, int MINB>
