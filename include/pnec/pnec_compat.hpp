@@ -287,6 +287,40 @@ inline double CostFunction(const BVs &bvs_1, const BVs &bvs_2, const Covs &covs,
   return out;
 }
 
+// src/common/common.cc:460-465
+template <class V2>
+inline Vec3 Unproject(const V2 &img_pt, const Mat3 &K_inv) {
+  const double *p = reinterpret_cast<const double *>(&img_pt);
+  Vec3 v = K_inv * Vec3(p[0], p[1], 1.0);
+  const double n = v.norm();
+  return Vec3(v[0] / n, v[1] / n, v[2] / n);
+}
+
+// src/common/common.cc:527-550: image-space covariances -> bearing-vector covariances (GPU)
+template <class BVs, class Covs>
+inline std::vector<Mat3> UnscentedTransform(const BVs &mus, const Covs &covs, const Mat3 &K_inv,
+                                            double kappa = 1.0, CameraModel camera_model = Pinhole) {
+  std::vector<Mat3> out(covs.size());
+  if (mus.size() != covs.size()) {
+    // the reference logs a warning and returns the covariances unchanged (common.cc:532-538)
+    for (std::size_t i = 0; i < covs.size(); ++i)
+      out[i] = *reinterpret_cast<const Mat3 *>(reinterpret_cast<const double *>(covs.data()) + 9 * i);
+    return out;
+  }
+  if (mus.size() == 0) return out;
+  const int model = (camera_model == Omnidirectional) ? PNEC_CAMERA_OMNIDIRECTIONAL : PNEC_CAMERA_PINHOLE;
+  if (pnec_unscented_transform_batch(detail::Handle(), static_cast<int64_t>(mus.size()), PNEC_MEM_HOST,
+                                     detail::AsDoubles(mus, 24), detail::AsDoubles(covs, 72), K_inv.data(),
+                                     kappa, model, out[0].data(), nullptr) != PNEC_OK)
+    throw std::runtime_error(std::string("pnec_unscented_transform_batch: ") + pnec_last_error());
+  return out;
+}
+// src/common/common.cc:467-525: single point
+inline Mat3 UnscentedTransform(const Vec3 &mu, const Mat3 &cov, const Mat3 &K_inv, double kappa = 1.0,
+                               CameraModel camera_model = Pinhole) {
+  return UnscentedTransform(std::vector<Vec3>{mu}, std::vector<Mat3>{cov}, K_inv, kappa, camera_model)[0];
+}
+
 // include/common/timing.h:48-67 (fields filled by the timed PNEC::Solve overload)
 struct FrameTiming {
   explicit FrameTiming(int id) : id_(id) {}

@@ -174,6 +174,27 @@ int pnec_cost_function_batch(pnec_handle *h, const pnec_batch *batch,
                              double *out_mean_energy /* [B] */,
                              void *cuda_stream);
 
+/* Camera models of pnec::common::CameraModel (include/common/common.h:61). */
+typedef enum pnec_camera_model {
+  PNEC_CAMERA_OMNIDIRECTIONAL = 0,
+  PNEC_CAMERA_PINHOLE = 1
+} pnec_camera_model;
+
+/* Unscented transform of n image-space covariances to 3x3 bearing-vector covariances:
+ * the step that produces the `covs_*` inputs of the solve.
+ * Replaces pnec::common::UnscentedTransform, both overloads
+ * (src/common/common.cc:467-550; declared include/common/common.h:103-113):
+ * 5 sigma points mu, mu +- C.col(i) with C the Cholesky factor of the 2x2 image-plane
+ * block (rotated into the tangent plane for omnidirectional cameras), weights
+ * kappa/(2+kappa) and 0.5/(2+kappa), projected with (K_inv p).normalized().
+ *   mus   [n][3]  image-space points (mu)           covs [n][9] column-major
+ *   K_inv [9]     column-major, HOST pointer        out  [n][9] column-major
+ * `memspace` applies to mus / covs / out. */
+int pnec_unscented_transform_batch(pnec_handle *h, int64_t n, int32_t memspace,
+                                   const double *mus, const double *covs,
+                                   const double *K_inv, double kappa, int32_t camera_model,
+                                   double *out_covs, void *cuda_stream);
+
 /* Number of kernels this handle has launched so far (bench bookkeeping). */
 int64_t pnec_launch_count(const pnec_handle *h);
 

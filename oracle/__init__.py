@@ -126,6 +126,9 @@ def lib() -> ctypes.CDLL:
         L.oracle_energy.argtypes = [ctypes.c_int, ctypes.c_int64, dp, dp, dp, dp,
                                     ctypes.c_double, dp, dp]
         L.oracle_energy.restype = ctypes.c_double
+        L.oracle_unscented_transform_batch.argtypes = [ctypes.c_int64, dp, dp, dp, ctypes.c_double,
+                                                       ctypes.c_int, dp]
+        L.oracle_unscented_transform_batch.restype = None
         _lib = L
     return _lib
 
@@ -261,3 +264,16 @@ def energy(variant, f1, f2, cov_t, cov_h, reg, q_xyzw, t) -> float:
     q, t = _c(q_xyzw), _c(t)
     return float(lib().oracle_energy(variant, f1.shape[0], _dp(f1), _dp(f2), _dp(cov_t),
                                      _dp(cov_h), reg, _dp(q), _dp(t)))
+
+
+OMNIDIRECTIONAL, PINHOLE = 0, 1
+
+
+def unscented_transform(mus, covs, K_inv=None, kappa=1.0, camera_model=PINHOLE):
+    """mus (n,3); covs (n,9) column-major; K_inv (9,) column-major -> (n,9) column-major."""
+    mus, covs = _c(mus, (3,)), _c(covs, (9,))
+    K = _c(np.eye(3).reshape(9) if K_inv is None else K_inv)
+    out = np.zeros((mus.shape[0], 9))
+    lib().oracle_unscented_transform_batch(mus.shape[0], _dp(mus), _dp(covs), _dp(K), float(kappa),
+                                           int(camera_model), _dp(out))
+    return out

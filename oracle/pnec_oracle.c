@@ -840,3 +840,83 @@ double oracle_energy(int variant, int64_t n, const double *f1, const double *f2,
   }
   return e;
 }
+
+/* ------------------------------------------------------- unscented transform */
+
+/* pnec::common::RotationBetweenPoints, src/common/common.cc:118-124 */
+static void rotation_between_points(const double p1[3], const double p2[3], double R[3][3]) {
+  double v[3], V[3][3], V2[3][3];
+  cross3(p1, p2, v);
+  const double c = dot3(p1, p2);
+  skew(v, V);
+  matmul(V, V, V2);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) R[i][j] = (i == j ? 1.0 : 0.0) + V[i][j] + V2[i][j] / (1 + c);
+}
+
+/* pnec::common::UnscentedTransform, src/common/common.cc:467-525.  camera_model:
+ * 0 = Omnidirectional, 1 = Pinhole (enum order of include/common/common.h:61).
+ * mu[3], cov[9] and K_inv[9] column-major; out[9] column-major. */
+void oracle_unscented_transform(const double mu[3], const double *cov, const double *K_inv,
+                                double kappa, int camera_model, double *out) {
+  const int n = 2, m = 2 * n + 1;
+  double S[3][3], K[3][3], C[3][3];
+  load_cov(cov, S);
+  load_cov(K_inv, K);
+  memset(C, 0, sizeof(C));
+  if (camera_model == 0) {
+    const double z[3] = {0.0, 0.0, 1.0};
+    const double nm = norm_n(mu, 3);
+    const double mn[3] = {mu[0] / nm, mu[1] / nm, mu[2] / nm};
+    double R[3][3], Rt[3][3], T1[3][3], T2[3][3], L[3][3];
+    rotation_between_points(z, mn, R);
+    transpose(R, Rt);
+    matmul(Rt, S, T1);
+    matmul(T1, R, T2);
+    memset(L, 0, sizeof(L));
+    L[0][0] = sqrt(T2[0][0]);
+    L[1][0] = T2[1][0] / L[0][0];
+    L[1][1] = sqrt(T2[1][1] - L[1][0] * L[1][0]);
+    matmul(R, L, C);
+  } else {
+    C[0][0] = sqrt(S[0][0]);
+    C[1][0] = S[1][0] / C[0][0];
+    C[1][1] = sqrt(S[1][1] - C[1][0] * C[1][0]);
+  }
+  double points[5][3], weights[5], tp[5][3], mean[3] = {0, 0, 0};
+  memcpy(points[0], mu, 3 * sizeof(double));
+  weights[0] = kappa / ((float)n + kappa);
+  for (int i = 0; i < n; ++i) {
+    for (int k = 0; k < 3; ++k) points[1 + i][k] = mu[k] + C[k][i];
+    weights[1 + i] = 0.5 / ((float)n + kappa);
+  }
+  for (int i = 0; i < n; ++i) {
+    for (int k = 0; k < 3; ++k) points[1 + n + i][k] = mu[k] - C[k][i];
+    weights[1 + n + i] = 0.5 / ((float)n + kappa);
+  }
+  for (int i = 0; i < m; ++i) {
+    double q[3];
+    if (camera_model == 0) memcpy(q, points[i], sizeof(q));
+    else matvec(K, points[i], q);
+    const double nq = norm_n(q, 3);
+    for (int k = 0; k < 3; ++k) {
+      tp[i][k] = q[k] / nq;
+      mean[k] = mean[k] + weights[i] * tp[i][k];
+    }
+  }
+  double sigma[3][3];
+  memset(sigma, 0, sizeof(sigma));
+  for (int i = 0; i < m; ++i)
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c)
+        sigma[r][c] = sigma[r][c] + weights[i] * (tp[i][r] - mean[r]) * (tp[i][c] - mean[c]);
+  for (int c = 0; c < 3; ++c)
+    for (int r = 0; r < 3; ++r) out[c * 3 + r] = sigma[r][c];
+}
+
+void oracle_unscented_transform_batch(int64_t n, const double *mus, const double *covs,
+                                      const double *K_inv, double kappa, int camera_model,
+                                      double *out) {
+  for (int64_t i = 0; i < n; ++i)
+    oracle_unscented_transform(mus + 3 * i, covs + 9 * i, K_inv, kappa, camera_model, out + 9 * i);
+}

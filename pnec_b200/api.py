@@ -16,6 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PNEC_B200_LIB") or os.path.join(_HERE, "lib", "libpnec_b200.so")
 
 NEC, TARGET, HOST, SYMMETRIC = 0, 1, 2, 3
+CAMERA_OMNIDIRECTIONAL, CAMERA_PINHOLE = 0, 1
 VARIANT_NAMES = {"nec": NEC, "target": TARGET, "host": HOST, "symmetric": SYMMETRIC}
 MEM_HOST, MEM_DEVICE = 0, 1
 
@@ -41,6 +42,7 @@ EXPORTED_SYMBOLS = (
     "pnec_solve_batch",
     "pnec_eval_batch",
     "pnec_cost_function_batch",
+    "pnec_unscented_transform_batch",
     "pnec_launch_count",
 )
 
@@ -139,6 +141,11 @@ def load_library() -> ctypes.CDLL:
     L.pnec_cost_function_batch.argtypes = [ctypes.c_void_p, ctypes.POINTER(_Batch),
                                            ctypes.c_void_p, ctypes.c_void_p]
     L.pnec_cost_function_batch.restype = ctypes.c_int
+    L.pnec_unscented_transform_batch.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,
+                                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                 ctypes.c_double, ctypes.c_int32, ctypes.c_void_p,
+                                                 ctypes.c_void_p]
+    L.pnec_unscented_transform_batch.restype = ctypes.c_int
     L.pnec_launch_count.argtypes = [ctypes.c_void_p]
     L.pnec_launch_count.restype = ctypes.c_int64
     _lib = L
@@ -359,6 +366,37 @@ class Handle:
             p = ctypes.c_void_p(out.ctypes.data)
         rc = self._lib.pnec_cost_function_batch(self._h, ctypes.byref(b), p, self._stream(device))
         self._check(rc, "pnec_cost_function_batch")
+        return out
+
+
+    def unscented_transform(self, mus, covs, K_inv=None, kappa=1.0, camera_model=CAMERA_PINHOLE):
+        """pnec::common::UnscentedTransform (src/common/common.cc:467-550) for n points.
+        mus (n,3), covs (n,9) column-major, K_inv (9,) column-major host array -> (n,9)."""
+        device = _is_torch(mus)
+        K = np.ascontiguousarray(np.eye(3).reshape(9) if K_inv is None else K_inv, dtype=np.float64).reshape(9)
+        if device:
+            import torch
+
+            n = mus.numel() // 3
+            if not (mus.is_cuda and covs.is_cuda and mus.is_contiguous() and covs.is_contiguous()
+                    and mus.dtype == torch.float64 and covs.dtype == torch.float64):
+                raise PnecError("device calls need contiguous float64 CUDA tensors")
+            out = torch.empty((n, 9), dtype=torch.float64, device=mus.device)
+            pm, pc, po = mus.data_ptr(), covs.data_ptr(), out.data_ptr()
+        else:
+            mus = self._prep_host(mus, (3,))
+            covs = self._prep_host(covs, (9,))
+            n = mus.shape[0]
+            out = np.empty((n, 9))
+            pm, pc, po = mus.ctypes.data, covs.ctypes.data, out.ctypes.data
+        ncov = (covs.numel() if device else covs.size) // 9
+        if ncov != n:
+            raise PnecError("mus and covs differ in length")
+        rc = self._lib.pnec_unscented_transform_batch(
+            self._h, n, MEM_DEVICE if device else MEM_HOST, ctypes.c_void_p(pm), ctypes.c_void_p(pc),
+            ctypes.c_void_p(K.ctypes.data), float(kappa), int(camera_model), ctypes.c_void_p(po),
+            self._stream(device))
+        self._check(rc, "pnec_unscented_transform_batch")
         return out
 
 

@@ -624,6 +624,98 @@ __global__ void __launch_bounds__(128) cost_kernel(BatchView bv, double *out) {
   if (tid == 0) out[b] = (s_red[0] + s_red[1] + s_red[2] + s_red[3]) / static_cast<double>(e - s);
 }
 
+// ------------------------------------------------------- unscented transform
+// pnec::common::UnscentedTransform, src/common/common.cc:467-525, one thread per point.
+// 96 B in + 72 B out per point, ~250 flops: HBM-bound.
+struct UtArgs {
+  const double *mus, *covs;
+  double *out;
+  long long n;
+  double Kinv[9];  // column-major
+  double kappa;
+  int camera_model;
+};
+
+__global__ void __launch_bounds__(128) unscented_kernel(const __grid_constant__ UtArgs a) {
+  const long long i = static_cast<long long>(blockIdx.x) * 128 + threadIdx.x;
+  if (i >= a.n) return;
+  double mu[3], S[9];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) mu[k] = a.mus[3 * i + k];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) S[k] = a.covs[9 * i + k];  // S[c * 3 + r]
+  const bool omni = (a.camera_model == PNEC_CAMERA_OMNIDIRECTIONAL);
+  // C = [c0 c1 0]: image-plane Cholesky columns (rotated for omnidirectional cameras)
+  double c0[3], c1[3];
+  if (omni) {
+    // RotationBetweenPoints((0,0,1), mu.normalized()), common.cc:118-124
+    const double inv_n = 1.0 / sqrt(mu[0] * mu[0] + mu[1] * mu[1] + mu[2] * mu[2]);
+    const double m[3] = {mu[0] * inv_n, mu[1] * inv_n, mu[2] * inv_n};
+    const double v[3] = {-m[1], m[0], 0.0};  // z x m
+    const double k = 1.0 / (1.0 + m[2]);
+    // R = I + [v]x + [v]x^2 k, row-major
+    double R[9];
+    R[0] = 1.0 + (-v[1] * v[1]) * k; R[1] = (v[0] * v[1]) * k;           R[2] = v[1];
+    R[3] = (v[0] * v[1]) * k;        R[4] = 1.0 + (-v[0] * v[0]) * k;    R[5] = -v[0];
+    R[6] = -v[1];                    R[7] = v[0];                        R[8] = 1.0 + (-(v[0] * v[0] + v[1] * v[1])) * k;
+    // local = (R^T S R) top-left 2x2:  local[p][q] = sum_rc R[r][p] S[r][c] R[c][q]
+    double SR[3][2];  // (S R)[:, 0:2]
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+        SR[r][q] = S[0 * 3 + r] * R[0 * 3 + q] + S[1 * 3 + r] * R[1 * 3 + q] + S[2 * 3 + r] * R[2 * 3 + q];
+    const double l_00 = R[0] * SR[0][0] + R[3] * SR[1][0] + R[6] * SR[2][0];
+    const double l_10 = R[1] * SR[0][0] + R[4] * SR[1][0] + R[7] * SR[2][0];
+    const double l_11 = R[1] * SR[0][1] + R[4] * SR[1][1] + R[7] * SR[2][1];
+    const double L00 = sqrt(l_00), L10 = l_10 / L00, L11 = sqrt(l_11 - L10 * L10);
+    // C = R * [[L00,0,0],[L10,L11,0],[0,0,0]]
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      c0[r] = R[r * 3 + 0] * L00 + R[r * 3 + 1] * L10;
+      c1[r] = R[r * 3 + 1] * L11;
+    }
+  } else {
+    const double L00 = sqrt(S[0]), L10 = S[1] / L00, L11 = sqrt(S[4] - L10 * L10);
+    c0[0] = L00; c0[1] = L10; c0[2] = 0.0;
+    c1[0] = 0.0; c1[1] = L11; c1[2] = 0.0;
+  }
+  const double nk = static_cast<double>(2.0f) + a.kappa;  // (float)n + kappa, common.cc:495
+  const double w0 = a.kappa / nk, wi = 0.5 / nk;
+  double tp[5][3], mean[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int p = 0; p < 5; ++p) {
+    const double sg = (p == 0) ? 0.0 : ((p <= 2) ? 1.0 : -1.0);
+    const double *c = (p == 1 || p == 3) ? c0 : c1;
+    double q[3] = {mu[0] + sg * c[0], mu[1] + sg * c[1], mu[2] + sg * c[2]};
+    if (!omni) {
+      const double x = a.Kinv[0] * q[0] + a.Kinv[3] * q[1] + a.Kinv[6] * q[2];
+      const double y = a.Kinv[1] * q[0] + a.Kinv[4] * q[1] + a.Kinv[7] * q[2];
+      const double z = a.Kinv[2] * q[0] + a.Kinv[5] * q[1] + a.Kinv[8] * q[2];
+      q[0] = x; q[1] = y; q[2] = z;
+    }
+    const double inv = 1.0 / sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+    const double w = (p == 0) ? w0 : wi;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      tp[p][k] = q[k] * inv;
+      mean[k] += w * tp[p][k];
+    }
+  }
+  double out[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int p = 0; p < 5; ++p) {
+    const double w = (p == 0) ? w0 : wi;
+    const double d[3] = {tp[p][0] - mean[0], tp[p][1] - mean[1], tp[p][2] - mean[2]};
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int r = 0; r < 3; ++r) out[c * 3 + r] += w * d[r] * d[c];
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) a.out[9 * i + k] = out[k];
+}
+
 }  // namespace pnec
 
 // =================================================================== host side
@@ -683,6 +775,7 @@ struct pnec_handle {
   // staging for HOST-memspace calls and for the device copy of offsets
   DevBuf d_f1, d_f2, d_ct, d_ch, d_off, d_poses;
   DevBuf d_out_poses, d_out_status, d_out_iters, d_out_cost, d_out_init, d_out_grad, d_out_jtj;
+  DevBuf d_ut_mu, d_ut_cov, d_ut_out;
   std::mutex mu;
 };
 
@@ -1010,7 +1103,8 @@ void pnec_destroy(pnec_handle *h) {
   cudaSetDevice(h->device);
   DevBuf *bufs[] = {&h->d_f1, &h->d_f2, &h->d_ct, &h->d_ch, &h->d_off, &h->d_poses,
                     &h->d_out_poses, &h->d_out_status, &h->d_out_iters, &h->d_out_cost,
-                    &h->d_out_init, &h->d_out_grad, &h->d_out_jtj};
+                    &h->d_out_init, &h->d_out_grad, &h->d_out_jtj, &h->d_ut_mu, &h->d_ut_cov,
+                    &h->d_ut_out};
   for (DevBuf *b : bufs) b->release();
   delete h;
 }
@@ -1146,6 +1240,52 @@ int pnec_cost_function_batch(pnec_handle *h, const pnec_batch *batch, double *ou
   if (host) {
     PNEC_CUDA(cudaMemcpyAsync(out_mean_energy, d_out, static_cast<size_t>(B) * 8,
                               cudaMemcpyDeviceToHost, stream));
+    PNEC_CUDA(cudaStreamSynchronize(stream));
+  }
+  return PNEC_OK;
+}
+
+int pnec_unscented_transform_batch(pnec_handle *h, int64_t n, int32_t memspace, const double *mus,
+                                   const double *covs, const double *K_inv, double kappa,
+                                   int32_t camera_model, double *out_covs, void *cuda_stream) {
+  if (!h) return fail(PNEC_ERR_INVALID_ARGUMENT, "handle is NULL");
+  if (n < 0) return fail(PNEC_ERR_INVALID_ARGUMENT, "n < 0");
+  if (n == 0) return PNEC_OK;
+  if (!mus || !covs || !out_covs) return fail(PNEC_ERR_INVALID_ARGUMENT, "NULL array");
+  if (camera_model != PNEC_CAMERA_OMNIDIRECTIONAL && camera_model != PNEC_CAMERA_PINHOLE)
+    return fail(PNEC_ERR_INVALID_ARGUMENT, "unknown camera model");
+  if (camera_model == PNEC_CAMERA_PINHOLE && !K_inv)
+    return fail(PNEC_ERR_INVALID_ARGUMENT, "K_inv is NULL for a pinhole camera");
+  if (memspace != PNEC_MEM_HOST && memspace != PNEC_MEM_DEVICE)
+    return fail(PNEC_ERR_INVALID_ARGUMENT, "unknown memspace");
+  std::lock_guard<std::mutex> lock(h->mu);
+  PNEC_CUDA(cudaSetDevice(h->device));
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  UtArgs a{};
+  a.n = n;
+  a.kappa = kappa;
+  a.camera_model = camera_model;
+  for (int k = 0; k < 9; ++k) a.Kinv[k] = K_inv ? K_inv[k] : ((k % 4 == 0) ? 1.0 : 0.0);
+  const size_t nn = static_cast<size_t>(n);
+  if (memspace == PNEC_MEM_HOST) {
+    PNEC_CUDA(h->d_ut_mu.ensure(nn * 24));
+    PNEC_CUDA(h->d_ut_cov.ensure(nn * 72));
+    PNEC_CUDA(h->d_ut_out.ensure(nn * 72));
+    PNEC_CUDA(cudaMemcpyAsync(h->d_ut_mu.p, mus, nn * 24, cudaMemcpyHostToDevice, stream));
+    PNEC_CUDA(cudaMemcpyAsync(h->d_ut_cov.p, covs, nn * 72, cudaMemcpyHostToDevice, stream));
+    a.mus = static_cast<const double *>(h->d_ut_mu.p);
+    a.covs = static_cast<const double *>(h->d_ut_cov.p);
+    a.out = static_cast<double *>(h->d_ut_out.p);
+  } else {
+    a.mus = mus;
+    a.covs = covs;
+    a.out = out_covs;
+  }
+  unscented_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, stream>>>(a);
+  PNEC_CUDA(cudaGetLastError());
+  h->launches++;
+  if (memspace == PNEC_MEM_HOST) {
+    PNEC_CUDA(cudaMemcpyAsync(out_covs, a.out, nn * 72, cudaMemcpyDeviceToHost, stream));
     PNEC_CUDA(cudaStreamSynchronize(stream));
   }
   return PNEC_OK;

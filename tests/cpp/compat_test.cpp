@@ -58,6 +58,18 @@ int main(int argc, char **argv) {
   print_pose("PNECCeresSymmetric", sym.Result(), sym.Status(), sym.Iterations());
   std::printf("CostFunction %.17g\n", pnec::common::CostFunction(bvs1, bvs2, covs_t, a));
 
+  // include/common/common.h:103-113: covariance propagation for the first 3 correspondences
+  {
+    std::vector<Vec3> mus(bvs2.begin(), bvs2.begin() + 3);
+    for (auto &m : mus) { m[0] *= 800; m[1] *= 800; m[2] *= 800; }
+    std::vector<Mat3> img(3);
+    for (auto &c : img) { c(0, 0) = 0.7; c(1, 1) = 0.4; c(0, 1) = c(1, 0) = 0.1; }
+    const auto proj = pnec::common::UnscentedTransform(mus, img, Mat3::Identity(), 1.0, pnec::common::Pinhole);
+    const Mat3 one = pnec::common::UnscentedTransform(mus[1], img[1], Mat3::Identity(), 1.0, pnec::common::Pinhole);
+    std::printf("UnscentedTransform %.17g %.17g %.17g %d\n", proj[1](0, 0), proj[1](0, 1), proj[1](2, 2),
+                (int)(one(0, 0) == proj[1](0, 0)));
+  }
+
   // unsupported orchestration must throw, not silently do something else
   pnec::rel_pose_estimation::PNEC full((pnec::rel_pose_estimation::Options()));
   try {

@@ -232,6 +232,44 @@ def test_cost_function_metric(handle):
         assert got[i] == pytest.approx(oracle.cost_function(f1, f2, ct, b.gt_poses[i]), rel=1e-11)
 
 
+@pytest.mark.parametrize("camera", [api.CAMERA_OMNIDIRECTIONAL, api.CAMERA_PINHOLE])
+def test_unscented_transform_matches_oracle(handle, golden_ut, camera):
+    """pnec_unscented_transform_batch vs the C restatement of common.cc:467-525 (fp64, 1e-12
+    of the largest entry) and vs the reference's python outputs on the committed vectors."""
+    rng = np.random.default_rng(17)
+    n = 5000
+    col = lambda M: np.swapaxes(M, -1, -2).reshape(-1, 9)
+    c3 = np.zeros((n, 3, 3))
+    c3[:, :2, :2] = syn.sample_covariances_2d(rng, (1, n), 1.5, "anisotropic_inhomogenous")[0]
+    if camera == api.CAMERA_OMNIDIRECTIONAL:
+        mus = syn._uniform_sphere(rng, (n,)) * 800.0
+        mus[:, 2] = np.abs(mus[:, 2]) + 1.0
+        ez = np.broadcast_to(np.array([0.0, 0.0, 1.0]), mus.shape)
+        Rp = syn.rotation_between_points(ez, syn._normalize(mus))
+        c3 = Rp @ c3 @ np.swapaxes(Rp, -1, -2)
+        K = None
+    else:
+        mus = np.stack([rng.uniform(0, 1241, n), rng.uniform(0, 376, n), np.ones(n)], -1)
+        Kinv = np.linalg.inv(np.array([[718.856, 0, 607.19], [0, 718.856, 185.2157], [0, 0, 1.0]]))
+        K = np.ascontiguousarray(Kinv.T).reshape(9)  # column-major
+    ref = oracle.unscented_transform(mus, col(c3), K, 1.0, camera)
+    got_h = handle.unscented_transform(mus, col(c3), K, 1.0, camera)
+    got_d = handle.unscented_transform(dev(mus), dev(col(c3)), K, 1.0, camera).cpu().numpy()
+    assert np.array_equal(got_h, got_d)
+    np.testing.assert_allclose(got_h, ref, rtol=0, atol=1e-12 * np.abs(ref).max())
+    assert np.abs(got_h - got_h.reshape(-1, 3, 3).transpose(0, 2, 1).reshape(-1, 9)).max() < 1e-20
+    u = golden_ut
+    if camera == api.CAMERA_OMNIDIRECTIONAL:
+        g = handle.unscented_transform(u["mus"], col(u["covs_omni"]), None, 1.0, camera)
+        np.testing.assert_allclose(g, col(u["ut_omni"]), rtol=0, atol=1e-12 * np.abs(u["ut_omni"]).max())
+    else:
+        g = handle.unscented_transform(u["mus_pinhole"], col(u["covs_local"]), None, 1.0, camera)
+        np.testing.assert_allclose(g, col(u["ut_pinhole"]), rtol=0, atol=1e-12 * np.abs(u["ut_pinhole"]).max())
+    assert handle.unscented_transform(np.zeros((0, 3)), np.zeros((0, 9))).shape == (0, 9)
+    with pytest.raises(api.PnecError, match="camera model"):
+        handle.unscented_transform(mus, col(c3), K, 1.0, 5)
+
+
 # -------------------------------------- BASELINE full size: structural properties
 
 
@@ -372,3 +410,9 @@ def test_cpp_compat_api_matches_oracle(tmp_path):
     assert float(lines["CostFunction"][0]) == pytest.approx(
         oracle.cost_function(b.bvs_host, b.bvs_target, b.covs_target, p), rel=1e-10)
     assert lines["SolveDefaultOptions"] == ["throws"]
+    mu = b.bvs_target[1] * 800.0
+    img = np.array([[0.7, 0.1, 0.0], [0.1, 0.4, 0.0], [0.0, 0.0, 0.0]])
+    ut = oracle.unscented_transform(mu[None], img.T.reshape(1, 9), None, 1.0, oracle.PINHOLE)[0].reshape(3, 3).T
+    got = [float(v) for v in lines["UnscentedTransform"][:3]]
+    np.testing.assert_allclose(got, [ut[0, 0], ut[0, 1], ut[2, 2]], rtol=1e-9, atol=1e-20)
+    assert lines["UnscentedTransform"][3] == "1"

@@ -33,6 +33,27 @@ def test_unscented_transform_matches_reference(golden_ut):
     np.testing.assert_allclose(rbp, u["rotation_between_points"], atol=1e-14)
 
 
+def test_oracle_unscented_transform_matches_reference(golden_ut):
+    """C restatement of common.cc:467-525 vs scripts/pnec/math.py:73-123 (diagonal local
+    covariance, where the python and C++ references coincide) and vs the numpy generator."""
+    u = golden_ut
+    col = lambda M: np.swapaxes(M, -1, -2).reshape(-1, 9)
+    o = oracle.unscented_transform(u["mus"], col(u["covs_omni"]), None, 1.0, oracle.OMNIDIRECTIONAL)
+    np.testing.assert_allclose(o, col(u["ut_omni"]), rtol=0, atol=1e-12 * np.abs(u["ut_omni"]).max())
+    o = oracle.unscented_transform(u["mus_pinhole"], col(u["covs_local"]), None, 1.0, oracle.PINHOLE)
+    np.testing.assert_allclose(o, col(u["ut_pinhole"]), rtol=0, atol=1e-12 * np.abs(u["ut_pinhole"]).max())
+    rng = np.random.default_rng(3)
+    mus = syn._uniform_sphere(rng, (64,)) * 800.0
+    mus[:, 2] = np.abs(mus[:, 2])
+    c3 = np.zeros((64, 3, 3))
+    c3[:, :2, :2] = syn.sample_covariances_2d(rng, (1, 64), 1.0, "anisotropic_inhomogenous")[0]
+    ez = np.broadcast_to(np.array([0.0, 0.0, 1.0]), mus.shape)
+    Rp = syn.rotation_between_points(ez, syn._normalize(mus))
+    c3o = Rp @ c3 @ np.swapaxes(Rp, -1, -2)
+    a = oracle.unscented_transform(mus, col(c3o), None, 1.0, oracle.OMNIDIRECTIONAL)
+    np.testing.assert_allclose(a, col(syn.unscented_transform(mus, c3o, syn.OMNIDIRECTIONAL)), rtol=0, atol=1e-20)
+
+
 VARIANTS = {"nec": oracle.NEC, "target": oracle.TARGET, "host": oracle.HOST,
             "symmetric": oracle.SYMMETRIC}
 CASES = ["c1_iso_omni_n100", "c2_aniso_omni_n512", "aniso_pinhole_n64", "aniso_omni_n10"]
