@@ -346,25 +346,24 @@ __device__ __forceinline__ double fast_rcp(double x) {
 // sqrt(x) for x >= 0 through rsqrt (no slow-path branch)
 __device__ __forceinline__ double fast_sqrt(double x) { return x > 0.0 ? x * rsqrt(x) : 0.0; }
 
-// sin(a)/a and cos(a) as polynomials in z = a^2, |a| <= 0.25 (truncation < 1e-19)
+// sin(a)/a and cos(a) as polynomials in z = a^2, |a| <= 0.25 (truncation < 1e-19).
+// Estrin evaluation: the dependent chain is 4 deep instead of 8 (fp64 latency is what the
+// serial LM phase is made of).
 __device__ __forceinline__ void small_sinc_cos(double z, double &sinc, double &cs) {
-  double p = -1.0 / 1307674368000.0;
-  p = fma(p, z, 1.0 / 6227020800.0);
-  p = fma(p, z, -1.0 / 39916800.0);
-  p = fma(p, z, 1.0 / 362880.0);
-  p = fma(p, z, -1.0 / 5040.0);
-  p = fma(p, z, 1.0 / 120.0);
-  p = fma(p, z, -1.0 / 6.0);
-  sinc = fma(p, z, 1.0);
-  double q = 1.0 / 20922789888000.0;
-  q = fma(q, z, -1.0 / 87178291200.0);
-  q = fma(q, z, 1.0 / 479001600.0);
-  q = fma(q, z, -1.0 / 3628800.0);
-  q = fma(q, z, 1.0 / 40320.0);
-  q = fma(q, z, -1.0 / 720.0);
-  q = fma(q, z, 1.0 / 24.0);
-  q = fma(q, z, -0.5);
-  cs = fma(q, z, 1.0);
+  const double z2 = z * z, z4 = z2 * z2;
+  // sinc = sum_k (-1)^k z^k / (2k+1)!,  k = 0..7
+  const double s01 = fma(z, -1.0 / 6.0, 1.0);
+  const double s23 = fma(z, -1.0 / 5040.0, 1.0 / 120.0);
+  const double s45 = fma(z, -1.0 / 39916800.0, 1.0 / 362880.0);
+  const double s67 = fma(z, -1.0 / 1307674368000.0, 1.0 / 6227020800.0);
+  sinc = fma(z4, fma(z2, s67, s45), fma(z2, s23, s01));
+  // cos = sum_k (-1)^k z^k / (2k)!,  k = 0..8
+  const double c01 = fma(z, -0.5, 1.0);
+  const double c23 = fma(z, -1.0 / 720.0, 1.0 / 24.0);
+  const double c45 = fma(z, -1.0 / 3628800.0, 1.0 / 40320.0);
+  const double c67 = fma(z, -1.0 / 87178291200.0, 1.0 / 479001600.0);
+  const double c8 = 1.0 / 20922789888000.0;
+  cs = fma(z4, fma(z4, c8, fma(z2, c67, c45)), fma(z2, c23, c01));
 }
 constexpr double kSmallAngle2 = 0.0625;  // (0.25 rad)^2
 
@@ -422,6 +421,27 @@ __device__ __forceinline__ void make_pose_const_sc(const double sc[4], const dou
   pc.R[6] = txz - twy;         pc.R[7] = tyz + twx;         pc.R[8] = 1.0 - (txx + tyy);
 }
 
+// Rare path of lm_step (a step above 0.25 rad): exact sin/cos.  Kept out of line so that the
+// Payne-Hanek slow paths of sincos() do not bloat the registers of the common path.
+__device__ __noinline__ void lm_candidate_large_step(const double *x, const double *sc,
+                                                     const double *delta, double *cand,
+                                                     double *scc) {
+  advance_sincos(cand[0], delta[0], sc[0], sc[1], scc[0], scc[1]);
+  advance_sincos(cand[1], delta[1], sc[2], sc[3], scc[2], scc[3]);
+  quat_plus_fast(x + 2, delta + 2, cand + 2);
+}
+
+// Rare path of gradient_converged: the quaternion part of || x - Plus(x, -g) ||_inf.
+__device__ __noinline__ double quaternion_chord_max(const double *q, const double *g) {
+  const double ng[3] = {-g[0], -g[1], -g[2]};
+  double qs[4];
+  quat_plus_fast(q, ng, qs);
+  double m = 0.0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) m = fmax(m, fabs(q[i] - qs[i]));
+  return m;
+}
+
 // gradient_max_norm <= tol, where gradient_max_norm = || x - Plus(x, -g) ||_inf
 // (TrustRegionMinimizer::EvaluateGradientAndJacobian).  The theta/phi part of
 // that norm is |g0|, |g1|; the quaternion part is only evaluated when those pass.
@@ -430,54 +450,59 @@ __device__ __forceinline__ bool gradient_converged(const double x[6], const doub
   if (!(fmax(fabs(g[0]), fabs(g[1])) <= tol)) return false;
   const double nd2 = g[2] * g[2] + g[3] * g[3] + g[4] * g[4];
   if (nd2 > kSmallAngle2) return false;  // chord 2 sin(|g|/2) is far above any tolerance
-  const double ng[3] = {-g[2], -g[3], -g[4]};
-  double qs[4];
-  quat_plus_fast(x + 2, ng, qs);
-  double m = 0.0;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) m = fmax(m, fabs(x[2 + i] - qs[i]));
-  return m <= tol;
+  return quaternion_chord_max(x + 2, g + 2) <= tol;
 }
 
-// 5x5 LDL^T solve of A y = b (A symmetric, upper part read).  Returns false if a
-// pivot is not positive (A not positive definite) or the solution is not finite:
-// LINEAR_SOLVER_FAILURE in Ceres terms, an invalid step.
-__device__ __forceinline__ bool ldlt_solve5(const double A[5][5], const double b[5], double y[5]) {
-  double L[5][5], d[5], id[5];
-  bool ok = true;
+// 5x5 SPD solve A d = b by block elimination over the (theta, phi | rotation) split with
+// closed-form 2x2 / 3x3 adjugate inverses: 2 reciprocals and a ~30-deep dependent chain
+// (LDL^T + substitutions is ~65 deep).  Returns false if A is not positive definite
+// (Sylvester: all leading minors of P and of the Schur complement positive) or the
+// solution is not finite: LINEAR_SOLVER_FAILURE in Ceres terms, an invalid step.
+__device__ __forceinline__ bool spd_solve5(const double A[5][5], const double b[5], double d[5]) {
+  // P = A[0:2,0:2]
+  const double p00 = A[0][0], p01 = A[0][1], p11 = A[1][1];
+  const double detP = fma(p00, p11, -p01 * p01);
+  const double iP = fast_rcp(detP);
+  const double i00 = p11 * iP, i01 = -p01 * iP, i11 = p00 * iP;  // P^-1
+  // W = P^-1 Q (2x3), u = P^-1 b1
+  double W0[3], W1[3];
 #pragma unroll
-  for (int j = 0; j < 5; ++j) {
-    double dj = A[j][j];
+  for (int j = 0; j < 3; ++j) {
+    W0[j] = fma(i00, A[0][2 + j], i01 * A[1][2 + j]);
+    W1[j] = fma(i01, A[0][2 + j], i11 * A[1][2 + j]);
+  }
+  const double u0 = fma(i00, b[0], i01 * b[1]), u1 = fma(i01, b[0], i11 * b[1]);
+  // Schur complement S = R - Q^T W (symmetric 3x3), c = b2 - Q^T u
+  double S[3][3], c[3];
 #pragma unroll
-    for (int k = 0; k < j; ++k) dj = fma(-L[j][k] * L[j][k], d[k], dj);
-    d[j] = dj;
-    ok = ok && (dj > 0.0) && (dj < CUDART_INF);
-    id[j] = fast_rcp(dj);
+  for (int i = 0; i < 3; ++i) {
 #pragma unroll
-    for (int i = j + 1; i < 5; ++i) {
-      double s = A[j][i];
-#pragma unroll
-      for (int k = 0; k < j; ++k) s = fma(-L[i][k] * L[j][k], d[k], s);
-      L[i][j] = s * id[j];
+    for (int j = i; j < 3; ++j) {
+      S[i][j] = A[2 + i][2 + j] - fma(A[0][2 + i], W0[j], A[1][2 + i] * W1[j]);
+      S[j][i] = S[i][j];
     }
+    c[i] = b[2 + i] - fma(A[0][2 + i], u0, A[1][2 + i] * u1);
   }
-  double z[5];
+  // adjugate of S
+  const double c00 = fma(S[1][1], S[2][2], -S[1][2] * S[1][2]);
+  const double c01 = fma(S[0][2], S[1][2], -S[0][1] * S[2][2]);
+  const double c02 = fma(S[0][1], S[1][2], -S[0][2] * S[1][1]);
+  const double c11 = fma(S[0][0], S[2][2], -S[0][2] * S[0][2]);
+  const double c12 = fma(S[0][1], S[0][2], -S[0][0] * S[1][2]);
+  const double c22 = fma(S[0][0], S[1][1], -S[0][1] * S[0][1]);
+  const double detS = fma(S[0][0], c00, fma(S[0][1], c01, S[0][2] * c02));
+  const double iS = fast_rcp(detS);
+  const double n0 = fma(c00, c[0], fma(c01, c[1], c02 * c[2]));
+  const double n1 = fma(c01, c[0], fma(c11, c[1], c12 * c[2]));
+  const double n2 = fma(c02, c[0], fma(c12, c[1], c22 * c[2]));
+  d[2] = n0 * iS;
+  d[3] = n1 * iS;
+  d[4] = n2 * iS;
+  d[0] = u0 - fma(W0[0], d[2], fma(W0[1], d[3], W0[2] * d[4]));
+  d[1] = u1 - fma(W1[0], d[2], fma(W1[1], d[3], W1[2] * d[4]));
+  bool ok = (p00 > 0.0) && (detP > 0.0) && (S[0][0] > 0.0) && (c22 > 0.0) && (detS > 0.0);
 #pragma unroll
-  for (int i = 0; i < 5; ++i) {
-    double s = b[i];
-#pragma unroll
-    for (int k = 0; k < i; ++k) s = fma(-L[i][k], z[k], s);
-    z[i] = s;
-  }
-#pragma unroll
-  for (int i = 4; i >= 0; --i) {
-    double s = z[i] * id[i];
-#pragma unroll
-    for (int k = i + 1; k < 5; ++k) s = fma(-L[k][i], y[k], s);
-    y[i] = s;
-  }
-#pragma unroll
-  for (int i = 0; i < 5; ++i) ok = ok && (fabs(y[i]) < CUDART_INF);
+  for (int i = 0; i < 5; ++i) ok = ok && (fabs(d[i]) < CUDART_INF);
   return ok;
 }
 
@@ -507,7 +532,7 @@ __device__ __forceinline__ bool lm_trust_region_step(const double *Hg, const dou
     lam[a] = diag[a] * inv_radius * inv_scale2[a];
     A[a][a] += lam[a];
   }
-  bool valid = ldlt_solve5(A, Hg + 15, d);
+  bool valid = spd_solve5(A, Hg + 15, d);
   mcc = 0.0;
 #pragma unroll
   for (int a = 0; a < 5; ++a) mcc = fma(d[a], fma(lam[a], d[a], Hg[15 + a]), mcc);
@@ -531,6 +556,14 @@ __device__ unsigned long long g_lm_probe[8];
 #else
 #define LM_PROBE(k) do { } while (0)
 #endif
+
+// The LM update runs on lane 0 of the LM warp only (measured 4 % faster than all 32 lanes
+// redundantly, and it keeps the fp64 pipe free for the co-resident CTAs' evaluations).
+// PNEC_LM_FULL_WARP=1 restores the redundant variant.
+#ifndef PNEC_LM_FULL_WARP
+#define PNEC_LM_FULL_WARP 0
+#endif
+constexpr bool kLmFullWarp = PNEC_LM_FULL_WARP != 0;
 
 template <bool FIRST>
 __device__ __forceinline__ void lm_step(LMState &st, const pnec_solver_opts &o, int lane,
@@ -615,15 +648,34 @@ __device__ __forceinline__ void lm_step(LMState &st, const pnec_solver_opts &o, 
   if (!done) {
     cand[0] = x[0] + delta[0];
     cand[1] = x[1] + delta[1];
-    advance_sincos(cand[0], delta[0], sc[0], sc[1], scc[0], scc[1]);
-    advance_sincos(cand[1], delta[1], sc[2], sc[3], scc[2], scc[3]);
-    quat_plus_fast(x + 2, delta + 2, cand + 2);
+    const double zt = delta[0] * delta[0], zp = delta[1] * delta[1];
+    const double zq = fma(delta[2], delta[2], fma(delta[3], delta[3], delta[4] * delta[4]));
+    if (fmax(fmax(zt, zp), zq) <= kSmallAngle2) {
+      // common case, one branch: three independent small-angle evaluations + angle addition
+      double sct, cdt, scp, cdp, sq, cq;
+      small_sinc_cos(zt, sct, cdt);
+      small_sinc_cos(zp, scp, cdp);
+      small_sinc_cos(zq, sq, cq);
+      const double sdt = delta[0] * sct, sdp = delta[1] * scp;
+      scc[0] = fma(sc[0], cdt, sc[1] * sdt);
+      scc[1] = fma(sc[1], cdt, -sc[0] * sdt);
+      scc[2] = fma(sc[2], cdp, sc[3] * sdp);
+      scc[3] = fma(sc[3], cdp, -sc[2] * sdp);
+      const double dx = sq * delta[2], dy = sq * delta[3], dz = sq * delta[4];
+      const double xx = x[2], xy = x[3], xz = x[4], xw = x[5];
+      cand[5] = cq * xw - dx * xx - dy * xy - dz * xz;
+      cand[2] = cq * xx + dx * xw + dy * xz - dz * xy;
+      cand[3] = cq * xy - dx * xz + dy * xw + dz * xx;
+      cand[4] = cq * xz + dx * xy - dy * xx + dz * xw;
+    } else {
+      lm_candidate_large_step(x, sc, delta, cand, scc);
+    }
     // ParameterToleranceReached depends on the step only.  Ceres evaluates the candidate's
     // cost first and then returns without applying the step, so the evaluation cannot change
     // the outcome: decide here and skip it.
-    double sn = 0.0;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) sn = fma(x[i] - cand[i], x[i] - cand[i], sn);
+    const double e0 = x[0] - cand[0], e1 = x[1] - cand[1], e2 = x[2] - cand[2];
+    const double e3 = x[3] - cand[3], e4 = x[4] - cand[4], e5 = x[5] - cand[5];
+    const double sn = fma(e0, e0, e1 * e1) + fma(e2, e2, e3 * e3) + fma(e4, e4, e5 * e5);
     // |x| <= |theta| + |phi| + |q| gives a cheap upper bound of the tolerance; the exact
     // norm is only formed when the step is small enough for the test to possibly pass.
     const double ptol_hi = o.parameter_tolerance * (fabs(x[0]) + fabs(x[1]) + 2.0 + o.parameter_tolerance);
@@ -642,7 +694,7 @@ __device__ __forceinline__ void lm_step(LMState &st, const pnec_solver_opts &o, 
     pass_mode = (mcc <= 1.05 * o.function_tolerance * x_cost) ? kPassCost : kPassFull;
   }
   LM_PROBE(3);  // candidate
-  __syncwarp();  // every lane has read the state it needs; lane 0 may now overwrite it
+  if (kLmFullWarp) __syncwarp();  // every lane has read the state it needs; lane 0 may now overwrite it
   if (lane == 0) {
     if (!done) {
       PoseConst pcn;

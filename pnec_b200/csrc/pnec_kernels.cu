@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) solve_kernel(const __grid_const
         const long long t1 = clock64();
         t_e += t1 - t0;
 #endif
-        if (warp == lmw) {
+        if (warp == lmw && (kLmFullWarp || lane == 0)) {
           if (first) lm_step<true>(s_lm, o, lane, s_pc);
           else lm_step<false>(s_lm, o, lane, s_pc);
         }
