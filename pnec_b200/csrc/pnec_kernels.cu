@@ -364,6 +364,173 @@ __global__ void __launch_bounds__(NW * 32, MINB) solve_kernel(const __grid_const
   }
 }
 
+// ------------------------------------------------------ solve kernel, streaming
+//
+// Same LM solve for frame pairs too large to keep 2+ of them resident per SM (N > 1024):
+// nothing is resident.  Warp w owns tiles w, w + NW, ... of the pair and a private S-stage
+// ring; lane 0 keeps the ring S tiles ahead with bulk async copies and simply wraps around
+// at the end of a pass, so the first tiles of the NEXT pass are already in flight while the
+// LM update runs.  Pass 1 comes from HBM; later passes hit L2 (the working set of the
+// resident CTAs is a few tens of MB).  On exit every warp drains its outstanding copies.
+template <int V, int NW, int S, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB)
+solve_stream_kernel(const __grid_constant__ SolveArgs args) {
+  constexpr int T = 32;
+  constexpr int kStageDoubles = T * VariantTraits<V>::kDoubles;
+  __shared__ __align__(8) uint64_t s_full[NW][S];
+  __shared__ PoseConst s_pc;
+  __shared__ LMState s_lm;
+  __shared__ double s_part[NW][kAccPad];
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler
+  const long long b = blockIdx.x;
+  long long s, e;
+  problem_range(args.bv, b, s, e);
+  const int n = static_cast<int>(e - s);
+  const long long g0 = s & ~1LL;
+  const int head = static_cast<int>(s - g0);
+  const int span = n + head;
+  const int ntiles = (n > 0) ? (span + T - 1) / T : 0;
+  const int nt_w = (ntiles > warp) ? (ntiles - warp + NW - 1) / NW : 0;  // tiles of this warp
+  const pnec_solver_opts &o = args.o;
+  const int lmw = (NW == 1) ? 0 : static_cast<int>((blockIdx.x + blockIdx.x / 148u) % NW);
+  const int lmt = lmw * 32;
+  double *ring = dyn_smem + static_cast<size_t>(warp) * S * kStageDoubles;
+  uint64_t *full = s_full[warp];
+
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < S; ++i) mbar_init(&full[i], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+
+  // producer: tile p_i of this warp's sequence goes to stage p_stage; wraps at nt_w
+  int p_i = 0, p_stage = 0, in_flight = 0;
+  auto producer_issue = [&]() {
+    if (lane == 0) {
+      const int k = warp + p_i * NW;
+      double *base = ring + p_stage * kStageDoubles;
+      issue_bulk<V>(args.bv, g0 + static_cast<long long>(k) * T, min(T, span - k * T), base,
+                    base + 3 * T, base + 6 * T, base + 15 * T, &full[p_stage]);
+    }
+    p_i = (p_i + 1 == nt_w) ? 0 : p_i + 1;
+    p_stage = (p_stage + 1 == S) ? 0 : p_stage + 1;
+    ++in_flight;
+  };
+  if (nt_w > 0) {
+#pragma unroll 1
+    for (int i = 0; i < S; ++i) producer_issue();
+  }
+
+  if (tid == lmt) {
+    // PNECCeres::InitValues(orientation, translation), pnec_ceres.cc:188-192
+    const double *p = args.bv.poses + 7 * b;
+    LMState &st = s_lm;
+    double *x = st.pts[0], *sc = st.scs[0];
+    angles_from_vec(p + 4, x[0], x[1]);
+    x[2] = p[0]; x[3] = p[1]; x[4] = p[2]; x[5] = p[3];
+    sincos(x[0], &sc[0], &sc[1]);
+    sincos(x[1], &sc[2], &sc[3]);
+    st.inv_radius = 1.0 / o.initial_trust_region_radius;
+    st.decrease_factor = 2.0;
+    st.inv_model_cost_change = 0.0;
+    st.x_cost = 0.0;
+    st.initial_cost = 0.0;
+    st.xi = 0;
+    st.ti = 0;
+    st.iteration = 0;
+    st.num_invalid = 0;
+    st.reuse_diagonal = 0;
+    st.step_successful = 1;
+    st.grad_converged = 0;
+    st.status = (n <= 0) ? PNEC_STATUS_EMPTY : PNEC_STATUS_MAX_ITERATIONS;
+    st.done = (n <= 0) ? 1 : 0;
+    st.pass_mode = kPassFull;
+    PoseConst pc0;
+    make_pose_const_sc(sc, x + 2, pc0);
+    s_pc = pc0;
+  }
+  __syncthreads();
+
+  int c_stage = 0;
+  uint32_t c_parity = 0;
+  if (n > 0) {
+    bool first = true;
+    for (;;) {
+      PoseConst pc;
+      load_pose_const(s_pc, pc);
+      const int mode = first ? kPassFull : s_lm.pass_mode;
+      double acc[kNumAcc];
+#pragma unroll
+      for (int i = 0; i < kNumAcc; ++i) acc[i] = 0.0;
+      for (int i = 0; i < nt_w; ++i) {
+        mbar_wait(&full[c_stage], c_parity);
+        const double *base = ring + c_stage * kStageDoubles;
+        const int idx = (warp + i * NW) * T + lane;
+        const bool valid = (idx >= head) && (idx < span);
+        double a1[3], a2[3], c1[9], c2[9];
+        if (valid) load_corr<V>(base, base + 3 * T, base + 6 * T, base + 15 * T, lane, a1, a2, c1, c2);
+        __syncwarp();  // the stage may be refilled
+        --in_flight;
+        producer_issue();
+        if (++c_stage == S) {
+          c_stage = 0;
+          c_parity ^= 1u;
+        }
+        if (valid) {
+          if (mode == kPassCost) {
+            const double r = residual_only<V>(pc, o.regularization, a1, a2, c1, c2);
+            acc[kNumAcc - 1] = fma(r, r, acc[kNumAcc - 1]);
+          } else {
+            double r, row[5];
+            residual_row<V>(pc, o.regularization, a1, a2, c1, c2, r, row);
+            accumulate(acc, r, row);
+          }
+        }
+      }
+      if (mode == kPassCost) {
+        const double cand_cost = block_reduce_scalar<NW>(acc[kNumAcc - 1], s_part, warp, lane, lmw);
+        if (warp == lmw) lm_after_cost_pass(s_lm, cand_cost, o, lane);
+      } else {
+        block_reduce<NW>(acc, s_part, warp, lane, s_lm.tot[s_lm.ti ^ 1], lmw);
+        if (warp == lmw && (kLmFullWarp || lane == 0)) {
+          if (first) lm_step<true>(s_lm, o, lane, s_pc);
+          else lm_step<false>(s_lm, o, lane, s_pc);
+        }
+      }
+      __syncthreads();
+      if (s_lm.done) break;
+      first = false;
+    }
+  }
+  // drain the copies that were issued ahead: the CTA must not exit with bulk copies in flight
+  while (in_flight > 0) {
+    mbar_wait(&full[c_stage], c_parity);
+    if (++c_stage == S) {
+      c_stage = 0;
+      c_parity ^= 1u;
+    }
+    --in_flight;
+  }
+
+  if (tid == lmt) {
+    // PNECCeres::Result(): q.normalized(), t(theta, phi); pnec_ceres.cc:201-206
+    const LMState &st = s_lm;
+    const double *x = st.pts[st.xi], *sc = st.scs[st.xi];
+    const double qn = sqrt(x[2] * x[2] + x[3] * x[3] + x[4] * x[4] + x[5] * x[5]);
+    const double iq = qn > 0.0 ? 1.0 / qn : 1.0;
+    double *op = args.out_poses + 7 * b;
+    op[0] = x[2] * iq; op[1] = x[3] * iq; op[2] = x[4] * iq; op[3] = x[5] * iq;
+    op[4] = sc[0] * sc[3]; op[5] = sc[0] * sc[2]; op[6] = sc[1];
+    if (args.out_status) args.out_status[b] = st.status;
+    if (args.out_iters) args.out_iters[b] = st.iteration;
+    if (args.out_cost) args.out_cost[b] = st.x_cost;
+    if (args.out_init_cost) args.out_init_cost[b] = st.initial_cost;
+  }
+}
+
 // ---------------------------------------------------------------- eval kernel
 
 struct EvalArgs {
@@ -944,12 +1111,52 @@ void dump_phase_timing(const SolveArgs &a) {
 }
 #endif
 
+template <int V, int NW, int S, int MINB>
+int launch_solve_stream_t(pnec_handle *h, const SolveArgs &a, cudaStream_t stream) {
+  auto kern = solve_stream_kernel<V, NW, S, MINB>;
+  const size_t dyn = static_cast<size_t>(NW) * S * 32 * VariantTraits<V>::kDoubles * 8;
+  PNEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(dyn)));
+  kern<<<static_cast<unsigned>(a.bv.num_problems), NW * 32, dyn, stream>>>(a);
+  PNEC_CUDA(cudaGetLastError());
+  h->launches++;
+  return PNEC_OK;
+}
+
+template <int V>
+int launch_solve_stream_v(pnec_handle *h, const SolveArgs &a, cudaStream_t stream) {
+  switch (env_int("PNEC_B200_STREAM_CFG", 3)) {
+    case 1: return launch_solve_stream_t<V, 6, 4, 2>(h, a, stream);   // 2 CTAs x 6 warps per SM
+    case 2: return launch_solve_stream_t<V, 12, 4, 1>(h, a, stream);  // 1 CTA x 12 warps
+    case 3: return launch_solve_stream_t<V, 4, 4, 3>(h, a, stream);   // 3 CTAs x 4 warps
+    case 4: return launch_solve_stream_t<V, 6, 3, 2>(h, a, stream);
+    default: return fail(PNEC_ERR_INVALID_ARGUMENT, "unknown PNEC_B200_STREAM_CFG");
+  }
+}
+
 int launch_solve(pnec_handle *h, const SolveArgs &a0, int variant, long long max_n,
                  cudaStream_t stream) {
   SolveArgs a = a0;
   if (a.bv.num_problems == 0) return PNEC_OK;
+  // Large frame pairs: stream every pass (bulk-copy rings) instead of keeping one pair per SM
+  // resident.  Needs 16-byte aligned arrays; SYMMETRIC (192 B / correspondence) stays resident-first.
+  const long long stream_min_n = env_int("PNEC_B200_STREAM_MIN_N", 1024);
+  if (bulk_ok(a.bv) && !env_int("PNEC_B200_NO_BULK", 0) && max_n > stream_min_n) {
+    a.use_bulk = 1;
+    a.cap_elems = 0;
+    a.dbg = nullptr;
+    switch (variant) {
+      case PNEC_VARIANT_NEC: return launch_solve_stream_v<PNEC_VARIANT_NEC>(h, a, stream);
+      case PNEC_VARIANT_TARGET: return launch_solve_stream_v<PNEC_VARIANT_TARGET>(h, a, stream);
+      case PNEC_VARIANT_HOST: return launch_solve_stream_v<PNEC_VARIANT_HOST>(h, a, stream);
+      default: return launch_solve_stream_v<PNEC_VARIANT_SYMMETRIC>(h, a, stream);
+    }
+  }
   int nw = env_int("PNEC_B200_SOLVE_WARPS", 0);
-  if (nw == 0) nw = max_n <= 64 ? 1 : max_n <= 192 ? 2 : max_n <= 1024 ? 4 : 8;
+  // Warps per frame pair (measured on B200, tools/nw_sweep.py): the solve is latency-bound, so
+  // what pays is the number of pairs resident per SM, not the width of one pair.  One warp per
+  // pair wins while >= 7 pairs fit in shared memory; 4 warps once only 3 fit.
+  if (nw == 0) nw = max_n <= 320 ? 1 : max_n <= 448 ? 2 : max_n <= 1024 ? 4 : 8;
   const int bpc = bytes_per_corr(variant);
   const size_t cap_bytes = h->smem_optin - kStaticSmemReserve;
   const long long want_elems = ((max_n + 1) + 1) & ~1LL;  // head element + round up to even

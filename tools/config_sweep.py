@@ -52,9 +52,22 @@ b = syn.make_batch(len(counts), 0, seed=4, camera=syn.PINHOLE, counts=counts)
 run("C4 4540x~2000 ragged, max 20 it", b.bvs_host, b.bvs_target, b.covs_target, b.init_poses,
     api.default_opts(api.TARGET, max_num_iterations=20), offsets=b.offsets)
 # C5: correspondence-count sweep at 4096 problems
-for N in (64, 128, 256, 512, 1024, 2048, 4096, 8192):
+for cfg in ("1", "2", "3", "4"):
+    os.environ["PNEC_B200_STREAM_CFG"] = cfg
+    run(f"C4 stream cfg {cfg}", b.bvs_host, b.bvs_target, b.covs_target, b.init_poses,
+        api.default_opts(api.TARGET, max_num_iterations=20), offsets=b.offsets)
+os.environ.pop("PNEC_B200_STREAM_CFG")
+os.environ["PNEC_B200_STREAM_MIN_N"] = "100000000"
+run("C4 resident/global path", b.bvs_host, b.bvs_target, b.covs_target, b.init_poses,
+    api.default_opts(api.TARGET, max_num_iterations=20), offsets=b.offsets)
+os.environ.pop("PNEC_B200_STREAM_MIN_N")
+for N in (64, 128, 256, 512, 768, 1024, 2048, 4096, 8192):
     base = syn.make_batch(128 if N <= 1024 else 32, N, seed=5)
     run(f"C5 4096x{N}", *tile_batch(base, 4096), opts, n_per_problem=N)
+    if 512 <= N <= 2048:
+        os.environ["PNEC_B200_STREAM_MIN_N"] = "100000000" if N > 940 else "0"
+        run(f"C5 4096x{N} other path ({'resident' if N > 940 else 'stream'})", *tile_batch(base, 4096), opts, n_per_problem=N)
+        os.environ.pop("PNEC_B200_STREAM_MIN_N")
 # unscented transform: one covariance per C2 correspondence
 n = 10000 * 512
 rng = np.random.default_rng(0)
