@@ -54,6 +54,21 @@ __device__ __forceinline__ void sym_mul(const double c[9], const double v[3], do
   o[2] = xz * v[0] + yz * v[1] + c[8] * v[2];
 }
 
+// Packed symmetric part (xx, xy, xz, yy, yz, zz) of a column-major 3x3.
+__device__ __forceinline__ void pack_sym(const double c[9], double s[6]) {
+  s[0] = c[0];
+  s[1] = 0.5 * (c[1] + c[3]);
+  s[2] = 0.5 * (c[2] + c[6]);
+  s[3] = c[4];
+  s[4] = 0.5 * (c[5] + c[7]);
+  s[5] = c[8];
+}
+__device__ __forceinline__ void sym_mul6(const double s[6], const double v[3], double o[3]) {
+  o[0] = s[0] * v[0] + s[1] * v[1] + s[2] * v[2];
+  o[1] = s[1] * v[0] + s[3] * v[1] + s[4] * v[2];
+  o[2] = s[2] * v[0] + s[4] * v[1] + s[5] * v[2];
+}
+
 // Per-problem constants of one evaluation point.
 struct PoseConst {
   double R[9];    // Eigen::Quaternion::toRotationMatrix(), q taken as stored
@@ -122,12 +137,13 @@ __device__ __forceinline__ void state_plus(const double x[6], const double d[5],
 // SYMMETRIC  s2 = b^T S2 b + c^T S1 c + reg,  c = t x h,  h = g
 //            (1/2) d(c^T S c)/dt = h x (S c)  (1/2) d(c^T S c)/dw = (t.h) S c - (S c . h) t
 //   r = e / s,   dr = (de - (e / s2) (1/2) ds2) / s
+// Covariances arrive as their packed symmetric part (pack_sym): x^T S x only sees sym(S).
 // The row returned is (dr/dtheta, dr/dphi, dr/dw) — the quaternion tangent
 // columns are 2 dr/dw; the factor is applied once after the reduction.
 template <int V>
 __device__ __forceinline__ void residual_row(const PoseConst &pc, double reg, const double f1[3],
-                                             const double f2[3], const double ct[9],
-                                             const double ch[9], double &r, double row[5]) {
+                                             const double f2[3], const double ct[6],
+                                             const double ch[6], double &r, double row[5]) {
   double g[3], a[3];
   rot(pc.R, f2, g);
   cross3(pc.t, f1, a);
@@ -140,7 +156,7 @@ __device__ __forceinline__ void residual_row(const PoseConst &pc, double reg, co
   } else if (V == PNEC_VARIANT_TARGET) {
     double b[3], Sb[3], RSb[3], p[3];
     rot_t(pc.R, a, b);
-    sym_mul(ct, b, Sb);
+    sym_mul6(ct, b, Sb);
     const double s2 = dot3(b, Sb) + reg;
     const double is = rsqrt(s2);
     r = e * is;
@@ -157,7 +173,7 @@ __device__ __forceinline__ void residual_row(const PoseConst &pc, double reg, co
     if (V == PNEC_VARIANT_SYMMETRIC) {
       double b[3], Sb[3], RSb[3];
       rot_t(pc.R, a, b);
-      sym_mul(ct, b, Sb);
+      sym_mul6(ct, b, Sb);
       s2 += dot3(b, Sb);
       rot(pc.R, Sb, RSb);
       cross3(f1, RSb, hdt);
@@ -170,7 +186,7 @@ __device__ __forceinline__ void residual_row(const PoseConst &pc, double reg, co
       h[0] = g[0]; h[1] = g[1]; h[2] = g[2];
     }
     cross3(pc.t, h, c);
-    sym_mul(V == PNEC_VARIANT_HOST ? ct : ch, c, Sc);
+    sym_mul6(V == PNEC_VARIANT_HOST ? ct : ch, c, Sc);
     s2 += dot3(c, Sc);
     cross3(h, Sc, hx);
     const double th = dot3(pc.t, h), sh = dot3(Sc, h);
@@ -201,8 +217,8 @@ __device__ __forceinline__ void residual_row(const PoseConst &pc, double reg, co
 // Residual only (cost passes of the LM loop): same expressions as residual_row.
 template <int V>
 __device__ __forceinline__ double residual_only(const PoseConst &pc, double reg, const double f1[3],
-                                                const double f2[3], const double ct[9],
-                                                const double ch[9]) {
+                                                const double f2[3], const double ct[6],
+                                                const double ch[6]) {
   double g[3], a[3];
   rot(pc.R, f2, g);
   cross3(pc.t, f1, a);
@@ -212,7 +228,7 @@ __device__ __forceinline__ double residual_only(const PoseConst &pc, double reg,
   if (V == PNEC_VARIANT_TARGET || V == PNEC_VARIANT_SYMMETRIC) {
     double b[3], Sb[3];
     rot_t(pc.R, a, b);
-    sym_mul(ct, b, Sb);
+    sym_mul6(ct, b, Sb);
     s2 = dot3(b, Sb) + reg;
   }
   if (V == PNEC_VARIANT_HOST || V == PNEC_VARIANT_SYMMETRIC) {
@@ -223,7 +239,7 @@ __device__ __forceinline__ double residual_only(const PoseConst &pc, double reg,
       h[0] = g[0]; h[1] = g[1]; h[2] = g[2];
     }
     cross3(pc.t, h, c);
-    sym_mul(V == PNEC_VARIANT_HOST ? ct : ch, c, Sc);
+    sym_mul6(V == PNEC_VARIANT_HOST ? ct : ch, c, Sc);
     s2 += dot3(c, Sc);
   }
   return e * rsqrt(s2);

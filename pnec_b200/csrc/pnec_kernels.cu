@@ -51,22 +51,27 @@ struct VariantTraits {
   static constexpr int kDoubles = 6 + (kHasCt ? 9 : 0) + (kHasCh ? 9 : 0);
 };
 
-// One correspondence from (f1, f2, ct, ch) arrays at element index i.
+// One correspondence from raw (f1, f2, ct, ch) arrays at element index i; the 3x3 covariances
+// are reduced to their packed symmetric part on the way in.
 template <int V>
 __device__ __forceinline__ void load_corr(const double *f1, const double *f2, const double *ct,
                                           const double *ch, long long i, double a1[3],
-                                          double a2[3], double c1[9], double c2[9]) {
+                                          double a2[3], double s1[6], double s2[6]) {
 #pragma unroll
   for (int k = 0; k < 3; ++k) a1[k] = f1[3 * i + k];
 #pragma unroll
   for (int k = 0; k < 3; ++k) a2[k] = f2[3 * i + k];
   if (VariantTraits<V>::kHasCt) {
+    double c[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) c1[k] = ct[9 * i + k];
+    for (int k = 0; k < 9; ++k) c[k] = ct[9 * i + k];
+    pack_sym(c, s1);
   }
   if (VariantTraits<V>::kHasCh) {
+    double c[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) c2[k] = ch[9 * i + k];
+    for (int k = 0; k < 9; ++k) c[k] = ch[9 * i + k];
+    pack_sym(c, s2);
   }
 }
 
@@ -75,7 +80,7 @@ __device__ __forceinline__ void eval_pass(const PoseConst &pc, double reg, const
                                           const double *f2, const double *ct, const double *ch,
                                           int begin, int end, int tid, double acc[kNumAcc]) {
   for (int i = begin + tid; i < end; i += NT) {
-    double a1[3], a2[3], c1[9], c2[9], r, row[5];
+    double a1[3], a2[3], c1[6], c2[6], r, row[5];
     load_corr<V>(f1, f2, ct, ch, i, a1, a2, c1, c2);
     residual_row<V>(pc, reg, a1, a2, c1, c2, r, row);
     accumulate(acc, r, row);
@@ -88,7 +93,7 @@ __device__ __forceinline__ double eval_pass_cost(const PoseConst &pc, double reg
                                                  const double *ch, int begin, int end, int tid) {
   double sum = 0.0;
   for (int i = begin + tid; i < end; i += NT) {
-    double a1[3], a2[3], c1[9], c2[9];
+    double a1[3], a2[3], c1[6], c2[6];
     load_corr<V>(f1, f2, ct, ch, i, a1, a2, c1, c2);
     const double r = residual_only<V>(pc, reg, a1, a2, c1, c2);
     sum = fma(r, r, sum);
@@ -211,6 +216,51 @@ struct SolveArgs {
   long long *dbg; // PNEC_PHASE_TIMING builds only: per-CTA cycle counters
 };
 
+// PNECCeres::InitValues(orientation, translation) (pnec_ceres.cc:188-192) + the start state of
+// the minimiser; called by one thread.
+__device__ __forceinline__ void solve_init_state(const SolveArgs &args, long long b, int n,
+                                                 LMState &st, PoseConst &s_pc) {
+  const double *p = args.bv.poses + 7 * b;
+  double *x = st.pts[0], *sc = st.scs[0];
+  angles_from_vec(p + 4, x[0], x[1]);
+  x[2] = p[0]; x[3] = p[1]; x[4] = p[2]; x[5] = p[3];
+  sincos(x[0], &sc[0], &sc[1]);
+  sincos(x[1], &sc[2], &sc[3]);
+  st.inv_radius = 1.0 / args.o.initial_trust_region_radius;
+  st.decrease_factor = 2.0;
+  st.inv_model_cost_change = 0.0;
+  st.x_cost = 0.0;
+  st.initial_cost = 0.0;
+  st.xi = 0;
+  st.ti = 0;
+  st.iteration = 0;
+  st.num_invalid = 0;
+  st.reuse_diagonal = 0;
+  st.step_successful = 1;
+  st.grad_converged = 0;
+  st.status = (n <= 0) ? PNEC_STATUS_EMPTY : PNEC_STATUS_MAX_ITERATIONS;
+  st.done = (n <= 0) ? 1 : 0;
+  st.pass_mode = kPassFull;
+  PoseConst pc0;
+  make_pose_const_sc(sc, x + 2, pc0);
+  s_pc = pc0;
+}
+
+// PNECCeres::Result(): q.normalized(), t(theta, phi) (pnec_ceres.cc:201-206) + the summary.
+__device__ __forceinline__ void solve_write_result(const SolveArgs &args, long long b,
+                                                   const LMState &st) {
+  const double *x = st.pts[st.xi], *sc = st.scs[st.xi];
+  const double qn = sqrt(x[2] * x[2] + x[3] * x[3] + x[4] * x[4] + x[5] * x[5]);
+  const double iq = qn > 0.0 ? 1.0 / qn : 1.0;
+  double *op = args.out_poses + 7 * b;
+  op[0] = x[2] * iq; op[1] = x[3] * iq; op[2] = x[4] * iq; op[3] = x[5] * iq;
+  op[4] = sc[0] * sc[3]; op[5] = sc[0] * sc[2]; op[6] = sc[1];
+  if (args.out_status) args.out_status[b] = st.status;
+  if (args.out_iters) args.out_iters[b] = st.iteration;
+  if (args.out_cost) args.out_cost[b] = st.x_cost;
+  if (args.out_init_cost) args.out_init_cost[b] = st.initial_cost;
+}
+
 extern __shared__ __align__(16) double dyn_smem[];
 
 template <int V, int NW, int MINB>
@@ -248,32 +298,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) solve_kernel(const __grid_const
     // get the HBM -> shared-memory copies going before the scalar set-up below
     if (n > 0 && resident && args.use_bulk)
       issue_bulk<V>(args.bv, g0, span, sf1, sf2, sct, sch, &s_bar);
-    // PNECCeres::InitValues(orientation, translation), pnec_ceres.cc:188-192
-    const double *p = args.bv.poses + 7 * b;
-    LMState &st = s_lm;
-    double *x = st.pts[0], *sc = st.scs[0];
-    angles_from_vec(p + 4, x[0], x[1]);
-    x[2] = p[0]; x[3] = p[1]; x[4] = p[2]; x[5] = p[3];
-    sincos(x[0], &sc[0], &sc[1]);
-    sincos(x[1], &sc[2], &sc[3]);
-    st.inv_radius = 1.0 / o.initial_trust_region_radius;
-    st.decrease_factor = 2.0;
-    st.inv_model_cost_change = 0.0;
-    st.x_cost = 0.0;
-    st.initial_cost = 0.0;
-    st.xi = 0;
-    st.ti = 0;
-    st.iteration = 0;
-    st.num_invalid = 0;
-    st.reuse_diagonal = 0;
-    st.step_successful = 1;
-    st.grad_converged = 0;
-    st.status = (n <= 0) ? PNEC_STATUS_EMPTY : PNEC_STATUS_MAX_ITERATIONS;
-    st.done = (n <= 0) ? 1 : 0;
-    st.pass_mode = kPassFull;
-    PoseConst pc0;
-    make_pose_const_sc(sc, x + 2, pc0);
-    s_pc = pc0;
+    solve_init_state(args, b, n, s_lm, s_pc);
   }
   __syncthreads();
 
@@ -348,25 +373,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) solve_kernel(const __grid_const
 #endif
   }
 
-  if (tid == lmt) {
-    // PNECCeres::Result(): q.normalized(), t(theta, phi); pnec_ceres.cc:201-206
-    const LMState &st = s_lm;
-    const double *x = st.pts[st.xi], *sc = st.scs[st.xi];
-    const double qn = sqrt(x[2] * x[2] + x[3] * x[3] + x[4] * x[4] + x[5] * x[5]);
-    const double iq = qn > 0.0 ? 1.0 / qn : 1.0;
-    double *op = args.out_poses + 7 * b;
-    op[0] = x[2] * iq; op[1] = x[3] * iq; op[2] = x[4] * iq; op[3] = x[5] * iq;
-    op[4] = sc[0] * sc[3]; op[5] = sc[0] * sc[2]; op[6] = sc[1];
-    if (args.out_status) args.out_status[b] = st.status;
-    if (args.out_iters) args.out_iters[b] = st.iteration;
-    if (args.out_cost) args.out_cost[b] = st.x_cost;
-    if (args.out_init_cost) args.out_init_cost[b] = st.initial_cost;
-  }
+  if (tid == lmt) solve_write_result(args, b, s_lm);
 }
 
 // ------------------------------------------------------ solve kernel, streaming
 //
-// Same LM solve for frame pairs too large to keep 2+ of them resident per SM (N > 1024):
+// Same LM solve for frame pairs too large to keep 2+ of them resident per SM (N > 896):
 // nothing is resident.  Warp w owns tiles w, w + NW, ... of the pair and a private S-stage
 // ring; lane 0 keeps the ring S tiles ahead with bulk async copies and simply wraps around
 // at the end of a pass, so the first tiles of the NEXT pass are already in flight while the
@@ -425,32 +437,7 @@ solve_stream_kernel(const __grid_constant__ SolveArgs args) {
   }
 
   if (tid == lmt) {
-    // PNECCeres::InitValues(orientation, translation), pnec_ceres.cc:188-192
-    const double *p = args.bv.poses + 7 * b;
-    LMState &st = s_lm;
-    double *x = st.pts[0], *sc = st.scs[0];
-    angles_from_vec(p + 4, x[0], x[1]);
-    x[2] = p[0]; x[3] = p[1]; x[4] = p[2]; x[5] = p[3];
-    sincos(x[0], &sc[0], &sc[1]);
-    sincos(x[1], &sc[2], &sc[3]);
-    st.inv_radius = 1.0 / o.initial_trust_region_radius;
-    st.decrease_factor = 2.0;
-    st.inv_model_cost_change = 0.0;
-    st.x_cost = 0.0;
-    st.initial_cost = 0.0;
-    st.xi = 0;
-    st.ti = 0;
-    st.iteration = 0;
-    st.num_invalid = 0;
-    st.reuse_diagonal = 0;
-    st.step_successful = 1;
-    st.grad_converged = 0;
-    st.status = (n <= 0) ? PNEC_STATUS_EMPTY : PNEC_STATUS_MAX_ITERATIONS;
-    st.done = (n <= 0) ? 1 : 0;
-    st.pass_mode = kPassFull;
-    PoseConst pc0;
-    make_pose_const_sc(sc, x + 2, pc0);
-    s_pc = pc0;
+    solve_init_state(args, b, n, s_lm, s_pc);
   }
   __syncthreads();
 
@@ -470,7 +457,7 @@ solve_stream_kernel(const __grid_constant__ SolveArgs args) {
         const double *base = ring + c_stage * kStageDoubles;
         const int idx = (warp + i * NW) * T + lane;
         const bool valid = (idx >= head) && (idx < span);
-        double a1[3], a2[3], c1[9], c2[9];
+        double a1[3], a2[3], c1[6], c2[6];
         if (valid) load_corr<V>(base, base + 3 * T, base + 6 * T, base + 15 * T, lane, a1, a2, c1, c2);
         __syncwarp();  // the stage may be refilled
         --in_flight;
@@ -515,20 +502,7 @@ solve_stream_kernel(const __grid_constant__ SolveArgs args) {
     --in_flight;
   }
 
-  if (tid == lmt) {
-    // PNECCeres::Result(): q.normalized(), t(theta, phi); pnec_ceres.cc:201-206
-    const LMState &st = s_lm;
-    const double *x = st.pts[st.xi], *sc = st.scs[st.xi];
-    const double qn = sqrt(x[2] * x[2] + x[3] * x[3] + x[4] * x[4] + x[5] * x[5]);
-    const double iq = qn > 0.0 ? 1.0 / qn : 1.0;
-    double *op = args.out_poses + 7 * b;
-    op[0] = x[2] * iq; op[1] = x[3] * iq; op[2] = x[4] * iq; op[3] = x[5] * iq;
-    op[4] = sc[0] * sc[3]; op[5] = sc[0] * sc[2]; op[6] = sc[1];
-    if (args.out_status) args.out_status[b] = st.status;
-    if (args.out_iters) args.out_iters[b] = st.iteration;
-    if (args.out_cost) args.out_cost[b] = st.x_cost;
-    if (args.out_init_cost) args.out_init_cost[b] = st.initial_cost;
-  }
+  if (tid == lmt) solve_write_result(args, b, s_lm);
 }
 
 // ---------------------------------------------------------------- eval kernel
@@ -603,7 +577,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(const __grid_consta
     }
     const int i = k * T + tid;
     const bool valid = (i >= head) && (i < span);
-    double a1[3], a2[3], c1[9], c2[9];
+    double a1[3], a2[3], c1[6], c2[6];
     if (valid) load_corr<V>(stage_f1(st), stage_f2(st), stage_ct(st), stage_ch(st), tid, a1, a2, c1, c2);
     __syncthreads();  // every thread holds its correspondence: the stage may be refilled
     if (tid == 0 && args.use_bulk && k + S < ntiles) issue_tile(k + S);
@@ -728,7 +702,7 @@ eval_warp_kernel(const __grid_constant__ EvalArgs args) {
       const double *base = ring + st * kStageDoubles;
       const int i = k * T + lane;
       const bool valid = (i >= head) && (i < span);
-      double a1[3], a2[3], c1[9], c2[9];
+      double a1[3], a2[3], c1[6], c2[6];
       if (valid) load_corr<V>(base, base + 3 * T, base + 6 * T, base + 15 * T, lane, a1, a2, c1, c2);
       __syncwarp();  // every lane holds its correspondence: the stage may be refilled
       producer_issue();
@@ -1140,7 +1114,7 @@ int launch_solve(pnec_handle *h, const SolveArgs &a0, int variant, long long max
   if (a.bv.num_problems == 0) return PNEC_OK;
   // Large frame pairs: stream every pass (bulk-copy rings) instead of keeping one pair per SM
   // resident.  Needs 16-byte aligned arrays; SYMMETRIC (192 B / correspondence) stays resident-first.
-  const long long stream_min_n = env_int("PNEC_B200_STREAM_MIN_N", 1024);
+  const long long stream_min_n = env_int("PNEC_B200_STREAM_MIN_N", 896);
   if (bulk_ok(a.bv) && !env_int("PNEC_B200_NO_BULK", 0) && max_n > stream_min_n) {
     a.use_bulk = 1;
     a.cap_elems = 0;

@@ -123,11 +123,11 @@ def test_solve_and_eval_against_oracle(handle, vname, B, N, camera):
 def test_ragged_batch_with_edge_sizes(handle, path, monkeypatch):
     """Empty problems, single correspondences, odd offsets, sizes around tile and
     resident-capacity boundaries, one problem larger than shared memory.  Run through both
-    solve kernels: the streaming one (default once a problem exceeds 1024 correspondences) and
-    the shared-memory-resident one with its global-memory fallback for oversized problems."""
-    monkeypatch.setenv("PNEC_B200_STREAM_MIN_N", "1024" if path == "stream" else "100000000")
+    solve kernels: the streaming one (default once a pair exceeds 896 correspondences) and
+    the shared-memory-resident one with its global-memory fallback for oversized pairs."""
     counts = np.array([0, 1, 2, 3, 5, 0, 31, 32, 33, 63, 64, 65, 127, 128, 129, 255, 257, 511, 513,
                        1000, 1023, 1887, 1889, 1890, 1891, 2500, 0, 77, 4100, 6])
+    monkeypatch.setenv("PNEC_B200_STREAM_MIN_N", "896" if path == "stream" else "100000000")
     B = len(counts)
     b = syn.make_batch(B, 0, seed=77, counts=counts)
     res = handle.solve_batch(dev(b.bvs_host), dev(b.bvs_target), dev(b.covs_target), None,

@@ -14,13 +14,13 @@ def timeit(fn, reps=20, warm=3):
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / reps
 opts = api.default_opts(api.TARGET)
-for N, B in ((32, 16384), (64, 16384), (128, 16384), (256, 12500), (384, 10000), (512, 10000), (768, 8192), (1024, 4096)):
+for N, B in ((64, 16384), (128, 16384), (256, 12500), (384, 10000), (512, 10000), (640, 8192), (768, 8192), (1024, 4096), (1536, 4096), (2048, 4096)):
     base = syn.make_batch(256, N, seed=5)
     rep = (B + 255) // 256
     f = lambda a, per: T(np.tile(a, (rep, 1))[: B * per])
     d = (f(base.bvs_host, N), f(base.bvs_target, N), f(base.covs_target, N), f(base.init_poses, 1))
     out = []
-    for nw in (1, 2, 4, 8):
+    for nw in (1, 2, 3, 4, 8):
         os.environ["PNEC_B200_SOLVE_WARPS"] = str(nw)
         os.environ["PNEC_B200_STREAM_MIN_N"] = "100000000"
         try:
@@ -28,4 +28,7 @@ for N, B in ((32, 16384), (64, 16384), (128, 16384), (256, 12500), (384, 10000),
             out.append(f"nw{nw}: {ms:.4f} ms ({B/ms/1e3:.1f}M/s)")
         except Exception as e:
             out.append(f"nw{nw}: fail")
+    os.environ.pop("PNEC_B200_SOLVE_WARPS"); os.environ["PNEC_B200_STREAM_MIN_N"] = "0"
+    ms = timeit(lambda: h.solve_batch(d[0], d[1], d[2], None, d[3], opts, n_per_problem=N))
+    out.append(f"stream: {ms:.4f}")
     print(f"N={N:5d} B={B:6d}  " + "  ".join(out), flush=True)
