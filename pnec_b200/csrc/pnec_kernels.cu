@@ -1104,6 +1104,10 @@ int launch_solve_stream_v(pnec_handle *h, const SolveArgs &a, cudaStream_t strea
     case 2: return launch_solve_stream_t<V, 12, 4, 1>(h, a, stream);  // 1 CTA x 12 warps
     case 3: return launch_solve_stream_t<V, 4, 4, 3>(h, a, stream);   // 3 CTAs x 4 warps
     case 4: return launch_solve_stream_t<V, 6, 3, 2>(h, a, stream);
+    case 5: return launch_solve_stream_t<V, 1, 4, 12>(h, a, stream);  // one warp per pair, 12 pairs per SM
+    case 6: return launch_solve_stream_t<V, 2, 4, 6>(h, a, stream);
+    case 7: return launch_solve_stream_t<V, 1, 3, 12>(h, a, stream);
+    case 8: return launch_solve_stream_t<V, 1, 6, 8>(h, a, stream);
     default: return fail(PNEC_ERR_INVALID_ARGUMENT, "unknown PNEC_B200_STREAM_CFG");
   }
 }

@@ -1,0 +1,28 @@
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from pnec_b200 import api, synthetic as syn
+dev = torch.device("cuda", 0); h = api.Handle(0)
+T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+def timeit(fn, reps=20, warm=3):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps): fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+opts = api.default_opts(api.TARGET)
+for N, B in ((256, 12500), (512, 10000), (768, 8192), (1024, 4096), (2048, 4096)):
+    base = syn.make_batch(500, N, seed=5)
+    rep = (B + 499) // 500
+    f = lambda a, per: T(np.tile(a, (rep, 1))[: B * per])
+    d = (f(base.bvs_host, N), f(base.bvs_target, N), f(base.covs_target, N), f(base.init_poses, 1))
+    out = []
+    os.environ["PNEC_B200_STREAM_MIN_N"] = "100000000"
+    ms = timeit(lambda: h.solve_batch(d[0], d[1], d[2], None, d[3], opts, n_per_problem=N)); out.append(f"resident {ms:.4f}")
+    os.environ["PNEC_B200_STREAM_MIN_N"] = "0"
+    for cfg in ("3", "5", "6", "7", "8"):
+        os.environ["PNEC_B200_STREAM_CFG"] = cfg
+        ms = timeit(lambda: h.solve_batch(d[0], d[1], d[2], None, d[3], opts, n_per_problem=N)); out.append(f"cfg{cfg} {ms:.4f}")
+    print(f"N={N} B={B}: " + "  ".join(out), flush=True)
