@@ -611,19 +611,21 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(const __grid_consta
 // cross-lane traffic is the transposing reduction once per problem.  Pose
 // constants (acos/atan2/sincos, the expensive scalar part) are prepared
 // lane-parallel for CHUNK problems at a time.
-template <int V, int WPC, int S, int CHUNK, int MINB>
+template <int V, int WPC, int S, int CHUNK, int MINB, int T>
 __global__ void __launch_bounds__(WPC * 32, MINB)
 eval_warp_kernel(const __grid_constant__ EvalArgs args) {
-  constexpr int T = 32;
+  static_assert(T % 32 == 0, "tiles are whole warps of correspondences");
   constexpr int kStageDoubles = T * VariantTraits<V>::kDoubles;
+  constexpr bool kCt = VariantTraits<V>::kHasCt, kCh = VariantTraits<V>::kHasCh;
   __shared__ __align__(8) uint64_t s_full[WPC][S];
   __shared__ PoseConst s_pcs[WPC][CHUNK];
 
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
   const long long W = static_cast<long long>(gridDim.x) * WPC;
   const long long gw = static_cast<long long>(blockIdx.x) * WPC + warp;
   const long long B = args.bv.num_problems;
-  const long long nmine = (B > gw) ? (B - gw + W - 1) / W : 0;
+  const int nmine = (B > gw) ? static_cast<int>((B - gw + W - 1) / W) : 0;
   double *ring = dyn_smem + static_cast<size_t>(warp) * S * kStageDoubles;
   uint64_t *full = s_full[warp];
 
@@ -634,34 +636,63 @@ eval_warp_kernel(const __grid_constant__ EvalArgs args) {
   }
   __syncwarp();
 
-  // producer cursor (uniform across the warp; only lane 0 issues)
-  long long pj = 0, pg0 = 0;
-  int ptile = 0, pntiles = 0, pspan = 0;
+  // ---- producer cursor (uniform across the warp; lane 0 issues).  Running pointers to the
+  // next tile of the current producer problem, elements left in it, next ring stage.
+  int pj = 0, p_left = 0, p_stage = 0;
+  const double *p_f1 = nullptr, *p_f2 = nullptr, *p_ct = nullptr, *p_ch = nullptr;
   auto producer_open = [&]() {  // position on the first tile of the next non-empty problem
     while (pj < nmine) {
       long long s, e;
       problem_range(args.bv, gw + pj * W, s, e);
       if (e > s) {
-        pg0 = s & ~1LL;
-        pspan = static_cast<int>(e - pg0);
-        pntiles = (pspan + T - 1) / T;
-        ptile = 0;
+        const long long g0 = s & ~1LL;  // even => 16-byte aligned in every array
+        p_left = static_cast<int>(e - g0);
+        p_f1 = args.bv.f1 + 3 * g0;
+        p_f2 = args.bv.f2 + 3 * g0;
+        if (kCt) p_ct = args.bv.ct + 9 * g0;
+        if (kCh) p_ch = args.bv.ch + 9 * g0;
         return;
       }
       ++pj;
     }
   };
-  long long issued = 0;
   auto producer_issue = [&]() {  // issue the current producer tile, then advance
     if (pj >= nmine) return;
-    const int st = static_cast<int>(issued % S);
-    double *base = ring + st * kStageDoubles;
+    const int cnt = min(T, p_left);
     if (lane == 0) {
-      issue_bulk<V>(args.bv, pg0 + static_cast<long long>(ptile) * T, min(T, pspan - ptile * T),
-                    base, base + 3 * T, base + 6 * T, base + 15 * T, &full[st]);
+      double *base = ring + p_stage * kStageDoubles;
+      int cb = cnt + (cnt & 1);  // bulk copies move 16-byte units: round up to an even count ...
+      if ((cnt & 1) && p_f1 + 3 * cb > args.bv.f1 + 3 * args.bv.total) {
+        cb = cnt - 1;  // ... unless that runs past the end of the batch: last element by hand
+#pragma unroll
+        for (int k = 0; k < 3; ++k) base[3 * cb + k] = p_f1[3 * cb + k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) base[3 * T + 3 * cb + k] = p_f2[3 * cb + k];
+        if (kCt) {
+#pragma unroll
+          for (int k = 0; k < 9; ++k) base[6 * T + 9 * cb + k] = p_ct[9 * cb + k];
+        }
+        if (kCh) {
+#pragma unroll
+          for (int k = 0; k < 9; ++k) base[15 * T + 9 * cb + k] = p_ch[9 * cb + k];
+        }
+      }
+      mbar_arrive_expect_tx(&full[p_stage], static_cast<uint32_t>(cb) * 8u * VariantTraits<V>::kDoubles);
+      if (cb > 0) {
+        bulk_g2s(base, p_f1, cb * 24u, &full[p_stage]);
+        bulk_g2s(base + 3 * T, p_f2, cb * 24u, &full[p_stage]);
+        if (kCt) bulk_g2s(base + 6 * T, p_ct, cb * 72u, &full[p_stage]);
+        if (kCh) bulk_g2s(base + 15 * T, p_ch, cb * 72u, &full[p_stage]);
+      }
     }
-    ++issued;
-    if (++ptile == pntiles) {
+    p_stage = (p_stage + 1 == S) ? 0 : p_stage + 1;
+    p_left -= T;
+    if (p_left > 0) {
+      p_f1 += 3 * T;
+      p_f2 += 3 * T;
+      if (kCt) p_ct += 9 * T;
+      if (kCh) p_ch += 9 * T;
+    } else {
       ++pj;
       producer_open();
     }
@@ -670,8 +701,9 @@ eval_warp_kernel(const __grid_constant__ EvalArgs args) {
 #pragma unroll 1
   for (int i = 0; i < S; ++i) producer_issue();
 
-  long long consumed = 0;
-  for (long long j = 0; j < nmine; ++j) {
+  int c_stage = 0;
+  uint32_t c_parity = 0;
+  for (int j = 0; j < nmine; ++j) {
     if (j % CHUNK == 0) {
       __syncwarp();
       if (lane < CHUNK && j + lane < nmine) {
@@ -689,29 +721,48 @@ eval_warp_kernel(const __grid_constant__ EvalArgs args) {
     long long s, e;
     problem_range(args.bv, prob, s, e);
     const int head = static_cast<int>(s & 1LL);
-    const int span = static_cast<int>(e - s) + head;
-    const int ntiles = (e > s) ? (span + T - 1) / T : 0;
+    int c_left = (e > s) ? static_cast<int>(e - s) + head : 0;  // elements left, head included
     PoseConst pc;
     load_pose_const(s_pcs[warp][j % CHUNK], pc);
     double acc[kNumAcc];
 #pragma unroll
     for (int i = 0; i < kNumAcc; ++i) acc[i] = 0.0;
-    for (int k = 0; k < ntiles; ++k) {
-      const int st = static_cast<int>(consumed % S);
-      mbar_wait(&full[st], static_cast<uint32_t>((consumed / S) & 1));
-      const double *base = ring + st * kStageDoubles;
-      const int i = k * T + lane;
-      const bool valid = (i >= head) && (i < span);
-      double a1[3], a2[3], c1[6], c2[6];
-      if (valid) load_corr<V>(base, base + 3 * T, base + 6 * T, base + 15 * T, lane, a1, a2, c1, c2);
-      __syncwarp();  // every lane holds its correspondence: the stage may be refilled
-      producer_issue();
-      ++consumed;
-      if (valid) {
-        double r, row[5];
-        residual_row<V>(pc, args.reg, a1, a2, c1, c2, r, row);
-        accumulate(acc, r, row);
+    int lo = head;  // first valid element of the tile: head on the first tile, 0 afterwards
+    while (c_left > 0) {
+      mbar_wait(&full[c_stage], c_parity);
+      const double *base = ring + c_stage * kStageDoubles;
+      if (T == 32) {
+        const bool valid = (lane >= lo) && (lane < c_left);
+        double a1[3], a2[3], c1[6], c2[6];
+        if (valid) load_corr<V>(base, base + 3 * T, base + 6 * T, base + 15 * T, lane, a1, a2, c1, c2);
+        __syncwarp();  // every lane holds its correspondence: the stage may be refilled
+        producer_issue();
+        if (valid) {
+          double r, row[5];
+          residual_row<V>(pc, args.reg, a1, a2, c1, c2, r, row);
+          accumulate(acc, r, row);
+        }
+      } else {
+        // wider tiles (larger bulk copies): the warp walks the tile 32 correspondences at a time
+#pragma unroll 1
+        for (int sub = 0; sub < T; sub += 32) {
+          const int i = sub + lane;
+          if ((i >= lo) && (i < c_left)) {
+            double a1[3], a2[3], c1[6], c2[6], r, row[5];
+            load_corr<V>(base, base + 3 * T, base + 6 * T, base + 15 * T, i, a1, a2, c1, c2);
+            residual_row<V>(pc, args.reg, a1, a2, c1, c2, r, row);
+            accumulate(acc, r, row);
+          }
+        }
+        __syncwarp();
+        producer_issue();
       }
+      if (++c_stage == S) {
+        c_stage = 0;
+        c_parity ^= 1u;
+      }
+      c_left -= T;
+      lo = 0;
     }
     const double v = warp_transpose_reduce(acc, lane);
     const int idx = warp_reduce_owner_index(lane);
@@ -775,16 +826,12 @@ struct UtArgs {
   double Kinv[9];  // column-major
   double kappa;
   int camera_model;
+  int use_bulk;  // mus / covs / out 16-byte aligned
 };
 
-__global__ void __launch_bounds__(128) unscented_kernel(const __grid_constant__ UtArgs a) {
-  const long long i = static_cast<long long>(blockIdx.x) * 128 + threadIdx.x;
-  if (i >= a.n) return;
-  double mu[3], S[9];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) mu[k] = a.mus[3 * i + k];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) S[k] = a.covs[9 * i + k];  // S[c * 3 + r]
+// The transform of one point: mu[3], S[9] (column-major) -> out[9] (column-major).
+__device__ __forceinline__ void unscented_point(const UtArgs &a, const double mu[3], const double S[9],
+                                                double out[9]) {
   const bool omni = (a.camera_model == PNEC_CAMERA_OMNIDIRECTIONAL);
   // C = [c0 c1 0]: image-plane Cholesky columns (rotated for omnidirectional cameras)
   double c0[3], c1[3];
@@ -843,7 +890,8 @@ __global__ void __launch_bounds__(128) unscented_kernel(const __grid_constant__ 
       mean[k] += w * tp[p][k];
     }
   }
-  double out[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int k = 0; k < 9; ++k) out[k] = 0.0;
 #pragma unroll
   for (int p = 0; p < 5; ++p) {
     const double w = (p == 0) ? w0 : wi;
@@ -853,8 +901,56 @@ __global__ void __launch_bounds__(128) unscented_kernel(const __grid_constant__ 
 #pragma unroll
       for (int r = 0; r < 3; ++r) out[c * 3 + r] += w * d[r] * d[c];
   }
+}
+
+// One CTA per tile of 128 points.  Full, 16-byte aligned tiles go through the TMA engine both
+// ways: two bulk loads (3 KB of points, 9 KB of covariances) into shared memory, each thread
+// transforms its point, results are staged over the covariance tile and leave as one 9 KB
+// bulk store.  The last partial tile (and unaligned arrays) use plain per-thread accesses.
+__global__ void __launch_bounds__(128) unscented_kernel(const __grid_constant__ UtArgs a) {
+  constexpr int T = 128;
+  __shared__ __align__(16) double s_mu[3 * T];
+  __shared__ __align__(16) double s_cov[9 * T];
+  __shared__ __align__(8) uint64_t s_bar;
+  const int tid = threadIdx.x;
+  const long long first = static_cast<long long>(blockIdx.x) * T;
+  const int cnt = static_cast<int>(min(static_cast<long long>(T), a.n - first));
+  double mu[3], S[9], out[9];
+  if (cnt == T && a.use_bulk) {
+    if (tid == 0) {
+      mbar_init(&s_bar, 1);
+      fence_mbar_init();
+      mbar_arrive_expect_tx(&s_bar, T * 96u);
+      bulk_g2s(s_mu, a.mus + 3 * first, T * 24u, &s_bar);
+      bulk_g2s(s_cov, a.covs + 9 * first, T * 72u, &s_bar);
+    }
+    __syncthreads();
+    mbar_wait(&s_bar, 0);
 #pragma unroll
-  for (int k = 0; k < 9; ++k) a.out[9 * i + k] = out[k];
+    for (int k = 0; k < 3; ++k) mu[k] = s_mu[3 * tid + k];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) S[k] = s_cov[9 * tid + k];
+    unscented_point(a, mu, S, out);
+    __syncthreads();  // every thread has read its covariance: the tile can be overwritten
+#pragma unroll
+    for (int k = 0; k < 9; ++k) s_cov[9 * tid + k] = out[k];
+    fence_proxy_async();  // generic-proxy writes -> visible to the bulk (async-proxy) store
+    __syncthreads();
+    if (tid == 0) {
+      bulk_s2g(a.out + 9 * first, s_cov, T * 72u);
+      bulk_commit_group();
+      bulk_wait_group_read0();  // shared memory must outlive the read
+    }
+  } else if (tid < cnt) {
+    const long long i = first + tid;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) mu[k] = a.mus[3 * i + k];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) S[k] = a.covs[9 * i + k];
+    unscented_point(a, mu, S, out);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) a.out[9 * i + k] = out[k];
+  }
 }
 
 }  // namespace pnec
@@ -1175,10 +1271,10 @@ int launch_eval_t(pnec_handle *h, const EvalArgs &a, cudaStream_t stream) {
   return PNEC_OK;
 }
 
-template <int V, int WPC, int S, int CHUNK, int MINB>
+template <int V, int WPC, int S, int CHUNK, int MINB, int T = 32>
 int launch_eval_warp_t(pnec_handle *h, const EvalArgs &a, cudaStream_t stream) {
-  auto kern = eval_warp_kernel<V, WPC, S, CHUNK, MINB>;
-  const size_t dyn = static_cast<size_t>(WPC) * S * 32 * VariantTraits<V>::kDoubles * 8;
+  auto kern = eval_warp_kernel<V, WPC, S, CHUNK, MINB, T>;
+  const size_t dyn = static_cast<size_t>(WPC) * S * T * VariantTraits<V>::kDoubles * 8;
   PNEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(dyn)));
   const long long want = (a.bv.num_problems + WPC - 1) / WPC;
@@ -1194,13 +1290,17 @@ template <int V>
 int launch_eval_v(pnec_handle *h, const EvalArgs &a, long long max_n, cudaStream_t stream) {
   (void)max_n;
   int cfg = env_int("PNEC_B200_EVAL_CFG", 0);
-  if (cfg == 0) cfg = a.use_bulk ? 10 : 2;
+  if (cfg == 0) cfg = a.use_bulk ? 11 : 2;  // 3 stages of 32 correspondences per warp: measured best
   switch (cfg) {
     case 2: return launch_eval_t<V, 4, 4, 3>(h, a, stream);    // CTA per problem, 128-wide tiles
     case 10: return launch_eval_warp_t<V, 4, 4, 8, 3>(h, a, stream);  // warp-private, 4 stages
-    case 11: return launch_eval_warp_t<V, 4, 3, 8, 3>(h, a, stream);
+    case 11: return launch_eval_warp_t<V, 4, 3, 8, 3>(h, a, stream);  // warp-private, 3 stages (default)
     case 12: return launch_eval_warp_t<V, 4, 6, 8, 2>(h, a, stream);
     case 13: return launch_eval_warp_t<V, 8, 3, 8, 2>(h, a, stream);
+    case 14: return launch_eval_warp_t<V, 4, 2, 8, 3, 64>(h, a, stream);   // 64-wide tiles, 2 stages
+    case 15: return launch_eval_warp_t<V, 4, 3, 8, 3, 64>(h, a, stream);   // 64-wide tiles, 3 stages (smem: 2 CTAs)
+    case 16: return launch_eval_warp_t<V, 4, 2, 8, 3, 128>(h, a, stream);  // 128-wide tiles
+    case 17: return launch_eval_warp_t<V, 4, 2, 8, 3>(h, a, stream);       // 32-wide tiles, 2 stages
     default: return fail(PNEC_ERR_INVALID_ARGUMENT, "unknown PNEC_B200_EVAL_CFG");
   }
 }
@@ -1466,6 +1566,7 @@ int pnec_unscented_transform_batch(pnec_handle *h, int64_t n, int32_t memspace, 
     a.covs = covs;
     a.out = out_covs;
   }
+  a.use_bulk = (aligned16(a.mus) && aligned16(a.covs) && aligned16(a.out) && !env_int("PNEC_B200_NO_BULK", 0)) ? 1 : 0;
   unscented_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, stream>>>(a);
   PNEC_CUDA(cudaGetLastError());
   h->launches++;
