@@ -1,0 +1,182 @@
+// pnec_aux.cuh — parity metric (pnec::common::CostFunction) and unscented transform kernels.
+#pragma once
+
+#include "pnec_batch.cuh"
+
+namespace pnec {
+
+// ---------------------------------------------------------------- cost kernel
+// pnec::common::CostFunction, src/common/common.cc:237-259: mean of
+// (t^T (f1 x R f2))^2 / (b^T S b), no regularisation.  pose: unit quaternion taken
+// from the normalised stored quaternion, translation as stored.
+__global__ void __launch_bounds__(128) cost_kernel(BatchView bv, double *out) {
+  __shared__ double s_red[4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long b = blockIdx.x;
+  long long s, e;
+  problem_range(bv, b, s, e);
+  const double *p = bv.poses + 7 * b;
+  const double qn = sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2] + p[3] * p[3]);
+  double x[6] = {0.0, 0.0, p[0] / qn, p[1] / qn, p[2] / qn, p[3] / qn};
+  PoseConst pc;
+  make_pose_const(x, pc);
+  const double t[3] = {p[4], p[5], p[6]};
+  double sum = 0.0;
+  for (long long i = s + tid; i < e; i += 128) {
+    double f1[3], f2[3], c[9], g[3], a[3], bb[3], Sb[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { f1[k] = bv.f1[3 * i + k]; f2[k] = bv.f2[3 * i + k]; }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) c[k] = bv.ct[9 * i + k];
+    rot(pc.R, f2, g);
+    cross3(t, f1, a);
+    const double num = dot3(a, g);
+    rot_t(pc.R, a, bb);
+    sym_mul(c, bb, Sb);
+    sum += num * num / dot3(bb, Sb);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) s_red[warp] = sum;
+  __syncthreads();
+  if (tid == 0) out[b] = (s_red[0] + s_red[1] + s_red[2] + s_red[3]) / static_cast<double>(e - s);
+}
+
+// ------------------------------------------------------- unscented transform
+// pnec::common::UnscentedTransform, src/common/common.cc:467-525, one thread per point.
+// 96 B in + 72 B out per point, ~250 flops: HBM-bound.
+struct UtArgs {
+  const double *mus, *covs;
+  double *out;
+  long long n;
+  double Kinv[9];  // column-major
+  double kappa;
+  int camera_model;
+  int use_bulk;  // mus / covs / out 16-byte aligned
+};
+
+// The transform of one point: mu[3], S[9] (column-major) -> out[9] (column-major).
+__device__ __forceinline__ void unscented_point(const UtArgs &a, const double mu[3], const double S[9],
+                                                double out[9]) {
+  const bool omni = (a.camera_model == PNEC_CAMERA_OMNIDIRECTIONAL);
+  // C = [c0 c1 0]: image-plane Cholesky columns (rotated for omnidirectional cameras)
+  double c0[3], c1[3];
+  if (omni) {
+    // RotationBetweenPoints((0,0,1), mu.normalized()), common.cc:118-124
+    const double inv_n = 1.0 / sqrt(mu[0] * mu[0] + mu[1] * mu[1] + mu[2] * mu[2]);
+    const double m[3] = {mu[0] * inv_n, mu[1] * inv_n, mu[2] * inv_n};
+    const double v[3] = {-m[1], m[0], 0.0};  // z x m
+    const double k = 1.0 / (1.0 + m[2]);
+    // R = I + [v]x + [v]x^2 k, row-major
+    double R[9];
+    R[0] = 1.0 + (-v[1] * v[1]) * k; R[1] = (v[0] * v[1]) * k;           R[2] = v[1];
+    R[3] = (v[0] * v[1]) * k;        R[4] = 1.0 + (-v[0] * v[0]) * k;    R[5] = -v[0];
+    R[6] = -v[1];                    R[7] = v[0];                        R[8] = 1.0 + (-(v[0] * v[0] + v[1] * v[1])) * k;
+    // local = (R^T S R) top-left 2x2:  local[p][q] = sum_rc R[r][p] S[r][c] R[c][q]
+    double SR[3][2];  // (S R)[:, 0:2]
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+        SR[r][q] = S[0 * 3 + r] * R[0 * 3 + q] + S[1 * 3 + r] * R[1 * 3 + q] + S[2 * 3 + r] * R[2 * 3 + q];
+    const double l_00 = R[0] * SR[0][0] + R[3] * SR[1][0] + R[6] * SR[2][0];
+    const double l_10 = R[1] * SR[0][0] + R[4] * SR[1][0] + R[7] * SR[2][0];
+    const double l_11 = R[1] * SR[0][1] + R[4] * SR[1][1] + R[7] * SR[2][1];
+    const double L00 = sqrt(l_00), L10 = l_10 / L00, L11 = sqrt(l_11 - L10 * L10);
+    // C = R * [[L00,0,0],[L10,L11,0],[0,0,0]]
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      c0[r] = R[r * 3 + 0] * L00 + R[r * 3 + 1] * L10;
+      c1[r] = R[r * 3 + 1] * L11;
+    }
+  } else {
+    const double L00 = sqrt(S[0]), L10 = S[1] / L00, L11 = sqrt(S[4] - L10 * L10);
+    c0[0] = L00; c0[1] = L10; c0[2] = 0.0;
+    c1[0] = 0.0; c1[1] = L11; c1[2] = 0.0;
+  }
+  const double nk = static_cast<double>(2.0f) + a.kappa;  // (float)n + kappa, common.cc:495
+  const double w0 = a.kappa / nk, wi = 0.5 / nk;
+  double tp[5][3], mean[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int p = 0; p < 5; ++p) {
+    const double sg = (p == 0) ? 0.0 : ((p <= 2) ? 1.0 : -1.0);
+    const double *c = (p == 1 || p == 3) ? c0 : c1;
+    double q[3] = {mu[0] + sg * c[0], mu[1] + sg * c[1], mu[2] + sg * c[2]};
+    if (!omni) {
+      const double x = a.Kinv[0] * q[0] + a.Kinv[3] * q[1] + a.Kinv[6] * q[2];
+      const double y = a.Kinv[1] * q[0] + a.Kinv[4] * q[1] + a.Kinv[7] * q[2];
+      const double z = a.Kinv[2] * q[0] + a.Kinv[5] * q[1] + a.Kinv[8] * q[2];
+      q[0] = x; q[1] = y; q[2] = z;
+    }
+    const double inv = 1.0 / sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+    const double w = (p == 0) ? w0 : wi;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      tp[p][k] = q[k] * inv;
+      mean[k] += w * tp[p][k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) out[k] = 0.0;
+#pragma unroll
+  for (int p = 0; p < 5; ++p) {
+    const double w = (p == 0) ? w0 : wi;
+    const double d[3] = {tp[p][0] - mean[0], tp[p][1] - mean[1], tp[p][2] - mean[2]};
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int r = 0; r < 3; ++r) out[c * 3 + r] += w * d[r] * d[c];
+  }
+}
+
+// One CTA per tile of 128 points.  Full, 16-byte aligned tiles go through the TMA engine both
+// ways: two bulk loads (3 KB of points, 9 KB of covariances) into shared memory, each thread
+// transforms its point, results are staged over the covariance tile and leave as one 9 KB
+// bulk store.  The last partial tile (and unaligned arrays) use plain per-thread accesses.
+__global__ void __launch_bounds__(128) unscented_kernel(const __grid_constant__ UtArgs a) {
+  constexpr int T = 128;
+  __shared__ __align__(16) double s_mu[3 * T];
+  __shared__ __align__(16) double s_cov[9 * T];
+  __shared__ __align__(8) uint64_t s_bar;
+  const int tid = threadIdx.x;
+  const long long first = static_cast<long long>(blockIdx.x) * T;
+  const int cnt = static_cast<int>(min(static_cast<long long>(T), a.n - first));
+  double mu[3], S[9], out[9];
+  if (cnt == T && a.use_bulk) {
+    if (tid == 0) {
+      mbar_init(&s_bar, 1);
+      fence_mbar_init();
+      mbar_arrive_expect_tx(&s_bar, T * 96u);
+      bulk_g2s(s_mu, a.mus + 3 * first, T * 24u, &s_bar);
+      bulk_g2s(s_cov, a.covs + 9 * first, T * 72u, &s_bar);
+    }
+    __syncthreads();
+    mbar_wait(&s_bar, 0);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) mu[k] = s_mu[3 * tid + k];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) S[k] = s_cov[9 * tid + k];
+    unscented_point(a, mu, S, out);
+    __syncthreads();  // every thread has read its covariance: the tile can be overwritten
+#pragma unroll
+    for (int k = 0; k < 9; ++k) s_cov[9 * tid + k] = out[k];
+    fence_proxy_async();  // generic-proxy writes -> visible to the bulk (async-proxy) store
+    __syncthreads();
+    if (tid == 0) {
+      bulk_s2g(a.out + 9 * first, s_cov, T * 72u);
+      bulk_commit_group();
+      bulk_wait_group_read0();  // shared memory must outlive the read
+    }
+  } else if (tid < cnt) {
+    const long long i = first + tid;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) mu[k] = a.mus[3 * i + k];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) S[k] = a.covs[9 * i + k];
+    unscented_point(a, mu, S, out);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) a.out[9 * i + k] = out[k];
+  }
+}
+
+}  // namespace pnec

@@ -1,0 +1,642 @@
+// pnec_capi.cu — host side and C-ABI (include/pnec_b200.h) of the B200 PNEC frame-pair solver.
+// The only translation unit: the sm_100a kernels live in the headers it includes.
+//
+//   pnec_solve.cuh   solve_kernel / solve_stream_kernel: whole LM solve per frame pair on device
+//   pnec_eval.cuh    eval_warp_kernel (K1): fused residual + Jacobian + J^T J, the roofline kernel
+//   pnec_aux.cuh     cost_kernel (parity metric), unscented_kernel (covariance propagation)
+//   pnec_lm.cuh      Ceres-semantics Levenberg-Marquardt update; pnec_device.cuh: the math
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "pnec_aux.cuh"
+#include "pnec_eval.cuh"
+#include "pnec_solve.cuh"
+
+// =================================================================== host side
+
+using namespace pnec;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string &msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define PNEC_CUDA(call)                                                                      \
+  do {                                                                                       \
+    cudaError_t err__ = (call);                                                              \
+    if (err__ != cudaSuccess)                                                                \
+      return fail(PNEC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(err__));     \
+  } while (0)
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int env_int(const char *name, int dflt) {
+  const char *v = std::getenv(name);
+  return (v && *v) ? std::atoi(v) : dflt;
+}
+
+}  // namespace
+
+struct pnec_handle {
+  int device = 0;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  int64_t launches = 0;
+  // staging for HOST-memspace calls and for the device copy of offsets
+  DevBuf d_f1, d_f2, d_ct, d_ch, d_off, d_poses;
+  DevBuf d_out_poses, d_out_status, d_out_iters, d_out_cost, d_out_init, d_out_grad, d_out_jtj;
+  DevBuf d_ut_mu, d_ut_cov, d_ut_out;
+  std::mutex mu;
+};
+
+namespace {
+
+struct Staged {
+  BatchView bv;
+  long long max_n = 0;
+};
+
+int validate_batch(const pnec_batch *b, int variant, bool need_poses) {
+  if (!b) return fail(PNEC_ERR_INVALID_ARGUMENT, "batch is NULL");
+  if (b->num_problems < 0) return fail(PNEC_ERR_INVALID_ARGUMENT, "num_problems < 0");
+  if (!b->offsets && b->n_per_problem < 0)
+    return fail(PNEC_ERR_INVALID_ARGUMENT, "n_per_problem < 0");
+  if (b->memspace != PNEC_MEM_HOST && b->memspace != PNEC_MEM_DEVICE)
+    return fail(PNEC_ERR_INVALID_ARGUMENT, "unknown memspace");
+  if (variant < PNEC_VARIANT_NEC || variant > PNEC_VARIANT_SYMMETRIC)
+    return fail(PNEC_ERR_INVALID_ARGUMENT, "unknown residual variant");
+  long long total = 0;
+  if (b->offsets) {
+    if (b->offsets[0] < 0) return fail(PNEC_ERR_INVALID_ARGUMENT, "offsets[0] < 0");
+    for (int64_t i = 0; i < b->num_problems; ++i)
+      if (b->offsets[i + 1] < b->offsets[i])
+        return fail(PNEC_ERR_INVALID_ARGUMENT, "offsets must be non-decreasing");
+    total = b->offsets[b->num_problems];
+  } else {
+    total = b->num_problems * b->n_per_problem;
+  }
+  if (total > 0) {
+    if (!b->bvs_host || !b->bvs_target)
+      return fail(PNEC_ERR_INVALID_ARGUMENT, "bearing vector arrays are NULL");
+    if (variant != PNEC_VARIANT_NEC && !b->covs_target)
+      return fail(PNEC_ERR_INVALID_ARGUMENT, "covs_target is NULL for a PNEC variant");
+    if (variant == PNEC_VARIANT_SYMMETRIC && !b->covs_host)
+      return fail(PNEC_ERR_INVALID_ARGUMENT, "covs_host is NULL for the SYMMETRIC variant");
+  }
+  if (need_poses && b->num_problems > 0 && !b->poses)
+    return fail(PNEC_ERR_INVALID_ARGUMENT, "poses is NULL");
+  return PNEC_OK;
+}
+
+// Builds the device view of a batch: copies H2D for HOST batches, always copies
+// the (host) offsets.  Everything is enqueued on `stream`.
+int stage_batch(pnec_handle *h, const pnec_batch *b, int variant, cudaStream_t stream,
+                Staged *out) {
+  const long long B = b->num_problems;
+  long long total, max_n = 0;
+  if (b->offsets) {
+    total = b->offsets[B];
+    for (long long i = 0; i < B; ++i) max_n = std::max<long long>(max_n, b->offsets[i + 1] - b->offsets[i]);
+  } else {
+    total = B * b->n_per_problem;
+    max_n = b->n_per_problem;
+  }
+  BatchView bv{};
+  bv.num_problems = B;
+  bv.total = b->offsets ? b->offsets[B] : total;
+  bv.n_uniform = b->offsets ? 0 : b->n_per_problem;
+  const long long base = b->offsets ? b->offsets[0] : 0;
+  (void)base;
+  if (b->offsets) {
+    PNEC_CUDA(h->d_off.ensure(sizeof(long long) * (B + 1)));
+    PNEC_CUDA(cudaMemcpyAsync(h->d_off.p, b->offsets, sizeof(long long) * (B + 1),
+                              cudaMemcpyHostToDevice, stream));
+    bv.offsets = static_cast<const long long *>(h->d_off.p);
+  }
+  const bool need_ct = variant != PNEC_VARIANT_NEC;
+  const bool need_ch = variant == PNEC_VARIANT_SYMMETRIC;
+  if (b->memspace == PNEC_MEM_HOST) {
+    const size_t nel = static_cast<size_t>(bv.total);
+    PNEC_CUDA(h->d_f1.ensure(nel * 24));
+    PNEC_CUDA(h->d_f2.ensure(nel * 24));
+    PNEC_CUDA(h->d_poses.ensure(static_cast<size_t>(B) * 56));
+    if (nel) {
+      PNEC_CUDA(cudaMemcpyAsync(h->d_f1.p, b->bvs_host, nel * 24, cudaMemcpyHostToDevice, stream));
+      PNEC_CUDA(cudaMemcpyAsync(h->d_f2.p, b->bvs_target, nel * 24, cudaMemcpyHostToDevice, stream));
+    }
+    if (need_ct) {
+      PNEC_CUDA(h->d_ct.ensure(nel * 72));
+      if (nel)
+        PNEC_CUDA(cudaMemcpyAsync(h->d_ct.p, b->covs_target, nel * 72, cudaMemcpyHostToDevice, stream));
+    }
+    if (need_ch) {
+      PNEC_CUDA(h->d_ch.ensure(nel * 72));
+      if (nel)
+        PNEC_CUDA(cudaMemcpyAsync(h->d_ch.p, b->covs_host, nel * 72, cudaMemcpyHostToDevice, stream));
+    }
+    if (B && b->poses)
+      PNEC_CUDA(cudaMemcpyAsync(h->d_poses.p, b->poses, static_cast<size_t>(B) * 56,
+                                cudaMemcpyHostToDevice, stream));
+    bv.f1 = static_cast<const double *>(h->d_f1.p);
+    bv.f2 = static_cast<const double *>(h->d_f2.p);
+    bv.ct = need_ct ? static_cast<const double *>(h->d_ct.p) : nullptr;
+    bv.ch = need_ch ? static_cast<const double *>(h->d_ch.p) : nullptr;
+    bv.poses = static_cast<const double *>(h->d_poses.p);
+  } else {
+    bv.f1 = b->bvs_host;
+    bv.f2 = b->bvs_target;
+    bv.ct = need_ct ? b->covs_target : nullptr;
+    bv.ch = need_ch ? b->covs_host : nullptr;
+    bv.poses = b->poses;
+  }
+  out->bv = bv;
+  out->max_n = max_n;
+  return PNEC_OK;
+}
+
+bool bulk_ok(const BatchView &bv) {
+  return aligned16(bv.f1) && aligned16(bv.f2) && (!bv.ct || aligned16(bv.ct)) &&
+         (!bv.ch || aligned16(bv.ch));
+}
+
+int bytes_per_corr(int variant) {
+  switch (variant) {
+    case PNEC_VARIANT_NEC: return 48;
+    case PNEC_VARIANT_SYMMETRIC: return 192;
+    default: return 120;
+  }
+}
+
+// ------------------------------------------------------------ kernel launchers
+
+constexpr size_t kStaticSmemReserve = 3072;  // static __shared__ of the kernels + slack
+
+template <int V, int NW, int MINB>
+int launch_solve_t(pnec_handle *h, const SolveArgs &a, size_t dyn, cudaStream_t stream) {
+  auto kern = solve_kernel<V, NW, MINB>;
+  PNEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(dyn)));
+  kern<<<static_cast<unsigned>(a.bv.num_problems), NW * 32, dyn, stream>>>(a);
+  PNEC_CUDA(cudaGetLastError());
+  h->launches++;
+  return PNEC_OK;
+}
+
+template <int V>
+int launch_solve_v(pnec_handle *h, const SolveArgs &a, int nw, size_t dyn, cudaStream_t stream) {
+  switch (nw) {
+    case 1: return launch_solve_t<V, 1, 8>(h, a, dyn, stream);
+    case 2: return launch_solve_t<V, 2, 4>(h, a, dyn, stream);
+    case 4: return launch_solve_t<V, 4, 3>(h, a, dyn, stream);
+    case 8: return launch_solve_t<V, 8, 1>(h, a, dyn, stream);
+    default: return fail(PNEC_ERR_INVALID_ARGUMENT, "unsupported warps per problem");
+  }
+}
+
+#ifdef PNEC_PHASE_TIMING
+void dump_phase_timing(const SolveArgs &a) {
+  cudaDeviceSynchronize();
+  const long long B = a.bv.num_problems;
+  std::vector<long long> hbuf(12 * B);
+  cudaMemcpy(hbuf.data(), a.dbg, sizeof(long long) * 12 * B, cudaMemcpyDeviceToHost);
+  double s[12] = {0};
+  for (long long b = 0; b < B; ++b)
+    for (int k = 0; k < 12; ++k) s[k] += hbuf[12 * b + k];
+  unsigned long long probe[8];
+  cudaMemcpyFromSymbol(probe, g_lm_probe, sizeof(probe));
+  std::fprintf(stderr, "[lm_step probes, cycles per CTA] judge %.0f bookkeeping %.0f tr-step %.0f candidate %.0f store %.0f\n",
+               (double)probe[0] / B, (double)probe[1] / B, (double)probe[2] / B, (double)probe[3] / B, (double)probe[4] / B);
+  unsigned long long zero[8] = {0};
+  cudaMemcpyToSymbol(g_lm_probe, zero, sizeof(zero));
+  std::fprintf(stderr, "[phase timing, mean cycles per CTA] warp0: eval %.0f lm %.0f barrier %.0f full-passes %.2f "
+               "total %.0f | warp1: eval %.0f lm(idle) %.0f barrier %.0f\n",
+               s[0] / B, s[1] / B, s[2] / B, s[3] / B, s[4] / B, s[6] / B, s[7] / B, s[8] / B);
+}
+#endif
+
+template <int V, int NW, int S, int MINB>
+int launch_solve_stream_t(pnec_handle *h, const SolveArgs &a, cudaStream_t stream) {
+  auto kern = solve_stream_kernel<V, NW, S, MINB>;
+  const size_t dyn = static_cast<size_t>(NW) * S * 32 * VariantTraits<V>::kDoubles * 8;
+  PNEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(dyn)));
+  kern<<<static_cast<unsigned>(a.bv.num_problems), NW * 32, dyn, stream>>>(a);
+  PNEC_CUDA(cudaGetLastError());
+  h->launches++;
+  return PNEC_OK;
+}
+
+template <int V>
+int launch_solve_stream_v(pnec_handle *h, const SolveArgs &a, cudaStream_t stream) {
+  switch (env_int("PNEC_B200_STREAM_CFG", 3)) {
+    case 1: return launch_solve_stream_t<V, 6, 4, 2>(h, a, stream);   // 2 CTAs x 6 warps per SM
+    case 2: return launch_solve_stream_t<V, 12, 4, 1>(h, a, stream);  // 1 CTA x 12 warps
+    case 3: return launch_solve_stream_t<V, 4, 4, 3>(h, a, stream);   // 3 CTAs x 4 warps
+    case 4: return launch_solve_stream_t<V, 6, 3, 2>(h, a, stream);
+    case 5: return launch_solve_stream_t<V, 1, 4, 12>(h, a, stream);  // one warp per pair, 12 pairs per SM
+    case 6: return launch_solve_stream_t<V, 2, 4, 6>(h, a, stream);
+    case 7: return launch_solve_stream_t<V, 1, 3, 12>(h, a, stream);
+    case 8: return launch_solve_stream_t<V, 1, 6, 8>(h, a, stream);
+    default: return fail(PNEC_ERR_INVALID_ARGUMENT, "unknown PNEC_B200_STREAM_CFG");
+  }
+}
+
+int launch_solve(pnec_handle *h, const SolveArgs &a0, int variant, long long max_n,
+                 cudaStream_t stream) {
+  SolveArgs a = a0;
+  if (a.bv.num_problems == 0) return PNEC_OK;
+  // Large frame pairs: stream every pass (bulk-copy rings) instead of keeping one pair per SM
+  // resident.  Needs 16-byte aligned arrays; SYMMETRIC (192 B / correspondence) stays resident-first.
+  const long long stream_min_n = env_int("PNEC_B200_STREAM_MIN_N", 896);
+  if (bulk_ok(a.bv) && !env_int("PNEC_B200_NO_BULK", 0) && max_n > stream_min_n) {
+    a.use_bulk = 1;
+    a.cap_elems = 0;
+    a.dbg = nullptr;
+    switch (variant) {
+      case PNEC_VARIANT_NEC: return launch_solve_stream_v<PNEC_VARIANT_NEC>(h, a, stream);
+      case PNEC_VARIANT_TARGET: return launch_solve_stream_v<PNEC_VARIANT_TARGET>(h, a, stream);
+      case PNEC_VARIANT_HOST: return launch_solve_stream_v<PNEC_VARIANT_HOST>(h, a, stream);
+      default: return launch_solve_stream_v<PNEC_VARIANT_SYMMETRIC>(h, a, stream);
+    }
+  }
+  int nw = env_int("PNEC_B200_SOLVE_WARPS", 0);
+  // Warps per frame pair (measured on B200, tools/nw_sweep.py): the solve is latency-bound, so
+  // what pays is the number of pairs resident per SM, not the width of one pair.  One warp per
+  // pair wins while >= 7 pairs fit in shared memory; 4 warps once only 3 fit.
+  if (nw == 0) nw = max_n <= 320 ? 1 : max_n <= 448 ? 2 : max_n <= 1024 ? 4 : 8;
+  const int bpc = bytes_per_corr(variant);
+  const size_t cap_bytes = h->smem_optin - kStaticSmemReserve;
+  const long long want_elems = ((max_n + 1) + 1) & ~1LL;  // head element + round up to even
+  long long cap_elems = std::min<long long>(want_elems, static_cast<long long>(cap_bytes / bpc) & ~1LL);
+  if (cap_elems < 2) cap_elems = 2;
+  a.cap_elems = static_cast<int>(cap_elems);
+  a.use_bulk = bulk_ok(a.bv) ? 1 : 0;
+  if (env_int("PNEC_B200_NO_BULK", 0)) a.use_bulk = 0;
+  a.dbg = nullptr;
+#ifdef PNEC_PHASE_TIMING
+  static long long *dbg_buf = nullptr;
+  if (!dbg_buf) cudaMalloc(&dbg_buf, sizeof(long long) * 12 * 1000000);
+  a.dbg = dbg_buf;
+#endif
+  const size_t dyn = static_cast<size_t>(cap_elems) * bpc;
+  int rc;
+  switch (variant) {
+    case PNEC_VARIANT_NEC: rc = launch_solve_v<PNEC_VARIANT_NEC>(h, a, nw, dyn, stream); break;
+    case PNEC_VARIANT_TARGET: rc = launch_solve_v<PNEC_VARIANT_TARGET>(h, a, nw, dyn, stream); break;
+    case PNEC_VARIANT_HOST: rc = launch_solve_v<PNEC_VARIANT_HOST>(h, a, nw, dyn, stream); break;
+    default: rc = launch_solve_v<PNEC_VARIANT_SYMMETRIC>(h, a, nw, dyn, stream); break;
+  }
+#ifdef PNEC_PHASE_TIMING
+  if (rc == PNEC_OK && env_int("PNEC_B200_DUMP_TIMING", 0)) dump_phase_timing(a);
+#endif
+  return rc;
+}
+
+template <int V, int NW, int S, int MINB>
+int launch_eval_t(pnec_handle *h, const EvalArgs &a, cudaStream_t stream) {
+  auto kern = eval_kernel<V, NW, S, MINB>;
+  const size_t dyn = static_cast<size_t>(S) * NW * 32 * VariantTraits<V>::kDoubles * 8;
+  PNEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(dyn)));
+  kern<<<static_cast<unsigned>(a.bv.num_problems), NW * 32, dyn, stream>>>(a);
+  PNEC_CUDA(cudaGetLastError());
+  h->launches++;
+  return PNEC_OK;
+}
+
+template <int V, int WPC, int S, int CHUNK, int MINB, int T = 32>
+int launch_eval_warp_t(pnec_handle *h, const EvalArgs &a, cudaStream_t stream) {
+  auto kern = eval_warp_kernel<V, WPC, S, CHUNK, MINB, T>;
+  const size_t dyn = static_cast<size_t>(WPC) * S * T * VariantTraits<V>::kDoubles * 8;
+  PNEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(dyn)));
+  const long long want = (a.bv.num_problems + WPC - 1) / WPC;
+  const long long cap = static_cast<long long>(h->sm_count) * MINB;
+  const unsigned grid = static_cast<unsigned>(std::max<long long>(1, std::min(want, cap)));
+  kern<<<grid, WPC * 32, dyn, stream>>>(a);
+  PNEC_CUDA(cudaGetLastError());
+  h->launches++;
+  return PNEC_OK;
+}
+
+template <int V>
+int launch_eval_v(pnec_handle *h, const EvalArgs &a, long long max_n, cudaStream_t stream) {
+  (void)max_n;
+  int cfg = env_int("PNEC_B200_EVAL_CFG", 0);
+  if (cfg == 0) cfg = a.use_bulk ? 11 : 2;  // 3 stages of 32 correspondences per warp: measured best
+  switch (cfg) {
+    case 2: return launch_eval_t<V, 4, 4, 3>(h, a, stream);    // CTA per problem, 128-wide tiles
+    case 10: return launch_eval_warp_t<V, 4, 4, 8, 3>(h, a, stream);  // warp-private, 4 stages
+    case 11: return launch_eval_warp_t<V, 4, 3, 8, 3>(h, a, stream);  // warp-private, 3 stages (default)
+    case 12: return launch_eval_warp_t<V, 4, 6, 8, 2>(h, a, stream);
+    case 13: return launch_eval_warp_t<V, 8, 3, 8, 2>(h, a, stream);
+    case 14: return launch_eval_warp_t<V, 4, 2, 8, 3, 64>(h, a, stream);   // 64-wide tiles, 2 stages
+    case 15: return launch_eval_warp_t<V, 4, 3, 8, 3, 64>(h, a, stream);   // 64-wide tiles, 3 stages (smem: 2 CTAs)
+    case 16: return launch_eval_warp_t<V, 4, 2, 8, 3, 128>(h, a, stream);  // 128-wide tiles
+    case 17: return launch_eval_warp_t<V, 4, 2, 8, 3>(h, a, stream);       // 32-wide tiles, 2 stages
+    default: return fail(PNEC_ERR_INVALID_ARGUMENT, "unknown PNEC_B200_EVAL_CFG");
+  }
+}
+
+int launch_eval(pnec_handle *h, const EvalArgs &a0, int variant, long long max_n,
+                cudaStream_t stream) {
+  EvalArgs a = a0;
+  if (a.bv.num_problems == 0) return PNEC_OK;
+  a.use_bulk = bulk_ok(a.bv) ? 1 : 0;
+  if (env_int("PNEC_B200_NO_BULK", 0)) a.use_bulk = 0;
+  switch (variant) {
+    case PNEC_VARIANT_NEC: return launch_eval_v<PNEC_VARIANT_NEC>(h, a, max_n, stream);
+    case PNEC_VARIANT_TARGET: return launch_eval_v<PNEC_VARIANT_TARGET>(h, a, max_n, stream);
+    case PNEC_VARIANT_HOST: return launch_eval_v<PNEC_VARIANT_HOST>(h, a, max_n, stream);
+    default: return launch_eval_v<PNEC_VARIANT_SYMMETRIC>(h, a, max_n, stream);
+  }
+}
+
+}  // namespace
+
+// ===================================================================== C-ABI
+
+extern "C" {
+
+int pnec_version(void) { return PNEC_B200_VERSION_MAJOR * 1000 + PNEC_B200_VERSION_MINOR; }
+
+const char *pnec_last_error(void) { return g_last_error.c_str(); }
+
+const char *pnec_status_string(int32_t status) {
+  switch (status) {
+    case PNEC_STATUS_CONVERGED_FUNCTION: return "converged: function tolerance";
+    case PNEC_STATUS_CONVERGED_PARAMETER: return "converged: parameter tolerance";
+    case PNEC_STATUS_CONVERGED_GRADIENT: return "converged: gradient tolerance";
+    case PNEC_STATUS_CONVERGED_RADIUS: return "converged: minimum trust region radius";
+    case PNEC_STATUS_MAX_ITERATIONS: return "no convergence: maximum iterations";
+    case PNEC_STATUS_FAILURE: return "failure: consecutive invalid steps";
+    case PNEC_STATUS_NONFINITE: return "failure: non-finite cost at the start point";
+    case PNEC_STATUS_EMPTY: return "empty problem";
+    default: return "unknown";
+  }
+}
+
+void pnec_solver_opts_default(pnec_solver_opts *o) {
+  if (!o) return;
+  o->variant = PNEC_VARIANT_TARGET;
+  o->max_num_iterations = 50;
+  o->max_num_consecutive_invalid_steps = 5;
+  o->jacobi_scaling = 1;
+  o->regularization = 1.0e-13;
+  o->function_tolerance = 1e-6;
+  o->gradient_tolerance = 1e-10;
+  o->parameter_tolerance = 1e-8;
+  o->initial_trust_region_radius = 1e4;
+  o->max_trust_region_radius = 1e16;
+  o->min_trust_region_radius = 1e-32;
+  o->min_relative_decrease = 1e-3;
+  o->min_lm_diagonal = 1e-6;
+  o->max_lm_diagonal = 1e32;
+}
+
+int pnec_create(int device, pnec_handle **out) {
+  if (!out) return fail(PNEC_ERR_INVALID_ARGUMENT, "out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(PNEC_ERR_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail(PNEC_ERR_INVALID_ARGUMENT, "bad device index");
+  PNEC_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop{};
+  PNEC_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(PNEC_ERR_UNSUPPORTED, "pnec_b200 is built for sm_100a (Blackwell) only");
+  pnec_handle *h = new (std::nothrow) pnec_handle();
+  if (!h) return fail(PNEC_ERR_ALLOC, "out of host memory");
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  h->smem_optin = prop.sharedMemPerBlockOptin;
+  *out = h;
+  return PNEC_OK;
+}
+
+void pnec_destroy(pnec_handle *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  DevBuf *bufs[] = {&h->d_f1, &h->d_f2, &h->d_ct, &h->d_ch, &h->d_off, &h->d_poses,
+                    &h->d_out_poses, &h->d_out_status, &h->d_out_iters, &h->d_out_cost,
+                    &h->d_out_init, &h->d_out_grad, &h->d_out_jtj, &h->d_ut_mu, &h->d_ut_cov,
+                    &h->d_ut_out};
+  for (DevBuf *b : bufs) b->release();
+  delete h;
+}
+
+int64_t pnec_launch_count(const pnec_handle *h) { return h ? h->launches : 0; }
+
+int pnec_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_solver_opts *opts,
+                     const pnec_solve_out *out, void *cuda_stream) {
+  if (!h || !opts || !out) return fail(PNEC_ERR_INVALID_ARGUMENT, "NULL argument");
+  int rc = validate_batch(batch, opts->variant, true);
+  if (rc != PNEC_OK) return rc;
+  const long long B = batch->num_problems;
+  if (B > 0 && !out->poses) return fail(PNEC_ERR_INVALID_ARGUMENT, "out->poses is NULL");
+  if (B == 0) return PNEC_OK;
+  std::lock_guard<std::mutex> lock(h->mu);
+  PNEC_CUDA(cudaSetDevice(h->device));
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  Staged st;
+  rc = stage_batch(h, batch, opts->variant, stream, &st);
+  if (rc != PNEC_OK) return rc;
+  SolveArgs a{};
+  a.bv = st.bv;
+  a.o = *opts;
+  const bool host = batch->memspace == PNEC_MEM_HOST;
+  if (host) {
+    PNEC_CUDA(h->d_out_poses.ensure(static_cast<size_t>(B) * 56));
+    PNEC_CUDA(h->d_out_status.ensure(static_cast<size_t>(B) * 4));
+    PNEC_CUDA(h->d_out_iters.ensure(static_cast<size_t>(B) * 4));
+    PNEC_CUDA(h->d_out_cost.ensure(static_cast<size_t>(B) * 8));
+    PNEC_CUDA(h->d_out_init.ensure(static_cast<size_t>(B) * 8));
+    a.out_poses = static_cast<double *>(h->d_out_poses.p);
+    a.out_status = out->status ? static_cast<int *>(h->d_out_status.p) : nullptr;
+    a.out_iters = out->iterations ? static_cast<int *>(h->d_out_iters.p) : nullptr;
+    a.out_cost = out->cost ? static_cast<double *>(h->d_out_cost.p) : nullptr;
+    a.out_init_cost = out->initial_cost ? static_cast<double *>(h->d_out_init.p) : nullptr;
+  } else {
+    a.out_poses = out->poses;
+    a.out_status = out->status;
+    a.out_iters = out->iterations;
+    a.out_cost = out->cost;
+    a.out_init_cost = out->initial_cost;
+  }
+  rc = launch_solve(h, a, opts->variant, st.max_n, stream);
+  if (rc != PNEC_OK) return rc;
+  if (host) {
+    PNEC_CUDA(cudaMemcpyAsync(out->poses, a.out_poses, static_cast<size_t>(B) * 56,
+                              cudaMemcpyDeviceToHost, stream));
+    if (out->status)
+      PNEC_CUDA(cudaMemcpyAsync(out->status, a.out_status, static_cast<size_t>(B) * 4,
+                                cudaMemcpyDeviceToHost, stream));
+    if (out->iterations)
+      PNEC_CUDA(cudaMemcpyAsync(out->iterations, a.out_iters, static_cast<size_t>(B) * 4,
+                                cudaMemcpyDeviceToHost, stream));
+    if (out->cost)
+      PNEC_CUDA(cudaMemcpyAsync(out->cost, a.out_cost, static_cast<size_t>(B) * 8,
+                                cudaMemcpyDeviceToHost, stream));
+    if (out->initial_cost)
+      PNEC_CUDA(cudaMemcpyAsync(out->initial_cost, a.out_init_cost, static_cast<size_t>(B) * 8,
+                                cudaMemcpyDeviceToHost, stream));
+    PNEC_CUDA(cudaStreamSynchronize(stream));
+  }
+  return PNEC_OK;
+}
+
+int pnec_eval_batch(pnec_handle *h, const pnec_batch *batch, int32_t variant,
+                    double regularization, const pnec_eval_out *out, void *cuda_stream) {
+  if (!h || !out) return fail(PNEC_ERR_INVALID_ARGUMENT, "NULL argument");
+  int rc = validate_batch(batch, variant, true);
+  if (rc != PNEC_OK) return rc;
+  const long long B = batch->num_problems;
+  if (B == 0) return PNEC_OK;
+  std::lock_guard<std::mutex> lock(h->mu);
+  PNEC_CUDA(cudaSetDevice(h->device));
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  Staged st;
+  rc = stage_batch(h, batch, variant, stream, &st);
+  if (rc != PNEC_OK) return rc;
+  EvalArgs a{};
+  a.bv = st.bv;
+  a.reg = regularization;
+  const bool host = batch->memspace == PNEC_MEM_HOST;
+  if (host) {
+    PNEC_CUDA(h->d_out_cost.ensure(static_cast<size_t>(B) * 8));
+    PNEC_CUDA(h->d_out_grad.ensure(static_cast<size_t>(B) * 40));
+    PNEC_CUDA(h->d_out_jtj.ensure(static_cast<size_t>(B) * 120));
+    a.out_cost = out->cost ? static_cast<double *>(h->d_out_cost.p) : nullptr;
+    a.out_grad = out->gradient ? static_cast<double *>(h->d_out_grad.p) : nullptr;
+    a.out_jtj = out->jtj ? static_cast<double *>(h->d_out_jtj.p) : nullptr;
+  } else {
+    a.out_cost = out->cost;
+    a.out_grad = out->gradient;
+    a.out_jtj = out->jtj;
+  }
+  rc = launch_eval(h, a, variant, st.max_n, stream);
+  if (rc != PNEC_OK) return rc;
+  if (host) {
+    if (out->cost)
+      PNEC_CUDA(cudaMemcpyAsync(out->cost, a.out_cost, static_cast<size_t>(B) * 8,
+                                cudaMemcpyDeviceToHost, stream));
+    if (out->gradient)
+      PNEC_CUDA(cudaMemcpyAsync(out->gradient, a.out_grad, static_cast<size_t>(B) * 40,
+                                cudaMemcpyDeviceToHost, stream));
+    if (out->jtj)
+      PNEC_CUDA(cudaMemcpyAsync(out->jtj, a.out_jtj, static_cast<size_t>(B) * 120,
+                                cudaMemcpyDeviceToHost, stream));
+    PNEC_CUDA(cudaStreamSynchronize(stream));
+  }
+  return PNEC_OK;
+}
+
+int pnec_cost_function_batch(pnec_handle *h, const pnec_batch *batch, double *out_mean_energy,
+                             void *cuda_stream) {
+  if (!h || !out_mean_energy) return fail(PNEC_ERR_INVALID_ARGUMENT, "NULL argument");
+  int rc = validate_batch(batch, PNEC_VARIANT_TARGET, true);
+  if (rc != PNEC_OK) return rc;
+  const long long B = batch->num_problems;
+  if (B == 0) return PNEC_OK;
+  std::lock_guard<std::mutex> lock(h->mu);
+  PNEC_CUDA(cudaSetDevice(h->device));
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  Staged st;
+  rc = stage_batch(h, batch, PNEC_VARIANT_TARGET, stream, &st);
+  if (rc != PNEC_OK) return rc;
+  const bool host = batch->memspace == PNEC_MEM_HOST;
+  double *d_out = out_mean_energy;
+  if (host) {
+    PNEC_CUDA(h->d_out_cost.ensure(static_cast<size_t>(B) * 8));
+    d_out = static_cast<double *>(h->d_out_cost.p);
+  }
+  cost_kernel<<<static_cast<unsigned>(B), 128, 0, stream>>>(st.bv, d_out);
+  PNEC_CUDA(cudaGetLastError());
+  h->launches++;
+  if (host) {
+    PNEC_CUDA(cudaMemcpyAsync(out_mean_energy, d_out, static_cast<size_t>(B) * 8,
+                              cudaMemcpyDeviceToHost, stream));
+    PNEC_CUDA(cudaStreamSynchronize(stream));
+  }
+  return PNEC_OK;
+}
+
+int pnec_unscented_transform_batch(pnec_handle *h, int64_t n, int32_t memspace, const double *mus,
+                                   const double *covs, const double *K_inv, double kappa,
+                                   int32_t camera_model, double *out_covs, void *cuda_stream) {
+  if (!h) return fail(PNEC_ERR_INVALID_ARGUMENT, "handle is NULL");
+  if (n < 0) return fail(PNEC_ERR_INVALID_ARGUMENT, "n < 0");
+  if (n == 0) return PNEC_OK;
+  if (!mus || !covs || !out_covs) return fail(PNEC_ERR_INVALID_ARGUMENT, "NULL array");
+  if (camera_model != PNEC_CAMERA_OMNIDIRECTIONAL && camera_model != PNEC_CAMERA_PINHOLE)
+    return fail(PNEC_ERR_INVALID_ARGUMENT, "unknown camera model");
+  if (camera_model == PNEC_CAMERA_PINHOLE && !K_inv)
+    return fail(PNEC_ERR_INVALID_ARGUMENT, "K_inv is NULL for a pinhole camera");
+  if (memspace != PNEC_MEM_HOST && memspace != PNEC_MEM_DEVICE)
+    return fail(PNEC_ERR_INVALID_ARGUMENT, "unknown memspace");
+  std::lock_guard<std::mutex> lock(h->mu);
+  PNEC_CUDA(cudaSetDevice(h->device));
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  UtArgs a{};
+  a.n = n;
+  a.kappa = kappa;
+  a.camera_model = camera_model;
+  for (int k = 0; k < 9; ++k) a.Kinv[k] = K_inv ? K_inv[k] : ((k % 4 == 0) ? 1.0 : 0.0);
+  const size_t nn = static_cast<size_t>(n);
+  if (memspace == PNEC_MEM_HOST) {
+    PNEC_CUDA(h->d_ut_mu.ensure(nn * 24));
+    PNEC_CUDA(h->d_ut_cov.ensure(nn * 72));
+    PNEC_CUDA(h->d_ut_out.ensure(nn * 72));
+    PNEC_CUDA(cudaMemcpyAsync(h->d_ut_mu.p, mus, nn * 24, cudaMemcpyHostToDevice, stream));
+    PNEC_CUDA(cudaMemcpyAsync(h->d_ut_cov.p, covs, nn * 72, cudaMemcpyHostToDevice, stream));
+    a.mus = static_cast<const double *>(h->d_ut_mu.p);
+    a.covs = static_cast<const double *>(h->d_ut_cov.p);
+    a.out = static_cast<double *>(h->d_ut_out.p);
+  } else {
+    a.mus = mus;
+    a.covs = covs;
+    a.out = out_covs;
+  }
+  a.use_bulk = (aligned16(a.mus) && aligned16(a.covs) && aligned16(a.out) && !env_int("PNEC_B200_NO_BULK", 0)) ? 1 : 0;
+  unscented_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, stream>>>(a);
+  PNEC_CUDA(cudaGetLastError());
+  h->launches++;
+  if (memspace == PNEC_MEM_HOST) {
+    PNEC_CUDA(cudaMemcpyAsync(out_covs, a.out, nn * 72, cudaMemcpyDeviceToHost, stream));
+    PNEC_CUDA(cudaStreamSynchronize(stream));
+  }
+  return PNEC_OK;
+}
+
+}  // extern "C"
