@@ -329,17 +329,20 @@ def test_c2_full_size_properties(handle, c2_batch):
     assert np.median(2 * np.arccos(np.clip(dq, -1, 1))) < 5e-4
 
 
-def test_c2_subsample_matches_oracle(handle, c2_batch):
+def test_c2_full_batch_matches_oracle(handle, c2_batch):
+    """All 10 000 frame pairs of BASELINE config C2 against the oracle (about a second of CPU
+    time on the box's cores): poses within the bar, identical iteration counts and statuses."""
     b = c2_batch
-    N, K = 512, 256
-    sl = slice(0, K * N)
-    res = handle.solve_batch(dev(b.bvs_host[sl]), dev(b.bvs_target[sl]), dev(b.covs_target[sl]), None,
-                             dev(b.init_poses[:K]), api.default_opts(api.TARGET), n_per_problem=N)
-    ref, info = oracle_solve(api.TARGET, b.bvs_host[sl], b.bvs_target[sl], b.covs_target[sl], None,
-                             b.init_poses[:K], n_per_problem=N)
+    N = 512
+    res = handle.solve_batch(dev(b.bvs_host), dev(b.bvs_target), dev(b.covs_target), None,
+                             dev(b.init_poses), api.default_opts(api.TARGET), n_per_problem=N)
+    ref, info = oracle_solve(api.TARGET, b.bvs_host, b.bvs_target, b.covs_target, None,
+                             b.init_poses, n_per_problem=N)
     r, t = max_pose_diff(res.poses.cpu().numpy(), ref)
     assert r <= ROT_TOL and t <= DIR_TOL, (r, t)
     assert np.array_equal(res.iterations.cpu().numpy(), info["iterations"])
+    assert np.array_equal(res.status.cpu().numpy(), info["status"])
+    np.testing.assert_allclose(res.cost.cpu().numpy(), info["final_cost"], rtol=1e-8)
 
 
 # ------------------------------------------- reference-shaped host interfaces
