@@ -112,10 +112,12 @@ def run_reference(args):
 
     oracle.build()
     threads = host_threads()
-    sample = min(args.problems, 2048)
-    batch = make_workload(sample, args.corr, seed=1)
+    batch = make_workload(min(args.problems, 2048), args.corr, seed=1)
+    # bounded sample: size each step for about a quarter of a second of wall clock on this box
+    rate = 0.0
     for _ in range(max(args.warmup, 1)):
-        cpu_oracle_rate(batch, min(sample, 4 * threads), threads)
+        rate = cpu_oracle_rate(batch, min(batch.num_problems, 8 * threads), threads)
+    sample = int(min(batch.num_problems, max(4 * threads, rate * 0.25)))
     t0 = time.perf_counter()
     for _ in range(args.steps):
         cpu_oracle_rate(batch, sample, threads)
