@@ -479,6 +479,41 @@ class NECCeres : public detail_opt::CeresLike {
 
 }  // namespace optimization
 
+// ------------------------------------------------------------------- features
+
+namespace features {
+
+// include/frames/keypoints.h:50-69.  The reference's constructor unprojects one keypoint on the
+// CPU with the Camera singleton's intrinsics; here a whole frame is unprojected in one GPU call.
+struct KeyPoint {
+  double point_[2] = {0, 0};
+  Vec3 bearing_vector_;
+  double img_covariance_[4] = {0, 0, 0, 0};  // column-major 2x2
+  Mat3 bv_covariance_;
+};
+
+// KeyPoint::Unproject (src/frames/keypoints.cc:49-62) for every keypoint: fills
+// bearing_vector_ and bv_covariance_ from point_ and img_covariance_.
+inline void UnprojectKeyPoints(std::vector<KeyPoint> &keypoints, const Mat3 &K_inv) {
+  const std::size_t n = keypoints.size();
+  if (n == 0) return;
+  std::vector<double> pts(2 * n), c2(4 * n), bvs(3 * n), covs(9 * n);
+  for (std::size_t i = 0; i < n; ++i) {
+    pts[2 * i] = keypoints[i].point_[0];
+    pts[2 * i + 1] = keypoints[i].point_[1];
+    for (int k = 0; k < 4; ++k) c2[4 * i + k] = keypoints[i].img_covariance_[k];
+  }
+  if (pnec_keypoints_unproject_batch(detail::Handle(), static_cast<int64_t>(n), PNEC_MEM_HOST, pts.data(),
+                                     c2.data(), K_inv.data(), bvs.data(), covs.data(), nullptr) != PNEC_OK)
+    throw std::runtime_error(std::string("pnec_keypoints_unproject_batch: ") + pnec_last_error());
+  for (std::size_t i = 0; i < n; ++i) {
+    for (int k = 0; k < 3; ++k) keypoints[i].bearing_vector_[k] = bvs[3 * i + k];
+    for (int k = 0; k < 9; ++k) keypoints[i].bv_covariance_.m[k] = covs[9 * i + k];
+  }
+}
+
+}  // namespace features
+
 // -------------------------------------------------------- rel_pose_estimation
 
 namespace rel_pose_estimation {

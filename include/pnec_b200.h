@@ -195,6 +195,19 @@ int pnec_unscented_transform_batch(pnec_handle *h, int64_t n, int32_t memspace,
                                    const double *K_inv, double kappa, int32_t camera_model,
                                    double *out_covs, void *cuda_stream);
 
+/* Keypoints to solver inputs: bearing vector + 3x3 bearing covariance of n keypoints from
+ * their pixel position and 2x2 image covariance, i.e. KeyPoint::Unproject
+ * (src/frames/keypoints.cc:49-62): bearing = Unproject(point, K_inv)
+ * (src/common/common.cc:460-465) and covariance = UnscentedTransform((x, y, 1),
+ * [[cov2, 0], [0, 0]], K_inv, 1.0, Pinhole).  The solver's inputs can then be produced on the
+ * device from 6 doubles per keypoint instead of being shipped as 12.
+ *   points [n][2]   covs2 [n][4] column-major 2x2 (Eigen::Matrix2d)   K_inv [9] HOST pointer
+ *   out_bvs [n][3]  out_covs [n][9] column-major */
+int pnec_keypoints_unproject_batch(pnec_handle *h, int64_t n, int32_t memspace,
+                                   const double *points, const double *covs2,
+                                   const double *K_inv, double *out_bvs, double *out_covs,
+                                   void *cuda_stream);
+
 /* Number of kernels this handle has launched so far (bench bookkeeping). */
 int64_t pnec_launch_count(const pnec_handle *h);
 

@@ -129,6 +129,8 @@ def lib() -> ctypes.CDLL:
         L.oracle_unscented_transform_batch.argtypes = [ctypes.c_int64, dp, dp, dp, ctypes.c_double,
                                                        ctypes.c_int, dp]
         L.oracle_unscented_transform_batch.restype = None
+        L.oracle_keypoints_unproject_batch.argtypes = [ctypes.c_int64, dp, dp, dp, dp, dp]
+        L.oracle_keypoints_unproject_batch.restype = None
         _lib = L
     return _lib
 
@@ -277,3 +279,11 @@ def unscented_transform(mus, covs, K_inv=None, kappa=1.0, camera_model=PINHOLE):
     lib().oracle_unscented_transform_batch(mus.shape[0], _dp(mus), _dp(covs), _dp(K), float(kappa),
                                            int(camera_model), _dp(out))
     return out
+
+
+def keypoints_unproject(points, covs2, K_inv):
+    """KeyPoint::Unproject for n keypoints -> (bvs (n,3), covs (n,9) column-major)."""
+    points, covs2, K = _c(points, (2,)), _c(covs2, (4,)), _c(K_inv)
+    bvs, covs = np.zeros((points.shape[0], 3)), np.zeros((points.shape[0], 9))
+    lib().oracle_keypoints_unproject_batch(points.shape[0], _dp(points), _dp(covs2), _dp(K), _dp(bvs), _dp(covs))
+    return bvs, covs

@@ -920,3 +920,20 @@ void oracle_unscented_transform_batch(int64_t n, const double *mus, const double
   for (int64_t i = 0; i < n; ++i)
     oracle_unscented_transform(mus + 3 * i, covs + 9 * i, K_inv, kappa, camera_model, out + 9 * i);
 }
+
+/* KeyPoint::Unproject, src/frames/keypoints.cc:49-62, for n keypoints.
+ * points[n][2], covs2[n][4] column-major 2x2, K_inv[9] column-major. */
+void oracle_keypoints_unproject_batch(int64_t n, const double *points, const double *covs2,
+                                      const double *K_inv, double *out_bvs, double *out_covs) {
+  double K[3][3];
+  load_cov(K_inv, K);
+  for (int64_t i = 0; i < n; ++i) {
+    const double mu[3] = {points[2 * i], points[2 * i + 1], 1.0};
+    double v[3];
+    matvec(K, mu, v); /* pnec::common::Unproject, common.cc:460-465 */
+    const double nv = norm_n(v, 3);
+    for (int k = 0; k < 3; ++k) out_bvs[3 * i + k] = v[k] / nv;
+    double cov[9] = {covs2[4 * i], covs2[4 * i + 1], 0.0, covs2[4 * i + 2], covs2[4 * i + 3], 0.0, 0.0, 0.0, 0.0};
+    oracle_unscented_transform(mu, cov, K_inv, 1.0, 1, out_covs + 9 * i);
+  }
+}

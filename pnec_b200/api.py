@@ -43,6 +43,7 @@ EXPORTED_SYMBOLS = (
     "pnec_eval_batch",
     "pnec_cost_function_batch",
     "pnec_unscented_transform_batch",
+    "pnec_keypoints_unproject_batch",
     "pnec_launch_count",
 )
 
@@ -146,6 +147,10 @@ def load_library() -> ctypes.CDLL:
                                                  ctypes.c_double, ctypes.c_int32, ctypes.c_void_p,
                                                  ctypes.c_void_p]
     L.pnec_unscented_transform_batch.restype = ctypes.c_int
+    L.pnec_keypoints_unproject_batch.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,
+                                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.pnec_keypoints_unproject_batch.restype = ctypes.c_int
     L.pnec_launch_count.argtypes = [ctypes.c_void_p]
     L.pnec_launch_count.restype = ctypes.c_int64
     _lib = L
@@ -398,6 +403,39 @@ class Handle:
             self._stream(device))
         self._check(rc, "pnec_unscented_transform_batch")
         return out
+
+
+    def keypoints_unproject(self, points, covs2, K_inv):
+        """KeyPoint::Unproject (src/frames/keypoints.cc:49-62) for n keypoints: points (n,2),
+        covs2 (n,4) column-major 2x2, K_inv (9,) column-major -> (bvs (n,3), covs (n,9))."""
+        device = _is_torch(points)
+        K = np.ascontiguousarray(K_inv, dtype=np.float64).reshape(9)
+        if device:
+            import torch
+
+            n = points.numel() // 2
+            if not (points.is_cuda and covs2.is_cuda and points.is_contiguous() and covs2.is_contiguous()
+                    and points.dtype == torch.float64 and covs2.dtype == torch.float64):
+                raise PnecError("device calls need contiguous float64 CUDA tensors")
+            bvs = torch.empty((n, 3), dtype=torch.float64, device=points.device)
+            covs = torch.empty((n, 9), dtype=torch.float64, device=points.device)
+            ptrs = (points.data_ptr(), covs2.data_ptr(), bvs.data_ptr(), covs.data_ptr())
+            ncov = covs2.numel() // 4
+        else:
+            points = self._prep_host(points, (2,))
+            covs2 = self._prep_host(covs2, (4,))
+            n = points.shape[0]
+            bvs, covs = np.empty((n, 3)), np.empty((n, 9))
+            ptrs = (points.ctypes.data, covs2.ctypes.data, bvs.ctypes.data, covs.ctypes.data)
+            ncov = covs2.shape[0]
+        if ncov != n:
+            raise PnecError("points and covs2 differ in length")
+        rc = self._lib.pnec_keypoints_unproject_batch(
+            self._h, n, MEM_DEVICE if device else MEM_HOST, ctypes.c_void_p(ptrs[0]),
+            ctypes.c_void_p(ptrs[1]), ctypes.c_void_p(K.ctypes.data), ctypes.c_void_p(ptrs[2]),
+            ctypes.c_void_p(ptrs[3]), self._stream(device))
+        self._check(rc, "pnec_keypoints_unproject_batch")
+        return bvs, covs
 
 
 _default_handles = {}

@@ -179,4 +179,80 @@ __global__ void __launch_bounds__(128) unscented_kernel(const __grid_constant__ 
   }
 }
 
+// KeyPoint::Unproject (src/frames/keypoints.cc:49-62) for n keypoints: one thread per keypoint,
+// 48 B in, 96 B out; full tiles of 128 keypoints move through the TMA engine both ways.
+struct KpArgs {
+  const double *points, *covs2;
+  double *out_bvs, *out_covs;
+  long long n;
+  double Kinv[9];  // column-major
+  int use_bulk;
+};
+
+__device__ __forceinline__ void keypoint_unproject(const KpArgs &a, const double pt[2],
+                                                   const double c2[4], double bv[3], double out[9]) {
+  // pnec::common::Unproject: (K_inv (x, y, 1)).normalized()
+  const double x = a.Kinv[0] * pt[0] + a.Kinv[3] * pt[1] + a.Kinv[6];
+  const double y = a.Kinv[1] * pt[0] + a.Kinv[4] * pt[1] + a.Kinv[7];
+  const double z = a.Kinv[2] * pt[0] + a.Kinv[5] * pt[1] + a.Kinv[8];
+  const double inv = 1.0 / sqrt(x * x + y * y + z * z);
+  bv[0] = x * inv; bv[1] = y * inv; bv[2] = z * inv;
+  UtArgs u{};
+#pragma unroll
+  for (int k = 0; k < 9; ++k) u.Kinv[k] = a.Kinv[k];
+  u.kappa = 1.0;
+  u.camera_model = PNEC_CAMERA_PINHOLE;
+  const double mu[3] = {pt[0], pt[1], 1.0};
+  const double S[9] = {c2[0], c2[1], 0.0, c2[2], c2[3], 0.0, 0.0, 0.0, 0.0};  // column-major
+  unscented_point(u, mu, S, out);
+}
+
+__global__ void __launch_bounds__(128) keypoint_kernel(const __grid_constant__ KpArgs a) {
+  constexpr int T = 128;
+  __shared__ __align__(16) double s_in[6 * T];    // points [2T] | covs2 [4T]
+  __shared__ __align__(16) double s_out[12 * T];  // bvs [3T] | covs [9T]
+  __shared__ __align__(8) uint64_t s_bar;
+  const int tid = threadIdx.x;
+  const long long first = static_cast<long long>(blockIdx.x) * T;
+  const int cnt = static_cast<int>(min(static_cast<long long>(T), a.n - first));
+  double pt[2], c2[4], bv[3], out[9];
+  if (cnt == T && a.use_bulk) {
+    if (tid == 0) {
+      mbar_init(&s_bar, 1);
+      fence_mbar_init();
+      mbar_arrive_expect_tx(&s_bar, T * 48u);
+      bulk_g2s(s_in, a.points + 2 * first, T * 16u, &s_bar);
+      bulk_g2s(s_in + 2 * T, a.covs2 + 4 * first, T * 32u, &s_bar);
+    }
+    __syncthreads();
+    mbar_wait(&s_bar, 0);
+    pt[0] = s_in[2 * tid]; pt[1] = s_in[2 * tid + 1];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) c2[k] = s_in[2 * T + 4 * tid + k];
+    keypoint_unproject(a, pt, c2, bv, out);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) s_out[3 * tid + k] = bv[k];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) s_out[3 * T + 9 * tid + k] = out[k];
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      bulk_s2g(a.out_bvs + 3 * first, s_out, T * 24u);
+      bulk_s2g(a.out_covs + 9 * first, s_out + 3 * T, T * 72u);
+      bulk_commit_group();
+      bulk_wait_group_read0();
+    }
+  } else if (tid < cnt) {
+    const long long i = first + tid;
+    pt[0] = a.points[2 * i]; pt[1] = a.points[2 * i + 1];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) c2[k] = a.covs2[4 * i + k];
+    keypoint_unproject(a, pt, c2, bv, out);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) a.out_bvs[3 * i + k] = bv[k];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) a.out_covs[9 * i + k] = out[k];
+  }
+}
+
 }  // namespace pnec

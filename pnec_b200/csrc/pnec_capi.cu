@@ -74,7 +74,7 @@ struct pnec_handle {
   // staging for HOST-memspace calls and for the device copy of offsets
   DevBuf d_f1, d_f2, d_ct, d_ch, d_off, d_poses;
   DevBuf d_out_poses, d_out_status, d_out_iters, d_out_cost, d_out_init, d_out_grad, d_out_jtj;
-  DevBuf d_ut_mu, d_ut_cov, d_ut_out;
+  DevBuf d_ut_mu, d_ut_cov, d_ut_out, d_kp_bv;
   std::mutex mu;
 };
 
@@ -451,7 +451,7 @@ void pnec_destroy(pnec_handle *h) {
   DevBuf *bufs[] = {&h->d_f1, &h->d_f2, &h->d_ct, &h->d_ch, &h->d_off, &h->d_poses,
                     &h->d_out_poses, &h->d_out_status, &h->d_out_iters, &h->d_out_cost,
                     &h->d_out_init, &h->d_out_grad, &h->d_out_jtj, &h->d_ut_mu, &h->d_ut_cov,
-                    &h->d_ut_out};
+                    &h->d_ut_out, &h->d_kp_bv};
   for (DevBuf *b : bufs) b->release();
   delete h;
 }
@@ -634,6 +634,53 @@ int pnec_unscented_transform_batch(pnec_handle *h, int64_t n, int32_t memspace, 
   h->launches++;
   if (memspace == PNEC_MEM_HOST) {
     PNEC_CUDA(cudaMemcpyAsync(out_covs, a.out, nn * 72, cudaMemcpyDeviceToHost, stream));
+    PNEC_CUDA(cudaStreamSynchronize(stream));
+  }
+  return PNEC_OK;
+}
+
+int pnec_keypoints_unproject_batch(pnec_handle *h, int64_t n, int32_t memspace, const double *points,
+                                   const double *covs2, const double *K_inv, double *out_bvs,
+                                   double *out_covs, void *cuda_stream) {
+  if (!h) return fail(PNEC_ERR_INVALID_ARGUMENT, "handle is NULL");
+  if (n < 0) return fail(PNEC_ERR_INVALID_ARGUMENT, "n < 0");
+  if (n == 0) return PNEC_OK;
+  if (!points || !covs2 || !K_inv || !out_bvs || !out_covs)
+    return fail(PNEC_ERR_INVALID_ARGUMENT, "NULL array");
+  if (memspace != PNEC_MEM_HOST && memspace != PNEC_MEM_DEVICE)
+    return fail(PNEC_ERR_INVALID_ARGUMENT, "unknown memspace");
+  std::lock_guard<std::mutex> lock(h->mu);
+  PNEC_CUDA(cudaSetDevice(h->device));
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  KpArgs a{};
+  a.n = n;
+  for (int k = 0; k < 9; ++k) a.Kinv[k] = K_inv[k];
+  const size_t nn = static_cast<size_t>(n);
+  if (memspace == PNEC_MEM_HOST) {
+    PNEC_CUDA(h->d_ut_mu.ensure(nn * 16));
+    PNEC_CUDA(h->d_ut_cov.ensure(nn * 32));
+    PNEC_CUDA(h->d_kp_bv.ensure(nn * 24));
+    PNEC_CUDA(h->d_ut_out.ensure(nn * 72));
+    PNEC_CUDA(cudaMemcpyAsync(h->d_ut_mu.p, points, nn * 16, cudaMemcpyHostToDevice, stream));
+    PNEC_CUDA(cudaMemcpyAsync(h->d_ut_cov.p, covs2, nn * 32, cudaMemcpyHostToDevice, stream));
+    a.points = static_cast<const double *>(h->d_ut_mu.p);
+    a.covs2 = static_cast<const double *>(h->d_ut_cov.p);
+    a.out_bvs = static_cast<double *>(h->d_kp_bv.p);
+    a.out_covs = static_cast<double *>(h->d_ut_out.p);
+  } else {
+    a.points = points;
+    a.covs2 = covs2;
+    a.out_bvs = out_bvs;
+    a.out_covs = out_covs;
+  }
+  a.use_bulk = (aligned16(a.points) && aligned16(a.covs2) && aligned16(a.out_bvs) &&
+                aligned16(a.out_covs) && !env_int("PNEC_B200_NO_BULK", 0)) ? 1 : 0;
+  keypoint_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, stream>>>(a);
+  PNEC_CUDA(cudaGetLastError());
+  h->launches++;
+  if (memspace == PNEC_MEM_HOST) {
+    PNEC_CUDA(cudaMemcpyAsync(out_bvs, a.out_bvs, nn * 24, cudaMemcpyDeviceToHost, stream));
+    PNEC_CUDA(cudaMemcpyAsync(out_covs, a.out_covs, nn * 72, cudaMemcpyDeviceToHost, stream));
     PNEC_CUDA(cudaStreamSynchronize(stream));
   }
   return PNEC_OK;

@@ -274,6 +274,33 @@ def test_unscented_transform_matches_oracle(handle, golden_ut, camera):
         handle.unscented_transform(mus, col(c3), K, 1.0, 5)
 
 
+def test_keypoints_unproject_matches_oracle(handle):
+    """pnec_keypoints_unproject_batch == KeyPoint::Unproject (keypoints.cc:49-62) restated in
+    the oracle; full TMA tiles, a ragged tail and unaligned device pointers."""
+    import torch
+
+    rng = np.random.default_rng(23)
+    n = 128 * 37 + 51
+    pts = np.stack([rng.uniform(0, 1241, n), rng.uniform(0, 376, n)], -1)
+    c2 = np.swapaxes(syn.sample_covariances_2d(rng, (1, n), 0.8, "anisotropic_inhomogenous")[0], -1, -2).reshape(n, 4)
+    Kinv = np.linalg.inv(np.array([[718.856, 0, 607.19], [0, 718.856, 185.2157], [0, 0, 1.0]])).T.reshape(9)
+    rb, rc = oracle.keypoints_unproject(pts, c2, Kinv)
+    hb, hc = handle.keypoints_unproject(pts, c2, Kinv)
+    db, dc = handle.keypoints_unproject(dev(pts), dev(c2), Kinv)
+    assert np.array_equal(hb, db.cpu().numpy()) and np.array_equal(hc, dc.cpu().numpy())
+    np.testing.assert_allclose(hb, rb, rtol=0, atol=1e-15)
+    np.testing.assert_allclose(hc, rc, rtol=0, atol=1e-12 * np.abs(rc).max())
+    flat = torch.empty(2 * n + 1, dtype=torch.float64, device="cuda")
+    shifted = flat[1:].view(n, 2)
+    shifted.copy_(torch.from_numpy(pts))
+    ub, uc = handle.keypoints_unproject(shifted, dev(c2), Kinv)  # plain (non-TMA) path
+    np.testing.assert_allclose(ub.cpu().numpy(), hb, rtol=0, atol=1e-15)
+    np.testing.assert_allclose(uc.cpu().numpy(), hc, rtol=0, atol=1e-13 * np.abs(hc).max())
+    # and the produced inputs drive the solver: bearing covariances are symmetric PSD, (numerically) rank 2
+    w = np.linalg.eigvalsh(hc.reshape(n, 3, 3))
+    assert (w[:, 2] > 0).all() and (np.abs(w[:, 0]) < 1e-5 * w[:, 2]).all()
+
+
 # -------------------------------------- BASELINE full size: structural properties
 
 

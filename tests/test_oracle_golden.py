@@ -54,6 +54,28 @@ def test_oracle_unscented_transform_matches_reference(golden_ut):
     np.testing.assert_allclose(a, col(syn.unscented_transform(mus, c3o, syn.OMNIDIRECTIONAL)), rtol=0, atol=1e-20)
 
 
+def test_oracle_keypoints_unproject_is_unproject_plus_unscented():
+    """KeyPoint::Unproject (keypoints.cc:49-62) == Unproject + pinhole unscented transform of
+    (x, y, 1) with the 2x2 covariance embedded in a 3x3."""
+    rng = np.random.default_rng(5)
+    n = 40
+    pts = np.stack([rng.uniform(0, 1241, n), rng.uniform(0, 376, n)], -1)
+    c2 = syn.sample_covariances_2d(rng, (1, n), 0.8, "anisotropic_inhomogenous")[0]
+    K = np.array([[718.856, 0, 607.19], [0, 718.856, 185.2157], [0, 0, 1.0]])
+    Kinv = np.linalg.inv(K)
+    bvs, covs = oracle.keypoints_unproject(pts, np.swapaxes(c2, -1, -2).reshape(n, 4), Kinv.T.reshape(9))
+    mu = np.concatenate([pts, np.ones((n, 1))], -1)
+    ray = mu @ Kinv.T
+    np.testing.assert_allclose(bvs, ray / np.linalg.norm(ray, axis=1, keepdims=True), atol=1e-15)
+    c3 = np.zeros((n, 3, 3))
+    c3[:, :2, :2] = c2
+    # numpy generator with K_inv applied by hand: sigma points in pixel space, rays through K_inv
+    ref = oracle.unscented_transform(mu, np.swapaxes(c3, -1, -2).reshape(n, 9), Kinv.T.reshape(9), 1.0, oracle.PINHOLE)
+    np.testing.assert_array_equal(covs, ref)
+    w = np.linalg.eigvalsh(covs.reshape(n, 3, 3))
+    assert (w[:, 2] > 0).all() and (np.abs(w[:, 0]) < 1e-5 * w[:, 2]).all()  # ~rank 2: tangent plane
+
+
 VARIANTS = {"nec": oracle.NEC, "target": oracle.TARGET, "host": oracle.HOST,
             "symmetric": oracle.SYMMETRIC}
 CASES = ["c1_iso_omni_n100", "c2_aniso_omni_n512", "aniso_pinhole_n64", "aniso_omni_n10"]

@@ -79,5 +79,14 @@ for cam, nm in ((api.CAMERA_PINHOLE, "pinhole"), (api.CAMERA_OMNIDIRECTIONAL, "o
     row = dict(config=f"unscented transform {nm}, {n} points", points=n, ms=ms, points_per_s=n / ms * 1e3,
                GBps=n * 168 / ms / 1e6, algorithmic_bytes_per_point=168)
     rows.append(row); print(json.dumps(row), flush=True)
+# keypoints -> solver inputs (KeyPoint::Unproject): 48 B in, 96 B out per keypoint
+pts = np.stack([rng.uniform(0, 1241, n), rng.uniform(0, 376, n)], -1)
+c2 = np.tile(np.array([0.6, 0.1, 0.1, 0.4]), (n, 1))
+Kinv = np.linalg.inv(np.array([[718.856, 0, 607.19], [0, 718.856, 185.2157], [0, 0, 1.0]])).T.reshape(9)
+dp, dc2 = T(pts), T(c2)
+ms = timeit(lambda: h.keypoints_unproject(dp, dc2, Kinv))
+row = dict(config=f"keypoints unproject, {n} keypoints", points=n, ms=ms, points_per_s=n / ms * 1e3,
+           GBps=n * 144 / ms / 1e6, algorithmic_bytes_per_point=144)
+rows.append(row); print(json.dumps(row), flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(rows, open("gpurun_out/configs_r01.json", "w"), indent=1)
