@@ -479,6 +479,54 @@ class NECCeres : public detail_opt::CeresLike {
 
 }  // namespace optimization
 
+// ------------------------------------------------ translation given rotation
+
+namespace common {
+// src/common/common.cc:127-181 composed: the NEC translation for a given rotation (GPU).
+// (ComposeM skips the first correspondence, as in the reference.)
+template <class BVs>
+inline Vec3 TranslationFromM_ComposeM(const BVs &bvs_1, const BVs &bvs_2, const Mat3 &rotation) {
+  const SE3 pose(rotation, Vec3(0, 0, 1));
+  pnec_batch b{};
+  b.num_problems = 1;
+  b.n_per_problem = static_cast<int64_t>(bvs_1.size());
+  b.memspace = PNEC_MEM_HOST;
+  b.bvs_host = detail::AsDoubles(bvs_1, 24);
+  b.bvs_target = detail::AsDoubles(bvs_2, 24);
+  b.poses = pose.data();
+  Vec3 t;
+  if (pnec_nec_translation_batch(detail::Handle(), &b, t.data(), nullptr, nullptr) != PNEC_OK)
+    throw std::runtime_error(std::string("pnec_nec_translation_batch: ") + pnec_last_error());
+  return t;
+}
+
+}  // namespace common
+
+namespace optimization {
+// The translation half of PNEC::WeightedEigensolver for a given rotation (pnec.cc:317-343):
+// builds A_i / B_i, scans {initial_translation} + fibonacci_sphere(500) and runs scf(..., 10)
+// (src/optimization/scf.cc).  Sign of the result is arbitrary, as with Eigen's eigenvectors.
+template <class BVs, class Covs>
+inline Vec3 ScfTranslation(const BVs &bvs_1, const BVs &bvs_2, const Covs &projected_covariances,
+                           const Mat3 &rotation, const Vec3 &initial_translation, double regularization,
+                           int fibonacci_samples = 500, int scf_steps = 10) {
+  const SE3 pose0(rotation, initial_translation);
+  pnec_batch b{};
+  b.num_problems = 1;
+  b.n_per_problem = static_cast<int64_t>(bvs_1.size());
+  b.memspace = PNEC_MEM_HOST;
+  b.bvs_host = detail::AsDoubles(bvs_1, 24);
+  b.bvs_target = detail::AsDoubles(bvs_2, 24);
+  b.covs_target = detail::AsDoubles(projected_covariances, 72);
+  b.poses = pose0.data();
+  Vec3 t;
+  if (pnec_scf_translation_batch(detail::Handle(), &b, regularization, fibonacci_samples, scf_steps,
+                                 t.data(), nullptr, nullptr) != PNEC_OK)
+    throw std::runtime_error(std::string("pnec_scf_translation_batch: ") + pnec_last_error());
+  return t;
+}
+}  // namespace optimization
+
 // ------------------------------------------------------------------- features
 
 namespace features {

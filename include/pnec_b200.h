@@ -208,6 +208,31 @@ int pnec_keypoints_unproject_batch(pnec_handle *h, int64_t n, int32_t memspace,
                                    const double *K_inv, double *out_bvs, double *out_covs,
                                    void *cuda_stream);
 
+/* Translation given rotation, probabilistic: the SCF stage of PNEC::WeightedEigensolver
+ * (src/rel_pose_estimation/pnec.cc:317-343) for B frame pairs.  Per pair, with R the rotation
+ * and t0 the translation of `batch->poses`:
+ *   A_i = n_i n_i^T, n_i = f1 x R f2;   B_i = [f1]x R S_i R^T [f1]x^T + regularization * I
+ *   start = first strict minimiser of sum_i t^T A_i t / t^T B_i t over {t0} followed by
+ *           fibonacci_sphere(fibonacci_samples)            (src/optimization/scf.cc:43-72)
+ *   then `scf_steps` iterations t <- eigenvector of the smallest eigenvalue of
+ *           E(t) = sum_i A_i / (t^T B_i t)                 (scf.cc:109-147, including the
+ *           `frac.resize(n)` + push_back quirk that makes frac[i] == 0)
+ * The reference calls it with 500 samples and 10 steps.  The sign of the result is that of the
+ * eigenvector routine (arbitrary, as with Eigen): compare modulo sign.  Pairs are limited to
+ * ~3100 correspondences (shared-memory resident); larger ones return PNEC_ERR_UNSUPPORTED.
+ *   out_translations [B][3]      out_cost [B] objective at the result, or NULL */
+int pnec_scf_translation_batch(pnec_handle *h, const pnec_batch *batch, double regularization,
+                               int32_t fibonacci_samples, int32_t scf_steps,
+                               double *out_translations, double *out_cost, void *cuda_stream);
+
+/* Translation given rotation, NEC: TranslationFromM(ComposeM(bvs_1, bvs_2, R))
+ * (src/common/common.cc:127-181; the translation of PNEC::Eigensolver, pnec.cc:270-278):
+ * M = sum_{i >= 1} n_i n_i^T (ComposeM skips the first correspondence, common.cc:131) and the
+ * unit eigenvector of its smallest eigenvalue (sign arbitrary).
+ *   out_translations [B][3]      out_M [B][6] (xx xy xz yy yz zz) or NULL */
+int pnec_nec_translation_batch(pnec_handle *h, const pnec_batch *batch, double *out_translations,
+                               double *out_M, void *cuda_stream);
+
 /* Number of kernels this handle has launched so far (bench bookkeeping). */
 int64_t pnec_launch_count(const pnec_handle *h);
 

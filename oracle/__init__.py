@@ -131,6 +131,15 @@ def lib() -> ctypes.CDLL:
         L.oracle_unscented_transform_batch.restype = None
         L.oracle_keypoints_unproject_batch.argtypes = [ctypes.c_int64, dp, dp, dp, dp, dp]
         L.oracle_keypoints_unproject_batch.restype = None
+        L.oracle_fibonacci_sphere.argtypes = [ctypes.c_int, dp]
+        L.oracle_fibonacci_sphere.restype = None
+        L.oracle_scf_objective.argtypes = [ctypes.c_int64, dp, dp, dp]
+        L.oracle_scf_objective.restype = ctypes.c_double
+        L.oracle_scf_translation.argtypes = [ctypes.c_int64, dp, dp, dp, dp, ctypes.c_double, ctypes.c_int,
+                                             ctypes.c_int, dp, dp]
+        L.oracle_scf_translation.restype = ctypes.c_int
+        L.oracle_nec_translation.argtypes = [ctypes.c_int64, dp, dp, dp, dp, dp]
+        L.oracle_nec_translation.restype = None
         _lib = L
     return _lib
 
@@ -287,3 +296,36 @@ def keypoints_unproject(points, covs2, K_inv):
     bvs, covs = np.zeros((points.shape[0], 3)), np.zeros((points.shape[0], 9))
     lib().oracle_keypoints_unproject_batch(points.shape[0], _dp(points), _dp(covs2), _dp(K), _dp(bvs), _dp(covs))
     return bvs, covs
+
+
+def fibonacci_sphere(samples: int) -> np.ndarray:
+    """pnec::optimization::fibonacci_sphere (scf.cc:53-72) -> (samples, 3)."""
+    pts = np.zeros((samples, 3))
+    lib().oracle_fibonacci_sphere(int(samples), _dp(pts))
+    return pts
+
+
+def scf_objective(A, B, t) -> float:
+    """pnec::optimization::obj_fun (scf.cc:43-51); A, B (n,3,3) row-indexed."""
+    A, B, t = _c(A, (3, 3)), _c(B, (3, 3)), _c(t)
+    return float(lib().oracle_scf_objective(A.shape[0], _dp(A), _dp(B), _dp(t)))
+
+
+def scf_translation(f1, f2, cov, pose7, reg=1e-13, samples=500, steps=10):
+    """SCF stage of PNEC::WeightedEigensolver for one pair -> (t (3,), objective)."""
+    f1, f2, cov, pose7 = _c(f1, (3,)), _c(f2, (3,)), _c(cov, (9,)), _c(pose7)
+    t = np.zeros(3)
+    cost = ctypes.c_double()
+    rc = lib().oracle_scf_translation(f1.shape[0], _dp(f1), _dp(f2), _dp(cov), _dp(pose7), float(reg),
+                                      int(samples), int(steps), _dp(t), ctypes.byref(cost))
+    if rc != 0:
+        raise RuntimeError("oracle_scf_translation failed")
+    return t, cost.value
+
+
+def nec_translation(f1, f2, pose7):
+    """TranslationFromM(ComposeM(...)) (common.cc:127-181) -> (t (3,), M6 (6,))."""
+    f1, f2, pose7 = _c(f1, (3,)), _c(f2, (3,)), _c(pose7)
+    t, M = np.zeros(3), np.zeros(6)
+    lib().oracle_nec_translation(f1.shape[0], _dp(f1), _dp(f2), _dp(pose7), _dp(t), _dp(M))
+    return t, M

@@ -937,3 +937,158 @@ void oracle_keypoints_unproject_batch(int64_t n, const double *points, const dou
     oracle_unscented_transform(mu, cov, K_inv, 1.0, 1, out_covs + 9 * i);
   }
 }
+
+/* ---------------------------------------------- translation given rotation */
+
+/* Smallest-eigenvalue eigenvector of a symmetric 3x3 by cyclic Jacobi rotations.  The
+ * reference uses Eigen::SelfAdjointEigenSolver (scf.cc:135) / Eigen::EigenSolver
+ * (common.cc:158); any converged symmetric eigen-solver gives the same eigenvector up to
+ * rounding and SIGN (Eigen's sign is an implementation detail: compare modulo sign). */
+static void sym3_smallest_eigvec(const double M[3][3], double v[3], double *lambda) {
+  double a[3][3], q[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  memcpy(a, M, sizeof(a));
+  for (int sweep = 0; sweep < 50; ++sweep) {
+    const double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
+    const double diag = a[0][0] * a[0][0] + a[1][1] * a[1][1] + a[2][2] * a[2][2];
+    if (off <= 1e-34 * diag || off == 0.0) break;
+    for (int p = 0; p < 2; ++p)
+      for (int r = p + 1; r < 3; ++r) {
+        if (a[p][r] == 0.0) continue;
+        const double theta = (a[r][r] - a[p][p]) / (2.0 * a[p][r]);
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+        for (int k = 0; k < 3; ++k) {
+          const double akp = a[k][p], akr = a[k][r];
+          a[k][p] = c * akp - sn * akr;
+          a[k][r] = sn * akp + c * akr;
+        }
+        for (int k = 0; k < 3; ++k) {
+          const double apk = a[p][k], ark = a[r][k];
+          a[p][k] = c * apk - sn * ark;
+          a[r][k] = sn * apk + c * ark;
+        }
+        for (int k = 0; k < 3; ++k) {
+          const double qkp = q[k][p], qkr = q[k][r];
+          q[k][p] = c * qkp - sn * qkr;
+          q[k][r] = sn * qkp + c * qkr;
+        }
+      }
+  }
+  int j = 0;
+  if (a[1][1] < a[j][j]) j = 1;
+  if (a[2][2] < a[j][j]) j = 2;
+  *lambda = a[j][j];
+  const double nv = sqrt(q[0][j] * q[0][j] + q[1][j] * q[1][j] + q[2][j] * q[2][j]);
+  for (int k = 0; k < 3; ++k) v[k] = q[k][j] / nv;
+}
+
+/* pnec::optimization::fibonacci_sphere, src/optimization/scf.cc:53-72 (float casts included). */
+void oracle_fibonacci_sphere(int samples, double *points) {
+  const double phi = M_PI * (3.0 - sqrt(5.0));
+  for (int i = 0; i < samples; ++i) {
+    const double y = 1.0 - ((float)i / (float)(samples - 1)) * 2.0;
+    const double radius = sqrt(1 - y * y);
+    const double theta = phi * (float)i;
+    points[3 * i] = cos(theta) * radius;
+    points[3 * i + 1] = y;
+    points[3 * i + 2] = sin(theta) * radius;
+  }
+}
+
+/* pnec::optimization::obj_fun, scf.cc:43-51 */
+static double scf_obj_fun(const double t[3], int64_t n, const double (*A)[3][3], const double (*B)[3][3]) {
+  double cost = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    double At[3], Bt[3];
+    matvec(A[i], t, At);
+    matvec(B[i], t, Bt);
+    cost += dot3(t, At) / dot3(t, Bt);
+  }
+  return cost;
+}
+
+double oracle_scf_objective(int64_t n, const double *A, const double *B, const double t[3]) {
+  return scf_obj_fun(t, n, (const double(*)[3][3])A, (const double(*)[3][3])B);
+}
+
+/* The SCF stage of PNEC::WeightedEigensolver for one frame pair:
+ * A_i / B_i (pnec.cc:317-328), Fibonacci scan (pnec.cc:330-340), scf (scf.cc:128-147 with
+ * alt_construct_E, scf.cc:109-126, whose `frac` vector is all zeros for i < n). */
+int oracle_scf_translation(int64_t n, const double *f1, const double *f2, const double *cov,
+                           const double pose7[7], double reg, int samples, int steps,
+                           double out_t[3], double *out_cost) {
+  double R[3][3], Rt[3][3];
+  pose_rot(pose7, R);
+  transpose(R, Rt);
+  double(*A)[3][3] = malloc(sizeof(double[3][3]) * ((size_t)n + 1));
+  double(*Bm)[3][3] = malloc(sizeof(double[3][3]) * ((size_t)n + 1));
+  double *pts = malloc(sizeof(double) * 3 * (size_t)(samples > 0 ? samples : 1));
+  if (!A || !Bm || !pts) return -1;
+  for (int64_t i = 0; i < n; ++i) {
+    double F[3][3], Ft[3][3], S[3][3], g[3], v[3], T1[3][3], T2[3][3];
+    skew(f1 + 3 * i, F);
+    transpose(F, Ft);
+    load_cov(cov + 9 * i, S);
+    matvec(R, f2 + 3 * i, g);
+    matvec(F, g, v); /* bv1_skew * rotation * bvs2[i] */
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) A[i][r][c] = v[r] * v[c];
+    matmul(F, R, T1);
+    matmul(T1, S, T2);
+    matmul(T2, Rt, T1);
+    matmul(T1, Ft, Bm[i]);
+    for (int r = 0; r < 3; ++r) Bm[i][r][r] += reg;
+  }
+  oracle_fibonacci_sphere(samples, pts);
+  double best[3] = {pose7[4], pose7[5], pose7[6]};
+  double best_cost = scf_obj_fun(best, n, A, Bm);
+  for (int k = 0; k < samples; ++k) {
+    const double c = scf_obj_fun(pts + 3 * k, n, A, Bm);
+    if (c < best_cost) {
+      best_cost = c;
+      memcpy(best, pts + 3 * k, sizeof(best));
+    }
+  }
+  double t[3] = {best[0], best[1], best[2]};
+  for (int it = 0; it < steps; ++it) {
+    double E[3][3];
+    memset(E, 0, sizeof(E));
+    for (int64_t i = 0; i < n; ++i) {
+      double Bt[3];
+      matvec(Bm[i], t, Bt);
+      const double phi_B = dot3(t, Bt);
+      const double frac = 0.0; /* sic: frac.resize(n) followed by push_back */
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) E[r][c] += (1.0 / phi_B) * (A[i][r][c] - frac * Bm[i][r][c]);
+    }
+    double lam;
+    sym3_smallest_eigvec(E, t, &lam);
+  }
+  memcpy(out_t, t, sizeof(t));
+  if (out_cost) *out_cost = scf_obj_fun(t, n, A, Bm);
+  free(A);
+  free(Bm);
+  free(pts);
+  return 0;
+}
+
+/* TranslationFromM(ComposeM(bvs_1, bvs_2, R)), common.cc:127-181.  out_M: xx xy xz yy yz zz. */
+void oracle_nec_translation(int64_t n, const double *f1, const double *f2, const double pose7[7],
+                            double out_t[3], double *out_M) {
+  double R[3][3], M[3][3];
+  pose_rot(pose7, R);
+  memset(M, 0, sizeof(M));
+  for (int64_t i = 1; i < n; ++i) { /* sic: ComposeM starts at i = 1 */
+    double g[3], nrm[3];
+    matvec(R, f2 + 3 * i, g);
+    cross3(f1 + 3 * i, g, nrm);
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) M[r][c] += nrm[r] * nrm[c];
+  }
+  double lam;
+  sym3_smallest_eigvec(M, out_t, &lam);
+  if (out_M) {
+    out_M[0] = M[0][0]; out_M[1] = M[0][1]; out_M[2] = M[0][2];
+    out_M[3] = M[1][1]; out_M[4] = M[1][2]; out_M[5] = M[2][2];
+  }
+}

@@ -44,6 +44,8 @@ EXPORTED_SYMBOLS = (
     "pnec_cost_function_batch",
     "pnec_unscented_transform_batch",
     "pnec_keypoints_unproject_batch",
+    "pnec_scf_translation_batch",
+    "pnec_nec_translation_batch",
     "pnec_launch_count",
 )
 
@@ -151,6 +153,13 @@ def load_library() -> ctypes.CDLL:
                                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     L.pnec_keypoints_unproject_batch.restype = ctypes.c_int
+    L.pnec_scf_translation_batch.argtypes = [ctypes.c_void_p, ctypes.POINTER(_Batch), ctypes.c_double,
+                                             ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
+                                             ctypes.c_void_p, ctypes.c_void_p]
+    L.pnec_scf_translation_batch.restype = ctypes.c_int
+    L.pnec_nec_translation_batch.argtypes = [ctypes.c_void_p, ctypes.POINTER(_Batch), ctypes.c_void_p,
+                                             ctypes.c_void_p, ctypes.c_void_p]
+    L.pnec_nec_translation_batch.restype = ctypes.c_int
     L.pnec_launch_count.argtypes = [ctypes.c_void_p]
     L.pnec_launch_count.restype = ctypes.c_int64
     _lib = L
@@ -436,6 +445,40 @@ class Handle:
             ctypes.c_void_p(ptrs[3]), self._stream(device))
         self._check(rc, "pnec_keypoints_unproject_batch")
         return bvs, covs
+
+
+    def _out(self, device, shape):
+        if device:
+            import torch
+
+            t = torch.empty(shape, dtype=torch.float64, device=torch.device("cuda", self.device))
+            return t, ctypes.c_void_p(t.data_ptr())
+        a = np.empty(shape)
+        return a, ctypes.c_void_p(a.ctypes.data)
+
+    def scf_translation_batch(self, bvs_host, bvs_target, covs_target, poses, regularization=1e-13,
+                              fibonacci_samples=500, scf_steps=10, *, offsets=None, n_per_problem=None):
+        """Translation given rotation by Fibonacci scan + SCF (pnec.cc:317-343, scf.cc) ->
+        (translations (B,3), objective (B,)).  `poses`: rotation quaternion + start translation."""
+        keep = []
+        b, device, B = self._batch(bvs_host, bvs_target, covs_target, None, poses, offsets, n_per_problem, keep)
+        t, pt = self._out(device, (B, 3))
+        c, pc = self._out(device, (B,))
+        rc = self._lib.pnec_scf_translation_batch(self._h, ctypes.byref(b), float(regularization),
+                                                  int(fibonacci_samples), int(scf_steps), pt, pc,
+                                                  self._stream(device))
+        self._check(rc, "pnec_scf_translation_batch")
+        return t, c
+
+    def nec_translation_batch(self, bvs_host, bvs_target, poses, *, offsets=None, n_per_problem=None):
+        """TranslationFromM(ComposeM(...)) (common.cc:127-181) -> (translations (B,3), M (B,6))."""
+        keep = []
+        b, device, B = self._batch(bvs_host, bvs_target, None, None, poses, offsets, n_per_problem, keep)
+        t, pt = self._out(device, (B, 3))
+        m, pm = self._out(device, (B, 6))
+        rc = self._lib.pnec_nec_translation_batch(self._h, ctypes.byref(b), pt, pm, self._stream(device))
+        self._check(rc, "pnec_nec_translation_batch")
+        return t, m
 
 
 _default_handles = {}

@@ -4,8 +4,10 @@
 //   pnec_solve.cuh   solve_kernel / solve_stream_kernel: whole LM solve per frame pair on device
 //   pnec_eval.cuh    eval_warp_kernel (K1): fused residual + Jacobian + J^T J, the roofline kernel
 //   pnec_aux.cuh     cost_kernel (parity metric), unscented_kernel (covariance propagation)
+//   pnec_translation.cuh  scf_kernel / nec_translation_kernel: translation given rotation
 //   pnec_lm.cuh      Ceres-semantics Levenberg-Marquardt update; pnec_device.cuh: the math
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -16,6 +18,7 @@
 #include "pnec_aux.cuh"
 #include "pnec_eval.cuh"
 #include "pnec_solve.cuh"
+#include "pnec_translation.cuh"
 
 // =================================================================== host side
 
@@ -74,7 +77,8 @@ struct pnec_handle {
   // staging for HOST-memspace calls and for the device copy of offsets
   DevBuf d_f1, d_f2, d_ct, d_ch, d_off, d_poses;
   DevBuf d_out_poses, d_out_status, d_out_iters, d_out_cost, d_out_init, d_out_grad, d_out_jtj;
-  DevBuf d_ut_mu, d_ut_cov, d_ut_out, d_kp_bv;
+  DevBuf d_ut_mu, d_ut_cov, d_ut_out, d_kp_bv, d_sphere, d_tr_out, d_tr_aux;
+  int sphere_samples = -1;
   std::mutex mu;
 };
 
@@ -451,7 +455,8 @@ void pnec_destroy(pnec_handle *h) {
   DevBuf *bufs[] = {&h->d_f1, &h->d_f2, &h->d_ct, &h->d_ch, &h->d_off, &h->d_poses,
                     &h->d_out_poses, &h->d_out_status, &h->d_out_iters, &h->d_out_cost,
                     &h->d_out_init, &h->d_out_grad, &h->d_out_jtj, &h->d_ut_mu, &h->d_ut_cov,
-                    &h->d_ut_out, &h->d_kp_bv};
+                    &h->d_ut_out, &h->d_kp_bv, &h->d_sphere, &h->d_tr_out,
+                    &h->d_tr_aux};
   for (DevBuf *b : bufs) b->release();
   delete h;
 }
@@ -681,6 +686,105 @@ int pnec_keypoints_unproject_batch(pnec_handle *h, int64_t n, int32_t memspace, 
   if (memspace == PNEC_MEM_HOST) {
     PNEC_CUDA(cudaMemcpyAsync(out_bvs, a.out_bvs, nn * 24, cudaMemcpyDeviceToHost, stream));
     PNEC_CUDA(cudaMemcpyAsync(out_covs, a.out_covs, nn * 72, cudaMemcpyDeviceToHost, stream));
+    PNEC_CUDA(cudaStreamSynchronize(stream));
+  }
+  return PNEC_OK;
+}
+
+int pnec_scf_translation_batch(pnec_handle *h, const pnec_batch *batch, double regularization,
+                               int32_t fibonacci_samples, int32_t scf_steps, double *out_translations,
+                               double *out_cost, void *cuda_stream) {
+  if (!h || !out_translations) return fail(PNEC_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (fibonacci_samples < 0 || scf_steps < 0)
+    return fail(PNEC_ERR_INVALID_ARGUMENT, "negative sample / step count");
+  int rc = validate_batch(batch, PNEC_VARIANT_TARGET, true);
+  if (rc != PNEC_OK) return rc;
+  const long long B = batch->num_problems;
+  if (B == 0) return PNEC_OK;
+  std::lock_guard<std::mutex> lock(h->mu);
+  PNEC_CUDA(cudaSetDevice(h->device));
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  Staged st;
+  rc = stage_batch(h, batch, PNEC_VARIANT_TARGET, stream, &st);
+  if (rc != PNEC_OK) return rc;
+  const size_t dyn = static_cast<size_t>(std::max<long long>(st.max_n, 1)) * 72;
+  if (dyn + kStaticSmemReserve > h->smem_optin)
+    return fail(PNEC_ERR_UNSUPPORTED, "pnec_scf_translation_batch: a frame pair exceeds the shared-memory capacity (~3100 correspondences)");
+  // fibonacci_sphere(samples), scf.cc:53-72, with its float casts
+  if (h->sphere_samples != fibonacci_samples) {
+    std::vector<double> pts(static_cast<size_t>(std::max(fibonacci_samples, 1)) * 3);
+    const double phi = M_PI * (3.0 - std::sqrt(5.0));
+    for (int i = 0; i < fibonacci_samples; ++i) {
+      const double y = 1.0 - ((float)i / (float)(fibonacci_samples - 1)) * 2.0;
+      const double radius = std::sqrt(1 - y * y);
+      const double theta = phi * (float)i;
+      pts[3 * i] = std::cos(theta) * radius;
+      pts[3 * i + 1] = y;
+      pts[3 * i + 2] = std::sin(theta) * radius;
+    }
+    PNEC_CUDA(h->d_sphere.ensure(pts.size() * 8));
+    PNEC_CUDA(cudaMemcpy(h->d_sphere.p, pts.data(), pts.size() * 8, cudaMemcpyHostToDevice));
+    h->sphere_samples = fibonacci_samples;
+  }
+  ScfArgs a{};
+  a.bv = st.bv;
+  a.sphere = static_cast<const double *>(h->d_sphere.p);
+  a.reg = regularization;
+  a.samples = fibonacci_samples;
+  a.steps = scf_steps;
+  a.cap_elems = static_cast<int>(dyn / 72);
+  const bool host = batch->memspace == PNEC_MEM_HOST;
+  if (host) {
+    PNEC_CUDA(h->d_tr_out.ensure(static_cast<size_t>(B) * 24));
+    PNEC_CUDA(h->d_tr_aux.ensure(static_cast<size_t>(B) * 8));
+    a.out_t = static_cast<double *>(h->d_tr_out.p);
+    a.out_cost = out_cost ? static_cast<double *>(h->d_tr_aux.p) : nullptr;
+  } else {
+    a.out_t = out_translations;
+    a.out_cost = out_cost;
+  }
+  auto kern = scf_kernel<4>;
+  PNEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
+  kern<<<static_cast<unsigned>(B), 128, dyn, stream>>>(a);
+  PNEC_CUDA(cudaGetLastError());
+  h->launches++;
+  if (host) {
+    PNEC_CUDA(cudaMemcpyAsync(out_translations, a.out_t, static_cast<size_t>(B) * 24, cudaMemcpyDeviceToHost, stream));
+    if (out_cost)
+      PNEC_CUDA(cudaMemcpyAsync(out_cost, a.out_cost, static_cast<size_t>(B) * 8, cudaMemcpyDeviceToHost, stream));
+    PNEC_CUDA(cudaStreamSynchronize(stream));
+  }
+  return PNEC_OK;
+}
+
+int pnec_nec_translation_batch(pnec_handle *h, const pnec_batch *batch, double *out_translations,
+                               double *out_M, void *cuda_stream) {
+  if (!h || !out_translations) return fail(PNEC_ERR_INVALID_ARGUMENT, "NULL argument");
+  int rc = validate_batch(batch, PNEC_VARIANT_NEC, true);
+  if (rc != PNEC_OK) return rc;
+  const long long B = batch->num_problems;
+  if (B == 0) return PNEC_OK;
+  std::lock_guard<std::mutex> lock(h->mu);
+  PNEC_CUDA(cudaSetDevice(h->device));
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  Staged st;
+  rc = stage_batch(h, batch, PNEC_VARIANT_NEC, stream, &st);
+  if (rc != PNEC_OK) return rc;
+  const bool host = batch->memspace == PNEC_MEM_HOST;
+  double *d_t = out_translations, *d_M = out_M;
+  if (host) {
+    PNEC_CUDA(h->d_tr_out.ensure(static_cast<size_t>(B) * 24));
+    PNEC_CUDA(h->d_tr_aux.ensure(static_cast<size_t>(B) * 48));
+    d_t = static_cast<double *>(h->d_tr_out.p);
+    d_M = out_M ? static_cast<double *>(h->d_tr_aux.p) : nullptr;
+  }
+  nec_translation_kernel<<<static_cast<unsigned>(B), 128, 0, stream>>>(st.bv, d_t, d_M);
+  PNEC_CUDA(cudaGetLastError());
+  h->launches++;
+  if (host) {
+    PNEC_CUDA(cudaMemcpyAsync(out_translations, d_t, static_cast<size_t>(B) * 24, cudaMemcpyDeviceToHost, stream));
+    if (out_M)
+      PNEC_CUDA(cudaMemcpyAsync(out_M, d_M, static_cast<size_t>(B) * 48, cudaMemcpyDeviceToHost, stream));
     PNEC_CUDA(cudaStreamSynchronize(stream));
   }
   return PNEC_OK;

@@ -34,6 +34,11 @@ def golden_ut():
 
 
 @pytest.fixture(scope="session")
+def golden_scf():
+    return np.load(os.path.join(GOLDEN, "reference_scf.npz"))
+
+
+@pytest.fixture(scope="session")
 def golden_solutions():
     return np.load(os.path.join(GOLDEN, "oracle_solutions.npz"))
 

@@ -98,6 +98,26 @@ def reference_fixtures():
              ut_omni=ut_omni, ut_pinhole=ut_pin)
 
 
+def reference_scf_fixtures():
+    """scripts/pnec/scf.py: fibonacci_sphere (double arithmetic; the C++ of scf.cc:53-72 casts
+    to float, so agreement is ~1e-7, not exact) and obj_fun (the sum of Rayleigh quotients)."""
+    sys.path.insert(0, REF_SCRIPTS)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import pnec.scf as rscf
+    rng = np.random.default_rng(77)
+    k = 12
+    v = rng.standard_normal((k, 3))
+    Ai = v[:, :, None] * v[:, None, :]
+    L = rng.standard_normal((k, 3, 3))
+    Bi = L @ np.swapaxes(L, -1, -2) + 0.1 * np.eye(3)
+    X = rng.standard_normal((9, 3))
+    X /= np.linalg.norm(X, axis=1, keepdims=True)
+    obj = rscf.obj_fun(X, Ai, Bi, n=3, k=k)
+    np.savez(os.path.join(HERE, "reference_scf.npz"), fibonacci_500=rscf.fibonacci_sphere(500),
+             Ai=Ai, Bi=Bi, X=X, obj_fun=obj)
+
+
 def oracle_fixtures():
     import oracle
     from pnec_b200 import synthetic as syn
@@ -148,6 +168,7 @@ def oracle_fixtures():
 
 if __name__ == "__main__":
     reference_fixtures()
+    reference_scf_fixtures()
     oracle_fixtures()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

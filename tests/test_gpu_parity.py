@@ -301,6 +301,43 @@ def test_keypoints_unproject_matches_oracle(handle):
     assert (w[:, 2] > 0).all() and (np.abs(w[:, 0]) < 1e-5 * w[:, 2]).all()
 
 
+def test_translation_given_rotation_matches_oracle(handle):
+    """pnec_scf_translation_batch / pnec_nec_translation_batch vs the oracle's restatement of
+    pnec.cc:317-343 + scf.cc and common.cc:127-181: direction within 1e-6 rad modulo sign (the
+    eigenvector sign is arbitrary in the reference too)."""
+    counts = np.array([40, 100, 257, 512, 33, 1000, 64, 5])
+    b = syn.make_batch(len(counts), 0, seed=91, counts=counts)
+    # start translations away from the optimum so that the Fibonacci scan matters
+    poses = b.gt_poses.copy()
+    poses[:, 4:] = syn._normalize(np.random.default_rng(2).standard_normal((len(counts), 3)))
+    t, c = handle.scf_translation_batch(b.bvs_host, b.bvs_target, b.covs_target, poses, 1e-13, 500, 10,
+                                        offsets=b.offsets)
+    td, cd = handle.scf_translation_batch(dev(b.bvs_host), dev(b.bvs_target), dev(b.covs_target), dev(poses),
+                                          1e-13, 500, 10, offsets=b.offsets)
+    assert np.array_equal(t, td.cpu().numpy()) and np.array_equal(c, cd.cpu().numpy())
+    tn, M = handle.nec_translation_batch(b.bvs_host, b.bvs_target, poses, offsets=b.offsets)
+    for i in range(len(counts)):
+        f1, f2, ct, _ = b.problem(i)
+        rt, rc = oracle.scf_translation(f1, f2, ct, poses[i], 1e-13, 500, 10)
+        assert direction_angle(t[i], rt) <= DIR_TOL, i
+        assert c[i] == pytest.approx(rc, rel=1e-9)
+        rn, rM = oracle.nec_translation(f1, f2, poses[i])
+        np.testing.assert_allclose(M[i], rM, rtol=0, atol=1e-12 * np.abs(rM).max())
+        if counts[i] >= 10:
+            assert direction_angle(tn[i], rn) <= DIR_TOL, i
+    # fewer scan samples / steps are honoured
+    t0, _ = handle.scf_translation_batch(b.bvs_host, b.bvs_target, b.covs_target, poses, 1e-13, 0, 0,
+                                         offsets=b.offsets)
+    np.testing.assert_array_equal(t0, poses[:, 4:])
+    t3, _ = handle.scf_translation_batch(b.bvs_host, b.bvs_target, b.covs_target, poses, 1e-10, 50, 3,
+                                         offsets=b.offsets)
+    r3, _ = oracle.scf_translation(*b.problem(3)[:3], poses[3], 1e-10, 50, 3)
+    assert direction_angle(t3[3], r3) <= DIR_TOL
+    with pytest.raises(api.PnecError, match="capacity"):
+        big = syn.make_batch(1, 4000, seed=1)
+        handle.scf_translation_batch(big.bvs_host, big.bvs_target, big.covs_target, big.gt_poses, n_per_problem=4000)
+
+
 # -------------------------------------- BASELINE full size: structural properties
 
 

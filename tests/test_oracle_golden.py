@@ -76,6 +76,44 @@ def test_oracle_keypoints_unproject_is_unproject_plus_unscented():
     assert (w[:, 2] > 0).all() and (np.abs(w[:, 0]) < 1e-5 * w[:, 2]).all()  # ~rank 2: tangent plane
 
 
+def test_oracle_scf_pieces_match_reference(golden_scf):
+    """obj_fun and fibonacci_sphere vs scripts/pnec/scf.py (committed outputs).  The C++
+    fibonacci_sphere casts to float (scf.cc:59,63), the python does not: 1e-6 agreement."""
+    g = golden_scf
+    for x, o in zip(g["X"], g["obj_fun"]):
+        assert oracle.scf_objective(g["Ai"], g["Bi"], x) == pytest.approx(float(o), rel=1e-13)
+    pts = oracle.fibonacci_sphere(500)
+    np.testing.assert_allclose(pts, g["fibonacci_500"], atol=2e-6)
+    np.testing.assert_allclose(np.linalg.norm(pts, axis=1), 1.0, atol=1e-15)
+    assert pts[0].tolist() == [0.0, 1.0, 0.0]
+
+
+def test_oracle_translation_given_rotation():
+    """SCF translation (pnec.cc:317-343 + scf.cc) and NEC translation (common.cc:127-181) at
+    the ground-truth rotation recover the ground-truth direction up to the noise level."""
+    b = syn.make_batch(4, 300, seed=8)
+    for i in range(4):
+        f1, f2, ct, _ = b.problem(i)
+        t, cost = oracle.scf_translation(f1, f2, ct, b.gt_poses[i], 1e-13, 500, 10)
+        assert np.linalg.norm(t) == pytest.approx(1.0, abs=1e-14)
+        assert direction_angle(t, b.gt_poses[i][4:]) < 5e-3
+        # the SCF fixed point does not depend on where the scan starts from
+        p2 = b.gt_poses[i].copy()
+        p2[4:] = [0.3, -0.2, 0.93]
+        t2, cost2 = oracle.scf_translation(f1, f2, ct, p2, 1e-13, 500, 10)
+        assert direction_angle(t, t2) < 1e-9 and cost2 == pytest.approx(cost, rel=1e-12)
+        tn, M = oracle.nec_translation(f1, f2, b.gt_poses[i])
+        assert direction_angle(tn, b.gt_poses[i][4:]) < 2e-2
+        # ComposeM skips correspondence 0 (common.cc:131)
+        R = syn.quaternion_to_matrix(b.gt_poses[i][:4])
+        n = np.cross(f1[1:], f2[1:] @ R.T)
+        Mref = n.T @ n
+        np.testing.assert_allclose(M, [Mref[0, 0], Mref[0, 1], Mref[0, 2], Mref[1, 1], Mref[1, 2], Mref[2, 2]],
+                                   rtol=1e-12, atol=1e-18)
+        w, V = np.linalg.eigh(Mref)
+        assert direction_angle(tn, V[:, 0]) < 1e-9
+
+
 VARIANTS = {"nec": oracle.NEC, "target": oracle.TARGET, "host": oracle.HOST,
             "symmetric": oracle.SYMMETRIC}
 CASES = ["c1_iso_omni_n100", "c2_aniso_omni_n512", "aniso_pinhole_n64", "aniso_omni_n10"]

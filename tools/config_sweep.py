@@ -88,5 +88,17 @@ ms = timeit(lambda: h.keypoints_unproject(dp, dc2, Kinv))
 row = dict(config=f"keypoints unproject, {n} keypoints", points=n, ms=ms, points_per_s=n / ms * 1e3,
            GBps=n * 144 / ms / 1e6, algorithmic_bytes_per_point=144)
 rows.append(row); print(json.dumps(row), flush=True)
+# translation given rotation on the C2 shape
+base = syn.make_batch(500, 512, seed=6)
+f1_, f2_, ct_, init_ = (T(x) for x in tile_batch(base, 10000))
+ms = timeit(lambda: h.scf_translation_batch(f1_, f2_, ct_, init_, 1e-13, 500, 10, n_per_problem=512), reps=5, warm=2)
+row = dict(config="SCF translation (500-point scan + 10 SCF steps), 10000x512", points=10000, ms=ms,
+           points_per_s=10000 / ms * 1e3, GBps=10000 * 512 * 120 / ms / 1e6, algorithmic_bytes_per_point=512 * 120,
+           rayleigh_quotients_per_s=10000 * 512 * 501 / ms * 1e3)
+rows.append(row); print(json.dumps(row), flush=True)
+ms = timeit(lambda: h.nec_translation_batch(f1_, f2_, init_, n_per_problem=512))
+row = dict(config="NEC translation (ComposeM + TranslationFromM), 10000x512", points=10000, ms=ms,
+           points_per_s=10000 / ms * 1e3, GBps=10000 * 512 * 48 / ms / 1e6, algorithmic_bytes_per_point=512 * 48)
+rows.append(row); print(json.dumps(row), flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(rows, open("gpurun_out/configs_r01.json", "w"), indent=1)
