@@ -233,6 +233,67 @@ int pnec_scf_translation_batch(pnec_handle *h, const pnec_batch *batch, double r
 int pnec_nec_translation_batch(pnec_handle *h, const pnec_batch *batch, double *out_translations,
                                double *out_M, void *cuda_stream);
 
+/* Rotation by NEC eigenvalue minimisation for B frame pairs:
+ *   rotation_t opengv::relative_pose::eigensolver(CentralRelativeAdapter(bvs1, bvs2, R12))
+ * as the reference calls it at src/rel_pose_estimation/pnec.cc:274 (PNEC::Eigensolver, no RANSAC)
+ * and pnec.cc:313 (PNEC::WeightedEigensolver).  opengv is a third-party dependency outside the
+ * reference tree; what is computed (restated from its publication, Kneip & Lynen ICCV 2013, and its
+ * public sources): the moments sum_i w_i f1_u f1_v f2 f2^T, then Levenberg-Marquardt (Eigen's MINPACK
+ * lmdif port: forward differences, ftol 5e-5, xtol 10 eps, maxfev 100) on the gradient of the smallest
+ * eigenvalue of M(c) = sum_i n_i n_i^T, n_i = f1_i x R'(c) f2_i, over the Cayley parameters c,
+ * started at the rotation of `batch->poses`.
+ *   weight_poses  NULL: unweighted (PNEC::Eigensolver).  Otherwise [B][7] (same memspace): f2_i is
+ *                 scaled by sqrt(Weight_i * 1e-8), Weight = 1 / (t^T [f1]x R S_i R^T [f1]x^T t + reg)
+ *                 at these poses (pnec::common::Weight, src/common/common.cc:183-208 with
+ *                 host_frame = false; pnec.cc:294-306); needs batch->covs_target.
+ *   out_poses     [B][7]: unit quaternion of the result; the translation of batch->poses is passed
+ *                 through unchanged
+ *   out_lm_info   [B] MINPACK termination code (1..8), or NULL
+ *   out_smallest_ev [B] smallest eigenvalue of opengv's (unnormalised) M at the result, or NULL */
+int pnec_eigensolver_batch(pnec_handle *h, const pnec_batch *batch, const double *weight_poses,
+                           double regularization, double *out_poses, int32_t *out_lm_info,
+                           double *out_smallest_ev, void *cuda_stream);
+
+/* pnec::rel_pose_estimation::Options as PNEC::Solve reads it
+ * (include/rel_pose_estimation/pnec_config.h:46-65). */
+typedef struct pnec_frame_opts {
+  int32_t use_nec;             /* use_nec_              false                                   */
+  int32_t use_ceres;           /* use_ceres_            true                                    */
+  int32_t weighted_iterations; /* weighted_iterations_  10                                      */
+  int32_t use_ransac;          /* use_ransac_: the reference defaults to true; RANSAC is not built,
+                                  a non-zero value returns PNEC_ERR_UNSUPPORTED                 */
+  int32_t fibonacci_samples;   /* 500, the literal at pnec.cc:331                               */
+  int32_t scf_steps;           /* 10,  the literal at pnec.cc:342                               */
+  pnec_solver_opts ceres;      /* ceres_options_ (+ regularization_); `variant` is ignored: NEC
+                                  when use_nec, TARGET otherwise                                */
+} pnec_frame_opts;
+
+/* Options() defaults except use_ransac = 0. */
+void pnec_frame_opts_default(pnec_frame_opts *opts);
+
+typedef struct pnec_frame_out {
+  double *poses;       /* [B][7] result of PNEC::Solve                                          */
+  double *es_poses;    /* [B][7] result of PNEC::Eigensolver (ES_solution, pnec.cc:86), or NULL */
+  int32_t *status;     /* [B] pnec_status of the refinement, or NULL (untouched if !use_ceres)  */
+  int32_t *iterations; /* [B] or NULL                                                           */
+  double *cost;        /* [B] or NULL                                                           */
+} pnec_frame_out;
+
+/* The whole frame-to-frame solve for B frame pairs, every stage on the device:
+ * Sophus::SE3d PNEC::Solve(bvs1, bvs2, projected_covs, initial_pose) with use_ransac_ == false
+ * (src/rel_pose_estimation/pnec.cc:77-124):
+ *   1. PNEC::Eigensolver (pnec.cc:273-279): pnec_eigensolver_batch from the rotation of
+ *      batch->poses, translation = TranslationFromM(ComposeM(..)) (pnec_nec_translation_batch)
+ *   2. use_nec: NECCeresSolver from 1 (or 1 itself if !use_ceres)
+ *   3. else weighted_iterations > 1: PNEC::WeightedEigensolver (pnec.cc:283-348):
+ *      (weighted_iterations - 1) x { weighted eigensolver started at the previous rotation, weights
+ *      from the pose of step 1; SCF translation started at the previous translation };
+ *      == 1: the pose of step 1;  == 0: batch->poses
+ *   4. use_ceres: CeresSolver (TARGET residual) from 3
+ * batch->covs_target may be NULL when use_nec. */
+int pnec_frame_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_frame_opts *opts,
+                           const pnec_frame_out *out, void *cuda_stream);
+
 /* Number of kernels this handle has launched so far (bench bookkeeping). */
 int64_t pnec_launch_count(const pnec_handle *h);
 

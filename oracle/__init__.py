@@ -69,6 +69,31 @@ class OracleInfo(ctypes.Structure):
     ]
 
 
+class OracleEsInfo(ctypes.Structure):
+    """Outcome of the restated opengv eigensolver (oracle/pnec_oracle_frame.c)."""
+    _fields_ = [
+        ("lm_info", ctypes.c_int32),  # MINPACK info code
+        ("nfev", ctypes.c_int32),
+        ("iterations", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+        ("smallest_ev", ctypes.c_double),
+        ("cayley", ctypes.c_double * 3),
+    ]
+
+
+class OracleFrameOpts(ctypes.Structure):
+    """pnec::rel_pose_estimation::Options as PNEC::Solve reads it (pnec_config.h:46-65), no RANSAC."""
+    _fields_ = [
+        ("use_nec", ctypes.c_int32),
+        ("use_ceres", ctypes.c_int32),
+        ("weighted_iterations", ctypes.c_int32),
+        ("fibonacci_samples", ctypes.c_int32),
+        ("scf_steps", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+        ("ceres", OracleOpts),
+    ]
+
+
 INFO_DTYPE = np.dtype(
     [
         ("status", np.int32),
@@ -87,9 +112,9 @@ _lib = None
 
 def build(force: bool = False) -> str:
     """Compile oracle/pnec_oracle.c (gcc) into oracle/_build/; returns the path."""
-    if force or not os.path.exists(_LIB_PATH) or (
-        os.path.exists(os.path.join(_HERE, "pnec_oracle.c"))
-        and os.path.getmtime(os.path.join(_HERE, "pnec_oracle.c")) > os.path.getmtime(_LIB_PATH)
+    srcs = [os.path.join(_HERE, f) for f in ("pnec_oracle.c", "pnec_oracle_frame.c")]
+    if force or not os.path.exists(_LIB_PATH) or any(
+        os.path.exists(f) and os.path.getmtime(f) > os.path.getmtime(_LIB_PATH) for f in srcs
     ):
         subprocess.run(["make", "-C", _HERE, "-s"] + (["-B"] if force else []), check=True)
     return _LIB_PATH
@@ -140,6 +165,28 @@ def lib() -> ctypes.CDLL:
         L.oracle_scf_translation.restype = ctypes.c_int
         L.oracle_nec_translation.argtypes = [ctypes.c_int64, dp, dp, dp, dp, dp]
         L.oracle_nec_translation.restype = None
+        ip = ctypes.POINTER(ctypes.c_int32)
+        L.oracle_es_smallest_ev.argtypes = [ctypes.c_int64, dp, dp, dp, dp, dp, dp]
+        L.oracle_es_smallest_ev.restype = ctypes.c_double
+        L.oracle_eigensolver.argtypes = [ctypes.c_int64, dp, dp, dp, dp, dp, ctypes.POINTER(OracleEsInfo)]
+        L.oracle_eigensolver.restype = ctypes.c_int
+        L.oracle_es_lm.argtypes = [ctypes.c_int64, dp, dp, dp, dp, ctypes.c_double, ctypes.c_double,
+                                   ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int, dp, ip, ip]
+        L.oracle_es_lm.restype = ctypes.c_int
+        L.oracle_nec_eigensolver_pose.argtypes = [ctypes.c_int64, dp, dp, dp, dp, ctypes.POINTER(OracleEsInfo)]
+        L.oracle_nec_eigensolver_pose.restype = ctypes.c_int
+        L.oracle_weights.argtypes = [ctypes.c_int64, dp, dp, dp, ctypes.c_double, dp]
+        L.oracle_weights.restype = None
+        L.oracle_weighted_eigensolver.argtypes = [ctypes.c_int64, dp, dp, dp, dp, ctypes.c_double, ctypes.c_int,
+                                                  ctypes.c_int, ctypes.c_int, dp]
+        L.oracle_weighted_eigensolver.restype = ctypes.c_int
+        L.oracle_frame_opts_default.argtypes = [ctypes.POINTER(OracleFrameOpts)]
+        L.oracle_frame_opts_default.restype = None
+        L.oracle_frame_solve.argtypes = [ctypes.POINTER(OracleFrameOpts), ctypes.c_int64, dp, dp, dp, dp, dp, dp]
+        L.oracle_frame_solve.restype = ctypes.c_int
+        L.oracle_frame_solve_batch.argtypes = [ctypes.POINTER(OracleFrameOpts), ctypes.c_int64, ctypes.c_int64,
+                                               ctypes.POINTER(ctypes.c_int64), dp, dp, dp, dp, dp, dp, ctypes.c_int]
+        L.oracle_frame_solve_batch.restype = ctypes.c_int
         _lib = L
     return _lib
 
@@ -329,3 +376,97 @@ def nec_translation(f1, f2, pose7):
     t, M = np.zeros(3), np.zeros(6)
     lib().oracle_nec_translation(f1.shape[0], _dp(f1), _dp(f2), _dp(pose7), _dp(t), _dp(M))
     return t, M
+
+
+# ----------------------------------------------------------------- front stages of PNEC::Solve
+
+
+def es_smallest_ev(f1, f2, cayley, weights=None):
+    """lambda_min of opengv's reduced M(c), its gradient (3,) and M (3,3) at a Cayley vector."""
+    f1, f2, c, w = _c(f1, (3,)), _c(f2, (3,)), _c(cayley), _c(weights)
+    jac, M = np.zeros(3), np.zeros(9)
+    ev = lib().oracle_es_smallest_ev(f1.shape[0], _dp(f1), _dp(f2), _dp(w), _dp(c), _dp(jac), _dp(M))
+    return float(ev), jac, M.reshape(3, 3)
+
+
+def eigensolver(f1, f2, init_pose7, weights=None):
+    """opengv::relative_pose::eigensolver restated -> (unit quaternion xyzw (4,), OracleEsInfo)."""
+    f1, f2, p, w = _c(f1, (3,)), _c(f2, (3,)), _c(init_pose7), _c(weights)
+    q = np.zeros(4)
+    info = OracleEsInfo()
+    lib().oracle_eigensolver(f1.shape[0], _dp(f1), _dp(f2), _dp(w), _dp(p), _dp(q), ctypes.byref(info))
+    return q, info
+
+
+def es_lm(f1, f2, x0, weights=None, ftol=5e-5, xtol=10 * np.finfo(float).eps, gtol=0.0, factor=100.0,
+          maxfev=100, fev_per_jacobian=4):
+    """The restated MINPACK lmdif alone on the eigensolver's residuals -> (x (3,), info, nfev)."""
+    f1, f2, x0, w = _c(f1, (3,)), _c(f2, (3,)), _c(x0), _c(weights)
+    x = np.zeros(3)
+    info, nfev = ctypes.c_int32(), ctypes.c_int32()
+    lib().oracle_es_lm(f1.shape[0], _dp(f1), _dp(f2), _dp(w), _dp(x0), ftol, xtol, gtol, factor, int(maxfev),
+                       int(fev_per_jacobian), _dp(x), ctypes.byref(info), ctypes.byref(nfev))
+    return x, info.value, nfev.value
+
+
+def nec_eigensolver_pose(f1, f2, init_pose7):
+    """PNEC::Eigensolver without RANSAC (pnec.cc:273-279) -> pose7."""
+    f1, f2, p = _c(f1, (3,)), _c(f2, (3,)), _c(init_pose7)
+    out = np.zeros(7)
+    info = OracleEsInfo()
+    lib().oracle_nec_eigensolver_pose(f1.shape[0], _dp(f1), _dp(f2), _dp(p), _dp(out), ctypes.byref(info))
+    return out, info
+
+
+def weights(f1, cov, pose7, reg=1e-13):
+    """pnec::common::Weight(host_frame=false) * 1e-8 (common.cc:183-208, pnec.cc:296-300)."""
+    f1, cov, p = _c(f1, (3,)), _c(cov, (9,)), _c(pose7)
+    w = np.zeros(f1.shape[0])
+    lib().oracle_weights(f1.shape[0], _dp(f1), _dp(cov), _dp(p), float(reg), _dp(w))
+    return w
+
+
+def weighted_eigensolver(f1, f2, cov, initial_pose7, reg=1e-13, weighted_iterations=10, samples=500, steps=10):
+    """PNEC::WeightedEigensolver (pnec.cc:283-348) -> pose7."""
+    f1, f2, cov, p = _c(f1, (3,)), _c(f2, (3,)), _c(cov, (9,)), _c(initial_pose7)
+    out = np.zeros(7)
+    rc = lib().oracle_weighted_eigensolver(f1.shape[0], _dp(f1), _dp(f2), _dp(cov), _dp(p), float(reg),
+                                           int(weighted_iterations), int(samples), int(steps), _dp(out))
+    if rc != 0:
+        raise RuntimeError("oracle_weighted_eigensolver failed")
+    return out
+
+
+def default_frame_opts(**overrides) -> OracleFrameOpts:
+    o = OracleFrameOpts()
+    lib().oracle_frame_opts_default(ctypes.byref(o))
+    for k, v in overrides.items():
+        if hasattr(o, k):
+            setattr(o, k, v)
+        elif hasattr(o.ceres, k):
+            setattr(o.ceres, k, v)
+        else:
+            raise AttributeError(k)
+    return o
+
+
+def frame_solve_batch(f1, f2, cov, init_poses, opts: OracleFrameOpts, offsets=None, n_per_problem=None,
+                      num_threads: int = 1):
+    """PNEC::Solve (no RANSAC) per frame pair -> (poses [B,7], eigensolver poses [B,7])."""
+    f1, f2, cov = _c(f1, (3,)), _c(f2, (3,)), _c(cov, (9,))
+    init_poses = _c(init_poses, (7,))
+    B = init_poses.shape[0]
+    if offsets is not None:
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        op = offsets.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))
+        n_per_problem = 0
+    else:
+        op = None
+        if n_per_problem is None:
+            n_per_problem = f1.shape[0] // max(B, 1)
+    out, es = np.zeros((B, 7)), np.zeros((B, 7))
+    rc = lib().oracle_frame_solve_batch(ctypes.byref(opts), B, n_per_problem, op, _dp(f1), _dp(f2), _dp(cov),
+                                        _dp(init_poses), _dp(out), _dp(es), num_threads)
+    if rc != 0:
+        raise RuntimeError("oracle_frame_solve_batch failed")
+    return out, es

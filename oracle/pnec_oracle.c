@@ -1092,3 +1092,6 @@ void oracle_nec_translation(int64_t n, const double *f1, const double *f2, const
     out_M[3] = M[1][1]; out_M[4] = M[1][2]; out_M[5] = M[2][2];
   }
 }
+
+/* front stages of PNEC::Solve (NEC eigensolver, weighted eigensolver, orchestration) */
+#include "pnec_oracle_frame.c"

@@ -46,6 +46,9 @@ EXPORTED_SYMBOLS = (
     "pnec_keypoints_unproject_batch",
     "pnec_scf_translation_batch",
     "pnec_nec_translation_batch",
+    "pnec_eigensolver_batch",
+    "pnec_frame_opts_default",
+    "pnec_frame_solve_batch",
     "pnec_launch_count",
 )
 
@@ -110,6 +113,31 @@ class _EvalOut(ctypes.Structure):
     ]
 
 
+class FrameOpts(ctypes.Structure):
+    """pnec_frame_opts == pnec::rel_pose_estimation::Options as PNEC::Solve reads it
+    (include/rel_pose_estimation/pnec_config.h:46-65)."""
+
+    _fields_ = [
+        ("use_nec", ctypes.c_int32),
+        ("use_ceres", ctypes.c_int32),
+        ("weighted_iterations", ctypes.c_int32),
+        ("use_ransac", ctypes.c_int32),
+        ("fibonacci_samples", ctypes.c_int32),
+        ("scf_steps", ctypes.c_int32),
+        ("ceres", SolverOpts),
+    ]
+
+
+class _FrameOut(ctypes.Structure):
+    _fields_ = [
+        ("poses", ctypes.c_void_p),
+        ("es_poses", ctypes.c_void_p),
+        ("status", ctypes.c_void_p),
+        ("iterations", ctypes.c_void_p),
+        ("cost", ctypes.c_void_p),
+    ]
+
+
 _lib = None
 
 
@@ -160,6 +188,15 @@ def load_library() -> ctypes.CDLL:
     L.pnec_nec_translation_batch.argtypes = [ctypes.c_void_p, ctypes.POINTER(_Batch), ctypes.c_void_p,
                                              ctypes.c_void_p, ctypes.c_void_p]
     L.pnec_nec_translation_batch.restype = ctypes.c_int
+    L.pnec_eigensolver_batch.argtypes = [ctypes.c_void_p, ctypes.POINTER(_Batch), ctypes.c_void_p,
+                                         ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_void_p]
+    L.pnec_eigensolver_batch.restype = ctypes.c_int
+    L.pnec_frame_opts_default.argtypes = [ctypes.POINTER(FrameOpts)]
+    L.pnec_frame_opts_default.restype = None
+    L.pnec_frame_solve_batch.argtypes = [ctypes.c_void_p, ctypes.POINTER(_Batch), ctypes.POINTER(FrameOpts),
+                                         ctypes.POINTER(_FrameOut), ctypes.c_void_p]
+    L.pnec_frame_solve_batch.restype = ctypes.c_int
     L.pnec_launch_count.argtypes = [ctypes.c_void_p]
     L.pnec_launch_count.restype = ctypes.c_int64
     _lib = L
@@ -178,6 +215,20 @@ def default_opts(variant: int = TARGET, regularization: float = 1e-13, **overrid
     return o
 
 
+def default_frame_opts(**overrides) -> FrameOpts:
+    """pnec_frame_opts_default + overrides; unknown names are looked up in the nested `ceres` options."""
+    o = FrameOpts()
+    load_library().pnec_frame_opts_default(ctypes.byref(o))
+    for k, v in overrides.items():
+        if k != "ceres" and hasattr(o, k):
+            setattr(o, k, v)
+        elif hasattr(o.ceres, k):
+            setattr(o.ceres, k, v)
+        else:
+            raise AttributeError(f"pnec_frame_opts has no field {k!r}")
+    return o
+
+
 def _is_torch(x) -> bool:
     return type(x).__module__.startswith("torch")
 
@@ -189,6 +240,15 @@ class SolveResult:
     iterations: object  # (B,) int32
     cost: object  # (B,) final 1/2 sum r^2
     initial_cost: object  # (B,)
+
+
+@dataclass
+class FrameResult:
+    poses: object  # (B,7) result of PNEC::Solve
+    es_poses: object  # (B,7) result of PNEC::Eigensolver (ES_solution)
+    status: object  # (B,) int32, refinement status
+    iterations: object  # (B,) int32
+    cost: object  # (B,)
 
 
 @dataclass
@@ -479,6 +539,58 @@ class Handle:
         rc = self._lib.pnec_nec_translation_batch(self._h, ctypes.byref(b), pt, pm, self._stream(device))
         self._check(rc, "pnec_nec_translation_batch")
         return t, m
+
+
+    def _out_i32(self, device, shape):
+        if device:
+            import torch
+
+            t = torch.zeros(shape, dtype=torch.int32, device=torch.device("cuda", self.device))
+            return t, ctypes.c_void_p(t.data_ptr())
+        a = np.zeros(shape, np.int32)
+        return a, ctypes.c_void_p(a.ctypes.data)
+
+    def eigensolver_batch(self, bvs_host, bvs_target, init_poses, *, covs_target=None, weight_poses=None,
+                          regularization=1e-13, offsets=None, n_per_problem=None):
+        """opengv::relative_pose::eigensolver for B frame pairs (pnec.cc:274 / :313) ->
+        (poses (B,7): result rotation + the input translation, lm_info (B,), smallest_ev (B,)).
+        `weight_poses` (B,7) switches on the weights of PNEC::WeightedEigensolver (needs covs_target)."""
+        keep = []
+        b, device, B = self._batch(bvs_host, bvs_target, covs_target, None, init_poses, offsets, n_per_problem, keep)
+        pw = None
+        if weight_poses is not None:
+            if device:
+                if not (_is_torch(weight_poses) and weight_poses.is_cuda and weight_poses.is_contiguous()):
+                    raise PnecError("weight_poses must be a contiguous CUDA tensor for device batches")
+                pw = ctypes.c_void_p(weight_poses.data_ptr())
+            else:
+                weight_poses = self._prep_host(weight_poses, (7,))
+                pw = ctypes.c_void_p(weight_poses.ctypes.data)
+            keep.append(weight_poses)
+        poses, pp = self._out(device, (B, 7))
+        info, pi = self._out_i32(device, (B,))
+        ev, pe = self._out(device, (B,))
+        rc = self._lib.pnec_eigensolver_batch(self._h, ctypes.byref(b), pw, float(regularization), pp, pi, pe,
+                                              self._stream(device))
+        self._check(rc, "pnec_eigensolver_batch")
+        return poses, info, ev
+
+    def frame_solve_batch(self, bvs_host, bvs_target, covs_target, init_poses,
+                          opts: Optional[FrameOpts] = None, *, offsets=None, n_per_problem=None) -> FrameResult:
+        """PNEC::Solve without RANSAC (pnec.cc:77-124) for B frame pairs, every stage on the device."""
+        opts = opts or default_frame_opts()
+        keep = []
+        b, device, B = self._batch(bvs_host, bvs_target, covs_target, None, init_poses, offsets, n_per_problem, keep)
+        poses, pp = self._out(device, (B, 7))
+        es, pes = self._out(device, (B, 7))
+        status, pst = self._out_i32(device, (B,))
+        iters, pit = self._out_i32(device, (B,))
+        cost, pc = self._out(device, (B,))
+        o = _FrameOut(pp, pes, pst, pit, pc)
+        rc = self._lib.pnec_frame_solve_batch(self._h, ctypes.byref(b), ctypes.byref(opts), ctypes.byref(o),
+                                              self._stream(device))
+        self._check(rc, "pnec_frame_solve_batch")
+        return FrameResult(poses, es, status, iters, cost)
 
 
 _default_handles = {}

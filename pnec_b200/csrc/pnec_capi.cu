@@ -5,6 +5,7 @@
 //   pnec_eval.cuh    eval_warp_kernel (K1): fused residual + Jacobian + J^T J, the roofline kernel
 //   pnec_aux.cuh     cost_kernel (parity metric), unscented_kernel (covariance propagation)
 //   pnec_translation.cuh  scf_kernel / nec_translation_kernel: translation given rotation
+//   pnec_eigensolver.cuh  es_moments_kernel / es_lm_kernel: rotation by NEC eigenvalue minimisation
 //   pnec_lm.cuh      Ceres-semantics Levenberg-Marquardt update; pnec_device.cuh: the math
 #include <algorithm>
 #include <cmath>
@@ -16,6 +17,7 @@
 #include <vector>
 
 #include "pnec_aux.cuh"
+#include "pnec_eigensolver.cuh"
 #include "pnec_eval.cuh"
 #include "pnec_solve.cuh"
 #include "pnec_translation.cuh"
@@ -78,6 +80,7 @@ struct pnec_handle {
   DevBuf d_f1, d_f2, d_ct, d_ch, d_off, d_poses;
   DevBuf d_out_poses, d_out_status, d_out_iters, d_out_cost, d_out_init, d_out_grad, d_out_jtj;
   DevBuf d_ut_mu, d_ut_cov, d_ut_out, d_kp_bv, d_sphere, d_tr_out, d_tr_aux;
+  DevBuf d_es_mom, d_es_w, d_es_info, d_es_ev, d_fr_es, d_fr_a, d_fr_b;  // eigensolver / frame pipeline
   int sphere_samples = -1;
   std::mutex mu;
 };
@@ -385,6 +388,148 @@ int launch_eval(pnec_handle *h, const EvalArgs &a0, int variant, long long max_n
   }
 }
 
+
+// ------------------------------------------------- stage launchers (device views only)
+
+// The refinement with its outputs: device arrays when `host` is false, else staged through the
+// handle and copied to the caller's host arrays (the caller synchronises).
+int run_solve(pnec_handle *h, const BatchView &bv, long long max_n, const pnec_solver_opts &o, bool host,
+              double *poses, int32_t *status, int32_t *iterations, double *cost, double *initial_cost,
+              cudaStream_t stream) {
+  const long long B = bv.num_problems;
+  SolveArgs a{};
+  a.bv = bv;
+  a.o = o;
+  if (host) {
+    PNEC_CUDA(h->d_out_poses.ensure(static_cast<size_t>(B) * 56));
+    PNEC_CUDA(h->d_out_status.ensure(static_cast<size_t>(B) * 4));
+    PNEC_CUDA(h->d_out_iters.ensure(static_cast<size_t>(B) * 4));
+    PNEC_CUDA(h->d_out_cost.ensure(static_cast<size_t>(B) * 8));
+    PNEC_CUDA(h->d_out_init.ensure(static_cast<size_t>(B) * 8));
+    a.out_poses = static_cast<double *>(h->d_out_poses.p);
+    a.out_status = status ? static_cast<int *>(h->d_out_status.p) : nullptr;
+    a.out_iters = iterations ? static_cast<int *>(h->d_out_iters.p) : nullptr;
+    a.out_cost = cost ? static_cast<double *>(h->d_out_cost.p) : nullptr;
+    a.out_init_cost = initial_cost ? static_cast<double *>(h->d_out_init.p) : nullptr;
+  } else {
+    a.out_poses = poses;
+    a.out_status = status;
+    a.out_iters = iterations;
+    a.out_cost = cost;
+    a.out_init_cost = initial_cost;
+  }
+  int rc = launch_solve(h, a, o.variant, max_n, stream);
+  if (rc != PNEC_OK) return rc;
+  if (host) {
+    PNEC_CUDA(cudaMemcpyAsync(poses, a.out_poses, static_cast<size_t>(B) * 56, cudaMemcpyDeviceToHost, stream));
+    if (status)
+      PNEC_CUDA(cudaMemcpyAsync(status, a.out_status, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToHost, stream));
+    if (iterations)
+      PNEC_CUDA(cudaMemcpyAsync(iterations, a.out_iters, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToHost, stream));
+    if (cost)
+      PNEC_CUDA(cudaMemcpyAsync(cost, a.out_cost, static_cast<size_t>(B) * 8, cudaMemcpyDeviceToHost, stream));
+    if (initial_cost)
+      PNEC_CUDA(cudaMemcpyAsync(initial_cost, a.out_init_cost, static_cast<size_t>(B) * 8, cudaMemcpyDeviceToHost, stream));
+  }
+  return PNEC_OK;
+}
+
+int ensure_sphere(pnec_handle *h, int fibonacci_samples) {
+  // fibonacci_sphere(samples), scf.cc:53-72, with its float casts
+  if (h->sphere_samples == fibonacci_samples) return PNEC_OK;
+  std::vector<double> pts(static_cast<size_t>(std::max(fibonacci_samples, 1)) * 3);
+  const double phi = M_PI * (3.0 - std::sqrt(5.0));
+  for (int i = 0; i < fibonacci_samples; ++i) {
+    const double y = 1.0 - ((float)i / (float)(fibonacci_samples - 1)) * 2.0;
+    const double radius = std::sqrt(1 - y * y);
+    const double theta = phi * (float)i;
+    pts[3 * i] = std::cos(theta) * radius;
+    pts[3 * i + 1] = y;
+    pts[3 * i + 2] = std::sin(theta) * radius;
+  }
+  PNEC_CUDA(h->d_sphere.ensure(pts.size() * 8));
+  PNEC_CUDA(cudaMemcpy(h->d_sphere.p, pts.data(), pts.size() * 8, cudaMemcpyHostToDevice));
+  h->sphere_samples = fibonacci_samples;
+  return PNEC_OK;
+}
+
+size_t scf_smem_bytes(long long max_n) { return static_cast<size_t>(std::max<long long>(max_n, 1)) * 72; }
+
+// scf_kernel: rotation + start translation from bv.poses, result at out_t + out_stride * b (may be the
+// translation slot of bv.poses itself: every read of the pose precedes the final write)
+int run_scf(pnec_handle *h, const BatchView &bv, long long max_n, double reg, int samples, int steps,
+            double *out_t, int out_stride, double *out_cost, cudaStream_t stream) {
+  const size_t dyn = scf_smem_bytes(max_n);
+  if (dyn + kStaticSmemReserve > h->smem_optin)
+    return fail(PNEC_ERR_UNSUPPORTED, "SCF translation: a frame pair exceeds the shared-memory capacity (~3100 correspondences)");
+  int rc = ensure_sphere(h, samples);
+  if (rc != PNEC_OK) return rc;
+  ScfArgs a{};
+  a.bv = bv;
+  a.sphere = static_cast<const double *>(h->d_sphere.p);
+  a.reg = reg;
+  a.samples = samples;
+  a.steps = steps;
+  a.cap_elems = static_cast<int>(dyn / 72);
+  a.out_t = out_t;
+  a.out_stride = out_stride;
+  a.out_cost = out_cost;
+  auto kern = scf_kernel<4>;
+  PNEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
+  kern<<<static_cast<unsigned>(bv.num_problems), 128, dyn, stream>>>(a);
+  PNEC_CUDA(cudaGetLastError());
+  h->launches++;
+  return PNEC_OK;
+}
+
+int run_nec_translation(pnec_handle *h, const BatchView &bv, double *out_t, int out_stride, double *out_M,
+                        cudaStream_t stream) {
+  nec_translation_kernel<<<static_cast<unsigned>(bv.num_problems), 128, 0, stream>>>(bv, out_t, out_stride, out_M);
+  PNEC_CUDA(cudaGetLastError());
+  h->launches++;
+  return PNEC_OK;
+}
+
+// moments of the eigensolver; weighted: bv.poses = the poses the weights are computed from
+int run_es_moments(pnec_handle *h, const BatchView &bv, bool weighted, double reg, double *d_mom,
+                   cudaStream_t stream) {
+  EsMomentArgs a{};
+  a.bv = bv;
+  a.reg = reg;
+  a.out = d_mom;
+  if (weighted)
+    es_moments_kernel<true><<<static_cast<unsigned>(bv.num_problems), 128, 0, stream>>>(a);
+  else
+    es_moments_kernel<false><<<static_cast<unsigned>(bv.num_problems), 128, 0, stream>>>(a);
+  PNEC_CUDA(cudaGetLastError());
+  h->launches++;
+  return PNEC_OK;
+}
+
+// opengv eigensolver_main with the parameters opengv sets (ftol 5e-5, xtol 10 eps, maxfev 100;
+// resetParameters(): factor 100, gtol 0, epsfcn 0)
+int run_es_lm(pnec_handle *h, long long B, const double *d_mom, const double *d_poses_in, double *d_poses_out,
+              int *d_info, double *d_ev, cudaStream_t stream) {
+  EsLmArgs a{};
+  a.moments = d_mom;
+  a.poses_in = d_poses_in;
+  a.poses_out = d_poses_out;
+  a.out_info = d_info;
+  a.out_nfev = nullptr;
+  a.out_ev = d_ev;
+  a.num_problems = B;
+  a.ftol = 0.00005;
+  a.xtol = 1.0e1 * DBL_EPSILON;
+  a.gtol = 0.0;
+  a.factor = 100.0;
+  a.maxfev = 100;
+  const unsigned grid = static_cast<unsigned>((B + kEsLmThreads - 1) / kEsLmThreads);
+  es_lm_kernel<<<grid, kEsLmThreads, 0, stream>>>(a);
+  PNEC_CUDA(cudaGetLastError());
+  h->launches++;
+  return PNEC_OK;
+}
+
 }  // namespace
 
 // ===================================================================== C-ABI
@@ -456,7 +601,8 @@ void pnec_destroy(pnec_handle *h) {
                     &h->d_out_poses, &h->d_out_status, &h->d_out_iters, &h->d_out_cost,
                     &h->d_out_init, &h->d_out_grad, &h->d_out_jtj, &h->d_ut_mu, &h->d_ut_cov,
                     &h->d_ut_out, &h->d_kp_bv, &h->d_sphere, &h->d_tr_out,
-                    &h->d_tr_aux};
+                    &h->d_tr_aux, &h->d_es_mom, &h->d_es_w, &h->d_es_info, &h->d_es_ev,
+                    &h->d_fr_es, &h->d_fr_a, &h->d_fr_b};
   for (DevBuf *b : bufs) b->release();
   delete h;
 }
@@ -477,47 +623,11 @@ int pnec_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_solver_
   Staged st;
   rc = stage_batch(h, batch, opts->variant, stream, &st);
   if (rc != PNEC_OK) return rc;
-  SolveArgs a{};
-  a.bv = st.bv;
-  a.o = *opts;
   const bool host = batch->memspace == PNEC_MEM_HOST;
-  if (host) {
-    PNEC_CUDA(h->d_out_poses.ensure(static_cast<size_t>(B) * 56));
-    PNEC_CUDA(h->d_out_status.ensure(static_cast<size_t>(B) * 4));
-    PNEC_CUDA(h->d_out_iters.ensure(static_cast<size_t>(B) * 4));
-    PNEC_CUDA(h->d_out_cost.ensure(static_cast<size_t>(B) * 8));
-    PNEC_CUDA(h->d_out_init.ensure(static_cast<size_t>(B) * 8));
-    a.out_poses = static_cast<double *>(h->d_out_poses.p);
-    a.out_status = out->status ? static_cast<int *>(h->d_out_status.p) : nullptr;
-    a.out_iters = out->iterations ? static_cast<int *>(h->d_out_iters.p) : nullptr;
-    a.out_cost = out->cost ? static_cast<double *>(h->d_out_cost.p) : nullptr;
-    a.out_init_cost = out->initial_cost ? static_cast<double *>(h->d_out_init.p) : nullptr;
-  } else {
-    a.out_poses = out->poses;
-    a.out_status = out->status;
-    a.out_iters = out->iterations;
-    a.out_cost = out->cost;
-    a.out_init_cost = out->initial_cost;
-  }
-  rc = launch_solve(h, a, opts->variant, st.max_n, stream);
+  rc = run_solve(h, st.bv, st.max_n, *opts, host, out->poses, out->status, out->iterations, out->cost,
+                 out->initial_cost, stream);
   if (rc != PNEC_OK) return rc;
-  if (host) {
-    PNEC_CUDA(cudaMemcpyAsync(out->poses, a.out_poses, static_cast<size_t>(B) * 56,
-                              cudaMemcpyDeviceToHost, stream));
-    if (out->status)
-      PNEC_CUDA(cudaMemcpyAsync(out->status, a.out_status, static_cast<size_t>(B) * 4,
-                                cudaMemcpyDeviceToHost, stream));
-    if (out->iterations)
-      PNEC_CUDA(cudaMemcpyAsync(out->iterations, a.out_iters, static_cast<size_t>(B) * 4,
-                                cudaMemcpyDeviceToHost, stream));
-    if (out->cost)
-      PNEC_CUDA(cudaMemcpyAsync(out->cost, a.out_cost, static_cast<size_t>(B) * 8,
-                                cudaMemcpyDeviceToHost, stream));
-    if (out->initial_cost)
-      PNEC_CUDA(cudaMemcpyAsync(out->initial_cost, a.out_init_cost, static_cast<size_t>(B) * 8,
-                                cudaMemcpyDeviceToHost, stream));
-    PNEC_CUDA(cudaStreamSynchronize(stream));
-  }
+  if (host) PNEC_CUDA(cudaStreamSynchronize(stream));
   return PNEC_OK;
 }
 
@@ -707,51 +817,20 @@ int pnec_scf_translation_batch(pnec_handle *h, const pnec_batch *batch, double r
   Staged st;
   rc = stage_batch(h, batch, PNEC_VARIANT_TARGET, stream, &st);
   if (rc != PNEC_OK) return rc;
-  const size_t dyn = static_cast<size_t>(std::max<long long>(st.max_n, 1)) * 72;
-  if (dyn + kStaticSmemReserve > h->smem_optin)
-    return fail(PNEC_ERR_UNSUPPORTED, "pnec_scf_translation_batch: a frame pair exceeds the shared-memory capacity (~3100 correspondences)");
-  // fibonacci_sphere(samples), scf.cc:53-72, with its float casts
-  if (h->sphere_samples != fibonacci_samples) {
-    std::vector<double> pts(static_cast<size_t>(std::max(fibonacci_samples, 1)) * 3);
-    const double phi = M_PI * (3.0 - std::sqrt(5.0));
-    for (int i = 0; i < fibonacci_samples; ++i) {
-      const double y = 1.0 - ((float)i / (float)(fibonacci_samples - 1)) * 2.0;
-      const double radius = std::sqrt(1 - y * y);
-      const double theta = phi * (float)i;
-      pts[3 * i] = std::cos(theta) * radius;
-      pts[3 * i + 1] = y;
-      pts[3 * i + 2] = std::sin(theta) * radius;
-    }
-    PNEC_CUDA(h->d_sphere.ensure(pts.size() * 8));
-    PNEC_CUDA(cudaMemcpy(h->d_sphere.p, pts.data(), pts.size() * 8, cudaMemcpyHostToDevice));
-    h->sphere_samples = fibonacci_samples;
-  }
-  ScfArgs a{};
-  a.bv = st.bv;
-  a.sphere = static_cast<const double *>(h->d_sphere.p);
-  a.reg = regularization;
-  a.samples = fibonacci_samples;
-  a.steps = scf_steps;
-  a.cap_elems = static_cast<int>(dyn / 72);
   const bool host = batch->memspace == PNEC_MEM_HOST;
+  double *d_t = out_translations, *d_c = out_cost;
   if (host) {
     PNEC_CUDA(h->d_tr_out.ensure(static_cast<size_t>(B) * 24));
     PNEC_CUDA(h->d_tr_aux.ensure(static_cast<size_t>(B) * 8));
-    a.out_t = static_cast<double *>(h->d_tr_out.p);
-    a.out_cost = out_cost ? static_cast<double *>(h->d_tr_aux.p) : nullptr;
-  } else {
-    a.out_t = out_translations;
-    a.out_cost = out_cost;
+    d_t = static_cast<double *>(h->d_tr_out.p);
+    d_c = out_cost ? static_cast<double *>(h->d_tr_aux.p) : nullptr;
   }
-  auto kern = scf_kernel<4>;
-  PNEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
-  kern<<<static_cast<unsigned>(B), 128, dyn, stream>>>(a);
-  PNEC_CUDA(cudaGetLastError());
-  h->launches++;
+  rc = run_scf(h, st.bv, st.max_n, regularization, fibonacci_samples, scf_steps, d_t, 3, d_c, stream);
+  if (rc != PNEC_OK) return rc;
   if (host) {
-    PNEC_CUDA(cudaMemcpyAsync(out_translations, a.out_t, static_cast<size_t>(B) * 24, cudaMemcpyDeviceToHost, stream));
+    PNEC_CUDA(cudaMemcpyAsync(out_translations, d_t, static_cast<size_t>(B) * 24, cudaMemcpyDeviceToHost, stream));
     if (out_cost)
-      PNEC_CUDA(cudaMemcpyAsync(out_cost, a.out_cost, static_cast<size_t>(B) * 8, cudaMemcpyDeviceToHost, stream));
+      PNEC_CUDA(cudaMemcpyAsync(out_cost, d_c, static_cast<size_t>(B) * 8, cudaMemcpyDeviceToHost, stream));
     PNEC_CUDA(cudaStreamSynchronize(stream));
   }
   return PNEC_OK;
@@ -778,13 +857,164 @@ int pnec_nec_translation_batch(pnec_handle *h, const pnec_batch *batch, double *
     d_t = static_cast<double *>(h->d_tr_out.p);
     d_M = out_M ? static_cast<double *>(h->d_tr_aux.p) : nullptr;
   }
-  nec_translation_kernel<<<static_cast<unsigned>(B), 128, 0, stream>>>(st.bv, d_t, d_M);
-  PNEC_CUDA(cudaGetLastError());
-  h->launches++;
+  rc = run_nec_translation(h, st.bv, d_t, 3, d_M, stream);
+  if (rc != PNEC_OK) return rc;
   if (host) {
     PNEC_CUDA(cudaMemcpyAsync(out_translations, d_t, static_cast<size_t>(B) * 24, cudaMemcpyDeviceToHost, stream));
     if (out_M)
       PNEC_CUDA(cudaMemcpyAsync(out_M, d_M, static_cast<size_t>(B) * 48, cudaMemcpyDeviceToHost, stream));
+    PNEC_CUDA(cudaStreamSynchronize(stream));
+  }
+  return PNEC_OK;
+}
+
+int pnec_eigensolver_batch(pnec_handle *h, const pnec_batch *batch, const double *weight_poses,
+                           double regularization, double *out_poses, int32_t *out_lm_info,
+                           double *out_smallest_ev, void *cuda_stream) {
+  if (!h || !out_poses) return fail(PNEC_ERR_INVALID_ARGUMENT, "NULL argument");
+  const bool weighted = weight_poses != nullptr;
+  const int variant = weighted ? PNEC_VARIANT_TARGET : PNEC_VARIANT_NEC;
+  int rc = validate_batch(batch, variant, true);
+  if (rc != PNEC_OK) return rc;
+  const long long B = batch->num_problems;
+  if (B == 0) return PNEC_OK;
+  std::lock_guard<std::mutex> lock(h->mu);
+  PNEC_CUDA(cudaSetDevice(h->device));
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  Staged st;
+  rc = stage_batch(h, batch, variant, stream, &st);
+  if (rc != PNEC_OK) return rc;
+  const bool host = batch->memspace == PNEC_MEM_HOST;
+  const size_t nb = static_cast<size_t>(B);
+  PNEC_CUDA(h->d_es_mom.ensure(nb * kEsMom * 8));
+  double *d_mom = static_cast<double *>(h->d_es_mom.p);
+  double *d_out = out_poses, *d_ev = out_smallest_ev;
+  int *d_info = out_lm_info;
+  const double *d_wp = weight_poses;
+  if (host) {
+    PNEC_CUDA(h->d_fr_a.ensure(nb * 56));
+    PNEC_CUDA(h->d_es_info.ensure(nb * 4));
+    PNEC_CUDA(h->d_es_ev.ensure(nb * 8));
+    d_out = static_cast<double *>(h->d_fr_a.p);
+    d_info = out_lm_info ? static_cast<int *>(h->d_es_info.p) : nullptr;
+    d_ev = out_smallest_ev ? static_cast<double *>(h->d_es_ev.p) : nullptr;
+    if (weighted) {
+      PNEC_CUDA(h->d_es_w.ensure(nb * 56));
+      PNEC_CUDA(cudaMemcpyAsync(h->d_es_w.p, weight_poses, nb * 56, cudaMemcpyHostToDevice, stream));
+      d_wp = static_cast<const double *>(h->d_es_w.p);
+    }
+  }
+  BatchView mv = st.bv;
+  if (weighted) mv.poses = d_wp;
+  rc = run_es_moments(h, mv, weighted, regularization, d_mom, stream);
+  if (rc != PNEC_OK) return rc;
+  rc = run_es_lm(h, B, d_mom, st.bv.poses, d_out, d_info, d_ev, stream);
+  if (rc != PNEC_OK) return rc;
+  if (host) {
+    PNEC_CUDA(cudaMemcpyAsync(out_poses, d_out, nb * 56, cudaMemcpyDeviceToHost, stream));
+    if (out_lm_info)
+      PNEC_CUDA(cudaMemcpyAsync(out_lm_info, d_info, nb * 4, cudaMemcpyDeviceToHost, stream));
+    if (out_smallest_ev)
+      PNEC_CUDA(cudaMemcpyAsync(out_smallest_ev, d_ev, nb * 8, cudaMemcpyDeviceToHost, stream));
+    PNEC_CUDA(cudaStreamSynchronize(stream));
+  }
+  return PNEC_OK;
+}
+
+void pnec_frame_opts_default(pnec_frame_opts *o) {
+  if (!o) return;
+  o->use_nec = 0;
+  o->use_ceres = 1;
+  o->weighted_iterations = 10;
+  o->use_ransac = 0;
+  o->fibonacci_samples = 500;
+  o->scf_steps = 10;
+  pnec_solver_opts_default(&o->ceres);
+}
+
+int pnec_frame_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_frame_opts *opts,
+                           const pnec_frame_out *out, void *cuda_stream) {
+  if (!h || !opts || !out) return fail(PNEC_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (opts->use_ransac)
+    return fail(PNEC_ERR_UNSUPPORTED, "pnec_frame_solve_batch: RANSAC (use_ransac_) is not implemented");
+  if (opts->weighted_iterations < 0 || opts->fibonacci_samples < 0 || opts->scf_steps < 0)
+    return fail(PNEC_ERR_INVALID_ARGUMENT, "negative iteration / sample / step count");
+  const bool nec = opts->use_nec != 0;
+  const bool weighted = !nec && opts->weighted_iterations > 1;
+  const int variant = nec ? PNEC_VARIANT_NEC : PNEC_VARIANT_TARGET;
+  int rc = validate_batch(batch, variant, true);
+  if (rc != PNEC_OK) return rc;
+  const long long B = batch->num_problems;
+  if (B > 0 && !out->poses) return fail(PNEC_ERR_INVALID_ARGUMENT, "out->poses is NULL");
+  if (B == 0) return PNEC_OK;
+  std::lock_guard<std::mutex> lock(h->mu);
+  PNEC_CUDA(cudaSetDevice(h->device));
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  Staged st;
+  rc = stage_batch(h, batch, variant, stream, &st);
+  if (rc != PNEC_OK) return rc;
+  if (weighted && scf_smem_bytes(st.max_n) + kStaticSmemReserve > h->smem_optin)
+    return fail(PNEC_ERR_UNSUPPORTED, "pnec_frame_solve_batch: the SCF stage keeps a frame pair in shared memory (~3100 correspondences at most)");
+  const bool host = batch->memspace == PNEC_MEM_HOST;
+  const size_t nb = static_cast<size_t>(B);
+  PNEC_CUDA(h->d_es_mom.ensure(nb * kEsMom * 8));
+  PNEC_CUDA(h->d_fr_es.ensure(nb * 56));
+  PNEC_CUDA(h->d_fr_a.ensure(nb * 56));
+  PNEC_CUDA(h->d_fr_b.ensure(nb * 56));
+  double *d_mom = static_cast<double *>(h->d_es_mom.p);
+  double *d_es = (!host && out->es_poses) ? out->es_poses : static_cast<double *>(h->d_fr_es.p);
+  double *d_a = static_cast<double *>(h->d_fr_a.p), *d_b = static_cast<double *>(h->d_fr_b.p);
+
+  // 1. PNEC::Eigensolver: rotation, then TranslationFromM(ComposeM(bvs1, bvs2, rotation))
+  rc = run_es_moments(h, st.bv, false, 0.0, d_mom, stream);
+  if (rc != PNEC_OK) return rc;
+  rc = run_es_lm(h, B, d_mom, st.bv.poses, d_es, nullptr, nullptr, stream);
+  if (rc != PNEC_OK) return rc;
+  BatchView ev = st.bv;
+  ev.poses = d_es;
+  rc = run_nec_translation(h, ev, d_es + 4, 7, nullptr, stream);
+  if (rc != PNEC_OK) return rc;
+
+  // 2./3. the start pose of the refinement
+  const double *d_init = d_es;
+  if (weighted) {
+    // weights from ES_solution in every iteration (pnec.cc:296-300): one set of weighted moments
+    rc = run_es_moments(h, ev, true, opts->ceres.regularization, d_mom, stream);
+    if (rc != PNEC_OK) return rc;
+    const double *cur = d_es;
+    for (int it = 0; it + 1 < opts->weighted_iterations; ++it) {
+      double *nxt = (it & 1) ? d_b : d_a;
+      rc = run_es_lm(h, B, d_mom, cur, nxt, nullptr, nullptr, stream);  // rotation; translation passed through
+      if (rc != PNEC_OK) return rc;
+      BatchView sv = st.bv;
+      sv.poses = nxt;
+      rc = run_scf(h, sv, st.max_n, opts->ceres.regularization, opts->fibonacci_samples, opts->scf_steps,
+                   nxt + 4, 7, nullptr, stream);
+      if (rc != PNEC_OK) return rc;
+      cur = nxt;
+    }
+    d_init = cur;
+  } else if (!nec && opts->weighted_iterations == 0) {
+    normalize_poses_kernel<<<static_cast<unsigned>((B + 127) / 128), 128, 0, stream>>>(st.bv.poses, d_a, B);
+    PNEC_CUDA(cudaGetLastError());
+    h->launches++;
+    d_init = d_a;
+  }
+
+  // 4. refinement
+  if (opts->use_ceres) {
+    pnec_solver_opts so = opts->ceres;
+    so.variant = variant;
+    BatchView rv = st.bv;
+    rv.poses = d_init;
+    rc = run_solve(h, rv, st.max_n, so, host, out->poses, out->status, out->iterations, out->cost, nullptr, stream);
+    if (rc != PNEC_OK) return rc;
+  } else {
+    PNEC_CUDA(cudaMemcpyAsync(out->poses, d_init, nb * 56, host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, stream));
+  }
+  if (host) {
+    if (out->es_poses)
+      PNEC_CUDA(cudaMemcpyAsync(out->es_poses, d_es, nb * 56, cudaMemcpyDeviceToHost, stream));
     PNEC_CUDA(cudaStreamSynchronize(stream));
   }
   return PNEC_OK;

@@ -1,0 +1,656 @@
+// pnec_eigensolver.cuh — rotation from the NEC eigenvalue minimisation:
+//   es_moments_kernel   the six 3x3 moment matrices of opengv::relative_pose::eigensolver
+//                       (xxF .. zxF = sum_i w_i f1_u f1_v f2 f2^T), optionally weighted with
+//                       pnec::common::Weight * 1e-8 (src/common/common.cc:183-208,
+//                       src/rel_pose_estimation/pnec.cc:294-306)
+//   es_lm_kernel        the minimisation itself: lambda_min(M(c)) over the Cayley parameters by
+//                       Levenberg-Marquardt on its gradient (Eigen's port of MINPACK lmdif as opengv
+//                       configures it), i.e. opengv::relative_pose::eigensolver(adapter) as called at
+//                       pnec.cc:274 (PNEC::Eigensolver) and pnec.cc:313 (PNEC::WeightedEigensolver)
+// opengv is not part of the reference tree (it arrives un-pinned inside basalt); the algorithm is
+// restated from its publication and public sources, see oracle/pnec_oracle_frame.c.
+//
+// The streaming part is one pass over f1, f2 (and the covariances for the weights); the
+// minimisation touches only the 36 moments of a frame pair, so it runs one THREAD per pair with
+// the moments in shared memory and a single call site for the function evaluation (a small state
+// machine) so that the lanes of a warp stay converged through the expensive part.
+#pragma once
+
+#include "pnec_translation.cuh"
+
+namespace pnec {
+
+constexpr int kEsMom = 36;  // sym(f1 f1^T) [6] x sym(f2 f2^T) [6], both in xx xy xz yy yz zz order
+
+// ------------------------------------------------------------------ moments
+
+struct EsMomentArgs {
+  BatchView bv;   // poses: the pose the weights are computed from (weighted only)
+  double reg;
+  double *out;    // [B][36]
+};
+
+// 48 -> 2 values per lane: after the five exchange steps lane L holds the warp-wide sums of the
+// value indices base(L) + {0, 1}, base = 24 b4 + 12 b3 + 6 b2 + 3 b1 + 2 b0 (the second one is
+// padding when b0 = 1).  Fixed order => deterministic.
+__device__ __forceinline__ void warp_transpose_reduce48(double v[48], int lane) {
+  exchange_step<48, 16>(v, lane);
+  exchange_step<24, 8>(v, lane);
+  exchange_step<12, 4>(v, lane);
+  exchange_step<6, 2>(v, lane);
+  v[3] = 0.0;
+  exchange_step<4, 1>(v, lane);
+}
+
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(128) es_moments_kernel(const __grid_constant__ EsMomentArgs args) {
+  __shared__ double s_part[4][kEsMom];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long b = blockIdx.x;
+  long long s, e;
+  problem_range(args.bv, b, s, e);
+  double R[9], t[3] = {0, 0, 0};
+  if (WEIGHTED) {
+    const double *pose = args.bv.poses + 7 * b;
+    pose_rotation(pose, R);
+    t[0] = pose[4]; t[1] = pose[5]; t[2] = pose[6];
+  }
+  double acc[48];
+#pragma unroll
+  for (int k = 0; k < 48; ++k) acc[k] = 0.0;
+  for (long long i = s + tid; i < e; i += 128) {
+    double f1[3], f2[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { f1[k] = args.bv.f1[3 * i + k]; f2[k] = args.bv.f2[3 * i + k]; }
+    if (WEIGHTED) {
+      // Weight(bv1, bv2, t, R, cov, reg, false) * 1e-8: 1 / (b^T S b + reg), b = R^T (t x f1);
+      // the adapter then holds f2 * sqrt(weight) (pnec.cc:302-306)
+      double c9[9], s6[6], a[3], bb[3], Sb[3];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) c9[k] = args.bv.ct[9 * i + k];
+      pack_sym(c9, s6);
+      cross3(t, f1, a);
+      rot_t(R, a, bb);
+      sym_mul6(s6, bb, Sb);
+      const double w = 1.0e-8 / (dot3(bb, Sb) + args.reg);
+      const double sw = sqrt(w);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) f2[k] *= sw;
+    }
+    const double A[6] = {f1[0] * f1[0], f1[0] * f1[1], f1[0] * f1[2], f1[1] * f1[1], f1[1] * f1[2], f1[2] * f1[2]};
+    const double F[6] = {f2[0] * f2[0], f2[0] * f2[1], f2[0] * f2[2], f2[1] * f2[1], f2[1] * f2[2], f2[2] * f2[2]};
+#pragma unroll
+    for (int p = 0; p < 6; ++p)
+#pragma unroll
+      for (int q = 0; q < 6; ++q) acc[6 * p + q] = fma(A[p], F[q], acc[6 * p + q]);
+  }
+  warp_transpose_reduce48(acc, lane);
+  const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1, b1 = (lane >> 1) & 1, b0 = lane & 1;
+  const int base = 24 * b4 + 12 * b3 + 6 * b2 + 3 * b1 + 2 * b0;
+  if (base < kEsMom) s_part[warp][base] = acc[0];
+  if (b0 == 0 && base + 1 < kEsMom) s_part[warp][base + 1] = acc[1];
+  __syncthreads();
+  if (tid < kEsMom) args.out[kEsMom * b + tid] = (s_part[0][tid] + s_part[1][tid]) + (s_part[2][tid] + s_part[3][tid]);
+}
+
+// ------------------------------------------------- lambda_min(M(c)) and gradient
+
+// scatter of W_uv = R' G_uv R'^T (sym 6) into M = sum n n^T (sym 6), n = f1 x R' f2:
+//   M_ab = sum eps_aup eps_bvs W_uv[p][s]
+template <int UV>
+__device__ __forceinline__ void es_scatter(const double W[6], double M[6]) {
+  // indices: 0 = 00, 1 = 01, 2 = 02, 3 = 11, 4 = 12, 5 = 22
+  if (UV == 0) { M[3] += W[5]; M[5] += W[3]; M[4] -= W[4]; }
+  if (UV == 1) { M[5] -= 2.0 * W[1]; M[1] -= W[5]; M[2] += W[4]; M[4] += W[2]; }
+  if (UV == 2) { M[3] -= 2.0 * W[2]; M[1] += W[4]; M[2] -= W[3]; M[4] += W[1]; }
+  if (UV == 3) { M[0] += W[5]; M[5] += W[0]; M[2] -= W[2]; }
+  if (UV == 4) { M[0] -= 2.0 * W[4]; M[1] += W[2]; M[2] += W[1]; M[4] -= W[0]; }
+  if (UV == 5) { M[0] += W[3]; M[3] += W[0]; M[1] -= W[1]; }
+}
+
+template <int UV>
+__device__ __forceinline__ void es_term(const double *mom, int stride, const double R[3][3],
+                                        const double dR[3][3][3], double M[6], double dM[3][6]) {
+  double G[6];
+#pragma unroll
+  for (int q = 0; q < 6; ++q) G[q] = mom[(6 * UV + q) * stride];
+  const double Gf[3][3] = {{G[0], G[1], G[2]}, {G[1], G[3], G[4]}, {G[2], G[4], G[5]}};
+  // P = G R'^T
+  double P[3][3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int sI = 0; sI < 3; ++sI) P[r][sI] = Gf[r][0] * R[sI][0] + Gf[r][1] * R[sI][1] + Gf[r][2] * R[sI][2];
+  // W = R' P (symmetric), dW_k = dR_k P + (dR_k P)^T
+  double W[6];
+  {
+    int k = 0;
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+#pragma unroll
+      for (int sI = p; sI < 3; ++sI) W[k++] = R[p][0] * P[0][sI] + R[p][1] * P[1][sI] + R[p][2] * P[2][sI];
+  }
+  es_scatter<UV>(W, M);
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    double dW[6];
+    int k = 0;
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+#pragma unroll
+      for (int sI = p; sI < 3; ++sI)
+        dW[k++] = (dR[d][p][0] * P[0][sI] + dR[d][p][1] * P[1][sI] + dR[d][p][2] * P[2][sI]) +
+                  (dR[d][sI][0] * P[0][p] + dR[d][sI][1] * P[1][p] + dR[d][sI][2] * P[2][p]);
+    es_scatter<UV>(dW, dM[d]);
+  }
+}
+
+// opengv eigensolver::getSmallestEVwithJacobian: closed-form smallest root of the characteristic
+// cubic of M(c) and its derivative with respect to the Cayley parameters.  `mom` points at this
+// problem's first moment; consecutive moments are `stride` doubles apart.
+__device__ __forceinline__ double es_smallest_ev(const double *mom, int stride, const double c[3], double grad[3]) {
+  const double x = c[0], y = c[1], z = c[2];
+  // opengv::math::cayley2rot_reduced: (1 + |c|^2) * rotation
+  const double R[3][3] = {{1 + x * x - y * y - z * z, 2 * (x * y - z), 2 * (x * z + y)},
+                          {2 * (x * y + z), 1 - x * x + y * y - z * z, 2 * (y * z - x)},
+                          {2 * (x * z - y), 2 * (y * z + x), 1 - x * x - y * y + z * z}};
+  const double dR[3][3][3] = {{{2 * x, 2 * y, 2 * z}, {2 * y, -2 * x, -2.0}, {2 * z, 2.0, -2 * x}},
+                              {{-2 * y, 2 * x, 2.0}, {2 * x, 2 * y, 2 * z}, {-2.0, 2 * z, -2 * y}},
+                              {{-2 * z, -2.0, 2 * x}, {2.0, -2 * z, 2 * y}, {2 * x, 2 * y, 2 * z}}};
+  double M[6] = {0, 0, 0, 0, 0, 0};
+  double dM[3][6] = {{0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}};
+  es_term<0>(mom, stride, R, dR, M, dM);
+  es_term<1>(mom, stride, R, dR, M, dM);
+  es_term<2>(mom, stride, R, dR, M, dM);
+  es_term<3>(mom, stride, R, dR, M, dM);
+  es_term<4>(mom, stride, R, dR, M, dM);
+  es_term<5>(mom, stride, R, dR, M, dM);
+  // M: 0 = 00, 1 = 01, 2 = 02, 3 = 11, 4 = 12, 5 = 22
+  const double m00 = M[0], m01 = M[1], m02 = M[2], m11 = M[3], m12 = M[4], m22 = M[5];
+  const double b = -m00 - m11 - m22;
+  const double cc = -m02 * m02 - m12 * m12 - m01 * m01 + m00 * m11 + m00 * m22 + m11 * m22;
+  const double d = m11 * m02 * m02 + m00 * m12 * m12 + m22 * m01 * m01 - m00 * m11 * m22 - 2 * m01 * m12 * m02;
+  const double s = 2 * b * b * b - 9 * b * cc + 27 * d;
+  const double q = b * b - 3 * cc;         // t = 4 q^3, sqrt(t) = 2 q^(3/2), w = (sqrt(t)/2)^(1/3) = sqrt(q)
+  const double w = sqrt(q);
+  const double sqrt_t = 2.0 * q * w;
+  const double t = 4.0 * q * q * q;
+  const double ratio = s / sqrt_t;
+  const double alpha = acos(ratio);
+  double sb, cb;
+  sincos(alpha / 3.0, &sb, &cb);
+  const double ev = (-b - 2.0 * (w * cb)) / 3.0;
+  const double inv_sin_alpha = -1.0 / sqrt(1.0 - (s * s) / t);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double j00 = dM[k][0], j01 = dM[k][1], j02 = dM[k][2], j11 = dM[k][3], j12 = dM[k][4], j22 = dM[k][5];
+    const double bj = -j00 - j11 - j22;
+    const double cj = -2.0 * m02 * j02 - 2.0 * m12 * j12 - 2.0 * m01 * j01 + j00 * m11 + m00 * j11 + j00 * m22 +
+                      m00 * j22 + j11 * m22 + m11 * j22;
+    const double dj = j11 * m02 * m02 + 2.0 * m11 * m02 * j02 + j00 * m12 * m12 + 2.0 * m00 * m12 * j12 +
+                      j22 * m01 * m01 + 2.0 * m22 * m01 * j01 - j00 * m11 * m22 - m00 * j11 * m22 - m00 * m11 * j22 -
+                      2.0 * (j01 * m12 * m02 + m01 * j12 * m02 + m01 * m12 * j02);
+    const double sj = 6.0 * b * b * bj - 9.0 * bj * cc - 9.0 * b * cj + 27.0 * dj;
+    const double qj = 2.0 * b * bj - 3.0 * cj;
+    const double tj = 12.0 * q * q * qj;
+    const double alphaj = inv_sin_alpha * (sj * sqrt_t - s * 0.5 * tj / sqrt_t) / t;
+    const double yj = -sb * (alphaj / 3.0);
+    const double wj = qj / (2.0 * w);
+    const double kj = wj * cb + w * yj;
+    grad[k] = (-bj - 2.0 * kj) / 3.0;
+  }
+  return ev;
+}
+
+// ------------------------------------------------------- MINPACK lmdif, n = m = 3
+
+__device__ __forceinline__ double pick3(const double v[3], int k) { return k == 0 ? v[0] : (k == 1 ? v[1] : v[2]); }
+__device__ __forceinline__ void put3(double v[3], int k, double x) {
+  if (k == 0) v[0] = x; else if (k == 1) v[1] = x; else v[2] = x;
+}
+__device__ __forceinline__ double enorm3(const double v[3]) { return sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
+
+// qrfac with column pivoting (a[i][j], row i, column j).  On exit: strict upper triangle = R,
+// rdiag = diagonal of R, lower trapezoid = Householder vectors, acnorm = input column norms.
+__device__ __forceinline__ void es_qrfac(double a[3][3], int ipvt[3], double rdiag[3], double acnorm[3]) {
+  double wa[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    acnorm[j] = sqrt(a[0][j] * a[0][j] + a[1][j] * a[1][j] + a[2][j] * a[2][j]);
+    rdiag[j] = acnorm[j];
+    wa[j] = acnorm[j];
+    ipvt[j] = j;
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    int kmax = j;
+    double best = rdiag[j];
+#pragma unroll
+    for (int k = j + 1; k < 3; ++k)
+      if (rdiag[k] > best) { best = rdiag[k]; kmax = k; }
+#pragma unroll
+    for (int k = j + 1; k < 3; ++k)
+      if (kmax == k) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { const double tmp = a[i][j]; a[i][j] = a[i][k]; a[i][k] = tmp; }
+        rdiag[k] = rdiag[j];
+        wa[k] = wa[j];
+        const int ti = ipvt[j]; ipvt[j] = ipvt[k]; ipvt[k] = ti;
+      }
+    double ss = 0.0;
+#pragma unroll
+    for (int i = j; i < 3; ++i) ss += a[i][j] * a[i][j];
+    double ajnorm = sqrt(ss);
+    if (ajnorm != 0.0) {
+      if (a[j][j] < 0.0) ajnorm = -ajnorm;
+#pragma unroll
+      for (int i = j; i < 3; ++i) a[i][j] /= ajnorm;
+      a[j][j] += 1.0;
+#pragma unroll
+      for (int k = j + 1; k < 3; ++k) {
+        double sum = 0.0;
+#pragma unroll
+        for (int i = j; i < 3; ++i) sum += a[i][j] * a[i][k];
+        const double temp = sum / a[j][j];
+#pragma unroll
+        for (int i = j; i < 3; ++i) a[i][k] -= temp * a[i][j];
+        if (rdiag[k] != 0.0) {
+          const double tq = a[j][k] / rdiag[k];
+          rdiag[k] *= sqrt(fmax(0.0, 1.0 - tq * tq));
+          const double qq = rdiag[k] / wa[k];
+          if (0.05 * qq * qq <= DBL_EPSILON) {
+            double rs = 0.0;
+#pragma unroll
+            for (int i = j + 1; i < 3; ++i) rs += a[i][k] * a[i][k];
+            rdiag[k] = sqrt(rs);
+            wa[k] = rdiag[k];
+          }
+        }
+      }
+    }
+    rdiag[j] = -ajnorm;
+  }
+}
+
+// qrsolv: r upper triangle in, lower triangle receives the transposed S; `dp[j]` = diag[ipvt[j]].
+// xp receives the solution in PIVOTED order (xp[j] belongs to variable ipvt[j]).
+__device__ __forceinline__ void es_qrsolv(double r[3][3], const double dp[3], const double qtb[3], double xp[3],
+                                          double sdiag[3]) {
+  double wa[3], save[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+#pragma unroll
+    for (int i = j; i < 3; ++i) r[i][j] = r[j][i];
+    save[j] = r[j][j];
+    wa[j] = qtb[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    if (dp[j] != 0.0) {
+#pragma unroll
+      for (int k = j; k < 3; ++k) sdiag[k] = 0.0;
+      sdiag[j] = dp[j];
+      double qtbpj = 0.0;
+#pragma unroll
+      for (int k = j; k < 3; ++k) {
+        if (sdiag[k] != 0.0) {
+          double sn, cs;
+          if (fabs(r[k][k]) < fabs(sdiag[k])) {
+            const double cotan = r[k][k] / sdiag[k];
+            sn = 0.5 / sqrt(0.25 + 0.25 * cotan * cotan);
+            cs = sn * cotan;
+          } else {
+            const double tn = sdiag[k] / r[k][k];
+            cs = 0.5 / sqrt(0.25 + 0.25 * tn * tn);
+            sn = cs * tn;
+          }
+          r[k][k] = cs * r[k][k] + sn * sdiag[k];
+          const double temp = cs * wa[k] + sn * qtbpj;
+          qtbpj = -sn * wa[k] + cs * qtbpj;
+          wa[k] = temp;
+#pragma unroll
+          for (int i = k + 1; i < 3; ++i) {
+            const double t2 = cs * r[i][k] + sn * sdiag[i];
+            sdiag[i] = -sn * r[i][k] + cs * sdiag[i];
+            r[i][k] = t2;
+          }
+        }
+      }
+    }
+    sdiag[j] = r[j][j];
+    r[j][j] = save[j];
+  }
+  int nsing = 3;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    if (sdiag[j] == 0.0 && nsing == 3) nsing = j;
+    if (nsing < 3) wa[j] = 0.0;
+  }
+#pragma unroll
+  for (int j = 2; j >= 0; --j) {
+    if (j < nsing) {
+      double sum = 0.0;
+#pragma unroll
+      for (int i = j + 1; i < 3; ++i)
+        if (i < nsing) sum += r[i][j] * wa[i];
+      wa[j] = (wa[j] - sum) / sdiag[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) xp[j] = wa[j];
+}
+
+// lmpar in pivoted coordinates: dp[j] = diag[ipvt[j]]; xp[j] = step component of variable ipvt[j].
+__device__ __forceinline__ void es_lmpar(double r[3][3], const double dp[3], const double qtb[3], double delta,
+                                         double &par, double xp[3]) {
+  const double dwarf = DBL_MIN;
+  double wa1[3], wa2[3], sdiag[3];
+  int nsing = 3;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    wa1[j] = qtb[j];
+    if (r[j][j] == 0.0 && nsing == 3) nsing = j;
+    if (nsing < 3) wa1[j] = 0.0;
+  }
+#pragma unroll
+  for (int j = 2; j >= 0; --j) {
+    if (j < nsing) {
+      wa1[j] /= r[j][j];
+      const double temp = wa1[j];
+#pragma unroll
+      for (int i = 0; i < j; ++i) wa1[i] -= r[i][j] * temp;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) { xp[j] = wa1[j]; wa2[j] = dp[j] * xp[j]; }
+  double dxnorm = enorm3(wa2);
+  double fp = dxnorm - delta;
+  if (fp <= 0.1 * delta) {
+    par = 0.0;
+    return;
+  }
+  double parl = 0.0;
+  if (nsing >= 3) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) wa1[j] = dp[j] * (wa2[j] / dxnorm);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      double sum = 0.0;
+#pragma unroll
+      for (int i = 0; i < j; ++i) sum += r[i][j] * wa1[i];
+      wa1[j] = (wa1[j] - sum) / r[j][j];
+    }
+    const double temp = enorm3(wa1);
+    parl = ((fp / delta) / temp) / temp;
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    double sum = 0.0;
+#pragma unroll
+    for (int i = 0; i <= j; ++i) sum += r[i][j] * qtb[i];
+    wa1[j] = sum / dp[j];
+  }
+  const double gnorm = enorm3(wa1);
+  double paru = gnorm / delta;
+  if (paru == 0.0) paru = dwarf / fmin(delta, 0.1);
+  par = fmin(fmax(par, parl), paru);
+  if (par == 0.0) par = gnorm / dxnorm;
+  for (int iter = 1;; ++iter) {
+    if (par == 0.0) par = fmax(dwarf, 0.001 * paru);
+    double temp = sqrt(par);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) wa1[j] = temp * dp[j];
+    es_qrsolv(r, wa1, qtb, xp, sdiag);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) wa2[j] = dp[j] * xp[j];
+    dxnorm = enorm3(wa2);
+    temp = fp;
+    fp = dxnorm - delta;
+    if (fabs(fp) <= 0.1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || iter == 10) break;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) wa1[j] = dp[j] * (wa2[j] / dxnorm);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      wa1[j] /= sdiag[j];
+      const double t2 = wa1[j];
+#pragma unroll
+      for (int i = j + 1; i < 3; ++i) wa1[i] -= r[i][j] * t2;
+    }
+    temp = enorm3(wa1);
+    const double parc = ((fp / delta) / temp) / temp;
+    if (fp > 0.0) parl = fmax(parl, par);
+    if (fp < 0.0) paru = fmin(paru, par);
+    par = fmax(parl, par + parc);
+  }
+}
+
+struct EsLmArgs {
+  const double *moments;   // [B][36]
+  const double *poses_in;  // [B][7]: start rotation (R12 of the adapter); translation is passed through
+  double *poses_out;       // [B][7]: unit quaternion of cayley2rot(result) + the input translation
+  int *out_info;           // [B] MINPACK info code, or nullptr
+  int *out_nfev;           // [B] function evaluations (Eigen's accounting), or nullptr
+  double *out_ev;          // [B] lambda_min of the reduced M at the result, or nullptr
+  long long num_problems;
+  double ftol, xtol, gtol, factor;
+  int maxfev;
+};
+
+constexpr int kEsLmThreads = 64;
+
+// One thread per frame pair.  States of the evaluation loop: 0 = f(x0), 1..3 = forward-difference
+// column j = state - 1, 4 = trial point.
+__global__ void __launch_bounds__(kEsLmThreads) es_lm_kernel(const __grid_constant__ EsLmArgs args) {
+  __shared__ double s_mom[kEsMom * kEsLmThreads];
+  const int tid = threadIdx.x;
+  const long long b = static_cast<long long>(blockIdx.x) * kEsLmThreads + tid;
+  const bool active = b < args.num_problems;
+  const long long bb = active ? b : args.num_problems - 1;
+  // coalesced staging of this CTA's moments, transposed to [k][thread]
+  {
+    const long long first = static_cast<long long>(blockIdx.x) * kEsLmThreads;
+    const long long cnt = min(static_cast<long long>(kEsLmThreads), args.num_problems - first);
+    for (long long i = tid; i < cnt * kEsMom; i += kEsLmThreads) {
+      const int p = static_cast<int>(i / kEsMom), k = static_cast<int>(i % kEsMom);
+      s_mom[k * kEsLmThreads + p] = args.moments[first * kEsMom + i];
+    }
+    __syncthreads();
+  }
+  const double *mom = s_mom + (active ? tid : 0);
+  const double *pin = args.poses_in + 7 * bb;
+  // opengv::math::rot2cayley: [c]x = (R - I)(R + I)^-1, i.e. q_xyz / q_w
+  double x[3] = {pin[0] / pin[3], pin[1] / pin[3], pin[2] / pin[3]};
+
+  const double epsmch = DBL_EPSILON;
+  const double eps = sqrt(epsmch);  // epsfcn = 0
+  double fvec[3] = {0, 0, 0}, r[3][3], diag[3] = {1, 1, 1}, dp[3], qtf[3] = {0, 0, 0}, wa1[3], wa2[3], acn[3];
+  int ipvt[3] = {0, 1, 2};
+  double fnorm = 0.0, par = 0.0, delta = 0.0, xnorm = 0.0, gnorm = 0.0, h = 0.0, pnorm = 0.0;
+  int info = 0, nfev = 0, iter = 1, state = 0;
+  bool done = !active;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) r[i][j] = 0.0;
+
+  while (!__all_sync(0xffffffffu, done)) {
+    // ---- the point to evaluate
+    double xe[3] = {x[0], x[1], x[2]};
+    if (state >= 1 && state <= 3) {
+      const double xj = pick3(x, state - 1);
+      h = eps * fabs(xj);
+      if (h == 0.0) h = eps;
+      put3(xe, state - 1, xj + h);
+    } else if (state == 4) {
+      xe[0] = wa2[0]; xe[1] = wa2[1]; xe[2] = wa2[2];
+    }
+    double fe[3];
+    es_smallest_ev(mom, kEsLmThreads, xe, fe);
+    if (done) continue;
+
+    bool need_step = false;
+    if (state == 0) {
+      fvec[0] = fe[0]; fvec[1] = fe[1]; fvec[2] = fe[2];
+      fnorm = enorm3(fvec);
+      nfev = 1;
+      state = 1;
+    } else if (state <= 3) {
+      const int j = state - 1;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const double v = (fe[i] - fvec[i]) / h;
+        if (j == 0) r[i][0] = v; else if (j == 1) r[i][1] = v; else r[i][2] = v;
+      }
+      if (state < 3) {
+        state += 1;
+      } else {
+        nfev += 4;  // Eigen's NumericalDiff (Forward) evaluates f(x) again: n + 1 calls per Jacobian
+        double rdiag[3];
+        es_qrfac(r, ipvt, rdiag, acn);
+        if (iter == 1) {
+#pragma unroll
+          for (int j2 = 0; j2 < 3; ++j2) diag[j2] = (acn[j2] == 0.0) ? 1.0 : acn[j2];
+          const double dx[3] = {diag[0] * x[0], diag[1] * x[1], diag[2] * x[2]};
+          xnorm = enorm3(dx);
+          delta = args.factor * xnorm;
+          if (delta == 0.0) delta = args.factor;
+        }
+        // qtf = first n components of Q^T fvec; store R's diagonal
+        double w4[3] = {fvec[0], fvec[1], fvec[2]};
+#pragma unroll
+        for (int j2 = 0; j2 < 3; ++j2) {
+          if (r[j2][j2] != 0.0) {
+            double sum = 0.0;
+#pragma unroll
+            for (int i = j2; i < 3; ++i) sum += r[i][j2] * w4[i];
+            const double temp = -sum / r[j2][j2];
+#pragma unroll
+            for (int i = j2; i < 3; ++i) w4[i] += r[i][j2] * temp;
+          }
+          r[j2][j2] = rdiag[j2];
+          qtf[j2] = w4[j2];
+        }
+        gnorm = 0.0;
+        if (fnorm != 0.0) {
+#pragma unroll
+          for (int j2 = 0; j2 < 3; ++j2) {
+            const double cn = pick3(acn, ipvt[j2]);
+            if (cn != 0.0) {
+              double sum = 0.0;
+#pragma unroll
+              for (int i = 0; i <= j2; ++i) sum += r[i][j2] * (qtf[i] / fnorm);
+              gnorm = fmax(gnorm, fabs(sum / cn));
+            }
+          }
+        }
+        if (gnorm <= args.gtol) {
+          info = 4;
+          done = true;
+        } else {
+#pragma unroll
+          for (int j2 = 0; j2 < 3; ++j2) diag[j2] = fmax(diag[j2], acn[j2]);
+#pragma unroll
+          for (int j2 = 0; j2 < 3; ++j2) dp[j2] = pick3(diag, ipvt[j2]);
+          need_step = true;
+        }
+      }
+    } else {
+      // ---- trial point evaluated: fe = f(x + p)
+      ++nfev;
+      const double fnorm1 = enorm3(fe);
+      double actred = -1.0;
+      if (0.1 * fnorm1 < fnorm) actred = 1.0 - (fnorm1 / fnorm) * (fnorm1 / fnorm);
+      // wa3 = R * P^T p  (wa1 holds p in pivoted order)
+      double w3[3] = {0, 0, 0};
+#pragma unroll
+      for (int j2 = 0; j2 < 3; ++j2)
+#pragma unroll
+        for (int i = 0; i <= j2; ++i) w3[i] += r[i][j2] * wa1[j2];
+      const double t1 = enorm3(w3) / fnorm, t2 = sqrt(par) * pnorm / fnorm;
+      const double temp1 = t1 * t1, temp2 = t2 * t2;
+      const double prered = temp1 + temp2 / 0.5;
+      const double dirder = -(temp1 + temp2);
+      double ratio = 0.0;
+      if (prered != 0.0) ratio = actred / prered;
+      if (ratio <= 0.25) {
+        double temp = 0.5;
+        if (actred < 0.0) temp = 0.5 * dirder / (dirder + 0.5 * actred);
+        if (0.1 * fnorm1 >= fnorm || temp < 0.1) temp = 0.1;
+        delta = temp * fmin(delta, pnorm / 0.1);
+        par /= temp;
+      } else if (!(par != 0.0 && ratio < 0.75)) {
+        delta = pnorm / 0.5;
+        par = 0.5 * par;
+      }
+      if (ratio >= 1e-4) {
+#pragma unroll
+        for (int j2 = 0; j2 < 3; ++j2) { x[j2] = wa2[j2]; fvec[j2] = fe[j2]; }
+        const double dx[3] = {diag[0] * x[0], diag[1] * x[1], diag[2] * x[2]};
+        xnorm = enorm3(dx);
+        fnorm = fnorm1;
+        ++iter;
+      }
+      const bool small_red = fabs(actred) <= args.ftol && prered <= args.ftol && 0.5 * ratio <= 1.0;
+      if (small_red) info = 1;
+      if (delta <= args.xtol * xnorm) info = 2;
+      if (small_red && info == 2) info = 3;
+      if (info == 0) {
+        if (nfev >= args.maxfev) info = 5;
+        if (fabs(actred) <= epsmch && prered <= epsmch && 0.5 * ratio <= 1.0) info = 6;
+        if (delta <= epsmch * xnorm) info = 7;
+        if (gnorm <= epsmch) info = 8;
+      }
+      if (info != 0) {
+        done = true;
+      } else if (ratio < 1e-4) {
+        need_step = true;  // inner loop of lmdif: same Jacobian, smaller region
+      } else {
+        state = 1;
+      }
+    }
+    if (need_step) {
+      // wa1 <- step in pivoted order, wa2 <- x + p
+      es_lmpar(r, dp, qtf, delta, par, wa1);
+      double dpn[3];
+#pragma unroll
+      for (int j2 = 0; j2 < 3; ++j2) {
+        wa1[j2] = -wa1[j2];
+        dpn[j2] = dp[j2] * wa1[j2];
+      }
+      wa2[0] = x[0]; wa2[1] = x[1]; wa2[2] = x[2];
+#pragma unroll
+      for (int j2 = 0; j2 < 3; ++j2) put3(wa2, ipvt[j2], pick3(x, ipvt[j2]) + wa1[j2]);
+      pnorm = enorm3(dpn);
+      if (iter == 1) delta = fmin(delta, pnorm);
+      state = 4;
+    }
+  }
+  if (active) {
+    double *po = args.poses_out + 7 * b;
+    const double sc = 1.0 / sqrt(1.0 + x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+    po[0] = x[0] * sc; po[1] = x[1] * sc; po[2] = x[2] * sc; po[3] = sc;
+    po[4] = pin[4]; po[5] = pin[5]; po[6] = pin[6];
+    if (args.out_info) args.out_info[b] = info;
+    if (args.out_nfev) args.out_nfev[b] = nfev;
+    if (args.out_ev) {
+      double g[3];
+      args.out_ev[b] = es_smallest_ev(mom, kEsLmThreads, x, g);
+    }
+  }
+}
+
+// ------------------------------------------------------------ pipeline helpers
+
+// Sophus::SE3d holds a unit quaternion: q <- q / |q| (PNEC::Solve with weighted_iterations_ == 0
+// hands `initial_pose` to the refinement, pnec.cc:107-109).
+__global__ void normalize_poses_kernel(const double *in, double *out, long long B) {
+  const long long b = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double *p = in + 7 * b;
+  const double inv = 1.0 / sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2] + p[3] * p[3]);
+  double *o = out + 7 * b;
+  o[0] = p[0] * inv; o[1] = p[1] * inv; o[2] = p[2] * inv; o[3] = p[3] * inv;
+  o[4] = p[4]; o[5] = p[5]; o[6] = p[6];
+}
+
+}  // namespace pnec

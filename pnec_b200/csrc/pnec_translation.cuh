@@ -97,7 +97,8 @@ __device__ __forceinline__ void block_sum6(double v[6], double (*s_red)[6], int 
 struct ScfArgs {
   BatchView bv;           // poses: rotation quaternion + start translation
   const double *sphere;   // [samples][3] fibonacci_sphere(samples)
-  double *out_t;          // [B][3]
+  double *out_t;          // translation of pair b at out_t + out_stride * b
+  int out_stride;         // 3 for a [B][3] array, 7 to write into the translation slot of a pose array
   double *out_cost;       // [B] obj_fun at the result, or nullptr
   double reg;
   int samples, steps;
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(NW * 32) scf_kernel(const __grid_constant__ Sc
   const int n = static_cast<int>(e - s);
   const double *pose = args.bv.poses + 7 * b;
   double *terms = dyn_smem;  // [n][9]
-  double *ot = args.out_t + 3 * b;
+  double *ot = args.out_t + static_cast<long long>(args.out_stride) * b;
   if (n <= 0 || n > args.cap_elems) {
     // nothing to minimise (or a pair beyond the shared-memory capacity, rejected on the host)
     if (tid == 0) { ot[0] = pose[4]; ot[1] = pose[5]; ot[2] = pose[6]; if (args.out_cost) args.out_cost[b] = 0.0; }
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(NW * 32) scf_kernel(const __grid_constant__ Sc
 
 // TranslationFromM(ComposeM(bvs_1, bvs_2, R)), common.cc:127-181.  ComposeM starts its loop at
 // i = 1 (common.cc:131): the first correspondence of a pair is skipped, as in the reference.
-__global__ void __launch_bounds__(128) nec_translation_kernel(BatchView bv, double *out_t, double *out_M) {
+__global__ void __launch_bounds__(128) nec_translation_kernel(BatchView bv, double *out_t, int out_stride, double *out_M) {
   __shared__ double s_red[4][6];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long b = blockIdx.x;
@@ -267,7 +268,8 @@ __global__ void __launch_bounds__(128) nec_translation_kernel(BatchView bv, doub
   if (tid == 0) {
     double v[3], lam;
     sym3_smallest_eigvec(M, v, lam);
-    out_t[3 * b] = v[0]; out_t[3 * b + 1] = v[1]; out_t[3 * b + 2] = v[2];
+    double *ot = out_t + static_cast<long long>(out_stride) * b;
+    ot[0] = v[0]; ot[1] = v[1]; ot[2] = v[2];
     if (out_M) {
 #pragma unroll
       for (int k = 0; k < 6; ++k) out_M[6 * b + k] = M[k];

@@ -1,0 +1,145 @@
+"""CPU: the oracle's restatement of the stages of PNEC::Solve in front of the refinement
+(oracle/pnec_oracle_frame.c) — pinned where something independent exists in this image:
+
+* the Levenberg-Marquardt (Eigen's port of MINPACK lmdif, as opengv's eigensolver configures it)
+  against the Fortran MINPACK behind scipy.optimize.leastsq, on the oracle's own residuals;
+* M(c) and lambda_min against numpy (np.cross, eigvalsh), the analytic gradient against central
+  differences of eigvalsh;
+* the weights against the reference's numpy energy denominators (scripts/pnec/common.py through the
+  committed golden file) and the literal formula of common.cc:183-208.
+
+That this IS what opengv executes stays unpinned: opengv is neither in the reference tree nor in
+this image (oracle/pnec_oracle_frame.c header).
+"""
+import numpy as np
+import pytest
+from scipy.optimize import leastsq
+
+import oracle
+from conftest import direction_angle, rotation_angle
+from pnec_b200 import synthetic as syn
+
+
+@pytest.fixture(scope="module")
+def batch():
+    return syn.make_batch(12, 150, seed=3, noise_level=1.0)
+
+
+def reduced_rotation(c):
+    x, y, z = c
+    return np.array([[1 + x * x - y * y - z * z, 2 * (x * y - z), 2 * (x * z + y)],
+                     [2 * (x * y + z), 1 - x * x + y * y - z * z, 2 * (y * z - x)],
+                     [2 * (x * z - y), 2 * (y * z + x), 1 - x * x - y * y + z * z]])
+
+
+def m_numpy(f1, f2, c, w=None):
+    f2w = f2 if w is None else f2 * np.sqrt(w)[:, None]
+    n = np.cross(f1, (reduced_rotation(c) @ f2w.T).T)
+    return n.T @ n
+
+
+def test_m_and_smallest_eigenvalue_match_numpy(batch):
+    rng = np.random.default_rng(0)
+    for k in range(batch.num_problems):
+        f1, f2, ct, _ = batch.problem(k)
+        c = rng.uniform(-0.3, 0.3, 3)
+        w = rng.uniform(0.5, 2.0, f1.shape[0]) if k % 2 else None
+        ev, jac, M = oracle.es_smallest_ev(f1, f2, c, w)
+        Mn = m_numpy(f1, f2, c, w)
+        np.testing.assert_allclose(M, Mn, rtol=0, atol=1e-13 * np.abs(Mn).max())
+        assert abs(ev - np.linalg.eigvalsh(Mn)[0]) <= 1e-12 * np.abs(Mn).max()
+        g = np.zeros(3)
+        for j in range(3):
+            h = 1e-6
+            cp, cm = c.copy(), c.copy()
+            cp[j] += h
+            cm[j] -= h
+            g[j] = (np.linalg.eigvalsh(m_numpy(f1, f2, cp, w))[0] - np.linalg.eigvalsh(m_numpy(f1, f2, cm, w))[0]) / (2 * h)
+        np.testing.assert_allclose(jac, g, rtol=1e-6, atol=1e-7 * np.abs(g).max())
+
+
+def test_lm_is_minpack_lmdif(batch):
+    """Same iterates as Fortran MINPACK (scipy.optimize.leastsq, Dfun=None -> lmdif): identical x,
+    identical termination code and function-evaluation count."""
+    eps = np.finfo(float).eps
+    for k in range(batch.num_problems):
+        f1, f2, _, _ = batch.problem(k)
+        x0 = batch.init_poses[k, :3] / batch.init_poses[k, 3]
+        fun = lambda x: oracle.es_smallest_ev(f1, f2, x)[1]
+        xs, _, infod, _, ier = leastsq(fun, x0, ftol=5e-5, xtol=10 * eps, gtol=0.0, maxfev=100, epsfcn=None,
+                                       factor=100, full_output=True)
+        xo, info, nfev = oracle.es_lm(f1, f2, x0, maxfev=100, fev_per_jacobian=3)
+        np.testing.assert_allclose(xo, xs, rtol=0, atol=1e-13)
+        assert info == ier and nfev == infod["nfev"], (k, info, ier, nfev, infod["nfev"])
+
+
+def test_lm_minpack_other_settings(batch):
+    eps = np.finfo(float).eps
+    f1, f2, _, _ = batch.problem(0)
+    x0 = np.array([0.3, -0.2, 0.25])  # far start: exercises the step-bound logic of lmpar
+    fun = lambda x: oracle.es_smallest_ev(f1, f2, x)[1]
+    for ftol, xtol, factor, maxfev in [(1e-8, 1e-8, 100.0, 400), (5e-5, 10 * eps, 0.1, 400), (1e-12, 1e-12, 1.0, 30)]:
+        xs, _, infod, _, ier = leastsq(fun, x0, ftol=ftol, xtol=xtol, gtol=0.0, maxfev=maxfev, factor=factor,
+                                       full_output=True)
+        xo, info, nfev = oracle.es_lm(f1, f2, x0, ftol=ftol, xtol=xtol, factor=factor, maxfev=maxfev,
+                                      fev_per_jacobian=3)
+        np.testing.assert_allclose(xo, xs, rtol=0, atol=1e-12)
+        assert info == ier and nfev == infod["nfev"]
+
+
+def test_eigensolver_finds_the_rotation_on_noise_free_data():
+    b = syn.make_batch(8, 60, seed=9, noise_level=1e-9)
+    for k in range(b.num_problems):
+        f1, f2, _, _ = b.problem(k)
+        q, info = oracle.eigensolver(f1, f2, b.init_poses[k])
+        assert rotation_angle(np.r_[q, 0, 0, 1], b.gt_poses[k]) < 1e-7
+        assert abs(info.smallest_ev) < 1e-12
+        pose, _ = oracle.nec_eigensolver_pose(f1, f2, b.init_poses[k])
+        if np.linalg.norm(b.gt_poses[k, 4:]) > 0:
+            assert direction_angle(pose[4:], b.gt_poses[k, 4:]) < 1e-5
+
+
+def test_weights_follow_common_cc(batch):
+    f1, f2, ct, _ = batch.problem(1)
+    pose = batch.gt_poses[1]
+    w = oracle.weights(f1, ct, pose, 1e-13)
+    R = syn.quaternion_to_matrix(pose[:4])
+    t = pose[4:]
+    for i in range(0, f1.shape[0], 17):
+        S = ct[i].reshape(3, 3).T  # column-major storage
+        tt = (t @ syn.skew(f1[i]) @ R)
+        assert w[i] == pytest.approx(1e-8 / (tt @ S @ tt + 1e-13), rel=1e-12)
+
+
+def test_weighted_eigensolver_iterations_are_consistent(batch):
+    """One weighted iteration by hand (weights -> eigensolver -> SCF) equals weighted_eigensolver(2)."""
+    f1, f2, ct, _ = batch.problem(2)
+    es, _ = oracle.nec_eigensolver_pose(f1, f2, batch.init_poses[2])
+    w = oracle.weights(f1, ct, es, 1e-13)
+    q, _ = oracle.eigensolver(f1, f2, es, w)
+    t, _ = oracle.scf_translation(f1, f2, ct, np.r_[q, es[4:]], 1e-13, 500, 10)
+    pose = oracle.weighted_eigensolver(f1, f2, ct, es, weighted_iterations=2)
+    np.testing.assert_allclose(pose[:4], q, atol=1e-15)
+    np.testing.assert_allclose(pose[4:], t, atol=1e-15)
+
+
+def test_frame_solve_option_matrix(batch):
+    """PNEC::Solve's branches (pnec.cc:93-123)."""
+    n = batch.n_per_problem
+    args = (batch.bvs_host, batch.bvs_target, batch.covs_target, batch.init_poses)
+    es_only, es = oracle.frame_solve_batch(*args, oracle.default_frame_opts(use_nec=1, use_ceres=0), n_per_problem=n)
+    np.testing.assert_array_equal(es_only, es)
+    wi1, _ = oracle.frame_solve_batch(*args, oracle.default_frame_opts(weighted_iterations=1, use_ceres=0), n_per_problem=n)
+    np.testing.assert_array_equal(wi1, es)
+    wi0, _ = oracle.frame_solve_batch(*args, oracle.default_frame_opts(weighted_iterations=0, use_ceres=0), n_per_problem=n)
+    np.testing.assert_allclose(wi0, batch.init_poses, atol=1e-15)
+    # weighted_iterations = 0 + Ceres == the plain refinement of the start pose
+    ref, _ = oracle.solve_batch(batch.bvs_host, batch.bvs_target, batch.covs_target, None, batch.init_poses,
+                                oracle.default_opts(oracle.TARGET), n_per_problem=n)
+    got, _ = oracle.frame_solve_batch(*args, oracle.default_frame_opts(weighted_iterations=0), n_per_problem=n)
+    np.testing.assert_allclose(got, ref, atol=1e-14)
+    # the full pipeline ends closer to the ground truth than the NEC eigensolver alone, on average
+    full, _ = oracle.frame_solve_batch(*args, oracle.default_frame_opts(), n_per_problem=n)
+    e_es = np.mean([rotation_angle(a, g) for a, g in zip(es, batch.gt_poses)])
+    e_full = np.mean([rotation_angle(a, g) for a, g in zip(full, batch.gt_poses)])
+    assert e_full < e_es
