@@ -587,21 +587,16 @@ class PNEC {
  public:
   explicit PNEC(const Options &options) : options_(options) {}
 
-  // src/rel_pose_estimation/pnec.cc:77-124.  Only the refinement stage is built in this
-  // library (the NEC eigensolver / RANSAC / weighted eigensolver +
-  // SCF stages in front of it are the "next" rows).  Solve() therefore accepts exactly
-  // the configuration in which the reference's Solve() reduces to the refinement of
-  // `initial_pose` (no RANSAC, weighted_iterations_ == 0, Ceres on, PNEC energy) and
-  // throws for configurations that need the unbuilt stages instead of silently
-  // computing something else.
+  // src/rel_pose_estimation/pnec.cc:77-124: Eigensolver -> (WeightedEigensolver) -> CeresSolver /
+  // NECCeresSolver, every stage on the GPU in one pnec_frame_solve_batch call.  RANSAC
+  // (use_ransac_, the reference's default) is not built: Solve() throws for it instead of
+  // silently skipping the stage; `inliers` is cleared as in the non-RANSAC branch (pnec.cc:277).
+  // Like the reference, the refinement runs with default Ceres options (pnec.cc:355 constructs
+  // `PNECCeres optimizer;`) and the TARGET noise frame, whatever options_ holds.
   template <class BVs, class Covs>
   SE3 Solve(const BVs &bvs1, const BVs &bvs2, const Covs &projected_covs, const SE3 &initial_pose) {
-    if (options_.use_ransac_ || options_.use_nec_ || options_.weighted_iterations_ != 0 || !options_.use_ceres_)
-      throw std::logic_error(
-          "pnec_b200: PNEC::Solve supports use_ransac_=false, use_nec_=false, weighted_iterations_=0, "
-          "use_ceres_=true (refinement of initial_pose); call CeresSolver/NECCeresSolver directly "
-          "with your own initialisation otherwise");
-    return CeresSolver(bvs1, bvs2, projected_covs, initial_pose);
+    SE3 es;
+    return SolveImpl(bvs1, bvs2, projected_covs, initial_pose, &es);
   }
   template <class BVs, class Covs>
   SE3 Solve(const BVs &bvs1, const BVs &bvs2, const Covs &projected_covs, const SE3 &initial_pose,
@@ -609,6 +604,8 @@ class PNEC {
     inliers.clear();
     return Solve(bvs1, bvs2, projected_covs, initial_pose);
   }
+  // The reference times its stages separately (pnec.cc:135-208); here they run back to back on the
+  // device inside one call, so the total goes to ceres_ and the stage fields stay zero.
   template <class BVs, class Covs>
   SE3 Solve(const BVs &bvs1, const BVs &bvs2, const Covs &projected_covs, const SE3 &initial_pose,
             common::FrameTiming &timing) {
@@ -617,6 +614,54 @@ class PNEC {
     timing.ceres_ = std::chrono::duration_cast<std::chrono::milliseconds>(
         std::chrono::high_resolution_clock::now() - tic);
     return r;
+  }
+  template <class BVs, class Covs>
+  SE3 Solve(const BVs &bvs1, const BVs &bvs2, const Covs &projected_covs, const SE3 &initial_pose,
+            std::vector<int> &inliers, common::FrameTiming &timing) {
+    inliers.clear();
+    return Solve(bvs1, bvs2, projected_covs, initial_pose, timing);
+  }
+
+  // PNEC::Eigensolver, use_ransac_ == false (pnec.cc:273-279): opengv::relative_pose::eigensolver
+  // rotation started at initial_pose, translation = TranslationFromM(ComposeM(bvs1, bvs2, rotation)).
+  template <class BVs>
+  SE3 Eigensolver(const BVs &bvs1, const BVs &bvs2, const SE3 &initial_pose, std::vector<int> &inliers) {
+    if (options_.use_ransac_)
+      throw std::logic_error("pnec_b200: PNEC::Eigensolver with use_ransac_=true is not implemented");
+    inliers.clear();
+    pnec_frame_opts fo = FrameOpts();
+    fo.use_nec = 1;
+    fo.use_ceres = 0;
+    pnec_batch b = MakeBatch(bvs1, bvs2, static_cast<const double *>(nullptr), initial_pose);
+    SE3 out;
+    pnec_frame_out o{};
+    o.poses = reinterpret_cast<double *>(&out);
+    if (pnec_frame_solve_batch(detail::Handle(), &b, &fo, &o, nullptr) != PNEC_OK)
+      throw std::runtime_error(std::string("pnec_frame_solve_batch: ") + pnec_last_error());
+    return out;
+  }
+
+  // PNEC::WeightedEigensolver (pnec.cc:283-348): `initial_pose` supplies the weights of every
+  // iteration and the first iteration's start.
+  template <class BVs, class Covs>
+  SE3 WeightedEigensolver(const BVs &bvs1, const BVs &bvs2, const Covs &projected_covariances,
+                          const SE3 &initial_pose) {
+    SE3 rel = initial_pose;
+    pnec_handle *h = detail::Handle();
+    for (std::size_t it = 0; it + 1 < options_.weighted_iterations_; ++it) {
+      pnec_batch b = MakeBatch(bvs1, bvs2, detail::AsDoubles(projected_covariances, 72), rel);
+      SE3 next;
+      if (pnec_eigensolver_batch(h, &b, initial_pose.data(), options_.regularization_,
+                                 reinterpret_cast<double *>(&next), nullptr, nullptr, nullptr) != PNEC_OK)
+        throw std::runtime_error(std::string("pnec_eigensolver_batch: ") + pnec_last_error());
+      b.poses = next.data();  // rotation of this iteration + previous translation as the scan's first candidate
+      Vec3 t;
+      if (pnec_scf_translation_batch(h, &b, options_.regularization_, 500, 10, t.data(), nullptr, nullptr) != PNEC_OK)
+        throw std::runtime_error(std::string("pnec_scf_translation_batch: ") + pnec_last_error());
+      next.t = t;
+      rel = next;
+    }
+    return rel;
   }
 
   // src/rel_pose_estimation/pnec.cc:350-370 — ignores options_.ceres_options_ and
@@ -681,11 +726,58 @@ class PNEC {
 
   int LastStatus() const { return last_status_; }
   int LastIterations() const { return last_iterations_; }
+  // ES_solution of the last Solve() (pnec.cc:86)
+  const SE3 &LastEigensolverPose() const { return last_es_; }
 
  protected:
+  pnec_frame_opts FrameOpts() const {
+    pnec_frame_opts fo;
+    pnec_frame_opts_default(&fo);
+    fo.use_nec = options_.use_nec_ ? 1 : 0;
+    fo.use_ceres = options_.use_ceres_ ? 1 : 0;
+    fo.weighted_iterations = static_cast<int32_t>(options_.weighted_iterations_);
+    fo.use_ransac = options_.use_ransac_ ? 1 : 0;
+    fo.ceres.regularization = options_.regularization_;
+    return fo;
+  }
+  template <class BVs>
+  static pnec_batch MakeBatch(const BVs &bvs1, const BVs &bvs2, const double *covs, const SE3 &pose) {
+    pnec_batch b{};
+    b.num_problems = 1;
+    b.n_per_problem = static_cast<int64_t>(bvs1.size());
+    b.memspace = PNEC_MEM_HOST;
+    b.bvs_host = detail::AsDoubles(bvs1, 24);
+    b.bvs_target = detail::AsDoubles(bvs2, 24);
+    b.covs_target = covs;
+    b.poses = pose.data();
+    return b;
+  }
+  template <class BVs, class Covs>
+  SE3 SolveImpl(const BVs &bvs1, const BVs &bvs2, const Covs &projected_covs, const SE3 &initial_pose, SE3 *es) {
+    if (options_.use_ransac_)
+      throw std::logic_error(
+          "pnec_b200: PNEC::Solve with use_ransac_=true is not implemented (set Options::use_ransac_ = false)");
+    const pnec_frame_opts fo = FrameOpts();
+    pnec_batch b = MakeBatch(bvs1, bvs2, detail::AsDoubles(projected_covs, 72), initial_pose);
+    SE3 out;
+    int32_t status = PNEC_STATUS_EMPTY, iters = 0;
+    pnec_frame_out o{};
+    o.poses = reinterpret_cast<double *>(&out);
+    o.es_poses = reinterpret_cast<double *>(es);
+    o.status = &status;
+    o.iterations = &iters;
+    if (pnec_frame_solve_batch(detail::Handle(), &b, &fo, &o, nullptr) != PNEC_OK)
+      throw std::runtime_error(std::string("pnec_frame_solve_batch: ") + pnec_last_error());
+    last_status_ = status;
+    last_iterations_ = iters;
+    last_es_ = *es;
+    return out;
+  }
+
   Options options_;
   int last_status_ = PNEC_STATUS_EMPTY;
   int last_iterations_ = 0;
+  SE3 last_es_;
 };
 
 }  // namespace rel_pose_estimation

@@ -81,6 +81,7 @@ struct pnec_handle {
   DevBuf d_out_poses, d_out_status, d_out_iters, d_out_cost, d_out_init, d_out_grad, d_out_jtj;
   DevBuf d_ut_mu, d_ut_cov, d_ut_out, d_kp_bv, d_sphere, d_tr_out, d_tr_aux;
   DevBuf d_es_mom, d_es_w, d_es_info, d_es_ev, d_fr_es, d_fr_a, d_fr_b;  // eigensolver / frame pipeline
+  DevBuf d_fr_cache, d_fr_flags;  // ScfScanCache[B]; int q_same[B], fixed[B]
   int sphere_samples = -1;
   std::mutex mu;
 };
@@ -458,7 +459,8 @@ size_t scf_smem_bytes(long long max_n) { return static_cast<size_t>(std::max<lon
 // scf_kernel: rotation + start translation from bv.poses, result at out_t + out_stride * b (may be the
 // translation slot of bv.poses itself: every read of the pose precedes the final write)
 int run_scf(pnec_handle *h, const BatchView &bv, long long max_n, double reg, int samples, int steps,
-            double *out_t, int out_stride, double *out_cost, cudaStream_t stream) {
+            double *out_t, int out_stride, double *out_cost, cudaStream_t stream,
+            ScfScanCache *cache = nullptr, const int *q_same = nullptr, int *fixed = nullptr) {
   const size_t dyn = scf_smem_bytes(max_n);
   if (dyn + kStaticSmemReserve > h->smem_optin)
     return fail(PNEC_ERR_UNSUPPORTED, "SCF translation: a frame pair exceeds the shared-memory capacity (~3100 correspondences)");
@@ -474,6 +476,9 @@ int run_scf(pnec_handle *h, const BatchView &bv, long long max_n, double reg, in
   a.out_t = out_t;
   a.out_stride = out_stride;
   a.out_cost = out_cost;
+  a.cache = cache;
+  a.q_same = q_same;
+  a.fixed = fixed;
   auto kern = scf_kernel<4>;
   PNEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
   kern<<<static_cast<unsigned>(bv.num_problems), 128, dyn, stream>>>(a);
@@ -509,7 +514,7 @@ int run_es_moments(pnec_handle *h, const BatchView &bv, bool weighted, double re
 // opengv eigensolver_main with the parameters opengv sets (ftol 5e-5, xtol 10 eps, maxfev 100;
 // resetParameters(): factor 100, gtol 0, epsfcn 0)
 int run_es_lm(pnec_handle *h, long long B, const double *d_mom, const double *d_poses_in, double *d_poses_out,
-              int *d_info, double *d_ev, cudaStream_t stream) {
+              int *d_info, double *d_ev, cudaStream_t stream, const int *fixed = nullptr, int *q_same = nullptr) {
   EsLmArgs a{};
   a.moments = d_mom;
   a.poses_in = d_poses_in;
@@ -517,6 +522,8 @@ int run_es_lm(pnec_handle *h, long long B, const double *d_mom, const double *d_
   a.out_info = d_info;
   a.out_nfev = nullptr;
   a.out_ev = d_ev;
+  a.fixed = fixed;
+  a.q_same = q_same;
   a.num_problems = B;
   a.ftol = 0.00005;
   a.xtol = 1.0e1 * DBL_EPSILON;
@@ -602,7 +609,7 @@ void pnec_destroy(pnec_handle *h) {
                     &h->d_out_init, &h->d_out_grad, &h->d_out_jtj, &h->d_ut_mu, &h->d_ut_cov,
                     &h->d_ut_out, &h->d_kp_bv, &h->d_sphere, &h->d_tr_out,
                     &h->d_tr_aux, &h->d_es_mom, &h->d_es_w, &h->d_es_info, &h->d_es_ev,
-                    &h->d_fr_es, &h->d_fr_a, &h->d_fr_b};
+                    &h->d_fr_es, &h->d_fr_a, &h->d_fr_b, &h->d_fr_cache, &h->d_fr_flags};
   for (DevBuf *b : bufs) b->release();
   delete h;
 }
@@ -981,15 +988,29 @@ int pnec_frame_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_f
     // weights from ES_solution in every iteration (pnec.cc:296-300): one set of weighted moments
     rc = run_es_moments(h, ev, true, opts->ceres.regularization, d_mom, stream);
     if (rc != PNEC_OK) return rc;
+    // The round (R, t) -> (R', t') is a deterministic map with everything else held constant, so
+    //  * a rotation that repeats bit for bit reuses its sphere scan (ScfScanCache), and
+    //  * a pair whose whole pose repeats has reached a fixed point: later rounds are skipped.
+    // Both give exactly what recomputing would.
+    PNEC_CUDA(h->d_fr_cache.ensure(nb * sizeof(ScfScanCache)));
+    PNEC_CUDA(h->d_fr_flags.ensure(nb * 2 * sizeof(int)));
+    ScfScanCache *d_cache = static_cast<ScfScanCache *>(h->d_fr_cache.p);
+    int *d_qsame = static_cast<int *>(h->d_fr_flags.p), *d_fixed = d_qsame + B;
+    const bool shortcuts = !env_int("PNEC_B200_NO_FRAME_SHORTCUTS", 0);
+    PNEC_CUDA(cudaMemsetAsync(d_cache, 0, nb * sizeof(ScfScanCache), stream));
+    PNEC_CUDA(cudaMemsetAsync(d_qsame, 0, nb * 2 * sizeof(int), stream));
     const double *cur = d_es;
     for (int it = 0; it + 1 < opts->weighted_iterations; ++it) {
       double *nxt = (it & 1) ? d_b : d_a;
-      rc = run_es_lm(h, B, d_mom, cur, nxt, nullptr, nullptr, stream);  // rotation; translation passed through
+      // rotation; translation passed through
+      rc = run_es_lm(h, B, d_mom, cur, nxt, nullptr, nullptr, stream, shortcuts ? d_fixed : nullptr,
+                     shortcuts ? d_qsame : nullptr);
       if (rc != PNEC_OK) return rc;
       BatchView sv = st.bv;
       sv.poses = nxt;
       rc = run_scf(h, sv, st.max_n, opts->ceres.regularization, opts->fibonacci_samples, opts->scf_steps,
-                   nxt + 4, 7, nullptr, stream);
+                   nxt + 4, 7, nullptr, stream, shortcuts ? d_cache : nullptr, shortcuts ? d_qsame : nullptr,
+                   shortcuts ? d_fixed : nullptr);
       if (rc != PNEC_OK) return rc;
       cur = nxt;
     }

@@ -431,6 +431,8 @@ struct EsLmArgs {
   int *out_info;           // [B] MINPACK info code, or nullptr
   int *out_nfev;           // [B] function evaluations (Eigen's accounting), or nullptr
   double *out_ev;          // [B] lambda_min of the reduced M at the result, or nullptr
+  const int *fixed;        // [B] or nullptr: pairs to pass through unchanged (fixed point reached)
+  int *q_same;             // [B] or nullptr: out, result quaternion == input quaternion bit for bit
   long long num_problems;
   double ftol, xtol, gtol, factor;
   int maxfev;
@@ -444,8 +446,10 @@ __global__ void __launch_bounds__(kEsLmThreads) es_lm_kernel(const __grid_consta
   __shared__ double s_mom[kEsMom * kEsLmThreads];
   const int tid = threadIdx.x;
   const long long b = static_cast<long long>(blockIdx.x) * kEsLmThreads + tid;
-  const bool active = b < args.num_problems;
-  const long long bb = active ? b : args.num_problems - 1;
+  const bool in_range = b < args.num_problems;
+  const long long bb = in_range ? b : args.num_problems - 1;
+  const bool passthrough = in_range && args.fixed && args.fixed[bb];
+  const bool active = in_range && !passthrough;
   // coalesced staging of this CTA's moments, transposed to [k][thread]
   {
     const long long first = static_cast<long long>(blockIdx.x) * kEsLmThreads;
@@ -625,11 +629,22 @@ __global__ void __launch_bounds__(kEsLmThreads) es_lm_kernel(const __grid_consta
       state = 4;
     }
   }
+  if (passthrough) {
+    double *po = args.poses_out + 7 * b;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) po[k] = pin[k];
+    if (args.q_same) args.q_same[b] = 1;
+  }
   if (active) {
     double *po = args.poses_out + 7 * b;
     const double sc = 1.0 / sqrt(1.0 + x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
     po[0] = x[0] * sc; po[1] = x[1] * sc; po[2] = x[2] * sc; po[3] = sc;
     po[4] = pin[4]; po[5] = pin[5]; po[6] = pin[6];
+    if (args.q_same)
+      args.q_same[b] = __double_as_longlong(po[0]) == __double_as_longlong(pin[0]) &&
+                       __double_as_longlong(po[1]) == __double_as_longlong(pin[1]) &&
+                       __double_as_longlong(po[2]) == __double_as_longlong(pin[2]) &&
+                       __double_as_longlong(po[3]) == __double_as_longlong(pin[3]);
     if (args.out_info) args.out_info[b] = info;
     if (args.out_nfev) args.out_nfev[b] = nfev;
     if (args.out_ev) {

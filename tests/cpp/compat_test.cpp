@@ -47,6 +47,31 @@ int main(int argc, char **argv) {
   print_pose("NECCeresSolver", c, pnec.LastStatus(), pnec.LastIterations());
   SE3 d = pnec.Solve(bvs1, bvs2, covs_t, init);
   print_pose("Solve", d, pnec.LastStatus(), pnec.LastIterations());
+  {
+    // the whole PNEC::Solve pipeline (pnec.cc:77-124) with the reference's defaults minus RANSAC
+    pnec::rel_pose_estimation::Options full;
+    full.use_ransac_ = false;
+    pnec::rel_pose_estimation::PNEC solver(full);
+    std::vector<int> inliers(3, 7);
+    SE3 r = solver.Solve(bvs1, bvs2, covs_t, init, inliers);
+    print_pose("SolveFull", r, solver.LastStatus(), (int)inliers.size());
+    print_pose("SolveFullES", solver.LastEigensolverPose(), 0, 0);
+    SE3 es = solver.Eigensolver(bvs1, bvs2, init, inliers);
+    print_pose("Eigensolver", es, 0, 0);
+    SE3 w = solver.WeightedEigensolver(bvs1, bvs2, covs_t, es);
+    print_pose("WeightedEigensolver", w, 0, 0);
+    full.use_nec_ = true;
+    pnec::rel_pose_estimation::PNEC nec(full);
+    print_pose("SolveNEC", nec.Solve(bvs1, bvs2, covs_t, init), nec.LastStatus(), nec.LastIterations());
+    bool threw = false;
+    try {
+      pnec::rel_pose_estimation::PNEC ransac((pnec::rel_pose_estimation::Options()));
+      ransac.Solve(bvs1, bvs2, covs_t, init);
+    } catch (const std::logic_error &) {
+      threw = true;
+    }
+    std::printf("RansacThrows %d\n", threw ? 1 : 0);
+  }
 
   // lower level: include/optimization/pnec_ceres.h:50-81
   pnec::optimization::PNECCeres opt;

@@ -481,6 +481,18 @@ def test_cpp_compat_api_matches_oracle(tmp_path):
     assert float(lines["CostFunction"][0]) == pytest.approx(
         oracle.cost_function(b.bvs_host, b.bvs_target, b.covs_target, p), rel=1e-10)
     assert lines["SolveDefaultOptions"] == ["throws"]
+    assert lines["RansacThrows"] == ["1"]
+    # the whole PNEC::Solve pipeline and its stages (pnec.cc:77-124, 273-348)
+    fref, fes = oracle.frame_solve_batch(b.bvs_host, b.bvs_target, b.covs_target, b.init_poses,
+                                         oracle.default_frame_opts(), n_per_problem=N)
+    nref, _ = oracle.frame_solve_batch(b.bvs_host, b.bvs_target, b.covs_target, b.init_poses,
+                                       oracle.default_frame_opts(use_nec=1), n_per_problem=N)
+    wref = oracle.weighted_eigensolver(b.bvs_host, b.bvs_target, b.covs_target, fes[0])
+    for tag, ref in (("SolveFull", fref[0]), ("SolveFullES", fes[0]), ("Eigensolver", fes[0]),
+                     ("WeightedEigensolver", wref), ("SolveNEC", nref[0])):
+        pose = np.array(lines[tag][:7], dtype=np.float64)
+        assert rotation_angle(pose, ref) <= ROT_TOL and direction_angle(pose[4:], ref[4:]) <= DIR_TOL, tag
+    assert lines["SolveFull"][8] == "0"  # inliers cleared, pnec.cc:277
     mu = b.bvs_target[1] * 800.0
     img = np.array([[0.7, 0.1, 0.0], [0.1, 0.4, 0.0], [0.0, 0.0, 0.0]])
     ut = oracle.unscented_transform(mu[None], img.T.reshape(1, 9), None, 1.0, oracle.PINHOLE)[0].reshape(3, 3).T
