@@ -82,6 +82,7 @@ struct pnec_handle {
   DevBuf d_ut_mu, d_ut_cov, d_ut_out, d_kp_bv, d_sphere, d_tr_out, d_tr_aux;
   DevBuf d_es_mom, d_es_w, d_es_info, d_es_ev, d_fr_es, d_fr_a, d_fr_b;  // eigensolver / frame pipeline
   DevBuf d_fr_cache, d_fr_flags;  // ScfScanCache[B]; int q_same[B], fixed[B]
+  DevBuf d_scf_defer;             // int count, cursor, pad[2], list[B]
   int sphere_samples = -1;
   std::mutex mu;
 };
@@ -479,11 +480,63 @@ int run_scf(pnec_handle *h, const BatchView &bv, long long max_n, double reg, in
   a.cache = cache;
   a.q_same = q_same;
   a.fixed = fixed;
-  auto kern = scf_kernel<4>;
+  a.dbg = nullptr;
+  static long long *dbg_buf = nullptr;
+  const bool debug = env_int("PNEC_B200_SCF_DEBUG", 0) != 0;
+  if (debug) {
+    if (!dbg_buf) cudaMalloc(&dbg_buf, sizeof(long long) * 4 * 1000000);
+    if (bv.num_problems <= 1000000) a.dbg = dbg_buf;
+  }
+  int nw = env_int("PNEC_B200_SCF_WARPS", 4);
+  if (nw != 1 && nw != 2 && nw != 8) nw = 4;
+  const int defer = env_int("PNEC_B200_SCF_DEFER", 48);  // survivors above which a pair goes to pass 2; 0 = one pass
+  int *d_defer = nullptr;
+  if (defer > 0) {
+    PNEC_CUDA(h->d_scf_defer.ensure(sizeof(int) * (4 + static_cast<size_t>(bv.num_problems))));
+    d_defer = static_cast<int *>(h->d_scf_defer.p);
+    PNEC_CUDA(cudaMemsetAsync(d_defer, 0, sizeof(int) * 4, stream));
+    a.defer_count = d_defer;
+    a.defer_list = d_defer + 4;
+    a.defer_threshold = defer;
+  }
+  void (*kern)(ScfArgs) = nw == 1 ? scf_kernel<1> : nw == 2 ? scf_kernel<2> : nw == 8 ? scf_kernel<8> : scf_kernel<4>;
   PNEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
-  kern<<<static_cast<unsigned>(bv.num_problems), 128, dyn, stream>>>(a);
+  kern<<<static_cast<unsigned>(bv.num_problems), nw * 32, dyn, stream>>>(a);
   PNEC_CUDA(cudaGetLastError());
   h->launches++;
+  if (defer > 0) {
+    ScfArgs a2 = a;
+    a2.defer_list = nullptr;
+    a2.defer_count = nullptr;
+    a2.work_list = d_defer + 4;
+    a2.work_count = d_defer;
+    a2.work_cursor = d_defer + 1;
+    auto kern2 = scf_list_kernel<16>;
+    PNEC_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
+    const unsigned grid2 = static_cast<unsigned>(std::min<long long>(bv.num_problems, 2LL * h->sm_count));
+    kern2<<<grid2, 16 * 32, dyn, stream>>>(a2);
+    PNEC_CUDA(cudaGetLastError());
+    h->launches++;
+  }
+  if (a.dbg) {  // debug only: synchronises
+    cudaStreamSynchronize(stream);
+    const long long B = bv.num_problems;
+    std::vector<long long> hb(4 * B);
+    cudaMemcpy(hb.data(), a.dbg, sizeof(long long) * 4 * B, cudaMemcpyDeviceToHost);
+    long long cnt[3] = {0, 0, 0}, surv = 0, max_surv = 0, max_cyc = 0, over64 = 0;
+    double cyc[3] = {0, 0, 0}, scan_cyc = 0;
+    for (long long b = 0; b < B; ++b) {
+      const int path = static_cast<int>(hb[4 * b]);
+      cnt[path]++;
+      cyc[path] += hb[4 * b + 3];
+      if (path == 2) { surv += hb[4 * b + 1]; scan_cyc += hb[4 * b + 2]; if (hb[4 * b + 1] > 64) over64++; }
+      max_surv = std::max(max_surv, hb[4 * b + 1]);
+      max_cyc = std::max(max_cyc, hb[4 * b + 3]);
+    }
+    std::fprintf(stderr, "[scf] fixed %lld | reused %lld (mean %.0f cyc) | scanned %lld (mean %.0f cyc, scan part %.0f, mean survivors %.1f, max %lld, >64: %lld) | max CTA %lld cyc\n",
+                 cnt[0], cnt[1], cnt[1] ? cyc[1] / cnt[1] : 0.0, cnt[2], cnt[2] ? cyc[2] / cnt[2] : 0.0,
+                 cnt[2] ? scan_cyc / cnt[2] : 0.0, cnt[2] ? double(surv) / cnt[2] : 0.0, max_surv, over64, max_cyc);
+  }
   return PNEC_OK;
 }
 
@@ -609,7 +662,7 @@ void pnec_destroy(pnec_handle *h) {
                     &h->d_out_init, &h->d_out_grad, &h->d_out_jtj, &h->d_ut_mu, &h->d_ut_cov,
                     &h->d_ut_out, &h->d_kp_bv, &h->d_sphere, &h->d_tr_out,
                     &h->d_tr_aux, &h->d_es_mom, &h->d_es_w, &h->d_es_info, &h->d_es_ev,
-                    &h->d_fr_es, &h->d_fr_a, &h->d_fr_b, &h->d_fr_cache, &h->d_fr_flags};
+                    &h->d_fr_es, &h->d_fr_a, &h->d_fr_b, &h->d_fr_cache, &h->d_fr_flags, &h->d_scf_defer};
   for (DevBuf *b : bufs) b->release();
   delete h;
 }

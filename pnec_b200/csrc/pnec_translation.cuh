@@ -62,6 +62,86 @@ __device__ __forceinline__ void sym3_smallest_eigvec(const double m[6], double v
   v[0] = x * inv; v[1] = y * inv; v[2] = z * inv;
 }
 
+// The same eigenvector without the rotation sweeps, for the SCF loop where one lane solves ten
+// eigenproblems in a row while its CTA waits: smallest eigenvalue from the trigonometric closed
+// form of the characteristic cubic, eigenvector as the largest cross product of two rows of
+// (A - lambda I), then one Rayleigh-quotient refinement (the closed form is only accurate to
+// eps * |A|; the Rayleigh quotient of the first vector is accurate to second order).  Accuracy of
+// the direction: eps * |A| / (lambda_2 - lambda_1), the same conditioning as any method.  Falls back
+// to the Jacobi routine when the matrix is (numerically) of rank <= 1 or not finite.
+__device__ __forceinline__ void sym3_null_vector(const double m[6], double lam, double v[3], double &nrm2) {
+  const double r0[3] = {m[0] - lam, m[1], m[2]};
+  const double r1[3] = {m[1], m[3] - lam, m[4]};
+  const double r2[3] = {m[2], m[4], m[5] - lam};
+  double c01[3], c02[3], c12[3];
+  cross3(r0, r1, c01);
+  cross3(r0, r2, c02);
+  cross3(r1, r2, c12);
+  const double n01 = dot3(c01, c01), n02 = dot3(c02, c02), n12 = dot3(c12, c12);
+  nrm2 = n01;
+  v[0] = c01[0]; v[1] = c01[1]; v[2] = c01[2];
+  if (n02 > nrm2) { nrm2 = n02; v[0] = c02[0]; v[1] = c02[1]; v[2] = c02[2]; }
+  if (n12 > nrm2) { nrm2 = n12; v[0] = c12[0]; v[1] = c12[1]; v[2] = c12[2]; }
+}
+
+__device__ __noinline__ void sym3_smallest_eigvec_jacobi(const double m[6], double v[3], double &lambda) {
+  sym3_smallest_eigvec(m, v, lambda);
+}
+
+__device__ __forceinline__ void sym3_smallest_eigvec_fast(const double m_in[6], double v[3], double &lambda) {
+  // scale to unit size: the closed form cubes the entries
+  double big = fmax(fmax(fabs(m_in[0]), fabs(m_in[3])), fabs(m_in[5]));
+  big = fmax(big, fmax(fmax(fabs(m_in[1]), fabs(m_in[2])), fabs(m_in[4])));
+  if (!(big > 0.0) || !(big < CUDART_INF)) { sym3_smallest_eigvec_jacobi(m_in, v, lambda); return; }
+  const double inv_big = fast_rcp(big);
+  double m[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) m[k] = m_in[k] * inv_big;
+  const double q = (m[0] + m[3] + m[5]) * (1.0 / 3.0);
+  const double p1 = m[1] * m[1] + m[2] * m[2] + m[4] * m[4];
+  const double d0 = m[0] - q, d1 = m[3] - q, d2 = m[5] - q;
+  const double p2 = d0 * d0 + d1 * d1 + d2 * d2 + 2.0 * p1;
+  double lam = q;
+  if (p2 > 0.0) {
+    const double ip = rsqrt(p2 * (1.0 / 6.0));  // 1 / p
+    const double b0 = d0 * ip, b3 = d1 * ip, b5 = d2 * ip, b1 = m[1] * ip, b2 = m[2] * ip, b4 = m[4] * ip;
+    const double det = b0 * (b3 * b5 - b4 * b4) - b1 * (b1 * b5 - b4 * b2) + b2 * (b1 * b4 - b3 * b2);
+    const double r = fmin(1.0, fmax(-1.0, 0.5 * det));
+    // r -> 1: the two smallest eigenvalues approach each other (the translation is then
+    // ill-determined, e.g. near-pure rotation) and the smallest root of the cubic below becomes a
+    // double root: rotation sweeps instead
+    if (1.0 - r < 1e-4) { sym3_smallest_eigvec_jacobi(m_in, v, lambda); return; }
+    // eigenvalues of (A - q I) / p are 2 y with 4 y^3 - 3 y = r (y = cos of the trigonometric
+    // form); the smallest one lies in [-1, -1/2], where the cubic is increasing and concave, so
+    // Newton from y = -1 climbs to it monotonically.
+    double y = -1.0;
+#pragma unroll 1
+    for (int it = 0; it < 64; ++it) {
+      const double f = fma(fma(4.0 * y, y, -3.0), y, -r);
+      const double fp = fma(12.0 * y, y, -3.0);
+      const double dy = f * fast_rcp(fp);
+      y -= dy;
+      if (fabs(dy) <= 4e-16) break;
+    }
+    lam = fma(2.0 * y, p2 * (1.0 / 6.0) * ip, q);  // q + 2 p y, p = p2/6 * (1/p)
+  }
+  double u[3], n2;
+  sym3_null_vector(m, lam, u, n2);
+  if (!(n2 > 1e-60)) { sym3_smallest_eigvec_jacobi(m_in, v, lambda); return; }
+  // Rayleigh quotient of u, then the null vector again
+  double Au[3];
+  sym_mul6(m, u, Au);
+  const double rq = dot3(u, Au) * fast_rcp(n2);
+  double w[3], n2b;
+  sym3_null_vector(m, rq, w, n2b);
+  if (!(n2b > 1e-60)) { w[0] = u[0]; w[1] = u[1]; w[2] = u[2]; n2b = n2; }
+  const double inv = rsqrt(n2b);
+  v[0] = w[0] * inv; v[1] = w[1] * inv; v[2] = w[2] * inv;
+  double Av[3];
+  sym_mul6(m, v, Av);
+  lambda = dot3(v, Av) * big;
+}
+
 // Rotation matrix (row-major) of the normalised stored quaternion: Sophus::SE3d::rotationMatrix().
 __device__ __forceinline__ void pose_rotation(const double *pose7, double R[9]) {
   const double qn = sqrt(pose7[0] * pose7[0] + pose7[1] * pose7[1] + pose7[2] * pose7[2] + pose7[3] * pose7[3]);
@@ -94,16 +174,21 @@ __device__ __forceinline__ void block_sum6(double v[6], double (*s_red)[6], int 
   __syncthreads();
 }
 
-// What a full scan of the sphere found for one frame pair, keyed by the rotation it was made with.
+// What a scan of the sphere established for one frame pair, keyed by the rotation it was made with.
 // The sphere costs depend on the rotation and the data only, so a later call with the bit-identical
-// quaternion (the weighted-eigensolver iterations of PNEC::WeightedEigensolver converge to one
-// within 1-3 rounds) can reuse them: the result is exactly what rescanning would give.
+// quaternion (the weighted-eigensolver rounds of PNEC::WeightedEigensolver converge to one within
+// 1-3 rounds) can reuse it: the outcome is exactly what rescanning would give.
+//   idx > 0:  the sphere minimum is `value`, first reached at sphere point idx (1-based)
+//   idx == 0: every sphere point costs at least `value` (all were pruned against it)
 struct ScfScanCache {
   double q[4];
-  double best_cost;
-  int best_idx;  // 1-based sphere index
+  double value;
+  int idx;
   int valid;
 };
+
+constexpr int kScfPrefix = 32;      // correspondences every sphere candidate is summed over before pruning
+constexpr int kScfMaxSurvivors = 512;
 
 struct ScfArgs {
   BatchView bv;           // poses: rotation quaternion + start translation
@@ -118,6 +203,18 @@ struct ScfArgs {
   const int *q_same;      // [B] or nullptr: this call's rotation equals the previous round's bit for bit
   int *fixed;             // [B] or nullptr: in: pair already at a fixed point of the iteration (skip);
                           //     out: set when q_same and the translation did not move either
+  // Two passes: the first (4 warps per pair) hands pairs whose scan cannot prune (flat cost
+  // landscape, e.g. near-pure rotation: hundreds of survivors) to a list; the second runs that list
+  // with 16 warps per pair on a few persistent CTAs, so that one such pair no longer sets the
+  // duration of the whole launch.
+  int *defer_list;        // pass 1: [B] pairs handed to pass 2, or nullptr (no deferral)
+  int *defer_count;       // pass 1: number of entries of defer_list
+  int defer_threshold;    // pass 1: survivors above which a pair is deferred
+  const int *work_list;   // pass 2: pairs to process (CTAs take entries through work_cursor), else nullptr
+  const int *work_count;
+  int *work_cursor;
+  long long *dbg;         // [B][4] or nullptr: path (0 fixed, 1 scan reused, 2 scanned), survivors,
+                          //     cycles of the scan, cycles of the whole CTA (PNEC_B200_SCF_DEBUG)
 };
 
 // per correspondence: n = f1 x R f2 and sym(B), B = [f1]x R S R^T [f1]x^T + reg I
@@ -165,22 +262,51 @@ __device__ __forceinline__ double scf_objective(const double *terms, int n, cons
   return cost;
 }
 
+// The rest of a candidate's sum, correspondences [begin, n): by one lane in index order
+// (`warp_parallel` false) or by the 32 lanes of a warp, lane-strided and tree-reduced in a fixed
+// order (every lane gets the sum).
+__device__ __forceinline__ double scf_objective_tail(const double *terms, int begin, int n, const double t[3],
+                                                     int lane, bool warp_parallel) {
+  const double txx = t[0] * t[0], txy = 2.0 * t[0] * t[1], txz = 2.0 * t[0] * t[2];
+  const double tyy = t[1] * t[1], tyz = 2.0 * t[1] * t[2], tzz = t[2] * t[2];
+  double cost = 0.0;
+  const int first = warp_parallel ? begin + lane : begin, step = warp_parallel ? 32 : 1;
+  for (int i = first; i < n; i += step) {
+    const double *w = terms + 9 * i;
+    const double e = t[0] * w[0] + t[1] * w[1] + t[2] * w[2];
+    const double den = w[3] * txx + w[4] * txy + w[5] * txz + w[6] * tyy + w[7] * tyz + w[8] * tzz;
+    cost = fma(e * e, fast_rcp(den), cost);
+  }
+  if (warp_parallel) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
+  }
+  return cost;
+}
+
 template <int NW>
-__global__ void __launch_bounds__(NW * 32) scf_kernel(const __grid_constant__ ScfArgs args) {
+__device__ __forceinline__ void scf_pair(const ScfArgs &args, const long long b) {
   constexpr int NT = NW * 32;
   __shared__ double s_red[NW][6];
   __shared__ double s_best_cost[NW];
   __shared__ int s_best_idx[NW];
   __shared__ double s_t[3];
+  __shared__ unsigned long long s_bound;  // bits of the running upper bound (costs are >= 0: ordered as integers)
+  __shared__ int s_nsurv;
+  __shared__ int s_surv_idx[kScfMaxSurvivors];
+  __shared__ double s_surv_part[kScfMaxSurvivors];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long b = blockIdx.x;
   long long s, e;
   problem_range(args.bv, b, s, e);
   const int n = static_cast<int>(e - s);
   const double *pose = args.bv.poses + 7 * b;
   double *terms = dyn_smem;  // [n][9]
   double *ot = args.out_t + static_cast<long long>(args.out_stride) * b;
-  if (args.fixed && args.fixed[b]) return;  // fixed point of the iteration: the result is already in place
+  const long long clk0 = clock64();
+  if (args.fixed && args.fixed[b]) {  // fixed point of the iteration: the result is already in place
+    if (args.dbg && tid == 0) { args.dbg[4 * b] = 0; args.dbg[4 * b + 1] = 0; args.dbg[4 * b + 2] = 0; args.dbg[4 * b + 3] = 0; }
+    return;
+  }
   if (n <= 0 || n > args.cap_elems) {
     // nothing to minimise (or a pair beyond the shared-memory capacity, rejected on the host)
     if (tid == 0) { ot[0] = pose[4]; ot[1] = pose[5]; ot[2] = pose[6]; if (args.out_cost) args.out_cost[b] = 0.0; }
@@ -201,9 +327,17 @@ __global__ void __launch_bounds__(NW * 32) scf_kernel(const __grid_constant__ Sc
   __syncthreads();
 
   // ---- scan: candidate 0 is the given translation, 1..samples the Fibonacci sphere; the first
-  // strict minimum wins (pnec.cc:332-340).  Candidate 0 is summed by the whole CTA; the sphere
-  // candidates are summed one per thread in index order, or taken from the cache when this exact
-  // rotation was scanned before.
+  // strict minimum wins (pnec.cc:332-340).
+  //
+  // Every term (t.n_i)^2 / (t^T B_i t) is non-negative (B_i is positive definite: reg > 0), so a
+  // partial sum is a lower bound of a candidate's cost and a candidate whose partial sum already
+  // EXCEEDS the cost of a fully evaluated one can never be the minimum: branch and bound, exact.
+  //   0. cost0 = cost of the given translation (whole CTA), the first bound;
+  //   1. every sphere candidate is summed over the first kScfPrefix correspondences; those not
+  //      above cost0 survive (typically none or a handful: the sphere is 0.16 rad coarse);
+  //   2. survivors are completed one per warp, tightening the bound as they finish.
+  // The set of completed candidates depends on timing, the minimum and its index do not: pruning
+  // is strict (ties are always evaluated) and every bound is the complete cost of a real candidate.
   const double t0[3] = {pose[4], pose[5], pose[6]};
   double cost0;
   {
@@ -219,29 +353,102 @@ __global__ void __launch_bounds__(NW * 32) scf_kernel(const __grid_constant__ Sc
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
     if (lane == 0) s_best_cost[warp] = part;
+    if (tid == 0) s_nsurv = 0;
     __syncthreads();
     cost0 = 0.0;
 #pragma unroll
     for (int w = 0; w < NW; ++w) cost0 += s_best_cost[w];
     __syncthreads();
   }
-  bool reuse = false;
-  double best = CUDART_INF;
-  int best_idx = 0x7fffffff;
+  // what is known about the sphere: minimum `sph_value` at point `sph_idx` (> 0), or only the lower
+  // bound `sph_value` (sph_idx == 0)
+  double sph_value = CUDART_INF;
+  int sph_idx = 0;
+  bool rescan = true;
   if (args.cache) {
     const ScfScanCache &c = args.cache[b];
-    reuse = c.valid && __double_as_longlong(c.q[0]) == __double_as_longlong(pose[0]) &&
-            __double_as_longlong(c.q[1]) == __double_as_longlong(pose[1]) &&
-            __double_as_longlong(c.q[2]) == __double_as_longlong(pose[2]) &&
-            __double_as_longlong(c.q[3]) == __double_as_longlong(pose[3]);
-    if (reuse) { best = c.best_cost; best_idx = c.best_idx; }
+    const bool same = c.valid && __double_as_longlong(c.q[0]) == __double_as_longlong(pose[0]) &&
+                      __double_as_longlong(c.q[1]) == __double_as_longlong(pose[1]) &&
+                      __double_as_longlong(c.q[2]) == __double_as_longlong(pose[2]) &&
+                      __double_as_longlong(c.q[3]) == __double_as_longlong(pose[3]);
+    // a lower bound only settles the comparison when it is not below the new cost0
+    if (same && (c.idx > 0 || c.value >= cost0)) {
+      rescan = false;
+      sph_value = c.value;
+      sph_idx = c.idx;
+    }
   }
-  if (!reuse) {  // block-uniform
+  if (rescan) {  // block-uniform
+    const bool prune = cost0 >= 0.0 && cost0 < CUDART_INF && args.reg > 0.0 && n > kScfPrefix;
+    const int npre = prune ? kScfPrefix : n;
+    if (tid == 0) s_bound = static_cast<unsigned long long>(__double_as_longlong(prune ? cost0 : CUDART_INF));
+    double best = CUDART_INF;  // complete costs seen by this thread / warp
+    int best_idx = 0x7fffffff;
     for (int c = 1 + tid; c <= args.samples; c += NT) {
       const double t[3] = {args.sphere[3 * (c - 1)], args.sphere[3 * (c - 1) + 1], args.sphere[3 * (c - 1) + 2]};
-      const double cost = scf_objective(terms, n, t);
-      if (cost < best || (cost == best && c < best_idx)) { best = cost; best_idx = c; }
+      const double part = scf_objective(terms, npre, t);
+      if (npre == n) {
+        if (part < best || (part == best && c < best_idx)) { best = part; best_idx = c; }
+      } else if (!(part > cost0)) {
+        const int slot = atomicAdd(&s_nsurv, 1);
+        if (slot < kScfMaxSurvivors) { s_surv_idx[slot] = c; s_surv_part[slot] = part; }
+      }
     }
+    __syncthreads();
+    const int nsurv = s_nsurv;
+    if (args.defer_list && nsurv > args.defer_threshold) {  // block-uniform: nothing has been written yet
+      if (tid == 0) args.defer_list[atomicAdd(args.defer_count, 1)] = static_cast<int>(b);
+      return;
+    }
+    if (nsurv > kScfMaxSurvivors) {
+      // more survivors than the list holds (a poor start translation): plain scan of the rest
+      if (tid == 0) s_bound = static_cast<unsigned long long>(__double_as_longlong(CUDART_INF));
+      best = CUDART_INF; best_idx = 0x7fffffff;
+      for (int c = 1 + tid; c <= args.samples; c += NT) {
+        const double t[3] = {args.sphere[3 * (c - 1)], args.sphere[3 * (c - 1) + 1], args.sphere[3 * (c - 1) + 2]};
+        const double cost = scf_objective(terms, npre, t) + scf_objective_tail(terms, npre, n, t, lane, false);
+        if (cost < best || (cost == best && c < best_idx)) { best = cost; best_idx = c; }
+      }
+    } else {
+      for (int sv = warp; sv < nsurv; sv += NW) {  // warp-uniform
+        const int c = s_surv_idx[sv];
+        const double part = s_surv_part[sv];
+        unsigned long long bits = 0;
+        if (lane == 0) bits = *reinterpret_cast<volatile unsigned long long *>(&s_bound);
+        bits = __shfl_sync(0xffffffffu, bits, 0);  // one read per warp: the decision is warp-uniform
+        if (part > __longlong_as_double(static_cast<long long>(bits))) continue;
+        const double t[3] = {args.sphere[3 * (c - 1)], args.sphere[3 * (c - 1) + 1], args.sphere[3 * (c - 1) + 2]};
+        // the rest of the sum by the whole warp, 64 correspondences at a time, re-checking the
+        // bound after every chunk: cost = part + chunk sums in order (fixed, timing-independent)
+        const double txx = t[0] * t[0], txy = 2.0 * t[0] * t[1], txz = 2.0 * t[0] * t[2];
+        const double tyy = t[1] * t[1], tyz = 2.0 * t[1] * t[2], tzz = t[2] * t[2];
+        double cost = part;
+        bool alive = true;
+        for (int base = npre; base < n; base += 64) {
+          double chunk = 0.0;
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int i = base + 32 * k + lane;
+            if (i < n) {
+              const double *w = terms + 9 * i;
+              const double e = t[0] * w[0] + t[1] * w[1] + t[2] * w[2];
+              const double den = w[3] * txx + w[4] * txy + w[5] * txz + w[6] * tyy + w[7] * tyz + w[8] * tzz;
+              chunk = fma(e * e, fast_rcp(den), chunk);
+            }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) chunk += __shfl_xor_sync(0xffffffffu, chunk, o);
+          cost += chunk;
+          if (lane == 0) bits = *reinterpret_cast<volatile unsigned long long *>(&s_bound);
+          bits = __shfl_sync(0xffffffffu, bits, 0);
+          if (cost > __longlong_as_double(static_cast<long long>(bits))) { alive = false; break; }
+        }
+        if (!alive) continue;
+        if (cost < best || (cost == best && c < best_idx)) { best = cost; best_idx = c; }
+        if (lane == 0) atomicMin(&s_bound, static_cast<unsigned long long>(__double_as_longlong(cost)));
+      }
+    }
+    // every lane of a warp holds the same (best, best_idx) in the survivor path, its own in the others
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const double oc = __shfl_xor_sync(0xffffffffu, best, o);
@@ -250,21 +457,26 @@ __global__ void __launch_bounds__(NW * 32) scf_kernel(const __grid_constant__ Sc
     }
     if (lane == 0) { s_best_cost[warp] = best; s_best_idx[warp] = best_idx; }
     __syncthreads();
-    if (tid == 0) {
-      for (int w = 1; w < NW; ++w)
-        if (s_best_cost[w] < best || (s_best_cost[w] == best && s_best_idx[w] < best_idx)) {
-          best = s_best_cost[w]; best_idx = s_best_idx[w];
-        }
-      if (args.cache) {
-        ScfScanCache &c = args.cache[b];
-        c.q[0] = pose[0]; c.q[1] = pose[1]; c.q[2] = pose[2]; c.q[3] = pose[3];
-        c.best_cost = best; c.best_idx = best_idx; c.valid = 1;
+#pragma unroll
+    for (int w = 0; w < NW; ++w)
+      if (w != warp && (s_best_cost[w] < best || (s_best_cost[w] == best && s_best_idx[w] < best_idx))) {
+        best = s_best_cost[w]; best_idx = s_best_idx[w];
       }
+    // pruned candidates cost more than min(cost0, best): `best` is the sphere minimum if it is below
+    // cost0, otherwise all that is known is that the sphere does not go below cost0
+    if (best_idx != 0x7fffffff && (best < cost0 || !prune)) { sph_value = best; sph_idx = best_idx; }
+    else { sph_value = cost0; sph_idx = 0; }
+    if (tid == 0 && args.cache) {
+      ScfScanCache &c = args.cache[b];
+      c.q[0] = pose[0]; c.q[1] = pose[1]; c.q[2] = pose[2]; c.q[3] = pose[3];
+      c.value = sph_value; c.idx = sph_idx; c.valid = 1;
     }
   }
+  const long long clk1 = clock64();
+  const int dbg_nsurv = rescan ? s_nsurv : 0;
   if (tid == 0) {
-    if (best_idx != 0x7fffffff && best < cost0) {
-      s_t[0] = args.sphere[3 * (best_idx - 1)]; s_t[1] = args.sphere[3 * (best_idx - 1) + 1]; s_t[2] = args.sphere[3 * (best_idx - 1) + 2];
+    if (sph_idx > 0 && sph_value < cost0) {
+      s_t[0] = args.sphere[3 * (sph_idx - 1)]; s_t[1] = args.sphere[3 * (sph_idx - 1) + 1]; s_t[2] = args.sphere[3 * (sph_idx - 1) + 2];
     } else {
       s_t[0] = t0[0]; s_t[1] = t0[1]; s_t[2] = t0[2];
     }
@@ -272,26 +484,74 @@ __global__ void __launch_bounds__(NW * 32) scf_kernel(const __grid_constant__ Sc
   __syncthreads();
 
   // ---- SCF: t <- eigenvector of the smallest eigenvalue of E(t) = sum_i A_i / (t^T B_i t)
-  // (alt_construct_E with frac[i] == 0, scf.cc:109-126: `frac.resize(n)` then push_back)
-  for (int it = 0; it < args.steps; ++it) {
-    const double t[3] = {s_t[0], s_t[1], s_t[2]};
-    const double txx = t[0] * t[0], txy = 2.0 * t[0] * t[1], txz = 2.0 * t[0] * t[2];
-    const double tyy = t[1] * t[1], tyz = 2.0 * t[1] * t[2], tzz = t[2] * t[2];
-    double E[6] = {0, 0, 0, 0, 0, 0};
-    for (int i = tid; i < n; i += NT) {
-      const double *w = terms + 9 * i;
-      const double den = w[3] * txx + w[4] * txy + w[5] * txz + w[6] * tyy + w[7] * tyz + w[8] * tzz;
-      const double inv = fast_rcp(den);
-      E[0] = fma(w[0] * w[0], inv, E[0]); E[1] = fma(w[0] * w[1], inv, E[1]); E[2] = fma(w[0] * w[2], inv, E[2]);
-      E[3] = fma(w[1] * w[1], inv, E[3]); E[4] = fma(w[1] * w[2], inv, E[4]); E[5] = fma(w[2] * w[2], inv, E[5]);
+  // (alt_construct_E with frac[i] == 0, scf.cc:109-126: `frac.resize(n)` then push_back).
+  // E is even in t and the step is a deterministic map, so once a step returns +-(its input) every
+  // later step returns the same vector, and once it returns +-(the input of the step before) the
+  // sequence alternates between two vectors: the loop stops there with exactly the vector the
+  // remaining steps would have produced.
+  {
+    double prev[3] = {0, 0, 0};  // input of the previous step (tid 0)
+    bool have_prev = false;
+    for (int it = 0; it < args.steps; ++it) {
+      const double t[3] = {s_t[0], s_t[1], s_t[2]};
+      const double txx = t[0] * t[0], txy = 2.0 * t[0] * t[1], txz = 2.0 * t[0] * t[2];
+      const double tyy = t[1] * t[1], tyz = 2.0 * t[1] * t[2], tzz = t[2] * t[2];
+      double E[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int i = tid; i < n; i += NT) {
+        const double *w = terms + 9 * i;
+        const double den = w[3] * txx + w[4] * txy + w[5] * txz + w[6] * tyy + w[7] * tyz + w[8] * tzz;
+        const double inv = fast_rcp(den);
+        E[0] = fma(w[0] * w[0], inv, E[0]); E[1] = fma(w[0] * w[1], inv, E[1]); E[2] = fma(w[0] * w[2], inv, E[2]);
+        E[3] = fma(w[1] * w[1], inv, E[3]); E[4] = fma(w[1] * w[2], inv, E[4]); E[5] = fma(w[2] * w[2], inv, E[5]);
+      }
+      // transposing warp reduction: lane L ends with the warp sum of E[4 b4 + 2 b3 + b2]
+      exchange_step<8, 16>(E, lane);
+      exchange_step<4, 8>(E, lane);
+      exchange_step<2, 4>(E, lane);
+      double sum = E[0];
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      const int eidx = 4 * ((lane >> 4) & 1) + 2 * ((lane >> 3) & 1) + ((lane >> 2) & 1);
+      if ((lane & 3) == 0 && eidx < 6) s_red[warp][eidx] = sum;
+      __syncthreads();
+      if (tid == 0) {
+        double Es[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          double a = 0.0;
+#pragma unroll
+          for (int w = 0; w < NW; ++w) a += s_red[w][k];
+          Es[k] = a;
+        }
+        double v[3], lam;
+        sym3_smallest_eigvec_fast(Es, v, lam);
+        auto same_up_to_sign = [](const double a[3], const double c[3]) {
+          const bool p = __double_as_longlong(a[0]) == __double_as_longlong(c[0]) &&
+                         __double_as_longlong(a[1]) == __double_as_longlong(c[1]) &&
+                         __double_as_longlong(a[2]) == __double_as_longlong(c[2]);
+          const bool m = __double_as_longlong(a[0]) == __double_as_longlong(-c[0]) &&
+                         __double_as_longlong(a[1]) == __double_as_longlong(-c[1]) &&
+                         __double_as_longlong(a[2]) == __double_as_longlong(-c[2]);
+          return p || m;
+        };
+        int stop = 0;
+        const int remaining = args.steps - 1 - it;
+        if (same_up_to_sign(v, t)) {
+          stop = 1;  // fixed point: every further step returns v
+        } else if (have_prev && same_up_to_sign(v, prev)) {
+          stop = 1;  // period two: v, t', v, t', ... with t' = step(v) = the current input's successor
+          if (remaining & 1) { v[0] = t[0]; v[1] = t[1]; v[2] = t[2]; }
+        }
+        // the successor of +-prev is t (as computed one step ago), so an odd number of remaining
+        // steps ends on t and an even number on v
+        prev[0] = t[0]; prev[1] = t[1]; prev[2] = t[2];
+        have_prev = true;
+        s_t[0] = v[0]; s_t[1] = v[1]; s_t[2] = v[2];
+        s_nsurv = stop;  // reuse as the stop flag (the scan is over)
+      }
+      __syncthreads();
+      if (s_nsurv) break;
     }
-    block_sum6<NW>(E, s_red, warp, lane);
-    if (tid == 0) {
-      double v[3], lam;
-      sym3_smallest_eigvec(E, v, lam);
-      s_t[0] = v[0]; s_t[1] = v[1]; s_t[2] = v[2];
-    }
-    __syncthreads();
   }
   if (tid == 0) {
     if (args.fixed && args.q_same && args.q_same[b] &&
@@ -299,11 +559,37 @@ __global__ void __launch_bounds__(NW * 32) scf_kernel(const __grid_constant__ Sc
         __double_as_longlong(s_t[1]) == __double_as_longlong(t0[1]) &&
         __double_as_longlong(s_t[2]) == __double_as_longlong(t0[2]))
       args.fixed[b] = 1;  // (rotation, translation) -> itself: every further round repeats it
+    if (args.dbg) {
+      args.dbg[4 * b] = rescan ? 2 : 1;
+      args.dbg[4 * b + 1] = dbg_nsurv;
+      args.dbg[4 * b + 2] = clk1 - clk0;
+      args.dbg[4 * b + 3] = clock64() - clk0;
+    }
     ot[0] = s_t[0]; ot[1] = s_t[1]; ot[2] = s_t[2];
     if (args.out_cost) {
       const double t[3] = {s_t[0], s_t[1], s_t[2]};
       args.out_cost[b] = scf_objective(terms, n, t);
     }
+  }
+}
+
+template <int NW>
+__global__ void __launch_bounds__(NW * 32) scf_kernel(const __grid_constant__ ScfArgs args) {
+  scf_pair<NW>(args, blockIdx.x);
+}
+
+// pass 2: persistent CTAs over the deferred pairs
+template <int NW>
+__global__ void __launch_bounds__(NW * 32) scf_list_kernel(const __grid_constant__ ScfArgs args) {
+  __shared__ int s_work;
+  const int count = *args.work_count;
+  for (;;) {
+    __syncthreads();  // the previous pair is finished with the shared memory (and s_work)
+    if (threadIdx.x == 0) s_work = atomicAdd(args.work_cursor, 1);
+    __syncthreads();
+    const int k = s_work;
+    if (k >= count) return;
+    scf_pair<NW>(args, args.work_list[k]);
   }
 }
 
