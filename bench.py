@@ -16,6 +16,10 @@ step ends with the NCCL all-gather of the poses.  Prints ONE JSON line (rank 0).
   roofline   the fused residual+Jacobian+JtJ kernel (K1, pnec_eval_batch) timed live:
              algorithmic bytes B*N*120 / CUDA-event time vs the measured HBM peak
   cpu_baseline   the CPU oracle (port of the reference's Ceres path) on the host cores
+  frame_pipeline the whole frame-to-frame solve (PNEC::Solve without RANSAC: NEC eigensolver ->
+             9 weighted eigensolver + SCF rounds -> refinement, pnec_frame_solve_batch) on the
+             same workload, next to the oracle's restatement of it on the host cores (N = 1 only;
+             an extra object, the headline metric above is unchanged)
 
 --impl reference times the reference's CPU algorithm (the oracle port; the real Ceres
 stack cannot be built here) with all host threads on a bounded sample.
@@ -101,6 +105,19 @@ def cpu_oracle_rate(batch, n_problems, threads):
     t0 = time.perf_counter()
     oracle.solve_batch(batch.bvs_host[sl], batch.bvs_target[sl], batch.covs_target[sl], None,
                        batch.init_poses[:n_problems], o, n_per_problem=N, num_threads=threads)
+    return n_problems / (time.perf_counter() - t0)
+
+
+def cpu_frame_rate(batch, n_problems, threads):
+    """pairs/s of the oracle's PNEC::Solve restatement (oracle/pnec_oracle_frame.c)."""
+    import oracle
+
+    N = batch.n_per_problem
+    sl = slice(0, n_problems * N)
+    t0 = time.perf_counter()
+    oracle.frame_solve_batch(batch.bvs_host[sl], batch.bvs_target[sl], batch.covs_target[sl],
+                             batch.init_poses[:n_problems], oracle.default_frame_opts(), n_per_problem=N,
+                             num_threads=threads)
     return n_problems / (time.perf_counter() - t0)
 
 
@@ -325,6 +342,27 @@ def run_b200(args):
            "d2h_bytes_per_step": B * (56 + 4 + 4 + 8 + 8), "ms_per_step": 1e3 * dt / e2e_steps,
            "steps": e2e_steps, "host_buffers": "pinned"}
 
+    # ---- the whole frame solve (SURVEY.md section 8f rows 1-2 + the refinement), device resident
+    frame = None
+    if world == 1:
+        fopts = api.default_frame_opts()
+        fstep = lambda: h.frame_solve_batch(f1, f2, ct, init, fopts, n_per_problem=N)
+        for _ in range(3):
+            fstep()
+        torch.cuda.synchronize()
+        f_reps = 10
+        l0 = h.launch_count
+        e0.record()
+        for _ in range(f_reps):
+            fstep()
+        e1.record()
+        torch.cuda.synchronize()
+        f_ms = e0.elapsed_time(e1) / f_reps
+        frame = {"value": B / (f_ms * 1e-3), "unit": "frame pairs/s", "ms_per_step": f_ms,
+                 "gpu_launches_per_step": (h.launch_count - l0) // f_reps,
+                 "config": "PNEC::Solve, use_ransac_=false, weighted_iterations_=10, use_ceres_=true "
+                           "(pnec_frame_solve_batch) on the C2 batch, inputs resident in HBM"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -354,6 +392,11 @@ def run_b200(args):
             "sample": f"first {sample} of the {B} C2 frame pairs, OpenMP over problems; "
                       f"1 thread: {rate_one:.1f} solves/s on the first {min(B, 512)}",
             "value_1core": rate_one}
+        fsample = min(B, 32 * threads)
+        frame["cpu_baseline"] = {"value": cpu_frame_rate(batch, fsample, threads), "unit": "frame pairs/s",
+                                 "cores": threads, "kind": "port",
+                                 "sample": f"first {fsample} of the {B} C2 frame pairs, OpenMP over pairs"}
+        line["frame_pipeline"] = frame
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -583,7 +583,7 @@ int run_es_lm(pnec_handle *h, long long B, const double *d_mom, const double *d_
   a.gtol = 0.0;
   a.factor = 100.0;
   a.maxfev = 100;
-  const unsigned grid = static_cast<unsigned>((B + kEsLmThreads - 1) / kEsLmThreads);
+  const unsigned grid = static_cast<unsigned>((B + kEsLmPairs - 1) / kEsLmPairs);
   es_lm_kernel<<<grid, kEsLmThreads, 0, stream>>>(a);
   PNEC_CUDA(cudaGetLastError());
   h->launches++;

@@ -11,9 +11,10 @@
 // restated from its publication and public sources, see oracle/pnec_oracle_frame.c.
 //
 // The streaming part is one pass over f1, f2 (and the covariances for the weights); the
-// minimisation touches only the 36 moments of a frame pair, so it runs one THREAD per pair with
-// the moments in shared memory and a single call site for the function evaluation (a small state
-// machine) so that the lanes of a warp stay converged through the expensive part.
+// minimisation touches only the 36 moments of a frame pair, so it runs FOUR LANES per pair (M and
+// its three derivatives are assembled one per lane) with the moments in shared memory and a single
+// call site for the function evaluation (a small state machine), so that the lanes of a warp stay
+// converged through the expensive part.
 #pragma once
 
 #include "pnec_translation.cuh"
@@ -108,82 +109,98 @@ __device__ __forceinline__ void es_scatter(const double W[6], double M[6]) {
   if (UV == 5) { M[0] += W[3]; M[3] += W[0]; M[1] -= W[1]; }
 }
 
+// One of the six (u, v) terms: X_uv = A P + (A P)^T with P = G_uv R'^T, scattered into Y.
+// With A = R'/2 that is W_uv = R' G_uv R'^T (Y = M); with A = dR'/dc_k it is dW_uv/dc_k (Y = dM/dc_k).
 template <int UV>
 __device__ __forceinline__ void es_term(const double *mom, int stride, const double R[3][3],
-                                        const double dR[3][3][3], double M[6], double dM[3][6]) {
+                                        const double A[3][3], double Y[6]) {
   double G[6];
 #pragma unroll
   for (int q = 0; q < 6; ++q) G[q] = mom[(6 * UV + q) * stride];
   const double Gf[3][3] = {{G[0], G[1], G[2]}, {G[1], G[3], G[4]}, {G[2], G[4], G[5]}};
-  // P = G R'^T
   double P[3][3];
 #pragma unroll
   for (int r = 0; r < 3; ++r)
 #pragma unroll
     for (int sI = 0; sI < 3; ++sI) P[r][sI] = Gf[r][0] * R[sI][0] + Gf[r][1] * R[sI][1] + Gf[r][2] * R[sI][2];
-  // W = R' P (symmetric), dW_k = dR_k P + (dR_k P)^T
-  double W[6];
-  {
-    int k = 0;
+  double X[6];
+  int k = 0;
 #pragma unroll
-    for (int p = 0; p < 3; ++p)
+  for (int p = 0; p < 3; ++p)
 #pragma unroll
-      for (int sI = p; sI < 3; ++sI) W[k++] = R[p][0] * P[0][sI] + R[p][1] * P[1][sI] + R[p][2] * P[2][sI];
-  }
-  es_scatter<UV>(W, M);
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    double dW[6];
-    int k = 0;
-#pragma unroll
-    for (int p = 0; p < 3; ++p)
-#pragma unroll
-      for (int sI = p; sI < 3; ++sI)
-        dW[k++] = (dR[d][p][0] * P[0][sI] + dR[d][p][1] * P[1][sI] + dR[d][p][2] * P[2][sI]) +
-                  (dR[d][sI][0] * P[0][p] + dR[d][sI][1] * P[1][p] + dR[d][sI][2] * P[2][p]);
-    es_scatter<UV>(dW, dM[d]);
-  }
+    for (int sI = p; sI < 3; ++sI)
+      X[k++] = (A[p][0] * P[0][sI] + A[p][1] * P[1][sI] + A[p][2] * P[2][sI]) +
+               (A[sI][0] * P[0][p] + A[sI][1] * P[1][p] + A[sI][2] * P[2][p]);
+  es_scatter<UV>(X, Y);
 }
 
 // opengv eigensolver::getSmallestEVwithJacobian: closed-form smallest root of the characteristic
-// cubic of M(c) and its derivative with respect to the Cayley parameters.  `mom` points at this
-// problem's first moment; consecutive moments are `stride` doubles apart.
-__device__ __forceinline__ double es_smallest_ev(const double *mom, int stride, const double c[3], double grad[3]) {
+// cubic of M(c) and its derivative with respect to the Cayley parameters, computed by a GROUP OF
+// FOUR LANES (sub = lane & 3): lane 0 assembles M, lanes 1..3 one dM/dc_k each; M is broadcast and
+// every lane then differentiates the closed form along its own dM.  All four lanes return the same
+// ev and grad.  `mom` points at this pair's first moment; consecutive moments are `stride` apart.
+__device__ __forceinline__ double es_smallest_ev(const double *mom, int stride, const double c[3], int sub,
+                                                 double grad[3]) {
   const double x = c[0], y = c[1], z = c[2];
   // opengv::math::cayley2rot_reduced: (1 + |c|^2) * rotation
   const double R[3][3] = {{1 + x * x - y * y - z * z, 2 * (x * y - z), 2 * (x * z + y)},
                           {2 * (x * y + z), 1 - x * x + y * y - z * z, 2 * (y * z - x)},
                           {2 * (x * z - y), 2 * (y * z + x), 1 - x * x - y * y + z * z}};
-  const double dR[3][3][3] = {{{2 * x, 2 * y, 2 * z}, {2 * y, -2 * x, -2.0}, {2 * z, 2.0, -2 * x}},
-                              {{-2 * y, 2 * x, 2.0}, {2 * x, 2 * y, 2 * z}, {-2.0, 2 * z, -2 * y}},
-                              {{-2 * z, -2.0, 2 * x}, {2.0, -2 * z, 2 * y}, {2 * x, 2 * y, 2 * z}}};
-  double M[6] = {0, 0, 0, 0, 0, 0};
-  double dM[3][6] = {{0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}};
-  es_term<0>(mom, stride, R, dR, M, dM);
-  es_term<1>(mom, stride, R, dR, M, dM);
-  es_term<2>(mom, stride, R, dR, M, dM);
-  es_term<3>(mom, stride, R, dR, M, dM);
-  es_term<4>(mom, stride, R, dR, M, dM);
-  es_term<5>(mom, stride, R, dR, M, dM);
+  // A = R'/2 (sub 0) or dR'/dc_(sub-1), selected by value so that the four lanes stay converged
+  const double hx = sub == 1 ? 1.0 : 0.0, hy = sub == 2 ? 1.0 : 0.0, hz = sub == 3 ? 1.0 : 0.0, h0 = sub == 0 ? 0.5 : 0.0;
+  // dR'/dx = 2 [[x, y, z], [y, -x, -1], [z, 1, -x]], dR'/dy = 2 [[-y, x, 1], [x, y, z], [-1, z, -y]],
+  // dR'/dz = 2 [[-z, -1, x], [1, -z, y], [x, y, z]]
+  double A[3][3];
+  A[0][0] = h0 * R[0][0] + 2 * (hx * x - hy * y - hz * z);
+  A[0][1] = h0 * R[0][1] + 2 * (hx * y + hy * x - hz);
+  A[0][2] = h0 * R[0][2] + 2 * (hx * z + hy + hz * x);
+  A[1][0] = h0 * R[1][0] + 2 * (hx * y + hy * x + hz);
+  A[1][1] = h0 * R[1][1] + 2 * (-hx * x + hy * y - hz * z);
+  A[1][2] = h0 * R[1][2] + 2 * (-hx + hy * z + hz * y);
+  A[2][0] = h0 * R[2][0] + 2 * (hx * z - hy + hz * x);
+  A[2][1] = h0 * R[2][1] + 2 * (hx + hy * z + hz * y);
+  A[2][2] = h0 * R[2][2] + 2 * (-hx * x - hy * y + hz * z);
+  double Y[6] = {0, 0, 0, 0, 0, 0};
+  es_term<0>(mom, stride, R, A, Y);
+  es_term<1>(mom, stride, R, A, Y);
+  es_term<2>(mom, stride, R, A, Y);
+  es_term<3>(mom, stride, R, A, Y);
+  es_term<4>(mom, stride, R, A, Y);
+  es_term<5>(mom, stride, R, A, Y);
+  // M from lane 0 of the group; this lane's derivative direction J = Y (meaningless on lane 0)
+  double M[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) M[k] = __shfl_sync(0xffffffffu, Y[k], 0, 4);
   // M: 0 = 00, 1 = 01, 2 = 02, 3 = 11, 4 = 12, 5 = 22
   const double m00 = M[0], m01 = M[1], m02 = M[2], m11 = M[3], m12 = M[4], m22 = M[5];
   const double b = -m00 - m11 - m22;
   const double cc = -m02 * m02 - m12 * m12 - m01 * m01 + m00 * m11 + m00 * m22 + m11 * m22;
   const double d = m11 * m02 * m02 + m00 * m12 * m12 + m22 * m01 * m01 - m00 * m11 * m22 - 2 * m01 * m12 * m02;
   const double s = 2 * b * b * b - 9 * b * cc + 27 * d;
-  const double q = b * b - 3 * cc;         // t = 4 q^3, sqrt(t) = 2 q^(3/2), w = (sqrt(t)/2)^(1/3) = sqrt(q)
-  const double w = sqrt(q);
-  const double sqrt_t = 2.0 * q * w;
-  const double t = 4.0 * q * q * q;
-  const double ratio = s / sqrt_t;
-  const double alpha = acos(ratio);
-  double sb, cb;
-  sincos(alpha / 3.0, &sb, &cb);
-  const double ev = (-b - 2.0 * (w * cb)) / 3.0;
-  const double inv_sin_alpha = -1.0 / sqrt(1.0 - (s * s) / t);
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const double j00 = dM[k][0], j01 = dM[k][1], j02 = dM[k][2], j11 = dM[k][3], j12 = dM[k][4], j22 = dM[k][5];
+  // t = 4 q^3, sqrt(t) = 2 q^(3/2), w = (sqrt(t)/2)^(1/3) = sqrt(q); everything below is opengv's chain
+  // rule with the divisions turned into reciprocals
+  const double q = b * b - 3 * cc;
+  const double irq = rsqrt(q);          // 1 / w
+  const double w = q * irq;
+  const double ist = 0.5 * irq * irq * irq;  // 1 / sqrt(t)
+  const double ratio = s * ist;         // cos(alpha)
+  // y = cos(alpha / 3): the largest root of 4 y^3 - 3 y = cos(alpha), in [1/2, 1] where the cubic is
+  // increasing and convex, so Newton from y = 1 descends to it monotonically (instead of acos + cos)
+  double cb = 1.0;
+#pragma unroll 1
+  for (int it = 0; it < 48; ++it) {
+    const double f = fma(fma(4.0 * cb, cb, -3.0), cb, -ratio);
+    const double fp = fma(12.0 * cb, cb, -3.0);
+    const double dy = f * fast_rcp(fp);
+    cb -= dy;
+    if (!(fabs(dy) > 4e-16)) break;
+  }
+  const double sb = sqrt(fmax(0.0, fma(-cb, cb, 1.0)));  // sin(alpha / 3) >= 0
+  const double ev = (-b - 2.0 * (w * cb)) * (1.0 / 3.0);
+  const double inv_sin_alpha = -rsqrt(fma(-ratio, ratio, 1.0));
+  double g;
+  {
+    const double j00 = Y[0], j01 = Y[1], j02 = Y[2], j11 = Y[3], j12 = Y[4], j22 = Y[5];
     const double bj = -j00 - j11 - j22;
     const double cj = -2.0 * m02 * j02 - 2.0 * m12 * j12 - 2.0 * m01 * j01 + j00 * m11 + m00 * j11 + j00 * m22 +
                       m00 * j22 + j11 * m22 + m11 * j22;
@@ -193,12 +210,16 @@ __device__ __forceinline__ double es_smallest_ev(const double *mom, int stride, 
     const double sj = 6.0 * b * b * bj - 9.0 * bj * cc - 9.0 * b * cj + 27.0 * dj;
     const double qj = 2.0 * b * bj - 3.0 * cj;
     const double tj = 12.0 * q * q * qj;
-    const double alphaj = inv_sin_alpha * (sj * sqrt_t - s * 0.5 * tj / sqrt_t) / t;
-    const double yj = -sb * (alphaj / 3.0);
-    const double wj = qj / (2.0 * w);
+    // d alpha = -(1 / sin alpha) d(s / sqrt t) = -(1 / sin alpha) (sj / sqrt t - s tj / (2 t sqrt t))
+    const double alphaj = inv_sin_alpha * (sj * ist - 0.5 * s * tj * (ist * ist * ist));
+    const double yj = -sb * (alphaj * (1.0 / 3.0));
+    const double wj = 0.5 * qj * irq;
     const double kj = wj * cb + w * yj;
-    grad[k] = (-bj - 2.0 * kj) / 3.0;
+    g = (-bj - 2.0 * kj) * (1.0 / 3.0);
   }
+  grad[0] = __shfl_sync(0xffffffffu, g, 1, 4);
+  grad[1] = __shfl_sync(0xffffffffu, g, 2, 4);
+  grad[2] = __shfl_sync(0xffffffffu, g, 3, 4);
   return ev;
 }
 
@@ -438,29 +459,31 @@ struct EsLmArgs {
   int maxfev;
 };
 
-constexpr int kEsLmThreads = 64;
+constexpr int kEsLmThreads = 128;
+constexpr int kEsLmPairs = kEsLmThreads / 4;  // four lanes per frame pair
 
-// One thread per frame pair.  States of the evaluation loop: 0 = f(x0), 1..3 = forward-difference
-// column j = state - 1, 4 = trial point.
+// Four lanes per frame pair: they share the function evaluation (see es_smallest_ev) and run the
+// scalar Levenberg-Marquardt logic redundantly, so a group never diverges.  States of the evaluation
+// loop: 0 = f(x0), 1..3 = forward-difference column j = state - 1, 4 = trial point.
 __global__ void __launch_bounds__(kEsLmThreads) es_lm_kernel(const __grid_constant__ EsLmArgs args) {
-  __shared__ double s_mom[kEsMom * kEsLmThreads];
-  const int tid = threadIdx.x;
-  const long long b = static_cast<long long>(blockIdx.x) * kEsLmThreads + tid;
+  __shared__ double s_mom[kEsMom * kEsLmPairs];
+  const int tid = threadIdx.x, sub = tid & 3, slot = tid >> 2;
+  const long long b = static_cast<long long>(blockIdx.x) * kEsLmPairs + slot;
   const bool in_range = b < args.num_problems;
   const long long bb = in_range ? b : args.num_problems - 1;
   const bool passthrough = in_range && args.fixed && args.fixed[bb];
   const bool active = in_range && !passthrough;
   // coalesced staging of this CTA's moments, transposed to [k][thread]
   {
-    const long long first = static_cast<long long>(blockIdx.x) * kEsLmThreads;
-    const long long cnt = min(static_cast<long long>(kEsLmThreads), args.num_problems - first);
+    const long long first = static_cast<long long>(blockIdx.x) * kEsLmPairs;
+    const long long cnt = min(static_cast<long long>(kEsLmPairs), args.num_problems - first);
     for (long long i = tid; i < cnt * kEsMom; i += kEsLmThreads) {
       const int p = static_cast<int>(i / kEsMom), k = static_cast<int>(i % kEsMom);
-      s_mom[k * kEsLmThreads + p] = args.moments[first * kEsMom + i];
+      s_mom[k * kEsLmPairs + p] = args.moments[first * kEsMom + i];
     }
     __syncthreads();
   }
-  const double *mom = s_mom + (active ? tid : 0);
+  const double *mom = s_mom + (active ? slot : 0);
   const double *pin = args.poses_in + 7 * bb;
   // opengv::math::rot2cayley: [c]x = (R - I)(R + I)^-1, i.e. q_xyz / q_w
   double x[3] = {pin[0] / pin[3], pin[1] / pin[3], pin[2] / pin[3]};
@@ -489,7 +512,7 @@ __global__ void __launch_bounds__(kEsLmThreads) es_lm_kernel(const __grid_consta
       xe[0] = wa2[0]; xe[1] = wa2[1]; xe[2] = wa2[2];
     }
     double fe[3];
-    es_smallest_ev(mom, kEsLmThreads, xe, fe);
+    es_smallest_ev(mom, kEsLmPairs, xe, sub, fe);
     if (done) continue;
 
     bool need_step = false;
@@ -629,13 +652,18 @@ __global__ void __launch_bounds__(kEsLmThreads) es_lm_kernel(const __grid_consta
       state = 4;
     }
   }
-  if (passthrough) {
+  if (passthrough && sub == 0) {
     double *po = args.poses_out + 7 * b;
 #pragma unroll
     for (int k = 0; k < 7; ++k) po[k] = pin[k];
     if (args.q_same) args.q_same[b] = 1;
   }
-  if (active) {
+  double ev_final = 0.0;
+  if (args.out_ev) {  // all four lanes of every group take part in the evaluation
+    double g[3];
+    ev_final = es_smallest_ev(mom, kEsLmPairs, x, sub, g);
+  }
+  if (active && sub == 0) {
     double *po = args.poses_out + 7 * b;
     const double sc = 1.0 / sqrt(1.0 + x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
     po[0] = x[0] * sc; po[1] = x[1] * sc; po[2] = x[2] * sc; po[3] = sc;
@@ -647,10 +675,7 @@ __global__ void __launch_bounds__(kEsLmThreads) es_lm_kernel(const __grid_consta
                        __double_as_longlong(po[3]) == __double_as_longlong(pin[3]);
     if (args.out_info) args.out_info[b] = info;
     if (args.out_nfev) args.out_nfev[b] = nfev;
-    if (args.out_ev) {
-      double g[3];
-      args.out_ev[b] = es_smallest_ev(mom, kEsLmThreads, x, g);
-    }
+    if (args.out_ev) args.out_ev[b] = ev_final;
   }
 }
 

@@ -287,6 +287,11 @@ __device__ __forceinline__ double scf_objective_tail(const double *terms, int be
 template <int NW>
 __device__ __forceinline__ void scf_pair(const ScfArgs &args, const long long b) {
   constexpr int NT = NW * 32;
+  // Sums whose value depends on how they are split over threads (cost0, E of the SCF steps) are
+  // always split over the first NWA = 4 warps, so that the 4-warp and the 16-warp launch of the
+  // same pair produce the same bits; the extra warps only serve the scan.
+  constexpr int NWA = NW < 4 ? NW : 4;
+  constexpr int NTA = NWA * 32;
   __shared__ double s_red[NW][6];
   __shared__ double s_best_cost[NW];
   __shared__ int s_best_idx[NW];
@@ -344,20 +349,22 @@ __device__ __forceinline__ void scf_pair(const ScfArgs &args, const long long b)
     const double txx = t0[0] * t0[0], txy = 2.0 * t0[0] * t0[1], txz = 2.0 * t0[0] * t0[2];
     const double tyy = t0[1] * t0[1], tyz = 2.0 * t0[1] * t0[2], tzz = t0[2] * t0[2];
     double part = 0.0;
-    for (int i = tid; i < n; i += NT) {
-      const double *w = terms + 9 * i;
-      const double e = t0[0] * w[0] + t0[1] * w[1] + t0[2] * w[2];
-      const double den = w[3] * txx + w[4] * txy + w[5] * txz + w[6] * tyy + w[7] * tyz + w[8] * tzz;
-      part = fma(e * e, fast_rcp(den), part);
-    }
+    if (warp < NWA) {
+      for (int i = tid; i < n; i += NTA) {
+        const double *w = terms + 9 * i;
+        const double e = t0[0] * w[0] + t0[1] * w[1] + t0[2] * w[2];
+        const double den = w[3] * txx + w[4] * txy + w[5] * txz + w[6] * tyy + w[7] * tyz + w[8] * tzz;
+        part = fma(e * e, fast_rcp(den), part);
+      }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    if (lane == 0) s_best_cost[warp] = part;
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      if (lane == 0) s_best_cost[warp] = part;
+    }
     if (tid == 0) s_nsurv = 0;
     __syncthreads();
     cost0 = 0.0;
 #pragma unroll
-    for (int w = 0; w < NW; ++w) cost0 += s_best_cost[w];
+    for (int w = 0; w < NWA; ++w) cost0 += s_best_cost[w];
     __syncthreads();
   }
   // what is known about the sphere: minimum `sph_value` at point `sph_idx` (> 0), or only the lower
@@ -496,23 +503,25 @@ __device__ __forceinline__ void scf_pair(const ScfArgs &args, const long long b)
       const double t[3] = {s_t[0], s_t[1], s_t[2]};
       const double txx = t[0] * t[0], txy = 2.0 * t[0] * t[1], txz = 2.0 * t[0] * t[2];
       const double tyy = t[1] * t[1], tyz = 2.0 * t[1] * t[2], tzz = t[2] * t[2];
-      double E[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      for (int i = tid; i < n; i += NT) {
-        const double *w = terms + 9 * i;
-        const double den = w[3] * txx + w[4] * txy + w[5] * txz + w[6] * tyy + w[7] * tyz + w[8] * tzz;
-        const double inv = fast_rcp(den);
-        E[0] = fma(w[0] * w[0], inv, E[0]); E[1] = fma(w[0] * w[1], inv, E[1]); E[2] = fma(w[0] * w[2], inv, E[2]);
-        E[3] = fma(w[1] * w[1], inv, E[3]); E[4] = fma(w[1] * w[2], inv, E[4]); E[5] = fma(w[2] * w[2], inv, E[5]);
+      if (warp < NWA) {
+        double E[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int i = tid; i < n; i += NTA) {
+          const double *w = terms + 9 * i;
+          const double den = w[3] * txx + w[4] * txy + w[5] * txz + w[6] * tyy + w[7] * tyz + w[8] * tzz;
+          const double inv = fast_rcp(den);
+          E[0] = fma(w[0] * w[0], inv, E[0]); E[1] = fma(w[0] * w[1], inv, E[1]); E[2] = fma(w[0] * w[2], inv, E[2]);
+          E[3] = fma(w[1] * w[1], inv, E[3]); E[4] = fma(w[1] * w[2], inv, E[4]); E[5] = fma(w[2] * w[2], inv, E[5]);
+        }
+        // transposing warp reduction: lane L ends with the warp sum of E[4 b4 + 2 b3 + b2]
+        exchange_step<8, 16>(E, lane);
+        exchange_step<4, 8>(E, lane);
+        exchange_step<2, 4>(E, lane);
+        double sum = E[0];
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        const int eidx = 4 * ((lane >> 4) & 1) + 2 * ((lane >> 3) & 1) + ((lane >> 2) & 1);
+        if ((lane & 3) == 0 && eidx < 6) s_red[warp][eidx] = sum;
       }
-      // transposing warp reduction: lane L ends with the warp sum of E[4 b4 + 2 b3 + b2]
-      exchange_step<8, 16>(E, lane);
-      exchange_step<4, 8>(E, lane);
-      exchange_step<2, 4>(E, lane);
-      double sum = E[0];
-      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-      const int eidx = 4 * ((lane >> 4) & 1) + 2 * ((lane >> 3) & 1) + ((lane >> 2) & 1);
-      if ((lane & 3) == 0 && eidx < 6) s_red[warp][eidx] = sum;
       __syncthreads();
       if (tid == 0) {
         double Es[6];
@@ -520,7 +529,7 @@ __device__ __forceinline__ void scf_pair(const ScfArgs &args, const long long b)
         for (int k = 0; k < 6; ++k) {
           double a = 0.0;
 #pragma unroll
-          for (int w = 0; w < NW; ++w) a += s_red[w][k];
+          for (int w = 0; w < NWA; ++w) a += s_red[w][k];
           Es[k] = a;
         }
         double v[3], lam;

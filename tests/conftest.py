@@ -39,6 +39,11 @@ def golden_scf():
 
 
 @pytest.fixture(scope="session")
+def golden_frame():
+    return np.load(os.path.join(GOLDEN, "oracle_frame.npz"))
+
+
+@pytest.fixture(scope="session")
 def golden_solutions():
     return np.load(os.path.join(GOLDEN, "oracle_solutions.npz"))
 

@@ -166,10 +166,50 @@ def oracle_fixtures():
     np.savez_compressed(os.path.join(HERE, "oracle_solutions.npz"), **out)
 
 
+def oracle_frame_fixtures():
+    """oracle_frame.npz: the front stages of PNEC::Solve (oracle/pnec_oracle_frame.c) on seeded
+    frame pairs: eigensolver rotations (plain and weighted), the NEC eigensolver pose, the
+    weighted-eigensolver pose and the result of the whole pipeline for several option sets, plus
+    the same outputs on inputs moved by one ulp (the tests only compare pairs on which the
+    algorithm itself is stable under that perturbation).  Minted by the oracle (the LM inside is
+    pinned against MINPACK, tests/test_oracle_frame.py); not reference outputs: opengv is not
+    available."""
+    import oracle
+    from pnec_b200 import synthetic as syn
+
+    out = {}
+    configs = {"default": {}, "nec_ceres": {"use_nec": 1}, "es_then_ceres": {"weighted_iterations": 1},
+               "weighted3_no_ceres": {"use_ceres": 0, "weighted_iterations": 3}}
+    for name, (B, N, cam, seed) in {"omni_n200": (24, 200, syn.OMNIDIRECTIONAL, 301),
+                                     "pinhole_n96": (24, 96, syn.PINHOLE, 302)}.items():
+        b = syn.make_batch(B, N, seed=seed, camera=cam)
+        rng = np.random.default_rng(seed)
+        f1p = b.bvs_host * (1.0 + rng.uniform(-1, 1, b.bvs_host.shape) * 2.0 ** -52)
+        f2p = b.bvs_target * (1.0 + rng.uniform(-1, 1, b.bvs_target.shape) * 2.0 ** -52)
+        out[f"{name}/f1"], out[f"{name}/f2"], out[f"{name}/cov"] = b.bvs_host, b.bvs_target, b.covs_target
+        out[f"{name}/init"], out[f"{name}/gt"], out[f"{name}/n"] = b.init_poses, b.gt_poses, np.int64(N)
+        for tag, (f1, f2) in {"": (b.bvs_host, b.bvs_target), "_ulp": (f1p, f2p)}.items():
+            es_q, w_q = np.zeros((B, 4)), np.zeros((B, 4))
+            for k in range(B):
+                s, e = b.range(k)
+                es_q[k], _ = oracle.eigensolver(f1[s:e], f2[s:e], b.init_poses[k])
+                w = oracle.weights(f1[s:e], b.covs_target[s:e], b.gt_poses[k], 1e-13)
+                w_q[k], _ = oracle.eigensolver(f1[s:e], f2[s:e], b.init_poses[k], w)
+            out[f"{name}/es_quat{tag}"] = es_q
+            out[f"{name}/weighted_es_quat{tag}"] = w_q  # weights from the ground-truth poses
+            for cname, kw in configs.items():
+                poses, es = oracle.frame_solve_batch(f1, f2, b.covs_target, b.init_poses,
+                                                     oracle.default_frame_opts(**kw), n_per_problem=N)
+                out[f"{name}/{cname}/poses{tag}"] = poses
+                out[f"{name}/es_pose{tag}"] = es
+    np.savez_compressed(os.path.join(HERE, "oracle_frame.npz"), **out)
+
+
 if __name__ == "__main__":
     reference_fixtures()
     reference_scf_fixtures()
     oracle_fixtures()
+    oracle_frame_fixtures()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -143,3 +143,22 @@ def test_frame_solve_option_matrix(batch):
     e_es = np.mean([rotation_angle(a, g) for a, g in zip(es, batch.gt_poses)])
     e_full = np.mean([rotation_angle(a, g) for a, g in zip(full, batch.gt_poses)])
     assert e_full < e_es
+
+
+def test_oracle_reproduces_committed_frame_fixtures(golden_frame):
+    """tests/golden/oracle_frame.npz (tests/golden/make_golden.py) guards the restatement against drift."""
+    g = golden_frame
+    for name in ("omni_n200", "pinhole_n96"):
+        n = int(g[f"{name}/n"])
+        f1, f2, cov, init = g[f"{name}/f1"], g[f"{name}/f2"], g[f"{name}/cov"], g[f"{name}/init"]
+        for k in (0, 7, 23):
+            q, _ = oracle.eigensolver(f1[k * n:(k + 1) * n], f2[k * n:(k + 1) * n], init[k])
+            assert rotation_angle(np.r_[q, 0, 0, 1], np.r_[g[f"{name}/es_quat"][k], 0, 0, 1]) < 1e-12
+        poses, es = oracle.frame_solve_batch(f1, f2, cov, init, oracle.default_frame_opts(), n_per_problem=n,
+                                             num_threads=oracle.max_threads())
+        stable = np.array([rotation_angle(a, b) < 1e-8 and direction_angle(a[4:], b[4:]) < 1e-8
+                           for a, b in zip(g[f"{name}/default/poses"], g[f"{name}/default/poses_ulp"])])
+        assert stable.mean() > 0.8
+        for k in np.nonzero(stable)[0]:
+            assert rotation_angle(poses[k], g[f"{name}/default/poses"][k]) < 1e-9
+            assert direction_angle(poses[k][4:], g[f"{name}/default/poses"][k][4:]) < 1e-9
