@@ -82,7 +82,11 @@ struct pnec_handle {
   DevBuf d_ut_mu, d_ut_cov, d_ut_out, d_kp_bv, d_sphere, d_tr_out, d_tr_aux;
   DevBuf d_es_mom, d_es_w, d_es_info, d_es_ev, d_fr_es, d_fr_a, d_fr_b;  // eigensolver / frame pipeline
   DevBuf d_fr_cache, d_fr_flags;  // ScfScanCache[B]; int q_same[B], fixed[B]
-  DevBuf d_scf_defer;             // int count, cursor, pad[2], list[B]
+  DevBuf d_scf_defer;             // int count, cursor, pad[2], list[B]  (standalone SCF calls)
+  DevBuf d_fr_defer;              // the same per chunk of a frame solve: (4 + B) ints
+  static constexpr int kMaxChunks = 8;
+  cudaStream_t side[kMaxChunks] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[kMaxChunks] = {};
   int sphere_samples = -1;
   std::mutex mu;
 };
@@ -391,6 +395,25 @@ int launch_eval(pnec_handle *h, const EvalArgs &a0, int variant, long long max_n
 }
 
 
+// Pairs [start, start + cnt) of a device view.  Ragged batches index their arrays absolutely
+// through `offsets`, so only the offsets pointer moves; uniform batches move the array bases.
+BatchView sub_view(const BatchView &bv, long long start, long long cnt) {
+  BatchView v = bv;
+  v.num_problems = cnt;
+  if (bv.offsets) {
+    v.offsets = bv.offsets + start;
+  } else {
+    const long long e0 = start * bv.n_uniform;
+    v.f1 = bv.f1 + 3 * e0;
+    v.f2 = bv.f2 + 3 * e0;
+    if (bv.ct) v.ct = bv.ct + 9 * e0;
+    if (bv.ch) v.ch = bv.ch + 9 * e0;
+    v.total = cnt * bv.n_uniform;
+  }
+  if (bv.poses) v.poses = bv.poses + 7 * start;
+  return v;
+}
+
 // ------------------------------------------------- stage launchers (device views only)
 
 // The refinement with its outputs: device arrays when `host` is false, else staged through the
@@ -461,7 +484,8 @@ size_t scf_smem_bytes(long long max_n) { return static_cast<size_t>(std::max<lon
 // translation slot of bv.poses itself: every read of the pose precedes the final write)
 int run_scf(pnec_handle *h, const BatchView &bv, long long max_n, double reg, int samples, int steps,
             double *out_t, int out_stride, double *out_cost, cudaStream_t stream,
-            ScfScanCache *cache = nullptr, const int *q_same = nullptr, int *fixed = nullptr) {
+            ScfScanCache *cache = nullptr, const int *q_same = nullptr, int *fixed = nullptr,
+            int *defer_buf = nullptr /* 4 + B ints, else the handle's */) {
   const size_t dyn = scf_smem_bytes(max_n);
   if (dyn + kStaticSmemReserve > h->smem_optin)
     return fail(PNEC_ERR_UNSUPPORTED, "SCF translation: a frame pair exceeds the shared-memory capacity (~3100 correspondences)");
@@ -490,10 +514,12 @@ int run_scf(pnec_handle *h, const BatchView &bv, long long max_n, double reg, in
   int nw = env_int("PNEC_B200_SCF_WARPS", 4);
   if (nw != 1 && nw != 2 && nw != 8) nw = 4;
   const int defer = env_int("PNEC_B200_SCF_DEFER", 48);  // survivors above which a pair goes to pass 2; 0 = one pass
-  int *d_defer = nullptr;
+  int *d_defer = defer_buf;
   if (defer > 0) {
-    PNEC_CUDA(h->d_scf_defer.ensure(sizeof(int) * (4 + static_cast<size_t>(bv.num_problems))));
-    d_defer = static_cast<int *>(h->d_scf_defer.p);
+    if (!d_defer) {
+      PNEC_CUDA(h->d_scf_defer.ensure(sizeof(int) * (4 + static_cast<size_t>(bv.num_problems))));
+      d_defer = static_cast<int *>(h->d_scf_defer.p);
+    }
     PNEC_CUDA(cudaMemsetAsync(d_defer, 0, sizeof(int) * 4, stream));
     a.defer_count = d_defer;
     a.defer_list = d_defer + 4;
@@ -662,8 +688,13 @@ void pnec_destroy(pnec_handle *h) {
                     &h->d_out_init, &h->d_out_grad, &h->d_out_jtj, &h->d_ut_mu, &h->d_ut_cov,
                     &h->d_ut_out, &h->d_kp_bv, &h->d_sphere, &h->d_tr_out,
                     &h->d_tr_aux, &h->d_es_mom, &h->d_es_w, &h->d_es_info, &h->d_es_ev,
-                    &h->d_fr_es, &h->d_fr_a, &h->d_fr_b, &h->d_fr_cache, &h->d_fr_flags, &h->d_scf_defer};
+                    &h->d_fr_es, &h->d_fr_a, &h->d_fr_b, &h->d_fr_cache, &h->d_fr_flags, &h->d_scf_defer, &h->d_fr_defer};
   for (DevBuf *b : bufs) b->release();
+  for (int i = 0; i < pnec_handle::kMaxChunks; ++i) {
+    if (h->side[i]) cudaStreamDestroy(h->side[i]);
+    if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+  }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   delete h;
 }
 
@@ -1017,76 +1048,130 @@ int pnec_frame_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_f
     return fail(PNEC_ERR_UNSUPPORTED, "pnec_frame_solve_batch: the SCF stage keeps a frame pair in shared memory (~3100 correspondences at most)");
   const bool host = batch->memspace == PNEC_MEM_HOST;
   const size_t nb = static_cast<size_t>(B);
+  // ---- scratch for the whole batch (allocated before anything is forked: cudaMalloc synchronises)
   PNEC_CUDA(h->d_es_mom.ensure(nb * kEsMom * 8));
   PNEC_CUDA(h->d_fr_es.ensure(nb * 56));
   PNEC_CUDA(h->d_fr_a.ensure(nb * 56));
   PNEC_CUDA(h->d_fr_b.ensure(nb * 56));
-  double *d_mom = static_cast<double *>(h->d_es_mom.p);
-  double *d_es = (!host && out->es_poses) ? out->es_poses : static_cast<double *>(h->d_fr_es.p);
-  double *d_a = static_cast<double *>(h->d_fr_a.p), *d_b = static_cast<double *>(h->d_fr_b.p);
-
-  // 1. PNEC::Eigensolver: rotation, then TranslationFromM(ComposeM(bvs1, bvs2, rotation))
-  rc = run_es_moments(h, st.bv, false, 0.0, d_mom, stream);
-  if (rc != PNEC_OK) return rc;
-  rc = run_es_lm(h, B, d_mom, st.bv.poses, d_es, nullptr, nullptr, stream);
-  if (rc != PNEC_OK) return rc;
-  BatchView ev = st.bv;
-  ev.poses = d_es;
-  rc = run_nec_translation(h, ev, d_es + 4, 7, nullptr, stream);
-  if (rc != PNEC_OK) return rc;
-
-  // 2./3. the start pose of the refinement
-  const double *d_init = d_es;
+  PNEC_CUDA(h->d_fr_cache.ensure(nb * sizeof(ScfScanCache)));
+  PNEC_CUDA(h->d_fr_flags.ensure(nb * 2 * sizeof(int)));
+  PNEC_CUDA(h->d_fr_defer.ensure(sizeof(int) * (4 * pnec_handle::kMaxChunks + nb)));
   if (weighted) {
-    // weights from ES_solution in every iteration (pnec.cc:296-300): one set of weighted moments
-    rc = run_es_moments(h, ev, true, opts->ceres.regularization, d_mom, stream);
+    rc = ensure_sphere(h, opts->fibonacci_samples);
     if (rc != PNEC_OK) return rc;
-    // The round (R, t) -> (R', t') is a deterministic map with everything else held constant, so
-    //  * a rotation that repeats bit for bit reuses its sphere scan (ScfScanCache), and
-    //  * a pair whose whole pose repeats has reached a fixed point: later rounds are skipped.
-    // Both give exactly what recomputing would.
-    PNEC_CUDA(h->d_fr_cache.ensure(nb * sizeof(ScfScanCache)));
-    PNEC_CUDA(h->d_fr_flags.ensure(nb * 2 * sizeof(int)));
-    ScfScanCache *d_cache = static_cast<ScfScanCache *>(h->d_fr_cache.p);
-    int *d_qsame = static_cast<int *>(h->d_fr_flags.p), *d_fixed = d_qsame + B;
-    const bool shortcuts = !env_int("PNEC_B200_NO_FRAME_SHORTCUTS", 0);
-    PNEC_CUDA(cudaMemsetAsync(d_cache, 0, nb * sizeof(ScfScanCache), stream));
-    PNEC_CUDA(cudaMemsetAsync(d_qsame, 0, nb * 2 * sizeof(int), stream));
-    const double *cur = d_es;
-    for (int it = 0; it + 1 < opts->weighted_iterations; ++it) {
-      double *nxt = (it & 1) ? d_b : d_a;
-      // rotation; translation passed through
-      rc = run_es_lm(h, B, d_mom, cur, nxt, nullptr, nullptr, stream, shortcuts ? d_fixed : nullptr,
-                     shortcuts ? d_qsame : nullptr);
-      if (rc != PNEC_OK) return rc;
-      BatchView sv = st.bv;
-      sv.poses = nxt;
-      rc = run_scf(h, sv, st.max_n, opts->ceres.regularization, opts->fibonacci_samples, opts->scf_steps,
-                   nxt + 4, 7, nullptr, stream, shortcuts ? d_cache : nullptr, shortcuts ? d_qsame : nullptr,
-                   shortcuts ? d_fixed : nullptr);
-      if (rc != PNEC_OK) return rc;
-      cur = nxt;
-    }
-    d_init = cur;
-  } else if (!nec && opts->weighted_iterations == 0) {
-    normalize_poses_kernel<<<static_cast<unsigned>((B + 127) / 128), 128, 0, stream>>>(st.bv.poses, d_a, B);
-    PNEC_CUDA(cudaGetLastError());
-    h->launches++;
-    d_init = d_a;
   }
+  double *o_poses = out->poses, *o_cost = out->cost;
+  int32_t *o_status = out->status, *o_iters = out->iterations;
+  if (host) {
+    PNEC_CUDA(h->d_out_poses.ensure(nb * 56));
+    PNEC_CUDA(h->d_out_status.ensure(nb * 4));
+    PNEC_CUDA(h->d_out_iters.ensure(nb * 4));
+    PNEC_CUDA(h->d_out_cost.ensure(nb * 8));
+    o_poses = static_cast<double *>(h->d_out_poses.p);
+    o_status = out->status ? static_cast<int32_t *>(h->d_out_status.p) : nullptr;
+    o_iters = out->iterations ? static_cast<int32_t *>(h->d_out_iters.p) : nullptr;
+    o_cost = out->cost ? static_cast<double *>(h->d_out_cost.p) : nullptr;
+  }
+  double *const d_mom = static_cast<double *>(h->d_es_mom.p);
+  double *const d_es = (!host && out->es_poses) ? out->es_poses : static_cast<double *>(h->d_fr_es.p);
+  double *const d_a = static_cast<double *>(h->d_fr_a.p), *const d_b = static_cast<double *>(h->d_fr_b.p);
+  ScfScanCache *const d_cache = static_cast<ScfScanCache *>(h->d_fr_cache.p);
+  int *const d_qsame = static_cast<int *>(h->d_fr_flags.p), *const d_fixed = d_qsame + B;
+  int *const d_defer = static_cast<int *>(h->d_fr_defer.p);
+  const bool shortcuts = !env_int("PNEC_B200_NO_FRAME_SHORTCUTS", 0);
 
-  // 4. refinement
-  if (opts->use_ceres) {
-    pnec_solver_opts so = opts->ceres;
-    so.variant = variant;
-    BatchView rv = st.bv;
-    rv.poses = d_init;
-    rc = run_solve(h, rv, st.max_n, so, host, out->poses, out->status, out->iterations, out->cost, nullptr, stream);
+  // The stages of one chunk of frame pairs, back to back on one stream.
+  auto run_chunk = [&](long long c0, long long cnt, int chunk, cudaStream_t cs) -> int {
+    const BatchView bv = sub_view(st.bv, c0, cnt);
+    double *mom = d_mom + kEsMom * c0, *es = d_es + 7 * c0, *pa = d_a + 7 * c0, *pb = d_b + 7 * c0;
+    int rcc;
+    // 1. PNEC::Eigensolver: rotation, then TranslationFromM(ComposeM(bvs1, bvs2, rotation))
+    if ((rcc = run_es_moments(h, bv, false, 0.0, mom, cs)) != PNEC_OK) return rcc;
+    if ((rcc = run_es_lm(h, cnt, mom, bv.poses, es, nullptr, nullptr, cs)) != PNEC_OK) return rcc;
+    BatchView ev = bv;
+    ev.poses = es;
+    if ((rcc = run_nec_translation(h, ev, es + 4, 7, nullptr, cs)) != PNEC_OK) return rcc;
+    // 2./3. the start pose of the refinement
+    const double *init = es;
+    if (weighted) {
+      // weights from ES_solution in every round (pnec.cc:296-300): one set of weighted moments
+      if ((rcc = run_es_moments(h, ev, true, opts->ceres.regularization, mom, cs)) != PNEC_OK) return rcc;
+      // The round (R, t) -> (R', t') is a deterministic map with everything else held constant, so
+      //  * a rotation that repeats bit for bit reuses its sphere scan (ScfScanCache), and
+      //  * a pair whose whole pose repeats has reached a fixed point: later rounds are skipped.
+      // Both give exactly what recomputing would.
+      ScfScanCache *cache = d_cache + c0;
+      int *qsame = d_qsame + c0, *fixed = d_fixed + c0;
+      int *defer = d_defer + (4 * chunk + c0);  // chunk k: 4 header ints, then its list (disjoint regions)
+      PNEC_CUDA(cudaMemsetAsync(cache, 0, static_cast<size_t>(cnt) * sizeof(ScfScanCache), cs));
+      PNEC_CUDA(cudaMemsetAsync(qsame, 0, static_cast<size_t>(cnt) * sizeof(int), cs));
+      PNEC_CUDA(cudaMemsetAsync(fixed, 0, static_cast<size_t>(cnt) * sizeof(int), cs));
+      const double *cur = es;
+      for (int it = 0; it + 1 < opts->weighted_iterations; ++it) {
+        double *nxt = (it & 1) ? pb : pa;
+        // rotation; translation passed through
+        if ((rcc = run_es_lm(h, cnt, mom, cur, nxt, nullptr, nullptr, cs, shortcuts ? fixed : nullptr,
+                             shortcuts ? qsame : nullptr)) != PNEC_OK)
+          return rcc;
+        BatchView sv = bv;
+        sv.poses = nxt;
+        if ((rcc = run_scf(h, sv, st.max_n, opts->ceres.regularization, opts->fibonacci_samples, opts->scf_steps,
+                           nxt + 4, 7, nullptr, cs, shortcuts ? cache : nullptr, shortcuts ? qsame : nullptr,
+                           shortcuts ? fixed : nullptr, defer)) != PNEC_OK)
+          return rcc;
+        cur = nxt;
+      }
+      init = cur;
+    } else if (!nec && opts->weighted_iterations == 0) {
+      normalize_poses_kernel<<<static_cast<unsigned>((cnt + 127) / 128), 128, 0, cs>>>(bv.poses, pa, cnt);
+      PNEC_CUDA(cudaGetLastError());
+      h->launches++;
+      init = pa;
+    }
+    // 4. refinement
+    if (opts->use_ceres) {
+      pnec_solver_opts so = opts->ceres;
+      so.variant = variant;
+      BatchView rv = bv;
+      rv.poses = init;
+      return run_solve(h, rv, st.max_n, so, false, o_poses + 7 * c0, o_status ? o_status + c0 : nullptr,
+                       o_iters ? o_iters + c0 : nullptr, o_cost ? o_cost + c0 : nullptr, nullptr, cs);
+    }
+    PNEC_CUDA(cudaMemcpyAsync(o_poses + 7 * c0, init, static_cast<size_t>(cnt) * 56, cudaMemcpyDeviceToDevice, cs));
+    return PNEC_OK;
+  };
+
+  // Frame pairs are independent and every stage ends in a tail (a few pairs need 100 function
+  // evaluations, or a sphere scan that cannot prune): the batch is cut into chunks that run their
+  // stages on separate streams, so one chunk's tail is filled with another chunk's work.
+  int chunks = env_int("PNEC_B200_FRAME_CHUNKS", 0);
+  if (chunks <= 0) chunks = B >= 4096 ? 4 : (B >= 1024 ? 2 : 1);
+  chunks = std::min<long long>(std::min(chunks, pnec_handle::kMaxChunks), B);
+  if (chunks == 1) {
+    rc = run_chunk(0, B, 0, stream);
     if (rc != PNEC_OK) return rc;
   } else {
-    PNEC_CUDA(cudaMemcpyAsync(out->poses, d_init, nb * 56, host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, stream));
+    if (!h->ev_fork) PNEC_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    PNEC_CUDA(cudaEventRecord(h->ev_fork, stream));
+    for (int c = 0; c < chunks; ++c) {
+      if (!h->side[c]) PNEC_CUDA(cudaStreamCreateWithFlags(&h->side[c], cudaStreamNonBlocking));
+      if (!h->ev_join[c]) PNEC_CUDA(cudaEventCreateWithFlags(&h->ev_join[c], cudaEventDisableTiming));
+      PNEC_CUDA(cudaStreamWaitEvent(h->side[c], h->ev_fork, 0));
+      const long long c0 = B * c / chunks, c1 = B * (c + 1) / chunks;
+      rc = run_chunk(c0, c1 - c0, c, h->side[c]);
+      if (rc != PNEC_OK) return rc;
+      PNEC_CUDA(cudaEventRecord(h->ev_join[c], h->side[c]));
+    }
+    for (int c = 0; c < chunks; ++c) PNEC_CUDA(cudaStreamWaitEvent(stream, h->ev_join[c], 0));
   }
   if (host) {
+    PNEC_CUDA(cudaMemcpyAsync(out->poses, o_poses, nb * 56, cudaMemcpyDeviceToHost, stream));
+    if (out->status && opts->use_ceres)
+      PNEC_CUDA(cudaMemcpyAsync(out->status, o_status, nb * 4, cudaMemcpyDeviceToHost, stream));
+    if (out->iterations && opts->use_ceres)
+      PNEC_CUDA(cudaMemcpyAsync(out->iterations, o_iters, nb * 4, cudaMemcpyDeviceToHost, stream));
+    if (out->cost && opts->use_ceres)
+      PNEC_CUDA(cudaMemcpyAsync(out->cost, o_cost, nb * 8, cudaMemcpyDeviceToHost, stream));
     if (out->es_poses)
       PNEC_CUDA(cudaMemcpyAsync(out->es_poses, d_es, nb * 56, cudaMemcpyDeviceToHost, stream));
     PNEC_CUDA(cudaStreamSynchronize(stream));
