@@ -218,8 +218,9 @@ int pnec_keypoints_unproject_batch(pnec_handle *h, int64_t n, int32_t memspace,
  *           E(t) = sum_i A_i / (t^T B_i t)                 (scf.cc:109-147, including the
  *           `frac.resize(n)` + push_back quirk that makes frac[i] == 0)
  * The reference calls it with 500 samples and 10 steps.  The sign of the result is that of the
- * eigenvector routine (arbitrary, as with Eigen): compare modulo sign.  Pairs are limited to
- * ~3100 correspondences (shared-memory resident); larger ones return PNEC_ERR_UNSUPPORTED.
+ * eigenvector routine (arbitrary, as with Eigen): compare modulo sign.  Pairs up to ~3000
+ * correspondences are processed out of shared memory; larger ones keep their per-correspondence
+ * terms in a device scratch array (slower, same arithmetic).
  *   out_translations [B][3]      out_cost [B] objective at the result, or NULL */
 int pnec_scf_translation_batch(pnec_handle *h, const pnec_batch *batch, double regularization,
                                int32_t fibonacci_samples, int32_t scf_steps,

@@ -84,6 +84,7 @@ struct pnec_handle {
   DevBuf d_fr_cache, d_fr_flags;  // ScfScanCache[B]; int q_same[B], fixed[B]
   DevBuf d_scf_defer;             // int count, cursor, pad[2], list[B]  (standalone SCF calls)
   DevBuf d_fr_defer;              // the same per chunk of a frame solve: (4 + B) ints
+  DevBuf d_scf_spill;             // [total][9] SCF terms of pairs that do not fit shared memory
   static constexpr int kMaxChunks = 8;
   cudaStream_t side[kMaxChunks] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[kMaxChunks] = {};
@@ -478,17 +479,31 @@ int ensure_sphere(pnec_handle *h, int fibonacci_samples) {
   return PNEC_OK;
 }
 
-size_t scf_smem_bytes(long long max_n) { return static_cast<size_t>(std::max<long long>(max_n, 1)) * 72; }
+// dynamic shared memory of the SCF kernels: the largest pair, capped at what the device offers
+size_t scf_smem_bytes(const pnec_handle *h, long long max_n) {
+  const size_t want = static_cast<size_t>(std::max<long long>(max_n, 1)) * 72;
+  const size_t cap = ((h->smem_optin - 8192) / 72) * 72;  // static shared memory of scf_list_kernel + slack
+  return std::min(want, cap);
+}
+
+// Pairs above the shared-memory capacity keep their terms in HBM: allocate before launching.
+int ensure_scf_spill(pnec_handle *h, const BatchView &bv, long long max_n) {
+  if (scf_smem_bytes(h, max_n) >= static_cast<size_t>(std::max<long long>(max_n, 1)) * 72) return PNEC_OK;
+  PNEC_CUDA(h->d_scf_spill.ensure(static_cast<size_t>(bv.total) * 72));
+  return PNEC_OK;
+}
 
 // scf_kernel: rotation + start translation from bv.poses, result at out_t + out_stride * b (may be the
-// translation slot of bv.poses itself: every read of the pose precedes the final write)
+// translation slot of bv.poses itself: every read of the pose precedes the final write).  `bv` may be a
+// sub-view; `spill_base` is the spill array of the WHOLE batch for ragged views (absolute indices) and
+// of this sub-view's first correspondence for uniform ones.
 int run_scf(pnec_handle *h, const BatchView &bv, long long max_n, double reg, int samples, int steps,
             double *out_t, int out_stride, double *out_cost, cudaStream_t stream,
             ScfScanCache *cache = nullptr, const int *q_same = nullptr, int *fixed = nullptr,
-            int *defer_buf = nullptr /* 4 + B ints, else the handle's */) {
-  const size_t dyn = scf_smem_bytes(max_n);
-  if (dyn + kStaticSmemReserve > h->smem_optin)
-    return fail(PNEC_ERR_UNSUPPORTED, "SCF translation: a frame pair exceeds the shared-memory capacity (~3100 correspondences)");
+            int *defer_buf = nullptr /* 4 + B ints, else the handle's */, double *spill = nullptr) {
+  const size_t dyn = scf_smem_bytes(h, max_n);
+  const bool fits = dyn >= static_cast<size_t>(std::max<long long>(max_n, 1)) * 72;
+  if (!fits && !spill) return fail(PNEC_ERR_INVALID_ARGUMENT, "internal: SCF spill array missing");
   int rc = ensure_sphere(h, samples);
   if (rc != PNEC_OK) return rc;
   ScfArgs a{};
@@ -498,6 +513,7 @@ int run_scf(pnec_handle *h, const BatchView &bv, long long max_n, double reg, in
   a.samples = samples;
   a.steps = steps;
   a.cap_elems = static_cast<int>(dyn / 72);
+  a.spill = fits ? nullptr : spill;
   a.out_t = out_t;
   a.out_stride = out_stride;
   a.out_cost = out_cost;
@@ -688,7 +704,7 @@ void pnec_destroy(pnec_handle *h) {
                     &h->d_out_init, &h->d_out_grad, &h->d_out_jtj, &h->d_ut_mu, &h->d_ut_cov,
                     &h->d_ut_out, &h->d_kp_bv, &h->d_sphere, &h->d_tr_out,
                     &h->d_tr_aux, &h->d_es_mom, &h->d_es_w, &h->d_es_info, &h->d_es_ev,
-                    &h->d_fr_es, &h->d_fr_a, &h->d_fr_b, &h->d_fr_cache, &h->d_fr_flags, &h->d_scf_defer, &h->d_fr_defer};
+                    &h->d_fr_es, &h->d_fr_a, &h->d_fr_b, &h->d_fr_cache, &h->d_fr_flags, &h->d_scf_defer, &h->d_fr_defer, &h->d_scf_spill};
   for (DevBuf *b : bufs) b->release();
   for (int i = 0; i < pnec_handle::kMaxChunks; ++i) {
     if (h->side[i]) cudaStreamDestroy(h->side[i]);
@@ -916,7 +932,10 @@ int pnec_scf_translation_batch(pnec_handle *h, const pnec_batch *batch, double r
     d_t = static_cast<double *>(h->d_tr_out.p);
     d_c = out_cost ? static_cast<double *>(h->d_tr_aux.p) : nullptr;
   }
-  rc = run_scf(h, st.bv, st.max_n, regularization, fibonacci_samples, scf_steps, d_t, 3, d_c, stream);
+  rc = ensure_scf_spill(h, st.bv, st.max_n);
+  if (rc != PNEC_OK) return rc;
+  rc = run_scf(h, st.bv, st.max_n, regularization, fibonacci_samples, scf_steps, d_t, 3, d_c, stream, nullptr,
+               nullptr, nullptr, nullptr, static_cast<double *>(h->d_scf_spill.p));
   if (rc != PNEC_OK) return rc;
   if (host) {
     PNEC_CUDA(cudaMemcpyAsync(out_translations, d_t, static_cast<size_t>(B) * 24, cudaMemcpyDeviceToHost, stream));
@@ -1044,8 +1063,6 @@ int pnec_frame_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_f
   Staged st;
   rc = stage_batch(h, batch, variant, stream, &st);
   if (rc != PNEC_OK) return rc;
-  if (weighted && scf_smem_bytes(st.max_n) + kStaticSmemReserve > h->smem_optin)
-    return fail(PNEC_ERR_UNSUPPORTED, "pnec_frame_solve_batch: the SCF stage keeps a frame pair in shared memory (~3100 correspondences at most)");
   const bool host = batch->memspace == PNEC_MEM_HOST;
   const size_t nb = static_cast<size_t>(B);
   // ---- scratch for the whole batch (allocated before anything is forked: cudaMalloc synchronises)
@@ -1059,7 +1076,10 @@ int pnec_frame_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_f
   if (weighted) {
     rc = ensure_sphere(h, opts->fibonacci_samples);
     if (rc != PNEC_OK) return rc;
+    rc = ensure_scf_spill(h, st.bv, st.max_n);
+    if (rc != PNEC_OK) return rc;
   }
+  double *const d_spill = static_cast<double *>(h->d_scf_spill.p);
   double *o_poses = out->poses, *o_cost = out->cost;
   int32_t *o_status = out->status, *o_iters = out->iterations;
   if (host) {
@@ -1117,7 +1137,8 @@ int pnec_frame_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_f
         sv.poses = nxt;
         if ((rcc = run_scf(h, sv, st.max_n, opts->ceres.regularization, opts->fibonacci_samples, opts->scf_steps,
                            nxt + 4, 7, nullptr, cs, shortcuts ? cache : nullptr, shortcuts ? qsame : nullptr,
-                           shortcuts ? fixed : nullptr, defer)) != PNEC_OK)
+                           shortcuts ? fixed : nullptr, defer,
+                           d_spill ? (st.bv.offsets ? d_spill : d_spill + 9 * c0 * st.bv.n_uniform) : nullptr)) != PNEC_OK)
           return rcc;
         cur = nxt;
       }

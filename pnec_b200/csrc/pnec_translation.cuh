@@ -199,6 +199,8 @@ struct ScfArgs {
   double reg;
   int samples, steps;
   int cap_elems;          // correspondences that fit the dynamic shared memory
+  double *spill;          // [total][9] terms of pairs above cap_elems (HBM / L2 instead of shared
+                          // memory: slower, same arithmetic), or nullptr if every pair fits
   ScfScanCache *cache;    // [B] or nullptr: reuse / record the sphere scan per rotation
   const int *q_same;      // [B] or nullptr: this call's rotation equals the previous round's bit for bit
   int *fixed;             // [B] or nullptr: in: pair already at a fixed point of the iteration (skip);
@@ -305,15 +307,16 @@ __device__ __forceinline__ void scf_pair(const ScfArgs &args, const long long b)
   problem_range(args.bv, b, s, e);
   const int n = static_cast<int>(e - s);
   const double *pose = args.bv.poses + 7 * b;
-  double *terms = dyn_smem;  // [n][9]
+  // [n][9]: shared memory, or this pair's slice of the spill array when it does not fit
+  double *terms = (n <= args.cap_elems || !args.spill) ? dyn_smem : args.spill + 9 * s;
   double *ot = args.out_t + static_cast<long long>(args.out_stride) * b;
   const long long clk0 = clock64();
   if (args.fixed && args.fixed[b]) {  // fixed point of the iteration: the result is already in place
     if (args.dbg && tid == 0) { args.dbg[4 * b] = 0; args.dbg[4 * b + 1] = 0; args.dbg[4 * b + 2] = 0; args.dbg[4 * b + 3] = 0; }
     return;
   }
-  if (n <= 0 || n > args.cap_elems) {
-    // nothing to minimise (or a pair beyond the shared-memory capacity, rejected on the host)
+  if (n <= 0 || (n > args.cap_elems && !args.spill)) {
+    // nothing to minimise (a pair beyond the shared-memory capacity without a spill array is rejected on the host)
     if (tid == 0) { ot[0] = pose[4]; ot[1] = pose[5]; ot[2] = pose[6]; if (args.out_cost) args.out_cost[b] = 0.0; }
     return;
   }

@@ -226,3 +226,22 @@ def test_frame_solve_shortcuts_are_exact(handle):
         del os.environ["PNEC_B200_SCF_DEFER"]
     np.testing.assert_array_equal(fast.poses, plain.poses)
     np.testing.assert_array_equal(fast.iterations, plain.iterations)
+
+
+def test_large_pairs_spill_to_device_memory(handle):
+    """Pairs beyond the shared-memory capacity of the SCF stage (~3000 correspondences)."""
+    counts = np.array([3600, 200, 4100], dtype=np.int64)
+    batch = syn.make_batch(len(counts), 0, seed=91, counts=counts)
+    for b in range(len(counts)):
+        f1, f2, ct, _ = batch.problem(b)
+        ref_t, ref_c = oracle.scf_translation(f1, f2, ct, batch.init_poses[b])
+        t, c = handle.scf_translation_batch(f1, f2, ct, batch.init_poses[b:b + 1], n_per_problem=len(f1))
+        assert direction_angle(t[0], ref_t) <= DIR_TOL
+        assert c[0] == pytest.approx(ref_c, rel=1e-9)
+    ref, ref_es = oracle.frame_solve_batch(batch.bvs_host, batch.bvs_target, batch.covs_target, batch.init_poses,
+                                           oracle.default_frame_opts(weighted_iterations=3), offsets=batch.offsets,
+                                           num_threads=oracle.max_threads())
+    res = handle.frame_solve_batch(batch.bvs_host, batch.bvs_target, batch.covs_target, batch.init_poses,
+                                   api.default_frame_opts(weighted_iterations=3), offsets=batch.offsets)
+    r, t = max_pose_diff(res.poses, ref)
+    assert r <= ROT_TOL and t <= DIR_TOL, (r, t)
