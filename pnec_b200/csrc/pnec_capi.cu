@@ -131,10 +131,9 @@ int validate_batch(const pnec_batch *b, int variant, bool need_poses) {
   return PNEC_OK;
 }
 
-// Builds the device view of a batch: copies H2D for HOST batches, always copies
-// the (host) offsets.  Everything is enqueued on `stream`.
-int stage_batch(pnec_handle *h, const pnec_batch *b, int variant, cudaStream_t stream,
-                Staged *out) {
+// Device view of a batch.  HOST batches: device buffers are (re)allocated and the view points into
+// them, but nothing is copied yet (stage_copy).  The (host) offsets are always copied.
+int stage_alloc(pnec_handle *h, const pnec_batch *b, int variant, cudaStream_t stream, Staged *out) {
   const long long B = b->num_problems;
   long long total, max_n = 0;
   if (b->offsets) {
@@ -146,10 +145,8 @@ int stage_batch(pnec_handle *h, const pnec_batch *b, int variant, cudaStream_t s
   }
   BatchView bv{};
   bv.num_problems = B;
-  bv.total = b->offsets ? b->offsets[B] : total;
+  bv.total = total;
   bv.n_uniform = b->offsets ? 0 : b->n_per_problem;
-  const long long base = b->offsets ? b->offsets[0] : 0;
-  (void)base;
   if (b->offsets) {
     PNEC_CUDA(h->d_off.ensure(sizeof(long long) * (B + 1)));
     PNEC_CUDA(cudaMemcpyAsync(h->d_off.p, b->offsets, sizeof(long long) * (B + 1),
@@ -159,27 +156,12 @@ int stage_batch(pnec_handle *h, const pnec_batch *b, int variant, cudaStream_t s
   const bool need_ct = variant != PNEC_VARIANT_NEC;
   const bool need_ch = variant == PNEC_VARIANT_SYMMETRIC;
   if (b->memspace == PNEC_MEM_HOST) {
-    const size_t nel = static_cast<size_t>(bv.total);
+    const size_t nel = static_cast<size_t>(total);
     PNEC_CUDA(h->d_f1.ensure(nel * 24));
     PNEC_CUDA(h->d_f2.ensure(nel * 24));
     PNEC_CUDA(h->d_poses.ensure(static_cast<size_t>(B) * 56));
-    if (nel) {
-      PNEC_CUDA(cudaMemcpyAsync(h->d_f1.p, b->bvs_host, nel * 24, cudaMemcpyHostToDevice, stream));
-      PNEC_CUDA(cudaMemcpyAsync(h->d_f2.p, b->bvs_target, nel * 24, cudaMemcpyHostToDevice, stream));
-    }
-    if (need_ct) {
-      PNEC_CUDA(h->d_ct.ensure(nel * 72));
-      if (nel)
-        PNEC_CUDA(cudaMemcpyAsync(h->d_ct.p, b->covs_target, nel * 72, cudaMemcpyHostToDevice, stream));
-    }
-    if (need_ch) {
-      PNEC_CUDA(h->d_ch.ensure(nel * 72));
-      if (nel)
-        PNEC_CUDA(cudaMemcpyAsync(h->d_ch.p, b->covs_host, nel * 72, cudaMemcpyHostToDevice, stream));
-    }
-    if (B && b->poses)
-      PNEC_CUDA(cudaMemcpyAsync(h->d_poses.p, b->poses, static_cast<size_t>(B) * 56,
-                                cudaMemcpyHostToDevice, stream));
+    if (need_ct) PNEC_CUDA(h->d_ct.ensure(nel * 72));
+    if (need_ch) PNEC_CUDA(h->d_ch.ensure(nel * 72));
     bv.f1 = static_cast<const double *>(h->d_f1.p);
     bv.f2 = static_cast<const double *>(h->d_f2.p);
     bv.ct = need_ct ? static_cast<const double *>(h->d_ct.p) : nullptr;
@@ -195,6 +177,37 @@ int stage_batch(pnec_handle *h, const pnec_batch *b, int variant, cudaStream_t s
   out->bv = bv;
   out->max_n = max_n;
   return PNEC_OK;
+}
+
+// H2D of pairs [p0, p1) of a HOST batch into the buffers of stage_alloc (no-op for DEVICE batches).
+int stage_copy(pnec_handle *h, const pnec_batch *b, int variant, long long p0, long long p1,
+               cudaStream_t stream) {
+  if (b->memspace != PNEC_MEM_HOST || p1 <= p0) return PNEC_OK;
+  const long long e0 = b->offsets ? b->offsets[p0] : p0 * b->n_per_problem;
+  const long long e1 = b->offsets ? b->offsets[p1] : p1 * b->n_per_problem;
+  const size_t nel = static_cast<size_t>(e1 - e0);
+  auto at = [](void *base, long long bytes) { return static_cast<char *>(base) + bytes; };
+  if (nel) {
+    PNEC_CUDA(cudaMemcpyAsync(at(h->d_f1.p, e0 * 24), b->bvs_host + 3 * e0, nel * 24, cudaMemcpyHostToDevice, stream));
+    PNEC_CUDA(cudaMemcpyAsync(at(h->d_f2.p, e0 * 24), b->bvs_target + 3 * e0, nel * 24, cudaMemcpyHostToDevice, stream));
+    if (variant != PNEC_VARIANT_NEC)
+      PNEC_CUDA(cudaMemcpyAsync(at(h->d_ct.p, e0 * 72), b->covs_target + 9 * e0, nel * 72, cudaMemcpyHostToDevice, stream));
+    if (variant == PNEC_VARIANT_SYMMETRIC)
+      PNEC_CUDA(cudaMemcpyAsync(at(h->d_ch.p, e0 * 72), b->covs_host + 9 * e0, nel * 72, cudaMemcpyHostToDevice, stream));
+  }
+  if (b->poses)
+    PNEC_CUDA(cudaMemcpyAsync(at(h->d_poses.p, p0 * 56), b->poses + 7 * p0, static_cast<size_t>(p1 - p0) * 56,
+                              cudaMemcpyHostToDevice, stream));
+  return PNEC_OK;
+}
+
+// Builds the device view of a batch: copies H2D for HOST batches, always copies
+// the (host) offsets.  Everything is enqueued on `stream`.
+int stage_batch(pnec_handle *h, const pnec_batch *b, int variant, cudaStream_t stream,
+                Staged *out) {
+  int rc = stage_alloc(h, b, variant, stream, out);
+  if (rc != PNEC_OK) return rc;
+  return stage_copy(h, b, variant, 0, b->num_problems, stream);
 }
 
 bool bulk_ok(const BatchView &bv) {
@@ -728,13 +741,77 @@ int pnec_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_solver_
   PNEC_CUDA(cudaSetDevice(h->device));
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
   Staged st;
-  rc = stage_batch(h, batch, opts->variant, stream, &st);
-  if (rc != PNEC_OK) return rc;
   const bool host = batch->memspace == PNEC_MEM_HOST;
-  rc = run_solve(h, st.bv, st.max_n, *opts, host, out->poses, out->status, out->iterations, out->cost,
-                 out->initial_cost, stream);
+  // HOST batches of some size are cut into chunks, each on its own stream: H2D of chunk k + 1 runs
+  // under the solve of chunk k and the D2H of its results (the copies are the bulk of such a call).
+  int chunks = 1;
+  if (host) {
+    const long long total = batch->offsets ? batch->offsets[B] : B * batch->n_per_problem;
+    chunks = env_int("PNEC_B200_H2D_CHUNKS", 0);
+    if (chunks <= 0) chunks = (total * bytes_per_corr(opts->variant) >= (64ll << 20) && B >= 64) ? 4 : 1;
+    chunks = static_cast<int>(std::min<long long>(std::min(chunks, pnec_handle::kMaxChunks), B));
+  }
+  if (chunks <= 1) {
+    rc = stage_batch(h, batch, opts->variant, stream, &st);
+    if (rc != PNEC_OK) return rc;
+    rc = run_solve(h, st.bv, st.max_n, *opts, host, out->poses, out->status, out->iterations, out->cost,
+                   out->initial_cost, stream);
+    if (rc != PNEC_OK) return rc;
+    if (host) PNEC_CUDA(cudaStreamSynchronize(stream));
+    return PNEC_OK;
+  }
+  rc = stage_alloc(h, batch, opts->variant, stream, &st);
   if (rc != PNEC_OK) return rc;
-  if (host) PNEC_CUDA(cudaStreamSynchronize(stream));
+  const size_t nb = static_cast<size_t>(B);
+  PNEC_CUDA(h->d_out_poses.ensure(nb * 56));
+  PNEC_CUDA(h->d_out_status.ensure(nb * 4));
+  PNEC_CUDA(h->d_out_iters.ensure(nb * 4));
+  PNEC_CUDA(h->d_out_cost.ensure(nb * 8));
+  PNEC_CUDA(h->d_out_init.ensure(nb * 8));
+  double *d_poses = static_cast<double *>(h->d_out_poses.p);
+  int32_t *d_status = out->status ? static_cast<int32_t *>(h->d_out_status.p) : nullptr;
+  int32_t *d_iters = out->iterations ? static_cast<int32_t *>(h->d_out_iters.p) : nullptr;
+  double *d_cost = out->cost ? static_cast<double *>(h->d_out_cost.p) : nullptr;
+  double *d_init = out->initial_cost ? static_cast<double *>(h->d_out_init.p) : nullptr;
+  if (!h->ev_fork) PNEC_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  PNEC_CUDA(cudaEventRecord(h->ev_fork, stream));  // after the copy of the offsets
+  for (int c = 0; c < chunks; ++c) {
+    if (!h->side[c]) PNEC_CUDA(cudaStreamCreateWithFlags(&h->side[c], cudaStreamNonBlocking));
+    if (!h->ev_join[c]) PNEC_CUDA(cudaEventCreateWithFlags(&h->ev_join[c], cudaEventDisableTiming));
+    cudaStream_t cs = h->side[c];
+    PNEC_CUDA(cudaStreamWaitEvent(cs, h->ev_fork, 0));
+    // chunk boundaries balance correspondences for ragged batches
+    long long p0, p1;
+    if (batch->offsets) {
+      const long long total = batch->offsets[B];
+      auto first_at = [&](long long target) {
+        return std::lower_bound(batch->offsets, batch->offsets + B, target) - batch->offsets;
+      };
+      p0 = c == 0 ? 0 : first_at(total * c / chunks);
+      p1 = c + 1 == chunks ? B : first_at(total * (c + 1) / chunks);
+    } else {
+      p0 = B * c / chunks;
+      p1 = B * (c + 1) / chunks;
+    }
+    if (p1 > p0) {
+      rc = stage_copy(h, batch, opts->variant, p0, p1, cs);
+      if (rc != PNEC_OK) return rc;
+      const BatchView bv = sub_view(st.bv, p0, p1 - p0);
+      rc = run_solve(h, bv, st.max_n, *opts, false, d_poses + 7 * p0, d_status ? d_status + p0 : nullptr,
+                     d_iters ? d_iters + p0 : nullptr, d_cost ? d_cost + p0 : nullptr,
+                     d_init ? d_init + p0 : nullptr, cs);
+      if (rc != PNEC_OK) return rc;
+      const size_t cnt = static_cast<size_t>(p1 - p0);
+      PNEC_CUDA(cudaMemcpyAsync(out->poses + 7 * p0, d_poses + 7 * p0, cnt * 56, cudaMemcpyDeviceToHost, cs));
+      if (d_status) PNEC_CUDA(cudaMemcpyAsync(out->status + p0, d_status + p0, cnt * 4, cudaMemcpyDeviceToHost, cs));
+      if (d_iters) PNEC_CUDA(cudaMemcpyAsync(out->iterations + p0, d_iters + p0, cnt * 4, cudaMemcpyDeviceToHost, cs));
+      if (d_cost) PNEC_CUDA(cudaMemcpyAsync(out->cost + p0, d_cost + p0, cnt * 8, cudaMemcpyDeviceToHost, cs));
+      if (d_init) PNEC_CUDA(cudaMemcpyAsync(out->initial_cost + p0, d_init + p0, cnt * 8, cudaMemcpyDeviceToHost, cs));
+    }
+    PNEC_CUDA(cudaEventRecord(h->ev_join[c], cs));
+  }
+  for (int c = 0; c < chunks; ++c) PNEC_CUDA(cudaStreamWaitEvent(stream, h->ev_join[c], 0));
+  PNEC_CUDA(cudaStreamSynchronize(stream));
   return PNEC_OK;
 }
 
