@@ -724,6 +724,31 @@ class PNEC {
       throw std::runtime_error(std::string("pnec_solve_batch: ") + pnec_last_error());
   }
 
+  // Batched Solve(): B frame pairs per call, flat C-ABI layout, host memory.
+  void SolveBatch(std::size_t num_problems, const int64_t *offsets, std::size_t n_per_problem, const double *bvs1,
+                  const double *bvs2, const double *projected_covariances, const SE3 *initial_poses, SE3 *results,
+                  SE3 *eigensolver_results = nullptr, int32_t *status = nullptr, int32_t *iterations = nullptr) {
+    if (options_.use_ransac_)
+      throw std::logic_error("pnec_b200: PNEC::SolveBatch with use_ransac_=true is not implemented");
+    const pnec_frame_opts fo = FrameOpts();
+    pnec_batch b{};
+    b.num_problems = static_cast<int64_t>(num_problems);
+    b.n_per_problem = static_cast<int64_t>(n_per_problem);
+    b.offsets = offsets;
+    b.memspace = PNEC_MEM_HOST;
+    b.bvs_host = bvs1;
+    b.bvs_target = bvs2;
+    b.covs_target = projected_covariances;
+    b.poses = reinterpret_cast<const double *>(initial_poses);
+    pnec_frame_out o{};
+    o.poses = reinterpret_cast<double *>(results);
+    o.es_poses = reinterpret_cast<double *>(eigensolver_results);
+    o.status = status;
+    o.iterations = iterations;
+    if (pnec_frame_solve_batch(detail::Handle(), &b, &fo, &o, nullptr) != PNEC_OK)
+      throw std::runtime_error(std::string("pnec_frame_solve_batch: ") + pnec_last_error());
+  }
+
   int LastStatus() const { return last_status_; }
   int LastIterations() const { return last_iterations_; }
   // ES_solution of the last Solve() (pnec.cc:86)

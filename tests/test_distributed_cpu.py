@@ -16,7 +16,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, ragged, out_dir):
+def _worker(rank, world, port, ragged, out_dir, frame=False):
     import sys
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -40,6 +40,22 @@ def _worker(rank, world, port, ragged, out_dir):
             return (torch.from_numpy(p), torch.from_numpy(info["status"].copy()),
                     torch.from_numpy(info["iterations"].copy()))
 
+        if frame:
+            # the whole frame solve (PNEC::Solve) shards the same way: pairs are independent
+            fo = oracle.default_frame_opts(weighted_iterations=3)
+
+            def frame_fn(f1, f2, ct, ch, poses, offsets=None, n_per_problem=None):
+                p, es = oracle.frame_solve_batch(f1, f2, ct, poses, fo, offsets=offsets, n_per_problem=n_per_problem)
+                z = torch.zeros(p.shape[0], dtype=torch.int32)
+                return torch.from_numpy(p), torch.from_numpy(es), z
+
+            poses, es, _ = distributed.solve_sharded(
+                frame_fn, B, N, b.offsets, b.bvs_host, b.bvs_target, b.covs_target, None, b.init_poses)
+            ref, ref_es = oracle.frame_solve_batch(b.bvs_host, b.bvs_target, b.covs_target, b.init_poses, fo,
+                                                   offsets=b.offsets, n_per_problem=N)
+            assert np.array_equal(poses.numpy(), ref) and np.array_equal(es.numpy(), ref_es)
+            open(os.path.join(out_dir, f"ok{rank}"), "w").close()
+            return
         poses, status, iters = distributed.solve_sharded(
             solve_fn, B, N, b.offsets, b.bvs_host, b.bvs_target, b.covs_target, None, b.init_poses)
         ref, info = oracle.solve_batch(b.bvs_host, b.bvs_target, b.covs_target, None, b.init_poses,
@@ -57,4 +73,10 @@ def _worker(rank, world, port, ragged, out_dir):
 def test_sharded_solve_matches_single_process(tmp_path, ragged):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), ragged, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
+
+
+def test_sharded_frame_solve_matches_single_process(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), True, str(tmp_path), True), nprocs=world, join=True)
     assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
