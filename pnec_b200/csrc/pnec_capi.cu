@@ -86,8 +86,11 @@ struct pnec_handle {
   DevBuf d_fr_defer;              // the same per chunk of a frame solve: (4 + B) ints
   DevBuf d_scf_spill;             // [total][9] SCF terms of pairs that do not fit shared memory
   static constexpr int kMaxChunks = 8;
-  cudaStream_t side[kMaxChunks] = {};
-  cudaEvent_t ev_fork = nullptr, ev_join[kMaxChunks] = {};
+  static constexpr int kMaxRounds = 64;
+  cudaStream_t side[kMaxChunks] = {}, lm_side[kMaxChunks] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[kMaxChunks] = {}, ev_es[kMaxChunks] = {};
+  cudaEvent_t ev_round[kMaxChunks][kMaxRounds] = {};
+  DevBuf d_fr_rounds;             // poses of every weighted round: [rounds][B][7]
   int sphere_samples = -1;
   std::mutex mu;
 };
@@ -513,7 +516,8 @@ int ensure_scf_spill(pnec_handle *h, const BatchView &bv, long long max_n) {
 int run_scf(pnec_handle *h, const BatchView &bv, long long max_n, double reg, int samples, int steps,
             double *out_t, int out_stride, double *out_cost, cudaStream_t stream,
             ScfScanCache *cache = nullptr, const int *q_same = nullptr, int *fixed = nullptr,
-            int *defer_buf = nullptr /* 4 + B ints, else the handle's */, double *spill = nullptr) {
+            int *defer_buf = nullptr /* 4 + B ints, else the handle's */, double *spill = nullptr,
+            const double *prev_poses = nullptr) {
   const size_t dyn = scf_smem_bytes(h, max_n);
   const bool fits = dyn >= static_cast<size_t>(std::max<long long>(max_n, 1)) * 72;
   if (!fits && !spill) return fail(PNEC_ERR_INVALID_ARGUMENT, "internal: SCF spill array missing");
@@ -533,6 +537,7 @@ int run_scf(pnec_handle *h, const BatchView &bv, long long max_n, double reg, in
   a.cache = cache;
   a.q_same = q_same;
   a.fixed = fixed;
+  a.prev_poses = prev_poses;
   a.dbg = nullptr;
   static long long *dbg_buf = nullptr;
   const bool debug = env_int("PNEC_B200_SCF_DEBUG", 0) != 0;
@@ -622,7 +627,8 @@ int run_es_moments(pnec_handle *h, const BatchView &bv, bool weighted, double re
 // opengv eigensolver_main with the parameters opengv sets (ftol 5e-5, xtol 10 eps, maxfev 100;
 // resetParameters(): factor 100, gtol 0, epsfcn 0)
 int run_es_lm(pnec_handle *h, long long B, const double *d_mom, const double *d_poses_in, double *d_poses_out,
-              int *d_info, double *d_ev, cudaStream_t stream, const int *fixed = nullptr, int *q_same = nullptr) {
+              int *d_info, double *d_ev, cudaStream_t stream, const int *fixed = nullptr, int *q_same = nullptr,
+              bool copy_translation = true) {
   EsLmArgs a{};
   a.moments = d_mom;
   a.poses_in = d_poses_in;
@@ -632,6 +638,7 @@ int run_es_lm(pnec_handle *h, long long B, const double *d_mom, const double *d_
   a.out_ev = d_ev;
   a.fixed = fixed;
   a.q_same = q_same;
+  a.copy_translation = copy_translation ? 1 : 0;
   a.num_problems = B;
   a.ftol = 0.00005;
   a.xtol = 1.0e1 * DBL_EPSILON;
@@ -721,8 +728,13 @@ void pnec_destroy(pnec_handle *h) {
   for (DevBuf *b : bufs) b->release();
   for (int i = 0; i < pnec_handle::kMaxChunks; ++i) {
     if (h->side[i]) cudaStreamDestroy(h->side[i]);
+    if (h->lm_side[i]) cudaStreamDestroy(h->lm_side[i]);
     if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+    if (h->ev_es[i]) cudaEventDestroy(h->ev_es[i]);
+    for (int r = 0; r < pnec_handle::kMaxRounds; ++r)
+      if (h->ev_round[i][r]) cudaEventDestroy(h->ev_round[i][r]);
   }
+  h->d_fr_rounds.release();
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   delete h;
 }
@@ -1150,6 +1162,10 @@ int pnec_frame_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_f
   PNEC_CUDA(h->d_fr_cache.ensure(nb * sizeof(ScfScanCache)));
   PNEC_CUDA(h->d_fr_flags.ensure(nb * 2 * sizeof(int)));
   PNEC_CUDA(h->d_fr_defer.ensure(sizeof(int) * (4 * pnec_handle::kMaxChunks + nb)));
+  const int weighted_rounds = weighted ? opts->weighted_iterations - 1 : 0;
+  if (weighted) PNEC_CUDA(h->d_fr_rounds.ensure(nb * 56 * static_cast<size_t>(weighted_rounds)));
+  double *const d_rounds = static_cast<double *>(h->d_fr_rounds.p);
+  const bool lm_ahead = weighted_rounds <= pnec_handle::kMaxRounds && !env_int("PNEC_B200_NO_LM_AHEAD", 0);
   if (weighted) {
     rc = ensure_sphere(h, opts->fibonacci_samples);
     if (rc != PNEC_OK) return rc;
@@ -1171,7 +1187,7 @@ int pnec_frame_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_f
   }
   double *const d_mom = static_cast<double *>(h->d_es_mom.p);
   double *const d_es = (!host && out->es_poses) ? out->es_poses : static_cast<double *>(h->d_fr_es.p);
-  double *const d_a = static_cast<double *>(h->d_fr_a.p), *const d_b = static_cast<double *>(h->d_fr_b.p);
+  double *const d_a = static_cast<double *>(h->d_fr_a.p);
   ScfScanCache *const d_cache = static_cast<ScfScanCache *>(h->d_fr_cache.p);
   int *const d_qsame = static_cast<int *>(h->d_fr_flags.p), *const d_fixed = d_qsame + B;
   int *const d_defer = static_cast<int *>(h->d_fr_defer.p);
@@ -1180,7 +1196,7 @@ int pnec_frame_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_f
   // The stages of one chunk of frame pairs, back to back on one stream.
   auto run_chunk = [&](long long c0, long long cnt, int chunk, cudaStream_t cs) -> int {
     const BatchView bv = sub_view(st.bv, c0, cnt);
-    double *mom = d_mom + kEsMom * c0, *es = d_es + 7 * c0, *pa = d_a + 7 * c0, *pb = d_b + 7 * c0;
+    double *mom = d_mom + kEsMom * c0, *es = d_es + 7 * c0, *pa = d_a + 7 * c0;
     int rcc;
     // 1. PNEC::Eigensolver: rotation, then TranslationFromM(ComposeM(bvs1, bvs2, rotation))
     if ((rcc = run_es_moments(h, bv, false, 0.0, mom, cs)) != PNEC_OK) return rcc;
@@ -1197,28 +1213,65 @@ int pnec_frame_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_f
       //  * a rotation that repeats bit for bit reuses its sphere scan (ScfScanCache), and
       //  * a pair whose whole pose repeats has reached a fixed point: later rounds are skipped.
       // Both give exactly what recomputing would.
+      //
+      // The rotation of round k depends on the rotation of round k - 1 only (the moments are
+      // constant), not on any translation, so the chain of rotation solves runs ahead on its own
+      // stream and the SCF rounds follow it: round k's SCF overlaps round k + 1's rotation solve.
       ScfScanCache *cache = d_cache + c0;
-      int *qsame = d_qsame + c0, *fixed = d_fixed + c0;
+      int *rot_same = d_qsame + c0, *fixed = d_fixed + c0;
       int *defer = d_defer + (4 * chunk + c0);  // chunk k: 4 header ints, then its list (disjoint regions)
       PNEC_CUDA(cudaMemsetAsync(cache, 0, static_cast<size_t>(cnt) * sizeof(ScfScanCache), cs));
-      PNEC_CUDA(cudaMemsetAsync(qsame, 0, static_cast<size_t>(cnt) * sizeof(int), cs));
+      PNEC_CUDA(cudaMemsetAsync(rot_same, 0, static_cast<size_t>(cnt) * sizeof(int), cs));
       PNEC_CUDA(cudaMemsetAsync(fixed, 0, static_cast<size_t>(cnt) * sizeof(int), cs));
-      const double *cur = es;
-      for (int it = 0; it + 1 < opts->weighted_iterations; ++it) {
-        double *nxt = (it & 1) ? pb : pa;
-        // rotation; translation passed through
-        if ((rcc = run_es_lm(h, cnt, mom, cur, nxt, nullptr, nullptr, cs, shortcuts ? fixed : nullptr,
-                             shortcuts ? qsame : nullptr)) != PNEC_OK)
-          return rcc;
-        BatchView sv = bv;
-        sv.poses = nxt;
-        if ((rcc = run_scf(h, sv, st.max_n, opts->ceres.regularization, opts->fibonacci_samples, opts->scf_steps,
-                           nxt + 4, 7, nullptr, cs, shortcuts ? cache : nullptr, shortcuts ? qsame : nullptr,
-                           shortcuts ? fixed : nullptr, defer,
-                           d_spill ? (st.bv.offsets ? d_spill : d_spill + 9 * c0 * st.bv.n_uniform) : nullptr)) != PNEC_OK)
-          return rcc;
-        cur = nxt;
+      const int rounds = opts->weighted_iterations - 1;
+      auto round_poses = [&](int k) {  // k = 0: the eigensolver pose; k >= 1: round k
+        return k == 0 ? es : d_rounds + 7 * (static_cast<long long>(k - 1) * B + c0);
+      };
+      cudaStream_t ls = cs;
+      if (lm_ahead) {
+        if (!h->lm_side[chunk]) {
+          // small kernels on the critical path: dispatch their blocks ahead of queued SCF blocks
+          int lo = 0, hi = 0;
+          PNEC_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+          PNEC_CUDA(cudaStreamCreateWithPriority(&h->lm_side[chunk], cudaStreamNonBlocking, hi));
+        }
+        if (!h->ev_es[chunk]) PNEC_CUDA(cudaEventCreateWithFlags(&h->ev_es[chunk], cudaEventDisableTiming));
+        ls = h->lm_side[chunk];
+        PNEC_CUDA(cudaEventRecord(h->ev_es[chunk], cs));
+        PNEC_CUDA(cudaStreamWaitEvent(ls, h->ev_es[chunk], 0));
       }
+      auto run_lm_round = [&](int k) -> int {
+        // a rotation that repeats once repeats forever: rot_same is both the skip flag and the result
+        return run_es_lm(h, cnt, mom, round_poses(k - 1), round_poses(k), nullptr, nullptr, ls,
+                         shortcuts ? rot_same : nullptr, shortcuts ? rot_same : nullptr, false);
+      };
+      auto run_scf_round = [&](int k) -> int {
+        BatchView sv = bv;
+        sv.poses = round_poses(k);
+        return run_scf(h, sv, st.max_n, opts->ceres.regularization, opts->fibonacci_samples, opts->scf_steps,
+                       round_poses(k) + 4, 7, nullptr, cs, shortcuts ? cache : nullptr, nullptr,
+                       shortcuts ? fixed : nullptr, defer,
+                       d_spill ? (st.bv.offsets ? d_spill : d_spill + 9 * c0 * st.bv.n_uniform) : nullptr,
+                       round_poses(k - 1));
+      };
+      if (lm_ahead) {
+        for (int k = 1; k <= rounds; ++k) {
+          if ((rcc = run_lm_round(k)) != PNEC_OK) return rcc;
+          cudaEvent_t &evk = h->ev_round[chunk][k - 1];
+          if (!evk) PNEC_CUDA(cudaEventCreateWithFlags(&evk, cudaEventDisableTiming));
+          PNEC_CUDA(cudaEventRecord(evk, ls));
+        }
+        for (int k = 1; k <= rounds; ++k) {
+          PNEC_CUDA(cudaStreamWaitEvent(cs, h->ev_round[chunk][k - 1], 0));
+          if ((rcc = run_scf_round(k)) != PNEC_OK) return rcc;
+        }
+      } else {
+        for (int k = 1; k <= rounds; ++k) {
+          if ((rcc = run_lm_round(k)) != PNEC_OK) return rcc;
+          if ((rcc = run_scf_round(k)) != PNEC_OK) return rcc;
+        }
+      }
+      const double *cur = round_poses(rounds);
       init = cur;
     } else if (!nec && opts->weighted_iterations == 0) {
       normalize_poses_kernel<<<static_cast<unsigned>((cnt + 127) / 128), 128, 0, cs>>>(bv.poses, pa, cnt);

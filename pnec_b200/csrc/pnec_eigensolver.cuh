@@ -454,6 +454,9 @@ struct EsLmArgs {
   double *out_ev;          // [B] lambda_min of the reduced M at the result, or nullptr
   const int *fixed;        // [B] or nullptr: pairs to pass through unchanged (fixed point reached)
   int *q_same;             // [B] or nullptr: out, result quaternion == input quaternion bit for bit
+                           // (may alias `fixed`: a rotation that repeats once repeats forever, because the
+                           // next call would start from the same bits)
+  int copy_translation;    // pass poses_in[4..6] through to poses_out[4..6]
   long long num_problems;
   double ftol, xtol, gtol, factor;
   int maxfev;
@@ -655,7 +658,8 @@ __global__ void __launch_bounds__(kEsLmThreads) es_lm_kernel(const __grid_consta
   if (passthrough && sub == 0) {
     double *po = args.poses_out + 7 * b;
 #pragma unroll
-    for (int k = 0; k < 7; ++k) po[k] = pin[k];
+    for (int k = 0; k < 4; ++k) po[k] = pin[k];
+    if (args.copy_translation) { po[4] = pin[4]; po[5] = pin[5]; po[6] = pin[6]; }
     if (args.q_same) args.q_same[b] = 1;
   }
   double ev_final = 0.0;
@@ -667,7 +671,7 @@ __global__ void __launch_bounds__(kEsLmThreads) es_lm_kernel(const __grid_consta
     double *po = args.poses_out + 7 * b;
     const double sc = 1.0 / sqrt(1.0 + x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
     po[0] = x[0] * sc; po[1] = x[1] * sc; po[2] = x[2] * sc; po[3] = sc;
-    po[4] = pin[4]; po[5] = pin[5]; po[6] = pin[6];
+    if (args.copy_translation) { po[4] = pin[4]; po[5] = pin[5]; po[6] = pin[6]; }
     if (args.q_same)
       args.q_same[b] = __double_as_longlong(po[0]) == __double_as_longlong(pin[0]) &&
                        __double_as_longlong(po[1]) == __double_as_longlong(pin[1]) &&

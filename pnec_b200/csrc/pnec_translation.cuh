@@ -203,6 +203,10 @@ struct ScfArgs {
                           // memory: slower, same arithmetic), or nullptr if every pair fits
   ScfScanCache *cache;    // [B] or nullptr: reuse / record the sphere scan per rotation
   const int *q_same;      // [B] or nullptr: this call's rotation equals the previous round's bit for bit
+  const double *prev_poses;  // [B][7] or nullptr: the previous round's poses.  When given, the start
+                          // translation is taken from THEM (bv.poses then only supplies the rotation),
+                          // q_same is decided by comparing the two quaternions, and a pair at a fixed
+                          // point copies its translation over instead of leaving the output untouched
   int *fixed;             // [B] or nullptr: in: pair already at a fixed point of the iteration (skip);
                           //     out: set when q_same and the translation did not move either
   // Two passes: the first (4 warps per pair) hands pairs whose scan cannot prune (flat cost
@@ -311,13 +315,17 @@ __device__ __forceinline__ void scf_pair(const ScfArgs &args, const long long b)
   double *terms = (n <= args.cap_elems || !args.spill) ? dyn_smem : args.spill + 9 * s;
   double *ot = args.out_t + static_cast<long long>(args.out_stride) * b;
   const long long clk0 = clock64();
-  if (args.fixed && args.fixed[b]) {  // fixed point of the iteration: the result is already in place
-    if (args.dbg && tid == 0) { args.dbg[4 * b] = 0; args.dbg[4 * b + 1] = 0; args.dbg[4 * b + 2] = 0; args.dbg[4 * b + 3] = 0; }
+  const double *tsrc = args.prev_poses ? args.prev_poses + 7 * b + 4 : pose + 4;  // start translation
+  if (args.fixed && args.fixed[b]) {  // fixed point of the iteration: the result is the previous round's
+    if (tid == 0) {
+      if (args.prev_poses) { ot[0] = tsrc[0]; ot[1] = tsrc[1]; ot[2] = tsrc[2]; }
+      if (args.dbg) { args.dbg[4 * b] = 0; args.dbg[4 * b + 1] = 0; args.dbg[4 * b + 2] = 0; args.dbg[4 * b + 3] = 0; }
+    }
     return;
   }
   if (n <= 0 || (n > args.cap_elems && !args.spill)) {
     // nothing to minimise (a pair beyond the shared-memory capacity without a spill array is rejected on the host)
-    if (tid == 0) { ot[0] = pose[4]; ot[1] = pose[5]; ot[2] = pose[6]; if (args.out_cost) args.out_cost[b] = 0.0; }
+    if (tid == 0) { ot[0] = tsrc[0]; ot[1] = tsrc[1]; ot[2] = tsrc[2]; if (args.out_cost) args.out_cost[b] = 0.0; }
     return;
   }
   double R[9];
@@ -346,7 +354,7 @@ __device__ __forceinline__ void scf_pair(const ScfArgs &args, const long long b)
   //   2. survivors are completed one per warp, tightening the bound as they finish.
   // The set of completed candidates depends on timing, the minimum and its index do not: pruning
   // is strict (ties are always evaluated) and every bound is the complete cost of a real candidate.
-  const double t0[3] = {pose[4], pose[5], pose[6]};
+  const double t0[3] = {tsrc[0], tsrc[1], tsrc[2]};
   double cost0;
   {
     const double txx = t0[0] * t0[0], txy = 2.0 * t0[0] * t0[1], txz = 2.0 * t0[0] * t0[2];
@@ -566,7 +574,15 @@ __device__ __forceinline__ void scf_pair(const ScfArgs &args, const long long b)
     }
   }
   if (tid == 0) {
-    if (args.fixed && args.q_same && args.q_same[b] &&
+    bool q_same = args.q_same && args.q_same[b];
+    if (args.prev_poses) {
+      const double *pq = args.prev_poses + 7 * b;
+      q_same = __double_as_longlong(pq[0]) == __double_as_longlong(pose[0]) &&
+               __double_as_longlong(pq[1]) == __double_as_longlong(pose[1]) &&
+               __double_as_longlong(pq[2]) == __double_as_longlong(pose[2]) &&
+               __double_as_longlong(pq[3]) == __double_as_longlong(pose[3]);
+    }
+    if (args.fixed && q_same &&
         __double_as_longlong(s_t[0]) == __double_as_longlong(t0[0]) &&
         __double_as_longlong(s_t[1]) == __double_as_longlong(t0[1]) &&
         __double_as_longlong(s_t[2]) == __double_as_longlong(t0[2]))
