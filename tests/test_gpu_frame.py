@@ -245,3 +245,22 @@ def test_large_pairs_spill_to_device_memory(handle):
                                    api.default_frame_opts(weighted_iterations=3), offsets=batch.offsets)
     r, t = max_pose_diff(res.poses, ref)
     assert r <= ROT_TOL and t <= DIR_TOL, (r, t)
+
+
+def test_frame_solve_ragged_device_batch(handle):
+    """KITTI-shaped ragged batch (C4 of BASELINE.json in miniature) with device pointers."""
+    counts = np.array([310, 97, 512, 1033, 64, 200, 777, 45], dtype=np.int64)
+    batch = syn.make_batch(len(counts), 0, seed=93, camera=syn.PINHOLE, counts=counts)
+    fo = dict(weighted_iterations=4, max_num_iterations=20)
+    ref, ref_es = oracle.frame_solve_batch(batch.bvs_host, batch.bvs_target, batch.covs_target, batch.init_poses,
+                                           oracle.default_frame_opts(**fo), offsets=batch.offsets,
+                                           num_threads=oracle.max_threads())
+    p = perturbed(batch)
+    ref_p, _ = oracle.frame_solve_batch(p.bvs_host, p.bvs_target, p.covs_target, p.init_poses,
+                                        oracle.default_frame_opts(**fo), offsets=batch.offsets,
+                                        num_threads=oracle.max_threads())
+    ok = well_posed(ref, ref_p, min_fraction=0.7)
+    res = handle.frame_solve_batch(dev(batch.bvs_host), dev(batch.bvs_target), dev(batch.covs_target),
+                                   dev(batch.init_poses), api.default_frame_opts(**fo), offsets=batch.offsets)
+    r, t = max_pose_diff(res.poses.cpu().numpy()[ok], ref[ok])
+    assert r <= ROT_TOL and t <= DIR_TOL, (r, t)
