@@ -1,0 +1,52 @@
+"""Parity stress of the frame pipeline: GPU pnec_frame_solve_batch vs the oracle's restatement of
+PNEC::Solve on thousands of pairs, with the oracle's own stability under a one-ulp input perturbation
+as the well-posedness yardstick.  Prints one JSON line per shape (-> profiles/)."""
+import copy, json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np, torch
+import oracle
+from conftest import rotation_angle, direction_angle
+from pnec_b200 import api, synthetic as syn
+h = api.Handle(0)
+dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+threads = len(os.sched_getaffinity(0))
+
+def perturbed(b, seed=0):
+    rng = np.random.default_rng(seed)
+    p = copy.copy(b)
+    p.bvs_host = b.bvs_host * (1.0 + rng.uniform(-1, 1, b.bvs_host.shape) * 2.0 ** -52)
+    p.bvs_target = b.bvs_target * (1.0 + rng.uniform(-1, 1, b.bvs_target.shape) * 2.0 ** -52)
+    return p
+
+def run(name, b, **kw):
+    fo = oracle.default_frame_opts()
+    t0 = time.time()
+    ref, ref_es = oracle.frame_solve_batch(b.bvs_host, b.bvs_target, b.covs_target, b.init_poses, fo, num_threads=threads, **kw)
+    dt = time.time() - t0
+    p = perturbed(b)
+    ref_p, ref_es_p = oracle.frame_solve_batch(p.bvs_host, p.bvs_target, p.covs_target, p.init_poses, fo, num_threads=threads, **kw)
+    res = h.frame_solve_batch(dev(b.bvs_host), dev(b.bvs_target), dev(b.covs_target), dev(b.init_poses),
+                              api.default_frame_opts(), **kw)
+    poses, es = res.poses.cpu().numpy(), res.es_poses.cpu().numpy()
+    ang = lambda A, Bm: (np.array([rotation_angle(a, c) for a, c in zip(A, Bm)]),
+                         np.array([direction_angle(a[4:], c[4:]) for a, c in zip(A, Bm)]))
+    sr, st = ang(ref, ref_p); er, et = ang(ref_es, ref_es_p)
+    ok = (sr <= 1e-8) & (st <= 1e-8)
+    ok_es = (er <= 1e-8) & (et <= 1e-8)
+    gr, gt = ang(poses, ref); ger, get = ang(es, ref_es)
+    row = dict(shape=name, pairs=len(poses), oracle_seconds=round(dt, 2), oracle_threads=threads,
+               well_posed_final=float(ok.mean()), well_posed_eigensolver=float(ok_es.mean()),
+               final_max_rot_well_posed=float(gr[ok].max()), final_max_dir_well_posed=float(gt[ok].max()),
+               es_max_rot_well_posed=float(ger[ok_es].max()), es_max_dir_well_posed=float(get[ok_es].max()),
+               final_over_1e6_well_posed=int(((gr > 1e-6) | (gt > 1e-6))[ok].sum()),
+               final_max_rot_all=float(gr.max()), final_median_rot_all=float(np.median(gr)),
+               oracle_self_max_rot=float(sr.max()), oracle_self_max_dir=float(st.max()))
+    print(json.dumps(row), flush=True)
+
+run("C2 shape 2000x512 omni aniso", syn.make_batch(2000, 512, seed=2025), n_per_problem=512)
+run("1500x200 pinhole aniso", syn.make_batch(1500, 200, seed=8, camera=syn.PINHOLE), n_per_problem=200)
+run("1500x100 omni iso noise 2px", syn.make_batch(1500, 100, seed=9, noise_type="isotropic_homogenous", noise_level=2.0), n_per_problem=100)
+counts = syn.kitti_like_counts(300)
+b = syn.make_batch(300, 0, seed=6, camera=syn.PINHOLE, counts=counts)
+run("KITTI-like ragged 300 x ~2000 pinhole", b, offsets=b.offsets)
