@@ -545,8 +545,12 @@ int run_scf(pnec_handle *h, const BatchView &bv, long long max_n, double reg, in
     if (!dbg_buf) cudaMalloc(&dbg_buf, sizeof(long long) * 4 * 1000000);
     if (bv.num_problems <= 1000000) a.dbg = dbg_buf;
   }
-  int nw = env_int("PNEC_B200_SCF_WARPS", 4);
-  if (nw != 1 && nw != 2 && nw != 8) nw = 4;
+  // warps per pair in pass 1: 4 while several pairs fit an SM; large pairs leave room for one or
+  // two CTAs per SM only, which then get more warps (the scan parallelises over them; the sums
+  // that depend on the thread split stay on 4 warps, so the result does not change)
+  int nw = env_int("PNEC_B200_SCF_WARPS", 0);
+  if (nw == 0) nw = dyn > 110 * 1024 ? 16 : dyn > 72 * 1024 ? 8 : 4;
+  if (nw != 1 && nw != 2 && nw != 8 && nw != 16) nw = 4;
   const int defer = env_int("PNEC_B200_SCF_DEFER", 48);  // survivors above which a pair goes to pass 2; 0 = one pass
   int *d_defer = defer_buf;
   if (defer > 0) {
@@ -559,7 +563,8 @@ int run_scf(pnec_handle *h, const BatchView &bv, long long max_n, double reg, in
     a.defer_list = d_defer + 4;
     a.defer_threshold = defer;
   }
-  void (*kern)(ScfArgs) = nw == 1 ? scf_kernel<1> : nw == 2 ? scf_kernel<2> : nw == 8 ? scf_kernel<8> : scf_kernel<4>;
+  void (*kern)(ScfArgs) = nw == 1 ? scf_kernel<1> : nw == 2 ? scf_kernel<2> : nw == 8 ? scf_kernel<8>
+                          : nw == 16 ? scf_kernel<16> : scf_kernel<4>;
   PNEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
   kern<<<static_cast<unsigned>(bv.num_problems), nw * 32, dyn, stream>>>(a);
   PNEC_CUDA(cudaGetLastError());
