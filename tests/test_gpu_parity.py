@@ -173,6 +173,24 @@ def test_host_and_device_memspace_agree_bitwise(handle):
     assert np.array_equal(host.poses, again.poses), "solve is not deterministic"
 
 
+@pytest.mark.parametrize("ragged", [False, True])
+@pytest.mark.parametrize("chunks", [2, 4, 8])
+def test_chunked_host_path_agrees_bitwise(handle, monkeypatch, ragged, chunks):
+    """HOST batches above 64 MB are cut into chunks on separate streams (H2D / solve / D2H overlap);
+    forced here on small batches, uniform and ragged (with empty and odd-sized pairs)."""
+    counts = np.array([5, 40, 1, 0, 33, 64, 12, 100, 7, 0, 51, 2, 96], dtype=np.int64) if ragged else None
+    B = len(counts) if ragged else 13
+    b = syn.make_batch(B, 40, seed=17, counts=counts)
+    o = api.default_opts(api.TARGET)
+    kw = dict(offsets=b.offsets) if ragged else dict(n_per_problem=40)
+    monkeypatch.setenv("PNEC_B200_H2D_CHUNKS", "1")
+    one = handle.solve_batch(b.bvs_host, b.bvs_target, b.covs_target, None, b.init_poses, o, **kw)
+    monkeypatch.setenv("PNEC_B200_H2D_CHUNKS", str(chunks))
+    cut = handle.solve_batch(b.bvs_host, b.bvs_target, b.covs_target, None, b.init_poses, o, **kw)
+    for name in ("poses", "status", "iterations", "cost", "initial_cost"):
+        assert np.array_equal(getattr(one, name), getattr(cut, name)), name
+
+
 def test_unaligned_device_pointers_take_the_plain_copy_path(handle):
     """Base pointers that are 8- but not 16-byte aligned cannot use cp.async.bulk."""
     import torch
