@@ -170,6 +170,88 @@ __device__ __forceinline__ void issue_bulk(const BatchView &bv, long long first,
   }
 }
 
+// Producer side of a warp-private ring of S tiles of T correspondences (shared by K1 and the moments
+// kernel): the warp owns problems gw, gw + W, gw + 2W, ... and streams their correspondences tile by
+// tile with bulk async copies; the ring runs ACROSS problem boundaries, so HBM requests never drain
+// between problems.  All members are warp-uniform; lane 0 issues.  Tiles start at even global
+// correspondence indices so that every byte range is 16-byte aligned for any ragged offset.
+template <int V, int S, int T>
+struct WarpTileProducer {
+  static constexpr int kStageDoubles = T * VariantTraits<V>::kDoubles;
+  static constexpr bool kCt = VariantTraits<V>::kHasCt, kCh = VariantTraits<V>::kHasCh;
+  const BatchView &bv;
+  double *ring;
+  uint64_t *full;
+  long long gw, W;
+  int nmine, lane;
+  int pj = 0, p_left = 0, p_stage = 0;
+  const double *p_f1 = nullptr, *p_f2 = nullptr, *p_ct = nullptr, *p_ch = nullptr;
+
+  __device__ __forceinline__ WarpTileProducer(const BatchView &bv_, double *ring_, uint64_t *full_, long long gw_,
+                                              long long W_, int nmine_, int lane_)
+      : bv(bv_), ring(ring_), full(full_), gw(gw_), W(W_), nmine(nmine_), lane(lane_) {}
+
+  // position on the first tile of the next non-empty problem
+  __device__ __forceinline__ void open() {
+    while (pj < nmine) {
+      long long s, e;
+      problem_range(bv, gw + pj * W, s, e);
+      if (e > s) {
+        const long long g0 = s & ~1LL;  // even => 16-byte aligned in every array
+        p_left = static_cast<int>(e - g0);
+        p_f1 = bv.f1 + 3 * g0;
+        p_f2 = bv.f2 + 3 * g0;
+        if (kCt) p_ct = bv.ct + 9 * g0;
+        if (kCh) p_ch = bv.ch + 9 * g0;
+        return;
+      }
+      ++pj;
+    }
+  }
+  // issue the current tile, then advance
+  __device__ __forceinline__ void issue() {
+    if (pj >= nmine) return;
+    const int cnt = min(T, p_left);
+    if (lane == 0) {
+      double *base = ring + p_stage * kStageDoubles;
+      int cb = cnt + (cnt & 1);  // bulk copies move 16-byte units: round up to an even count ...
+      if ((cnt & 1) && p_f1 + 3 * cb > bv.f1 + 3 * bv.total) {
+        cb = cnt - 1;  // ... unless that runs past the end of the batch: last element by hand
+#pragma unroll
+        for (int k = 0; k < 3; ++k) base[3 * cb + k] = p_f1[3 * cb + k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) base[3 * T + 3 * cb + k] = p_f2[3 * cb + k];
+        if (kCt) {
+#pragma unroll
+          for (int k = 0; k < 9; ++k) base[6 * T + 9 * cb + k] = p_ct[9 * cb + k];
+        }
+        if (kCh) {
+#pragma unroll
+          for (int k = 0; k < 9; ++k) base[15 * T + 9 * cb + k] = p_ch[9 * cb + k];
+        }
+      }
+      mbar_arrive_expect_tx(&full[p_stage], static_cast<uint32_t>(cb) * 8u * VariantTraits<V>::kDoubles);
+      if (cb > 0) {
+        bulk_g2s(base, p_f1, cb * 24u, &full[p_stage]);
+        bulk_g2s(base + 3 * T, p_f2, cb * 24u, &full[p_stage]);
+        if (kCt) bulk_g2s(base + 6 * T, p_ct, cb * 72u, &full[p_stage]);
+        if (kCh) bulk_g2s(base + 15 * T, p_ch, cb * 72u, &full[p_stage]);
+      }
+    }
+    p_stage = (p_stage + 1 == S) ? 0 : p_stage + 1;
+    p_left -= T;
+    if (p_left > 0) {
+      p_f1 += 3 * T;
+      p_f2 += 3 * T;
+      if (kCt) p_ct += 9 * T;
+      if (kCh) p_ch += 9 * T;
+    } else {
+      ++pj;
+      open();
+    }
+  }
+};
+
 // Same region, plain cooperative loads (unaligned base pointers).
 template <int V, int NT>
 __device__ __forceinline__ void copy_plain(const BatchView &bv, long long first, int cnt,

@@ -620,10 +620,27 @@ int run_es_moments(pnec_handle *h, const BatchView &bv, bool weighted, double re
   a.bv = bv;
   a.reg = reg;
   a.out = d_mom;
-  if (weighted)
+  if (bulk_ok(bv) && !env_int("PNEC_B200_NO_BULK", 0)) {
+    // persistent warp-private rings (TMA), 4 warps x 3 stages, 3 CTAs per SM
+    constexpr int WPC = 4, S = 3, MINB = 3;
+    const long long want = (bv.num_problems + WPC - 1) / WPC;
+    const unsigned grid = static_cast<unsigned>(std::max<long long>(1, std::min<long long>(want, 1LL * h->sm_count * MINB)));
+    if (weighted) {
+      auto kern = es_moments_warp_kernel<true, WPC, S, MINB>;
+      const size_t dyn = static_cast<size_t>(WPC) * S * 32 * VariantTraits<PNEC_VARIANT_TARGET>::kDoubles * 8;
+      PNEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
+      kern<<<grid, WPC * 32, dyn, stream>>>(a);
+    } else {
+      auto kern = es_moments_warp_kernel<false, WPC, S, MINB>;
+      const size_t dyn = static_cast<size_t>(WPC) * S * 32 * VariantTraits<PNEC_VARIANT_NEC>::kDoubles * 8;
+      PNEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
+      kern<<<grid, WPC * 32, dyn, stream>>>(a);
+    }
+  } else if (weighted) {
     es_moments_kernel<true><<<static_cast<unsigned>(bv.num_problems), 128, 0, stream>>>(a);
-  else
+  } else {
     es_moments_kernel<false><<<static_cast<unsigned>(bv.num_problems), 128, 0, stream>>>(a);
+  }
   PNEC_CUDA(cudaGetLastError());
   h->launches++;
   return PNEC_OK;

@@ -43,6 +43,30 @@ __device__ __forceinline__ void warp_transpose_reduce48(double v[48], int lane) 
   exchange_step<4, 1>(v, lane);
 }
 
+// one correspondence into the 36 sums (acc[6 p + q] += sym(f1 f1^T)[p] * sym(f2 f2^T)[q])
+template <bool WEIGHTED>
+__device__ __forceinline__ void es_accumulate(const double R[9], const double t[3], double reg, const double f1[3],
+                                              double f2[3], const double s6[6], double acc[48]) {
+  if (WEIGHTED) {
+    // Weight(bv1, bv2, t, R, cov, reg, false) * 1e-8: 1 / (b^T S b + reg), b = R^T (t x f1);
+    // the adapter then holds f2 * sqrt(weight) (pnec.cc:302-306)
+    double a[3], bb[3], Sb[3];
+    cross3(t, f1, a);
+    rot_t(R, a, bb);
+    sym_mul6(s6, bb, Sb);
+    const double w = 1.0e-8 / (dot3(bb, Sb) + reg);
+    const double sw = sqrt(w);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) f2[k] *= sw;
+  }
+  const double A[6] = {f1[0] * f1[0], f1[0] * f1[1], f1[0] * f1[2], f1[1] * f1[1], f1[1] * f1[2], f1[2] * f1[2]};
+  const double F[6] = {f2[0] * f2[0], f2[0] * f2[1], f2[0] * f2[2], f2[1] * f2[1], f2[1] * f2[2], f2[2] * f2[2]};
+#pragma unroll
+  for (int p = 0; p < 6; ++p)
+#pragma unroll
+    for (int q = 0; q < 6; ++q) acc[6 * p + q] = fma(A[p], F[q], acc[6 * p + q]);
+}
+
 template <bool WEIGHTED>
 __global__ void __launch_bounds__(128) es_moments_kernel(const __grid_constant__ EsMomentArgs args) {
   __shared__ double s_part[4][kEsMom];
@@ -63,27 +87,14 @@ __global__ void __launch_bounds__(128) es_moments_kernel(const __grid_constant__
     double f1[3], f2[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) { f1[k] = args.bv.f1[3 * i + k]; f2[k] = args.bv.f2[3 * i + k]; }
+    double s6[6] = {0, 0, 0, 0, 0, 0};
     if (WEIGHTED) {
-      // Weight(bv1, bv2, t, R, cov, reg, false) * 1e-8: 1 / (b^T S b + reg), b = R^T (t x f1);
-      // the adapter then holds f2 * sqrt(weight) (pnec.cc:302-306)
-      double c9[9], s6[6], a[3], bb[3], Sb[3];
+      double c9[9];
 #pragma unroll
       for (int k = 0; k < 9; ++k) c9[k] = args.bv.ct[9 * i + k];
       pack_sym(c9, s6);
-      cross3(t, f1, a);
-      rot_t(R, a, bb);
-      sym_mul6(s6, bb, Sb);
-      const double w = 1.0e-8 / (dot3(bb, Sb) + args.reg);
-      const double sw = sqrt(w);
-#pragma unroll
-      for (int k = 0; k < 3; ++k) f2[k] *= sw;
     }
-    const double A[6] = {f1[0] * f1[0], f1[0] * f1[1], f1[0] * f1[2], f1[1] * f1[1], f1[1] * f1[2], f1[2] * f1[2]};
-    const double F[6] = {f2[0] * f2[0], f2[0] * f2[1], f2[0] * f2[2], f2[1] * f2[1], f2[1] * f2[2], f2[2] * f2[2]};
-#pragma unroll
-    for (int p = 0; p < 6; ++p)
-#pragma unroll
-      for (int q = 0; q < 6; ++q) acc[6 * p + q] = fma(A[p], F[q], acc[6 * p + q]);
+    es_accumulate<WEIGHTED>(R, t, args.reg, f1, f2, s6, acc);
   }
   warp_transpose_reduce48(acc, lane);
   const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1, b1 = (lane >> 1) & 1, b0 = lane & 1;
@@ -92,6 +103,77 @@ __global__ void __launch_bounds__(128) es_moments_kernel(const __grid_constant__
   if (b0 == 0 && base + 1 < kEsMom) s_part[warp][base + 1] = acc[1];
   __syncthreads();
   if (tid < kEsMom) args.out[kEsMom * b + tid] = (s_part[0][tid] + s_part[1][tid]) + (s_part[2][tid] + s_part[3][tid]);
+}
+
+// The same sums as a persistent, barrier-free stream (the K1 scheme): every warp owns whole frame
+// pairs and a private S-stage ring of 32-correspondence tiles filled by bulk async copies (TMA) that
+// runs across pair boundaries.  Needs 16-byte aligned arrays; es_moments_kernel is the fallback.
+template <bool WEIGHTED, int WPC, int S, int MINB>
+__global__ void __launch_bounds__(WPC * 32, MINB)
+es_moments_warp_kernel(const __grid_constant__ EsMomentArgs args) {
+  constexpr int V = WEIGHTED ? PNEC_VARIANT_TARGET : PNEC_VARIANT_NEC;
+  constexpr int T = 32;
+  constexpr int kStageDoubles = T * VariantTraits<V>::kDoubles;
+  __shared__ __align__(8) uint64_t s_full[WPC][S];
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
+  const long long W = static_cast<long long>(gridDim.x) * WPC;
+  const long long gw = static_cast<long long>(blockIdx.x) * WPC + warp;
+  const long long B = args.bv.num_problems;
+  const int nmine = (B > gw) ? static_cast<int>((B - gw + W - 1) / W) : 0;
+  double *ring = dyn_smem + static_cast<size_t>(warp) * S * kStageDoubles;
+  uint64_t *full = s_full[warp];
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < S; ++i) mbar_init(&full[i], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  WarpTileProducer<V, S, T> prod(args.bv, ring, full, gw, W, nmine, lane);
+  prod.open();
+#pragma unroll 1
+  for (int i = 0; i < S; ++i) prod.issue();
+
+  int c_stage = 0;
+  uint32_t c_parity = 0;
+  for (int j = 0; j < nmine; ++j) {
+    const long long prob = gw + j * W;
+    long long s, e;
+    problem_range(args.bv, prob, s, e);
+    const int head = static_cast<int>(s & 1LL);
+    int c_left = (e > s) ? static_cast<int>(e - s) + head : 0;  // elements left, head included
+    double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, t[3] = {0, 0, 0};
+    if (WEIGHTED) {
+      const double *pose = args.bv.poses + 7 * prob;
+      pose_rotation(pose, R);
+      t[0] = pose[4]; t[1] = pose[5]; t[2] = pose[6];
+    }
+    double acc[48];
+#pragma unroll
+    for (int k = 0; k < 48; ++k) acc[k] = 0.0;
+    int lo = head;  // first valid element of the tile: head on the first tile, 0 afterwards
+    while (c_left > 0) {
+      mbar_wait(&full[c_stage], c_parity);
+      const double *base = ring + c_stage * kStageDoubles;
+      const bool valid = (lane >= lo) && (lane < c_left);
+      double a1[3], a2[3], c1[6], c2[6];
+      if (valid) load_corr<V>(base, base + 3 * T, base + 6 * T, base + 15 * T, lane, a1, a2, c1, c2);
+      __syncwarp();  // every lane holds its correspondence: the stage may be refilled
+      prod.issue();
+      if (valid) es_accumulate<WEIGHTED>(R, t, args.reg, a1, a2, c1, acc);
+      if (++c_stage == S) {
+        c_stage = 0;
+        c_parity ^= 1u;
+      }
+      c_left -= T;
+      lo = 0;
+    }
+    warp_transpose_reduce48(acc, lane);
+    const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1, b1 = (lane >> 1) & 1, b0 = lane & 1;
+    const int idx = 24 * b4 + 12 * b3 + 6 * b2 + 3 * b1 + 2 * b0;
+    if (idx < kEsMom) args.out[kEsMom * prob + idx] = acc[0];
+    if (b0 == 0 && idx + 1 < kEsMom) args.out[kEsMom * prob + idx + 1] = acc[1];
+  }
 }
 
 // ------------------------------------------------- lambda_min(M(c)) and gradient

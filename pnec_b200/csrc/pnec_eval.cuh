@@ -138,70 +138,11 @@ eval_warp_kernel(const __grid_constant__ EvalArgs args) {
   }
   __syncwarp();
 
-  // ---- producer cursor (uniform across the warp; lane 0 issues).  Running pointers to the
-  // next tile of the current producer problem, elements left in it, next ring stage.
-  int pj = 0, p_left = 0, p_stage = 0;
-  const double *p_f1 = nullptr, *p_f2 = nullptr, *p_ct = nullptr, *p_ch = nullptr;
-  auto producer_open = [&]() {  // position on the first tile of the next non-empty problem
-    while (pj < nmine) {
-      long long s, e;
-      problem_range(args.bv, gw + pj * W, s, e);
-      if (e > s) {
-        const long long g0 = s & ~1LL;  // even => 16-byte aligned in every array
-        p_left = static_cast<int>(e - g0);
-        p_f1 = args.bv.f1 + 3 * g0;
-        p_f2 = args.bv.f2 + 3 * g0;
-        if (kCt) p_ct = args.bv.ct + 9 * g0;
-        if (kCh) p_ch = args.bv.ch + 9 * g0;
-        return;
-      }
-      ++pj;
-    }
-  };
-  auto producer_issue = [&]() {  // issue the current producer tile, then advance
-    if (pj >= nmine) return;
-    const int cnt = min(T, p_left);
-    if (lane == 0) {
-      double *base = ring + p_stage * kStageDoubles;
-      int cb = cnt + (cnt & 1);  // bulk copies move 16-byte units: round up to an even count ...
-      if ((cnt & 1) && p_f1 + 3 * cb > args.bv.f1 + 3 * args.bv.total) {
-        cb = cnt - 1;  // ... unless that runs past the end of the batch: last element by hand
-#pragma unroll
-        for (int k = 0; k < 3; ++k) base[3 * cb + k] = p_f1[3 * cb + k];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) base[3 * T + 3 * cb + k] = p_f2[3 * cb + k];
-        if (kCt) {
-#pragma unroll
-          for (int k = 0; k < 9; ++k) base[6 * T + 9 * cb + k] = p_ct[9 * cb + k];
-        }
-        if (kCh) {
-#pragma unroll
-          for (int k = 0; k < 9; ++k) base[15 * T + 9 * cb + k] = p_ch[9 * cb + k];
-        }
-      }
-      mbar_arrive_expect_tx(&full[p_stage], static_cast<uint32_t>(cb) * 8u * VariantTraits<V>::kDoubles);
-      if (cb > 0) {
-        bulk_g2s(base, p_f1, cb * 24u, &full[p_stage]);
-        bulk_g2s(base + 3 * T, p_f2, cb * 24u, &full[p_stage]);
-        if (kCt) bulk_g2s(base + 6 * T, p_ct, cb * 72u, &full[p_stage]);
-        if (kCh) bulk_g2s(base + 15 * T, p_ch, cb * 72u, &full[p_stage]);
-      }
-    }
-    p_stage = (p_stage + 1 == S) ? 0 : p_stage + 1;
-    p_left -= T;
-    if (p_left > 0) {
-      p_f1 += 3 * T;
-      p_f2 += 3 * T;
-      if (kCt) p_ct += 9 * T;
-      if (kCh) p_ch += 9 * T;
-    } else {
-      ++pj;
-      producer_open();
-    }
-  };
-  producer_open();
+  // ---- producer (uniform across the warp; lane 0 issues): see WarpTileProducer
+  WarpTileProducer<V, S, T> prod(args.bv, ring, full, gw, W, nmine, lane);
+  prod.open();
 #pragma unroll 1
-  for (int i = 0; i < S; ++i) producer_issue();
+  for (int i = 0; i < S; ++i) prod.issue();
 
   int c_stage = 0;
   uint32_t c_parity = 0;
@@ -238,7 +179,7 @@ eval_warp_kernel(const __grid_constant__ EvalArgs args) {
         double a1[3], a2[3], c1[6], c2[6];
         if (valid) load_corr<V>(base, base + 3 * T, base + 6 * T, base + 15 * T, lane, a1, a2, c1, c2);
         __syncwarp();  // every lane holds its correspondence: the stage may be refilled
-        producer_issue();
+        prod.issue();
         if (valid) {
           double r, row[5];
           residual_row<V>(pc, args.reg, a1, a2, c1, c2, r, row);
@@ -257,7 +198,7 @@ eval_warp_kernel(const __grid_constant__ EvalArgs args) {
           }
         }
         __syncwarp();
-        producer_issue();
+        prod.issue();
       }
       if (++c_stage == S) {
         c_stage = 0;
