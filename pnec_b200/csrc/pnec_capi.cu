@@ -14,6 +14,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "pnec_aux.cuh"
@@ -91,6 +92,7 @@ struct pnec_handle {
   cudaEvent_t ev_fork = nullptr, ev_join[kMaxChunks] = {}, ev_es[kMaxChunks] = {};
   cudaEvent_t ev_round[kMaxChunks][kMaxRounds] = {};
   DevBuf d_fr_rounds;             // poses of every weighted round: [rounds][B][7]
+  std::unordered_map<const void *, size_t> dyn_smem_set;  // kernel -> opt-in dynamic shared memory already granted
   int sphere_samples = -1;
   std::mutex mu;
 };
@@ -101,6 +103,18 @@ struct Staged {
   BatchView bv;
   long long max_n = 0;
 };
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-kernel maximum: raise it only when a launch
+// needs more than any earlier one (saves one driver call per launch on the hot path).
+template <class Kernel>
+cudaError_t ensure_dyn_smem(pnec_handle *h, Kernel kern, size_t dyn) {
+  const void *key = reinterpret_cast<const void *>(kern);
+  auto it = h->dyn_smem_set.find(key);
+  if (it != h->dyn_smem_set.end() && it->second >= dyn) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn));
+  if (e == cudaSuccess) h->dyn_smem_set[key] = dyn;
+  return e;
+}
 
 int validate_batch(const pnec_batch *b, int variant, bool need_poses) {
   if (!b) return fail(PNEC_ERR_INVALID_ARGUMENT, "batch is NULL");
@@ -233,8 +247,7 @@ constexpr size_t kStaticSmemReserve = 3072;  // static __shared__ of the kernels
 template <int V, int NW, int MINB>
 int launch_solve_t(pnec_handle *h, const SolveArgs &a, size_t dyn, cudaStream_t stream) {
   auto kern = solve_kernel<V, NW, MINB>;
-  PNEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 static_cast<int>(dyn)));
+  PNEC_CUDA(ensure_dyn_smem(h, kern, dyn));
   kern<<<static_cast<unsigned>(a.bv.num_problems), NW * 32, dyn, stream>>>(a);
   PNEC_CUDA(cudaGetLastError());
   h->launches++;
@@ -277,8 +290,7 @@ template <int V, int NW, int S, int MINB>
 int launch_solve_stream_t(pnec_handle *h, const SolveArgs &a, cudaStream_t stream) {
   auto kern = solve_stream_kernel<V, NW, S, MINB>;
   const size_t dyn = static_cast<size_t>(NW) * S * 32 * VariantTraits<V>::kDoubles * 8;
-  PNEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 static_cast<int>(dyn)));
+  PNEC_CUDA(ensure_dyn_smem(h, kern, dyn));
   kern<<<static_cast<unsigned>(a.bv.num_problems), NW * 32, dyn, stream>>>(a);
   PNEC_CUDA(cudaGetLastError());
   h->launches++;
@@ -355,8 +367,7 @@ template <int V, int NW, int S, int MINB>
 int launch_eval_t(pnec_handle *h, const EvalArgs &a, cudaStream_t stream) {
   auto kern = eval_kernel<V, NW, S, MINB>;
   const size_t dyn = static_cast<size_t>(S) * NW * 32 * VariantTraits<V>::kDoubles * 8;
-  PNEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 static_cast<int>(dyn)));
+  PNEC_CUDA(ensure_dyn_smem(h, kern, dyn));
   kern<<<static_cast<unsigned>(a.bv.num_problems), NW * 32, dyn, stream>>>(a);
   PNEC_CUDA(cudaGetLastError());
   h->launches++;
@@ -367,8 +378,7 @@ template <int V, int WPC, int S, int CHUNK, int MINB, int T = 32>
 int launch_eval_warp_t(pnec_handle *h, const EvalArgs &a, cudaStream_t stream) {
   auto kern = eval_warp_kernel<V, WPC, S, CHUNK, MINB, T>;
   const size_t dyn = static_cast<size_t>(WPC) * S * T * VariantTraits<V>::kDoubles * 8;
-  PNEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 static_cast<int>(dyn)));
+  PNEC_CUDA(ensure_dyn_smem(h, kern, dyn));
   const long long want = (a.bv.num_problems + WPC - 1) / WPC;
   const long long cap = static_cast<long long>(h->sm_count) * MINB;
   const unsigned grid = static_cast<unsigned>(std::max<long long>(1, std::min(want, cap)));
@@ -565,7 +575,7 @@ int run_scf(pnec_handle *h, const BatchView &bv, long long max_n, double reg, in
   }
   void (*kern)(ScfArgs) = nw == 1 ? scf_kernel<1> : nw == 2 ? scf_kernel<2> : nw == 8 ? scf_kernel<8>
                           : nw == 16 ? scf_kernel<16> : scf_kernel<4>;
-  PNEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
+  PNEC_CUDA(ensure_dyn_smem(h, kern, dyn));
   kern<<<static_cast<unsigned>(bv.num_problems), nw * 32, dyn, stream>>>(a);
   PNEC_CUDA(cudaGetLastError());
   h->launches++;
@@ -577,7 +587,7 @@ int run_scf(pnec_handle *h, const BatchView &bv, long long max_n, double reg, in
     a2.work_count = d_defer;
     a2.work_cursor = d_defer + 1;
     auto kern2 = scf_list_kernel<16>;
-    PNEC_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
+    PNEC_CUDA(ensure_dyn_smem(h, kern2, dyn));
     const unsigned grid2 = static_cast<unsigned>(std::min<long long>(bv.num_problems, 2LL * h->sm_count));
     kern2<<<grid2, 16 * 32, dyn, stream>>>(a2);
     PNEC_CUDA(cudaGetLastError());
@@ -628,12 +638,12 @@ int run_es_moments(pnec_handle *h, const BatchView &bv, bool weighted, double re
     if (weighted) {
       auto kern = es_moments_warp_kernel<true, WPC, S, MINB>;
       const size_t dyn = static_cast<size_t>(WPC) * S * 32 * VariantTraits<PNEC_VARIANT_TARGET>::kDoubles * 8;
-      PNEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
+      PNEC_CUDA(ensure_dyn_smem(h, kern, dyn));
       kern<<<grid, WPC * 32, dyn, stream>>>(a);
     } else {
       auto kern = es_moments_warp_kernel<false, WPC, S, MINB>;
       const size_t dyn = static_cast<size_t>(WPC) * S * 32 * VariantTraits<PNEC_VARIANT_NEC>::kDoubles * 8;
-      PNEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
+      PNEC_CUDA(ensure_dyn_smem(h, kern, dyn));
       kern<<<grid, WPC * 32, dyn, stream>>>(a);
     }
   } else if (weighted) {

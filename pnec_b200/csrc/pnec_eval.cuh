@@ -118,7 +118,6 @@ __global__ void __launch_bounds__(WPC * 32, MINB)
 eval_warp_kernel(const __grid_constant__ EvalArgs args) {
   static_assert(T % 32 == 0, "tiles are whole warps of correspondences");
   constexpr int kStageDoubles = T * VariantTraits<V>::kDoubles;
-  constexpr bool kCt = VariantTraits<V>::kHasCt, kCh = VariantTraits<V>::kHasCh;
   __shared__ __align__(8) uint64_t s_full[WPC][S];
   __shared__ PoseConst s_pcs[WPC][CHUNK];
 
