@@ -268,6 +268,26 @@ __device__ __forceinline__ double scf_objective(const double *terms, int n, cons
   return cost;
 }
 
+// The same sum, abandoned as soon as it exceeds `bound` (checked every 4 terms).  The terms are
+// non-negative, so the partial sums only grow: a sum that is abandoned would have ended above the
+// bound as well, and one that is not abandoned is returned unchanged (same operations, same order).
+__device__ __forceinline__ double scf_objective_bounded(const double *terms, int n, const double t[3], double bound) {
+  const double txx = t[0] * t[0], txy = 2.0 * t[0] * t[1], txz = 2.0 * t[0] * t[2];
+  const double tyy = t[1] * t[1], tyz = 2.0 * t[1] * t[2], tzz = t[2] * t[2];
+  double cost = 0.0;
+  for (int i0 = 0; i0 < n; i0 += 4) {
+    const int i1 = min(i0 + 4, n);
+    for (int i = i0; i < i1; ++i) {
+      const double *w = terms + 9 * i;
+      const double e = t[0] * w[0] + t[1] * w[1] + t[2] * w[2];
+      const double den = w[3] * txx + w[4] * txy + w[5] * txz + w[6] * tyy + w[7] * tyz + w[8] * tzz;
+      cost = fma(e * e, fast_rcp(den), cost);
+    }
+    if (cost > bound) break;
+  }
+  return cost;
+}
+
 // The rest of a candidate's sum, correspondences [begin, n): by one lane in index order
 // (`warp_parallel` false) or by the 32 lanes of a warp, lane-strided and tree-reduced in a fixed
 // order (every lane gets the sum).
@@ -404,7 +424,9 @@ __device__ __forceinline__ void scf_pair(const ScfArgs &args, const long long b)
     int best_idx = 0x7fffffff;
     for (int c = 1 + tid; c <= args.samples; c += NT) {
       const double t[3] = {args.sphere[3 * (c - 1)], args.sphere[3 * (c - 1) + 1], args.sphere[3 * (c - 1) + 2]};
-      const double part = scf_objective(terms, npre, t);
+      // with pruning on, a candidate is dropped at the first checkpoint above cost0 (most are after
+      // four terms: the sphere is coarse); survivors carry the full 32-term prefix
+      const double part = prune ? scf_objective_bounded(terms, npre, t, cost0) : scf_objective(terms, npre, t);
       if (npre == n) {
         if (part < best || (part == best && c < best_idx)) { best = part; best_idx = c; }
       } else if (!(part > cost0)) {
