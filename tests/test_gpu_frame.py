@@ -264,3 +264,28 @@ def test_frame_solve_ragged_device_batch(handle):
                                    dev(batch.init_poses), api.default_frame_opts(**fo), offsets=batch.offsets)
     r, t = max_pose_diff(res.poses.cpu().numpy()[ok], ref[ok])
     assert r <= ROT_TOL and t <= DIR_TOL, (r, t)
+
+
+def test_frame_solve_degenerate_inputs_terminate(handle):
+    """Empty pairs, pairs below the minimal sample size and a pure rotation (the eigensolver's
+    singular case) must terminate with a pose per pair; empty pairs keep their start pose."""
+    counts = np.array([0, 1, 3, 6, 40, 0, 25], dtype=np.int64)
+    batch = syn.make_batch(len(counts), 0, seed=12, counts=counts)
+    # pair 4: pure rotation (no translation): f2 = R^T f1 exactly
+    s, e = batch.range(4)
+    R = syn.quaternion_to_matrix(batch.gt_poses[4, :4])
+    batch.bvs_target[s:e] = batch.bvs_host[s:e] @ R
+    res = handle.frame_solve_batch(batch.bvs_host, batch.bvs_target, batch.covs_target, batch.init_poses,
+                                   api.default_frame_opts(), offsets=batch.offsets)
+    assert res.poses.shape == (len(counts), 7)
+    assert (res.status[counts == 0] == 7).all()  # PNEC_STATUS_EMPTY
+    for b in np.nonzero(counts == 0)[0]:
+        q0 = batch.init_poses[b, :4] / np.linalg.norm(batch.init_poses[b, :4])
+        np.testing.assert_allclose(res.poses[b, :4], q0, atol=1e-15)
+    ok = counts >= 25
+    assert np.isfinite(res.poses[ok]).all()
+    # the pure rotation is recovered even though its translation is undefined
+    assert rotation_angle(res.poses[4], batch.gt_poses[4]) < 1e-6
+    ref, _ = oracle.frame_solve_batch(batch.bvs_host, batch.bvs_target, batch.covs_target, batch.init_poses,
+                                      oracle.default_frame_opts(), offsets=batch.offsets)
+    assert rotation_angle(res.poses[6], ref[6]) <= ROT_TOL
