@@ -8,12 +8,16 @@
 //   pnec_eigensolver.cuh  es_moments_kernel / es_lm_kernel: rotation by NEC eigenvalue minimisation
 //   pnec_lm.cuh      Ceres-semantics Levenberg-Marquardt update; pnec_device.cuh: the math
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -70,6 +74,138 @@ int env_int(const char *name, int dflt) {
   return (v && *v) ? std::atoi(v) : dflt;
 }
 
+// ---------------------------------------------------------- pageable host inputs
+//
+// The reference hands over std::vector storage, i.e. pageable memory, which cudaMemcpyAsync moves
+// through the driver's own bounce buffer at ~11 GB/s.  HostStager copies such inputs into a ring of
+// pinned slots with a few worker threads (a parallel memcpy runs at several times that) and sends
+// every slot with its own async copy, so the DMA of one slot overlaps the memcpy of the next.
+class CopyPool {
+ public:
+  explicit CopyPool(int threads) : n_(std::max(1, threads)) {
+    for (int i = 1; i < n_; ++i) workers_.emplace_back([this, i] { loop(i); });
+  }
+  ~CopyPool() {
+    {
+      std::lock_guard<std::mutex> l(mu_);
+      stop_ = true;
+      ++gen_;
+    }
+    cv_.notify_all();
+    for (auto &t : workers_) t.join();
+  }
+  // memcpy(dst, src, bytes) split over the pool; returns when done
+  void copy(void *dst, const void *src, size_t bytes) {
+    if (n_ == 1 || bytes < (1u << 20)) {
+      std::memcpy(dst, src, bytes);
+      return;
+    }
+    {
+      std::lock_guard<std::mutex> l(mu_);
+      dst_ = static_cast<char *>(dst);
+      src_ = static_cast<const char *>(src);
+      bytes_ = bytes;
+      pending_ = n_ - 1;
+      ++gen_;
+    }
+    cv_.notify_all();
+    part(0);
+    std::unique_lock<std::mutex> l(mu_);
+    done_.wait(l, [this] { return pending_ == 0; });
+  }
+
+ private:
+  void part(int i) {
+    const size_t per = ((bytes_ + n_ - 1) / n_ + 4095) & ~size_t(4095);
+    const size_t b0 = std::min(bytes_, per * i), b1 = std::min(bytes_, per * (i + 1));
+    if (b1 > b0) std::memcpy(dst_ + b0, src_ + b0, b1 - b0);
+  }
+  void loop(int i) {
+    unsigned long long seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> l(mu_);
+        cv_.wait(l, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (stop_) return;
+      }
+      part(i);
+      {
+        std::lock_guard<std::mutex> l(mu_);
+        --pending_;
+      }
+      done_.notify_one();
+    }
+  }
+  int n_;
+  std::vector<std::thread> workers_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  unsigned long long gen_ = 0;
+  int pending_ = 0;
+  bool stop_ = false;
+  char *dst_ = nullptr;
+  const char *src_ = nullptr;
+  size_t bytes_ = 0;
+};
+
+class HostStager {
+ public:
+  static constexpr int kSlots = 4;
+  static constexpr size_t kSlotBytes = 8u << 20;
+  ~HostStager() {
+    for (int i = 0; i < kSlots; ++i) {
+      if (ev_[i]) cudaEventDestroy(ev_[i]);
+    }
+    if (ring_) cudaFreeHost(ring_);
+  }
+  static bool pageable(const void *p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+      cudaGetLastError();
+      return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+  }
+  // dst (device) <- src (pageable host), enqueued on `stream`; returns when the last slot is queued
+  cudaError_t h2d(void *dst, const void *src, size_t bytes, cudaStream_t stream) {
+    if (!ring_) {
+      cudaError_t e = cudaHostAlloc(&ring_, kSlots * kSlotBytes, cudaHostAllocDefault);
+      if (e != cudaSuccess) return e;
+      for (int i = 0; i < kSlots; ++i) {
+        e = cudaEventCreateWithFlags(&ev_[i], cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+      }
+      int t = static_cast<int>(std::thread::hardware_concurrency());
+      if (const char *v = std::getenv("PNEC_B200_COPY_THREADS")) t = 2 * std::atoi(v);
+      pool_.reset(new CopyPool(std::min(8, std::max(1, t / 2))));
+    }
+    for (size_t off = 0; off < bytes; off += kSlotBytes) {
+      const size_t n = std::min(kSlotBytes, bytes - off);
+      char *slot = static_cast<char *>(ring_) + static_cast<size_t>(next_) * kSlotBytes;
+      if (used_[next_]) {
+        cudaError_t e = cudaEventSynchronize(ev_[next_]);  // the slot's previous DMA has drained
+        if (e != cudaSuccess) return e;
+      }
+      pool_->copy(slot, static_cast<const char *>(src) + off, n);
+      cudaError_t e = cudaMemcpyAsync(static_cast<char *>(dst) + off, slot, n, cudaMemcpyHostToDevice, stream);
+      if (e != cudaSuccess) return e;
+      e = cudaEventRecord(ev_[next_], stream);
+      if (e != cudaSuccess) return e;
+      used_[next_] = true;
+      next_ = (next_ + 1) % kSlots;
+    }
+    return cudaSuccess;
+  }
+
+ private:
+  void *ring_ = nullptr;
+  cudaEvent_t ev_[kSlots] = {};
+  bool used_[kSlots] = {};
+  int next_ = 0;
+  std::unique_ptr<CopyPool> pool_;
+};
+
 }  // namespace
 
 struct pnec_handle {
@@ -93,6 +229,7 @@ struct pnec_handle {
   cudaEvent_t ev_round[kMaxChunks][kMaxRounds] = {};
   DevBuf d_fr_rounds;             // poses of every weighted round: [rounds][B][7]
   std::unordered_map<const void *, size_t> dyn_smem_set;  // kernel -> opt-in dynamic shared memory already granted
+  HostStager stager;              // pinned ring + copy threads for pageable host inputs
   int sphere_samples = -1;
   std::mutex mu;
 };
@@ -204,13 +341,17 @@ int stage_copy(pnec_handle *h, const pnec_batch *b, int variant, long long p0, l
   const long long e1 = b->offsets ? b->offsets[p1] : p1 * b->n_per_problem;
   const size_t nel = static_cast<size_t>(e1 - e0);
   auto at = [](void *base, long long bytes) { return static_cast<char *>(base) + bytes; };
+  // pinned sources go straight to the copy engine; large pageable ones through the pinned ring
+  auto h2d = [&](void *dst, const double *src, size_t bytes) -> cudaError_t {
+    if (bytes >= (4u << 20) && !env_int("PNEC_B200_NO_STAGER", 0) && HostStager::pageable(src))
+      return h->stager.h2d(dst, src, bytes, stream);
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream);
+  };
   if (nel) {
-    PNEC_CUDA(cudaMemcpyAsync(at(h->d_f1.p, e0 * 24), b->bvs_host + 3 * e0, nel * 24, cudaMemcpyHostToDevice, stream));
-    PNEC_CUDA(cudaMemcpyAsync(at(h->d_f2.p, e0 * 24), b->bvs_target + 3 * e0, nel * 24, cudaMemcpyHostToDevice, stream));
-    if (variant != PNEC_VARIANT_NEC)
-      PNEC_CUDA(cudaMemcpyAsync(at(h->d_ct.p, e0 * 72), b->covs_target + 9 * e0, nel * 72, cudaMemcpyHostToDevice, stream));
-    if (variant == PNEC_VARIANT_SYMMETRIC)
-      PNEC_CUDA(cudaMemcpyAsync(at(h->d_ch.p, e0 * 72), b->covs_host + 9 * e0, nel * 72, cudaMemcpyHostToDevice, stream));
+    PNEC_CUDA(h2d(at(h->d_f1.p, e0 * 24), b->bvs_host + 3 * e0, nel * 24));
+    PNEC_CUDA(h2d(at(h->d_f2.p, e0 * 24), b->bvs_target + 3 * e0, nel * 24));
+    if (variant != PNEC_VARIANT_NEC) PNEC_CUDA(h2d(at(h->d_ct.p, e0 * 72), b->covs_target + 9 * e0, nel * 72));
+    if (variant == PNEC_VARIANT_SYMMETRIC) PNEC_CUDA(h2d(at(h->d_ch.p, e0 * 72), b->covs_host + 9 * e0, nel * 72));
   }
   if (b->poses)
     PNEC_CUDA(cudaMemcpyAsync(at(h->d_poses.p, p0 * 56), b->poses + 7 * p0, static_cast<size_t>(p1 - p0) * 56,
