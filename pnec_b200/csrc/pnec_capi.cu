@@ -217,7 +217,7 @@ struct pnec_handle {
   DevBuf d_f1, d_f2, d_ct, d_ch, d_off, d_poses;
   DevBuf d_out_poses, d_out_status, d_out_iters, d_out_cost, d_out_init, d_out_grad, d_out_jtj;
   DevBuf d_ut_mu, d_ut_cov, d_ut_out, d_kp_bv, d_sphere, d_tr_out, d_tr_aux;
-  DevBuf d_es_mom, d_es_w, d_es_info, d_es_ev, d_fr_es, d_fr_a, d_fr_b;  // eigensolver / frame pipeline
+  DevBuf d_es_mom, d_es_w, d_es_info, d_es_ev, d_fr_es, d_fr_a;  // eigensolver / frame pipeline
   DevBuf d_fr_cache, d_fr_flags;  // ScfScanCache[B]; int q_same[B], fixed[B]
   DevBuf d_scf_defer;             // int count, cursor, pad[2], list[B]  (standalone SCF calls)
   DevBuf d_fr_defer;              // the same per chunk of a frame solve: (4 + B) ints
@@ -897,7 +897,7 @@ void pnec_destroy(pnec_handle *h) {
                     &h->d_out_init, &h->d_out_grad, &h->d_out_jtj, &h->d_ut_mu, &h->d_ut_cov,
                     &h->d_ut_out, &h->d_kp_bv, &h->d_sphere, &h->d_tr_out,
                     &h->d_tr_aux, &h->d_es_mom, &h->d_es_w, &h->d_es_info, &h->d_es_ev,
-                    &h->d_fr_es, &h->d_fr_a, &h->d_fr_b, &h->d_fr_cache, &h->d_fr_flags, &h->d_scf_defer, &h->d_fr_defer, &h->d_scf_spill};
+                    &h->d_fr_es, &h->d_fr_a, &h->d_fr_cache, &h->d_fr_flags, &h->d_scf_defer, &h->d_fr_defer, &h->d_scf_spill};
   for (DevBuf *b : bufs) b->release();
   for (int i = 0; i < pnec_handle::kMaxChunks; ++i) {
     if (h->side[i]) cudaStreamDestroy(h->side[i]);
@@ -1331,7 +1331,6 @@ int pnec_frame_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_f
   PNEC_CUDA(h->d_es_mom.ensure(nb * kEsMom * 8));
   PNEC_CUDA(h->d_fr_es.ensure(nb * 56));
   PNEC_CUDA(h->d_fr_a.ensure(nb * 56));
-  PNEC_CUDA(h->d_fr_b.ensure(nb * 56));
   PNEC_CUDA(h->d_fr_cache.ensure(nb * sizeof(ScfScanCache)));
   PNEC_CUDA(h->d_fr_flags.ensure(nb * 2 * sizeof(int)));
   PNEC_CUDA(h->d_fr_defer.ensure(sizeof(int) * (4 * pnec_handle::kMaxChunks + nb)));

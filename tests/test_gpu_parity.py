@@ -191,6 +191,22 @@ def test_chunked_host_path_agrees_bitwise(handle, monkeypatch, ragged, chunks):
         assert np.array_equal(getattr(one, name), getattr(cut, name)), name
 
 
+def test_pageable_host_batch_through_the_staging_ring(handle, monkeypatch):
+    """A 72 MB batch in pageable (numpy) memory: chunked streams + pinned staging ring with copy
+    threads; the results must equal the device-resident call bit for bit, with and without the ring."""
+    B, N = 3000, 200
+    b = syn.make_batch(B, N, seed=23)
+    o = api.default_opts(api.TARGET)
+    devr = handle.solve_batch(dev(b.bvs_host), dev(b.bvs_target), dev(b.covs_target), None, dev(b.init_poses), o,
+                              n_per_problem=N)
+    host = handle.solve_batch(b.bvs_host, b.bvs_target, b.covs_target, None, b.init_poses, o, n_per_problem=N)
+    monkeypatch.setenv("PNEC_B200_NO_STAGER", "1")
+    plain = handle.solve_batch(b.bvs_host, b.bvs_target, b.covs_target, None, b.init_poses, o, n_per_problem=N)
+    for r in (host, plain):
+        assert np.array_equal(r.poses, devr.poses.cpu().numpy())
+        assert np.array_equal(r.iterations, devr.iterations.cpu().numpy())
+
+
 def test_unaligned_device_pointers_take_the_plain_copy_path(handle):
     """Base pointers that are 8- but not 16-byte aligned cannot use cp.async.bulk."""
     import torch
