@@ -6,6 +6,7 @@
 //   pnec_aux.cuh     cost_kernel (parity metric), unscented_kernel (covariance propagation)
 //   pnec_translation.cuh  scf_kernel / nec_translation_kernel: translation given rotation
 //   pnec_eigensolver.cuh  es_moments_kernel / es_lm_kernel: rotation by NEC eigenvalue minimisation
+//   pnec_frame.cuh   frame_rounds_kernel: all weighted rounds of one pair in one launch (small batches)
 //   pnec_lm.cuh      Ceres-semantics Levenberg-Marquardt update; pnec_device.cuh: the math
 #include <algorithm>
 #include <atomic>
@@ -24,6 +25,7 @@
 #include "pnec_aux.cuh"
 #include "pnec_eigensolver.cuh"
 #include "pnec_eval.cuh"
+#include "pnec_frame.cuh"
 #include "pnec_solve.cuh"
 #include "pnec_translation.cuh"
 
@@ -1338,6 +1340,8 @@ int pnec_frame_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_f
   if (weighted) PNEC_CUDA(h->d_fr_rounds.ensure(nb * 56 * static_cast<size_t>(weighted_rounds)));
   double *const d_rounds = static_cast<double *>(h->d_fr_rounds.p);
   const bool lm_ahead = weighted_rounds <= pnec_handle::kMaxRounds && !env_int("PNEC_B200_NO_LM_AHEAD", 0);
+  // small batches: one launch for all weighted rounds of a pair (the per-round launches would dominate)
+  const bool fused_rounds = weighted && B <= env_int("PNEC_B200_FUSED_ROUNDS_MAX_PAIRS", 512);
   if (weighted) {
     rc = ensure_sphere(h, opts->fibonacci_samples);
     if (rc != PNEC_OK) return rc;
@@ -1396,6 +1400,34 @@ int pnec_frame_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_f
       PNEC_CUDA(cudaMemsetAsync(rot_same, 0, static_cast<size_t>(cnt) * sizeof(int), cs));
       PNEC_CUDA(cudaMemsetAsync(fixed, 0, static_cast<size_t>(cnt) * sizeof(int), cs));
       const int rounds = opts->weighted_iterations - 1;
+      if (fused_rounds) {
+        // small batch: all rounds of a pair in one CTA and one launch (pnec_frame.cuh)
+        const size_t dyn = scf_smem_bytes(h, st.max_n);
+        const bool fits = dyn >= static_cast<size_t>(std::max<long long>(st.max_n, 1)) * 72;
+        FrameRoundsArgs fa{};
+        fa.scf.bv = bv;
+        fa.scf.sphere = static_cast<const double *>(h->d_sphere.p);
+        fa.scf.reg = opts->ceres.regularization;
+        fa.scf.samples = opts->fibonacci_samples;
+        fa.scf.steps = opts->scf_steps;
+        fa.scf.cap_elems = static_cast<int>(dyn / 72);
+        fa.scf.spill = fits ? nullptr : (st.bv.offsets ? d_spill : d_spill + 9 * c0 * st.bv.n_uniform);
+        fa.scf.cache = shortcuts ? cache : nullptr;
+        fa.scf.fixed = shortcuts ? fixed : nullptr;
+        fa.lm = EsLmParams{0.00005, 1.0e1 * DBL_EPSILON, 0.0, 100.0, 100};
+        fa.moments = mom;
+        fa.es_poses = es;
+        fa.rounds = d_rounds + 7 * c0;  // round k of pair b at rounds + 7 ((k - 1) B' + b), B' = this chunk's pairs
+        fa.final_poses = pa;
+        fa.num_problems = cnt;
+        fa.num_rounds = rounds;
+        auto kern = frame_rounds_kernel<4>;
+        PNEC_CUDA(ensure_dyn_smem(h, kern, dyn));
+        kern<<<static_cast<unsigned>(cnt), 128, dyn, cs>>>(fa);
+        PNEC_CUDA(cudaGetLastError());
+        h->launches++;
+        init = pa;
+      } else {
       auto round_poses = [&](int k) {  // k = 0: the eigensolver pose; k >= 1: round k
         return k == 0 ? es : d_rounds + 7 * (static_cast<long long>(k - 1) * B + c0);
       };
@@ -1443,8 +1475,8 @@ int pnec_frame_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_f
           if ((rcc = run_scf_round(k)) != PNEC_OK) return rcc;
         }
       }
-      const double *cur = round_poses(rounds);
-      init = cur;
+      init = round_poses(rounds);
+      }
     } else if (!nec && opts->weighted_iterations == 0) {
       normalize_poses_kernel<<<static_cast<unsigned>((cnt + 127) / 128), 128, 0, cs>>>(bv.poses, pa, cnt);
       PNEC_CUDA(cudaGetLastError());
@@ -1470,6 +1502,7 @@ int pnec_frame_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_f
   int chunks = env_int("PNEC_B200_FRAME_CHUNKS", 0);
   if (chunks <= 0) chunks = B >= 4096 ? 4 : (B >= 1024 ? 2 : 1);
   chunks = std::min<long long>(std::min(chunks, pnec_handle::kMaxChunks), B);
+  if (fused_rounds) chunks = 1;  // the fused kernel lays its round poses out for one chunk
   if (chunks == 1) {
     rc = run_chunk(0, B, 0, stream);
     if (rc != PNEC_OK) return rc;

@@ -547,32 +547,18 @@ struct EsLmArgs {
 constexpr int kEsLmThreads = 128;
 constexpr int kEsLmPairs = kEsLmThreads / 4;  // four lanes per frame pair
 
-// Four lanes per frame pair: they share the function evaluation (see es_smallest_ev) and run the
-// scalar Levenberg-Marquardt logic redundantly, so a group never diverges.  States of the evaluation
-// loop: 0 = f(x0), 1..3 = forward-difference column j = state - 1, 4 = trial point.
-__global__ void __launch_bounds__(kEsLmThreads) es_lm_kernel(const __grid_constant__ EsLmArgs args) {
-  __shared__ double s_mom[kEsMom * kEsLmPairs];
-  const int tid = threadIdx.x, sub = tid & 3, slot = tid >> 2;
-  const long long b = static_cast<long long>(blockIdx.x) * kEsLmPairs + slot;
-  const bool in_range = b < args.num_problems;
-  const long long bb = in_range ? b : args.num_problems - 1;
-  const bool passthrough = in_range && args.fixed && args.fixed[bb];
-  const bool active = in_range && !passthrough;
-  // coalesced staging of this CTA's moments, transposed to [k][thread]
-  {
-    const long long first = static_cast<long long>(blockIdx.x) * kEsLmPairs;
-    const long long cnt = min(static_cast<long long>(kEsLmPairs), args.num_problems - first);
-    for (long long i = tid; i < cnt * kEsMom; i += kEsLmThreads) {
-      const int p = static_cast<int>(i / kEsMom), k = static_cast<int>(i % kEsMom);
-      s_mom[k * kEsLmPairs + p] = args.moments[first * kEsMom + i];
-    }
-    __syncthreads();
-  }
-  const double *mom = s_mom + (active ? slot : 0);
-  const double *pin = args.poses_in + 7 * bb;
-  // opengv::math::rot2cayley: [c]x = (R - I)(R + I)^-1, i.e. q_xyz / q_w
-  double x[3] = {pin[0] / pin[3], pin[1] / pin[3], pin[2] / pin[3]};
+// The Levenberg-Marquardt run of one 4-lane group (opengv's eigensolver_main on the 36 moments at
+// `mom`, consecutive moments `stride` doubles apart).  Must be called by all 32 lanes of a warp;
+// groups without work pass active = false.  The four lanes share the function evaluation (see
+// es_smallest_ev) and run the scalar logic redundantly, so a group never diverges.  States of the
+// evaluation loop: 0 = f(x0), 1..3 = forward-difference column j = state - 1, 4 = trial point.
+struct EsLmParams {
+  double ftol, xtol, gtol, factor;
+  int maxfev;
+};
 
+__device__ __forceinline__ void es_lm_group(const double *mom, int stride, const EsLmParams &args, bool active,
+                                            int sub, double x[3], int &info_out, int &nfev_out) {
   const double epsmch = DBL_EPSILON;
   const double eps = sqrt(epsmch);  // epsfcn = 0
   double fvec[3] = {0, 0, 0}, r[3][3], diag[3] = {1, 1, 1}, dp[3], qtf[3] = {0, 0, 0}, wa1[3], wa2[3], acn[3];
@@ -597,7 +583,7 @@ __global__ void __launch_bounds__(kEsLmThreads) es_lm_kernel(const __grid_consta
       xe[0] = wa2[0]; xe[1] = wa2[1]; xe[2] = wa2[2];
     }
     double fe[3];
-    es_smallest_ev(mom, kEsLmPairs, xe, sub, fe);
+    es_smallest_ev(mom, stride, xe, sub, fe);
     if (done) continue;
 
     bool need_step = false;
@@ -737,6 +723,37 @@ __global__ void __launch_bounds__(kEsLmThreads) es_lm_kernel(const __grid_consta
       state = 4;
     }
   }
+  info_out = info;
+  nfev_out = nfev;
+}
+
+// Four lanes per frame pair (es_lm_group), 32 pairs per CTA, moments staged in shared memory.
+__global__ void __launch_bounds__(kEsLmThreads) es_lm_kernel(const __grid_constant__ EsLmArgs args) {
+  __shared__ double s_mom[kEsMom * kEsLmPairs];
+  const int tid = threadIdx.x, sub = tid & 3, slot = tid >> 2;
+  const long long b = static_cast<long long>(blockIdx.x) * kEsLmPairs + slot;
+  const bool in_range = b < args.num_problems;
+  const long long bb = in_range ? b : args.num_problems - 1;
+  const bool passthrough = in_range && args.fixed && args.fixed[bb];
+  const bool active = in_range && !passthrough;
+  // coalesced staging of this CTA's moments, transposed to [k][thread]
+  {
+    const long long first = static_cast<long long>(blockIdx.x) * kEsLmPairs;
+    const long long cnt = min(static_cast<long long>(kEsLmPairs), args.num_problems - first);
+    for (long long i = tid; i < cnt * kEsMom; i += kEsLmThreads) {
+      const int p = static_cast<int>(i / kEsMom), k = static_cast<int>(i % kEsMom);
+      s_mom[k * kEsLmPairs + p] = args.moments[first * kEsMom + i];
+    }
+    __syncthreads();
+  }
+  const double *mom = s_mom + (active ? slot : 0);
+  const double *pin = args.poses_in + 7 * bb;
+  // opengv::math::rot2cayley: [c]x = (R - I)(R + I)^-1, i.e. q_xyz / q_w
+  double x[3] = {pin[0] / pin[3], pin[1] / pin[3], pin[2] / pin[3]};
+
+  const EsLmParams params{args.ftol, args.xtol, args.gtol, args.factor, args.maxfev};
+  int info = 0, nfev = 0;
+  es_lm_group(mom, kEsLmPairs, params, active, sub, x, info, nfev);
   if (passthrough && sub == 0) {
     double *po = args.poses_out + 7 * b;
 #pragma unroll

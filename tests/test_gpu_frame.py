@@ -289,3 +289,20 @@ def test_frame_solve_degenerate_inputs_terminate(handle):
     ref, _ = oracle.frame_solve_batch(batch.bvs_host, batch.bvs_target, batch.covs_target, batch.init_poses,
                                       oracle.default_frame_opts(), offsets=batch.offsets)
     assert rotation_angle(res.poses[6], ref[6]) <= ROT_TOL
+
+
+def test_fused_rounds_kernel_matches_per_round_kernels(handle, monkeypatch):
+    """Small batches run all weighted rounds of a pair in one launch (pnec_frame.cuh): same device
+    functions and order of operations as the per-round kernels, compiled into a different kernel, so
+    the results may differ in the last bit (the compiler's choice of which product of a sum of
+    products to fuse) but no more."""
+    counts = np.array([200, 64, 333, 0, 12, 512, 97, 150], dtype=np.int64)
+    batch = syn.make_batch(len(counts), 0, seed=95, counts=counts)
+    args = (batch.bvs_host, batch.bvs_target, batch.covs_target, batch.init_poses)
+    for kw in (dict(), dict(weighted_iterations=2), dict(use_ceres=0)):
+        monkeypatch.setenv("PNEC_B200_FUSED_ROUNDS_MAX_PAIRS", "512")
+        fused = handle.frame_solve_batch(*args, api.default_frame_opts(**kw), offsets=batch.offsets)
+        monkeypatch.setenv("PNEC_B200_FUSED_ROUNDS_MAX_PAIRS", "0")
+        rounds = handle.frame_solve_batch(*args, api.default_frame_opts(**kw), offsets=batch.offsets)
+        np.testing.assert_allclose(fused.poses, rounds.poses, rtol=0, atol=1e-13)
+        np.testing.assert_array_equal(fused.es_poses, rounds.es_poses)
