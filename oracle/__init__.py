@@ -7,6 +7,9 @@ cpu_baseline / --impl reference legs of bench.py.  The product package
 Parity status: residual functors pinned against the reference's numpy energies
 (tests/golden/); the Ceres LM loop is restated from upstream behaviour and is
 PARITY UNPINNED (Ceres is neither vendored by the reference nor installed here).
+Front stages of PNEC::Solve (oracle/pnec_oracle_frame.c): the eigensolver's LM is
+pinned against scipy's MINPACK, its eigenvalue/gradient against numpy; that the
+restated steps are what opengv executes is PARITY UNPINNED (opengv unavailable).
 """
 from __future__ import annotations
 

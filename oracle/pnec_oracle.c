@@ -17,6 +17,10 @@
  *     numeric_diff.h, manifold.cc) as documented in SURVEY.md section 8c.  The
  *     reference holds no golden vectors for it.
  *
+ *   - front stages of PNEC::Solve (opengv's rotation eigensolver, weighted eigensolver,
+ *     orchestration): pnec_oracle_frame.c, included at the end of this file; its header states
+ *     what is pinned (the LM against MINPACK) and what is not (that it is what opengv executes).
+ *
  * What is restated, with the reference lines it follows:
  *   functor_*            include/optimization/pnec_residual.h:50-150,
  *                        include/optimization/nec_residual.h:47-69
