@@ -253,18 +253,31 @@ __device__ __forceinline__ void scf_terms(const double R[9], double reg, const d
   out[8] = dot3(G[2], Su[2]) + reg;  // zz
 }
 
+// One Rayleigh quotient (t.n)^2 / (t^T B t) added to `acc`, with the rounding sequence spelled out
+// (explicit fma / __dmul_rn: nothing for the compiler to contract differently in different kernels or
+// call sites), so that every path that sums a candidate's terms in the same order gets the same bits.
+struct ScfDir {
+  double t0, t1, t2, txx, txy, txz, tyy, tyz, tzz;
+};
+__device__ __forceinline__ ScfDir scf_dir(const double t[3]) {
+  ScfDir d;
+  d.t0 = t[0]; d.t1 = t[1]; d.t2 = t[2];
+  d.txx = __dmul_rn(t[0], t[0]); d.txy = __dmul_rn(2.0 * t[0], t[1]); d.txz = __dmul_rn(2.0 * t[0], t[2]);
+  d.tyy = __dmul_rn(t[1], t[1]); d.tyz = __dmul_rn(2.0 * t[1], t[2]); d.tzz = __dmul_rn(t[2], t[2]);
+  return d;
+}
+__device__ __forceinline__ double scf_add_term(const ScfDir &d, const double *w, double acc) {
+  const double e = fma(d.t2, w[2], fma(d.t1, w[1], __dmul_rn(d.t0, w[0])));
+  const double den = fma(w[8], d.tzz, fma(w[7], d.tyz, fma(w[6], d.tyy, fma(w[5], d.txz, fma(w[4], d.txy, __dmul_rn(w[3], d.txx))))));
+  return fma(__dmul_rn(e, e), fast_rcp(den), acc);
+}
+
 // sum_i (t.n_i)^2 / (t^T B_i t) over the correspondences in shared memory, in index order
 // (obj_fun, scf.cc:43-51)
 __device__ __forceinline__ double scf_objective(const double *terms, int n, const double t[3]) {
-  const double txx = t[0] * t[0], txy = 2.0 * t[0] * t[1], txz = 2.0 * t[0] * t[2];
-  const double tyy = t[1] * t[1], tyz = 2.0 * t[1] * t[2], tzz = t[2] * t[2];
+  const ScfDir d = scf_dir(t);
   double cost = 0.0;
-  for (int i = 0; i < n; ++i) {
-    const double *w = terms + 9 * i;  // same address in every lane: broadcast
-    const double e = t[0] * w[0] + t[1] * w[1] + t[2] * w[2];
-    const double den = w[3] * txx + w[4] * txy + w[5] * txz + w[6] * tyy + w[7] * tyz + w[8] * tzz;
-    cost = fma(e * e, fast_rcp(den), cost);
-  }
+  for (int i = 0; i < n; ++i) cost = scf_add_term(d, terms + 9 * i, cost);  // same address in every lane: broadcast
   return cost;
 }
 
@@ -272,42 +285,42 @@ __device__ __forceinline__ double scf_objective(const double *terms, int n, cons
 // non-negative, so the partial sums only grow: a sum that is abandoned would have ended above the
 // bound as well, and one that is not abandoned is returned unchanged (same operations, same order).
 __device__ __forceinline__ double scf_objective_bounded(const double *terms, int n, const double t[3], double bound) {
-  const double txx = t[0] * t[0], txy = 2.0 * t[0] * t[1], txz = 2.0 * t[0] * t[2];
-  const double tyy = t[1] * t[1], tyz = 2.0 * t[1] * t[2], tzz = t[2] * t[2];
+  const ScfDir d = scf_dir(t);
   double cost = 0.0;
   for (int i0 = 0; i0 < n; i0 += 4) {
     const int i1 = min(i0 + 4, n);
-    for (int i = i0; i < i1; ++i) {
-      const double *w = terms + 9 * i;
-      const double e = t[0] * w[0] + t[1] * w[1] + t[2] * w[2];
-      const double den = w[3] * txx + w[4] * txy + w[5] * txz + w[6] * tyy + w[7] * tyz + w[8] * tzz;
-      cost = fma(e * e, fast_rcp(den), cost);
-    }
+    for (int i = i0; i < i1; ++i) cost = scf_add_term(d, terms + 9 * i, cost);
     if (cost > bound) break;
   }
   return cost;
 }
 
-// The rest of a candidate's sum, correspondences [begin, n): by one lane in index order
-// (`warp_parallel` false) or by the 32 lanes of a warp, lane-strided and tree-reduced in a fixed
-// order (every lane gets the sum).
-__device__ __forceinline__ double scf_objective_tail(const double *terms, int begin, int n, const double t[3],
-                                                     int lane, bool warp_parallel) {
-  const double txx = t[0] * t[0], txy = 2.0 * t[0] * t[1], txz = 2.0 * t[0] * t[2];
-  const double tyy = t[1] * t[1], tyz = 2.0 * t[1] * t[2], tzz = t[2] * t[2];
+// The rest of a candidate's sum, correspondences [begin, n), by one lane in index order.
+__device__ __forceinline__ double scf_objective_tail(const double *terms, int begin, int n, const double t[3]) {
+  const ScfDir d = scf_dir(t);
   double cost = 0.0;
-  const int first = warp_parallel ? begin + lane : begin, step = warp_parallel ? 32 : 1;
-  for (int i = first; i < n; i += step) {
-    const double *w = terms + 9 * i;
-    const double e = t[0] * w[0] + t[1] * w[1] + t[2] * w[2];
-    const double den = w[3] * txx + w[4] * txy + w[5] * txz + w[6] * tyy + w[7] * tyz + w[8] * tzz;
-    cost = fma(e * e, fast_rcp(den), cost);
-  }
-  if (warp_parallel) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
-  }
+  for (int i = begin; i < n; ++i) cost = scf_add_term(d, terms + 9 * i, cost);
   return cost;
+}
+
+// One 64-correspondence chunk [base, base + 64) of a candidate's sum the way a warp computes it —
+// lane l sums elements base + l and base + 32 + l, then a xor-butterfly over the lanes — but
+// evaluated by ONE lane (the butterfly's additions replayed in the same order: after the step with
+// offset o the lower o slots hold what lanes 0 .. o-1 hold).  Same bits as the warp version.
+__device__ __forceinline__ double scf_chunk_one_lane(const double *terms, int base, int n, const ScfDir &d) {
+  double p[32];
+#pragma unroll
+  for (int l = 0; l < 32; ++l) {
+    double c = 0.0;
+    if (base + l < n) c = scf_add_term(d, terms + 9 * (base + l), c);
+    if (base + 32 + l < n) c = scf_add_term(d, terms + 9 * (base + 32 + l), c);
+    p[l] = c;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int l = 0; l < o; ++l) p[l] += p[l + o];
+  return p[0];
 }
 
 template <int NW>
@@ -377,16 +390,10 @@ __device__ __forceinline__ void scf_pair(const ScfArgs &args, const long long b)
   const double t0[3] = {tsrc[0], tsrc[1], tsrc[2]};
   double cost0;
   {
-    const double txx = t0[0] * t0[0], txy = 2.0 * t0[0] * t0[1], txz = 2.0 * t0[0] * t0[2];
-    const double tyy = t0[1] * t0[1], tyz = 2.0 * t0[1] * t0[2], tzz = t0[2] * t0[2];
     double part = 0.0;
     if (warp < NWA) {
-      for (int i = tid; i < n; i += NTA) {
-        const double *w = terms + 9 * i;
-        const double e = t0[0] * w[0] + t0[1] * w[1] + t0[2] * w[2];
-        const double den = w[3] * txx + w[4] * txy + w[5] * txz + w[6] * tyy + w[7] * tyz + w[8] * tzz;
-        part = fma(e * e, fast_rcp(den), part);
-      }
+      const ScfDir d0 = scf_dir(t0);
+      for (int i = tid; i < n; i += NTA) part = scf_add_term(d0, terms + 9 * i, part);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
       if (lane == 0) s_best_cost[warp] = part;
@@ -446,10 +453,29 @@ __device__ __forceinline__ void scf_pair(const ScfArgs &args, const long long b)
       best = CUDART_INF; best_idx = 0x7fffffff;
       for (int c = 1 + tid; c <= args.samples; c += NT) {
         const double t[3] = {args.sphere[3 * (c - 1)], args.sphere[3 * (c - 1) + 1], args.sphere[3 * (c - 1) + 2]};
-        const double cost = scf_objective(terms, npre, t) + scf_objective_tail(terms, npre, n, t, lane, false);
+        const double cost = scf_objective(terms, npre, t) + scf_objective_tail(terms, npre, n, t);
         if (cost < best || (cost == best && c < best_idx)) { best = cost; best_idx = c; }
       }
     } else {
+      if (NW >= 16 && nsurv > 8 * NW) {  // compile-time: only the 16-warp kernel carries this path
+        // many survivors (a flat cost landscape): one candidate per LANE, no shuffles; every chunk is
+        // summed in the order a warp would use (scf_chunk_one_lane), so a candidate's cost does not
+        // depend on which of the two paths completed it
+        for (int sv = tid; sv < nsurv; sv += NT) {
+          const int c = s_surv_idx[sv];
+          double cost = s_surv_part[sv];
+          const double t[3] = {args.sphere[3 * (c - 1)], args.sphere[3 * (c - 1) + 1], args.sphere[3 * (c - 1) + 2]};
+          const ScfDir d = scf_dir(t);
+          bool alive = !(cost > __longlong_as_double(static_cast<long long>(*reinterpret_cast<volatile unsigned long long *>(&s_bound))));
+          for (int base = npre; alive && base < n; base += 64) {
+            cost += scf_chunk_one_lane(terms, base, n, d);
+            alive = !(cost > __longlong_as_double(static_cast<long long>(*reinterpret_cast<volatile unsigned long long *>(&s_bound))));
+          }
+          if (!alive) continue;
+          if (cost < best || (cost == best && c < best_idx)) { best = cost; best_idx = c; }
+          atomicMin(&s_bound, static_cast<unsigned long long>(__double_as_longlong(cost)));
+        }
+      } else {
       for (int sv = warp; sv < nsurv; sv += NW) {  // warp-uniform
         const int c = s_surv_idx[sv];
         const double part = s_surv_part[sv];
@@ -460,8 +486,7 @@ __device__ __forceinline__ void scf_pair(const ScfArgs &args, const long long b)
         const double t[3] = {args.sphere[3 * (c - 1)], args.sphere[3 * (c - 1) + 1], args.sphere[3 * (c - 1) + 2]};
         // the rest of the sum by the whole warp, 64 correspondences at a time, re-checking the
         // bound after every chunk: cost = part + chunk sums in order (fixed, timing-independent)
-        const double txx = t[0] * t[0], txy = 2.0 * t[0] * t[1], txz = 2.0 * t[0] * t[2];
-        const double tyy = t[1] * t[1], tyz = 2.0 * t[1] * t[2], tzz = t[2] * t[2];
+        const ScfDir d = scf_dir(t);
         double cost = part;
         bool alive = true;
         for (int base = npre; base < n; base += 64) {
@@ -469,12 +494,7 @@ __device__ __forceinline__ void scf_pair(const ScfArgs &args, const long long b)
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
             const int i = base + 32 * k + lane;
-            if (i < n) {
-              const double *w = terms + 9 * i;
-              const double e = t[0] * w[0] + t[1] * w[1] + t[2] * w[2];
-              const double den = w[3] * txx + w[4] * txy + w[5] * txz + w[6] * tyy + w[7] * tyz + w[8] * tzz;
-              chunk = fma(e * e, fast_rcp(den), chunk);
-            }
+            if (i < n) chunk = scf_add_term(d, terms + 9 * i, chunk);
           }
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) chunk += __shfl_xor_sync(0xffffffffu, chunk, o);
@@ -486,6 +506,7 @@ __device__ __forceinline__ void scf_pair(const ScfArgs &args, const long long b)
         if (!alive) continue;
         if (cost < best || (cost == best && c < best_idx)) { best = cost; best_idx = c; }
         if (lane == 0) atomicMin(&s_bound, static_cast<unsigned long long>(__double_as_longlong(cost)));
+      }
       }
     }
     // every lane of a warp holds the same (best, best_idx) in the survivor path, its own in the others
