@@ -268,7 +268,9 @@ __device__ __forceinline__ ScfDir scf_dir(const double t[3]) {
 }
 __device__ __forceinline__ double scf_add_term(const ScfDir &d, const double *w, double acc) {
   const double e = fma(d.t2, w[2], fma(d.t1, w[1], __dmul_rn(d.t0, w[0])));
-  const double den = fma(w[8], d.tzz, fma(w[7], d.tyz, fma(w[6], d.tyy, fma(w[5], d.txz, fma(w[4], d.txy, __dmul_rn(w[3], d.txx))))));
+  // t^T B t as three independent pairs (a shorter dependent chain than one long fma ladder)
+  const double den = __dadd_rn(__dadd_rn(fma(w[4], d.txy, __dmul_rn(w[3], d.txx)), fma(w[6], d.tyy, __dmul_rn(w[5], d.txz))),
+                               fma(w[8], d.tzz, __dmul_rn(w[7], d.tyz)));
   return fma(__dmul_rn(e, e), fast_rcp(den), acc);
 }
 
@@ -323,7 +325,7 @@ __device__ __forceinline__ double scf_chunk_one_lane(const double *terms, int ba
   return p[0];
 }
 
-template <int NW>
+template <int NW, bool LANE_SERIAL = false>
 __device__ __forceinline__ void scf_pair(const ScfArgs &args, const long long b) {
   constexpr int NT = NW * 32;
   // Sums whose value depends on how they are split over threads (cost0, E of the SCF steps) are
@@ -457,7 +459,7 @@ __device__ __forceinline__ void scf_pair(const ScfArgs &args, const long long b)
         if (cost < best || (cost == best && c < best_idx)) { best = cost; best_idx = c; }
       }
     } else {
-      if (NW >= 16 && nsurv > 8 * NW) {  // compile-time: only the 16-warp kernel carries this path
+      if (LANE_SERIAL && nsurv > 8 * NW) {  // compile-time: only the pass-2 kernel carries this path
         // many survivors (a flat cost landscape): one candidate per LANE, no shuffles; every chunk is
         // summed in the order a warp would use (scf_chunk_one_lane), so a candidate's cost does not
         // depend on which of the two paths completed it
@@ -660,7 +662,7 @@ __global__ void __launch_bounds__(NW * 32) scf_list_kernel(const __grid_constant
     __syncthreads();
     const int k = s_work;
     if (k >= count) return;
-    scf_pair<NW>(args, args.work_list[k]);
+    scf_pair<NW, true>(args, args.work_list[k]);
   }
 }
 
