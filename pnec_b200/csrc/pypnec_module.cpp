@@ -124,6 +124,35 @@ py::array_t<double> pyceresnec(const py::object &host_bvs, const py::object &tar
   return matrix_from_pose(optimizer.Result());
 }
 
+// Addition to the reference's module: the whole frame solve, PNEC::Solve with use_ransac_ = false
+// (src/rel_pose_estimation/pnec.cc:77-124), with the Options fields it reads as keyword arguments.
+py::array_t<double> pysolve(const py::object &host_bvs, const py::object &target_bvs,
+                            const py::object &target_covariances, const py::object &init_pose,
+                            double regularization, int weighted_iterations, bool use_nec, bool use_ceres) {
+  arr f1 = as_vectors(host_bvs, "host_bvs"), f2 = as_vectors(target_bvs, "target_bvs");
+  const py::ssize_t n = f1.shape(0);
+  if (f2.shape(0) != n) throw std::invalid_argument("host_bvs and target_bvs differ in length");
+  if (weighted_iterations < 0) throw std::invalid_argument("weighted_iterations < 0");
+  std::vector<double> c2 = as_covariances(target_covariances, n, "target_covariances");
+  const pnec::SE3 sp_init_pose = pose_from_matrix(init_pose);
+  pnec::rel_pose_estimation::Options options;
+  options.use_ransac_ = false;
+  options.use_nec_ = use_nec;
+  options.use_ceres_ = use_ceres;
+  options.weighted_iterations_ = static_cast<std::size_t>(weighted_iterations);
+  options.regularization_ = regularization;
+  pnec::rel_pose_estimation::PNEC solver(options);
+  Span3 s1{reinterpret_cast<const pnec::Vec3 *>(f1.data()), static_cast<size_t>(n)};
+  Span3 s2{reinterpret_cast<const pnec::Vec3 *>(f2.data()), static_cast<size_t>(n)};
+  Span9 m2{reinterpret_cast<const pnec::Mat3 *>(c2.data()), static_cast<size_t>(n)};
+  pnec::SE3 result;
+  {
+    py::gil_scoped_release release;
+    result = solver.Solve(s1, s2, m2, sp_init_pose);
+  }
+  return matrix_from_pose(result);
+}
+
 // Batched: bvs (B,N,3), covariances (B,N,3,3) or None, init_poses (B,4,4) -> (B,4,4)
 py::array_t<double> solve_batch(int variant, const py::object &host_bvs, const py::object &target_bvs,
                                 const py::object &host_covariances, const py::object &target_covariances,
@@ -197,6 +226,10 @@ PYBIND11_MODULE(pypnec, m) {
         "ceres");  // docstrings as in python/pypnec.cpp:252-253
   m.def("pyceresnec", &pyceresnec, py::arg("host_bvs"), py::arg("target_bvs"), py::arg("init_pose"),
         "ceres nec");
+  m.def("pysolve", &pysolve, py::arg("host_bvs"), py::arg("target_bvs"), py::arg("target_covariances"),
+        py::arg("init_pose"), py::arg("regularization") = 1.0e-13, py::arg("weighted_iterations") = 10,
+        py::arg("use_nec") = false, py::arg("use_ceres") = true,
+        "PNEC::Solve without RANSAC: NEC eigensolver, weighted eigensolver + SCF, refinement");
   m.def("pyceres_batch",
         [](const py::object &a, const py::object &b, const py::object &c, const py::object &d,
            const py::object &e, double reg) { return solve_batch(PNEC_VARIANT_SYMMETRIC, a, b, c, d, e, reg); },

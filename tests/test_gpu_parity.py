@@ -480,6 +480,12 @@ def test_pypnec_module_matches_oracle():
     assert rotation_angle(gott, reft) <= ROT_TOL and direction_angle(gott[4:], reft[4:]) <= DIR_TOL
     with pytest.raises(ValueError):
         pypnec.pyceresnec(f1, f2[:-1], init)
+    # addition: the whole frame solve (PNEC::Solve without RANSAC)
+    full = pypnec.pysolve(f1, f2, cov_t, init, 1e-13)
+    fref, _ = oracle.frame_solve_batch(b.bvs_host, b.bvs_target, b.covs_target, b.init_poses,
+                                       oracle.default_frame_opts(), n_per_problem=N)
+    gotf = np.concatenate([syn.matrix_to_quaternion(full[:3, :3]), full[:3, 3]])
+    assert rotation_angle(gotf, fref[0]) <= ROT_TOL and direction_angle(gotf[4:], fref[0][4:]) <= DIR_TOL
 
 
 def test_cpp_compat_api_matches_oracle(tmp_path):
