@@ -97,6 +97,18 @@ class OracleFrameOpts(ctypes.Structure):
     ]
 
 
+class OracleRansacOpts(ctypes.Structure):
+    """opengv::sac::Ransac settings as PNEC::Eigensolver uses them (pnec.cc:241-251)."""
+    _fields_ = [
+        ("max_iterations", ctypes.c_int32),
+        ("sample_size", ctypes.c_int32),
+        ("threshold", ctypes.c_double),
+        ("probability", ctypes.c_double),
+        ("max_variation", ctypes.c_double),
+        ("seed", ctypes.c_uint64),
+    ]
+
+
 INFO_DTYPE = np.dtype(
     [
         ("status", np.int32),
@@ -190,6 +202,11 @@ def lib() -> ctypes.CDLL:
         L.oracle_frame_solve_batch.argtypes = [ctypes.POINTER(OracleFrameOpts), ctypes.c_int64, ctypes.c_int64,
                                                ctypes.POINTER(ctypes.c_int64), dp, dp, dp, dp, dp, dp, ctypes.c_int]
         L.oracle_frame_solve_batch.restype = ctypes.c_int
+        L.oracle_ransac_opts_default.argtypes = [ctypes.POINTER(OracleRansacOpts)]
+        L.oracle_ransac_opts_default.restype = None
+        L.oracle_ransac_eigensolver.argtypes = [ctypes.POINTER(OracleRansacOpts), ctypes.c_int64, ctypes.c_int64,
+                                                dp, dp, dp, dp, ctypes.POINTER(ctypes.c_uint8), ip, ip]
+        L.oracle_ransac_eigensolver.restype = ctypes.c_int
         _lib = L
     return _lib
 
@@ -473,3 +490,25 @@ def frame_solve_batch(f1, f2, cov, init_poses, opts: OracleFrameOpts, offsets=No
     if rc != 0:
         raise RuntimeError("oracle_frame_solve_batch failed")
     return out, es
+
+
+def ransac_eigensolver(f1, f2, init_pose7, pair_index=0, **overrides):
+    """PNEC::Eigensolver with use_ransac_ (pnec.cc:239-272), restated (groundwork, no CUDA path yet)
+    -> (pose7, inlier mask (n,) bool, iterations)."""
+    f1, f2, p = _c(f1, (3,)), _c(f2, (3,)), _c(init_pose7)
+    o = OracleRansacOpts()
+    lib().oracle_ransac_opts_default(ctypes.byref(o))
+    for k, v in overrides.items():
+        if not hasattr(o, k):
+            raise AttributeError(k)
+        setattr(o, k, v)
+    out = np.zeros(7)
+    mask = np.zeros(f1.shape[0], dtype=np.uint8)
+    ni, it = ctypes.c_int32(), ctypes.c_int32()
+    rc = lib().oracle_ransac_eigensolver(ctypes.byref(o), int(pair_index), f1.shape[0], _dp(f1), _dp(f2), _dp(p),
+                                         _dp(out), mask.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)),
+                                         ctypes.byref(ni), ctypes.byref(it))
+    if rc != 0:
+        raise RuntimeError(f"oracle_ransac_eigensolver failed ({rc})")
+    assert int(mask.sum()) == ni.value
+    return out, mask.astype(bool), it.value

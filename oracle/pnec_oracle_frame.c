@@ -722,3 +722,188 @@ int oracle_frame_solve_batch(const oracle_frame_opts *o, int64_t num_problems, i
   }
   return rc;
 }
+
+/* ------------------------------------------------------------------ RANSAC
+ *
+ * GROUNDWORK for SURVEY.md section 8f row 3 (no CUDA counterpart yet): PNEC::Eigensolver with
+ * use_ransac_ == true (src/rel_pose_estimation/pnec.cc:239-272), i.e.
+ *   opengv::sac::Ransac<opengv::sac_problems::relative_pose::EigensolverSacProblem>
+ * with threshold_ = 1e-6, max_iterations_ = Options::max_ransac_iterations_ (5000), sample size
+ * Options::ransac_sample_size_ (10), probability 0.99, followed by optimizeModelCoefficients on the
+ * inliers and TranslationFromM(ComposeM(inlier bvs, rotation)).
+ *
+ * PARITY UNPINNED, and only ever statistically pinnable: opengv (not in the reference tree) draws
+ * its samples and start perturbations with rand().  Restated from opengv's public sources as
+ * recalled (sac/implementation/Ransac.hpp `computeModel`, sac_problems/relative_pose/
+ * EigensolverSacProblem.cpp, triangulation/methods.cpp `triangulate2`):
+ *   per iteration: a sample of `sample_size` distinct correspondences; start rotation = R12 with its
+ *   Cayley parameters moved by U(-0.01, 0.01) each; eigensolver on the sample -> rotation, and
+ *   translation = eigenvector of the smallest eigenvalue of M (sign: towards the optical flow of the
+ *   sample's first correspondence); score of every correspondence = (1 - f1 . p/|p|) + (1 - f2 . p'/|p'|)
+ *   with p the midpoint triangulation and p' = R^T (p - t); inlier iff score < threshold; keep the
+ *   first model with strictly more inliers; k = log(1 - 0.99) / log(1 - w^n) after every improvement;
+ *   stop when iterations >= k or > max_iterations.
+ * Differences by construction: the random stream (a counter-based generator keyed by (seed, pair,
+ * iteration, draw), so that a parallel implementation can replay it) and samples drawn by a fresh
+ * partial Fisher-Yates per iteration (opengv keeps its shuffled index array across iterations: the
+ * same distribution, a different stream).
+ */
+
+static uint64_t rs_mix(uint64_t z) { /* splitmix64 finaliser */
+  z += 0x9e3779b97f4a7c15ULL;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+  return z ^ (z >> 31);
+}
+/* uniform in [0, 1) for (seed, pair, iteration, draw) */
+static double rs_uniform(uint64_t seed, uint64_t pair, uint64_t iteration, uint64_t draw) {
+  const uint64_t h = rs_mix(rs_mix(rs_mix(seed ^ 0x51ed270b7a2f3c15ULL) + pair) + (iteration << 8) + draw);
+  return (double)(h >> 11) * (1.0 / 9007199254740992.0);
+}
+
+typedef struct oracle_ransac_opts {
+  int32_t max_iterations; /* 5000 */
+  int32_t sample_size;    /* 10   */
+  double threshold;       /* 1e-6 */
+  double probability;     /* 0.99 */
+  double max_variation;   /* 0.01 */
+  uint64_t seed;
+} oracle_ransac_opts;
+
+void oracle_ransac_opts_default(oracle_ransac_opts *o) {
+  o->max_iterations = 5000;
+  o->sample_size = 10;
+  o->threshold = 1.0e-6;
+  o->probability = 0.99;
+  o->max_variation = 0.01;
+  o->seed = 1;
+}
+
+/* opengv::triangulation::triangulate2 (midpoint) + the bearing-vector reprojection score of
+ * EigensolverSacProblem::getSelectedDistancesToModel */
+static double ransac_score(const double R[3][3], const double t[3], const double f1[3], const double f2[3]) {
+  double g[3];
+  matvec(R, f2, g); /* f2 in frame 1 */
+  const double b0 = dot3(t, f1), b1 = dot3(t, g);
+  const double a00 = dot3(f1, f1), a10 = dot3(f1, g), a01 = -a10, a11 = -dot3(g, g);
+  const double det = a00 * a11 - a01 * a10;
+  const double l0 = (a11 * b0 - a01 * b1) / det, l1 = (-a10 * b0 + a00 * b1) / det;
+  double p[3], pp[3], d[3];
+  for (int k = 0; k < 3; ++k) p[k] = 0.5 * (l0 * f1[k] + t[k] + l1 * g[k]);
+  for (int k = 0; k < 3; ++k) d[k] = p[k] - t[k];
+  for (int k = 0; k < 3; ++k) pp[k] = R[0][k] * d[0] + R[1][k] * d[1] + R[2][k] * d[2]; /* R^T (p - t) */
+  const double np = norm_n(p, 3), npp = norm_n(pp, 3);
+  return (1.0 - dot3(f1, p) / np) + (1.0 - dot3(f2, pp) / npp);
+}
+
+/* eigensolver on a subset: rotation (quaternion) + translation direction with opengv's sign rule */
+static void ransac_model(int64_t m, const int64_t *idx, const double *f1, const double *f2, const double start_cayley[3],
+                         double R[3][3], double t[3], double quat[4]) {
+  es_moments mom;
+  memset(&mom, 0, sizeof(mom));
+  for (int64_t s = 0; s < m; ++s) {
+    const double *a = f1 + 3 * idx[s], *b = f2 + 3 * idx[s];
+    for (int u = 0; u < 3; ++u)
+      for (int v = 0; v < 3; ++v)
+        for (int r = 0; r < 3; ++r)
+          for (int c = 0; c < 3; ++c) mom.G[u][v][r][c] += a[u] * a[v] * b[r] * b[c];
+  }
+  lm_params p;
+  es_default_params(&p);
+  double x[3] = {start_cayley[0], start_cayley[1], start_cayley[2]};
+  lm_result res;
+  lm_minimize(es_step_fcn, &mom, &p, x, &res);
+  cayley2quat(x, quat);
+  quat_to_rot(quat, R);
+  double M[3][3], lam;
+  es_compose_m(&mom, x, M, NULL);
+  sym3_smallest_eigvec(M, t, &lam);
+  /* sign: along the optical flow f1 - R f2 of the first correspondence of the subset */
+  double g[3];
+  matvec(R, f2 + 3 * idx[0], g);
+  const double *a0 = f1 + 3 * idx[0];
+  const double flow = (a0[0] - g[0]) * t[0] + (a0[1] - g[1]) * t[1] + (a0[2] - g[2]) * t[2];
+  if (flow < 0.0)
+    for (int k = 0; k < 3; ++k) t[k] = -t[k];
+}
+
+/* PNEC::Eigensolver with RANSAC for one frame pair.  inlier_mask[n] (0/1), returns the number of
+ * RANSAC iterations in *iterations.  out_pose7: optimised rotation + TranslationFromM(ComposeM(inliers)). */
+int oracle_ransac_eigensolver(const oracle_ransac_opts *o, int64_t pair_index, int64_t n, const double *f1,
+                              const double *f2, const double init_pose7[7], double out_pose7[7],
+                              uint8_t *inlier_mask, int32_t *num_inliers, int32_t *iterations) {
+  const int ns = o->sample_size;
+  if (n < ns || ns < 1) return -2;
+  int64_t *perm = malloc(sizeof(int64_t) * (size_t)n), *sample = malloc(sizeof(int64_t) * (size_t)ns);
+  int64_t *inl = malloc(sizeof(int64_t) * (size_t)n);
+  if (!perm || !sample || !inl) return -1;
+  double c0[3];
+  rot2cayley_pose(init_pose7, c0);
+  int best = -1, iters = 0;
+  double bestR[3][3], bestt[3], bestq[4] = {0, 0, 0, 1}, k = 1.0;
+  memset(bestR, 0, sizeof(bestR));
+  memset(bestt, 0, sizeof(bestt));
+  while ((double)iters < k) {
+    for (int64_t i = 0; i < n; ++i) perm[i] = i;
+    for (int s = 0; s < ns; ++s) { /* partial Fisher-Yates */
+      const int64_t j = s + (int64_t)(rs_uniform(o->seed, (uint64_t)pair_index, (uint64_t)iters, (uint64_t)s) * (double)(n - s));
+      const int64_t tmp = perm[s];
+      perm[s] = perm[j];
+      perm[j] = tmp;
+      sample[s] = perm[s];
+    }
+    double c[3], R[3][3], t[3], q[4];
+    for (int d = 0; d < 3; ++d)
+      c[d] = c0[d] + (rs_uniform(o->seed, (uint64_t)pair_index, (uint64_t)iters, (uint64_t)(ns + d)) - 0.5) * 2.0 * o->max_variation;
+    ransac_model(ns, sample, f1, f2, c, R, t, q);
+    int count = 0;
+    for (int64_t i = 0; i < n; ++i)
+      if (ransac_score(R, t, f1 + 3 * i, f2 + 3 * i) < o->threshold) ++count;
+    if (count > best) {
+      best = count;
+      memcpy(bestR, R, sizeof(bestR));
+      memcpy(bestt, t, sizeof(bestt));
+      memcpy(bestq, q, sizeof(bestq));
+      const double w = (double)count / (double)n;
+      double p_no = 1.0 - pow(w, (double)ns);
+      if (p_no < DBL_EPSILON) p_no = DBL_EPSILON;
+      if (p_no > 1.0 - DBL_EPSILON) p_no = 1.0 - DBL_EPSILON;
+      k = log(1.0 - o->probability) / log(p_no);
+    }
+    ++iters;
+    if (iters > o->max_iterations) break;
+  }
+  int64_t ni = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const int in = ransac_score(bestR, bestt, f1 + 3 * i, f2 + 3 * i) < o->threshold;
+    if (inlier_mask) inlier_mask[i] = (uint8_t)in;
+    if (in) inl[ni++] = i;
+  }
+  if (num_inliers) *num_inliers = (int32_t)ni;
+  if (iterations) *iterations = iters;
+  /* optimizeModelCoefficients: eigensolver over the inliers from the best model's rotation, then
+   * TranslationFromM(ComposeM(in_bvs1, in_bvs2, rotation)) -- ComposeM skips the first inlier */
+  double R[3][3], t[3], q[4] = {bestq[0], bestq[1], bestq[2], bestq[3]};
+  if (ni >= 1) {
+    const double cb[3] = {bestq[0] / bestq[3], bestq[1] / bestq[3], bestq[2] / bestq[3]};
+    ransac_model(ni, inl, f1, f2, cb, R, t, q);
+    double Mi[3][3], lam;
+    memset(Mi, 0, sizeof(Mi));
+    for (int64_t s = 1; s < ni; ++s) {
+      double g[3], nrm[3];
+      matvec(R, f2 + 3 * inl[s], g);
+      cross3(f1 + 3 * inl[s], g, nrm);
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) Mi[r][c] += nrm[r] * nrm[c];
+    }
+    sym3_smallest_eigvec(Mi, t, &lam);
+  } else {
+    memcpy(t, init_pose7 + 4, sizeof(t));
+  }
+  memcpy(out_pose7, q, sizeof(q));
+  memcpy(out_pose7 + 4, t, sizeof(t));
+  free(perm);
+  free(sample);
+  free(inl);
+  return 0;
+}

@@ -162,3 +162,30 @@ def test_oracle_reproduces_committed_frame_fixtures(golden_frame):
         for k in np.nonzero(stable)[0]:
             assert rotation_angle(poses[k], g[f"{name}/default/poses"][k]) < 1e-9
             assert direction_angle(poses[k][4:], g[f"{name}/default/poses"][k][4:]) < 1e-9
+
+
+def test_ransac_restatement_separates_outliers():
+    """Groundwork for SURVEY 8f row 3 (no CUDA path yet): the restated opengv RANSAC over the
+    eigensolver (pnec.cc:239-272) on pairs with 25 % gross outliers finds the inlier set, stops after
+    the number of iterations opengv's formula prescribes, and recovers the rotation the plain
+    eigensolver loses."""
+    b = syn.make_batch(4, 300, seed=41, noise_level=0.25)
+    rng = np.random.default_rng(0)
+    for k in range(b.num_problems):
+        f1, f2, _, _ = b.problem(k)
+        f2 = f2.copy()
+        bad = rng.choice(300, 75, replace=False)
+        v = rng.standard_normal((75, 3))
+        f2[bad] = v / np.linalg.norm(v, axis=1, keepdims=True)
+        truth = np.ones(300, bool)
+        truth[bad] = False
+        pose, mask, iters = oracle.ransac_eigensolver(f1, f2, b.init_poses[k], pair_index=k)
+        assert (mask & ~truth).sum() == 0 and (mask & truth).sum() >= 0.95 * truth.sum()
+        w = mask.mean()
+        assert iters == int(np.ceil(np.log(0.01) / np.log(1 - w ** 10))) or iters <= 5001
+        plain, _ = oracle.nec_eigensolver_pose(f1, f2, b.init_poses[k])
+        assert rotation_angle(pose, b.gt_poses[k]) < 1e-3 < rotation_angle(plain, b.gt_poses[k])
+        # deterministic in (seed, pair index); a different seed draws different samples
+        again, mask2, _ = oracle.ransac_eigensolver(f1, f2, b.init_poses[k], pair_index=k)
+        np.testing.assert_array_equal(pose, again)
+        np.testing.assert_array_equal(mask, mask2)
