@@ -66,6 +66,32 @@ def test_options_struct_matches_oracle_layout():
     assert ctypes.sizeof(api.SolverOpts) == 4 * 4 + 10 * 8
 
 
+def test_frame_options_are_the_reference_defaults():
+    """pnec::rel_pose_estimation::Options (pnec_config.h:46-65) as PNEC::Solve reads it, except
+    use_ransac (not built: the default is the configuration that runs)."""
+    import oracle
+
+    f = api.default_frame_opts()
+    assert (f.use_nec, f.use_ceres, f.weighted_iterations, f.use_ransac) == (0, 1, 10, 0)
+    assert (f.fibonacci_samples, f.scf_steps) == (500, 10)  # literals of pnec.cc:331 and :342
+    assert f.ceres.regularization == 1e-13 and f.ceres.max_num_iterations == 50
+    assert ctypes.sizeof(api.FrameOpts) == 6 * 4 + ctypes.sizeof(api.SolverOpts)
+    o = oracle.default_frame_opts()
+    for name in ("use_nec", "use_ceres", "weighted_iterations", "fibonacci_samples", "scf_steps"):
+        assert getattr(o, name) == getattr(f, name), name
+    g = api.default_frame_opts(weighted_iterations=3, regularization=1e-10)
+    assert g.weighted_iterations == 3 and g.ceres.regularization == 1e-10
+    with pytest.raises(AttributeError):
+        api.default_frame_opts(no_such_field=1)
+
+
+def test_frame_entry_points_reject_null_arguments():
+    lib = api.load_library()
+    assert lib.pnec_frame_solve_batch(None, None, None, None, None) == -1
+    assert lib.pnec_eigensolver_batch(None, None, None, 0.0, None, None, None, None) == -1
+    lib.pnec_frame_opts_default(None)  # must be a no-op
+
+
 def test_no_cpu_fallback_without_gpu():
     """The product path must fail loudly when there is no device."""
     import torch
