@@ -46,7 +46,8 @@ int fail(int code, const std::string &msg) {
   do {                                                                                       \
     cudaError_t err__ = (call);                                                              \
     if (err__ != cudaSuccess)                                                                \
-      return fail(PNEC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(err__));     \
+      return fail(PNEC_ERR_CUDA, std::string(#call) + " (pnec_capi.cu:" + std::to_string(__LINE__) + \
+                                 "): " + cudaGetErrorString(err__));                         \
   } while (0)
 
 struct DevBuf {
@@ -230,7 +231,6 @@ struct pnec_handle {
   cudaEvent_t ev_fork = nullptr, ev_join[kMaxChunks] = {}, ev_es[kMaxChunks] = {};
   cudaEvent_t ev_round[kMaxChunks][kMaxRounds] = {};
   DevBuf d_fr_rounds;             // poses of every weighted round: [rounds][B][7]
-  std::unordered_map<const void *, size_t> dyn_smem_set;  // kernel -> opt-in dynamic shared memory already granted
   HostStager stager;              // pinned ring + copy threads for pageable host inputs
   int sphere_samples = -1;
   std::mutex mu;
@@ -243,15 +243,20 @@ struct Staged {
   long long max_n = 0;
 };
 
-// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-kernel maximum: raise it only when a launch
-// needs more than any earlier one (saves one driver call per launch on the hot path).
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-kernel maximum that belongs to the device
+// context, not to a handle: the bookkeeping is process-wide (per device and kernel), and the limit is
+// only ever raised -- a second handle asking for less must not lower it under a launch of the first.
 template <class Kernel>
 cudaError_t ensure_dyn_smem(pnec_handle *h, Kernel kern, size_t dyn) {
+  static std::mutex mu;
+  static std::unordered_map<const void *, size_t> granted[64];
   const void *key = reinterpret_cast<const void *>(kern);
-  auto it = h->dyn_smem_set.find(key);
-  if (it != h->dyn_smem_set.end() && it->second >= dyn) return cudaSuccess;
+  std::lock_guard<std::mutex> lock(mu);
+  auto &map = granted[h->device & 63];
+  auto it = map.find(key);
+  if (it != map.end() && it->second >= dyn) return cudaSuccess;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn));
-  if (e == cudaSuccess) h->dyn_smem_set[key] = dyn;
+  if (e == cudaSuccess) map[key] = dyn;
   return e;
 }
 

@@ -325,6 +325,55 @@ __device__ __forceinline__ double scf_chunk_one_lane(const double *terms, int ba
   return p[0];
 }
 
+// ---- the contraction-sensitive arithmetic of a pair, compiled ONCE
+//
+// scf_pair is instantiated in several kernels (4-warp pass 1, 16-warp pass 2, the fused rounds kernel
+// of small batches).  Plain expressions such as a*b + c*d may be contracted into different fma's in
+// different instantiations, which changes last bits; the frame solve relies on a pair giving the SAME
+// bits whichever kernel processes it (scan cache, fixed points, two passes).  Everything that is not
+// already spelled out with explicit roundings (scf_add_term) therefore lives in these three
+// out-of-line functions: one body, one SASS, called from every kernel.  Each is called once per
+// thread and phase (not per correspondence), so the call costs nothing measurable.
+
+// terms[9 i .. 9 i + 8] for the correspondences tid, tid + nt, ... of a pair
+__device__ __noinline__ void scf_fill_terms(const double *f1, const double *f2, const double *ct, long long s, int n,
+                                            int tid, int nt, const double *pose, double reg, double *terms) {
+  double R[9];
+  pose_rotation(pose, R);
+  for (int i = tid; i < n; i += nt) {
+    double a1[3], a2[3], c9[9], w[9];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { a1[k] = f1[3 * (s + i) + k]; a2[k] = f2[3 * (s + i) + k]; }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) c9[k] = ct[9 * (s + i) + k];
+    scf_terms(R, reg, a1, a2, c9, w);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) terms[9 * i + k] = w[k];
+  }
+}
+
+// this thread's share of E(t) = sum_i n_i n_i^T / (t^T B_i t): correspondences tid, tid + nta, ...
+__device__ __noinline__ void scf_step_partial(const double *terms, int n, int tid, int nta, double t0, double t1,
+                                              double t2, double *E /* [6] */) {
+  const double txx = t0 * t0, txy = 2.0 * t0 * t1, txz = 2.0 * t0 * t2;
+  const double tyy = t1 * t1, tyz = 2.0 * t1 * t2, tzz = t2 * t2;
+  double e0 = 0, e1 = 0, e2 = 0, e3 = 0, e4 = 0, e5 = 0;
+  for (int i = tid; i < n; i += nta) {
+    const double *w = terms + 9 * i;
+    const double den = w[3] * txx + w[4] * txy + w[5] * txz + w[6] * tyy + w[7] * tyz + w[8] * tzz;
+    const double inv = fast_rcp(den);
+    e0 = fma(w[0] * w[0], inv, e0); e1 = fma(w[0] * w[1], inv, e1); e2 = fma(w[0] * w[2], inv, e2);
+    e3 = fma(w[1] * w[1], inv, e3); e4 = fma(w[1] * w[2], inv, e4); e5 = fma(w[2] * w[2], inv, e5);
+  }
+  E[0] = e0; E[1] = e1; E[2] = e2; E[3] = e3; E[4] = e4; E[5] = e5;
+}
+
+__device__ __noinline__ void scf_eigvec(const double *Es /* [6] */, double *v /* [3] */) {
+  double m[6] = {Es[0], Es[1], Es[2], Es[3], Es[4], Es[5]}, vv[3], lam;
+  sym3_smallest_eigvec_fast(m, vv, lam);
+  v[0] = vv[0]; v[1] = vv[1]; v[2] = vv[2];
+}
+
 template <int NW, bool LANE_SERIAL = false>
 __device__ __forceinline__ void scf_pair(const ScfArgs &args, const long long b) {
   constexpr int NT = NW * 32;
@@ -363,18 +412,7 @@ __device__ __forceinline__ void scf_pair(const ScfArgs &args, const long long b)
     if (tid == 0) { ot[0] = tsrc[0]; ot[1] = tsrc[1]; ot[2] = tsrc[2]; if (args.out_cost) args.out_cost[b] = 0.0; }
     return;
   }
-  double R[9];
-  pose_rotation(pose, R);
-  for (int i = tid; i < n; i += NT) {
-    double a1[3], a2[3], c9[9], w[9];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { a1[k] = args.bv.f1[3 * (s + i) + k]; a2[k] = args.bv.f2[3 * (s + i) + k]; }
-#pragma unroll
-    for (int k = 0; k < 9; ++k) c9[k] = args.bv.ct[9 * (s + i) + k];
-    scf_terms(R, args.reg, a1, a2, c9, w);
-#pragma unroll
-    for (int k = 0; k < 9; ++k) terms[9 * i + k] = w[k];
-  }
+  scf_fill_terms(args.bv.f1, args.bv.f2, args.bv.ct, s, n, tid, NT, pose, args.reg, terms);
   __syncthreads();
 
   // ---- scan: candidate 0 is the given translation, 1..samples the Fibonacci sphere; the first
@@ -557,17 +595,9 @@ __device__ __forceinline__ void scf_pair(const ScfArgs &args, const long long b)
     bool have_prev = false;
     for (int it = 0; it < args.steps; ++it) {
       const double t[3] = {s_t[0], s_t[1], s_t[2]};
-      const double txx = t[0] * t[0], txy = 2.0 * t[0] * t[1], txz = 2.0 * t[0] * t[2];
-      const double tyy = t[1] * t[1], tyz = 2.0 * t[1] * t[2], tzz = t[2] * t[2];
       if (warp < NWA) {
         double E[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int i = tid; i < n; i += NTA) {
-          const double *w = terms + 9 * i;
-          const double den = w[3] * txx + w[4] * txy + w[5] * txz + w[6] * tyy + w[7] * tyz + w[8] * tzz;
-          const double inv = fast_rcp(den);
-          E[0] = fma(w[0] * w[0], inv, E[0]); E[1] = fma(w[0] * w[1], inv, E[1]); E[2] = fma(w[0] * w[2], inv, E[2]);
-          E[3] = fma(w[1] * w[1], inv, E[3]); E[4] = fma(w[1] * w[2], inv, E[4]); E[5] = fma(w[2] * w[2], inv, E[5]);
-        }
+        scf_step_partial(terms, n, tid, NTA, t[0], t[1], t[2], E);
         // transposing warp reduction: lane L ends with the warp sum of E[4 b4 + 2 b3 + b2]
         exchange_step<8, 16>(E, lane);
         exchange_step<4, 8>(E, lane);
@@ -588,8 +618,8 @@ __device__ __forceinline__ void scf_pair(const ScfArgs &args, const long long b)
           for (int w = 0; w < NWA; ++w) a += s_red[w][k];
           Es[k] = a;
         }
-        double v[3], lam;
-        sym3_smallest_eigvec_fast(Es, v, lam);
+        double v[3];
+        scf_eigvec(Es, v);
         auto same_up_to_sign = [](const double a[3], const double c[3]) {
           const bool p = __double_as_longlong(a[0]) == __double_as_longlong(c[0]) &&
                          __double_as_longlong(a[1]) == __double_as_longlong(c[1]) &&
