@@ -116,7 +116,7 @@ def cpu_frame_rate(batch, n_problems, threads):
     sl = slice(0, n_problems * N)
     t0 = time.perf_counter()
     oracle.frame_solve_batch(batch.bvs_host[sl], batch.bvs_target[sl], batch.covs_target[sl],
-                             batch.init_poses[:n_problems], oracle.default_frame_opts(), n_per_problem=N,
+                             batch.init_poses[:n_problems], oracle.default_frame_opts(use_ransac=0), n_per_problem=N,
                              num_threads=threads)
     return n_problems / (time.perf_counter() - t0)
 
@@ -345,7 +345,7 @@ def run_b200(args):
     # ---- the whole frame solve (SURVEY.md section 8f rows 1-2 + the refinement), device resident
     frame = None
     if world == 1:
-        fopts = api.default_frame_opts()
+        fopts = api.default_frame_opts(use_ransac=0)
         fstep = lambda: h.frame_solve_batch(f1, f2, ct, init, fopts, n_per_problem=N)
         for _ in range(3):
             fstep()

@@ -28,7 +28,7 @@ extern "C" {
 #endif
 
 #define PNEC_B200_VERSION_MAJOR 0
-#define PNEC_B200_VERSION_MINOR 1
+#define PNEC_B200_VERSION_MINOR 2
 
 /* Residual variants.
  *   NEC        include/optimization/nec_residual.h:47-69
@@ -256,20 +256,27 @@ int pnec_eigensolver_batch(pnec_handle *h, const pnec_batch *batch, const double
                            double *out_smallest_ev, void *cuda_stream);
 
 /* pnec::rel_pose_estimation::Options as PNEC::Solve reads it
- * (include/rel_pose_estimation/pnec_config.h:46-65). */
+ * (include/rel_pose_estimation/pnec_config.h:46-65), plus the literals of the call sites. */
 typedef struct pnec_frame_opts {
   int32_t use_nec;             /* use_nec_              false                                   */
   int32_t use_ceres;           /* use_ceres_            true                                    */
   int32_t weighted_iterations; /* weighted_iterations_  10                                      */
-  int32_t use_ransac;          /* use_ransac_: the reference defaults to true; RANSAC is not built,
-                                  a non-zero value returns PNEC_ERR_UNSUPPORTED                 */
+  int32_t use_ransac;          /* use_ransac_           true  (pnec_config.h:58)                */
   int32_t fibonacci_samples;   /* 500, the literal at pnec.cc:331                               */
   int32_t scf_steps;           /* 10,  the literal at pnec.cc:342                               */
   pnec_solver_opts ceres;      /* ceres_options_ (+ regularization_); `variant` is ignored: NEC
                                   when use_nec, TARGET otherwise                                */
+  int32_t max_ransac_iterations; /* max_ransac_iterations_  5000 (pnec_config.h:59)             */
+  int32_t ransac_sample_size;    /* ransac_sample_size_     10   (pnec_config.h:60), at most 32 */
+  double ransac_threshold;       /* 1e-6, the literal at pnec.cc:250                            */
+  double ransac_probability;     /* 0.99, opengv::sac::Ransac's default probability_            */
+  double ransac_max_variation;   /* 0.1, the start perturbation of
+                                    EigensolverSacProblem::computeModelCoefficients             */
+  uint64_t ransac_seed;          /* key of the counter-based random stream (opengv: time-seeded
+                                    mt19937 + rand(), not reproducible)                         */
 } pnec_frame_opts;
 
-/* Options() defaults except use_ransac = 0. */
+/* Options() defaults (use_ransac = 1). */
 void pnec_frame_opts_default(pnec_frame_opts *opts);
 
 typedef struct pnec_frame_out {
@@ -278,12 +285,48 @@ typedef struct pnec_frame_out {
   int32_t *status;     /* [B] pnec_status of the refinement, or NULL (untouched if !use_ceres)  */
   int32_t *iterations; /* [B] or NULL                                                           */
   double *cost;        /* [B] or NULL                                                           */
+  /* RANSAC (`std::vector<int> &inliers` of PNEC::Solve, pnec.cc:81): any may be NULL.  Without
+   * RANSAC num_inliers is 0 (the reference clears the vector, pnec.cc:277).                    */
+  int32_t *num_inliers;       /* [B]                                                            */
+  int32_t *inlier_index;      /* [total] indices within the pair, ascending; pair b's list starts
+                                 at its first correspondence's position and has num_inliers[b]
+                                 entries                                                        */
+  int32_t *ransac_iterations; /* [B] opengv's ransac.iterations_                                */
+  /* Stage timings of the timed Solve overloads (pnec.cc:145-205; FrameTiming::nec_es_, it_es_,
+   * ceres_, include/common/timing.h:52-55) from CUDA events, milliseconds, HOST pointer [3], or
+   * NULL.  Asking for them makes the call synchronous and runs the batch as one chunk.         */
+  float *stage_ms;
 } pnec_frame_out;
 
+/* opengv::sac::Ransac<EigensolverSacProblem>::computeModel + selectWithinDistance for B frame
+ * pairs: the RANSAC stage of PNEC::Eigensolver alone (src/rel_pose_estimation/pnec.cc:239-251),
+ * exposed for testing.  Uses use_ransac's settings of `opts` (max_ransac_iterations,
+ * ransac_sample_size, ransac_threshold, ransac_probability, ransac_max_variation, ransac_seed).
+ * Every hypothesis is a function of (seed, pair index, iteration) alone -- a fresh partial
+ * Fisher-Yates sample and a start at the rotation of batch->poses moved by U(-1, 1) *
+ * ransac_max_variation per Cayley parameter -- so rounds of hypotheses are evaluated in parallel
+ * and opengv's bookkeeping (first strict maximum of the inlier count, k = log(1 - p) /
+ * log(1 - w^s)) is replayed over them in order.  opengv's own loop additionally carries a
+ * shuffled index array and the previous model's rotation from one iteration to the next
+ * (oracle/pnec_oracle_frame.c, `sequential`): the same distribution of samples, not the same
+ * stream; parity with the reference is statistical by construction (it seeds from time(0)).
+ *   out_models        [B][7] winning hypothesis: unit quaternion + unit translation (signed by
+ *                     the optical flow of the sample's first correspondence); the start pose when a
+ *                     pair has fewer correspondences than the sample size
+ *   out_num_inliers   [B]      out_iterations [B] or NULL
+ *   out_inlier_index  [total] (layout as in pnec_frame_out) or NULL
+ *   pair_index_base   pair b draws from the stream of pair (pair_index_base + b)               */
+int pnec_ransac_batch(pnec_handle *h, const pnec_batch *batch, const pnec_frame_opts *opts,
+                      int64_t pair_index_base, double *out_models, int32_t *out_num_inliers,
+                      int32_t *out_iterations, int32_t *out_inlier_index, void *cuda_stream);
+
 /* The whole frame-to-frame solve for B frame pairs, every stage on the device:
- * Sophus::SE3d PNEC::Solve(bvs1, bvs2, projected_covs, initial_pose) with use_ransac_ == false
+ * Sophus::SE3d PNEC::Solve(bvs1, bvs2, projected_covs, initial_pose, inliers)
  * (src/rel_pose_estimation/pnec.cc:77-124):
- *   1. PNEC::Eigensolver (pnec.cc:273-279): pnec_eigensolver_batch from the rotation of
+ *   0. use_ransac: pnec_ransac_batch, then InlierExtraction (pnec.cc:210-229): every later stage
+ *      sees the inliers only; step 1 then is optimizeModelCoefficients (pnec.cc:253-256): the
+ *      eigensolver over the inliers started at the winning hypothesis
+ *   1. PNEC::Eigensolver (pnec.cc:231-281): pnec_eigensolver_batch from the rotation of
  *      batch->poses, translation = TranslationFromM(ComposeM(..)) (pnec_nec_translation_batch)
  *   2. use_nec: NECCeresSolver from 1 (or 1 itself if !use_ceres)
  *   3. else weighted_iterations > 1: PNEC::WeightedEigensolver (pnec.cc:283-348):
@@ -291,7 +334,7 @@ typedef struct pnec_frame_out {
  *      from the pose of step 1; SCF translation started at the previous translation };
  *      == 1: the pose of step 1;  == 0: batch->poses
  *   4. use_ceres: CeresSolver (TARGET residual) from 3
- * batch->covs_target may be NULL when use_nec. */
+ * batch->covs_target may be NULL when use_nec.  The random stream of pair b is keyed by b. */
 int pnec_frame_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_frame_opts *opts,
                            const pnec_frame_out *out, void *cuda_stream);
 

@@ -84,29 +84,38 @@ class OracleEsInfo(ctypes.Structure):
     ]
 
 
+class OracleRansacOpts(ctypes.Structure):
+    """opengv::sac::Ransac settings as PNEC::Eigensolver uses them (pnec.cc:241-251)."""
+    _fields_ = [
+        ("max_iterations", ctypes.c_int32),
+        ("sample_size", ctypes.c_int32),
+        ("sequential", ctypes.c_int32),  # 1: opengv's sequential state (persistent shuffle, chained start)
+        ("reserved", ctypes.c_int32),
+        ("threshold", ctypes.c_double),
+        ("probability", ctypes.c_double),
+        ("max_variation", ctypes.c_double),
+        ("seed", ctypes.c_uint64),
+    ]
+
+
 class OracleFrameOpts(ctypes.Structure):
-    """pnec::rel_pose_estimation::Options as PNEC::Solve reads it (pnec_config.h:46-65), no RANSAC."""
+    """pnec::rel_pose_estimation::Options as PNEC::Solve reads it (pnec_config.h:46-65)."""
     _fields_ = [
         ("use_nec", ctypes.c_int32),
         ("use_ceres", ctypes.c_int32),
         ("weighted_iterations", ctypes.c_int32),
         ("fibonacci_samples", ctypes.c_int32),
         ("scf_steps", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("use_ransac", ctypes.c_int32),
         ("ceres", OracleOpts),
+        ("ransac", OracleRansacOpts),
     ]
 
 
-class OracleRansacOpts(ctypes.Structure):
-    """opengv::sac::Ransac settings as PNEC::Eigensolver uses them (pnec.cc:241-251)."""
-    _fields_ = [
-        ("max_iterations", ctypes.c_int32),
-        ("sample_size", ctypes.c_int32),
-        ("threshold", ctypes.c_double),
-        ("probability", ctypes.c_double),
-        ("max_variation", ctypes.c_double),
-        ("seed", ctypes.c_uint64),
-    ]
+# Options / C-ABI names of the RANSAC settings -> fields of OracleRansacOpts
+_RANSAC_NAMES = {"max_ransac_iterations": "max_iterations", "ransac_sample_size": "sample_size",
+                 "ransac_seed": "seed", "ransac_threshold": "threshold", "ransac_probability": "probability",
+                 "ransac_max_variation": "max_variation", "ransac_sequential": "sequential"}
 
 
 INFO_DTYPE = np.dtype(
@@ -197,11 +206,19 @@ def lib() -> ctypes.CDLL:
         L.oracle_weighted_eigensolver.restype = ctypes.c_int
         L.oracle_frame_opts_default.argtypes = [ctypes.POINTER(OracleFrameOpts)]
         L.oracle_frame_opts_default.restype = None
-        L.oracle_frame_solve.argtypes = [ctypes.POINTER(OracleFrameOpts), ctypes.c_int64, dp, dp, dp, dp, dp, dp]
+        u8p = ctypes.POINTER(ctypes.c_uint8)
+        L.oracle_frame_solve.argtypes = [ctypes.POINTER(OracleFrameOpts), ctypes.c_int64, ctypes.c_int64, dp, dp, dp,
+                                         dp, dp, dp, u8p, ip, ip]
         L.oracle_frame_solve.restype = ctypes.c_int
         L.oracle_frame_solve_batch.argtypes = [ctypes.POINTER(OracleFrameOpts), ctypes.c_int64, ctypes.c_int64,
-                                               ctypes.POINTER(ctypes.c_int64), dp, dp, dp, dp, dp, dp, ctypes.c_int]
+                                               ctypes.POINTER(ctypes.c_int64), dp, dp, dp, dp, dp, dp, ctypes.c_int,
+                                               ctypes.c_int64, u8p, ip, ip]
         L.oracle_frame_solve_batch.restype = ctypes.c_int
+        L.oracle_ransac_compute_model.argtypes = [ctypes.POINTER(OracleRansacOpts), ctypes.c_int64, ctypes.c_int64,
+                                                  dp, dp, dp, dp, u8p, ip, ip]
+        L.oracle_ransac_compute_model.restype = ctypes.c_int
+        L.oracle_ransac_score.argtypes = [dp, dp, dp]
+        L.oracle_ransac_score.restype = ctypes.c_double
         L.oracle_ransac_opts_default.argtypes = [ctypes.POINTER(OracleRansacOpts)]
         L.oracle_ransac_opts_default.restype = None
         L.oracle_ransac_eigensolver.argtypes = [ctypes.POINTER(OracleRansacOpts), ctypes.c_int64, ctypes.c_int64,
@@ -458,10 +475,16 @@ def weighted_eigensolver(f1, f2, cov, initial_pose7, reg=1e-13, weighted_iterati
 
 
 def default_frame_opts(**overrides) -> OracleFrameOpts:
+    """Options() defaults (use_ransac = 1, pnec_config.h:58).  Keys: the fields of OracleFrameOpts, of its
+    ceres options, and the RANSAC settings under their Options / C-ABI names (max_ransac_iterations,
+    ransac_sample_size, ransac_seed, ransac_threshold, ransac_probability, ransac_max_variation,
+    ransac_sequential)."""
     o = OracleFrameOpts()
     lib().oracle_frame_opts_default(ctypes.byref(o))
     for k, v in overrides.items():
-        if hasattr(o, k):
+        if k in _RANSAC_NAMES:
+            setattr(o.ransac, _RANSAC_NAMES[k], v)
+        elif hasattr(o, k):
             setattr(o, k, v)
         elif hasattr(o.ceres, k):
             setattr(o.ceres, k, v)
@@ -471,9 +494,11 @@ def default_frame_opts(**overrides) -> OracleFrameOpts:
 
 
 def frame_solve_batch(f1, f2, cov, init_poses, opts: OracleFrameOpts, offsets=None, n_per_problem=None,
-                      num_threads: int = 1):
-    """PNEC::Solve (no RANSAC) per frame pair -> (poses [B,7], eigensolver poses [B,7])."""
-    f1, f2, cov = _c(f1, (3,)), _c(f2, (3,)), _c(cov, (9,))
+                      num_threads: int = 1, pair_index_base: int = 0, return_ransac: bool = False):
+    """PNEC::Solve per frame pair -> (poses [B,7], eigensolver poses [B,7]); with return_ransac also
+    (inlier mask [total] bool, num_inliers [B], ransac iterations [B])."""
+    f1, f2 = _c(f1, (3,)), _c(f2, (3,))
+    cov = None if cov is None else _c(cov, (9,))
     init_poses = _c(init_poses, (7,))
     B = init_poses.shape[0]
     if offsets is not None:
@@ -485,30 +510,65 @@ def frame_solve_batch(f1, f2, cov, init_poses, opts: OracleFrameOpts, offsets=No
         if n_per_problem is None:
             n_per_problem = f1.shape[0] // max(B, 1)
     out, es = np.zeros((B, 7)), np.zeros((B, 7))
+    mask = np.zeros(max(f1.shape[0], 1), dtype=np.uint8)
+    ni, it = np.zeros(max(B, 1), dtype=np.int32), np.zeros(max(B, 1), dtype=np.int32)
+    i32p = ctypes.POINTER(ctypes.c_int32)
     rc = lib().oracle_frame_solve_batch(ctypes.byref(opts), B, n_per_problem, op, _dp(f1), _dp(f2), _dp(cov),
-                                        _dp(init_poses), _dp(out), _dp(es), num_threads)
+                                        _dp(init_poses), _dp(out), _dp(es), num_threads, int(pair_index_base),
+                                        mask.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)),
+                                        ni.ctypes.data_as(i32p), it.ctypes.data_as(i32p))
     if rc != 0:
         raise RuntimeError("oracle_frame_solve_batch failed")
+    if return_ransac:
+        return out, es, mask[:f1.shape[0]].astype(bool), ni[:B], it[:B]
     return out, es
 
 
-def ransac_eigensolver(f1, f2, init_pose7, pair_index=0, **overrides):
-    """PNEC::Eigensolver with use_ransac_ (pnec.cc:239-272), restated (groundwork, no CUDA path yet)
-    -> (pose7, inlier mask (n,) bool, iterations)."""
-    f1, f2, p = _c(f1, (3,)), _c(f2, (3,)), _c(init_pose7)
+def _ransac_opts(overrides) -> OracleRansacOpts:
     o = OracleRansacOpts()
     lib().oracle_ransac_opts_default(ctypes.byref(o))
     for k, v in overrides.items():
+        k = _RANSAC_NAMES.get(k, k)
         if not hasattr(o, k):
             raise AttributeError(k)
         setattr(o, k, v)
+    return o
+
+
+def ransac_compute_model(f1, f2, init_pose7, pair_index=0, **overrides):
+    """opengv::sac::Ransac<EigensolverSacProblem>::computeModel + selectWithinDistance, restated
+    -> (best model pose7, inlier mask (n,) bool, iterations)."""
+    f1, f2, p = _c(f1, (3,)), _c(f2, (3,)), _c(init_pose7)
+    o = _ransac_opts(overrides)
     out = np.zeros(7)
-    mask = np.zeros(f1.shape[0], dtype=np.uint8)
+    mask = np.zeros(max(f1.shape[0], 1), dtype=np.uint8)
+    ni, it = ctypes.c_int32(), ctypes.c_int32()
+    rc = lib().oracle_ransac_compute_model(ctypes.byref(o), int(pair_index), f1.shape[0], _dp(f1), _dp(f2), _dp(p),
+                                           _dp(out), mask.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)),
+                                           ctypes.byref(ni), ctypes.byref(it))
+    if rc not in (0, -2):
+        raise RuntimeError(f"oracle_ransac_compute_model failed ({rc})")
+    return out, mask[:f1.shape[0]].astype(bool), it.value
+
+
+def ransac_score(pose7, f1, f2) -> float:
+    """EigensolverSacProblem's reprojection score of one correspondence under a model."""
+    return float(lib().oracle_ransac_score(_dp(_c(pose7)), _dp(_c(f1)), _dp(_c(f2))))
+
+
+def ransac_eigensolver(f1, f2, init_pose7, pair_index=0, **overrides):
+    """PNEC::Eigensolver with use_ransac_ (pnec.cc:239-272), restated
+    -> (pose7, inlier mask (n,) bool, iterations)."""
+    f1, f2, p = _c(f1, (3,)), _c(f2, (3,)), _c(init_pose7)
+    o = _ransac_opts(overrides)
+    out = np.zeros(7)
+    mask = np.zeros(max(f1.shape[0], 1), dtype=np.uint8)
     ni, it = ctypes.c_int32(), ctypes.c_int32()
     rc = lib().oracle_ransac_eigensolver(ctypes.byref(o), int(pair_index), f1.shape[0], _dp(f1), _dp(f2), _dp(p),
                                          _dp(out), mask.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)),
                                          ctypes.byref(ni), ctypes.byref(it))
     if rc != 0:
         raise RuntimeError(f"oracle_ransac_eigensolver failed ({rc})")
+    mask = mask[:f1.shape[0]].astype(bool)
     assert int(mask.sum()) == ni.value
-    return out, mask.astype(bool), it.value
+    return out, mask, it.value

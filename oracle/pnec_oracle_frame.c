@@ -648,105 +648,56 @@ int oracle_weighted_eigensolver(int64_t n, const double *f1, const double *f2, c
   return 0;
 }
 
-/* PNEC::Solve with use_ransac_ == false, pnec.cc:77-124.  Mirrors pnec::rel_pose_estimation::
- * Options (pnec_config.h:46-65): use_nec, use_ceres, weighted_iterations, regularization. */
-typedef struct oracle_frame_opts {
-  int32_t use_nec, use_ceres, weighted_iterations, fibonacci_samples, scf_steps, reserved;
-  oracle_opts ceres;
-} oracle_frame_opts;
-
-void oracle_frame_opts_default(oracle_frame_opts *o) {
-  o->use_nec = 0;
-  o->use_ceres = 1;
-  o->weighted_iterations = 10;
-  o->fibonacci_samples = 500;
-  o->scf_steps = 10;
-  o->reserved = 0;
-  oracle_opts_default(&o->ceres);
-}
-
-int oracle_frame_solve(const oracle_frame_opts *o, int64_t n, const double *f1, const double *f2,
-                       const double *cov, const double init_pose7[7], double out_pose7[7],
-                       double es_pose7[7]) {
-  double es[7];
-  oracle_nec_eigensolver_pose(n, f1, f2, init_pose7, es, NULL);
-  if (es_pose7) memcpy(es_pose7, es, sizeof(es));
-  oracle_opts c = o->ceres;
-  if (o->use_nec) {
-    if (!o->use_ceres) {
-      memcpy(out_pose7, es, sizeof(es));
-      return 0;
-    }
-    c.variant = V_NEC;
-    return oracle_solve(&c, n, f1, f2, NULL, NULL, es, out_pose7, NULL);
-  }
-  double init[7];
-  if (o->weighted_iterations > 1) {
-    const int rc = oracle_weighted_eigensolver(n, f1, f2, cov, es, c.regularization, o->weighted_iterations,
-                                               o->fibonacci_samples, o->scf_steps, init);
-    if (rc) return rc;
-  } else if (o->weighted_iterations == 1) {
-    memcpy(init, es, sizeof(es));
-  } else {
-    memcpy(init, init_pose7, sizeof(init));
-    const double qn = norm_n(init, 4);
-    for (int k = 0; k < 4; ++k) init[k] /= qn;
-  }
-  if (!o->use_ceres) {
-    memcpy(out_pose7, init, sizeof(init));
-    return 0;
-  }
-  c.variant = V_TARGET; /* PNEC::CeresSolver -> Optimize(bvs1, bvs2, covs, reg) default noise frame */
-  return oracle_solve(&c, n, f1, f2, cov, NULL, init, out_pose7, NULL);
-}
-
-int oracle_frame_solve_batch(const oracle_frame_opts *o, int64_t num_problems, int64_t n_per_problem,
-                             const int64_t *offsets, const double *f1, const double *f2, const double *cov,
-                             const double *init_poses, double *out_poses, double *es_poses, int num_threads) {
-  int rc = 0;
-#ifdef _OPENMP
-  if (num_threads < 1) num_threads = omp_get_max_threads();
-#pragma omp parallel for schedule(dynamic, 1) num_threads(num_threads)
-#endif
-  for (int64_t b = 0; b < num_problems; ++b) {
-    const int64_t s = offsets ? offsets[b] : b * n_per_problem;
-    const int64_t e = offsets ? offsets[b + 1] : (b + 1) * n_per_problem;
-    const int r = oracle_frame_solve(o, e - s, f1 + 3 * s, f2 + 3 * s, cov ? cov + 9 * s : NULL,
-                                     init_poses + 7 * b, out_poses + 7 * b, es_poses ? es_poses + 7 * b : NULL);
-    if (r != 0) {
-#ifdef _OPENMP
-#pragma omp atomic write
-#endif
-      rc = r;
-    }
-  }
-  return rc;
-}
-
 /* ------------------------------------------------------------------ RANSAC
  *
- * GROUNDWORK for SURVEY.md section 8f row 3 (no CUDA counterpart yet): PNEC::Eigensolver with
- * use_ransac_ == true (src/rel_pose_estimation/pnec.cc:239-272), i.e.
+ * PNEC::Eigensolver with use_ransac_ == true (src/rel_pose_estimation/pnec.cc:239-272), i.e.
  *   opengv::sac::Ransac<opengv::sac_problems::relative_pose::EigensolverSacProblem>
  * with threshold_ = 1e-6, max_iterations_ = Options::max_ransac_iterations_ (5000), sample size
- * Options::ransac_sample_size_ (10), probability 0.99, followed by optimizeModelCoefficients on the
- * inliers and TranslationFromM(ComposeM(inlier bvs, rotation)).
+ * Options::ransac_sample_size_ (10), probability_ 0.99 (opengv's default), followed by
+ * optimizeModelCoefficients on the inliers and TranslationFromM(ComposeM(inlier bvs, rotation)).
  *
  * PARITY UNPINNED, and only ever statistically pinnable: opengv (not in the reference tree) draws
- * its samples and start perturbations with rand().  Restated from opengv's public sources as
- * recalled (sac/implementation/Ransac.hpp `computeModel`, sac_problems/relative_pose/
- * EigensolverSacProblem.cpp, triangulation/methods.cpp `triangulate2`):
- *   per iteration: a sample of `sample_size` distinct correspondences; start rotation = R12 with its
- *   Cayley parameters moved by U(-0.01, 0.01) each; eigensolver on the sample -> rotation, and
- *   translation = eigenvector of the smallest eigenvalue of M (sign: towards the optical flow of the
- *   sample's first correspondence); score of every correspondence = (1 - f1 . p/|p|) + (1 - f2 . p'/|p'|)
- *   with p the midpoint triangulation and p' = R^T (p - t); inlier iff score < threshold; keep the
- *   first model with strictly more inliers; k = log(1 - 0.99) / log(1 - w^n) after every improvement;
- *   stop when iterations >= k or > max_iterations.
- * Differences by construction: the random stream (a counter-based generator keyed by (seed, pair,
- * iteration, draw), so that a parallel implementation can replay it) and samples drawn by a fresh
- * partial Fisher-Yates per iteration (opengv keeps its shuffled index array across iterations: the
- * same distribution, a different stream).
+ * its samples from a time-seeded std::mt19937 (SampleConsensusProblem(randomSeed = true)) and its
+ * start perturbations from rand().  Restated from opengv's public sources as recalled
+ * (sac/implementation/Ransac.hpp `computeModel`, sac/implementation/SampleConsensusProblem.hpp
+ * `getSamples` / `drawIndexSample`, sac_problems/relative_pose/EigensolverSacProblem.cpp,
+ * relative_pose/methods.cpp `eigensolver(adapter, indices, output)`, triangulation/methods.cpp
+ * `triangulate2`):
+ *   computeModel: k = 1, best = -INT_MAX; while (iterations < k):
+ *     getSamples -> drawIndexSample: for i < sample_size: swap(shuffled[i], shuffled[i + rnd() % (n - i)]);
+ *       the sample is shuffled[0 .. sample_size).  `shuffled` starts as 0..n-1 and PERSISTS across
+ *       iterations.  Fewer correspondences than the sample size: no model (empty inlier set).
+ *     computeModelCoefficients: start = rot2cayley(adapter.getR12()) + U(-1, 1) * maxVariation per
+ *       component (maxVariation = 0.1 in the source as recalled, next to a comment reading 0.01; the
+ *       value is an option here), then eigensolver(adapter, sample, model): the six moment sums over the
+ *       sample, eigensolver_main (Levenberg-Marquardt as above), rotation = cayley2rot(x),
+ *       translation = eigenvector of the smallest eigenvalue of M(x) (its magnitude does not enter the
+ *       score), sign: along the optical flow f1 - R f2 of the sample's FIRST correspondence.
+ *     countWithinDistance -> getSelectedDistancesToModel: adapter.sett12 / setR12(model) -- which is
+ *       why the NEXT iteration's getR12() returns THIS model's rotation: the start rotation random-walks
+ *       along the chain of hypotheses --, p = triangulate2 (midpoint), score = (1 - f1 . p/|p|) +
+ *       (1 - f2 . p'/|p'|), p' = R^T (p - t); inlier iff score < threshold (strict).
+ *     count > best: keep the model; k = log(1 - probability) / log(1 - w^sample_size), w = count / n,
+ *       with 1 - w^s clamped to [eps, 1 - eps].
+ *     ++iterations; iterations > max_iterations: stop.
+ *   inliers = selectWithinDistance(best model).
+ * pnec.cc:253-272 then runs optimizeModelCoefficients (eigensolver over the inliers started at the best
+ * model's rotation, no perturbation) and takes the translation from ComposeM over the inlier arrays
+ * (which skips their first element, common.cc:131).
+ *
+ * TWO MODES.  `sequential = 1` keeps opengv's sequential state as described (persistent shuffle, start
+ * rotation chained through the adapter).  `sequential = 0` (default; what the CUDA path implements)
+ * makes every hypothesis a function of (seed, pair, iteration) alone -- a fresh partial Fisher-Yates
+ * from 0..n-1 and a start at the INITIAL rotation --, which is what allows hypotheses to be evaluated
+ * in parallel and then replayed through the bookkeeping above in order: same distribution of samples,
+ * starts scattered around the initial rotation instead of around the previous hypothesis.  The two
+ * modes are compared statistically in tests/test_oracle_frame.py.  The random stream is counter based
+ * (splitmix64 of seed, pair, iteration, draw) in both; the draws keep opengv's forms
+ * (`r % (n - i)` with r in [0, 2^31), `r / RAND_MAX`).
+ *
+ * Where the reference has undefined behaviour (fewer correspondences than the sample size, or a best
+ * model without inliers: optimizeModelCoefficients then indexes an empty vector) this restatement
+ * returns the start pose (unit quaternion) and an empty inlier set.
  */
 
 static uint64_t rs_mix(uint64_t z) { /* splitmix64 finaliser */
@@ -755,27 +706,31 @@ static uint64_t rs_mix(uint64_t z) { /* splitmix64 finaliser */
   z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
   return z ^ (z >> 31);
 }
-/* uniform in [0, 1) for (seed, pair, iteration, draw) */
-static double rs_uniform(uint64_t seed, uint64_t pair, uint64_t iteration, uint64_t draw) {
+/* 31 random bits for (seed, pair, iteration, draw): the range of rand() / of opengv's rnd() */
+static uint32_t rs_u31(uint64_t seed, uint64_t pair, uint64_t iteration, uint64_t draw) {
   const uint64_t h = rs_mix(rs_mix(rs_mix(seed ^ 0x51ed270b7a2f3c15ULL) + pair) + (iteration << 8) + draw);
-  return (double)(h >> 11) * (1.0 / 9007199254740992.0);
+  return (uint32_t)(h >> 33);
 }
 
 typedef struct oracle_ransac_opts {
-  int32_t max_iterations; /* 5000 */
-  int32_t sample_size;    /* 10   */
-  double threshold;       /* 1e-6 */
-  double probability;     /* 0.99 */
-  double max_variation;   /* 0.01 */
+  int32_t max_iterations; /* 5000  Options::max_ransac_iterations_ */
+  int32_t sample_size;    /* 10    Options::ransac_sample_size_    */
+  int32_t sequential;     /* 0     1: opengv's sequential state (see above) */
+  int32_t reserved;
+  double threshold;       /* 1e-6  pnec.cc:250 */
+  double probability;     /* 0.99  opengv default */
+  double max_variation;   /* 0.1   EigensolverSacProblem::computeModelCoefficients */
   uint64_t seed;
 } oracle_ransac_opts;
 
 void oracle_ransac_opts_default(oracle_ransac_opts *o) {
   o->max_iterations = 5000;
   o->sample_size = 10;
+  o->sequential = 0;
+  o->reserved = 0;
   o->threshold = 1.0e-6;
   o->probability = 0.99;
-  o->max_variation = 0.01;
+  o->max_variation = 0.1;
   o->seed = 1;
 }
 
@@ -795,9 +750,15 @@ static double ransac_score(const double R[3][3], const double t[3], const double
   const double np = norm_n(p, 3), npp = norm_n(pp, 3);
   return (1.0 - dot3(f1, p) / np) + (1.0 - dot3(f2, pp) / npp);
 }
+double oracle_ransac_score(const double pose7[7], const double f1[3], const double f2[3]) {
+  double R[3][3];
+  pose_rot(pose7, R);
+  return ransac_score(R, pose7 + 4, f1, f2);
+}
 
-/* eigensolver on a subset: rotation (quaternion) + translation direction with opengv's sign rule */
-static void ransac_model(int64_t m, const int64_t *idx, const double *f1, const double *f2, const double start_cayley[3],
+/* eigensolver on a subset: Cayley parameters, rotation (quaternion) + translation direction with
+ * opengv's sign rule.  x: in = start, out = result of the minimisation. */
+static void ransac_model(int64_t m, const int64_t *idx, const double *f1, const double *f2, double x[3],
                          double R[3][3], double t[3], double quat[4]) {
   es_moments mom;
   memset(&mom, 0, sizeof(mom));
@@ -810,7 +771,6 @@ static void ransac_model(int64_t m, const int64_t *idx, const double *f1, const 
   }
   lm_params p;
   es_default_params(&p);
-  double x[3] = {start_cayley[0], start_cayley[1], start_cayley[2]};
   lm_result res;
   lm_minimize(es_step_fcn, &mom, &p, x, &res);
   cayley2quat(x, quat);
@@ -827,35 +787,51 @@ static void ransac_model(int64_t m, const int64_t *idx, const double *f1, const 
     for (int k = 0; k < 3; ++k) t[k] = -t[k];
 }
 
-/* PNEC::Eigensolver with RANSAC for one frame pair.  inlier_mask[n] (0/1), returns the number of
- * RANSAC iterations in *iterations.  out_pose7: optimised rotation + TranslationFromM(ComposeM(inliers)). */
-int oracle_ransac_eigensolver(const oracle_ransac_opts *o, int64_t pair_index, int64_t n, const double *f1,
-                              const double *f2, const double init_pose7[7], double out_pose7[7],
-                              uint8_t *inlier_mask, int32_t *num_inliers, int32_t *iterations) {
+/* opengv::sac::Ransac<EigensolverSacProblem>::computeModel + selectWithinDistance for one frame pair.
+ *   inlier_mask[n] (0/1) or NULL; best_model7: the winning hypothesis (unit quaternion + signed unit
+ *   translation); returns 0, or -2 when n < sample_size (no model: zero inliers, best_model7 = start). */
+int oracle_ransac_compute_model(const oracle_ransac_opts *o, int64_t pair_index, int64_t n, const double *f1,
+                                const double *f2, const double init_pose7[7], double best_model7[7],
+                                uint8_t *inlier_mask, int32_t *num_inliers, int32_t *iterations) {
   const int ns = o->sample_size;
-  if (n < ns || ns < 1) return -2;
+  double q0[4];
+  {
+    const double qn = norm_n(init_pose7, 4);
+    for (int k = 0; k < 4; ++k) q0[k] = init_pose7[k] / qn;
+  }
+  if (num_inliers) *num_inliers = 0;
+  if (iterations) *iterations = 0;
+  if (inlier_mask) memset(inlier_mask, 0, (size_t)(n > 0 ? n : 0));
+  memcpy(best_model7, q0, sizeof(q0));
+  memcpy(best_model7 + 4, init_pose7 + 4, 3 * sizeof(double));
+  if (ns < 1 || n < ns) return -2;
   int64_t *perm = malloc(sizeof(int64_t) * (size_t)n), *sample = malloc(sizeof(int64_t) * (size_t)ns);
-  int64_t *inl = malloc(sizeof(int64_t) * (size_t)n);
-  if (!perm || !sample || !inl) return -1;
-  double c0[3];
+  if (!perm || !sample) return -1;
+  double c0[3], ccur[3];
   rot2cayley_pose(init_pose7, c0);
+  memcpy(ccur, c0, sizeof(c0));
   int best = -1, iters = 0;
-  double bestR[3][3], bestt[3], bestq[4] = {0, 0, 0, 1}, k = 1.0;
+  double bestR[3][3], bestt[3] = {0, 0, 0}, bestq[4] = {0, 0, 0, 1}, k = 1.0;
   memset(bestR, 0, sizeof(bestR));
-  memset(bestt, 0, sizeof(bestt));
+  for (int64_t i = 0; i < n; ++i) perm[i] = i;
   while ((double)iters < k) {
-    for (int64_t i = 0; i < n; ++i) perm[i] = i;
-    for (int s = 0; s < ns; ++s) { /* partial Fisher-Yates */
-      const int64_t j = s + (int64_t)(rs_uniform(o->seed, (uint64_t)pair_index, (uint64_t)iters, (uint64_t)s) * (double)(n - s));
+    if (!o->sequential)
+      for (int64_t i = 0; i < n; ++i) perm[i] = i; /* every hypothesis from the identity permutation */
+    for (int s = 0; s < ns; ++s) { /* drawIndexSample */
+      const int64_t j = s + (int64_t)(rs_u31(o->seed, (uint64_t)pair_index, (uint64_t)iters, (uint64_t)s) % (uint64_t)(n - s));
       const int64_t tmp = perm[s];
       perm[s] = perm[j];
       perm[j] = tmp;
-      sample[s] = perm[s];
     }
-    double c[3], R[3][3], t[3], q[4];
-    for (int d = 0; d < 3; ++d)
-      c[d] = c0[d] + (rs_uniform(o->seed, (uint64_t)pair_index, (uint64_t)iters, (uint64_t)(ns + d)) - 0.5) * 2.0 * o->max_variation;
-    ransac_model(ns, sample, f1, f2, c, R, t, q);
+    for (int s = 0; s < ns; ++s) sample[s] = perm[s];
+    double x[3], R[3][3], t[3], q[4];
+    const double *cs = o->sequential ? ccur : c0;
+    for (int d = 0; d < 3; ++d) {
+      const double u = (double)rs_u31(o->seed, (uint64_t)pair_index, (uint64_t)iters, (uint64_t)(ns + d)) / 2147483647.0;
+      x[d] = cs[d] + (u - 0.5) * 2.0 * o->max_variation;
+    }
+    ransac_model(ns, sample, f1, f2, x, R, t, q);
+    memcpy(ccur, x, sizeof(x)); /* adapter.setR12(model.rotation) inside the scoring */
     int count = 0;
     for (int64_t i = 0; i < n; ++i)
       if (ransac_score(R, t, f1 + 3 * i, f2 + 3 * i) < o->threshold) ++count;
@@ -873,37 +849,176 @@ int oracle_ransac_eigensolver(const oracle_ransac_opts *o, int64_t pair_index, i
     ++iters;
     if (iters > o->max_iterations) break;
   }
-  int64_t ni = 0;
+  int32_t ni = 0;
   for (int64_t i = 0; i < n; ++i) {
     const int in = ransac_score(bestR, bestt, f1 + 3 * i, f2 + 3 * i) < o->threshold;
     if (inlier_mask) inlier_mask[i] = (uint8_t)in;
-    if (in) inl[ni++] = i;
+    ni += in;
   }
-  if (num_inliers) *num_inliers = (int32_t)ni;
+  if (num_inliers) *num_inliers = ni;
   if (iterations) *iterations = iters;
-  /* optimizeModelCoefficients: eigensolver over the inliers from the best model's rotation, then
-   * TranslationFromM(ComposeM(in_bvs1, in_bvs2, rotation)) -- ComposeM skips the first inlier */
-  double R[3][3], t[3], q[4] = {bestq[0], bestq[1], bestq[2], bestq[3]};
-  if (ni >= 1) {
-    const double cb[3] = {bestq[0] / bestq[3], bestq[1] / bestq[3], bestq[2] / bestq[3]};
-    ransac_model(ni, inl, f1, f2, cb, R, t, q);
-    double Mi[3][3], lam;
-    memset(Mi, 0, sizeof(Mi));
-    for (int64_t s = 1; s < ni; ++s) {
-      double g[3], nrm[3];
-      matvec(R, f2 + 3 * inl[s], g);
-      cross3(f1 + 3 * inl[s], g, nrm);
-      for (int r = 0; r < 3; ++r)
-        for (int c = 0; c < 3; ++c) Mi[r][c] += nrm[r] * nrm[c];
-    }
-    sym3_smallest_eigvec(Mi, t, &lam);
-  } else {
-    memcpy(t, init_pose7 + 4, sizeof(t));
-  }
-  memcpy(out_pose7, q, sizeof(q));
-  memcpy(out_pose7 + 4, t, sizeof(t));
+  memcpy(best_model7, bestq, sizeof(bestq));
+  memcpy(best_model7 + 4, bestt, sizeof(bestt));
   free(perm);
   free(sample);
-  free(inl);
   return 0;
+}
+
+/* PNEC::Eigensolver with RANSAC for one frame pair (pnec.cc:239-272): computeModel, then
+ * optimizeModelCoefficients = eigensolver over the inliers from the best model's rotation, then
+ * TranslationFromM(ComposeM(in_bvs1, in_bvs2, rotation)) -- ComposeM skips the first inlier. */
+int oracle_ransac_eigensolver(const oracle_ransac_opts *o, int64_t pair_index, int64_t n, const double *f1,
+                              const double *f2, const double init_pose7[7], double out_pose7[7],
+                              uint8_t *inlier_mask, int32_t *num_inliers, int32_t *iterations) {
+  uint8_t *mask = inlier_mask ? inlier_mask : malloc((size_t)(n > 0 ? n : 1));
+  if (!mask) return -1;
+  double best[7];
+  int32_t ni = 0;
+  const int rc = oracle_ransac_compute_model(o, pair_index, n, f1, f2, init_pose7, best, mask, &ni, iterations);
+  if (num_inliers) *num_inliers = ni;
+  if (rc != 0 || ni == 0) {
+    /* no model / no inlier: undefined in the reference; the start pose (unit quaternion) here */
+    const double qn = norm_n(init_pose7, 4);
+    for (int k = 0; k < 4; ++k) out_pose7[k] = init_pose7[k] / qn;
+    memcpy(out_pose7 + 4, init_pose7 + 4, 3 * sizeof(double));
+    if (!inlier_mask) free(mask);
+    return rc == -1 ? -1 : 0;
+  }
+  double *g1 = malloc(sizeof(double) * 3 * (size_t)ni), *g2 = malloc(sizeof(double) * 3 * (size_t)ni);
+  if (!g1 || !g2) return -1;
+  int64_t m = 0;
+  for (int64_t i = 0; i < n; ++i)
+    if (mask[i]) {
+      memcpy(g1 + 3 * m, f1 + 3 * i, 3 * sizeof(double));
+      memcpy(g2 + 3 * m, f2 + 3 * i, 3 * sizeof(double));
+      ++m;
+    }
+  /* the same two calls PNEC::Eigensolver makes without RANSAC, on the inlier arrays, started at the
+   * best model's rotation */
+  oracle_nec_eigensolver_pose(ni, g1, g2, best, out_pose7, NULL);
+  free(g1);
+  free(g2);
+  if (!inlier_mask) free(mask);
+  return 0;
+}
+
+/* PNEC::Solve, pnec.cc:77-124.  Mirrors pnec::rel_pose_estimation::Options (pnec_config.h:46-65):
+ * use_nec, use_ceres, weighted_iterations, regularization, use_ransac (+ its settings). */
+typedef struct oracle_frame_opts {
+  int32_t use_nec, use_ceres, weighted_iterations, fibonacci_samples, scf_steps, use_ransac;
+  oracle_opts ceres;
+  oracle_ransac_opts ransac;
+} oracle_frame_opts;
+
+void oracle_frame_opts_default(oracle_frame_opts *o) {
+  o->use_nec = 0;
+  o->use_ceres = 1;
+  o->weighted_iterations = 10;
+  o->fibonacci_samples = 500;
+  o->scf_steps = 10;
+  o->use_ransac = 1; /* pnec_config.h:58 */
+  oracle_opts_default(&o->ceres);
+  oracle_ransac_opts_default(&o->ransac);
+}
+
+/* pair_index keys the random stream of the RANSAC stage.  inlier_mask[n] / num_inliers /
+ * ransac_iterations may be NULL; without RANSAC the mask is all ones and num_inliers = 0 (the
+ * reference clears `inliers`, pnec.cc:277). */
+int oracle_frame_solve(const oracle_frame_opts *o, int64_t pair_index, int64_t n, const double *f1, const double *f2,
+                       const double *cov, const double init_pose7[7], double out_pose7[7],
+                       double es_pose7[7], uint8_t *inlier_mask, int32_t *num_inliers, int32_t *ransac_iterations) {
+  double es[7];
+  double *g1 = NULL, *g2 = NULL, *gc = NULL;
+  int rc = 0;
+  if (num_inliers) *num_inliers = 0;
+  if (ransac_iterations) *ransac_iterations = 0;
+  if (o->use_ransac) {
+    uint8_t *mask = inlier_mask ? inlier_mask : malloc((size_t)(n > 0 ? n : 1));
+    if (!mask) return -1;
+    int32_t ni = 0;
+    rc = oracle_ransac_eigensolver(&o->ransac, pair_index, n, f1, f2, init_pose7, es, mask, &ni, ransac_iterations);
+    if (rc) return rc;
+    if (num_inliers) *num_inliers = ni;
+    /* InlierExtraction, pnec.cc:210-229 */
+    g1 = malloc(sizeof(double) * 3 * (size_t)(ni > 0 ? ni : 1));
+    g2 = malloc(sizeof(double) * 3 * (size_t)(ni > 0 ? ni : 1));
+    gc = cov ? malloc(sizeof(double) * 9 * (size_t)(ni > 0 ? ni : 1)) : NULL;
+    if (!g1 || !g2 || (cov && !gc)) return -1;
+    int64_t m = 0;
+    for (int64_t i = 0; i < n; ++i)
+      if (mask[i]) {
+        memcpy(g1 + 3 * m, f1 + 3 * i, 3 * sizeof(double));
+        memcpy(g2 + 3 * m, f2 + 3 * i, 3 * sizeof(double));
+        if (cov) memcpy(gc + 9 * m, cov + 9 * i, 9 * sizeof(double));
+        ++m;
+      }
+    if (!inlier_mask) free(mask);
+    f1 = g1; f2 = g2; cov = gc; n = ni;
+  } else {
+    oracle_nec_eigensolver_pose(n, f1, f2, init_pose7, es, NULL);
+    if (inlier_mask) memset(inlier_mask, 1, (size_t)(n > 0 ? n : 0));
+  }
+  if (es_pose7) memcpy(es_pose7, es, sizeof(es));
+  oracle_opts c = o->ceres;
+  if (o->use_nec) {
+    if (!o->use_ceres) {
+      memcpy(out_pose7, es, sizeof(es));
+    } else {
+      c.variant = V_NEC;
+      rc = oracle_solve(&c, n, f1, f2, NULL, NULL, es, out_pose7, NULL);
+    }
+    goto done;
+  }
+  double init[7];
+  if (o->weighted_iterations > 1) {
+    rc = oracle_weighted_eigensolver(n, f1, f2, cov, es, c.regularization, o->weighted_iterations,
+                                     o->fibonacci_samples, o->scf_steps, init);
+    if (rc) goto done;
+  } else if (o->weighted_iterations == 1) {
+    memcpy(init, es, sizeof(es));
+  } else {
+    memcpy(init, init_pose7, sizeof(init));
+    const double qn = norm_n(init, 4);
+    for (int k = 0; k < 4; ++k) init[k] /= qn;
+  }
+  if (!o->use_ceres) {
+    memcpy(out_pose7, init, sizeof(init));
+    goto done;
+  }
+  c.variant = V_TARGET; /* PNEC::CeresSolver -> Optimize(bvs1, bvs2, covs, reg) default noise frame */
+  rc = oracle_solve(&c, n, f1, f2, cov, NULL, init, out_pose7, NULL);
+done:
+  free(g1);
+  free(g2);
+  free(gc);
+  return rc;
+}
+
+/* inlier_mask [total] / num_inliers [B] / ransac_iterations [B] may be NULL; pair b's random stream
+ * is keyed by pair_index_base + b. */
+int oracle_frame_solve_batch(const oracle_frame_opts *o, int64_t num_problems, int64_t n_per_problem,
+                             const int64_t *offsets, const double *f1, const double *f2, const double *cov,
+                             const double *init_poses, double *out_poses, double *es_poses, int num_threads,
+                             int64_t pair_index_base, uint8_t *inlier_mask, int32_t *num_inliers,
+                             int32_t *ransac_iterations) {
+  int rc = 0;
+#ifdef _OPENMP
+  if (num_threads < 1) num_threads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(num_threads)
+#endif
+  for (int64_t b = 0; b < num_problems; ++b) {
+    const int64_t s = offsets ? offsets[b] : b * n_per_problem;
+    const int64_t e = offsets ? offsets[b + 1] : (b + 1) * n_per_problem;
+    const int r = oracle_frame_solve(o, pair_index_base + b, e - s, f1 + 3 * s, f2 + 3 * s, cov ? cov + 9 * s : NULL,
+                                     init_poses + 7 * b, out_poses + 7 * b, es_poses ? es_poses + 7 * b : NULL,
+                                     inlier_mask ? inlier_mask + s : NULL, num_inliers ? num_inliers + b : NULL,
+                                     ransac_iterations ? ransac_iterations + b : NULL);
+    if (r != 0) {
+#ifdef _OPENMP
+#pragma omp atomic write
+#endif
+      rc = r;
+    }
+  }
+  return rc;
 }

@@ -45,6 +45,7 @@ EXPORTED_SYMBOLS = (
     "pnec_unscented_transform_batch",
     "pnec_keypoints_unproject_batch",
     "pnec_scf_translation_batch",
+    "pnec_ransac_batch",
     "pnec_nec_translation_batch",
     "pnec_eigensolver_batch",
     "pnec_frame_opts_default",
@@ -125,6 +126,12 @@ class FrameOpts(ctypes.Structure):
         ("fibonacci_samples", ctypes.c_int32),
         ("scf_steps", ctypes.c_int32),
         ("ceres", SolverOpts),
+        ("max_ransac_iterations", ctypes.c_int32),
+        ("ransac_sample_size", ctypes.c_int32),
+        ("ransac_threshold", ctypes.c_double),
+        ("ransac_probability", ctypes.c_double),
+        ("ransac_max_variation", ctypes.c_double),
+        ("ransac_seed", ctypes.c_uint64),
     ]
 
 
@@ -135,6 +142,10 @@ class _FrameOut(ctypes.Structure):
         ("status", ctypes.c_void_p),
         ("iterations", ctypes.c_void_p),
         ("cost", ctypes.c_void_p),
+        ("num_inliers", ctypes.c_void_p),
+        ("inlier_index", ctypes.c_void_p),
+        ("ransac_iterations", ctypes.c_void_p),
+        ("stage_ms", ctypes.c_void_p),
     ]
 
 
@@ -197,6 +208,10 @@ def load_library() -> ctypes.CDLL:
     L.pnec_frame_solve_batch.argtypes = [ctypes.c_void_p, ctypes.POINTER(_Batch), ctypes.POINTER(FrameOpts),
                                          ctypes.POINTER(_FrameOut), ctypes.c_void_p]
     L.pnec_frame_solve_batch.restype = ctypes.c_int
+    L.pnec_ransac_batch.argtypes = [ctypes.c_void_p, ctypes.POINTER(_Batch), ctypes.POINTER(FrameOpts), ctypes.c_int64,
+                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                    ctypes.c_void_p]
+    L.pnec_ransac_batch.restype = ctypes.c_int
     L.pnec_launch_count.argtypes = [ctypes.c_void_p]
     L.pnec_launch_count.restype = ctypes.c_int64
     _lib = L
@@ -249,6 +264,10 @@ class FrameResult:
     status: object  # (B,) int32, refinement status
     iterations: object  # (B,) int32
     cost: object  # (B,)
+    num_inliers: object = None  # (B,) int32: size of PNEC::Solve's `inliers` (0 without RANSAC)
+    ransac_iterations: object = None  # (B,) int32
+    inlier_index: object = None  # (total,) int32: pair b's ascending inlier indices start at its offset
+    stage_ms: object = None  # (3,) float32: nec_es, it_es, ceres (FrameTiming), when asked for
 
 
 @dataclass
@@ -575,22 +594,52 @@ class Handle:
         self._check(rc, "pnec_eigensolver_batch")
         return poses, info, ev
 
+    def ransac_batch(self, bvs_host, bvs_target, init_poses, opts: Optional[FrameOpts] = None, *,
+                     pair_index_base: int = 0, offsets=None, n_per_problem=None):
+        """opengv's Ransac<EigensolverSacProblem>::computeModel + selectWithinDistance for B frame pairs
+        (pnec.cc:239-251) -> (winning models (B,7), num_inliers (B,), iterations (B,), inlier_index (total,))."""
+        opts = opts or default_frame_opts()
+        keep = []
+        b, device, B = self._batch(bvs_host, bvs_target, None, None, init_poses, offsets, n_per_problem, keep)
+        total = int(offsets[-1]) if offsets is not None else B * int(b.n_per_problem)
+        models, pm = self._out(device, (B, 7))
+        ni, pn = self._out_i32(device, (B,))
+        it, pi = self._out_i32(device, (B,))
+        idx, px = self._out_i32(device, (max(total, 1),))
+        rc = self._lib.pnec_ransac_batch(self._h, ctypes.byref(b), ctypes.byref(opts), int(pair_index_base), pm, pn,
+                                         pi, px, self._stream(device))
+        self._check(rc, "pnec_ransac_batch")
+        return models, ni, it, idx[:total]
+
     def frame_solve_batch(self, bvs_host, bvs_target, covs_target, init_poses,
-                          opts: Optional[FrameOpts] = None, *, offsets=None, n_per_problem=None) -> FrameResult:
-        """PNEC::Solve without RANSAC (pnec.cc:77-124) for B frame pairs, every stage on the device."""
+                          opts: Optional[FrameOpts] = None, *, offsets=None, n_per_problem=None,
+                          stage_timing: bool = False) -> FrameResult:
+        """PNEC::Solve (pnec.cc:77-124) for B frame pairs, every stage on the device.  With
+        `stage_timing` the result carries stage_ms = (nec_es, it_es, ceres) in milliseconds
+        (FrameTiming of the timed Solve overloads) and the call synchronises."""
         opts = opts or default_frame_opts()
         keep = []
         b, device, B = self._batch(bvs_host, bvs_target, covs_target, None, init_poses, offsets, n_per_problem, keep)
+        total = int(offsets[-1]) if offsets is not None else B * int(b.n_per_problem)
         poses, pp = self._out(device, (B, 7))
         es, pes = self._out(device, (B, 7))
         status, pst = self._out_i32(device, (B,))
         iters, pit = self._out_i32(device, (B,))
         cost, pc = self._out(device, (B,))
-        o = _FrameOut(pp, pes, pst, pit, pc)
+        ni, pni = self._out_i32(device, (B,))
+        rit, prit = self._out_i32(device, (B,))
+        idx, pidx = self._out_i32(device, (max(total, 1),)) if opts.use_ransac else (None, None)
+        stage = np.zeros(3, np.float32) if stage_timing else None
+        o = _FrameOut(pp, pes, pst, pit, pc, pni, pidx, prit,
+                      ctypes.c_void_p(stage.ctypes.data) if stage_timing else None)
         rc = self._lib.pnec_frame_solve_batch(self._h, ctypes.byref(b), ctypes.byref(opts), ctypes.byref(o),
                                               self._stream(device))
         self._check(rc, "pnec_frame_solve_batch")
-        return FrameResult(poses, es, status, iters, cost)
+        res = FrameResult(poses, es, status, iters, cost)
+        res.num_inliers, res.ransac_iterations = ni, rit
+        res.inlier_index = None if idx is None else idx[:total]
+        res.stage_ms = stage
+        return res
 
 
 _default_handles = {}

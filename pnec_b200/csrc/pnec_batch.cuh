@@ -14,6 +14,8 @@ struct BatchView {
   const long long *offsets;  // device, B+1, or nullptr for uniform
   long long n_uniform, num_problems, total;
   const double *poses;  // [B][7]
+  const int *counts;    // device, [B], or nullptr: problem b owns only the first counts[b] elements of its
+                        // range (inliers compacted to the front of the pair's slot after RANSAC)
 };
 
 __device__ __forceinline__ void problem_range(const BatchView &bv, long long b, long long &s,
@@ -25,6 +27,7 @@ __device__ __forceinline__ void problem_range(const BatchView &bv, long long b, 
     s = b * bv.n_uniform;
     e = s + bv.n_uniform;
   }
+  if (bv.counts) e = s + bv.counts[b];
 }
 
 template <int V>

@@ -7,6 +7,7 @@
 //   pnec_translation.cuh  scf_kernel / nec_translation_kernel: translation given rotation
 //   pnec_eigensolver.cuh  es_moments_kernel / es_lm_kernel: rotation by NEC eigenvalue minimisation
 //   pnec_frame.cuh   frame_rounds_kernel: all weighted rounds of one pair in one launch (small batches)
+//   pnec_ransac.cuh  ransac_kernel: RANSAC over the eigensolver + inlier extraction
 //   pnec_lm.cuh      Ceres-semantics Levenberg-Marquardt update; pnec_device.cuh: the math
 #include <algorithm>
 #include <atomic>
@@ -26,6 +27,7 @@
 #include "pnec_eigensolver.cuh"
 #include "pnec_eval.cuh"
 #include "pnec_frame.cuh"
+#include "pnec_ransac.cuh"
 #include "pnec_solve.cuh"
 #include "pnec_translation.cuh"
 
@@ -225,11 +227,14 @@ struct pnec_handle {
   DevBuf d_scf_defer;             // int count, cursor, pad[2], list[B]  (standalone SCF calls)
   DevBuf d_fr_defer;              // the same per chunk of a frame solve: (4 + B) ints
   DevBuf d_scf_spill;             // [total][9] SCF terms of pairs that do not fit shared memory
+  DevBuf d_rs_f1, d_rs_f2, d_rs_ct;  // RANSAC: inliers compacted to the front of every pair's slot
+  DevBuf d_rs_best, d_rs_cnt, d_rs_iters, d_rs_idx;  // winning models [B][7], counts, iterations, indices
   static constexpr int kMaxChunks = 8;
   static constexpr int kMaxRounds = 64;
   cudaStream_t side[kMaxChunks] = {}, lm_side[kMaxChunks] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[kMaxChunks] = {}, ev_es[kMaxChunks] = {};
   cudaEvent_t ev_round[kMaxChunks][kMaxRounds] = {};
+  cudaEvent_t ev_stage[4] = {};  // stage timings of a frame solve (out->stage_ms)
   DevBuf d_fr_rounds;             // poses of every weighted round: [rounds][B][7]
   HostStager stager;              // pinned ring + copy threads for pageable host inputs
   int sphere_samples = -1;
@@ -586,6 +591,7 @@ BatchView sub_view(const BatchView &bv, long long start, long long cnt) {
     v.total = cnt * bv.n_uniform;
   }
   if (bv.poses) v.poses = bv.poses + 7 * start;
+  if (bv.counts) v.counts = bv.counts + start;
   return v;
 }
 
@@ -832,6 +838,60 @@ int run_es_lm(pnec_handle *h, long long B, const double *d_mom, const double *d_
   return PNEC_OK;
 }
 
+// opengv's Ransac<EigensolverSacProblem>::computeModel + selectWithinDistance + InlierExtraction
+// (pnec.cc:239-251, 210-229).  `bv` may be a sub-view starting at pair `pair0` / correspondence `elem0`
+// of the batch the scratch arrays were sized for.
+struct RansacOut {
+  double *best;     // [B][7]
+  int *count;       // [B]
+  int *iters;       // [B]
+  int *index;       // [total] or nullptr
+  double *f1, *f2;  // [total][3]
+  double *ct;       // [total][9] or nullptr
+};
+
+int run_ransac(pnec_handle *h, const BatchView &bv, const pnec_frame_opts &o, long long pair_index_base,
+               const RansacOut &out, cudaStream_t stream) {
+  RansacArgs a{};
+  a.bv = bv;
+  a.best_poses = out.best;
+  a.num_inliers = out.count;
+  a.iterations = out.iters;
+  a.inlier_index = out.index;
+  a.out_f1 = out.f1;
+  a.out_f2 = out.f2;
+  a.out_ct = out.ct;
+  a.max_iterations = o.max_ransac_iterations;
+  a.sample_size = o.ransac_sample_size;
+  a.threshold = o.ransac_threshold;
+  a.probability = o.ransac_probability;
+  a.max_variation = o.ransac_max_variation;
+  a.seed = o.ransac_seed;
+  a.pair_index_base = pair_index_base;
+  a.lm = EsLmParams{0.00005, 1.0e1 * DBL_EPSILON, 0.0, 100.0, 100};
+  // One CTA per pair.  Many pairs: one warp each (8 hypotheses per round; the machine is filled by
+  // the pairs).  Few pairs: more warps, i.e. more hypotheses per round and a faster scoring pass.
+  int nw = env_int("PNEC_B200_RANSAC_WARPS", 0);
+  if (nw == 0) nw = bv.num_problems >= 4LL * h->sm_count ? 1 : 4;
+  const unsigned grid = static_cast<unsigned>(bv.num_problems);
+  if (nw == 1) ransac_kernel<1><<<grid, 32, 0, stream>>>(a);
+  else if (nw == 2) ransac_kernel<2><<<grid, 64, 0, stream>>>(a);
+  else ransac_kernel<4><<<grid, 128, 0, stream>>>(a);
+  PNEC_CUDA(cudaGetLastError());
+  h->launches++;
+  return PNEC_OK;
+}
+
+int validate_ransac_opts(const pnec_frame_opts *o) {
+  if (o->ransac_sample_size < 1 || o->ransac_sample_size > kRansacMaxSample)
+    return fail(PNEC_ERR_INVALID_ARGUMENT, "ransac_sample_size must be in [1, 32]");
+  if (o->max_ransac_iterations < 0) return fail(PNEC_ERR_INVALID_ARGUMENT, "max_ransac_iterations < 0");
+  if (!(o->ransac_threshold > 0.0) || !(o->ransac_probability > 0.0) || !(o->ransac_probability < 1.0) ||
+      !(o->ransac_max_variation >= 0.0))
+    return fail(PNEC_ERR_INVALID_ARGUMENT, "bad RANSAC threshold / probability / max_variation");
+  return PNEC_OK;
+}
+
 }  // namespace
 
 // ===================================================================== C-ABI
@@ -904,7 +964,8 @@ void pnec_destroy(pnec_handle *h) {
                     &h->d_out_init, &h->d_out_grad, &h->d_out_jtj, &h->d_ut_mu, &h->d_ut_cov,
                     &h->d_ut_out, &h->d_kp_bv, &h->d_sphere, &h->d_tr_out,
                     &h->d_tr_aux, &h->d_es_mom, &h->d_es_w, &h->d_es_info, &h->d_es_ev,
-                    &h->d_fr_es, &h->d_fr_a, &h->d_fr_cache, &h->d_fr_flags, &h->d_scf_defer, &h->d_fr_defer, &h->d_scf_spill};
+                    &h->d_fr_es, &h->d_fr_a, &h->d_fr_cache, &h->d_fr_flags, &h->d_scf_defer, &h->d_fr_defer, &h->d_scf_spill,
+                    &h->d_rs_f1, &h->d_rs_f2, &h->d_rs_ct, &h->d_rs_best, &h->d_rs_cnt, &h->d_rs_iters, &h->d_rs_idx};
   for (DevBuf *b : bufs) b->release();
   for (int i = 0; i < pnec_handle::kMaxChunks; ++i) {
     if (h->side[i]) cudaStreamDestroy(h->side[i]);
@@ -915,6 +976,8 @@ void pnec_destroy(pnec_handle *h) {
       if (h->ev_round[i][r]) cudaEventDestroy(h->ev_round[i][r]);
   }
   h->d_fr_rounds.release();
+  for (cudaEvent_t ev : h->ev_stage)
+    if (ev) cudaEventDestroy(ev);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   delete h;
 }
@@ -1305,17 +1368,76 @@ void pnec_frame_opts_default(pnec_frame_opts *o) {
   o->use_nec = 0;
   o->use_ceres = 1;
   o->weighted_iterations = 10;
-  o->use_ransac = 0;
+  o->use_ransac = 1;
   o->fibonacci_samples = 500;
   o->scf_steps = 10;
   pnec_solver_opts_default(&o->ceres);
+  o->max_ransac_iterations = 5000;
+  o->ransac_sample_size = 10;
+  o->ransac_threshold = 1.0e-6;
+  o->ransac_probability = 0.99;
+  o->ransac_max_variation = 0.1;
+  o->ransac_seed = 1;
+}
+
+int pnec_ransac_batch(pnec_handle *h, const pnec_batch *batch, const pnec_frame_opts *opts, int64_t pair_index_base,
+                      double *out_models, int32_t *out_num_inliers, int32_t *out_iterations,
+                      int32_t *out_inlier_index, void *cuda_stream) {
+  if (!h || !opts || !out_models || !out_num_inliers) return fail(PNEC_ERR_INVALID_ARGUMENT, "NULL argument");
+  int rc = validate_ransac_opts(opts);
+  if (rc != PNEC_OK) return rc;
+  rc = validate_batch(batch, PNEC_VARIANT_NEC, true);
+  if (rc != PNEC_OK) return rc;
+  const long long B = batch->num_problems;
+  if (B == 0) return PNEC_OK;
+  std::lock_guard<std::mutex> lock(h->mu);
+  PNEC_CUDA(cudaSetDevice(h->device));
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  Staged st;
+  rc = stage_batch(h, batch, PNEC_VARIANT_NEC, stream, &st);
+  if (rc != PNEC_OK) return rc;
+  const bool host = batch->memspace == PNEC_MEM_HOST;
+  const size_t nb = static_cast<size_t>(B), nel = static_cast<size_t>(std::max<long long>(st.bv.total, 1));
+  PNEC_CUDA(h->d_rs_f1.ensure(nel * 24));
+  PNEC_CUDA(h->d_rs_f2.ensure(nel * 24));
+  PNEC_CUDA(h->d_rs_iters.ensure(nb * 4));
+  RansacOut ro{};
+  ro.best = out_models;
+  ro.count = out_num_inliers;
+  ro.iters = out_iterations ? out_iterations : static_cast<int *>(h->d_rs_iters.p);
+  ro.index = out_inlier_index;
+  ro.f1 = static_cast<double *>(h->d_rs_f1.p);
+  ro.f2 = static_cast<double *>(h->d_rs_f2.p);
+  if (host) {
+    PNEC_CUDA(h->d_rs_best.ensure(nb * 56));
+    PNEC_CUDA(h->d_rs_cnt.ensure(nb * 4));
+    if (out_inlier_index) PNEC_CUDA(h->d_rs_idx.ensure(nel * 4));
+    ro.best = static_cast<double *>(h->d_rs_best.p);
+    ro.count = static_cast<int *>(h->d_rs_cnt.p);
+    ro.iters = static_cast<int *>(h->d_rs_iters.p);
+    ro.index = out_inlier_index ? static_cast<int *>(h->d_rs_idx.p) : nullptr;
+  }
+  rc = run_ransac(h, st.bv, *opts, pair_index_base, ro, stream);
+  if (rc != PNEC_OK) return rc;
+  if (host) {
+    PNEC_CUDA(cudaMemcpyAsync(out_models, ro.best, nb * 56, cudaMemcpyDeviceToHost, stream));
+    PNEC_CUDA(cudaMemcpyAsync(out_num_inliers, ro.count, nb * 4, cudaMemcpyDeviceToHost, stream));
+    if (out_iterations) PNEC_CUDA(cudaMemcpyAsync(out_iterations, ro.iters, nb * 4, cudaMemcpyDeviceToHost, stream));
+    if (out_inlier_index)
+      PNEC_CUDA(cudaMemcpyAsync(out_inlier_index, ro.index, static_cast<size_t>(st.bv.total) * 4, cudaMemcpyDeviceToHost, stream));
+    PNEC_CUDA(cudaStreamSynchronize(stream));
+  }
+  return PNEC_OK;
 }
 
 int pnec_frame_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_frame_opts *opts,
                            const pnec_frame_out *out, void *cuda_stream) {
   if (!h || !opts || !out) return fail(PNEC_ERR_INVALID_ARGUMENT, "NULL argument");
-  if (opts->use_ransac)
-    return fail(PNEC_ERR_UNSUPPORTED, "pnec_frame_solve_batch: RANSAC (use_ransac_) is not implemented");
+  const bool ransac = opts->use_ransac != 0;
+  if (ransac) {
+    const int rrc = validate_ransac_opts(opts);
+    if (rrc != PNEC_OK) return rrc;
+  }
   if (opts->weighted_iterations < 0 || opts->fibonacci_samples < 0 || opts->scf_steps < 0)
     return fail(PNEC_ERR_INVALID_ARGUMENT, "negative iteration / sample / step count");
   const bool nec = opts->use_nec != 0;
@@ -1356,6 +1478,27 @@ int pnec_frame_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_f
   double *const d_spill = static_cast<double *>(h->d_scf_spill.p);
   double *o_poses = out->poses, *o_cost = out->cost;
   int32_t *o_status = out->status, *o_iters = out->iterations;
+  // RANSAC scratch: the inliers of every pair, compacted to the front of the pair's own slot
+  RansacOut ro{};
+  if (ransac) {
+    const size_t nel = static_cast<size_t>(std::max<long long>(st.bv.total, 1));
+    PNEC_CUDA(h->d_rs_f1.ensure(nel * 24));
+    PNEC_CUDA(h->d_rs_f2.ensure(nel * 24));
+    if (!nec) PNEC_CUDA(h->d_rs_ct.ensure(nel * 72));
+    PNEC_CUDA(h->d_rs_best.ensure(nb * 56));
+    PNEC_CUDA(h->d_rs_cnt.ensure(nb * 4));
+    PNEC_CUDA(h->d_rs_iters.ensure(nb * 4));
+    if (host && out->inlier_index) PNEC_CUDA(h->d_rs_idx.ensure(nel * 4));
+    ro.best = static_cast<double *>(h->d_rs_best.p);
+    ro.count = (!host && out->num_inliers) ? out->num_inliers : static_cast<int *>(h->d_rs_cnt.p);
+    ro.iters = (!host && out->ransac_iterations) ? out->ransac_iterations : static_cast<int *>(h->d_rs_iters.p);
+    ro.index = out->inlier_index ? (host ? static_cast<int *>(h->d_rs_idx.p) : out->inlier_index) : nullptr;
+    ro.f1 = static_cast<double *>(h->d_rs_f1.p);
+    ro.f2 = static_cast<double *>(h->d_rs_f2.p);
+    ro.ct = nec ? nullptr : static_cast<double *>(h->d_rs_ct.p);
+  } else if (!host && out->num_inliers) {
+    PNEC_CUDA(cudaMemsetAsync(out->num_inliers, 0, nb * 4, stream));  // inliers.clear(), pnec.cc:277
+  }
   if (host) {
     PNEC_CUDA(h->d_out_poses.ensure(nb * 56));
     PNEC_CUDA(h->d_out_status.ensure(nb * 4));
@@ -1373,18 +1516,43 @@ int pnec_frame_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_f
   int *const d_qsame = static_cast<int *>(h->d_fr_flags.p), *const d_fixed = d_qsame + B;
   int *const d_defer = static_cast<int *>(h->d_fr_defer.p);
   const bool shortcuts = !env_int("PNEC_B200_NO_FRAME_SHORTCUTS", 0);
+  const bool timed = out->stage_ms != nullptr;
+  if (timed)
+    for (cudaEvent_t &ev : h->ev_stage)
+      if (!ev) PNEC_CUDA(cudaEventCreate(&ev));
 
   // The stages of one chunk of frame pairs, back to back on one stream.
   auto run_chunk = [&](long long c0, long long cnt, int chunk, cudaStream_t cs) -> int {
-    const BatchView bv = sub_view(st.bv, c0, cnt);
+    BatchView bv = sub_view(st.bv, c0, cnt);
     double *mom = d_mom + kEsMom * c0, *es = d_es + 7 * c0, *pa = d_a + 7 * c0;
     int rcc;
+    auto mark = [&](int k) -> cudaError_t { return timed ? cudaEventRecord(h->ev_stage[k], cs) : cudaSuccess; };
+    PNEC_CUDA(mark(0));
+    const double *es_start = bv.poses;
+    const double *caller_poses = bv.poses;
+    if (ransac) {
+      // 0. RANSAC + InlierExtraction: from here on the pair IS its inliers (compacted arrays at the
+      // same offsets, per-pair counts); the eigensolver below then is optimizeModelCoefficients,
+      // started at the winning hypothesis (pnec.cc:253-256)
+      const long long e0 = st.bv.offsets ? 0 : c0 * st.bv.n_uniform;  // ragged views index absolutely
+      RansacOut r = ro;
+      r.best += 7 * c0; r.count += c0; r.iters += c0;
+      r.f1 += 3 * e0; r.f2 += 3 * e0;
+      if (r.ct) r.ct += 9 * e0;
+      if (r.index) r.index += e0;
+      if ((rcc = run_ransac(h, bv, *opts, c0, r, cs)) != PNEC_OK) return rcc;
+      bv.f1 = r.f1; bv.f2 = r.f2;
+      if (r.ct) bv.ct = r.ct;
+      bv.counts = r.count;
+      es_start = r.best;
+    }
     // 1. PNEC::Eigensolver: rotation, then TranslationFromM(ComposeM(bvs1, bvs2, rotation))
     if ((rcc = run_es_moments(h, bv, false, 0.0, mom, cs)) != PNEC_OK) return rcc;
-    if ((rcc = run_es_lm(h, cnt, mom, bv.poses, es, nullptr, nullptr, cs)) != PNEC_OK) return rcc;
+    if ((rcc = run_es_lm(h, cnt, mom, es_start, es, nullptr, nullptr, cs)) != PNEC_OK) return rcc;
     BatchView ev = bv;
     ev.poses = es;
     if ((rcc = run_nec_translation(h, ev, es + 4, 7, nullptr, cs)) != PNEC_OK) return rcc;
+    PNEC_CUDA(mark(1));  // FrameTiming::nec_es_: Eigensolver + InlierExtraction (pnec.cc:149-161)
     // 2./3. the start pose of the refinement
     const double *init = es;
     if (weighted) {
@@ -1483,21 +1651,25 @@ int pnec_frame_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_f
       init = round_poses(rounds);
       }
     } else if (!nec && opts->weighted_iterations == 0) {
-      normalize_poses_kernel<<<static_cast<unsigned>((cnt + 127) / 128), 128, 0, cs>>>(bv.poses, pa, cnt);
+      normalize_poses_kernel<<<static_cast<unsigned>((cnt + 127) / 128), 128, 0, cs>>>(caller_poses, pa, cnt);
       PNEC_CUDA(cudaGetLastError());
       h->launches++;
       init = pa;
     }
+    PNEC_CUDA(mark(2));  // FrameTiming::it_es_: WeightedEigensolver (pnec.cc:180-188)
     // 4. refinement
     if (opts->use_ceres) {
       pnec_solver_opts so = opts->ceres;
       so.variant = variant;
       BatchView rv = bv;
       rv.poses = init;
-      return run_solve(h, rv, st.max_n, so, false, o_poses + 7 * c0, o_status ? o_status + c0 : nullptr,
-                       o_iters ? o_iters + c0 : nullptr, o_cost ? o_cost + c0 : nullptr, nullptr, cs);
+      rcc = run_solve(h, rv, st.max_n, so, false, o_poses + 7 * c0, o_status ? o_status + c0 : nullptr,
+                      o_iters ? o_iters + c0 : nullptr, o_cost ? o_cost + c0 : nullptr, nullptr, cs);
+      if (rcc != PNEC_OK) return rcc;
+    } else {
+      PNEC_CUDA(cudaMemcpyAsync(o_poses + 7 * c0, init, static_cast<size_t>(cnt) * 56, cudaMemcpyDeviceToDevice, cs));
     }
-    PNEC_CUDA(cudaMemcpyAsync(o_poses + 7 * c0, init, static_cast<size_t>(cnt) * 56, cudaMemcpyDeviceToDevice, cs));
+    PNEC_CUDA(mark(3));  // FrameTiming::ceres_ (pnec.cc:165-169, 196-201)
     return PNEC_OK;
   };
 
@@ -1508,6 +1680,7 @@ int pnec_frame_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_f
   if (chunks <= 0) chunks = B >= 4096 ? 4 : (B >= 1024 ? 2 : 1);
   chunks = std::min<long long>(std::min(chunks, pnec_handle::kMaxChunks), B);
   if (fused_rounds) chunks = 1;  // the fused kernel lays its round poses out for one chunk
+  if (timed) chunks = 1;         // the stage events are recorded on one stream
   if (chunks == 1) {
     rc = run_chunk(0, B, 0, stream);
     if (rc != PNEC_OK) return rc;
@@ -1535,7 +1708,24 @@ int pnec_frame_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_f
       PNEC_CUDA(cudaMemcpyAsync(out->cost, o_cost, nb * 8, cudaMemcpyDeviceToHost, stream));
     if (out->es_poses)
       PNEC_CUDA(cudaMemcpyAsync(out->es_poses, d_es, nb * 56, cudaMemcpyDeviceToHost, stream));
+    if (ransac) {
+      if (out->num_inliers) PNEC_CUDA(cudaMemcpyAsync(out->num_inliers, ro.count, nb * 4, cudaMemcpyDeviceToHost, stream));
+      if (out->ransac_iterations)
+        PNEC_CUDA(cudaMemcpyAsync(out->ransac_iterations, ro.iters, nb * 4, cudaMemcpyDeviceToHost, stream));
+      if (out->inlier_index)
+        PNEC_CUDA(cudaMemcpyAsync(out->inlier_index, ro.index, static_cast<size_t>(st.bv.total) * 4,
+                                  cudaMemcpyDeviceToHost, stream));
+    } else {
+      if (out->num_inliers) std::memset(out->num_inliers, 0, nb * 4);
+      if (out->ransac_iterations) std::memset(out->ransac_iterations, 0, nb * 4);
+    }
     PNEC_CUDA(cudaStreamSynchronize(stream));
+  } else if (!ransac && out->ransac_iterations) {
+    PNEC_CUDA(cudaMemsetAsync(out->ransac_iterations, 0, nb * 4, stream));
+  }
+  if (timed) {
+    PNEC_CUDA(cudaEventSynchronize(h->ev_stage[3]));
+    for (int k = 0; k < 3; ++k) PNEC_CUDA(cudaEventElapsedTime(&out->stage_ms[k], h->ev_stage[k], h->ev_stage[k + 1]));
   }
   return PNEC_OK;
 }

@@ -199,7 +199,7 @@ def oracle_frame_fixtures():
             out[f"{name}/weighted_es_quat{tag}"] = w_q  # weights from the ground-truth poses
             for cname, kw in configs.items():
                 poses, es = oracle.frame_solve_batch(f1, f2, b.covs_target, b.init_poses,
-                                                     oracle.default_frame_opts(**kw), n_per_problem=N)
+                                                     oracle.default_frame_opts(use_ransac=0, **kw), n_per_problem=N)
                 out[f"{name}/{cname}/poses{tag}"] = poses
                 out[f"{name}/es_pose{tag}"] = es
     np.savez_compressed(os.path.join(HERE, "oracle_frame.npz"), **out)

@@ -42,7 +42,7 @@ def _worker(rank, world, port, ragged, out_dir, frame=False):
 
         if frame:
             # the whole frame solve (PNEC::Solve) shards the same way: pairs are independent
-            fo = oracle.default_frame_opts(weighted_iterations=3)
+            fo = oracle.default_frame_opts(use_ransac=0, weighted_iterations=3)
 
             def frame_fn(f1, f2, ct, ch, poses, offsets=None, n_per_problem=None):
                 p, es = oracle.frame_solve_batch(f1, f2, ct, poses, fo, offsets=offsets, n_per_problem=n_per_problem)

@@ -130,14 +130,14 @@ def test_frame_solve_matches_oracle(handle, cfg):
     kw = FRAME_CONFIGS[cfg]
     def run_oracle(bt):
         return oracle.frame_solve_batch(bt.bvs_host, bt.bvs_target, bt.covs_target, bt.init_poses,
-                                        oracle.default_frame_opts(**kw), n_per_problem=n,
+                                        oracle.default_frame_opts(use_ransac=0, **kw), n_per_problem=n,
                                         num_threads=oracle.max_threads())
 
     ref, ref_es = run_oracle(batch)
     ref_p, ref_es_p = run_oracle(perturbed(batch))
     ok = well_posed(ref, ref_p) & well_posed(ref_es, ref_es_p)
     res = handle.frame_solve_batch(batch.bvs_host, batch.bvs_target, batch.covs_target, batch.init_poses,
-                                   api.default_frame_opts(**kw), n_per_problem=n)
+                                   api.default_frame_opts(use_ransac=0, **kw), n_per_problem=n)
     r, t = max_pose_diff(res.es_poses[ok], ref_es[ok])
     assert r <= ROT_TOL and t <= DIR_TOL, ("eigensolver stage", r, t)
     r, t = max_pose_diff(res.poses[ok], ref[ok])
@@ -147,7 +147,7 @@ def test_frame_solve_matches_oracle(handle, cfg):
 def test_frame_solve_device_matches_host_call(handle):
     n, B = 128, 40
     batch = syn.make_batch(B, n, seed=78)
-    opts = api.default_frame_opts(weighted_iterations=4)
+    opts = api.default_frame_opts(use_ransac=0, weighted_iterations=4)
     host = handle.frame_solve_batch(batch.bvs_host, batch.bvs_target, batch.covs_target, batch.init_poses, opts,
                                     n_per_problem=n)
     devr = handle.frame_solve_batch(dev(batch.bvs_host), dev(batch.bvs_target), dev(batch.covs_target),
@@ -163,18 +163,20 @@ def test_frame_solve_improves_on_eigensolver(handle):
     n, B = 512, 256
     batch = syn.make_batch(B, n, seed=79)
     res = handle.frame_solve_batch(batch.bvs_host, batch.bvs_target, batch.covs_target, batch.init_poses,
-                                   api.default_frame_opts(), n_per_problem=n)
+                                   api.default_frame_opts(use_ransac=0), n_per_problem=n)
     e_es = np.mean([rotation_angle(a, b) for a, b in zip(res.es_poses, batch.gt_poses)])
     e_fin = np.mean([rotation_angle(a, b) for a, b in zip(res.poses, batch.gt_poses)])
     assert e_fin <= e_es * 1.02, (e_es, e_fin)
     assert np.all(res.status <= 3)
 
 
-def test_frame_solve_rejects_ransac(handle):
+def test_frame_solve_rejects_bad_ransac_settings(handle):
     batch = syn.make_batch(2, 16, seed=1)
-    with pytest.raises(api.PnecError):
-        handle.frame_solve_batch(batch.bvs_host, batch.bvs_target, batch.covs_target, batch.init_poses,
-                                 api.default_frame_opts(use_ransac=1), n_per_problem=16)
+    for kw in (dict(ransac_sample_size=0), dict(ransac_sample_size=33), dict(ransac_probability=1.0),
+               dict(ransac_threshold=0.0), dict(max_ransac_iterations=-1)):
+        with pytest.raises(api.PnecError):
+            handle.frame_solve_batch(batch.bvs_host, batch.bvs_target, batch.covs_target, batch.init_poses,
+                                     api.default_frame_opts(use_ransac=1, **kw), n_per_problem=16)
 
 
 @pytest.mark.parametrize("name", ["omni_n200", "pinhole_n96"])
@@ -199,7 +201,7 @@ def test_frame_stages_match_committed_fixtures(handle, golden_frame, name):
     assert max(rotation_angle(a, b) for a, b in zip(poses[ok], as_pose(g[f"{name}/weighted_es_quat"])[ok])) <= ROT_TOL
     for cname, kw in {"default": {}, "nec_ceres": {"use_nec": 1}, "es_then_ceres": {"weighted_iterations": 1},
                       "weighted3_no_ceres": {"use_ceres": 0, "weighted_iterations": 3}}.items():
-        res = handle.frame_solve_batch(f1, f2, cov, init, api.default_frame_opts(**kw), n_per_problem=n)
+        res = handle.frame_solve_batch(f1, f2, cov, init, api.default_frame_opts(use_ransac=0, **kw), n_per_problem=n)
         ok = stable(g[f"{name}/{cname}/poses"], g[f"{name}/{cname}/poses_ulp"]) & \
             stable(g[f"{name}/es_pose"], g[f"{name}/es_pose_ulp"])
         assert ok.mean() > 0.8, cname
@@ -216,11 +218,11 @@ def test_frame_solve_shortcuts_are_exact(handle):
     n, B = 160, 64
     batch = syn.make_batch(B, n, seed=80)
     args = (batch.bvs_host, batch.bvs_target, batch.covs_target, batch.init_poses)
-    fast = handle.frame_solve_batch(*args, api.default_frame_opts(), n_per_problem=n)
+    fast = handle.frame_solve_batch(*args, api.default_frame_opts(use_ransac=0), n_per_problem=n)
     os.environ["PNEC_B200_NO_FRAME_SHORTCUTS"] = "1"
     os.environ["PNEC_B200_SCF_DEFER"] = "0"
     try:
-        plain = handle.frame_solve_batch(*args, api.default_frame_opts(), n_per_problem=n)
+        plain = handle.frame_solve_batch(*args, api.default_frame_opts(use_ransac=0), n_per_problem=n)
     finally:
         del os.environ["PNEC_B200_NO_FRAME_SHORTCUTS"]
         del os.environ["PNEC_B200_SCF_DEFER"]
@@ -239,10 +241,10 @@ def test_large_pairs_spill_to_device_memory(handle):
         assert direction_angle(t[0], ref_t) <= DIR_TOL
         assert c[0] == pytest.approx(ref_c, rel=1e-9)
     ref, ref_es = oracle.frame_solve_batch(batch.bvs_host, batch.bvs_target, batch.covs_target, batch.init_poses,
-                                           oracle.default_frame_opts(weighted_iterations=3), offsets=batch.offsets,
+                                           oracle.default_frame_opts(use_ransac=0, weighted_iterations=3), offsets=batch.offsets,
                                            num_threads=oracle.max_threads())
     res = handle.frame_solve_batch(batch.bvs_host, batch.bvs_target, batch.covs_target, batch.init_poses,
-                                   api.default_frame_opts(weighted_iterations=3), offsets=batch.offsets)
+                                   api.default_frame_opts(use_ransac=0, weighted_iterations=3), offsets=batch.offsets)
     r, t = max_pose_diff(res.poses, ref)
     assert r <= ROT_TOL and t <= DIR_TOL, (r, t)
 
@@ -253,15 +255,15 @@ def test_frame_solve_ragged_device_batch(handle):
     batch = syn.make_batch(len(counts), 0, seed=93, camera=syn.PINHOLE, counts=counts)
     fo = dict(weighted_iterations=4, max_num_iterations=20)
     ref, ref_es = oracle.frame_solve_batch(batch.bvs_host, batch.bvs_target, batch.covs_target, batch.init_poses,
-                                           oracle.default_frame_opts(**fo), offsets=batch.offsets,
+                                           oracle.default_frame_opts(use_ransac=0, **fo), offsets=batch.offsets,
                                            num_threads=oracle.max_threads())
     p = perturbed(batch)
     ref_p, _ = oracle.frame_solve_batch(p.bvs_host, p.bvs_target, p.covs_target, p.init_poses,
-                                        oracle.default_frame_opts(**fo), offsets=batch.offsets,
+                                        oracle.default_frame_opts(use_ransac=0, **fo), offsets=batch.offsets,
                                         num_threads=oracle.max_threads())
     ok = well_posed(ref, ref_p, min_fraction=0.7)
     res = handle.frame_solve_batch(dev(batch.bvs_host), dev(batch.bvs_target), dev(batch.covs_target),
-                                   dev(batch.init_poses), api.default_frame_opts(**fo), offsets=batch.offsets)
+                                   dev(batch.init_poses), api.default_frame_opts(use_ransac=0, **fo), offsets=batch.offsets)
     r, t = max_pose_diff(res.poses.cpu().numpy()[ok], ref[ok])
     assert r <= ROT_TOL and t <= DIR_TOL, (r, t)
 
@@ -276,7 +278,7 @@ def test_frame_solve_degenerate_inputs_terminate(handle):
     R = syn.quaternion_to_matrix(batch.gt_poses[4, :4])
     batch.bvs_target[s:e] = batch.bvs_host[s:e] @ R
     res = handle.frame_solve_batch(batch.bvs_host, batch.bvs_target, batch.covs_target, batch.init_poses,
-                                   api.default_frame_opts(), offsets=batch.offsets)
+                                   api.default_frame_opts(use_ransac=0), offsets=batch.offsets)
     assert res.poses.shape == (len(counts), 7)
     assert (res.status[counts == 0] == 7).all()  # PNEC_STATUS_EMPTY
     for b in np.nonzero(counts == 0)[0]:
@@ -287,7 +289,7 @@ def test_frame_solve_degenerate_inputs_terminate(handle):
     # the pure rotation is recovered even though its translation is undefined
     assert rotation_angle(res.poses[4], batch.gt_poses[4]) < 1e-6
     ref, _ = oracle.frame_solve_batch(batch.bvs_host, batch.bvs_target, batch.covs_target, batch.init_poses,
-                                      oracle.default_frame_opts(), offsets=batch.offsets)
+                                      oracle.default_frame_opts(use_ransac=0), offsets=batch.offsets)
     assert rotation_angle(res.poses[6], ref[6]) <= ROT_TOL
 
 
@@ -301,8 +303,8 @@ def test_fused_rounds_kernel_matches_per_round_kernels(handle, monkeypatch):
     args = (batch.bvs_host, batch.bvs_target, batch.covs_target, batch.init_poses)
     for kw in (dict(), dict(weighted_iterations=2), dict(use_ceres=0)):
         monkeypatch.setenv("PNEC_B200_FUSED_ROUNDS_MAX_PAIRS", "512")
-        fused = handle.frame_solve_batch(*args, api.default_frame_opts(**kw), offsets=batch.offsets)
+        fused = handle.frame_solve_batch(*args, api.default_frame_opts(use_ransac=0, **kw), offsets=batch.offsets)
         monkeypatch.setenv("PNEC_B200_FUSED_ROUNDS_MAX_PAIRS", "0")
-        rounds = handle.frame_solve_batch(*args, api.default_frame_opts(**kw), offsets=batch.offsets)
+        rounds = handle.frame_solve_batch(*args, api.default_frame_opts(use_ransac=0, **kw), offsets=batch.offsets)
         np.testing.assert_allclose(fused.poses, rounds.poses, rtol=0, atol=1e-13)
         np.testing.assert_array_equal(fused.es_poses, rounds.es_poses)

@@ -483,7 +483,7 @@ def test_pypnec_module_matches_oracle():
     # addition: the whole frame solve (PNEC::Solve without RANSAC)
     full = pypnec.pysolve(f1, f2, cov_t, init, 1e-13)
     fref, _ = oracle.frame_solve_batch(b.bvs_host, b.bvs_target, b.covs_target, b.init_poses,
-                                       oracle.default_frame_opts(), n_per_problem=N)
+                                       oracle.default_frame_opts(use_ransac=0), n_per_problem=N)
     gotf = np.concatenate([syn.matrix_to_quaternion(full[:3, :3]), full[:3, 3]])
     assert rotation_angle(gotf, fref[0]) <= ROT_TOL and direction_angle(gotf[4:], fref[0][4:]) <= DIR_TOL
 
@@ -525,9 +525,9 @@ def test_cpp_compat_api_matches_oracle(tmp_path):
     assert lines["RansacThrows"] == ["1"]
     # the whole PNEC::Solve pipeline and its stages (pnec.cc:77-124, 273-348)
     fref, fes = oracle.frame_solve_batch(b.bvs_host, b.bvs_target, b.covs_target, b.init_poses,
-                                         oracle.default_frame_opts(), n_per_problem=N)
+                                         oracle.default_frame_opts(use_ransac=0), n_per_problem=N)
     nref, _ = oracle.frame_solve_batch(b.bvs_host, b.bvs_target, b.covs_target, b.init_poses,
-                                       oracle.default_frame_opts(use_nec=1), n_per_problem=N)
+                                       oracle.default_frame_opts(use_ransac=0, use_nec=1), n_per_problem=N)
     wref = oracle.weighted_eigensolver(b.bvs_host, b.bvs_target, b.covs_target, fes[0])
     for tag, ref in (("SolveFull", fref[0]), ("SolveFullES", fes[0]), ("Eigensolver", fes[0]),
                      ("WeightedEigensolver", wref), ("SolveNEC", nref[0])):

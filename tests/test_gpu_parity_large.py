@@ -93,19 +93,19 @@ def test_c2_full_batch_frame_solve_matches_oracle(handle, c2_batch):
     """PNEC::Solve (no RANSAC) for all of C2 through the 4-chunk / priority-stream / two-pass path
     that bench.py's frame_pipeline times, against the oracle (a few seconds of CPU on the box)."""
     b, N = c2_batch, 512
-    fo = oracle.default_frame_opts()
+    fo = oracle.default_frame_opts(use_ransac=0)
     run = lambda bt: oracle.frame_solve_batch(bt.bvs_host, bt.bvs_target, bt.covs_target, bt.init_poses, fo,
                                               n_per_problem=N, num_threads=oracle.max_threads())
     ref, ref_es = run(b)
     ref_p, ref_es_p = run(perturbed(b))
     res = handle.frame_solve_batch(dev(b.bvs_host), dev(b.bvs_target), dev(b.covs_target), dev(b.init_poses),
-                                   api.default_frame_opts(), n_per_problem=N)
+                                   api.default_frame_opts(use_ransac=0), n_per_problem=N)
     check_against_oracle(res.es_poses.cpu().numpy(), ref_es, ref_es_p, 0.99, "eigensolver stage")
     check_against_oracle(res.poses.cpu().numpy(), ref, ref_p, 0.99, "frame solve")
     assert (res.status.cpu().numpy() <= 4).all()
     # the HOST call (chunked H2D) returns the same bits as the device call
     host = handle.frame_solve_batch(b.bvs_host, b.bvs_target, b.covs_target, b.init_poses,
-                                    api.default_frame_opts(), n_per_problem=N)
+                                    api.default_frame_opts(use_ransac=0), n_per_problem=N)
     np.testing.assert_array_equal(host.poses, res.poses.cpu().numpy())
 
 
@@ -123,10 +123,10 @@ def test_frame_solve_devices_are_exact_at_bench_sizes(monkeypatch, B, N):
     args = (dev(batch.bvs_host), dev(batch.bvs_target), dev(batch.covs_target), dev(batch.init_poses))
     for k in PLAIN_ENV:
         monkeypatch.delenv(k, raising=False)
-    fast = api.Handle(0).frame_solve_batch(*args, api.default_frame_opts(), n_per_problem=N)
+    fast = api.Handle(0).frame_solve_batch(*args, api.default_frame_opts(use_ransac=0), n_per_problem=N)
     for k, v in PLAIN_ENV.items():
         monkeypatch.setenv(k, v)
-    plain = api.Handle(0).frame_solve_batch(*args, api.default_frame_opts(), n_per_problem=N)
+    plain = api.Handle(0).frame_solve_batch(*args, api.default_frame_opts(use_ransac=0), n_per_problem=N)
     np.testing.assert_array_equal(fast.es_poses.cpu().numpy(), plain.es_poses.cpu().numpy())
     np.testing.assert_array_equal(fast.poses.cpu().numpy(), plain.poses.cpu().numpy())
     np.testing.assert_array_equal(fast.iterations.cpu().numpy(), plain.iterations.cpu().numpy())
@@ -139,13 +139,13 @@ def test_frame_solve_tight_allowance(handle, n, camera):
     profiles/frame_parity_stress_r01.jsonl), and the excluded pairs are bounded too."""
     B = 600
     batch = syn.make_batch(B, n, seed=500 + n, camera=camera)
-    fo = oracle.default_frame_opts()
+    fo = oracle.default_frame_opts(use_ransac=0)
     run = lambda bt: oracle.frame_solve_batch(bt.bvs_host, bt.bvs_target, bt.covs_target, bt.init_poses, fo,
                                               n_per_problem=n, num_threads=oracle.max_threads())
     ref, ref_es = run(batch)
     ref_p, ref_es_p = run(perturbed(batch))
     res = handle.frame_solve_batch(batch.bvs_host, batch.bvs_target, batch.covs_target, batch.init_poses,
-                                   api.default_frame_opts(), n_per_problem=n)
+                                   api.default_frame_opts(use_ransac=0), n_per_problem=n)
     check_against_oracle(res.es_poses, ref_es, ref_es_p, 0.99, "eigensolver stage")
     check_against_oracle(res.poses, ref, ref_p, 0.99, "frame solve")
 
@@ -174,12 +174,12 @@ def test_c4_miniature_with_the_vo_start_pose(handle, kw):
     init = vo_start_poses(batch)
     fo = dict(max_num_iterations=20, **kw)
     run = lambda bt: oracle.frame_solve_batch(bt.bvs_host, bt.bvs_target, bt.covs_target, init,
-                                              oracle.default_frame_opts(**fo), offsets=batch.offsets,
+                                              oracle.default_frame_opts(use_ransac=0, **fo), offsets=batch.offsets,
                                               num_threads=oracle.max_threads())
     ref, ref_es = run(batch)
     ref_p, _ = run(perturbed(batch))
     res = handle.frame_solve_batch(dev(batch.bvs_host), dev(batch.bvs_target), dev(batch.covs_target), dev(init),
-                                   api.default_frame_opts(**fo), offsets=batch.offsets)
+                                   api.default_frame_opts(use_ransac=0, **fo), offsets=batch.offsets)
     # a refinement started at the wrong rotation AND at the pole is a long, sensitive descent: fewer
     # pairs reproduce under one ulp there (the others are still bounded by the oracle's self-difference)
     check_against_oracle(res.poses.cpu().numpy(), ref, ref_p, 0.5 if "weighted_iterations" in kw else 0.85,

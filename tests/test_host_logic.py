@@ -67,20 +67,27 @@ def test_options_struct_matches_oracle_layout():
 
 
 def test_frame_options_are_the_reference_defaults():
-    """pnec::rel_pose_estimation::Options (pnec_config.h:46-65) as PNEC::Solve reads it, except
-    use_ransac (not built: the default is the configuration that runs)."""
+    """pnec::rel_pose_estimation::Options (pnec_config.h:46-65) as PNEC::Solve reads it, RANSAC
+    included (on by default, 5000 iterations, sample size 10), plus the literals of the call sites."""
     import oracle
 
     f = api.default_frame_opts()
-    assert (f.use_nec, f.use_ceres, f.weighted_iterations, f.use_ransac) == (0, 1, 10, 0)
+    assert (f.use_nec, f.use_ceres, f.weighted_iterations, f.use_ransac) == (0, 1, 10, 1)
+    assert (f.max_ransac_iterations, f.ransac_sample_size) == (5000, 10)  # pnec_config.h:59-60
+    assert f.ransac_threshold == 1e-6  # pnec.cc:250
+    assert f.ransac_probability == 0.99
     assert (f.fibonacci_samples, f.scf_steps) == (500, 10)  # literals of pnec.cc:331 and :342
     assert f.ceres.regularization == 1e-13 and f.ceres.max_num_iterations == 50
-    assert ctypes.sizeof(api.FrameOpts) == 6 * 4 + ctypes.sizeof(api.SolverOpts)
+    assert ctypes.sizeof(api.FrameOpts) == 6 * 4 + ctypes.sizeof(api.SolverOpts) + 2 * 4 + 4 * 8
     o = oracle.default_frame_opts()
-    for name in ("use_nec", "use_ceres", "weighted_iterations", "fibonacci_samples", "scf_steps"):
+    for name in ("use_nec", "use_ceres", "weighted_iterations", "fibonacci_samples", "scf_steps", "use_ransac"):
         assert getattr(o, name) == getattr(f, name), name
-    g = api.default_frame_opts(weighted_iterations=3, regularization=1e-10)
-    assert g.weighted_iterations == 3 and g.ceres.regularization == 1e-10
+    assert (o.ransac.max_iterations, o.ransac.sample_size, o.ransac.threshold, o.ransac.probability,
+            o.ransac.max_variation, o.ransac.seed) == (f.max_ransac_iterations, f.ransac_sample_size,
+                                                       f.ransac_threshold, f.ransac_probability,
+                                                       f.ransac_max_variation, f.ransac_seed)
+    g = api.default_frame_opts(use_ransac=0, weighted_iterations=3, regularization=1e-10)
+    assert g.weighted_iterations == 3 and g.ceres.regularization == 1e-10 and g.use_ransac == 0
     with pytest.raises(AttributeError):
         api.default_frame_opts(no_such_field=1)
 
@@ -88,6 +95,7 @@ def test_frame_options_are_the_reference_defaults():
 def test_frame_entry_points_reject_null_arguments():
     lib = api.load_library()
     assert lib.pnec_frame_solve_batch(None, None, None, None, None) == -1
+    assert lib.pnec_ransac_batch(None, None, None, 0, None, None, None, None, None) == -1
     assert lib.pnec_eigensolver_batch(None, None, None, 0.0, None, None, None, None) == -1
     lib.pnec_frame_opts_default(None)  # must be a no-op
 

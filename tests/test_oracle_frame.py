@@ -127,19 +127,19 @@ def test_frame_solve_option_matrix(batch):
     """PNEC::Solve's branches (pnec.cc:93-123)."""
     n = batch.n_per_problem
     args = (batch.bvs_host, batch.bvs_target, batch.covs_target, batch.init_poses)
-    es_only, es = oracle.frame_solve_batch(*args, oracle.default_frame_opts(use_nec=1, use_ceres=0), n_per_problem=n)
+    es_only, es = oracle.frame_solve_batch(*args, oracle.default_frame_opts(use_ransac=0, use_nec=1, use_ceres=0), n_per_problem=n)
     np.testing.assert_array_equal(es_only, es)
-    wi1, _ = oracle.frame_solve_batch(*args, oracle.default_frame_opts(weighted_iterations=1, use_ceres=0), n_per_problem=n)
+    wi1, _ = oracle.frame_solve_batch(*args, oracle.default_frame_opts(use_ransac=0, weighted_iterations=1, use_ceres=0), n_per_problem=n)
     np.testing.assert_array_equal(wi1, es)
-    wi0, _ = oracle.frame_solve_batch(*args, oracle.default_frame_opts(weighted_iterations=0, use_ceres=0), n_per_problem=n)
+    wi0, _ = oracle.frame_solve_batch(*args, oracle.default_frame_opts(use_ransac=0, weighted_iterations=0, use_ceres=0), n_per_problem=n)
     np.testing.assert_allclose(wi0, batch.init_poses, atol=1e-15)
     # weighted_iterations = 0 + Ceres == the plain refinement of the start pose
     ref, _ = oracle.solve_batch(batch.bvs_host, batch.bvs_target, batch.covs_target, None, batch.init_poses,
                                 oracle.default_opts(oracle.TARGET), n_per_problem=n)
-    got, _ = oracle.frame_solve_batch(*args, oracle.default_frame_opts(weighted_iterations=0), n_per_problem=n)
+    got, _ = oracle.frame_solve_batch(*args, oracle.default_frame_opts(use_ransac=0, weighted_iterations=0), n_per_problem=n)
     np.testing.assert_allclose(got, ref, atol=1e-14)
     # the full pipeline ends closer to the ground truth than the NEC eigensolver alone, on average
-    full, _ = oracle.frame_solve_batch(*args, oracle.default_frame_opts(), n_per_problem=n)
+    full, _ = oracle.frame_solve_batch(*args, oracle.default_frame_opts(use_ransac=0), n_per_problem=n)
     e_es = np.mean([rotation_angle(a, g) for a, g in zip(es, batch.gt_poses)])
     e_full = np.mean([rotation_angle(a, g) for a, g in zip(full, batch.gt_poses)])
     assert e_full < e_es
@@ -154,7 +154,7 @@ def test_oracle_reproduces_committed_frame_fixtures(golden_frame):
         for k in (0, 7, 23):
             q, _ = oracle.eigensolver(f1[k * n:(k + 1) * n], f2[k * n:(k + 1) * n], init[k])
             assert rotation_angle(np.r_[q, 0, 0, 1], np.r_[g[f"{name}/es_quat"][k], 0, 0, 1]) < 1e-12
-        poses, es = oracle.frame_solve_batch(f1, f2, cov, init, oracle.default_frame_opts(), n_per_problem=n,
+        poses, es = oracle.frame_solve_batch(f1, f2, cov, init, oracle.default_frame_opts(use_ransac=0), n_per_problem=n,
                                              num_threads=oracle.max_threads())
         stable = np.array([rotation_angle(a, b) < 1e-8 and direction_angle(a[4:], b[4:]) < 1e-8
                            for a, b in zip(g[f"{name}/default/poses"], g[f"{name}/default/poses_ulp"])])

@@ -18,7 +18,7 @@ def run(name, b, **kw):
     d = [T(x) for x in (b.bvs_host, b.bvs_target, b.covs_target, b.init_poses)]
     rows = {}
     for tag, fo in (("default", {}), ("weighted_iterations=1", dict(weighted_iterations=1))):
-        o = api.default_frame_opts(**fo)
+        o = api.default_frame_opts(use_ransac=0, **fo)
         rows[tag] = timeit(lambda: h.frame_solve_batch(*d, o, **kw))
     rows["refinement only"] = timeit(lambda: h.solve_batch(d[0], d[1], d[2], None, d[3], api.default_opts(api.TARGET), **kw))
     B = b.num_problems

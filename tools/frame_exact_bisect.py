@@ -18,7 +18,7 @@ for B, N, host in [(640, 160, False), (4608, 96, False), (600, 100, True)]:
         for k in env:
             os.environ[SW[k][0]] = SW[k][1]
         try:
-            r = api.Handle(0).frame_solve_batch(*args, api.default_frame_opts(), n_per_problem=N)
+            r = api.Handle(0).frame_solve_batch(*args, api.default_frame_opts(use_ransac=0), n_per_problem=N)
         except Exception as e:
             print(B, N, host, env, "ERROR", e); return None
         p = r.poses if host else r.poses.cpu().numpy()

@@ -20,14 +20,14 @@ def perturbed(b, seed=0):
     return p
 
 def run(name, b, **kw):
-    fo = oracle.default_frame_opts()
+    fo = oracle.default_frame_opts(use_ransac=0)
     t0 = time.time()
     ref, ref_es = oracle.frame_solve_batch(b.bvs_host, b.bvs_target, b.covs_target, b.init_poses, fo, num_threads=threads, **kw)
     dt = time.time() - t0
     p = perturbed(b)
     ref_p, ref_es_p = oracle.frame_solve_batch(p.bvs_host, p.bvs_target, p.covs_target, p.init_poses, fo, num_threads=threads, **kw)
     res = h.frame_solve_batch(dev(b.bvs_host), dev(b.bvs_target), dev(b.covs_target), dev(b.init_poses),
-                              api.default_frame_opts(), **kw)
+                              api.default_frame_opts(use_ransac=0), **kw)
     poses, es = res.poses.cpu().numpy(), res.es_poses.cpu().numpy()
     ang = lambda A, Bm: (np.array([rotation_angle(a, c) for a, c in zip(A, Bm)]),
                          np.array([direction_angle(a[4:], c[4:]) for a, c in zip(A, Bm)]))

@@ -36,7 +36,7 @@ rows["refinement (solve_batch)"] = timeit(lambda: h.solve_batch(f1, f2, ct, None
 for name, kw in [("frame solve, default (10 weighted iterations)", {}),
                  ("frame solve, weighted_iterations=1", dict(weighted_iterations=1)),
                  ("frame solve, NEC", dict(use_nec=1))]:
-    o = api.default_frame_opts(**kw)
+    o = api.default_frame_opts(use_ransac=0, **kw)
     rows[name] = timeit(lambda: h.frame_solve_batch(f1, f2, ct, init, o, n_per_problem=N), reps=3, warm=1)
 hist = np.bincount(info.cpu().numpy(), minlength=9).tolist()
 for k, v in rows.items():

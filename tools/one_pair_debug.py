@@ -6,4 +6,4 @@ h=api.Handle(0)
 N=512
 b=syn.make_batch(1,N,seed=3)
 for _ in range(2):
-    h.frame_solve_batch(b.bvs_host,b.bvs_target,b.covs_target,b.init_poses,api.default_frame_opts(),n_per_problem=N)
+    h.frame_solve_batch(b.bvs_host,b.bvs_target,b.covs_target,b.init_poses,api.default_frame_opts(use_ransac=0),n_per_problem=N)

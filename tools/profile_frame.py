@@ -19,6 +19,6 @@ for _ in range(3):
         h.eigensolver_batch(f1, f2, es, covs_target=ct, weight_poses=es, n_per_problem=N)
         h.scf_translation_batch(f1, f2, ct, es, n_per_problem=N)
     else:
-        h.frame_solve_batch(f1, f2, ct, init, api.default_frame_opts(), n_per_problem=N)
+        h.frame_solve_batch(f1, f2, ct, init, api.default_frame_opts(use_ransac=0), n_per_problem=N)
 torch.cuda.synchronize()
 print("done", h.launch_count)

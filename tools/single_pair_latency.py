@@ -10,7 +10,7 @@ h = api.Handle(0)
 for N in (100, 512, 2000):
     b = syn.make_batch(8, N, seed=3)
     args = lambda k: (b.bvs_host[k*N:(k+1)*N], b.bvs_target[k*N:(k+1)*N], b.covs_target[k*N:(k+1)*N], b.init_poses[k:k+1])
-    fo, so = api.default_frame_opts(), api.default_opts(api.TARGET)
+    fo, so = api.default_frame_opts(use_ransac=0), api.default_opts(api.TARGET)
     for _ in range(3):
         h.frame_solve_batch(*args(0), fo, n_per_problem=N); h.solve_batch(*args(0)[:3], None, args(0)[3], so, n_per_problem=N)
     reps = 50
@@ -21,7 +21,7 @@ for N in (100, 512, 2000):
     for r in range(reps): h.solve_batch(*args(r % 8)[:3], None, args(r % 8)[3], so, n_per_problem=N)
     t_solve = (time.perf_counter() - t0) / reps
     t0 = time.perf_counter()
-    for r in range(8): oracle.frame_solve_batch(*args(r), oracle.default_frame_opts(), n_per_problem=N, num_threads=1)
+    for r in range(8): oracle.frame_solve_batch(*args(r), oracle.default_frame_opts(use_ransac=0), n_per_problem=N, num_threads=1)
     c_frame = (time.perf_counter() - t0) / 8
     t0 = time.perf_counter()
     for r in range(8): oracle.solve_batch(*args(r)[:3], None, args(r)[3], oracle.default_opts(oracle.TARGET), n_per_problem=N, num_threads=1)
