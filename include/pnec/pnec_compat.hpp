@@ -28,9 +28,25 @@
 #include <cstdlib>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "../pnec_b200.h"
+
+// Interop with the reference's own pose / vector types when their headers are on the include path
+// (they are not needed otherwise).
+#if defined(__has_include)
+#if __has_include(<Eigen/Core>) && __has_include(<Eigen/Geometry>)
+#include <Eigen/Core>
+#include <Eigen/Geometry>
+#define PNEC_COMPAT_HAS_EIGEN 1
+#endif
+#if defined(PNEC_COMPAT_HAS_EIGEN) && __has_include(<sophus/se3.hpp>)
+#include <sophus/se3.hpp>
+#define PNEC_COMPAT_HAS_SOPHUS 1
+#endif
+#endif
 
 namespace pnec {
 
@@ -127,12 +143,33 @@ struct Quat {  // x, y, z, w == Eigen::Quaterniond::coeffs()
 };
 static_assert(sizeof(Quat) == 32, "Quat must be layout-identical to Eigen::Quaterniond");
 
+namespace detail {
+template <class...>
+using void_t = void;
+// anything that looks like Sophus::SE3d: .unit_quaternion() with x()/y()/z()/w(), .translation() indexable
+template <class S, class = void>
+struct is_se3_like : std::false_type {};
+template <class S>
+struct is_se3_like<S, void_t<decltype(std::declval<const S &>().unit_quaternion().x()),
+                             decltype(std::declval<const S &>().unit_quaternion().w()),
+                             decltype(std::declval<const S &>().translation()[0])>> : std::true_type {};
+}  // namespace detail
+
 struct SE3 {  // memory order of Sophus::SE3d: unit quaternion (x,y,z,w), translation
   Quat q;
   Vec3 t;
   SE3() {}
   SE3(const Quat &q_, const Vec3 &t_) : q(q_.normalized()), t(t_) {}
   SE3(const Mat3 &R, const Vec3 &t_) : q(Quat::FromRotationMatrix(R).normalized()), t(t_) {}
+  // from the reference's pose type (Sophus::SE3d) or anything with the same accessors: a call site
+  // that passes `const Sophus::SE3d &initial_pose` compiles unchanged
+  template <class S, class = typename std::enable_if<detail::is_se3_like<S>::value && !std::is_same<S, SE3>::value>::type>
+  SE3(const S &o) {  // NOLINT(google-explicit-constructor): the conversion is the point
+    const auto &oq = o.unit_quaternion();
+    q = Quat(oq.w(), oq.x(), oq.y(), oq.z()).normalized();
+    const auto &ot = o.translation();
+    t = Vec3(ot[0], ot[1], ot[2]);
+  }
   const Quat &unit_quaternion() const { return q; }
   Mat3 rotationMatrix() const { return q.toRotationMatrix(); }
   const Vec3 &translation() const { return t; }
@@ -143,11 +180,20 @@ struct SE3 {  // memory order of Sophus::SE3d: unit quaternion (x,y,z,w), transl
             R(2, 0), R(2, 1), R(2, 2), t[2], 0, 0, 0, 1};
   }
   const double *data() const { return q.c; }
+#ifdef PNEC_COMPAT_HAS_SOPHUS
+  // back to the reference's type: `Sophus::SE3d rel_pose = pnec.Solve(...)` compiles unchanged
+  operator Sophus::SE3d() const {  // NOLINT(google-explicit-constructor)
+    return Sophus::SE3d(Eigen::Quaterniond(q.c[3], q.c[0], q.c[1], q.c[2]), Eigen::Vector3d(t[0], t[1], t[2]));
+  }
+#endif
 };
 static_assert(sizeof(SE3) == 56, "SE3 must be 7 contiguous doubles");
 
 namespace detail {
 
+// One handle per calling thread: the reference's solver objects are per-call locals
+// (`PNECCeres optimizer;`, pnec.cc:355), so concurrent callers never contend; here every thread gets
+// its own device scratch and the handle-wide mutex of the C-ABI is never shared.
 inline pnec_handle *Handle() {
   struct Holder {
     pnec_handle *h = nullptr;
@@ -158,7 +204,7 @@ inline pnec_handle *Handle() {
     }
     ~Holder() { pnec_destroy(h); }
   };
-  static Holder holder;  // no CPU fallback: construction throws without a B200
+  static thread_local Holder holder;  // no CPU fallback: construction throws without a B200
   return holder.h;
 }
 
@@ -581,64 +627,70 @@ struct Options {
   int min_matches_ = 30;
   int min_inliers_ = 10;
   int min_matches_further_ = 20;
+  // extension (not in the reference): key of RANSAC's random stream.  opengv seeds from time(0) and
+  // rand(), so the reference is not reproducible run to run; this implementation is, per seed.
+  std::uint64_t ransac_seed_ = 1;
 };
 
 class PNEC {
  public:
   explicit PNEC(const Options &options) : options_(options) {}
 
-  // src/rel_pose_estimation/pnec.cc:77-124: Eigensolver -> (WeightedEigensolver) -> CeresSolver /
-  // NECCeresSolver, every stage on the GPU in one pnec_frame_solve_batch call.  RANSAC
-  // (use_ransac_, the reference's default) is not built: Solve() throws for it instead of
-  // silently skipping the stage; `inliers` is cleared as in the non-RANSAC branch (pnec.cc:277).
-  // Like the reference, the refinement runs with default Ceres options (pnec.cc:355 constructs
-  // `PNECCeres optimizer;`) and the TARGET noise frame, whatever options_ holds.
+  // src/rel_pose_estimation/pnec.cc:77-124: Eigensolver (+ RANSAC and InlierExtraction with
+  // use_ransac_, the default) -> (WeightedEigensolver) -> CeresSolver / NECCeresSolver, every stage on
+  // the GPU in one pnec_frame_solve_batch call.  `inliers` receives ransac.inliers_ (ascending indices
+  // into bvs1 / bvs2) and is cleared without RANSAC (pnec.cc:277).  Like the reference, the refinement
+  // runs with default Ceres options (pnec.cc:355 constructs `PNECCeres optimizer;`) and the TARGET
+  // noise frame, whatever options_ holds.
   template <class BVs, class Covs>
   SE3 Solve(const BVs &bvs1, const BVs &bvs2, const Covs &projected_covs, const SE3 &initial_pose) {
-    SE3 es;
-    return SolveImpl(bvs1, bvs2, projected_covs, initial_pose, &es);
+    std::vector<int> inliers;
+    return Solve(bvs1, bvs2, projected_covs, initial_pose, inliers);
   }
   template <class BVs, class Covs>
   SE3 Solve(const BVs &bvs1, const BVs &bvs2, const Covs &projected_covs, const SE3 &initial_pose,
             std::vector<int> &inliers) {
-    inliers.clear();
-    return Solve(bvs1, bvs2, projected_covs, initial_pose);
+    return SolveImpl(bvs1, bvs2, detail::AsDoubles(projected_covs, 72), initial_pose, FrameOpts(), &inliers, nullptr);
   }
-  // The reference times its stages separately (pnec.cc:135-208); here they run back to back on the
-  // device inside one call, so the total goes to ceres_ and the stage fields stay zero.
+  // The timed overloads (pnec.cc:127-208): nec_es_ = Eigensolver + InlierExtraction, it_es_ =
+  // WeightedEigensolver, avg_it_es_ = it_es_ / weighted_iterations_, ceres_ = the refinement --
+  // measured with CUDA events around the same stages on the device, truncated to milliseconds like
+  // the reference's duration_cast (a single pair takes well under one: expect zeros).
   template <class BVs, class Covs>
   SE3 Solve(const BVs &bvs1, const BVs &bvs2, const Covs &projected_covs, const SE3 &initial_pose,
             common::FrameTiming &timing) {
-    const auto tic = std::chrono::high_resolution_clock::now();
-    SE3 r = Solve(bvs1, bvs2, projected_covs, initial_pose);
-    timing.ceres_ = std::chrono::duration_cast<std::chrono::milliseconds>(
-        std::chrono::high_resolution_clock::now() - tic);
-    return r;
+    std::vector<int> inliers;
+    return Solve(bvs1, bvs2, projected_covs, initial_pose, inliers, timing);
   }
   template <class BVs, class Covs>
   SE3 Solve(const BVs &bvs1, const BVs &bvs2, const Covs &projected_covs, const SE3 &initial_pose,
             std::vector<int> &inliers, common::FrameTiming &timing) {
-    inliers.clear();
-    return Solve(bvs1, bvs2, projected_covs, initial_pose, timing);
+    float ms[3] = {0, 0, 0};
+    SE3 r = SolveImpl(bvs1, bvs2, detail::AsDoubles(projected_covs, 72), initial_pose, FrameOpts(), &inliers, ms);
+    last_stage_ms_[0] = ms[0]; last_stage_ms_[1] = ms[1]; last_stage_ms_[2] = ms[2];
+    const auto to_ms = [](double v) { return std::chrono::milliseconds(static_cast<long long>(v)); };
+    timing.nec_es_ = to_ms(ms[0]);
+    if (!options_.use_nec_) {
+      timing.it_es_ = to_ms(options_.weighted_iterations_ > 1 ? ms[1] : 0.0);
+      if (options_.weighted_iterations_ > 1)
+        timing.avg_it_es_ = to_ms(ms[1] / static_cast<double>(options_.weighted_iterations_));
+    }
+    timing.ceres_ = to_ms(options_.use_ceres_ ? ms[2] : 0.0);
+    return r;
   }
+  // stage times of the last timed Solve in (fractional) milliseconds: nec_es, it_es, ceres
+  const double *LastStageMilliseconds() const { return last_stage_ms_; }
 
-  // PNEC::Eigensolver, use_ransac_ == false (pnec.cc:273-279): opengv::relative_pose::eigensolver
-  // rotation started at initial_pose, translation = TranslationFromM(ComposeM(bvs1, bvs2, rotation)).
+  // PNEC::Eigensolver (pnec.cc:231-281): with use_ransac_ opengv's RANSAC over the eigensolver,
+  // optimizeModelCoefficients on the inliers and the translation from ComposeM over the inliers;
+  // without, opengv::relative_pose::eigensolver started at initial_pose and the translation from
+  // ComposeM over everything (`inliers` cleared).
   template <class BVs>
   SE3 Eigensolver(const BVs &bvs1, const BVs &bvs2, const SE3 &initial_pose, std::vector<int> &inliers) {
-    if (options_.use_ransac_)
-      throw std::logic_error("pnec_b200: PNEC::Eigensolver with use_ransac_=true is not implemented");
-    inliers.clear();
     pnec_frame_opts fo = FrameOpts();
     fo.use_nec = 1;
     fo.use_ceres = 0;
-    pnec_batch b = MakeBatch(bvs1, bvs2, static_cast<const double *>(nullptr), initial_pose);
-    SE3 out;
-    pnec_frame_out o{};
-    o.poses = reinterpret_cast<double *>(&out);
-    if (pnec_frame_solve_batch(detail::Handle(), &b, &fo, &o, nullptr) != PNEC_OK)
-      throw std::runtime_error(std::string("pnec_frame_solve_batch: ") + pnec_last_error());
-    return out;
+    return SolveImpl(bvs1, bvs2, static_cast<const double *>(nullptr), initial_pose, fo, &inliers, nullptr);
   }
 
   // PNEC::WeightedEigensolver (pnec.cc:283-348): `initial_pose` supplies the weights of every
@@ -727,9 +779,8 @@ class PNEC {
   // Batched Solve(): B frame pairs per call, flat C-ABI layout, host memory.
   void SolveBatch(std::size_t num_problems, const int64_t *offsets, std::size_t n_per_problem, const double *bvs1,
                   const double *bvs2, const double *projected_covariances, const SE3 *initial_poses, SE3 *results,
-                  SE3 *eigensolver_results = nullptr, int32_t *status = nullptr, int32_t *iterations = nullptr) {
-    if (options_.use_ransac_)
-      throw std::logic_error("pnec_b200: PNEC::SolveBatch with use_ransac_=true is not implemented");
+                  SE3 *eigensolver_results = nullptr, int32_t *status = nullptr, int32_t *iterations = nullptr,
+                  int32_t *num_inliers = nullptr, int32_t *inlier_index = nullptr) {
     const pnec_frame_opts fo = FrameOpts();
     pnec_batch b{};
     b.num_problems = static_cast<int64_t>(num_problems);
@@ -745,6 +796,8 @@ class PNEC {
     o.es_poses = reinterpret_cast<double *>(eigensolver_results);
     o.status = status;
     o.iterations = iterations;
+    o.num_inliers = num_inliers;    // [B]
+    o.inlier_index = inlier_index;  // [total], pair b's list at its offset (pnec_b200.h)
     if (pnec_frame_solve_batch(detail::Handle(), &b, &fo, &o, nullptr) != PNEC_OK)
       throw std::runtime_error(std::string("pnec_frame_solve_batch: ") + pnec_last_error());
   }
@@ -762,6 +815,9 @@ class PNEC {
     fo.use_ceres = options_.use_ceres_ ? 1 : 0;
     fo.weighted_iterations = static_cast<int32_t>(options_.weighted_iterations_);
     fo.use_ransac = options_.use_ransac_ ? 1 : 0;
+    fo.max_ransac_iterations = options_.max_ransac_iterations_;
+    fo.ransac_sample_size = options_.ransac_sample_size_;
+    fo.ransac_seed = options_.ransac_seed_;
     fo.ceres.regularization = options_.regularization_;
     return fo;
   }
@@ -777,25 +833,28 @@ class PNEC {
     b.poses = pose.data();
     return b;
   }
-  template <class BVs, class Covs>
-  SE3 SolveImpl(const BVs &bvs1, const BVs &bvs2, const Covs &projected_covs, const SE3 &initial_pose, SE3 *es) {
-    if (options_.use_ransac_)
-      throw std::logic_error(
-          "pnec_b200: PNEC::Solve with use_ransac_=true is not implemented (set Options::use_ransac_ = false)");
-    const pnec_frame_opts fo = FrameOpts();
-    pnec_batch b = MakeBatch(bvs1, bvs2, detail::AsDoubles(projected_covs, 72), initial_pose);
-    SE3 out;
-    int32_t status = PNEC_STATUS_EMPTY, iters = 0;
+  template <class BVs>
+  SE3 SolveImpl(const BVs &bvs1, const BVs &bvs2, const double *covs, const SE3 &initial_pose,
+                const pnec_frame_opts &fo, std::vector<int> *inliers, float *stage_ms) {
+    pnec_batch b = MakeBatch(bvs1, bvs2, covs, initial_pose);
+    SE3 out, es;
+    int32_t status = PNEC_STATUS_EMPTY, iters = 0, num_inliers = 0;
+    const std::size_t n = bvs1.size();
+    std::vector<int32_t> index(fo.use_ransac && inliers ? n : 0);
     pnec_frame_out o{};
     o.poses = reinterpret_cast<double *>(&out);
-    o.es_poses = reinterpret_cast<double *>(es);
+    o.es_poses = reinterpret_cast<double *>(&es);
     o.status = &status;
     o.iterations = &iters;
+    o.num_inliers = &num_inliers;
+    o.inlier_index = index.empty() ? nullptr : index.data();
+    o.stage_ms = stage_ms;
     if (pnec_frame_solve_batch(detail::Handle(), &b, &fo, &o, nullptr) != PNEC_OK)
       throw std::runtime_error(std::string("pnec_frame_solve_batch: ") + pnec_last_error());
+    if (inliers) inliers->assign(index.begin(), index.begin() + (index.empty() ? 0 : num_inliers));
     last_status_ = status;
     last_iterations_ = iters;
-    last_es_ = *es;
+    last_es_ = es;
     return out;
   }
 
@@ -803,6 +862,7 @@ class PNEC {
   int last_status_ = PNEC_STATUS_EMPTY;
   int last_iterations_ = 0;
   SE3 last_es_;
+  double last_stage_ms_[3] = {0, 0, 0};
 };
 
 }  // namespace rel_pose_estimation

@@ -346,8 +346,16 @@ class Handle:
             B = poses.shape[0]
             b.memspace = MEM_HOST
         keep.extend([f1, f2, ct, ch, poses])
-        if f2 is not None and (f2.numel() if device else f2.size) != total * 3:
+        size = (lambda t: t.numel()) if device else (lambda a: a.size)
+        if f2 is not None and size(f2) != total * 3:
             raise PnecError("bvs_host and bvs_target differ in size")
+        # the C side cannot see array lengths: an undersized covariance or pose array would be read
+        # out of bounds there
+        for name, arr in (("covs_target", ct), ("covs_host", ch)):
+            if arr is not None and size(arr) != total * 9:
+                raise PnecError(f"{name} must hold 9 doubles per correspondence ({total * 9}), got {size(arr)}")
+        if poses is not None and size(poses) != B * 7:
+            raise PnecError("poses must hold 7 doubles per frame pair")
         b.num_problems = B
         if offsets is not None:
             offsets = np.ascontiguousarray(offsets, dtype=np.int64)

@@ -79,6 +79,47 @@ int env_int(const char *name, int dflt) {
   return (v && *v) ? std::atoi(v) : dflt;
 }
 
+// Tuning / debugging switches (PNEC_B200_* environment variables), read ONCE when a handle is
+// created: no getenv on the call path (a single-pair solve is a 0.1 ms affair).
+struct Config {
+  int dump_timing = 0;
+  int eval_cfg = 0;
+  int frame_chunks = 0;
+  int fused_rounds_max_pairs = 512;
+  int h2d_chunks = 0;
+  int no_bulk = 0;
+  int no_frame_shortcuts = 0;
+  int no_lm_ahead = 0;
+  int no_stager = 0;
+  int ransac_warps = 0;
+  int scf_debug = 0;
+  int scf_defer = 48;
+  int scf_warps = 0;
+  int solve_warps = 0;
+  int stream_cfg = 3;
+  int stream_min_n = 896;
+  int copy_threads = 0;  // PNEC_B200_COPY_THREADS: worker threads of the pageable-input stager (0 = auto)
+  void load() {
+    dump_timing = env_int("PNEC_B200_DUMP_TIMING", 0);
+    eval_cfg = env_int("PNEC_B200_EVAL_CFG", 0);
+    frame_chunks = env_int("PNEC_B200_FRAME_CHUNKS", 0);
+    fused_rounds_max_pairs = env_int("PNEC_B200_FUSED_ROUNDS_MAX_PAIRS", 512);
+    h2d_chunks = env_int("PNEC_B200_H2D_CHUNKS", 0);
+    no_bulk = env_int("PNEC_B200_NO_BULK", 0);
+    no_frame_shortcuts = env_int("PNEC_B200_NO_FRAME_SHORTCUTS", 0);
+    no_lm_ahead = env_int("PNEC_B200_NO_LM_AHEAD", 0);
+    no_stager = env_int("PNEC_B200_NO_STAGER", 0);
+    ransac_warps = env_int("PNEC_B200_RANSAC_WARPS", 0);
+    scf_debug = env_int("PNEC_B200_SCF_DEBUG", 0);
+    scf_defer = env_int("PNEC_B200_SCF_DEFER", 48);
+    scf_warps = env_int("PNEC_B200_SCF_WARPS", 0);
+    solve_warps = env_int("PNEC_B200_SOLVE_WARPS", 0);
+    stream_cfg = env_int("PNEC_B200_STREAM_CFG", 3);
+    stream_min_n = env_int("PNEC_B200_STREAM_MIN_N", 896);
+    copy_threads = env_int("PNEC_B200_COPY_THREADS", 0);
+  }
+};
+
 // ---------------------------------------------------------- pageable host inputs
 //
 // The reference hands over std::vector storage, i.e. pageable memory, which cudaMemcpyAsync moves
@@ -158,6 +199,7 @@ class HostStager {
  public:
   static constexpr int kSlots = 4;
   static constexpr size_t kSlotBytes = 8u << 20;
+  int copy_threads = 0;  // 0 = auto
   ~HostStager() {
     for (int i = 0; i < kSlots; ++i) {
       if (ev_[i]) cudaEventDestroy(ev_[i]);
@@ -182,7 +224,7 @@ class HostStager {
         if (e != cudaSuccess) return e;
       }
       int t = static_cast<int>(std::thread::hardware_concurrency());
-      if (const char *v = std::getenv("PNEC_B200_COPY_THREADS")) t = 2 * std::atoi(v);
+      if (copy_threads > 0) t = 2 * copy_threads;
       pool_.reset(new CopyPool(std::min(8, std::max(1, t / 2))));
     }
     for (size_t off = 0; off < bytes; off += kSlotBytes) {
@@ -218,6 +260,7 @@ struct pnec_handle {
   int sm_count = 0;
   size_t smem_optin = 0;
   int64_t launches = 0;
+  Config cfg;
   // staging for HOST-memspace calls and for the device copy of offsets
   DevBuf d_f1, d_f2, d_ct, d_ch, d_off, d_poses;
   DevBuf d_out_poses, d_out_status, d_out_iters, d_out_cost, d_out_init, d_out_grad, d_out_jtj;
@@ -235,6 +278,8 @@ struct pnec_handle {
   cudaEvent_t ev_fork = nullptr, ev_join[kMaxChunks] = {}, ev_es[kMaxChunks] = {};
   cudaEvent_t ev_round[kMaxChunks][kMaxRounds] = {};
   cudaEvent_t ev_stage[4] = {};  // stage timings of a frame solve (out->stage_ms)
+  cudaEvent_t ev_last = nullptr; // end of the previous call's device work (see CallScope)
+  cudaStream_t last_stream = nullptr;
   DevBuf d_fr_rounds;             // poses of every weighted round: [rounds][B][7]
   HostStager stager;              // pinned ring + copy threads for pageable host inputs
   int sphere_samples = -1;
@@ -242,6 +287,31 @@ struct pnec_handle {
 };
 
 namespace {
+
+// Every call of a handle uses the same scratch buffers, and DEVICE-memspace calls return before their
+// kernels have run: a later call on ANOTHER stream must not touch the scratch while they are in
+// flight.  The end of every call is marked with an event on its stream and a call on a different
+// stream waits for it first (same stream: stream order already serialises).  If a call fails after it
+// has forked work onto the handle's side streams, the device is synchronised before returning, so that
+// no copy into or out of the caller's buffers is still in flight.
+struct CallScope {
+  pnec_handle *h;
+  cudaStream_t stream;
+  bool forked = false, ok = false;
+  CallScope(pnec_handle *h_, cudaStream_t s) : h(h_), stream(s) {
+    if (h->ev_last && h->last_stream != stream) cudaStreamWaitEvent(stream, h->ev_last, 0);
+  }
+  ~CallScope() {
+    if (forked && !ok) cudaDeviceSynchronize();
+    if (!h->ev_last && cudaEventCreateWithFlags(&h->ev_last, cudaEventDisableTiming) != cudaSuccess) {
+      h->ev_last = nullptr;
+      cudaGetLastError();
+      return;
+    }
+    cudaEventRecord(h->ev_last, stream);
+    h->last_stream = stream;
+  }
+};
 
 struct Staged {
   BatchView bv;
@@ -274,14 +344,23 @@ int validate_batch(const pnec_batch *b, int variant, bool need_poses) {
     return fail(PNEC_ERR_INVALID_ARGUMENT, "unknown memspace");
   if (variant < PNEC_VARIANT_NEC || variant > PNEC_VARIANT_SYMMETRIC)
     return fail(PNEC_ERR_INVALID_ARGUMENT, "unknown residual variant");
+  // grids are one CTA per frame pair and the kernels index a pair's correspondences with int
+  if (b->num_problems > 0x7fffffffLL) return fail(PNEC_ERR_INVALID_ARGUMENT, "more than 2^31 - 1 frame pairs");
   long long total = 0;
   if (b->offsets) {
     if (b->offsets[0] < 0) return fail(PNEC_ERR_INVALID_ARGUMENT, "offsets[0] < 0");
-    for (int64_t i = 0; i < b->num_problems; ++i)
+    for (int64_t i = 0; i < b->num_problems; ++i) {
       if (b->offsets[i + 1] < b->offsets[i])
         return fail(PNEC_ERR_INVALID_ARGUMENT, "offsets must be non-decreasing");
+      if (b->offsets[i + 1] - b->offsets[i] > 0x7ffffff0LL)
+        return fail(PNEC_ERR_INVALID_ARGUMENT, "a frame pair has more than 2^31 - 16 correspondences");
+    }
     total = b->offsets[b->num_problems];
   } else {
+    if (b->n_per_problem > 0x7ffffff0LL)
+      return fail(PNEC_ERR_INVALID_ARGUMENT, "n_per_problem exceeds 2^31 - 16");
+    if (b->num_problems > 0 && b->n_per_problem > (0x7fffffffffffffffLL / 72) / b->num_problems)
+      return fail(PNEC_ERR_INVALID_ARGUMENT, "num_problems * n_per_problem overflows");
     total = b->num_problems * b->n_per_problem;
   }
   if (total > 0) {
@@ -355,7 +434,7 @@ int stage_copy(pnec_handle *h, const pnec_batch *b, int variant, long long p0, l
   auto at = [](void *base, long long bytes) { return static_cast<char *>(base) + bytes; };
   // pinned sources go straight to the copy engine; large pageable ones through the pinned ring
   auto h2d = [&](void *dst, const double *src, size_t bytes) -> cudaError_t {
-    if (bytes >= (4u << 20) && !env_int("PNEC_B200_NO_STAGER", 0) && HostStager::pageable(src))
+    if (bytes >= (4u << 20) && !h->cfg.no_stager && HostStager::pageable(src))
       return h->stager.h2d(dst, src, bytes, stream);
     return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream);
   };
@@ -452,7 +531,7 @@ int launch_solve_stream_t(pnec_handle *h, const SolveArgs &a, cudaStream_t strea
 
 template <int V>
 int launch_solve_stream_v(pnec_handle *h, const SolveArgs &a, cudaStream_t stream) {
-  switch (env_int("PNEC_B200_STREAM_CFG", 3)) {
+  switch (h->cfg.stream_cfg) {
     case 1: return launch_solve_stream_t<V, 6, 4, 2>(h, a, stream);   // 2 CTAs x 6 warps per SM
     case 2: return launch_solve_stream_t<V, 12, 4, 1>(h, a, stream);  // 1 CTA x 12 warps
     case 3: return launch_solve_stream_t<V, 4, 4, 3>(h, a, stream);   // 3 CTAs x 4 warps
@@ -471,8 +550,8 @@ int launch_solve(pnec_handle *h, const SolveArgs &a0, int variant, long long max
   if (a.bv.num_problems == 0) return PNEC_OK;
   // Large frame pairs: stream every pass (bulk-copy rings) instead of keeping one pair per SM
   // resident.  Needs 16-byte aligned arrays; SYMMETRIC (192 B / correspondence) stays resident-first.
-  const long long stream_min_n = env_int("PNEC_B200_STREAM_MIN_N", 896);
-  if (bulk_ok(a.bv) && !env_int("PNEC_B200_NO_BULK", 0) && max_n > stream_min_n) {
+  const long long stream_min_n = h->cfg.stream_min_n;
+  if (bulk_ok(a.bv) && !h->cfg.no_bulk && max_n > stream_min_n) {
     a.use_bulk = 1;
     a.cap_elems = 0;
     a.dbg = nullptr;
@@ -483,7 +562,7 @@ int launch_solve(pnec_handle *h, const SolveArgs &a0, int variant, long long max
       default: return launch_solve_stream_v<PNEC_VARIANT_SYMMETRIC>(h, a, stream);
     }
   }
-  int nw = env_int("PNEC_B200_SOLVE_WARPS", 0);
+  int nw = h->cfg.solve_warps;
   // Warps per frame pair (measured on B200, tools/nw_sweep.py): the solve is latency-bound, so
   // what pays is the number of pairs resident per SM, not the width of one pair.  One warp per
   // pair wins while >= 7 pairs fit in shared memory; 4 warps once only 3 fit.
@@ -495,7 +574,7 @@ int launch_solve(pnec_handle *h, const SolveArgs &a0, int variant, long long max
   if (cap_elems < 2) cap_elems = 2;
   a.cap_elems = static_cast<int>(cap_elems);
   a.use_bulk = bulk_ok(a.bv) ? 1 : 0;
-  if (env_int("PNEC_B200_NO_BULK", 0)) a.use_bulk = 0;
+  if (h->cfg.no_bulk) a.use_bulk = 0;
   a.dbg = nullptr;
 #ifdef PNEC_PHASE_TIMING
   static long long *dbg_buf = nullptr;
@@ -511,7 +590,7 @@ int launch_solve(pnec_handle *h, const SolveArgs &a0, int variant, long long max
     default: rc = launch_solve_v<PNEC_VARIANT_SYMMETRIC>(h, a, nw, dyn, stream); break;
   }
 #ifdef PNEC_PHASE_TIMING
-  if (rc == PNEC_OK && env_int("PNEC_B200_DUMP_TIMING", 0)) dump_phase_timing(a);
+  if (rc == PNEC_OK && h->cfg.dump_timing) dump_phase_timing(a);
 #endif
   return rc;
 }
@@ -544,7 +623,7 @@ int launch_eval_warp_t(pnec_handle *h, const EvalArgs &a, cudaStream_t stream) {
 template <int V>
 int launch_eval_v(pnec_handle *h, const EvalArgs &a, long long max_n, cudaStream_t stream) {
   (void)max_n;
-  int cfg = env_int("PNEC_B200_EVAL_CFG", 0);
+  int cfg = h->cfg.eval_cfg;
   if (cfg == 0) cfg = a.use_bulk ? 11 : 2;  // 3 stages of 32 correspondences per warp: measured best
   switch (cfg) {
     case 2: return launch_eval_t<V, 4, 4, 3>(h, a, stream);    // CTA per problem, 128-wide tiles
@@ -565,7 +644,7 @@ int launch_eval(pnec_handle *h, const EvalArgs &a0, int variant, long long max_n
   EvalArgs a = a0;
   if (a.bv.num_problems == 0) return PNEC_OK;
   a.use_bulk = bulk_ok(a.bv) ? 1 : 0;
-  if (env_int("PNEC_B200_NO_BULK", 0)) a.use_bulk = 0;
+  if (h->cfg.no_bulk) a.use_bulk = 0;
   switch (variant) {
     case PNEC_VARIANT_NEC: return launch_eval_v<PNEC_VARIANT_NEC>(h, a, max_n, stream);
     case PNEC_VARIANT_TARGET: return launch_eval_v<PNEC_VARIANT_TARGET>(h, a, max_n, stream);
@@ -704,7 +783,7 @@ int run_scf(pnec_handle *h, const BatchView &bv, long long max_n, double reg, in
   a.prev_poses = prev_poses;
   a.dbg = nullptr;
   static long long *dbg_buf = nullptr;
-  const bool debug = env_int("PNEC_B200_SCF_DEBUG", 0) != 0;
+  const bool debug = h->cfg.scf_debug != 0;
   if (debug) {
     if (!dbg_buf) cudaMalloc(&dbg_buf, sizeof(long long) * 4 * 1000000);
     if (bv.num_problems <= 1000000) a.dbg = dbg_buf;
@@ -712,10 +791,10 @@ int run_scf(pnec_handle *h, const BatchView &bv, long long max_n, double reg, in
   // warps per pair in pass 1: 4 while several pairs fit an SM; large pairs leave room for one or
   // two CTAs per SM only, which then get more warps (the scan parallelises over them; the sums
   // that depend on the thread split stay on 4 warps, so the result does not change)
-  int nw = env_int("PNEC_B200_SCF_WARPS", 0);
+  int nw = h->cfg.scf_warps;
   if (nw == 0) nw = dyn > 110 * 1024 ? 16 : dyn > 72 * 1024 ? 8 : 4;
   if (nw != 1 && nw != 2 && nw != 8 && nw != 16) nw = 4;
-  const int defer = env_int("PNEC_B200_SCF_DEFER", 48);  // survivors above which a pair goes to pass 2; 0 = one pass
+  const int defer = h->cfg.scf_defer;  // survivors above which a pair goes to pass 2; 0 = one pass
   int *d_defer = defer_buf;
   if (defer > 0) {
     if (!d_defer) {
@@ -784,7 +863,7 @@ int run_es_moments(pnec_handle *h, const BatchView &bv, bool weighted, double re
   a.bv = bv;
   a.reg = reg;
   a.out = d_mom;
-  if (bulk_ok(bv) && !env_int("PNEC_B200_NO_BULK", 0)) {
+  if (bulk_ok(bv) && !h->cfg.no_bulk) {
     // persistent warp-private rings (TMA), 4 warps x 3 stages, 3 CTAs per SM
     constexpr int WPC = 4, S = 3, MINB = 3;
     const long long want = (bv.num_problems + WPC - 1) / WPC;
@@ -871,7 +950,7 @@ int run_ransac(pnec_handle *h, const BatchView &bv, const pnec_frame_opts &o, lo
   a.lm = EsLmParams{0.00005, 1.0e1 * DBL_EPSILON, 0.0, 100.0, 100};
   // One CTA per pair.  Many pairs: one warp each (8 hypotheses per round; the machine is filled by
   // the pairs).  Few pairs: more warps, i.e. more hypotheses per round and a faster scoring pass.
-  int nw = env_int("PNEC_B200_RANSAC_WARPS", 0);
+  int nw = h->cfg.ransac_warps;
   if (nw == 0) nw = bv.num_problems >= 4LL * h->sm_count ? 1 : 4;
   const unsigned grid = static_cast<unsigned>(bv.num_problems);
   if (nw == 1) ransac_kernel<1><<<grid, 32, 0, stream>>>(a);
@@ -952,6 +1031,8 @@ int pnec_create(int device, pnec_handle **out) {
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
   h->smem_optin = prop.sharedMemPerBlockOptin;
+  h->cfg.load();
+  h->stager.copy_threads = h->cfg.copy_threads;
   *out = h;
   return PNEC_OK;
 }
@@ -979,6 +1060,7 @@ void pnec_destroy(pnec_handle *h) {
   for (cudaEvent_t ev : h->ev_stage)
     if (ev) cudaEventDestroy(ev);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_last) cudaEventDestroy(h->ev_last);
   delete h;
 }
 
@@ -995,6 +1077,7 @@ int pnec_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_solver_
   std::lock_guard<std::mutex> lock(h->mu);
   PNEC_CUDA(cudaSetDevice(h->device));
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  CallScope scope(h, stream);
   Staged st;
   const bool host = batch->memspace == PNEC_MEM_HOST;
   // HOST batches of some size are cut into chunks, each on its own stream: H2D of chunk k + 1 runs
@@ -1002,7 +1085,7 @@ int pnec_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_solver_
   int chunks = 1;
   if (host) {
     const long long total = batch->offsets ? batch->offsets[B] : B * batch->n_per_problem;
-    chunks = env_int("PNEC_B200_H2D_CHUNKS", 0);
+    chunks = h->cfg.h2d_chunks;
     if (chunks <= 0) chunks = (total * bytes_per_corr(opts->variant) >= (64ll << 20) && B >= 64) ? 4 : 1;
     chunks = static_cast<int>(std::min<long long>(std::min(chunks, pnec_handle::kMaxChunks), B));
   }
@@ -1030,6 +1113,7 @@ int pnec_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_solver_
   double *d_init = out->initial_cost ? static_cast<double *>(h->d_out_init.p) : nullptr;
   if (!h->ev_fork) PNEC_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   PNEC_CUDA(cudaEventRecord(h->ev_fork, stream));  // after the copy of the offsets
+  scope.forked = true;
   for (int c = 0; c < chunks; ++c) {
     if (!h->side[c]) PNEC_CUDA(cudaStreamCreateWithFlags(&h->side[c], cudaStreamNonBlocking));
     if (!h->ev_join[c]) PNEC_CUDA(cudaEventCreateWithFlags(&h->ev_join[c], cudaEventDisableTiming));
@@ -1067,6 +1151,7 @@ int pnec_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_solver_
   }
   for (int c = 0; c < chunks; ++c) PNEC_CUDA(cudaStreamWaitEvent(stream, h->ev_join[c], 0));
   PNEC_CUDA(cudaStreamSynchronize(stream));
+  scope.ok = true;
   return PNEC_OK;
 }
 
@@ -1080,6 +1165,7 @@ int pnec_eval_batch(pnec_handle *h, const pnec_batch *batch, int32_t variant,
   std::lock_guard<std::mutex> lock(h->mu);
   PNEC_CUDA(cudaSetDevice(h->device));
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  CallScope scope(h, stream);
   Staged st;
   rc = stage_batch(h, batch, variant, stream, &st);
   if (rc != PNEC_OK) return rc;
@@ -1126,6 +1212,7 @@ int pnec_cost_function_batch(pnec_handle *h, const pnec_batch *batch, double *ou
   std::lock_guard<std::mutex> lock(h->mu);
   PNEC_CUDA(cudaSetDevice(h->device));
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  CallScope scope(h, stream);
   Staged st;
   rc = stage_batch(h, batch, PNEC_VARIANT_TARGET, stream, &st);
   if (rc != PNEC_OK) return rc;
@@ -1162,6 +1249,7 @@ int pnec_unscented_transform_batch(pnec_handle *h, int64_t n, int32_t memspace, 
   std::lock_guard<std::mutex> lock(h->mu);
   PNEC_CUDA(cudaSetDevice(h->device));
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  CallScope scope(h, stream);
   UtArgs a{};
   a.n = n;
   a.kappa = kappa;
@@ -1182,7 +1270,7 @@ int pnec_unscented_transform_batch(pnec_handle *h, int64_t n, int32_t memspace, 
     a.covs = covs;
     a.out = out_covs;
   }
-  a.use_bulk = (aligned16(a.mus) && aligned16(a.covs) && aligned16(a.out) && !env_int("PNEC_B200_NO_BULK", 0)) ? 1 : 0;
+  a.use_bulk = (aligned16(a.mus) && aligned16(a.covs) && aligned16(a.out) && !h->cfg.no_bulk) ? 1 : 0;
   unscented_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, stream>>>(a);
   PNEC_CUDA(cudaGetLastError());
   h->launches++;
@@ -1206,6 +1294,7 @@ int pnec_keypoints_unproject_batch(pnec_handle *h, int64_t n, int32_t memspace, 
   std::lock_guard<std::mutex> lock(h->mu);
   PNEC_CUDA(cudaSetDevice(h->device));
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  CallScope scope(h, stream);
   KpArgs a{};
   a.n = n;
   for (int k = 0; k < 9; ++k) a.Kinv[k] = K_inv[k];
@@ -1228,7 +1317,7 @@ int pnec_keypoints_unproject_batch(pnec_handle *h, int64_t n, int32_t memspace, 
     a.out_covs = out_covs;
   }
   a.use_bulk = (aligned16(a.points) && aligned16(a.covs2) && aligned16(a.out_bvs) &&
-                aligned16(a.out_covs) && !env_int("PNEC_B200_NO_BULK", 0)) ? 1 : 0;
+                aligned16(a.out_covs) && !h->cfg.no_bulk) ? 1 : 0;
   keypoint_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, stream>>>(a);
   PNEC_CUDA(cudaGetLastError());
   h->launches++;
@@ -1253,6 +1342,7 @@ int pnec_scf_translation_batch(pnec_handle *h, const pnec_batch *batch, double r
   std::lock_guard<std::mutex> lock(h->mu);
   PNEC_CUDA(cudaSetDevice(h->device));
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  CallScope scope(h, stream);
   Staged st;
   rc = stage_batch(h, batch, PNEC_VARIANT_TARGET, stream, &st);
   if (rc != PNEC_OK) return rc;
@@ -1288,6 +1378,7 @@ int pnec_nec_translation_batch(pnec_handle *h, const pnec_batch *batch, double *
   std::lock_guard<std::mutex> lock(h->mu);
   PNEC_CUDA(cudaSetDevice(h->device));
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  CallScope scope(h, stream);
   Staged st;
   rc = stage_batch(h, batch, PNEC_VARIANT_NEC, stream, &st);
   if (rc != PNEC_OK) return rc;
@@ -1323,6 +1414,7 @@ int pnec_eigensolver_batch(pnec_handle *h, const pnec_batch *batch, const double
   std::lock_guard<std::mutex> lock(h->mu);
   PNEC_CUDA(cudaSetDevice(h->device));
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  CallScope scope(h, stream);
   Staged st;
   rc = stage_batch(h, batch, variant, stream, &st);
   if (rc != PNEC_OK) return rc;
@@ -1393,6 +1485,7 @@ int pnec_ransac_batch(pnec_handle *h, const pnec_batch *batch, const pnec_frame_
   std::lock_guard<std::mutex> lock(h->mu);
   PNEC_CUDA(cudaSetDevice(h->device));
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  CallScope scope(h, stream);
   Staged st;
   rc = stage_batch(h, batch, PNEC_VARIANT_NEC, stream, &st);
   if (rc != PNEC_OK) return rc;
@@ -1451,6 +1544,7 @@ int pnec_frame_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_f
   std::lock_guard<std::mutex> lock(h->mu);
   PNEC_CUDA(cudaSetDevice(h->device));
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  CallScope scope(h, stream);
   Staged st;
   rc = stage_batch(h, batch, variant, stream, &st);
   if (rc != PNEC_OK) return rc;
@@ -1466,9 +1560,9 @@ int pnec_frame_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_f
   const int weighted_rounds = weighted ? opts->weighted_iterations - 1 : 0;
   if (weighted) PNEC_CUDA(h->d_fr_rounds.ensure(nb * 56 * static_cast<size_t>(weighted_rounds)));
   double *const d_rounds = static_cast<double *>(h->d_fr_rounds.p);
-  const bool lm_ahead = weighted_rounds <= pnec_handle::kMaxRounds && !env_int("PNEC_B200_NO_LM_AHEAD", 0);
+  const bool lm_ahead = weighted_rounds <= pnec_handle::kMaxRounds && !h->cfg.no_lm_ahead;
   // small batches: one launch for all weighted rounds of a pair (the per-round launches would dominate)
-  const bool fused_rounds = weighted && B <= env_int("PNEC_B200_FUSED_ROUNDS_MAX_PAIRS", 512);
+  const bool fused_rounds = weighted && B <= h->cfg.fused_rounds_max_pairs;
   if (weighted) {
     rc = ensure_sphere(h, opts->fibonacci_samples);
     if (rc != PNEC_OK) return rc;
@@ -1515,8 +1609,9 @@ int pnec_frame_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_f
   ScfScanCache *const d_cache = static_cast<ScfScanCache *>(h->d_fr_cache.p);
   int *const d_qsame = static_cast<int *>(h->d_fr_flags.p), *const d_fixed = d_qsame + B;
   int *const d_defer = static_cast<int *>(h->d_fr_defer.p);
-  const bool shortcuts = !env_int("PNEC_B200_NO_FRAME_SHORTCUTS", 0);
+  const bool shortcuts = !h->cfg.no_frame_shortcuts;
   const bool timed = out->stage_ms != nullptr;
+  scope.forked = true;  // chunks and the rotation chain run on the handle's side streams
   if (timed)
     for (cudaEvent_t &ev : h->ev_stage)
       if (!ev) PNEC_CUDA(cudaEventCreate(&ev));
@@ -1676,7 +1771,7 @@ int pnec_frame_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_f
   // Frame pairs are independent and every stage ends in a tail (a few pairs need 100 function
   // evaluations, or a sphere scan that cannot prune): the batch is cut into chunks that run their
   // stages on separate streams, so one chunk's tail is filled with another chunk's work.
-  int chunks = env_int("PNEC_B200_FRAME_CHUNKS", 0);
+  int chunks = h->cfg.frame_chunks;
   if (chunks <= 0) chunks = B >= 4096 ? 4 : (B >= 1024 ? 2 : 1);
   chunks = std::min<long long>(std::min(chunks, pnec_handle::kMaxChunks), B);
   if (fused_rounds) chunks = 1;  // the fused kernel lays its round poses out for one chunk
@@ -1727,6 +1822,7 @@ int pnec_frame_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_f
     PNEC_CUDA(cudaEventSynchronize(h->ev_stage[3]));
     for (int k = 0; k < 3; ++k) PNEC_CUDA(cudaEventElapsedTime(&out->stage_ms[k], h->ev_stage[k], h->ev_stage[k + 1]));
   }
+  scope.ok = true;
   return PNEC_OK;
 }
 

@@ -8,6 +8,8 @@
 // or (N,3)/(N,3,3) ndarrays.  Batched extensions: pyceres_batch / pyceresnec_batch /
 // pyceres_target_batch.  The KLT / demo helpers of the reference module (add, mat2,
 // matrices, cppimg, KLTMatching, KLTImageMatching) are image-side and out of scope.
+#include <algorithm>
+#include <cstdint>
 #include <pybind11/numpy.h>
 #include <pybind11/pybind11.h>
 
@@ -124,11 +126,13 @@ py::array_t<double> pyceresnec(const py::object &host_bvs, const py::object &tar
   return matrix_from_pose(optimizer.Result());
 }
 
-// Addition to the reference's module: the whole frame solve, PNEC::Solve with use_ransac_ = false
-// (src/rel_pose_estimation/pnec.cc:77-124), with the Options fields it reads as keyword arguments.
-py::array_t<double> pysolve(const py::object &host_bvs, const py::object &target_bvs,
-                            const py::object &target_covariances, const py::object &init_pose,
-                            double regularization, int weighted_iterations, bool use_nec, bool use_ceres) {
+// Addition to the reference's module: the whole frame solve, PNEC::Solve
+// (src/rel_pose_estimation/pnec.cc:77-124), with the Options fields it reads as keyword arguments
+// (defaults as pnec_config.h:46-65, RANSAC included).  Returns (pose 4x4, inlier indices).
+py::tuple pysolve_inliers(const py::object &host_bvs, const py::object &target_bvs,
+                          const py::object &target_covariances, const py::object &init_pose, double regularization,
+                          int weighted_iterations, bool use_nec, bool use_ceres, bool use_ransac,
+                          int max_ransac_iterations, int ransac_sample_size, std::uint64_t ransac_seed) {
   arr f1 = as_vectors(host_bvs, "host_bvs"), f2 = as_vectors(target_bvs, "target_bvs");
   const py::ssize_t n = f1.shape(0);
   if (f2.shape(0) != n) throw std::invalid_argument("host_bvs and target_bvs differ in length");
@@ -136,7 +140,10 @@ py::array_t<double> pysolve(const py::object &host_bvs, const py::object &target
   std::vector<double> c2 = as_covariances(target_covariances, n, "target_covariances");
   const pnec::SE3 sp_init_pose = pose_from_matrix(init_pose);
   pnec::rel_pose_estimation::Options options;
-  options.use_ransac_ = false;
+  options.use_ransac_ = use_ransac;
+  options.max_ransac_iterations_ = max_ransac_iterations;
+  options.ransac_sample_size_ = ransac_sample_size;
+  options.ransac_seed_ = ransac_seed;
   options.use_nec_ = use_nec;
   options.use_ceres_ = use_ceres;
   options.weighted_iterations_ = static_cast<std::size_t>(weighted_iterations);
@@ -146,11 +153,24 @@ py::array_t<double> pysolve(const py::object &host_bvs, const py::object &target
   Span3 s2{reinterpret_cast<const pnec::Vec3 *>(f2.data()), static_cast<size_t>(n)};
   Span9 m2{reinterpret_cast<const pnec::Mat3 *>(c2.data()), static_cast<size_t>(n)};
   pnec::SE3 result;
+  std::vector<int> inliers;
   {
     py::gil_scoped_release release;
-    result = solver.Solve(s1, s2, m2, sp_init_pose);
+    result = solver.Solve(s1, s2, m2, sp_init_pose, inliers);
   }
-  return matrix_from_pose(result);
+  py::array_t<int> idx(static_cast<py::ssize_t>(inliers.size()));
+  std::copy(inliers.begin(), inliers.end(), idx.mutable_data());
+  return py::make_tuple(matrix_from_pose(result), idx);
+}
+
+py::array_t<double> pysolve(const py::object &host_bvs, const py::object &target_bvs,
+                            const py::object &target_covariances, const py::object &init_pose,
+                            double regularization, int weighted_iterations, bool use_nec, bool use_ceres,
+                            bool use_ransac, int max_ransac_iterations, int ransac_sample_size,
+                            std::uint64_t ransac_seed) {
+  return pysolve_inliers(host_bvs, target_bvs, target_covariances, init_pose, regularization, weighted_iterations,
+                         use_nec, use_ceres, use_ransac, max_ransac_iterations, ransac_sample_size, ransac_seed)[0]
+      .cast<py::array_t<double>>();
 }
 
 // Batched: bvs (B,N,3), covariances (B,N,3,3) or None, init_poses (B,4,4) -> (B,4,4)
@@ -228,8 +248,14 @@ PYBIND11_MODULE(pypnec, m) {
         "ceres nec");
   m.def("pysolve", &pysolve, py::arg("host_bvs"), py::arg("target_bvs"), py::arg("target_covariances"),
         py::arg("init_pose"), py::arg("regularization") = 1.0e-13, py::arg("weighted_iterations") = 10,
-        py::arg("use_nec") = false, py::arg("use_ceres") = true,
-        "PNEC::Solve without RANSAC: NEC eigensolver, weighted eigensolver + SCF, refinement");
+        py::arg("use_nec") = false, py::arg("use_ceres") = true, py::arg("use_ransac") = true,
+        py::arg("max_ransac_iterations") = 5000, py::arg("ransac_sample_size") = 10, py::arg("ransac_seed") = 1,
+        "PNEC::Solve: (RANSAC over the) NEC eigensolver, weighted eigensolver + SCF, refinement");
+  m.def("pysolve_inliers", &pysolve_inliers, py::arg("host_bvs"), py::arg("target_bvs"),
+        py::arg("target_covariances"), py::arg("init_pose"), py::arg("regularization") = 1.0e-13,
+        py::arg("weighted_iterations") = 10, py::arg("use_nec") = false, py::arg("use_ceres") = true,
+        py::arg("use_ransac") = true, py::arg("max_ransac_iterations") = 5000, py::arg("ransac_sample_size") = 10,
+        py::arg("ransac_seed") = 1, "PNEC::Solve -> (pose, inliers)");
   m.def("pyceres_batch",
         [](const py::object &a, const py::object &b, const py::object &c, const py::object &d,
            const py::object &e, double reg) { return solve_batch(PNEC_VARIANT_SYMMETRIC, a, b, c, d, e, reg); },

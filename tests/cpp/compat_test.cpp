@@ -3,6 +3,7 @@
 // cov_h[n*9], init pose7.  Output (text): one line per API with 7 pose numbers + status + iters.
 #include <cstdio>
 #include <cstdlib>
+#include <thread>
 #include <vector>
 
 #include "pnec/pnec_compat.hpp"
@@ -63,14 +64,41 @@ int main(int argc, char **argv) {
     full.use_nec_ = true;
     pnec::rel_pose_estimation::PNEC nec(full);
     print_pose("SolveNEC", nec.Solve(bvs1, bvs2, covs_t, init), nec.LastStatus(), nec.LastIterations());
-    bool threw = false;
-    try {
-      pnec::rel_pose_estimation::PNEC ransac((pnec::rel_pose_estimation::Options()));
-      ransac.Solve(bvs1, bvs2, covs_t, init);
-    } catch (const std::logic_error &) {
-      threw = true;
-    }
-    std::printf("RansacThrows %d\n", threw ? 1 : 0);
+  }
+  {
+    // the reference's DEFAULT options (use_ransac_ = true, pnec_config.h:58), as run_simulation's
+    // PNEC() uses them (src/run_simulation.cc:74-86), incl. the timed overload (pnec.cc:135-208)
+    pnec::rel_pose_estimation::PNEC solver((pnec::rel_pose_estimation::Options()));
+    std::vector<int> inliers(3, 7);
+    SE3 r = solver.Solve(bvs1, bvs2, covs_t, init, inliers);
+    print_pose("SolveDefault", r, solver.LastStatus(), (int)inliers.size());
+    print_pose("SolveDefaultES", solver.LastEigensolverPose(), 0, 0);
+    std::printf("SolveDefaultInliers");
+    for (int i : inliers) std::printf(" %d", i);
+    std::printf("\n");
+    pnec::common::FrameTiming timing(0);
+    std::vector<int> inliers2;
+    SE3 r2 = solver.Solve(bvs1, bvs2, covs_t, init, inliers2, timing);
+    const double *ms = solver.LastStageMilliseconds();
+    std::printf("SolveTimed %d %d %.6f %.6f %.6f %lld\n", (int)(r2.q.c[0] == r.q.c[0] && r2.t[2] == r.t[2]),
+                (int)(inliers2 == inliers), ms[0], ms[1], ms[2],
+                (long long)(timing.nec_es_.count() + timing.it_es_.count() + timing.ceres_.count()));
+    std::vector<int> es_inliers;
+    SE3 es = solver.Eigensolver(bvs1, bvs2, init, es_inliers);
+    print_pose("EigensolverRansac", es, 0, (int)es_inliers.size());
+    // re-entrancy: concurrent callers (one handle per thread) get the sequential results
+    SE3 t_out[4];
+    std::vector<std::thread> threads;
+    for (int k = 0; k < 4; ++k)
+      threads.emplace_back([&, k] {
+        pnec::rel_pose_estimation::PNEC local((pnec::rel_pose_estimation::Options()));
+        for (int rep = 0; rep < 3; ++rep) t_out[k] = local.Solve(bvs1, bvs2, covs_t, init);
+      });
+    for (auto &t : threads) t.join();
+    int same = 0;
+    for (int k = 0; k < 4; ++k)
+      same += (int)(t_out[k].q.c[0] == r.q.c[0] && t_out[k].q.c[3] == r.q.c[3] && t_out[k].t[1] == r.t[1]);
+    std::printf("Threads %d\n", same);
   }
 
   // lower level: include/optimization/pnec_ceres.h:50-81
@@ -95,13 +123,5 @@ int main(int argc, char **argv) {
                 (int)(one(0, 0) == proj[1](0, 0)));
   }
 
-  // unsupported orchestration must throw, not silently do something else
-  pnec::rel_pose_estimation::PNEC full((pnec::rel_pose_estimation::Options()));
-  try {
-    full.Solve(bvs1, bvs2, covs_t, init);
-    std::printf("SolveDefaultOptions no-throw\n");
-  } catch (const std::logic_error &) {
-    std::printf("SolveDefaultOptions throws\n");
-  }
   return 0;
 }

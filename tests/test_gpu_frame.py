@@ -211,21 +211,17 @@ def test_frame_stages_match_committed_fixtures(handle, golden_frame, name):
         assert r <= ROT_TOL and t <= DIR_TOL, (cname, "es", r, t)
 
 
-def test_frame_solve_shortcuts_are_exact(handle):
-    """The scan cache / fixed-point skipping / two-pass launch must not change a single bit."""
-    import os
-
+def test_frame_solve_shortcuts_are_exact(handle, monkeypatch):
+    """The scan cache / fixed-point skipping / two-pass launch must not change a single bit (small
+    batch: the fused rounds kernel; the per-round kernels at bench sizes are covered by
+    test_gpu_parity_large.py).  The switches are read when a handle is created."""
     n, B = 160, 64
     batch = syn.make_batch(B, n, seed=80)
     args = (batch.bvs_host, batch.bvs_target, batch.covs_target, batch.init_poses)
     fast = handle.frame_solve_batch(*args, api.default_frame_opts(use_ransac=0), n_per_problem=n)
-    os.environ["PNEC_B200_NO_FRAME_SHORTCUTS"] = "1"
-    os.environ["PNEC_B200_SCF_DEFER"] = "0"
-    try:
-        plain = handle.frame_solve_batch(*args, api.default_frame_opts(use_ransac=0), n_per_problem=n)
-    finally:
-        del os.environ["PNEC_B200_NO_FRAME_SHORTCUTS"]
-        del os.environ["PNEC_B200_SCF_DEFER"]
+    monkeypatch.setenv("PNEC_B200_NO_FRAME_SHORTCUTS", "1")
+    monkeypatch.setenv("PNEC_B200_SCF_DEFER", "0")
+    plain = api.Handle(0).frame_solve_batch(*args, api.default_frame_opts(use_ransac=0), n_per_problem=n)
     np.testing.assert_array_equal(fast.poses, plain.poses)
     np.testing.assert_array_equal(fast.iterations, plain.iterations)
 
@@ -303,8 +299,8 @@ def test_fused_rounds_kernel_matches_per_round_kernels(handle, monkeypatch):
     args = (batch.bvs_host, batch.bvs_target, batch.covs_target, batch.init_poses)
     for kw in (dict(), dict(weighted_iterations=2), dict(use_ceres=0)):
         monkeypatch.setenv("PNEC_B200_FUSED_ROUNDS_MAX_PAIRS", "512")
-        fused = handle.frame_solve_batch(*args, api.default_frame_opts(use_ransac=0, **kw), offsets=batch.offsets)
+        fused = api.Handle(0).frame_solve_batch(*args, api.default_frame_opts(use_ransac=0, **kw), offsets=batch.offsets)
         monkeypatch.setenv("PNEC_B200_FUSED_ROUNDS_MAX_PAIRS", "0")
-        rounds = handle.frame_solve_batch(*args, api.default_frame_opts(use_ransac=0, **kw), offsets=batch.offsets)
-        np.testing.assert_allclose(fused.poses, rounds.poses, rtol=0, atol=1e-13)
+        rounds = api.Handle(0).frame_solve_batch(*args, api.default_frame_opts(use_ransac=0, **kw), offsets=batch.offsets)
+        np.testing.assert_allclose(fused.poses, rounds.poses, rtol=0, atol=1e-13)  # (rotation LM: two instantiations)
         np.testing.assert_array_equal(fused.es_poses, rounds.es_poses)

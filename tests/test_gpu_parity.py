@@ -128,6 +128,7 @@ def test_ragged_batch_with_edge_sizes(handle, path, monkeypatch):
     counts = np.array([0, 1, 2, 3, 5, 0, 31, 32, 33, 63, 64, 65, 127, 128, 129, 255, 257, 511, 513,
                        1000, 1023, 1887, 1889, 1890, 1891, 2500, 0, 77, 4100, 6])
     monkeypatch.setenv("PNEC_B200_STREAM_MIN_N", "896" if path == "stream" else "100000000")
+    handle = api.Handle(0)  # the switches are read when a handle is created
     B = len(counts)
     b = syn.make_batch(B, 0, seed=77, counts=counts)
     res = handle.solve_batch(dev(b.bvs_host), dev(b.bvs_target), dev(b.covs_target), None,
@@ -183,10 +184,11 @@ def test_chunked_host_path_agrees_bitwise(handle, monkeypatch, ragged, chunks):
     b = syn.make_batch(B, 40, seed=17, counts=counts)
     o = api.default_opts(api.TARGET)
     kw = dict(offsets=b.offsets) if ragged else dict(n_per_problem=40)
+    # (the switches are read when a handle is created)
     monkeypatch.setenv("PNEC_B200_H2D_CHUNKS", "1")
-    one = handle.solve_batch(b.bvs_host, b.bvs_target, b.covs_target, None, b.init_poses, o, **kw)
+    one = api.Handle(0).solve_batch(b.bvs_host, b.bvs_target, b.covs_target, None, b.init_poses, o, **kw)
     monkeypatch.setenv("PNEC_B200_H2D_CHUNKS", str(chunks))
-    cut = handle.solve_batch(b.bvs_host, b.bvs_target, b.covs_target, None, b.init_poses, o, **kw)
+    cut = api.Handle(0).solve_batch(b.bvs_host, b.bvs_target, b.covs_target, None, b.init_poses, o, **kw)
     for name in ("poses", "status", "iterations", "cost", "initial_cost"):
         assert np.array_equal(getattr(one, name), getattr(cut, name)), name
 
@@ -201,7 +203,7 @@ def test_pageable_host_batch_through_the_staging_ring(handle, monkeypatch):
                               n_per_problem=N)
     host = handle.solve_batch(b.bvs_host, b.bvs_target, b.covs_target, None, b.init_poses, o, n_per_problem=N)
     monkeypatch.setenv("PNEC_B200_NO_STAGER", "1")
-    plain = handle.solve_batch(b.bvs_host, b.bvs_target, b.covs_target, None, b.init_poses, o, n_per_problem=N)
+    plain = api.Handle(0).solve_batch(b.bvs_host, b.bvs_target, b.covs_target, None, b.init_poses, o, n_per_problem=N)
     for r in (host, plain):
         assert np.array_equal(r.poses, devr.poses.cpu().numpy())
         assert np.array_equal(r.iterations, devr.iterations.cpu().numpy())
@@ -480,11 +482,17 @@ def test_pypnec_module_matches_oracle():
     assert rotation_angle(gott, reft) <= ROT_TOL and direction_angle(gott[4:], reft[4:]) <= DIR_TOL
     with pytest.raises(ValueError):
         pypnec.pyceresnec(f1, f2[:-1], init)
-    # addition: the whole frame solve (PNEC::Solve without RANSAC)
-    full = pypnec.pysolve(f1, f2, cov_t, init, 1e-13)
+    # addition: the whole frame solve (PNEC::Solve), without and with (the default) RANSAC
+    full = pypnec.pysolve(f1, f2, cov_t, init, 1e-13, use_ransac=False)
     fref, _ = oracle.frame_solve_batch(b.bvs_host, b.bvs_target, b.covs_target, b.init_poses,
                                        oracle.default_frame_opts(use_ransac=0), n_per_problem=N)
     gotf = np.concatenate([syn.matrix_to_quaternion(full[:3, :3]), full[:3, 3]])
+    assert rotation_angle(gotf, fref[0]) <= ROT_TOL and direction_angle(gotf[4:], fref[0][4:]) <= DIR_TOL
+    full, inl = pypnec.pysolve_inliers(f1, f2, cov_t, init)
+    fref, _, rmask, rni, _ = oracle.frame_solve_batch(b.bvs_host, b.bvs_target, b.covs_target, b.init_poses,
+                                                      oracle.default_frame_opts(), n_per_problem=N, return_ransac=True)
+    gotf = np.concatenate([syn.matrix_to_quaternion(full[:3, :3]), full[:3, 3]])
+    assert np.array_equal(inl, np.nonzero(rmask)[0]) and len(inl) == rni[0]
     assert rotation_angle(gotf, fref[0]) <= ROT_TOL and direction_angle(gotf[4:], fref[0][4:]) <= DIR_TOL
 
 
@@ -492,7 +500,7 @@ def test_cpp_compat_api_matches_oracle(tmp_path):
     """The reference's C++ call shapes (PNEC::CeresSolver & co) through pnec_compat.hpp."""
     exe = tmp_path / "compat_test"
     lib = os.path.join(ROOT, "pnec_b200", "lib")
-    subprocess.run(["/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++", "-std=c++17", "-O1",
+    subprocess.run(["/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++", "-std=c++17", "-O1", "-pthread",
                     "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "compat_test.cpp"),
                     "-o", str(exe), "-L", lib, "-lpnec_b200", f"-Wl,-rpath,{lib}"], check=True)
     N = 120
@@ -521,8 +529,18 @@ def test_cpp_compat_api_matches_oracle(tmp_path):
     check("PNECCeresSymmetric", oracle.SYMMETRIC, 1e-13, b.covs_target, b.covs_host)
     assert float(lines["CostFunction"][0]) == pytest.approx(
         oracle.cost_function(b.bvs_host, b.bvs_target, b.covs_target, p), rel=1e-10)
-    assert lines["SolveDefaultOptions"] == ["throws"]
-    assert lines["RansacThrows"] == ["1"]
+    # PNEC(Options()) -- RANSAC on, the reference's default (pnec_config.h:58; run_simulation.cc:74-86)
+    dref, des, rmask, rni, _ = oracle.frame_solve_batch(b.bvs_host, b.bvs_target, b.covs_target, b.init_poses,
+                                                        oracle.default_frame_opts(), n_per_problem=N, return_ransac=True)
+    for tag, ref in (("SolveDefault", dref[0]), ("SolveDefaultES", des[0]), ("EigensolverRansac", des[0])):
+        pose = np.array(lines[tag][:7], dtype=np.float64)
+        assert rotation_angle(pose, ref) <= ROT_TOL and direction_angle(pose[4:], ref[4:]) <= DIR_TOL, tag
+    assert int(lines["SolveDefault"][8]) == rni[0] == int(lines["EigensolverRansac"][8])
+    assert [int(v) for v in lines["SolveDefaultInliers"]] == list(np.nonzero(rmask)[0])
+    same_pose, same_inliers, ms0, ms1, ms2, total_ms = lines["SolveTimed"]
+    assert same_pose == "1" and same_inliers == "1"
+    assert float(ms0) > 0 and float(ms1) > 0 and float(ms2) > 0 and int(total_ms) <= float(ms0) + float(ms1) + float(ms2)
+    assert lines["Threads"] == ["4"]
     # the whole PNEC::Solve pipeline and its stages (pnec.cc:77-124, 273-348)
     fref, fes = oracle.frame_solve_batch(b.bvs_host, b.bvs_target, b.covs_target, b.init_poses,
                                          oracle.default_frame_opts(use_ransac=0), n_per_problem=N)
@@ -534,6 +552,18 @@ def test_cpp_compat_api_matches_oracle(tmp_path):
         pose = np.array(lines[tag][:7], dtype=np.float64)
         assert rotation_angle(pose, ref) <= ROT_TOL and direction_angle(pose[4:], ref[4:]) <= DIR_TOL, tag
     assert lines["SolveFull"][8] == "0"  # inliers cleared, pnec.cc:277
+    # the same call site written against Sophus::SE3d / Eigen containers (mock headers, tests/cpp/mock)
+    exe2 = tmp_path / "compat_interop"
+    subprocess.run(["/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++", "-std=c++17", "-O1",
+                    "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "tests", "cpp", "mock"),
+                    os.path.join(ROOT, "tests", "cpp", "compat_interop_test.cpp"),
+                    "-o", str(exe2), "-L", lib, "-lpnec_b200", f"-Wl,-rpath,{lib}"], check=True)
+    out2 = subprocess.run([str(exe2), str(blob)], check=True, capture_output=True, text=True).stdout
+    lines2 = {l.split()[0]: l.split()[1:] for l in out2.strip().splitlines()}
+    pose = np.array(lines2["SolveSophus"][:7], dtype=np.float64)
+    assert rotation_angle(pose, dref[0]) <= ROT_TOL and direction_angle(pose[4:], dref[0][4:]) <= DIR_TOL
+    assert int(lines2["SolveSophus"][8]) == rni[0]
+    assert lines2["CeresSolverSophus"][:7] == lines["CeresSolver"][:7]
     mu = b.bvs_target[1] * 800.0
     img = np.array([[0.7, 0.1, 0.0], [0.1, 0.4, 0.0], [0.0, 0.0, 0.0]])
     ut = oracle.unscented_transform(mu[None], img.T.reshape(1, 9), None, 1.0, oracle.PINHOLE)[0].reshape(3, 3).T

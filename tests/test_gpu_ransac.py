@@ -149,7 +149,8 @@ def test_ransac_separates_outliers_statistically(handle):
     assert (mask == mask2).mean() >= 0.98
     w = res.num_inliers / n
     k = np.log(0.01) / np.log(1 - w ** 10)
-    assert (res.ransac_iterations <= np.ceil(k) + 1).all()
+    # the loop runs until iterations >= k of the best model (longer only if that model was found late)
+    assert (res.ransac_iterations >= k - 1e-9).all() and np.median(res.ransac_iterations) <= np.median(np.ceil(k)) + 1
     err = np.array([rotation_angle(a, b) for a, b in zip(res.poses, batch.gt_poses)])
     err2 = np.array([rotation_angle(a, b) for a, b in zip(other.poses, batch.gt_poses)])
     err_plain = np.array([rotation_angle(a, b) for a, b in zip(plain.poses, batch.gt_poses)])

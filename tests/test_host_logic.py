@@ -198,3 +198,18 @@ def test_shard_arrays_rebases_offsets():
     assert np.array_equal(lf1, f1[2:9]) and np.array_equal(lposes, poses[1:3])
     lf1, lposes, loff = distributed.shard_arrays((2, 4), 5, None, np.arange(60.0).reshape(20, 3), poses=poses)
     assert loff is None and lf1.shape == (10, 3)
+
+
+def test_compat_header_compiles_against_sophus_style_call_sites(tmp_path):
+    """include/pnec/pnec_compat.hpp with the reference's own types at the call site (Sophus::SE3d,
+    std::vector<Eigen::Vector3d>): Eigen / Sophus are absent from the image, so minimal mock headers
+    (tests/cpp/mock) stand in for them; this only proves the interop overloads compile and link."""
+    import subprocess
+
+    lib = os.path.join(ROOT, "pnec_b200", "lib")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    for src, extra in (("compat_interop_test.cpp", ["-I", os.path.join(ROOT, "tests", "cpp", "mock")]),
+                       ("compat_test.cpp", ["-pthread"])):
+        subprocess.run([cxx, "-std=c++17", "-O0", "-Wall", "-I", os.path.join(ROOT, "include"), *extra,
+                        os.path.join(ROOT, "tests", "cpp", src), "-o", str(tmp_path / src.replace(".cpp", "")),
+                        "-L", lib, "-lpnec_b200", f"-Wl,-rpath,{lib}"], check=True)

@@ -53,21 +53,21 @@ run("C4 4540x~2000 ragged, max 20 it", b.bvs_host, b.bvs_target, b.covs_target, 
     api.default_opts(api.TARGET, max_num_iterations=20), offsets=b.offsets)
 # C5: correspondence-count sweep at 4096 problems
 for cfg in ("1", "2", "3", "4"):
-    os.environ["PNEC_B200_STREAM_CFG"] = cfg
+    os.environ["PNEC_B200_STREAM_CFG"] = cfg; h = api.Handle(0)  # switches are read at handle creation
     run(f"C4 stream cfg {cfg}", b.bvs_host, b.bvs_target, b.covs_target, b.init_poses,
         api.default_opts(api.TARGET, max_num_iterations=20), offsets=b.offsets)
-os.environ.pop("PNEC_B200_STREAM_CFG")
-os.environ["PNEC_B200_STREAM_MIN_N"] = "100000000"
+os.environ.pop("PNEC_B200_STREAM_CFG"); h = api.Handle(0)  # switches are read at handle creation
+os.environ["PNEC_B200_STREAM_MIN_N"] = "100000000"; h = api.Handle(0)  # switches are read at handle creation
 run("C4 resident/global path", b.bvs_host, b.bvs_target, b.covs_target, b.init_poses,
     api.default_opts(api.TARGET, max_num_iterations=20), offsets=b.offsets)
-os.environ.pop("PNEC_B200_STREAM_MIN_N")
+os.environ.pop("PNEC_B200_STREAM_MIN_N"); h = api.Handle(0)  # switches are read at handle creation
 for N in (64, 128, 256, 512, 768, 1024, 2048, 4096, 8192):
     base = syn.make_batch(128 if N <= 1024 else 32, N, seed=5)
     run(f"C5 4096x{N}", *tile_batch(base, 4096), opts, n_per_problem=N)
     if 512 <= N <= 2048:
-        os.environ["PNEC_B200_STREAM_MIN_N"] = "100000000" if N > 940 else "0"
+        os.environ["PNEC_B200_STREAM_MIN_N"] = "100000000" if N > 940 else "0"; h = api.Handle(0)  # switches are read at handle creation
         run(f"C5 4096x{N} other path ({'resident' if N > 940 else 'stream'})", *tile_batch(base, 4096), opts, n_per_problem=N)
-        os.environ.pop("PNEC_B200_STREAM_MIN_N")
+        os.environ.pop("PNEC_B200_STREAM_MIN_N"); h = api.Handle(0)  # switches are read at handle creation
 # unscented transform: one covariance per C2 correspondence
 n = 10000 * 512
 rng = np.random.default_rng(0)

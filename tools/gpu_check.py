@@ -72,7 +72,7 @@ if __name__ == "__main__":
         f1, f2, ct, init = T(b.bvs_host), T(b.bvs_target), T(b.covs_target), T(b.init_poses)
         opts = api.default_opts(api.TARGET)
         for cfg in ("11", "14", "17"):
-            os.environ["PNEC_B200_EVAL_CFG"] = cfg
+            os.environ["PNEC_B200_EVAL_CFG"] = cfg; h = api.Handle(0)  # switches are read at handle creation
             med, mn = timeit(lambda: h.eval_batch(f1, f2, ct, None, init, api.TARGET, 1e-13, n_per_problem=N))
             a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a_.record()
@@ -81,10 +81,10 @@ if __name__ == "__main__":
             print(f'   back-to-back: {loop:.4f} ms -> {B*N*120/loop/1e6:.1f} GB/s')
             print(f"eval cfg{cfg}: med {med:.4f} ms min {mn:.4f} ms -> {B*N*120/mn/1e6:.1f} GB/s", flush=True)
         for nw in ("2", "4", "8"):
-            os.environ["PNEC_B200_SOLVE_WARPS"] = nw
+            os.environ["PNEC_B200_SOLVE_WARPS"] = nw; h = api.Handle(0)  # switches are read at handle creation
             med, mn = timeit(lambda: h.solve_batch(f1, f2, ct, None, init, opts, n_per_problem=N))
             print(f"solve nw{nw}: med {med:.4f} ms min {mn:.4f} ms -> {B/med*1e3:.3e} solves/s", flush=True)
-        os.environ.pop("PNEC_B200_SOLVE_WARPS")
+        os.environ.pop("PNEC_B200_SOLVE_WARPS"); h = api.Handle(0)  # switches are read at handle creation
         res = h.solve_batch(f1, f2, ct, None, init, opts, n_per_problem=N); torch.cuda.synchronize()
         print("iters hist", np.bincount(res.iterations.cpu().numpy()), "status", np.bincount(res.status.cpu().numpy()), flush=True)
         t0 = time.time()

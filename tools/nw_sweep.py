@@ -21,14 +21,14 @@ for N, B in ((64, 16384), (128, 16384), (256, 12500), (384, 10000), (512, 10000)
     d = (f(base.bvs_host, N), f(base.bvs_target, N), f(base.covs_target, N), f(base.init_poses, 1))
     out = []
     for nw in (1, 2, 3, 4, 8):
-        os.environ["PNEC_B200_SOLVE_WARPS"] = str(nw)
-        os.environ["PNEC_B200_STREAM_MIN_N"] = "100000000"
+        os.environ["PNEC_B200_SOLVE_WARPS"] = str(nw); h = api.Handle(0)  # switches are read at handle creation
+        os.environ["PNEC_B200_STREAM_MIN_N"] = "100000000"; h = api.Handle(0)  # switches are read at handle creation
         try:
             ms = timeit(lambda: h.solve_batch(d[0], d[1], d[2], None, d[3], opts, n_per_problem=N))
             out.append(f"nw{nw}: {ms:.4f} ms ({B/ms/1e3:.1f}M/s)")
         except Exception as e:
             out.append(f"nw{nw}: fail")
-    os.environ.pop("PNEC_B200_SOLVE_WARPS"); os.environ["PNEC_B200_STREAM_MIN_N"] = "0"
+    os.environ.pop("PNEC_B200_SOLVE_WARPS"); os.environ["PNEC_B200_STREAM_MIN_N"] = "0"; h = api.Handle(0)  # switches are read at handle creation
     ms = timeit(lambda: h.solve_batch(d[0], d[1], d[2], None, d[3], opts, n_per_problem=N))
     out.append(f"stream: {ms:.4f}")
     print(f"N={N:5d} B={B:6d}  " + "  ".join(out), flush=True)

@@ -11,7 +11,7 @@ T = lambda a: torch.from_numpy(np.ascontiguousarray(np.tile(a, (rep, 1))[: (B * 
 f1, f2, ct, init = T(base.bvs_host), T(base.bvs_target), T(base.covs_target), T(base.init_poses)
 h = api.Handle(0)
 opts = api.default_opts(api.TARGET)
-os.environ["PNEC_B200_DUMP_TIMING"] = "1"
+os.environ["PNEC_B200_DUMP_TIMING"] = "1"; h = api.Handle(0)  # switches are read at handle creation
 for i in range(3):
     h.solve_batch(f1, f2, ct, None, init, opts, n_per_problem=N)
     torch.cuda.synchronize()

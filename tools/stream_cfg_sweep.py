@@ -19,10 +19,10 @@ for N, B in ((256, 12500), (512, 10000), (768, 8192), (1024, 4096), (2048, 4096)
     f = lambda a, per: T(np.tile(a, (rep, 1))[: B * per])
     d = (f(base.bvs_host, N), f(base.bvs_target, N), f(base.covs_target, N), f(base.init_poses, 1))
     out = []
-    os.environ["PNEC_B200_STREAM_MIN_N"] = "100000000"
+    os.environ["PNEC_B200_STREAM_MIN_N"] = "100000000"; h = api.Handle(0)  # switches are read at handle creation
     ms = timeit(lambda: h.solve_batch(d[0], d[1], d[2], None, d[3], opts, n_per_problem=N)); out.append(f"resident {ms:.4f}")
-    os.environ["PNEC_B200_STREAM_MIN_N"] = "0"
+    os.environ["PNEC_B200_STREAM_MIN_N"] = "0"; h = api.Handle(0)  # switches are read at handle creation
     for cfg in ("3", "5", "6", "7", "8"):
-        os.environ["PNEC_B200_STREAM_CFG"] = cfg
+        os.environ["PNEC_B200_STREAM_CFG"] = cfg; h = api.Handle(0)  # switches are read at handle creation
         ms = timeit(lambda: h.solve_batch(d[0], d[1], d[2], None, d[3], opts, n_per_problem=N)); out.append(f"cfg{cfg} {ms:.4f}")
     print(f"N={N} B={B}: " + "  ".join(out), flush=True)
