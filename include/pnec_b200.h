@@ -338,6 +338,57 @@ int pnec_ransac_batch(pnec_handle *h, const pnec_batch *batch, const pnec_frame_
 int pnec_frame_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_frame_opts *opts,
                            const pnec_frame_out *out, void *cuda_stream);
 
+/* ---- Solver inputs from keypoints: the frame-level boundary.
+ *
+ * In the reference the solver's inputs are assembled per frame pair by Frame2Frame::GetFeatures
+ * (src/rel_pose_estimation/frame2frame.cc:359-392) from the matched keypoints of the two frames,
+ * whose bearing vector and 3x3 covariance were derived at construction from the pixel position
+ * and the 2x2 image covariance (KeyPoint::Unproject, src/frames/keypoints.cc:49-62).  Here that
+ * derivation runs on the device for exactly the matched keypoints, so a caller hands over what a
+ * KeyPoint is constructed from: 16 B (host keypoint) + 48 B (target keypoint) per correspondence
+ * instead of 120 B -- the host link is what bounds an end-to-end call.
+ *
+ * Two keypoint tables (host frame(s) / target frame(s)); correspondence i of the batch uses row
+ * host_index[i] / target_index[i] (match.queryIdx / match.trainIdx resolved to table rows), or row
+ * i when the index array is NULL.  Covariances: 2x2 column-major (Eigen::Matrix2d, [K][4]) or,
+ * with packed_covs, their symmetric part (xx, xy, yy), [K][3].  The target table's covariances
+ * give covs_target (noise frame Target, the reference's default); host_covs2 is only needed
+ * for the SYMMETRIC variant. */
+typedef struct pnec_keypoint_batch {
+  int64_t num_problems;        /* B frame pairs                                           */
+  int64_t n_per_problem;       /* uniform N when offsets == NULL                          */
+  const int64_t *offsets;      /* [B+1] HOST pointer, or NULL                             */
+  int32_t memspace;            /* pnec_memspace of every pointer below except K_inv       */
+  int32_t packed_covs;         /* 0: [K][4] column-major 2x2;  1: [K][3] (xx, xy, yy)     */
+  int64_t num_host_keypoints;  /* rows of host_points (/ host_covs2)                      */
+  int64_t num_target_keypoints;/* rows of target_points / target_covs2                    */
+  const double *host_points;   /* [Kh][2] KeyPoint::point_                                */
+  const double *target_points; /* [Kt][2]                                                 */
+  const double *host_covs2;    /* [Kh][4|3] KeyPoint::img_covariance_, or NULL            */
+  const double *target_covs2;  /* [Kt][4|3], or NULL for NEC-only use                     */
+  const int32_t *host_index;   /* [total] or NULL                                         */
+  const int32_t *target_index; /* [total] or NULL                                         */
+  const double *K_inv;         /* [9] column-major, HOST pointer                          */
+  const double *poses;         /* [B][7] start poses                                      */
+} pnec_keypoint_batch;
+
+/* Builds the solver's inputs on the device (one pass: unprojection + unscented transform of the
+ * matched keypoints) and returns them as a DEVICE-memspace pnec_batch in *out_batch, usable with
+ * every entry point above.  The arrays belong to the handle and stay valid until the next call
+ * on it that stages a HOST batch or keypoints.  Enqueued on `cuda_stream`. */
+int pnec_keypoints_to_batch(pnec_handle *h, const pnec_keypoint_batch *kb, pnec_batch *out_batch,
+                            void *cuda_stream);
+
+/* pnec_solve_batch / pnec_frame_solve_batch fed from keypoints.  `out` pointers live in
+ * kb->memspace.  HOST: the keypoint tables are cut into chunks whose copy, assembly, solve and
+ * result copy overlap; returns with the results in the caller's buffers. */
+int pnec_solve_from_keypoints_batch(pnec_handle *h, const pnec_keypoint_batch *kb,
+                                    const pnec_solver_opts *opts, const pnec_solve_out *out,
+                                    void *cuda_stream);
+int pnec_frame_solve_from_keypoints_batch(pnec_handle *h, const pnec_keypoint_batch *kb,
+                                          const pnec_frame_opts *opts, const pnec_frame_out *out,
+                                          void *cuda_stream);
+
 /* Number of kernels this handle has launched so far (bench bookkeeping). */
 int64_t pnec_launch_count(const pnec_handle *h);
 

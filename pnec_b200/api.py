@@ -46,6 +46,9 @@ EXPORTED_SYMBOLS = (
     "pnec_keypoints_unproject_batch",
     "pnec_scf_translation_batch",
     "pnec_ransac_batch",
+    "pnec_keypoints_to_batch",
+    "pnec_solve_from_keypoints_batch",
+    "pnec_frame_solve_from_keypoints_batch",
     "pnec_nec_translation_batch",
     "pnec_eigensolver_batch",
     "pnec_frame_opts_default",
@@ -149,6 +152,26 @@ class _FrameOut(ctypes.Structure):
     ]
 
 
+class _KeypointBatch(ctypes.Structure):
+    _fields_ = [
+        ("num_problems", ctypes.c_int64),
+        ("n_per_problem", ctypes.c_int64),
+        ("offsets", ctypes.c_void_p),
+        ("memspace", ctypes.c_int32),
+        ("packed_covs", ctypes.c_int32),
+        ("num_host_keypoints", ctypes.c_int64),
+        ("num_target_keypoints", ctypes.c_int64),
+        ("host_points", ctypes.c_void_p),
+        ("target_points", ctypes.c_void_p),
+        ("host_covs2", ctypes.c_void_p),
+        ("target_covs2", ctypes.c_void_p),
+        ("host_index", ctypes.c_void_p),
+        ("target_index", ctypes.c_void_p),
+        ("K_inv", ctypes.c_void_p),
+        ("poses", ctypes.c_void_p),
+    ]
+
+
 _lib = None
 
 
@@ -212,6 +235,16 @@ def load_library() -> ctypes.CDLL:
                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                     ctypes.c_void_p]
     L.pnec_ransac_batch.restype = ctypes.c_int
+    L.pnec_keypoints_to_batch.argtypes = [ctypes.c_void_p, ctypes.POINTER(_KeypointBatch), ctypes.POINTER(_Batch),
+                                          ctypes.c_void_p]
+    L.pnec_keypoints_to_batch.restype = ctypes.c_int
+    L.pnec_solve_from_keypoints_batch.argtypes = [ctypes.c_void_p, ctypes.POINTER(_KeypointBatch),
+                                                  ctypes.POINTER(SolverOpts), ctypes.POINTER(_SolveOut), ctypes.c_void_p]
+    L.pnec_solve_from_keypoints_batch.restype = ctypes.c_int
+    L.pnec_frame_solve_from_keypoints_batch.argtypes = [ctypes.c_void_p, ctypes.POINTER(_KeypointBatch),
+                                                        ctypes.POINTER(FrameOpts), ctypes.POINTER(_FrameOut),
+                                                        ctypes.c_void_p]
+    L.pnec_frame_solve_from_keypoints_batch.restype = ctypes.c_int
     L.pnec_launch_count.argtypes = [ctypes.c_void_p]
     L.pnec_launch_count.restype = ctypes.c_int64
     _lib = L
@@ -647,6 +680,126 @@ class Handle:
         res.num_inliers, res.ransac_iterations = ni, rit
         res.inlier_index = None if idx is None else idx[:total]
         res.stage_ms = stage
+        return res
+
+
+    # ------------------------------------------------------------ from keypoints
+    def _keypoint_batch(self, host_points, target_points, target_covs2, init_poses, K_inv, host_covs2, host_index,
+                        target_index, packed, offsets, n_per_problem, keep):
+        device = _is_torch(host_points)
+        kb = _KeypointBatch()
+        cd = 3 if packed else 4
+        if device:
+            import torch
+
+            def chk(t, dtype):
+                if t is None:
+                    return None
+                if not (t.is_cuda and t.dtype == dtype and t.is_contiguous() and t.device.index == self.device):
+                    raise PnecError("device keypoint batches need contiguous CUDA tensors on the handle's device "
+                                    "(float64 tables, int32 indices)")
+                return t
+
+            hp, tp, hc, tc, poses = (chk(x, torch.float64) for x in (host_points, target_points, host_covs2,
+                                                                      target_covs2, init_poses))
+            hi, ti = chk(host_index, torch.int32), chk(target_index, torch.int32)
+            size = lambda t: t.numel()
+            ptr = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+            kb.memspace = MEM_DEVICE
+        else:
+            f64 = lambda a, tail: None if a is None else np.ascontiguousarray(a, dtype=np.float64).reshape((-1,) + tail)
+            i32 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.int32).reshape(-1)
+            hp, tp = f64(host_points, (2,)), f64(target_points, (2,))
+            hc, tc = f64(host_covs2, (cd,)), f64(target_covs2, (cd,))
+            poses = f64(init_poses, (7,))
+            hi, ti = i32(host_index), i32(target_index)
+            size = lambda a: a.size
+            ptr = lambda a: None if a is None else ctypes.c_void_p(a.ctypes.data)
+            kb.memspace = MEM_HOST
+        kinv = np.ascontiguousarray(K_inv, dtype=np.float64).reshape(9)  # column-major, as keypoints_unproject
+        keep.extend([hp, tp, hc, tc, poses, hi, ti, kinv])
+        kh, kt = size(hp) // 2, size(tp) // 2
+        B = size(poses) // 7
+        if hc is not None and size(hc) != kh * cd:
+            raise PnecError("host_covs2 does not match host_points")
+        if tc is not None and size(tc) != kt * cd:
+            raise PnecError("target_covs2 does not match target_points")
+        if offsets is not None:
+            offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+            if offsets.shape != (B + 1,):
+                raise PnecError("offsets must have num_problems + 1 entries")
+            keep.append(offsets)
+            kb.offsets = ctypes.c_void_p(offsets.ctypes.data)
+            kb.n_per_problem = 0
+            total = int(offsets[-1])
+        else:
+            if n_per_problem is None:
+                ref = size(hi) if hi is not None else kh
+                n_per_problem = ref // B if B else 0
+            kb.offsets = None
+            kb.n_per_problem = int(n_per_problem)
+            total = B * int(n_per_problem)
+        for name, idx in (("host_index", hi), ("target_index", ti)):
+            if idx is not None and size(idx) != total:
+                raise PnecError(f"{name} must have one entry per correspondence")
+        kb.num_problems = B
+        kb.packed_covs = 1 if packed else 0
+        kb.num_host_keypoints, kb.num_target_keypoints = kh, kt
+        kb.host_points, kb.target_points = ptr(hp), ptr(tp)
+        kb.host_covs2, kb.target_covs2 = ptr(hc), ptr(tc)
+        kb.host_index, kb.target_index = ptr(hi), ptr(ti)
+        kb.K_inv = ctypes.c_void_p(kinv.ctypes.data)
+        kb.poses = ptr(poses)
+        return kb, device, B, total
+
+    def solve_from_keypoints(self, host_points, target_points, target_covs2, init_poses, K_inv,
+                             opts: Optional[SolverOpts] = None, *, host_covs2=None, host_index=None,
+                             target_index=None, packed=False, offsets=None, n_per_problem=None,
+                             out: Optional[SolveResult] = None) -> SolveResult:
+        """pnec_solve_batch fed from keypoints (pixel + 2x2 image covariance per keypoint, the fields
+        of the reference's KeyPoint; Frame2Frame::GetFeatures on the device)."""
+        opts = opts or default_opts(TARGET)
+        keep = []
+        kb, device, B, _ = self._keypoint_batch(host_points, target_points, target_covs2, init_poses, K_inv,
+                                                host_covs2, host_index, target_index, packed, offsets,
+                                                n_per_problem, keep)
+        if out is None:
+            poses, _ = self._out(device, (B, 7))
+            status, _ = self._out_i32(device, (B,))
+            iters, _ = self._out_i32(device, (B,))
+            cost, _ = self._out(device, (B,))
+            init_cost, _ = self._out(device, (B,))
+            out = SolveResult(poses, status, iters, cost, init_cost)
+        p = (lambda t: ctypes.c_void_p(t.data_ptr())) if device else (lambda a: ctypes.c_void_p(a.ctypes.data))
+        o = _SolveOut(p(out.poses), p(out.status), p(out.iterations), p(out.cost), p(out.initial_cost))
+        rc = self._lib.pnec_solve_from_keypoints_batch(self._h, ctypes.byref(kb), ctypes.byref(opts), ctypes.byref(o),
+                                                       self._stream(device))
+        self._check(rc, "pnec_solve_from_keypoints_batch")
+        return out
+
+    def frame_solve_from_keypoints(self, host_points, target_points, target_covs2, init_poses, K_inv,
+                                   opts: Optional[FrameOpts] = None, *, host_index=None, target_index=None,
+                                   packed=False, offsets=None, n_per_problem=None) -> FrameResult:
+        """pnec_frame_solve_batch (PNEC::Solve) fed from keypoints."""
+        opts = opts or default_frame_opts()
+        keep = []
+        kb, device, B, total = self._keypoint_batch(host_points, target_points, target_covs2, init_poses, K_inv, None,
+                                                    host_index, target_index, packed, offsets, n_per_problem, keep)
+        poses, pp = self._out(device, (B, 7))
+        es, pes = self._out(device, (B, 7))
+        status, pst = self._out_i32(device, (B,))
+        iters, pit = self._out_i32(device, (B,))
+        cost, pc = self._out(device, (B,))
+        ni, pni = self._out_i32(device, (B,))
+        rit, prit = self._out_i32(device, (B,))
+        idx, pidx = self._out_i32(device, (max(total, 1),)) if opts.use_ransac else (None, None)
+        o = _FrameOut(pp, pes, pst, pit, pc, pni, pidx, prit, None)
+        rc = self._lib.pnec_frame_solve_from_keypoints_batch(self._h, ctypes.byref(kb), ctypes.byref(opts),
+                                                             ctypes.byref(o), self._stream(device))
+        self._check(rc, "pnec_frame_solve_from_keypoints_batch")
+        res = FrameResult(poses, es, status, iters, cost)
+        res.num_inliers, res.ransac_iterations = ni, rit
+        res.inlier_index = None if idx is None else idx[:total]
         return res
 
 

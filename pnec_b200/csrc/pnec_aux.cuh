@@ -189,22 +189,33 @@ struct KpArgs {
   int use_bulk;
 };
 
-__device__ __forceinline__ void keypoint_unproject(const KpArgs &a, const double pt[2],
-                                                   const double c2[4], double bv[3], double out[9]) {
+// Out of line: ONE body for keypoint_kernel and keypoint_assemble_kernel, so that solver inputs
+// built from keypoints on the way in are bit-identical to those of pnec_keypoints_unproject_batch.
+__device__ __noinline__ void keypoint_unproject_kinv(const double *Kinv, double px, double py, double c0, double c1,
+                                                     double c2v, double c3, double *bv, double *out) {
   // pnec::common::Unproject: (K_inv (x, y, 1)).normalized()
-  const double x = a.Kinv[0] * pt[0] + a.Kinv[3] * pt[1] + a.Kinv[6];
-  const double y = a.Kinv[1] * pt[0] + a.Kinv[4] * pt[1] + a.Kinv[7];
-  const double z = a.Kinv[2] * pt[0] + a.Kinv[5] * pt[1] + a.Kinv[8];
+  const double x = Kinv[0] * px + Kinv[3] * py + Kinv[6];
+  const double y = Kinv[1] * px + Kinv[4] * py + Kinv[7];
+  const double z = Kinv[2] * px + Kinv[5] * py + Kinv[8];
   const double inv = 1.0 / sqrt(x * x + y * y + z * z);
   bv[0] = x * inv; bv[1] = y * inv; bv[2] = z * inv;
+  if (!out) return;
   UtArgs u{};
 #pragma unroll
-  for (int k = 0; k < 9; ++k) u.Kinv[k] = a.Kinv[k];
+  for (int k = 0; k < 9; ++k) u.Kinv[k] = Kinv[k];
   u.kappa = 1.0;
   u.camera_model = PNEC_CAMERA_PINHOLE;
-  const double mu[3] = {pt[0], pt[1], 1.0};
-  const double S[9] = {c2[0], c2[1], 0.0, c2[2], c2[3], 0.0, 0.0, 0.0, 0.0};  // column-major
-  unscented_point(u, mu, S, out);
+  const double mu[3] = {px, py, 1.0};
+  const double S[9] = {c0, c1, 0.0, c2v, c3, 0.0, 0.0, 0.0, 0.0};  // column-major
+  double o9[9];
+  unscented_point(u, mu, S, o9);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) out[k] = o9[k];
+}
+
+__device__ __forceinline__ void keypoint_unproject(const KpArgs &a, const double pt[2],
+                                                   const double c2[4], double bv[3], double out[9]) {
+  keypoint_unproject_kinv(a.Kinv, pt[0], pt[1], c2[0], c2[1], c2[2], c2[3], bv, out);
 }
 
 __global__ void __launch_bounds__(128) keypoint_kernel(const __grid_constant__ KpArgs a) {
@@ -252,6 +263,50 @@ __global__ void __launch_bounds__(128) keypoint_kernel(const __grid_constant__ K
     for (int k = 0; k < 3; ++k) a.out_bvs[3 * i + k] = bv[k];
 #pragma unroll
     for (int k = 0; k < 9; ++k) a.out_covs[9 * i + k] = out[k];
+  }
+}
+
+// Frame2Frame::GetFeatures (src/rel_pose_estimation/frame2frame.cc:359-392) on the device: the solver's
+// inputs of `total` correspondences from the keypoints of the two frames -- pixel position and 2x2
+// image covariance, the fields a pnec::features::KeyPoint is constructed from (keypoints.cc:42-62) --
+// selected by the matches' query / train indices.  64 B per correspondence cross the host link
+// instead of 120.
+struct KpAssembleArgs {
+  const double *host_points, *target_points;   // [Kh][2], [Kt][2]
+  const double *host_covs2, *target_covs2;     // [K][4] column-major 2x2, or [K][3] (xx, xy, yy) when packed
+  const int *host_index, *target_index;        // [total] rows of the two tables, or nullptr: row i
+  double *f1, *f2, *ct, *ch;                   // [total][3], [total][3], [total][9], [total][9] (ct / ch may be null)
+  long long first, count;                      // correspondences [first, first + count)
+  double Kinv[9];
+  int packed;
+};
+
+__global__ void __launch_bounds__(128) keypoint_assemble_kernel(const __grid_constant__ KpAssembleArgs a) {
+  const long long i = a.first + static_cast<long long>(blockIdx.x) * 128 + threadIdx.x;
+  if (i >= a.first + a.count) return;
+  const long long hi = a.host_index ? a.host_index[i] : i, ti = a.target_index ? a.target_index[i] : i;
+  auto cov = [&](const double *tab, long long r, double c[4]) {
+    if (a.packed) { c[0] = tab[3 * r]; c[1] = tab[3 * r + 1]; c[2] = c[1]; c[3] = tab[3 * r + 2]; }
+    else { c[0] = tab[4 * r]; c[1] = tab[4 * r + 1]; c[2] = tab[4 * r + 2]; c[3] = tab[4 * r + 3]; }
+  };
+  double bv[3], o9[9], c[4] = {0, 0, 0, 0};
+  if (a.ch) cov(a.host_covs2, hi, c);
+  keypoint_unproject_kinv(a.Kinv, a.host_points[2 * hi], a.host_points[2 * hi + 1], c[0], c[1], c[2], c[3], bv,
+                          a.ch ? o9 : nullptr);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) a.f1[3 * i + k] = bv[k];
+  if (a.ch) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) a.ch[9 * i + k] = o9[k];
+  }
+  if (a.ct) cov(a.target_covs2, ti, c);
+  keypoint_unproject_kinv(a.Kinv, a.target_points[2 * ti], a.target_points[2 * ti + 1], c[0], c[1], c[2], c[3], bv,
+                          a.ct ? o9 : nullptr);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) a.f2[3 * i + k] = bv[k];
+  if (a.ct) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) a.ct[9 * i + k] = o9[k];
   }
 }
 

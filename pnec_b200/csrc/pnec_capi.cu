@@ -92,6 +92,8 @@ struct Config {
   int no_lm_ahead = 0;
   int no_stager = 0;
   int ransac_warps = 0;
+  int ransac_occ = 16;  // PNEC_B200_RANSAC_OCC: warps per SM the RANSAC kernels are compiled for (8, 12, 16)
+  int ransac_defer = -1;  // PNEC_B200_RANSAC_DEFER: iterations after which pass 1 hands a pair to pass 2 (0: never)
   int scf_debug = 0;
   int scf_defer = 48;
   int scf_warps = 0;
@@ -110,6 +112,8 @@ struct Config {
     no_lm_ahead = env_int("PNEC_B200_NO_LM_AHEAD", 0);
     no_stager = env_int("PNEC_B200_NO_STAGER", 0);
     ransac_warps = env_int("PNEC_B200_RANSAC_WARPS", 0);
+    ransac_occ = env_int("PNEC_B200_RANSAC_OCC", 16);
+    ransac_defer = env_int("PNEC_B200_RANSAC_DEFER", -1);
     scf_debug = env_int("PNEC_B200_SCF_DEBUG", 0);
     scf_defer = env_int("PNEC_B200_SCF_DEFER", 48);
     scf_warps = env_int("PNEC_B200_SCF_WARPS", 0);
@@ -272,6 +276,9 @@ struct pnec_handle {
   DevBuf d_scf_spill;             // [total][9] SCF terms of pairs that do not fit shared memory
   DevBuf d_rs_f1, d_rs_f2, d_rs_ct;  // RANSAC: inliers compacted to the front of every pair's slot
   DevBuf d_rs_best, d_rs_cnt, d_rs_iters, d_rs_idx;  // winning models [B][7], counts, iterations, indices
+  DevBuf d_rs_state, d_rs_defer, d_rs_prefix, d_rs_hyp;  // pass 2 of the RANSAC stage (pnec_ransac.cuh)
+  DevBuf d_kp_hp, d_kp_tp, d_kp_hc, d_kp_tc, d_kp_hi, d_kp_ti;  // keypoint tables and match indices (HOST callers)
+  DevBuf d_kp_out[8];  // device outputs of the from-keypoints entry points for HOST callers
   static constexpr int kMaxChunks = 8;
   static constexpr int kMaxRounds = 64;
   cudaStream_t side[kMaxChunks] = {}, lm_side[kMaxChunks] = {};
@@ -283,7 +290,7 @@ struct pnec_handle {
   DevBuf d_fr_rounds;             // poses of every weighted round: [rounds][B][7]
   HostStager stager;              // pinned ring + copy threads for pageable host inputs
   int sphere_samples = -1;
-  std::mutex mu;
+  std::recursive_mutex mu;  // the keypoint entry points call the batch entry points on the same handle
 };
 
 namespace {
@@ -929,8 +936,20 @@ struct RansacOut {
   double *ct;       // [total][9] or nullptr
 };
 
+// scratch of the two-pass scheme for a batch of B pairs cut into at most kMaxChunks chunks (each chunk
+// owns the slice [c0, c0 + cnt) of every array and its own 4-int header)
+int ensure_ransac_scratch(pnec_handle *h, long long B) {
+  const size_t nb = static_cast<size_t>(B);
+  PNEC_CUDA(h->d_rs_state.ensure(nb * sizeof(RansacPairState)));
+  PNEC_CUDA(h->d_rs_defer.ensure(sizeof(int) * (4 * pnec_handle::kMaxChunks + nb)));
+  PNEC_CUDA(h->d_rs_prefix.ensure(sizeof(int) * (pnec_handle::kMaxChunks + nb)));
+  PNEC_CUDA(h->d_rs_hyp.ensure(sizeof(int) * nb * kRansacSuper));
+  return PNEC_OK;
+}
+
+// `bv`: pairs [pair0, pair0 + bv.num_problems) of the batch the scratch was sized for, chunk `chunk`.
 int run_ransac(pnec_handle *h, const BatchView &bv, const pnec_frame_opts &o, long long pair_index_base,
-               const RansacOut &out, cudaStream_t stream) {
+               const RansacOut &out, long long pair0, int chunk, cudaStream_t stream) {
   RansacArgs a{};
   a.bv = bv;
   a.best_poses = out.best;
@@ -948,16 +967,57 @@ int run_ransac(pnec_handle *h, const BatchView &bv, const pnec_frame_opts &o, lo
   a.seed = o.ransac_seed;
   a.pair_index_base = pair_index_base;
   a.lm = EsLmParams{0.00005, 1.0e1 * DBL_EPSILON, 0.0, 100.0, 100};
-  // One CTA per pair.  Many pairs: one warp each (8 hypotheses per round; the machine is filled by
-  // the pairs).  Few pairs: more warps, i.e. more hypotheses per round and a faster scoring pass.
+  // Pass 1, one CTA per pair.  Many pairs: one warp each (8 hypotheses per round; the machine is filled
+  // by the pairs).  Few pairs: more warps, i.e. more hypotheses per round and a faster scoring pass.
   int nw = h->cfg.ransac_warps;
   if (nw == 0) nw = bv.num_problems >= 4LL * h->sm_count ? 1 : 4;
+  // Pairs unfinished after a few rounds go to pass 2 (their hypotheses spread over the whole device).
+  int defer_after = h->cfg.ransac_defer;
+  if (defer_after < 0) defer_after = nw == 1 ? 24 : 56;
+  if (o.max_ransac_iterations + 1 <= defer_after) defer_after = 0;
+  a.defer_after = defer_after;
+  a.state = static_cast<RansacPairState *>(h->d_rs_state.p) + pair0;
+  a.defer = static_cast<int *>(h->d_rs_defer.p) + (4 * chunk + pair0);
+  a.blk_prefix = static_cast<int *>(h->d_rs_prefix.p) + (chunk + pair0);
+  a.hyp_count = static_cast<int *>(h->d_rs_hyp.p) + pair0 * kRansacSuper;
+  if (defer_after > 0) PNEC_CUDA(cudaMemsetAsync(a.defer, 0, 4 * sizeof(int), stream));
   const unsigned grid = static_cast<unsigned>(bv.num_problems);
-  if (nw == 1) ransac_kernel<1><<<grid, 32, 0, stream>>>(a);
-  else if (nw == 2) ransac_kernel<2><<<grid, 64, 0, stream>>>(a);
-  else ransac_kernel<4><<<grid, 128, 0, stream>>>(a);
+  // registers per thread: 255 (8 warps per SM), 168 (12) or 128 (16); the hypotheses are latency bound
+  const int occ = h->cfg.ransac_occ;
+  if (nw == 1) {
+    if (occ == 8) ransac_kernel<1, 8><<<grid, 32, 0, stream>>>(a);
+    else if (occ == 12) ransac_kernel<1, 12><<<grid, 32, 0, stream>>>(a);
+    else ransac_kernel<1, 16><<<grid, 32, 0, stream>>>(a);
+  } else if (nw == 2) {
+    if (occ == 8) ransac_kernel<2, 4><<<grid, 64, 0, stream>>>(a);
+    else if (occ == 12) ransac_kernel<2, 6><<<grid, 64, 0, stream>>>(a);
+    else ransac_kernel<2, 8><<<grid, 64, 0, stream>>>(a);
+  } else {
+    if (occ == 8) ransac_kernel<4, 2><<<grid, 128, 0, stream>>>(a);
+    else if (occ == 12) ransac_kernel<4, 3><<<grid, 128, 0, stream>>>(a);
+    else ransac_kernel<4, 4><<<grid, 128, 0, stream>>>(a);
+  }
   PNEC_CUDA(cudaGetLastError());
   h->launches++;
+  if (defer_after > 0) {
+    // Pass 2: every super-round finishes a deferred pair or consumes its whole grant (ransac_grant), so
+    // this many super-rounds cover the worst case; with nothing (left) to do the kernels return at once.
+    int rounds = 0;
+    for (int it = defer_after; it <= o.max_ransac_iterations; ++rounds) it += ransac_grant(it, o.max_ransac_iterations);
+    const int per_sm = occ == 8 ? 2 : occ == 12 ? 3 : 4;  // CTAs of 4 independent warps per SM
+    const unsigned pgrid = static_cast<unsigned>(std::min<long long>(
+        1LL * per_sm * h->sm_count, (bv.num_problems * (kRansacSuper / kRansacBlock) + 3) / 4));
+    ransac_plan_kernel<<<1, 1024, 0, stream>>>(a, 0);
+    for (int r = 0; r < rounds; ++r) {
+      if (per_sm == 2) ransac_hyp_kernel<4, 2><<<pgrid, 128, 0, stream>>>(a);
+      else if (per_sm == 3) ransac_hyp_kernel<4, 3><<<pgrid, 128, 0, stream>>>(a);
+      else ransac_hyp_kernel<4, 4><<<pgrid, 128, 0, stream>>>(a);
+      ransac_plan_kernel<<<1, 1024, 0, stream>>>(a, 1);
+    }
+    ransac_final_kernel<<<static_cast<unsigned>(std::min<long long>(2LL * h->sm_count, bv.num_problems)), 128, 0, stream>>>(a);
+    PNEC_CUDA(cudaGetLastError());
+    h->launches += 2 + 2 * rounds;
+  }
   return PNEC_OK;
 }
 
@@ -1046,8 +1106,11 @@ void pnec_destroy(pnec_handle *h) {
                     &h->d_ut_out, &h->d_kp_bv, &h->d_sphere, &h->d_tr_out,
                     &h->d_tr_aux, &h->d_es_mom, &h->d_es_w, &h->d_es_info, &h->d_es_ev,
                     &h->d_fr_es, &h->d_fr_a, &h->d_fr_cache, &h->d_fr_flags, &h->d_scf_defer, &h->d_fr_defer, &h->d_scf_spill,
-                    &h->d_rs_f1, &h->d_rs_f2, &h->d_rs_ct, &h->d_rs_best, &h->d_rs_cnt, &h->d_rs_iters, &h->d_rs_idx};
+                    &h->d_rs_f1, &h->d_rs_f2, &h->d_rs_ct, &h->d_rs_best, &h->d_rs_cnt, &h->d_rs_iters, &h->d_rs_idx,
+                    &h->d_rs_state, &h->d_rs_defer, &h->d_rs_prefix, &h->d_rs_hyp,
+                    &h->d_kp_hp, &h->d_kp_tp, &h->d_kp_hc, &h->d_kp_tc, &h->d_kp_hi, &h->d_kp_ti};
   for (DevBuf *b : bufs) b->release();
+  for (DevBuf &b : h->d_kp_out) b.release();
   for (int i = 0; i < pnec_handle::kMaxChunks; ++i) {
     if (h->side[i]) cudaStreamDestroy(h->side[i]);
     if (h->lm_side[i]) cudaStreamDestroy(h->lm_side[i]);
@@ -1074,7 +1137,7 @@ int pnec_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_solver_
   const long long B = batch->num_problems;
   if (B > 0 && !out->poses) return fail(PNEC_ERR_INVALID_ARGUMENT, "out->poses is NULL");
   if (B == 0) return PNEC_OK;
-  std::lock_guard<std::mutex> lock(h->mu);
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   PNEC_CUDA(cudaSetDevice(h->device));
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
   CallScope scope(h, stream);
@@ -1162,7 +1225,7 @@ int pnec_eval_batch(pnec_handle *h, const pnec_batch *batch, int32_t variant,
   if (rc != PNEC_OK) return rc;
   const long long B = batch->num_problems;
   if (B == 0) return PNEC_OK;
-  std::lock_guard<std::mutex> lock(h->mu);
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   PNEC_CUDA(cudaSetDevice(h->device));
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
   CallScope scope(h, stream);
@@ -1209,7 +1272,7 @@ int pnec_cost_function_batch(pnec_handle *h, const pnec_batch *batch, double *ou
   if (rc != PNEC_OK) return rc;
   const long long B = batch->num_problems;
   if (B == 0) return PNEC_OK;
-  std::lock_guard<std::mutex> lock(h->mu);
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   PNEC_CUDA(cudaSetDevice(h->device));
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
   CallScope scope(h, stream);
@@ -1246,7 +1309,7 @@ int pnec_unscented_transform_batch(pnec_handle *h, int64_t n, int32_t memspace, 
     return fail(PNEC_ERR_INVALID_ARGUMENT, "K_inv is NULL for a pinhole camera");
   if (memspace != PNEC_MEM_HOST && memspace != PNEC_MEM_DEVICE)
     return fail(PNEC_ERR_INVALID_ARGUMENT, "unknown memspace");
-  std::lock_guard<std::mutex> lock(h->mu);
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   PNEC_CUDA(cudaSetDevice(h->device));
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
   CallScope scope(h, stream);
@@ -1291,7 +1354,7 @@ int pnec_keypoints_unproject_batch(pnec_handle *h, int64_t n, int32_t memspace, 
     return fail(PNEC_ERR_INVALID_ARGUMENT, "NULL array");
   if (memspace != PNEC_MEM_HOST && memspace != PNEC_MEM_DEVICE)
     return fail(PNEC_ERR_INVALID_ARGUMENT, "unknown memspace");
-  std::lock_guard<std::mutex> lock(h->mu);
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   PNEC_CUDA(cudaSetDevice(h->device));
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
   CallScope scope(h, stream);
@@ -1339,7 +1402,7 @@ int pnec_scf_translation_batch(pnec_handle *h, const pnec_batch *batch, double r
   if (rc != PNEC_OK) return rc;
   const long long B = batch->num_problems;
   if (B == 0) return PNEC_OK;
-  std::lock_guard<std::mutex> lock(h->mu);
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   PNEC_CUDA(cudaSetDevice(h->device));
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
   CallScope scope(h, stream);
@@ -1375,7 +1438,7 @@ int pnec_nec_translation_batch(pnec_handle *h, const pnec_batch *batch, double *
   if (rc != PNEC_OK) return rc;
   const long long B = batch->num_problems;
   if (B == 0) return PNEC_OK;
-  std::lock_guard<std::mutex> lock(h->mu);
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   PNEC_CUDA(cudaSetDevice(h->device));
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
   CallScope scope(h, stream);
@@ -1411,7 +1474,7 @@ int pnec_eigensolver_batch(pnec_handle *h, const pnec_batch *batch, const double
   if (rc != PNEC_OK) return rc;
   const long long B = batch->num_problems;
   if (B == 0) return PNEC_OK;
-  std::lock_guard<std::mutex> lock(h->mu);
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   PNEC_CUDA(cudaSetDevice(h->device));
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
   CallScope scope(h, stream);
@@ -1482,7 +1545,7 @@ int pnec_ransac_batch(pnec_handle *h, const pnec_batch *batch, const pnec_frame_
   if (rc != PNEC_OK) return rc;
   const long long B = batch->num_problems;
   if (B == 0) return PNEC_OK;
-  std::lock_guard<std::mutex> lock(h->mu);
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   PNEC_CUDA(cudaSetDevice(h->device));
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
   CallScope scope(h, stream);
@@ -1510,7 +1573,9 @@ int pnec_ransac_batch(pnec_handle *h, const pnec_batch *batch, const pnec_frame_
     ro.iters = static_cast<int *>(h->d_rs_iters.p);
     ro.index = out_inlier_index ? static_cast<int *>(h->d_rs_idx.p) : nullptr;
   }
-  rc = run_ransac(h, st.bv, *opts, pair_index_base, ro, stream);
+  rc = ensure_ransac_scratch(h, B);
+  if (rc != PNEC_OK) return rc;
+  rc = run_ransac(h, st.bv, *opts, pair_index_base, ro, 0, 0, stream);
   if (rc != PNEC_OK) return rc;
   if (host) {
     PNEC_CUDA(cudaMemcpyAsync(out_models, ro.best, nb * 56, cudaMemcpyDeviceToHost, stream));
@@ -1541,7 +1606,7 @@ int pnec_frame_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_f
   const long long B = batch->num_problems;
   if (B > 0 && !out->poses) return fail(PNEC_ERR_INVALID_ARGUMENT, "out->poses is NULL");
   if (B == 0) return PNEC_OK;
-  std::lock_guard<std::mutex> lock(h->mu);
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   PNEC_CUDA(cudaSetDevice(h->device));
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
   CallScope scope(h, stream);
@@ -1583,6 +1648,10 @@ int pnec_frame_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_f
     PNEC_CUDA(h->d_rs_cnt.ensure(nb * 4));
     PNEC_CUDA(h->d_rs_iters.ensure(nb * 4));
     if (host && out->inlier_index) PNEC_CUDA(h->d_rs_idx.ensure(nel * 4));
+    {
+      const int src = ensure_ransac_scratch(h, B);
+      if (src != PNEC_OK) return src;
+    }
     ro.best = static_cast<double *>(h->d_rs_best.p);
     ro.count = (!host && out->num_inliers) ? out->num_inliers : static_cast<int *>(h->d_rs_cnt.p);
     ro.iters = (!host && out->ransac_iterations) ? out->ransac_iterations : static_cast<int *>(h->d_rs_iters.p);
@@ -1635,7 +1704,7 @@ int pnec_frame_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_f
       r.f1 += 3 * e0; r.f2 += 3 * e0;
       if (r.ct) r.ct += 9 * e0;
       if (r.index) r.index += e0;
-      if ((rcc = run_ransac(h, bv, *opts, c0, r, cs)) != PNEC_OK) return rcc;
+      if ((rcc = run_ransac(h, bv, *opts, c0, r, c0, chunk, cs)) != PNEC_OK) return rcc;
       bv.f1 = r.f1; bv.f2 = r.f2;
       if (r.ct) bv.ct = r.ct;
       bv.counts = r.count;
@@ -1823,6 +1892,339 @@ int pnec_frame_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_f
     for (int k = 0; k < 3; ++k) PNEC_CUDA(cudaEventElapsedTime(&out->stage_ms[k], h->ev_stage[k], h->ev_stage[k + 1]));
   }
   scope.ok = true;
+  return PNEC_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ keypoints -> batch
+
+namespace {
+
+struct KpStaged {
+  KpAssembleArgs a;       // device pointers of tables / indices / outputs
+  long long total = 0;
+  int cov_doubles = 4;
+  bool host = false, indexed = false;
+};
+
+int validate_keypoints(const pnec_keypoint_batch *kb, bool need_poses, long long *total_out) {
+  if (!kb) return fail(PNEC_ERR_INVALID_ARGUMENT, "keypoint batch is NULL");
+  if (kb->num_problems < 0 || kb->num_problems > 0x7fffffffLL) return fail(PNEC_ERR_INVALID_ARGUMENT, "bad num_problems");
+  if (kb->memspace != PNEC_MEM_HOST && kb->memspace != PNEC_MEM_DEVICE)
+    return fail(PNEC_ERR_INVALID_ARGUMENT, "unknown memspace");
+  long long total;
+  if (kb->offsets) {
+    if (kb->offsets[0] < 0) return fail(PNEC_ERR_INVALID_ARGUMENT, "offsets[0] < 0");
+    for (int64_t i = 0; i < kb->num_problems; ++i)
+      if (kb->offsets[i + 1] < kb->offsets[i] || kb->offsets[i + 1] - kb->offsets[i] > 0x7ffffff0LL)
+        return fail(PNEC_ERR_INVALID_ARGUMENT, "offsets must be non-decreasing (and a pair below 2^31 correspondences)");
+    total = kb->offsets[kb->num_problems];
+  } else {
+    if (kb->n_per_problem < 0 || kb->n_per_problem > 0x7ffffff0LL) return fail(PNEC_ERR_INVALID_ARGUMENT, "bad n_per_problem");
+    if (kb->num_problems > 0 && kb->n_per_problem > (0x7fffffffffffffffLL / 72) / kb->num_problems)
+      return fail(PNEC_ERR_INVALID_ARGUMENT, "num_problems * n_per_problem overflows");
+    total = kb->num_problems * kb->n_per_problem;
+  }
+  if (total > 0) {
+    if (!kb->host_points || !kb->target_points || !kb->K_inv)
+      return fail(PNEC_ERR_INVALID_ARGUMENT, "keypoint tables / K_inv are NULL");
+    if (kb->num_host_keypoints < 0 || kb->num_target_keypoints < 0 || kb->num_host_keypoints > 0x7fffffffLL ||
+        kb->num_target_keypoints > 0x7fffffffLL)
+      return fail(PNEC_ERR_INVALID_ARGUMENT, "bad keypoint table size");
+    if (!kb->host_index && kb->num_host_keypoints < total)
+      return fail(PNEC_ERR_INVALID_ARGUMENT, "host keypoint table shorter than the batch (no host_index given)");
+    if (!kb->target_index && kb->num_target_keypoints < total)
+      return fail(PNEC_ERR_INVALID_ARGUMENT, "target keypoint table shorter than the batch (no target_index given)");
+    if (kb->memspace == PNEC_MEM_HOST) {  // host indices can be checked; device ones are the caller's contract
+      if (kb->host_index)
+        for (long long i = 0; i < total; ++i)
+          if (kb->host_index[i] < 0 || kb->host_index[i] >= kb->num_host_keypoints)
+            return fail(PNEC_ERR_INVALID_ARGUMENT, "host_index out of range");
+      if (kb->target_index)
+        for (long long i = 0; i < total; ++i)
+          if (kb->target_index[i] < 0 || kb->target_index[i] >= kb->num_target_keypoints)
+            return fail(PNEC_ERR_INVALID_ARGUMENT, "target_index out of range");
+    }
+  }
+  if (need_poses && kb->num_problems > 0 && !kb->poses) return fail(PNEC_ERR_INVALID_ARGUMENT, "poses is NULL");
+  *total_out = total;
+  return PNEC_OK;
+}
+
+// Device buffers for the assembled batch (and, for HOST callers, for the tables); nothing is copied yet.
+int kp_alloc(pnec_handle *h, const pnec_keypoint_batch *kb, long long total, KpStaged *ks) {
+  const size_t nel = static_cast<size_t>(std::max<long long>(total, 1));
+  const bool need_ct = kb->target_covs2 != nullptr, need_ch = kb->host_covs2 != nullptr;
+  PNEC_CUDA(h->d_f1.ensure(nel * 24));
+  PNEC_CUDA(h->d_f2.ensure(nel * 24));
+  if (need_ct) PNEC_CUDA(h->d_ct.ensure(nel * 72));
+  if (need_ch) PNEC_CUDA(h->d_ch.ensure(nel * 72));
+  PNEC_CUDA(h->d_poses.ensure(static_cast<size_t>(std::max<long long>(kb->num_problems, 1)) * 56));
+  ks->total = total;
+  ks->cov_doubles = kb->packed_covs ? 3 : 4;
+  ks->host = kb->memspace == PNEC_MEM_HOST;
+  ks->indexed = kb->host_index || kb->target_index;
+  KpAssembleArgs &a = ks->a;
+  a = KpAssembleArgs{};
+  a.f1 = static_cast<double *>(h->d_f1.p);
+  a.f2 = static_cast<double *>(h->d_f2.p);
+  a.ct = need_ct ? static_cast<double *>(h->d_ct.p) : nullptr;
+  a.ch = need_ch ? static_cast<double *>(h->d_ch.p) : nullptr;
+  a.packed = kb->packed_covs ? 1 : 0;
+  for (int k = 0; k < 9; ++k) a.Kinv[k] = kb->K_inv[k];
+  if (ks->host) {
+    const size_t kh = static_cast<size_t>(std::max<long long>(kb->num_host_keypoints, 1));
+    const size_t kt = static_cast<size_t>(std::max<long long>(kb->num_target_keypoints, 1));
+    PNEC_CUDA(h->d_kp_hp.ensure(kh * 16));
+    PNEC_CUDA(h->d_kp_tp.ensure(kt * 16));
+    if (need_ch) PNEC_CUDA(h->d_kp_hc.ensure(kh * 8 * ks->cov_doubles));
+    if (need_ct) PNEC_CUDA(h->d_kp_tc.ensure(kt * 8 * ks->cov_doubles));
+    if (kb->host_index) PNEC_CUDA(h->d_kp_hi.ensure(nel * 4));
+    if (kb->target_index) PNEC_CUDA(h->d_kp_ti.ensure(nel * 4));
+    a.host_points = static_cast<const double *>(h->d_kp_hp.p);
+    a.target_points = static_cast<const double *>(h->d_kp_tp.p);
+    a.host_covs2 = need_ch ? static_cast<const double *>(h->d_kp_hc.p) : nullptr;
+    a.target_covs2 = need_ct ? static_cast<const double *>(h->d_kp_tc.p) : nullptr;
+    a.host_index = kb->host_index ? static_cast<const int *>(h->d_kp_hi.p) : nullptr;
+    a.target_index = kb->target_index ? static_cast<const int *>(h->d_kp_ti.p) : nullptr;
+  } else {
+    a.host_points = kb->host_points;
+    a.target_points = kb->target_points;
+    a.host_covs2 = kb->host_covs2;
+    a.target_covs2 = kb->target_covs2;
+    a.host_index = kb->host_index;
+    a.target_index = kb->target_index;
+  }
+  return PNEC_OK;
+}
+
+// H2D of what correspondences [e0, e1) need (HOST callers): with index arrays the whole tables (once,
+// e0 == 0), else the matching rows.  Then the assembly kernel for [e0, e1).  Poses [p0, p1) ride along.
+int kp_stage_range(pnec_handle *h, const pnec_keypoint_batch *kb, const KpStaged &ks, long long e0, long long e1,
+                   long long p0, long long p1, cudaStream_t stream) {
+  auto h2d = [&](void *dst, const void *src, size_t bytes) -> cudaError_t {
+    if (bytes == 0) return cudaSuccess;
+    if (bytes >= (4u << 20) && !h->cfg.no_stager && HostStager::pageable(src)) return h->stager.h2d(dst, src, bytes, stream);
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream);
+  };
+  auto at = [](const void *base, long long bytes) { return const_cast<char *>(static_cast<const char *>(base)) + bytes; };
+  const size_t cd = static_cast<size_t>(ks.cov_doubles) * 8;
+  if (ks.host) {
+    if (ks.indexed) {
+      if (e0 == 0) {
+        PNEC_CUDA(h2d(h->d_kp_hp.p, kb->host_points, static_cast<size_t>(kb->num_host_keypoints) * 16));
+        PNEC_CUDA(h2d(h->d_kp_tp.p, kb->target_points, static_cast<size_t>(kb->num_target_keypoints) * 16));
+        if (ks.a.ch) PNEC_CUDA(h2d(h->d_kp_hc.p, kb->host_covs2, static_cast<size_t>(kb->num_host_keypoints) * cd));
+        if (ks.a.ct) PNEC_CUDA(h2d(h->d_kp_tc.p, kb->target_covs2, static_cast<size_t>(kb->num_target_keypoints) * cd));
+        if (kb->host_index) PNEC_CUDA(h2d(h->d_kp_hi.p, kb->host_index, static_cast<size_t>(ks.total) * 4));
+        if (kb->target_index) PNEC_CUDA(h2d(h->d_kp_ti.p, kb->target_index, static_cast<size_t>(ks.total) * 4));
+      }
+    } else {
+      const size_t n = static_cast<size_t>(e1 - e0);
+      PNEC_CUDA(h2d(at(h->d_kp_hp.p, e0 * 16), at(kb->host_points, e0 * 16), n * 16));
+      PNEC_CUDA(h2d(at(h->d_kp_tp.p, e0 * 16), at(kb->target_points, e0 * 16), n * 16));
+      if (ks.a.ch) PNEC_CUDA(h2d(at(h->d_kp_hc.p, e0 * cd), at(kb->host_covs2, e0 * cd), n * cd));
+      if (ks.a.ct) PNEC_CUDA(h2d(at(h->d_kp_tc.p, e0 * cd), at(kb->target_covs2, e0 * cd), n * cd));
+    }
+    if (kb->poses && p1 > p0)
+      PNEC_CUDA(cudaMemcpyAsync(at(h->d_poses.p, p0 * 56), kb->poses + 7 * p0, static_cast<size_t>(p1 - p0) * 56,
+                                cudaMemcpyHostToDevice, stream));
+  }
+  if (e1 > e0) {
+    KpAssembleArgs a = ks.a;
+    a.first = e0;
+    a.count = e1 - e0;
+    keypoint_assemble_kernel<<<static_cast<unsigned>((a.count + 127) / 128), 128, 0, stream>>>(a);
+    PNEC_CUDA(cudaGetLastError());
+    h->launches++;
+  }
+  return PNEC_OK;
+}
+
+pnec_batch kp_device_batch(pnec_handle *h, const pnec_keypoint_batch *kb, const KpStaged &ks) {
+  pnec_batch b{};
+  b.num_problems = kb->num_problems;
+  b.n_per_problem = kb->n_per_problem;
+  b.offsets = kb->offsets;
+  b.memspace = PNEC_MEM_DEVICE;
+  b.bvs_host = ks.a.f1;
+  b.bvs_target = ks.a.f2;
+  b.covs_target = ks.a.ct;
+  b.covs_host = ks.a.ch;
+  b.poses = ks.host ? static_cast<const double *>(h->d_poses.p) : kb->poses;
+  return b;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pnec_keypoints_to_batch(pnec_handle *h, const pnec_keypoint_batch *kb, pnec_batch *out_batch, void *cuda_stream) {
+  if (!h || !out_batch) return fail(PNEC_ERR_INVALID_ARGUMENT, "NULL argument");
+  long long total = 0;
+  int rc = validate_keypoints(kb, false, &total);
+  if (rc != PNEC_OK) return rc;
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
+  PNEC_CUDA(cudaSetDevice(h->device));
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  CallScope scope(h, stream);
+  KpStaged ks;
+  rc = kp_alloc(h, kb, total, &ks);
+  if (rc != PNEC_OK) return rc;
+  rc = kp_stage_range(h, kb, ks, 0, total, 0, kb->num_problems, stream);
+  if (rc != PNEC_OK) return rc;
+  *out_batch = kp_device_batch(h, kb, ks);
+  return PNEC_OK;
+}
+
+int pnec_solve_from_keypoints_batch(pnec_handle *h, const pnec_keypoint_batch *kb, const pnec_solver_opts *opts,
+                                    const pnec_solve_out *out, void *cuda_stream) {
+  if (!h || !opts || !out) return fail(PNEC_ERR_INVALID_ARGUMENT, "NULL argument");
+  long long total = 0;
+  int rc = validate_keypoints(kb, true, &total);
+  if (rc != PNEC_OK) return rc;
+  const long long B = kb->num_problems;
+  if (B > 0 && !out->poses) return fail(PNEC_ERR_INVALID_ARGUMENT, "out->poses is NULL");
+  if (total > 0 && opts->variant != PNEC_VARIANT_NEC && !kb->target_covs2)
+    return fail(PNEC_ERR_INVALID_ARGUMENT, "target_covs2 is NULL for a PNEC variant");
+  if (total > 0 && opts->variant == PNEC_VARIANT_SYMMETRIC && !kb->host_covs2)
+    return fail(PNEC_ERR_INVALID_ARGUMENT, "host_covs2 is NULL for the SYMMETRIC variant");
+  if (B == 0) return PNEC_OK;
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
+  PNEC_CUDA(cudaSetDevice(h->device));
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  CallScope scope(h, stream);
+  KpStaged ks;
+  rc = kp_alloc(h, kb, total, &ks);
+  if (rc != PNEC_OK) return rc;
+  pnec_batch db = kp_device_batch(h, kb, ks);
+  if (!ks.host) {
+    rc = kp_stage_range(h, kb, ks, 0, total, 0, B, stream);
+    if (rc != PNEC_OK) return rc;
+    return pnec_solve_batch(h, &db, opts, out, cuda_stream);
+  }
+  // HOST: device outputs, then chunks (copy + assembly of chunk k + 1 under the solve of chunk k)
+  const size_t nb = static_cast<size_t>(B);
+  const size_t sizes[5] = {56, 4, 4, 8, 8};
+  void *host_ptr[5] = {out->poses, out->status, out->iterations, out->cost, out->initial_cost};
+  void *dev_ptr[5] = {};
+  for (int k = 0; k < 5; ++k) {
+    if (!host_ptr[k]) continue;
+    PNEC_CUDA(h->d_kp_out[k].ensure(nb * sizes[k]));
+    dev_ptr[k] = h->d_kp_out[k].p;
+  }
+  int chunks = h->cfg.h2d_chunks;
+  if (chunks <= 0) chunks = (total * 64 >= (32ll << 20) && B >= 64 && !ks.indexed) ? 4 : 1;
+  if (ks.indexed) chunks = 1;
+  chunks = static_cast<int>(std::min<long long>(std::min(chunks, pnec_handle::kMaxChunks), B));
+  if (!h->ev_fork) PNEC_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  PNEC_CUDA(cudaEventRecord(h->ev_fork, stream));
+  scope.forked = true;
+  for (int c = 0; c < chunks; ++c) {
+    if (!h->side[c]) PNEC_CUDA(cudaStreamCreateWithFlags(&h->side[c], cudaStreamNonBlocking));
+    if (!h->ev_join[c]) PNEC_CUDA(cudaEventCreateWithFlags(&h->ev_join[c], cudaEventDisableTiming));
+    cudaStream_t cs = h->side[c];
+    PNEC_CUDA(cudaStreamWaitEvent(cs, h->ev_fork, 0));
+    long long p0, p1;
+    if (kb->offsets) {
+      auto first_at = [&](long long target) { return std::lower_bound(kb->offsets, kb->offsets + B, target) - kb->offsets; };
+      p0 = c == 0 ? 0 : first_at(total * c / chunks);
+      p1 = c + 1 == chunks ? B : first_at(total * (c + 1) / chunks);
+    } else {
+      p0 = B * c / chunks;
+      p1 = B * (c + 1) / chunks;
+    }
+    if (p1 > p0) {
+      const long long e0 = kb->offsets ? kb->offsets[p0] : p0 * kb->n_per_problem;
+      const long long e1 = kb->offsets ? kb->offsets[p1] : p1 * kb->n_per_problem;
+      rc = kp_stage_range(h, kb, ks, e0, e1, p0, p1, cs);
+      if (rc != PNEC_OK) return rc;
+      pnec_batch sb = db;  // pairs [p0, p1): ragged views index absolutely, uniform ones move their bases
+      sb.num_problems = p1 - p0;
+      sb.poses = db.poses + 7 * p0;
+      if (kb->offsets) {
+        sb.offsets = kb->offsets + p0;
+      } else {
+        sb.bvs_host += 3 * e0;
+        sb.bvs_target += 3 * e0;
+        if (sb.covs_target) sb.covs_target += 9 * e0;
+        if (sb.covs_host) sb.covs_host += 9 * e0;
+      }
+      pnec_solve_out so{};
+      so.poses = static_cast<double *>(dev_ptr[0]) + 7 * p0;
+      so.status = dev_ptr[1] ? static_cast<int32_t *>(dev_ptr[1]) + p0 : nullptr;
+      so.iterations = dev_ptr[2] ? static_cast<int32_t *>(dev_ptr[2]) + p0 : nullptr;
+      so.cost = dev_ptr[3] ? static_cast<double *>(dev_ptr[3]) + p0 : nullptr;
+      so.initial_cost = dev_ptr[4] ? static_cast<double *>(dev_ptr[4]) + p0 : nullptr;
+      rc = pnec_solve_batch(h, &sb, opts, &so, cs);
+      if (rc != PNEC_OK) return rc;
+      for (int k = 0; k < 5; ++k)
+        if (host_ptr[k])
+          PNEC_CUDA(cudaMemcpyAsync(static_cast<char *>(host_ptr[k]) + sizes[k] * p0,
+                                    static_cast<char *>(dev_ptr[k]) + sizes[k] * p0, sizes[k] * (p1 - p0),
+                                    cudaMemcpyDeviceToHost, cs));
+    }
+    PNEC_CUDA(cudaEventRecord(h->ev_join[c], cs));
+  }
+  for (int c = 0; c < chunks; ++c) PNEC_CUDA(cudaStreamWaitEvent(stream, h->ev_join[c], 0));
+  PNEC_CUDA(cudaStreamSynchronize(stream));
+  scope.ok = true;
+  return PNEC_OK;
+}
+
+int pnec_frame_solve_from_keypoints_batch(pnec_handle *h, const pnec_keypoint_batch *kb, const pnec_frame_opts *opts,
+                                          const pnec_frame_out *out, void *cuda_stream) {
+  if (!h || !opts || !out) return fail(PNEC_ERR_INVALID_ARGUMENT, "NULL argument");
+  long long total = 0;
+  int rc = validate_keypoints(kb, true, &total);
+  if (rc != PNEC_OK) return rc;
+  const long long B = kb->num_problems;
+  if (B > 0 && !out->poses) return fail(PNEC_ERR_INVALID_ARGUMENT, "out->poses is NULL");
+  if (total > 0 && !opts->use_nec && !kb->target_covs2)
+    return fail(PNEC_ERR_INVALID_ARGUMENT, "target_covs2 is NULL for the PNEC pipeline");
+  if (B == 0) return PNEC_OK;
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
+  PNEC_CUDA(cudaSetDevice(h->device));
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  CallScope scope(h, stream);
+  KpStaged ks;
+  rc = kp_alloc(h, kb, total, &ks);
+  if (rc != PNEC_OK) return rc;
+  rc = kp_stage_range(h, kb, ks, 0, total, 0, B, stream);
+  if (rc != PNEC_OK) return rc;
+  pnec_batch db = kp_device_batch(h, kb, ks);
+  if (!ks.host) return pnec_frame_solve_batch(h, &db, opts, out, cuda_stream);
+  // HOST: results through device buffers of the handle
+  const size_t nb = static_cast<size_t>(B), nel = static_cast<size_t>(std::max<long long>(total, 1));
+  const size_t sizes[8] = {56, 56, 4, 4, 8, 4, 4, 4}, counts[8] = {nb, nb, nb, nb, nb, nb, nel, nb};
+  void *host_ptr[8] = {out->poses, out->es_poses, out->status, out->iterations, out->cost, out->num_inliers,
+                       out->inlier_index, out->ransac_iterations};
+  void *dev_ptr[8] = {};
+  for (int k = 0; k < 8; ++k) {
+    if (!host_ptr[k]) continue;
+    PNEC_CUDA(h->d_kp_out[k].ensure(counts[k] * sizes[k]));
+    dev_ptr[k] = h->d_kp_out[k].p;
+  }
+  pnec_frame_out fo{};
+  fo.poses = static_cast<double *>(dev_ptr[0]);
+  fo.es_poses = static_cast<double *>(dev_ptr[1]);
+  fo.status = static_cast<int32_t *>(dev_ptr[2]);
+  fo.iterations = static_cast<int32_t *>(dev_ptr[3]);
+  fo.cost = static_cast<double *>(dev_ptr[4]);
+  fo.num_inliers = static_cast<int32_t *>(dev_ptr[5]);
+  fo.inlier_index = static_cast<int32_t *>(dev_ptr[6]);
+  fo.ransac_iterations = static_cast<int32_t *>(dev_ptr[7]);
+  fo.stage_ms = out->stage_ms;
+  rc = pnec_frame_solve_batch(h, &db, opts, &fo, cuda_stream);
+  if (rc != PNEC_OK) return rc;
+  for (int k = 0; k < 8; ++k) {
+    if (!host_ptr[k]) continue;
+    if ((k == 2 || k == 3 || k == 4) && !opts->use_ceres) continue;  // untouched without the refinement
+    if (k == 6 && !opts->use_ransac) continue;                      // no inlier list without RANSAC
+    PNEC_CUDA(cudaMemcpyAsync(host_ptr[k], dev_ptr[k], counts[k] * sizes[k], cudaMemcpyDeviceToHost, stream));
+  }
+  PNEC_CUDA(cudaStreamSynchronize(stream));
   return PNEC_OK;
 }
 

@@ -12,9 +12,20 @@
 // order.  The outcome equals the sequential loop's; hypotheses of a round beyond the stopping point
 // are wasted work, which is why rounds start small.
 //
-// One CTA per frame pair, NW warps, 8 NW hypotheses per full round.  After the loop the winning model
-// selects the inliers, which are written out compacted (bearing vectors, covariances, indices) at the
-// pair's own offset: the stages that follow run on those arrays with a per-pair count.
+// Pass 1 (ransac_kernel): one CTA per frame pair, NW warps, 8 NW hypotheses per full round; clean data
+// stops after one or two rounds.  A pair that is not finished after `defer_after` iterations (many
+// outliers, or a degenerate pair that never collects inliers and runs to max_iterations) is handed
+// to pass 2, which spreads the remaining hypotheses of such pairs over the WHOLE device in
+// super-rounds (ransac_hyp_kernel: blocks of 32 hypotheses as work items of a persistent grid, as many
+// as the current k asks for; ransac_plan_kernel: the bookkeeping replayed in order, and the plan of
+// the next super-round), so a 5000-iteration pair costs a few super-rounds instead of 5000 / 8 rounds
+// of one CTA.  ransac_final_kernel then rebuilds the winning hypothesis and extracts the inliers.
+// Everything a hypothesis computes lives in ONE out-of-line function (ransac_hypothesis) and the score
+// is spelled out with explicit roundings, so all kernels produce the same bits for the same hypothesis.
+//
+// After the loop the winning model selects the inliers, which are written out compacted (bearing
+// vectors, covariances, indices) at the pair's own offset: the stages that follow run on those arrays
+// with a per-pair count.
 #pragma once
 
 #include "pnec_eigensolver.cuh"
@@ -22,6 +33,15 @@
 namespace pnec {
 
 constexpr int kRansacMaxSample = 32;
+constexpr int kRansacSuper = 1024;   // hypotheses per pair and super-round of pass 2
+constexpr int kRansacBlock = 8;      // hypotheses per work item of pass 2 (one warp: eight 4-lane groups)
+
+// what pass 1 hands to pass 2 for an unfinished pair, and what pass 2 updates
+struct RansacPairState {
+  double best[16];     // winning hypothesis so far: R (9, row-major), t (3), q (4) -- valid if best_in_state
+  double k;            // opengv's k
+  int best_count, iters, done, best_h, best_in_state, pad;
+};
 
 struct RansacArgs {
   BatchView bv;              // f1, f2 (+ ct when out_ct), poses: start rotation (R12 of the adapter)
@@ -37,6 +57,13 @@ struct RansacArgs {
   unsigned long long seed;
   long long pair_index_base; // pair b draws from the stream of pair_index_base + b
   EsLmParams lm;
+  // two passes
+  int defer_after;           // pass 1 hands over pairs unfinished after this many iterations (0: never)
+  RansacPairState *state;    // [B]
+  int *defer;                // [0] number of deferred pairs, [1] work cursor, [2] work items of the current
+                             // super-round, [3] cursor of ransac_final_kernel; the list follows at defer + 4 [B]
+  int *blk_prefix;           // [B + 1] exclusive prefix of the work items per deferred slot
+  int *hyp_count;            // [B][kRansacSuper] inlier counts of the current super-round
 };
 
 __device__ __forceinline__ unsigned long long rs_mix(unsigned long long z) {  // splitmix64 finaliser
@@ -81,217 +108,180 @@ __device__ __forceinline__ void quat_rotation(const double q[4], double R[9]) {
   R[6] = 2.0 * (x * z - y * w);       R[7] = 2.0 * (y * z + x * w);       R[8] = 1.0 - 2.0 * (x * x + y * y);
 }
 
-// EigensolverSacProblem::getSelectedDistancesToModel for one correspondence: midpoint triangulation
-// (opengv::triangulation::triangulate2) and the two 1 - cos reprojection errors.  m: R (9) then t (3).
-__device__ __forceinline__ double ransac_score(const double *m, const double f1[3], const double f2[3]) {
-  const double g[3] = {m[0] * f2[0] + m[1] * f2[1] + m[2] * f2[2], m[3] * f2[0] + m[4] * f2[1] + m[5] * f2[2],
-                       m[6] * f2[0] + m[7] * f2[1] + m[8] * f2[2]};
-  const double t[3] = {m[9], m[10], m[11]};
-  const double b0 = dot3(t, f1), b1 = dot3(t, g);
-  const double a00 = dot3(f1, f1), a10 = dot3(f1, g), a01 = -a10, a11 = -dot3(g, g);
-  const double idet = fast_rcp(a00 * a11 - a01 * a10);
-  const double l0 = (a11 * b0 - a01 * b1) * idet, l1 = (-a10 * b0 + a00 * b1) * idet;
-  double p[3], d[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    p[k] = 0.5 * (l0 * f1[k] + t[k] + l1 * g[k]);
-    d[k] = p[k] - t[k];
-  }
-  const double pp[3] = {m[0] * d[0] + m[3] * d[1] + m[6] * d[2], m[1] * d[0] + m[4] * d[1] + m[7] * d[2],
-                        m[2] * d[0] + m[5] * d[1] + m[8] * d[2]};  // R^T (p - t)
-  return (1.0 - dot3(f1, p) * rsqrt(dot3(p, p))) + (1.0 - dot3(f2, pp) * rsqrt(dot3(pp, pp)));
+// a . b with the rounding sequence spelled out (see ransac_score)
+__device__ __forceinline__ double rdot(double a0, double a1, double a2, double b0, double b1, double b2) {
+  return fma(a2, b2, fma(a1, b1, __dmul_rn(a0, b0)));
 }
 
-template <int NW>
-__global__ void __launch_bounds__(NW * 32) ransac_kernel(const __grid_constant__ RansacArgs args) {
-  constexpr int NT = NW * 32, NG = NW * 8;  // threads, 4-lane groups = hypotheses per full round
-  __shared__ double s_mom[kEsMom * NG];     // [k][g]
-  __shared__ double s_model[NG][16];        // R (9), t (3), q (4)
-  __shared__ double s_best[16];
-  __shared__ int s_front[kRansacMaxSample][NG], s_bpos[kRansacMaxSample][NG], s_bval[kRansacMaxSample][NG];
-  __shared__ int s_count[NW][NG];
-  __shared__ int s_state[4];                // best count, iterations, done, hypotheses of the next round
-  __shared__ double s_k;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, sub = tid & 3, g = tid >> 2;
-  const long long b = blockIdx.x;
-  long long s, e;
-  problem_range(args.bv, b, s, e);
-  const int n = static_cast<int>(e - s);
-  const int ns = args.sample_size;
-  const double *f1 = args.bv.f1 + 3 * s, *f2 = args.bv.f2 + 3 * s;
-  const double *pose = args.bv.poses + 7 * b;
-  const unsigned long long pair = static_cast<unsigned long long>(args.pair_index_base + b);
-  // Sophus::SE3d holds a unit quaternion
-  const double qn = 1.0 / sqrt(pose[0] * pose[0] + pose[1] * pose[1] + pose[2] * pose[2] + pose[3] * pose[3]);
-  if (n < ns || ns < 1) {  // getSamples: "Can not select %zu unique points out of %zu": no model
-    if (tid == 0) {
-      double *bp = args.best_poses + 7 * b;
-      bp[0] = pose[0] * qn; bp[1] = pose[1] * qn; bp[2] = pose[2] * qn; bp[3] = pose[3] * qn;
-      bp[4] = pose[4]; bp[5] = pose[5]; bp[6] = pose[6];
-      args.num_inliers[b] = 0;
-      args.iterations[b] = 0;
-    }
-    return;
-  }
-  // opengv::math::rot2cayley of the start rotation
-  const double c0[3] = {pose[0] / pose[3], pose[1] / pose[3], pose[2] / pose[3]};
-  if (tid == 0) {
-    s_state[0] = -1;
-    s_state[1] = 0;
-    s_state[2] = 0;
-    s_state[3] = NG < 8 ? NG : 8;  // first round: 8 hypotheses (clean data stops after a handful)
-    s_k = 1.0;
-  }
-  __syncthreads();
+// EigensolverSacProblem::getSelectedDistancesToModel for one correspondence: midpoint triangulation
+// (opengv::triangulation::triangulate2) and the two 1 - cos reprojection errors.  m: R (9) then t (3).
+// Explicit fma / __dmul_rn / __dadd_rn throughout: the inlier decision of a correspondence must not
+// depend on which kernel (pass 1, pass 2, final selection) evaluates it.
+__device__ __forceinline__ double ransac_score(const double *m, const double f1[3], const double f2[3]) {
+  const double g0 = rdot(m[0], m[1], m[2], f2[0], f2[1], f2[2]);
+  const double g1 = rdot(m[3], m[4], m[5], f2[0], f2[1], f2[2]);
+  const double g2 = rdot(m[6], m[7], m[8], f2[0], f2[1], f2[2]);
+  const double t0 = m[9], t1 = m[10], t2 = m[11];
+  const double b0 = rdot(t0, t1, t2, f1[0], f1[1], f1[2]), b1 = rdot(t0, t1, t2, g0, g1, g2);
+  const double a00 = rdot(f1[0], f1[1], f1[2], f1[0], f1[1], f1[2]);
+  const double a10 = rdot(f1[0], f1[1], f1[2], g0, g1, g2);
+  const double a11 = -rdot(g0, g1, g2, g0, g1, g2);
+  // A = [[a00, -a10], [a10, a11]], lambda = A^-1 b
+  const double idet = fast_rcp(fma(a00, a11, __dmul_rn(a10, a10)));
+  const double l0 = __dmul_rn(fma(a11, b0, __dmul_rn(a10, b1)), idet);
+  const double l1 = __dmul_rn(fma(a00, b1, -__dmul_rn(a10, b0)), idet);
+  const double p0 = __dmul_rn(0.5, fma(l1, g0, fma(l0, f1[0], t0)));
+  const double p1 = __dmul_rn(0.5, fma(l1, g1, fma(l0, f1[1], t1)));
+  const double p2 = __dmul_rn(0.5, fma(l1, g2, fma(l0, f1[2], t2)));
+  const double d0 = __dadd_rn(p0, -t0), d1 = __dadd_rn(p1, -t1), d2 = __dadd_rn(p2, -t2);
+  const double q0 = rdot(m[0], m[3], m[6], d0, d1, d2);  // R^T (p - t)
+  const double q1 = rdot(m[1], m[4], m[7], d0, d1, d2);
+  const double q2 = rdot(m[2], m[5], m[8], d0, d1, d2);
+  const double e1 = fma(-rdot(f1[0], f1[1], f1[2], p0, p1, p2), rsqrt(rdot(p0, p1, p2, p0, p1, p2)), 1.0);
+  const double e2 = fma(-rdot(f2[0], f2[1], f2[2], q0, q1, q2), rsqrt(rdot(q0, q1, q2, q0, q1, q2)), 1.0);
+  return __dadd_rn(e1, e2);
+}
 
-  for (int base = 0;;) {
-    const int round = s_state[3];
-    // ---------------------------------------------------------------- hypotheses of this round
-    const int h = base + g;                                  // == opengv's iterations_ for this hypothesis
-    const bool active = g < round && h <= args.max_iterations;
-    double x[3] = {c0[0], c0[1], c0[2]};
-    if (active) {
-      if (sub == 0) {
-        // drawIndexSample from the identity permutation: front = positions 0 .. ns-1, the touched
-        // positions beyond them in a short list
-        int nb = 0;
-        for (int i = 0; i < ns; ++i) s_front[i][g] = i;
-        for (int i = 0; i < ns; ++i) {
-          const int j = i + static_cast<int>(rs_u31(args.seed, pair, h, i) % static_cast<unsigned>(n - i));
-          const int vi = s_front[i][g];
-          if (j < ns) {
-            s_front[i][g] = s_front[j][g];
-            s_front[j][g] = vi;
-          } else {
-            int k = 0;
-            while (k < nb && s_bpos[k][g] != j) ++k;
-            if (k == nb) { s_bpos[k][g] = j; s_bval[k][g] = j; ++nb; }
-            s_front[i][g] = s_bval[k][g];
-            s_bval[k][g] = vi;
-          }
-        }
-      }
-      __syncwarp(0xfu << (lane & ~3));
-      // the 36 moment sums over the sample, in sample order: lane `sub` owns the rows p = sub and
-      // p = sub + 4 of sym(f1 f1^T) (x) sym(f2 f2^T)
-      double acc0[6] = {0, 0, 0, 0, 0, 0}, acc1[6] = {0, 0, 0, 0, 0, 0};
+// Everything one hypothesis computes (getSamples + computeModelCoefficients of iteration h), by the
+// 4-lane group `g` of its warp; ALL 32 lanes of a warp call it together (the Levenberg-Marquardt
+// loop votes across the warp), groups without work pass active = false.  Out of line: ONE body for
+// every kernel, so that a hypothesis is the same bits wherever it is evaluated.  Shared-memory
+// scratch of the calling CTA: s_mom [36][NG], s_front / s_bpos / s_bval [kRansacMaxSample][NG];
+// the model goes to model16 = R (9), t (3), q (4) (written by lane 0 of the group).
+__device__ __noinline__ void ransac_hypothesis(const double *f1, const double *f2, int n, int ns, double c0x, double c0y,
+                                               double c0z, unsigned long long seed, unsigned long long pair, int h,
+                                               double max_variation, const EsLmParams *lm, bool active, int g,
+                                               int NG, double *s_mom, int *s_front, int *s_bpos, int *s_bval,
+                                               double *model16) {
+  const int lane = threadIdx.x & 31, sub = lane & 3;
+  double x[3] = {c0x, c0y, c0z};
+  if (active) {
+    if (sub == 0) {
+      // drawIndexSample from the identity permutation: front = positions 0 .. ns-1, the touched
+      // positions beyond them in a short list
+      int nb = 0;
+      for (int i = 0; i < ns; ++i) s_front[i * NG + g] = i;
       for (int i = 0; i < ns; ++i) {
-        const int idx = s_front[i][g];
-        const double a[3] = {f1[3 * idx], f1[3 * idx + 1], f1[3 * idx + 2]};
-        const double c[3] = {f2[3 * idx], f2[3 * idx + 1], f2[3 * idx + 2]};
-        const double A[6] = {a[0] * a[0], a[0] * a[1], a[0] * a[2], a[1] * a[1], a[1] * a[2], a[2] * a[2]};
-        const double F[6] = {c[0] * c[0], c[0] * c[1], c[0] * c[2], c[1] * c[1], c[1] * c[2], c[2] * c[2]};
-        const double A0 = sub == 0 ? A[0] : sub == 1 ? A[1] : sub == 2 ? A[2] : A[3];
-        const double A1 = sub == 0 ? A[4] : A[5];
-#pragma unroll
-        for (int q = 0; q < 6; ++q) {
-          acc0[q] = fma(A0, F[q], acc0[q]);
-          acc1[q] = fma(A1, F[q], acc1[q]);
+        const int j = i + static_cast<int>(rs_u31(seed, pair, h, i) % static_cast<unsigned>(n - i));
+        const int vi = s_front[i * NG + g];
+        if (j < ns) {
+          s_front[i * NG + g] = s_front[j * NG + g];
+          s_front[j * NG + g] = vi;
+        } else {
+          int k = 0;
+          while (k < nb && s_bpos[k * NG + g] != j) ++k;
+          if (k == nb) { s_bpos[k * NG + g] = j; s_bval[k * NG + g] = j; ++nb; }
+          s_front[i * NG + g] = s_bval[k * NG + g];
+          s_bval[k * NG + g] = vi;
         }
       }
+    }
+    __syncwarp(0xfu << (lane & ~3));
+    // the 36 moment sums over the sample, in sample order: lane `sub` owns the rows p = sub and
+    // p = sub + 4 of sym(f1 f1^T) (x) sym(f2 f2^T)
+    double acc0[6] = {0, 0, 0, 0, 0, 0}, acc1[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < ns; ++i) {
+      const int idx = s_front[i * NG + g];
+      const double a[3] = {f1[3 * idx], f1[3 * idx + 1], f1[3 * idx + 2]};
+      const double c[3] = {f2[3 * idx], f2[3 * idx + 1], f2[3 * idx + 2]};
+      const double A[6] = {a[0] * a[0], a[0] * a[1], a[0] * a[2], a[1] * a[1], a[1] * a[2], a[2] * a[2]};
+      const double F[6] = {c[0] * c[0], c[0] * c[1], c[0] * c[2], c[1] * c[1], c[1] * c[2], c[2] * c[2]};
+      const double A0 = sub == 0 ? A[0] : sub == 1 ? A[1] : sub == 2 ? A[2] : A[3];
+      const double A1 = sub == 0 ? A[4] : A[5];
 #pragma unroll
       for (int q = 0; q < 6; ++q) {
-        s_mom[(6 * sub + q) * NG + g] = acc0[q];
-        if (sub < 2) s_mom[(6 * (sub + 4) + q) * NG + g] = acc1[q];
-      }
-      // computeModelCoefficients: "randomize the starting point a bit"
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        const double u = static_cast<double>(rs_u31(args.seed, pair, h, ns + d)) / 2147483647.0;
-        x[d] = c0[d] + (u - 0.5) * 2.0 * args.max_variation;
+        acc0[q] = fma(A0, F[q], acc0[q]);
+        acc1[q] = fma(A1, F[q], acc1[q]);
       }
     }
-    __syncwarp();
-    {
-      int info, nfev;
-      es_lm_group(s_mom + g, NG, args.lm, active, sub, x, info, nfev);
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      s_mom[(6 * sub + q) * NG + g] = acc0[q];
+      if (sub < 2) s_mom[(6 * (sub + 4) + q) * NG + g] = acc1[q];
     }
-    if (active) {
-      // eigensolver_main's tail: rotation = cayley2rot(x), translation along the eigenvector of the
-      // smallest eigenvalue of M(x), towards the optical flow of the sample's first correspondence
-      double M[6], t[3], lam, q[4], R[9];
-      es_compose_m(s_mom + g, NG, x, M);
-      sym3_smallest_eigvec(M, t, lam);
-      const double sc = 1.0 / sqrt(1.0 + x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
-      q[0] = x[0] * sc; q[1] = x[1] * sc; q[2] = x[2] * sc; q[3] = sc;
-      quat_rotation(q, R);
-      const int i0 = s_front[0][g];
-      const double a[3] = {f1[3 * i0], f1[3 * i0 + 1], f1[3 * i0 + 2]};
-      const double c[3] = {f2[3 * i0], f2[3 * i0 + 1], f2[3 * i0 + 2]};
-      double gg[3];
-      rot(R, c, gg);
-      const double flow = (a[0] - gg[0]) * t[0] + (a[1] - gg[1]) * t[1] + (a[2] - gg[2]) * t[2];
-      if (flow < 0.0) { t[0] = -t[0]; t[1] = -t[1]; t[2] = -t[2]; }
-      if (sub == 0) {
+    // computeModelCoefficients: "randomize the starting point a bit"
 #pragma unroll
-        for (int k = 0; k < 9; ++k) s_model[g][k] = R[k];
-        s_model[g][9] = t[0]; s_model[g][10] = t[1]; s_model[g][11] = t[2];
-        s_model[g][12] = q[0]; s_model[g][13] = q[1]; s_model[g][14] = q[2]; s_model[g][15] = q[3];
-      }
+    for (int d = 0; d < 3; ++d) {
+      const double u = static_cast<double>(rs_u31(seed, pair, h, ns + d)) / 2147483647.0;
+      x[d] += (u - 0.5) * 2.0 * max_variation;
     }
-    __syncthreads();
-    // ---------------------------------------------------------------- countWithinDistance
-    // every thread scores its correspondences against all hypotheses of the round; ballots make
-    // the counts warp-uniform
-    {
-      int cnt[NG];
-#pragma unroll
-      for (int k = 0; k < NG; ++k) cnt[k] = 0;
-      const int nh = min(round, args.max_iterations - base + 1);  // active hypotheses: 0 .. nh-1
-      for (int i0 = warp * 32; i0 < n; i0 += NT) {
-        const int i = i0 + lane;
-        const bool valid = i < n;
-        const int ii = valid ? i : n - 1;
-        const double a[3] = {f1[3 * ii], f1[3 * ii + 1], f1[3 * ii + 2]};
-        const double c[3] = {f2[3 * ii], f2[3 * ii + 1], f2[3 * ii + 2]};
-#pragma unroll
-        for (int k = 0; k < NG; ++k) {
-          if (k < nh) {  // warp-uniform
-            const bool in = valid && ransac_score(s_model[k], a, c) < args.threshold;
-            cnt[k] += __popc(__ballot_sync(0xffffffffu, in));
-          }
-        }
-      }
-      if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < NG; ++k) s_count[warp][k] = cnt[k];
-      }
-    }
-    __syncthreads();
-    // ---------------------------------------------------------------- computeModel's bookkeeping, in order
-    if (tid == 0) {
-      int best = s_state[0], iters = s_state[1], done = 0;
-      double k = s_k;
-      for (int j = 0; j < round; ++j) {
-        if (!(static_cast<double>(iters) < k)) { done = 1; break; }
-        int count = 0;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) count += s_count[w][j];
-        if (count > best) {
-          best = count;
-#pragma unroll
-          for (int m = 0; m < 16; ++m) s_best[m] = s_model[j][m];
-          const double wfrac = static_cast<double>(count) / static_cast<double>(n);
-          double p_no = 1.0 - pow(wfrac, static_cast<double>(ns));
-          p_no = fmax(DBL_EPSILON, p_no);
-          p_no = fmin(1.0 - DBL_EPSILON, p_no);
-          k = log(1.0 - args.probability) / log(p_no);
-        }
-        ++iters;
-        if (iters > args.max_iterations) { done = 1; break; }
-      }
-      if (!done && !(static_cast<double>(iters) < k)) done = 1;
-      s_state[0] = best; s_state[1] = iters; s_state[2] = done;
-      s_state[3] = min(NG, 2 * round);
-      s_k = k;
-    }
-    __syncthreads();
-    if (s_state[2]) break;
-    base += round;
   }
+  __syncwarp();
+  {
+    int info, nfev;
+    es_lm_group(s_mom + g, NG, *lm, active, sub, x, info, nfev);
+  }
+  if (active) {
+    // eigensolver_main's tail: rotation = cayley2rot(x), translation along the eigenvector of the
+    // smallest eigenvalue of M(x), towards the optical flow of the sample's first correspondence
+    double M[6], t[3], lam, q[4], R[9];
+    es_compose_m(s_mom + g, NG, x, M);
+    sym3_smallest_eigvec(M, t, lam);
+    const double sc = 1.0 / sqrt(1.0 + x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+    q[0] = x[0] * sc; q[1] = x[1] * sc; q[2] = x[2] * sc; q[3] = sc;
+    quat_rotation(q, R);
+    const int i0 = s_front[g];
+    const double a[3] = {f1[3 * i0], f1[3 * i0 + 1], f1[3 * i0 + 2]};
+    const double c[3] = {f2[3 * i0], f2[3 * i0 + 1], f2[3 * i0 + 2]};
+    double gg[3];
+    rot(R, c, gg);
+    const double flow = (a[0] - gg[0]) * t[0] + (a[1] - gg[1]) * t[1] + (a[2] - gg[2]) * t[2];
+    if (flow < 0.0) { t[0] = -t[0]; t[1] = -t[1]; t[2] = -t[2]; }
+    if (sub == 0) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) model16[k] = R[k];
+      model16[9] = t[0]; model16[10] = t[1]; model16[11] = t[2];
+      model16[12] = q[0]; model16[13] = q[1]; model16[14] = q[2]; model16[15] = q[3];
+    }
+  }
+}
 
-  // -------------------------------------------------------------------- selectWithinDistance + InlierExtraction
-  __shared__ int s_wcnt[NW];
+// opengv's k after a new best model with `count` inliers of n
+__device__ __forceinline__ double ransac_k(int count, int n, int ns, double probability) {
+  const double w = static_cast<double>(count) / static_cast<double>(n);
+  double p_no = 1.0 - pow(w, static_cast<double>(ns));
+  p_no = fmax(DBL_EPSILON, p_no);
+  p_no = fmin(1.0 - DBL_EPSILON, p_no);
+  return log(1.0 - probability) / log(p_no);
+}
+
+// countWithinDistance of NH models (shared memory, 16 doubles apart) over the pair's correspondences
+// by the whole CTA; per-warp counts to s_count[warp * NH + k] (ballots make them warp-uniform).
+template <int NW, int NH>
+__device__ __forceinline__ void ransac_count(const double *f1, const double *f2, int n, const double *s_model, int nh,
+                                             double threshold, int *s_count, int warp) {
+  constexpr int NT = NW * 32;
+  const int lane = threadIdx.x & 31;
+  int cnt[NH];
+#pragma unroll
+  for (int k = 0; k < NH; ++k) cnt[k] = 0;
+  for (int i0 = warp * 32; i0 < n; i0 += NT) {
+    const int i = i0 + lane;
+    const bool valid = i < n;
+    const int ii = valid ? i : n - 1;
+    const double a[3] = {f1[3 * ii], f1[3 * ii + 1], f1[3 * ii + 2]};
+    const double c[3] = {f2[3 * ii], f2[3 * ii + 1], f2[3 * ii + 2]};
+#pragma unroll
+    for (int k = 0; k < NH; ++k) {
+      if (k < nh) {  // warp-uniform
+        const bool in = valid && ransac_score(s_model + 16 * k, a, c) < threshold;
+        cnt[k] += __popc(__ballot_sync(0xffffffffu, in));
+      }
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NH; ++k) s_count[warp * NH + k] = cnt[k];
+  }
+}
+
+// selectWithinDistance(best model) + InlierExtraction (pnec.cc:210-229) by the whole CTA; writes the
+// pair's outputs.  s_best: the winning model in shared memory.
+template <int NW>
+__device__ __forceinline__ void ransac_select(const RansacArgs &args, long long b, long long s, int n, const double *f1,
+                                              const double *f2, const double *s_best, int iterations, int *s_wcnt) {
+  constexpr int NT = NW * 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int running = 0;
   for (int i0 = 0; i0 < n; i0 += NT) {
     const int i = i0 + tid;
@@ -326,16 +316,294 @@ __global__ void __launch_bounds__(NW * 32) ransac_kernel(const __grid_constant__
     __syncthreads();
   }
   if (tid == 0) {
+    const double *pose = args.bv.poses + 7 * b;
     double *bp = args.best_poses + 7 * b;
     if (running > 0) {
       bp[0] = s_best[12]; bp[1] = s_best[13]; bp[2] = s_best[14]; bp[3] = s_best[15];
       bp[4] = s_best[9]; bp[5] = s_best[10]; bp[6] = s_best[11];
     } else {  // a best model without inliers: undefined in the reference; the start pose here (as the oracle)
+      const double qn = 1.0 / sqrt(pose[0] * pose[0] + pose[1] * pose[1] + pose[2] * pose[2] + pose[3] * pose[3]);
       bp[0] = pose[0] * qn; bp[1] = pose[1] * qn; bp[2] = pose[2] * qn; bp[3] = pose[3] * qn;
       bp[4] = pose[4]; bp[5] = pose[5]; bp[6] = pose[6];
     }
     args.num_inliers[b] = running;
-    args.iterations[b] = s_state[1];
+    args.iterations[b] = iterations;
+  }
+}
+
+// ------------------------------------------------------------------ pass 1: one CTA per pair
+
+template <int NW, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB) ransac_kernel(const __grid_constant__ RansacArgs args) {
+  constexpr int NG = NW * 8;  // 4-lane groups = hypotheses per full round
+  __shared__ double s_mom[kEsMom * NG];     // [k][g]
+  __shared__ double s_model[NG * 16];       // R (9), t (3), q (4)
+  __shared__ double s_best[16];
+  __shared__ int s_front[kRansacMaxSample * NG], s_bpos[kRansacMaxSample * NG], s_bval[kRansacMaxSample * NG];
+  __shared__ int s_count[NW * NG];
+  __shared__ int s_state[5];                // best count, iterations, done, hypotheses of the next round, best h
+  __shared__ int s_wcnt[NW];
+  __shared__ double s_k;
+  const int tid = threadIdx.x, g = tid >> 2;
+  const long long b = blockIdx.x;
+  long long s, e;
+  problem_range(args.bv, b, s, e);
+  const int n = static_cast<int>(e - s);
+  const int ns = args.sample_size;
+  const double *f1 = args.bv.f1 + 3 * s, *f2 = args.bv.f2 + 3 * s;
+  const double *pose = args.bv.poses + 7 * b;
+  const unsigned long long pair = static_cast<unsigned long long>(args.pair_index_base + b);
+  if (n < ns || ns < 1) {  // getSamples: "Can not select %zu unique points out of %zu": no model
+    if (tid == 0) {
+      // Sophus::SE3d holds a unit quaternion
+      const double qn = 1.0 / sqrt(pose[0] * pose[0] + pose[1] * pose[1] + pose[2] * pose[2] + pose[3] * pose[3]);
+      double *bp = args.best_poses + 7 * b;
+      bp[0] = pose[0] * qn; bp[1] = pose[1] * qn; bp[2] = pose[2] * qn; bp[3] = pose[3] * qn;
+      bp[4] = pose[4]; bp[5] = pose[5]; bp[6] = pose[6];
+      args.num_inliers[b] = 0;
+      args.iterations[b] = 0;
+    }
+    return;
+  }
+  // opengv::math::rot2cayley of the start rotation
+  const double c0[3] = {pose[0] / pose[3], pose[1] / pose[3], pose[2] / pose[3]};
+  if (tid == 0) {
+    s_state[0] = -1;
+    s_state[1] = 0;
+    s_state[2] = 0;
+    s_state[3] = NG < 8 ? NG : 8;  // first round: 8 hypotheses (clean data stops after a handful)
+    s_state[4] = -1;
+    s_k = 1.0;
+  }
+  __syncthreads();
+
+  for (int base = 0;;) {
+    const int round = s_state[3];
+    const int h = base + g;  // == opengv's iterations_ for this hypothesis
+    const bool active = g < round && h <= args.max_iterations;
+    ransac_hypothesis(f1, f2, n, ns, c0[0], c0[1], c0[2], args.seed, pair, h, args.max_variation, &args.lm, active, g,
+                      NG, s_mom, s_front, s_bpos, s_bval, s_model + 16 * g);
+    __syncthreads();
+    ransac_count<NW, NG>(f1, f2, n, s_model, min(round, args.max_iterations - base + 1), args.threshold, s_count,
+                         tid >> 5);
+    __syncthreads();
+    // computeModel's bookkeeping, in order
+    if (tid == 0) {
+      int best = s_state[0], iters = s_state[1], done = 0;
+      double k = s_k;
+      for (int j = 0; j < round; ++j) {
+        if (!(static_cast<double>(iters) < k)) { done = 1; break; }
+        int count = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) count += s_count[w * NG + j];
+        if (count > best) {
+          best = count;
+          s_state[4] = base + j;
+#pragma unroll
+          for (int m = 0; m < 16; ++m) s_best[m] = s_model[16 * j + m];
+          k = ransac_k(count, n, ns, args.probability);
+        }
+        ++iters;
+        if (iters > args.max_iterations) { done = 1; break; }
+      }
+      if (!done && !(static_cast<double>(iters) < k)) done = 1;
+      s_state[0] = best; s_state[1] = iters; s_state[2] = done;
+      s_state[3] = min(NG, 2 * round);
+      s_k = k;
+    }
+    __syncthreads();
+    if (s_state[2]) break;
+    base += round;
+    if (args.defer_after > 0 && s_state[1] >= args.defer_after) {
+      // unfinished: the rest of this pair's hypotheses are spread over the device by pass 2
+      if (tid == 0) {
+        RansacPairState &st = args.state[b];
+#pragma unroll
+        for (int m = 0; m < 16; ++m) st.best[m] = s_best[m];
+        st.k = s_k;
+        st.best_count = s_state[0];
+        st.iters = s_state[1];
+        st.done = 0;
+        st.best_h = s_state[4];
+        st.best_in_state = 1;
+        args.defer[4 + atomicAdd(args.defer, 1)] = static_cast<int>(b);
+      }
+      return;
+    }
+  }
+  ransac_select<NW>(args, b, s, n, f1, f2, s_best, s_state[1], s_wcnt);
+}
+
+// ------------------------------------------------------------------ pass 2
+
+// Hypotheses a deferred pair gets in the next super-round, as work items of kRansacBlock (0 when done):
+// what the current k still asks for, but never more than it has consumed so far (and at most
+// kRansacSuper).  k is a poor predictor early on -- with outliers the first good model typically drops
+// it from thousands to below a hundred -- so the speculation doubles instead of trusting it: the
+// hypotheses computed stay within twice those the sequential loop consumes.
+__host__ __device__ __forceinline__ int ransac_grant(int iters, int max_iterations) {
+  const int grow = iters > 4 * kRansacBlock ? iters : 4 * kRansacBlock;
+  const int left = max_iterations + 1 - iters;
+  const int cap = grow < kRansacSuper ? grow : kRansacSuper;
+  return left < cap ? left : cap;
+}
+__device__ __forceinline__ int ransac_blocks_wanted(const RansacPairState &st, int max_iterations) {
+  if (st.done) return 0;
+  const double want_d = ceil(st.k) - static_cast<double>(st.iters);
+  const int cap = ransac_grant(st.iters, max_iterations);
+  int want = want_d > static_cast<double>(cap) ? cap : static_cast<int>(want_d);
+  want = max(1, min(want, cap));
+  return (want + kRansacBlock - 1) / kRansacBlock;
+}
+
+// One CTA, after pass 1 and after every ransac_hyp_kernel: replays the bookkeeping over the counts of
+// the super-round that just ran (first call: none), then plans the next one (work items per slot,
+// their exclusive prefix, the total) and rewinds the work cursor.
+__global__ void __launch_bounds__(1024) ransac_plan_kernel(const __grid_constant__ RansacArgs args, int have_counts) {
+  __shared__ int s_scan[1024];
+  __shared__ int s_running;
+  const int tid = threadIdx.x;
+  const int count = args.defer[0];
+  const int *list = args.defer + 4;
+  if (tid == 0) s_running = 0;
+  __syncthreads();
+  for (int base = 0; base < count; base += 1024) {
+    const int slot = base + tid;
+    int want = 0;
+    if (slot < count) {
+      const long long b = list[slot];
+      RansacPairState &st = args.state[b];
+      if (have_counts && !st.done) {
+        long long s, e;
+        problem_range(args.bv, b, s, e);
+        const int n = static_cast<int>(e - s);
+        const int nh = (args.blk_prefix[slot + 1] - args.blk_prefix[slot]) * kRansacBlock;
+        const int *cnt = args.hyp_count + static_cast<long long>(slot) * kRansacSuper;
+        int best = st.best_count, iters = st.iters, done = 0, best_h = st.best_h, in_state = st.best_in_state;
+        const int first = iters;
+        double k = st.k;
+        for (int j = 0; j < nh; ++j) {
+          if (!(static_cast<double>(iters) < k)) { done = 1; break; }
+          const int c = cnt[j];
+          if (c > best) {
+            best = c;
+            best_h = first + j;
+            in_state = 0;
+            k = ransac_k(c, n, args.sample_size, args.probability);
+          }
+          ++iters;
+          if (iters > args.max_iterations) { done = 1; break; }
+        }
+        if (!done && !(static_cast<double>(iters) < k)) done = 1;
+        st.best_count = best; st.iters = iters; st.done = done; st.best_h = best_h; st.best_in_state = in_state;
+        st.k = k;
+      }
+      want = ransac_blocks_wanted(st, args.max_iterations);
+    }
+    // exclusive scan of `want` over this chunk of slots
+    s_scan[tid] = want;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      const int v = tid >= o ? s_scan[tid - o] : 0;
+      __syncthreads();
+      s_scan[tid] += v;
+      __syncthreads();
+    }
+    if (slot < count) args.blk_prefix[slot] = s_running + s_scan[tid] - want;
+    __syncthreads();
+    if (tid == 1023) s_running += s_scan[1023];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    args.blk_prefix[count] = s_running;
+    args.defer[1] = 0;
+    args.defer[2] = s_running;
+    args.defer[3] = 0;
+  }
+}
+
+// Persistent grid of INDEPENDENT warps: a work item is one block of 8 hypotheses of one deferred pair
+// (the eight 4-lane groups of a warp, as in pass 1 with one warp per pair), scored against all of the
+// pair's correspondences by the same warp.  No CTA-wide barrier: a warp whose Levenberg-Marquardt runs
+// long holds up nobody else.
+template <int WPC, int MINB>
+__global__ void __launch_bounds__(WPC * 32, MINB) ransac_hyp_kernel(const __grid_constant__ RansacArgs args) {
+  constexpr int NG = 8;
+  __shared__ double s_mom[WPC][kEsMom * NG];
+  __shared__ double s_model[WPC][NG * 16];
+  __shared__ int s_front[WPC][kRansacMaxSample * NG], s_bpos[WPC][kRansacMaxSample * NG], s_bval[WPC][kRansacMaxSample * NG];
+  __shared__ int s_count[WPC][NG];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2;
+  const int total = args.defer[2], count = args.defer[0];
+  const int *list = args.defer + 4;
+  for (;;) {
+    int w = 0;
+    if (lane == 0) w = atomicAdd(args.defer + 1, 1);
+    w = __shfl_sync(0xffffffffu, w, 0);
+    if (w >= total) return;
+    // slot with blk_prefix[slot] <= w < blk_prefix[slot + 1]
+    int lo = 0, hi = count;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (args.blk_prefix[mid] <= w) lo = mid; else hi = mid;
+    }
+    const int slot = lo, blk = w - args.blk_prefix[slot];
+    const long long b = list[slot];
+    long long s, e;
+    problem_range(args.bv, b, s, e);
+    const int n = static_cast<int>(e - s);
+    const double *f1 = args.bv.f1 + 3 * s, *f2 = args.bv.f2 + 3 * s;
+    const double *pose = args.bv.poses + 7 * b;
+    const int first = args.state[b].iters + blk * kRansacBlock;
+    const int h = first + g;
+    const bool active = h <= args.max_iterations;
+    ransac_hypothesis(f1, f2, n, args.sample_size, pose[0] / pose[3], pose[1] / pose[3], pose[2] / pose[3], args.seed,
+                      static_cast<unsigned long long>(args.pair_index_base + b), h, args.max_variation, &args.lm, active,
+                      g, NG, s_mom[warp], s_front[warp], s_bpos[warp], s_bval[warp], s_model[warp] + 16 * g);
+    __syncwarp();
+    const int nh = min(NG, args.max_iterations - first + 1);
+    ransac_count<1, NG>(f1, f2, n, s_model[warp], nh, args.threshold, s_count[warp], 0);
+    __syncwarp();
+    if (lane < NG)
+      args.hyp_count[static_cast<long long>(slot) * kRansacSuper + blk * kRansacBlock + lane] = lane < nh ? s_count[warp][lane] : 0;
+    __syncwarp();
+  }
+}
+
+// Persistent grid over the deferred pairs: rebuild the winning hypothesis when pass 2 found it (the
+// same out-of-line function: the same bits the count was made with), then the inlier extraction.
+__global__ void __launch_bounds__(128) ransac_final_kernel(const __grid_constant__ RansacArgs args) {
+  constexpr int NW = 4, NG = 32;
+  __shared__ double s_mom[kEsMom * NG];
+  __shared__ double s_best[16];
+  __shared__ int s_front[kRansacMaxSample * NG], s_bpos[kRansacMaxSample * NG], s_bval[kRansacMaxSample * NG];
+  __shared__ int s_wcnt[NW];
+  __shared__ int s_work;
+  const int tid = threadIdx.x, g = tid >> 2;
+  const int count = args.defer[0];
+  const int *list = args.defer + 4;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_work = atomicAdd(args.defer + 3, 1);
+    __syncthreads();
+    const int slot = s_work;
+    if (slot >= count) return;
+    const long long b = list[slot];
+    const RansacPairState &st = args.state[b];
+    long long s, e;
+    problem_range(args.bv, b, s, e);
+    const int n = static_cast<int>(e - s);
+    const double *f1 = args.bv.f1 + 3 * s, *f2 = args.bv.f2 + 3 * s;
+    const double *pose = args.bv.poses + 7 * b;
+    if (st.best_in_state) {
+      if (tid < 16) s_best[tid] = st.best[tid];
+    } else if (tid < 32) {  // warp 0, group 0 recomputes hypothesis best_h
+      ransac_hypothesis(f1, f2, n, args.sample_size, pose[0] / pose[3], pose[1] / pose[3], pose[2] / pose[3], args.seed,
+                        static_cast<unsigned long long>(args.pair_index_base + b), st.best_h, args.max_variation,
+                        &args.lm, g == 0, g, NG, s_mom, s_front, s_bpos, s_bval, s_best);
+    }
+    __syncthreads();
+    ransac_select<NW>(args, b, s, n, f1, f2, s_best, st.iters, s_wcnt);
   }
 }
 
