@@ -95,13 +95,22 @@ typedef struct pnec_solver_opts {
   double max_lm_diagonal;                    /* 1e32                          */
 } pnec_solver_opts;
 
+/* Layout of the covariance arrays.  The path only ever forms x^T S x, so only sym(S) matters:
+ * PACKED carries exactly that, (xx, (xy+yx)/2, (xz+zx)/2, yy, (yz+zy)/2, zz) per correspondence,
+ * 48 bytes instead of 72 over the host link (96 instead of 120 per correspondence), and gives
+ * bit-identical results (the kernels reduce a full matrix to the same six numbers on load). */
+typedef enum pnec_cov_layout {
+  PNEC_COV_FULL = 0,   /* double[n][9], column-major 3x3 == std::vector<Eigen::Matrix3d> */
+  PNEC_COV_PACKED = 1  /* double[n][6], symmetric part                                   */
+} pnec_cov_layout;
+
 /* A batch of independent frame pairs. */
 typedef struct pnec_batch {
   int64_t num_problems;      /* B                                             */
   int64_t n_per_problem;     /* uniform N when offsets == NULL                */
   const int64_t *offsets;    /* B+1 entries, HOST pointer always, or NULL     */
   int32_t memspace;          /* pnec_memspace of every pointer below          */
-  int32_t reserved;
+  int32_t cov_layout;        /* pnec_cov_layout of covs_target / covs_host    */
   const double *bvs_host;    /* [total][3]  f1, frame-1 ("host") bearings     */
   const double *bvs_target;  /* [total][3]  f2, frame-2 ("target") bearings   */
   const double *covs_target; /* [total][9]  TARGET, SYMMETRIC; HOST uses it too

@@ -90,7 +90,7 @@ class _Batch(ctypes.Structure):
         ("n_per_problem", ctypes.c_int64),
         ("offsets", ctypes.c_void_p),
         ("memspace", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("cov_layout", ctypes.c_int32),
         ("bvs_host", ctypes.c_void_p),
         ("bvs_target", ctypes.c_void_p),
         ("covs_target", ctypes.c_void_p),
@@ -363,6 +363,7 @@ class Handle:
                     raise PnecError("tensor is on a different device than the handle")
                 return t
 
+            packed = ct is not None and ct.dim() == 2 and ct.shape[1] == 6
             f1, f2, ct, ch, poses = (dev(x, None) for x in (f1, f2, ct, ch, poses))
             ptr = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
             total = f1.numel() // 3
@@ -371,8 +372,10 @@ class Handle:
         else:
             f1 = self._prep_host(f1, (3,))
             f2 = self._prep_host(f2, (3,))
-            ct = self._prep_host(ct, (9,))
-            ch = self._prep_host(ch, (9,))
+            # covariances: (total, 9) / (total, 3, 3) column-major 3x3, or (total, 6) packed symmetric
+            packed = ct is not None and np.asarray(ct).ndim == 2 and np.asarray(ct).shape[1] == 6
+            ct = self._prep_host(ct, (6,) if packed else (9,))
+            ch = self._prep_host(ch, (6,) if packed else (9,))
             poses = self._prep_host(poses, (7,))
             ptr = lambda a: None if a is None else ctypes.c_void_p(a.ctypes.data)
             total = f1.shape[0]
@@ -384,9 +387,11 @@ class Handle:
             raise PnecError("bvs_host and bvs_target differ in size")
         # the C side cannot see array lengths: an undersized covariance or pose array would be read
         # out of bounds there
+        per = 6 if packed else 9
         for name, arr in (("covs_target", ct), ("covs_host", ch)):
-            if arr is not None and size(arr) != total * 9:
-                raise PnecError(f"{name} must hold 9 doubles per correspondence ({total * 9}), got {size(arr)}")
+            if arr is not None and size(arr) != total * per:
+                raise PnecError(f"{name} must hold {per} doubles per correspondence ({total * per}), got {size(arr)}")
+        b.cov_layout = 1 if packed else 0
         if poses is not None and size(poses) != B * 7:
             raise PnecError("poses must hold 7 doubles per frame pair")
         b.num_problems = B

@@ -266,6 +266,17 @@ __global__ void __launch_bounds__(128) keypoint_kernel(const __grid_constant__ K
   }
 }
 
+// PNEC_COV_PACKED -> the 3x3 layout the kernels stream (pack_sym of the result returns the input bits)
+__global__ void __launch_bounds__(256) expand_covs_kernel(const double *packed, double *full, long long first,
+                                                          long long count) {
+  const long long i = first + static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= first + count) return;
+  const double *s = packed + 6 * i;
+  double *c = full + 9 * i;
+  const double xx = s[0], xy = s[1], xz = s[2], yy = s[3], yz = s[4], zz = s[5];
+  c[0] = xx; c[1] = xy; c[2] = xz; c[3] = xy; c[4] = yy; c[5] = yz; c[6] = xz; c[7] = yz; c[8] = zz;
+}
+
 // Frame2Frame::GetFeatures (src/rel_pose_estimation/frame2frame.cc:359-392) on the device: the solver's
 // inputs of `total` correspondences from the keypoints of the two frames -- pixel position and 2x2
 // image covariance, the fields a pnec::features::KeyPoint is constructed from (keypoints.cc:42-62) --

@@ -278,6 +278,7 @@ struct pnec_handle {
   DevBuf d_rs_best, d_rs_cnt, d_rs_iters, d_rs_idx;  // winning models [B][7], counts, iterations, indices
   DevBuf d_rs_state, d_rs_defer, d_rs_prefix, d_rs_hyp;  // pass 2 of the RANSAC stage (pnec_ransac.cuh)
   DevBuf d_kp_hp, d_kp_tp, d_kp_hc, d_kp_tc, d_kp_hi, d_kp_ti;  // keypoint tables and match indices (HOST callers)
+  DevBuf d_pk_ct, d_pk_ch;  // PNEC_COV_PACKED covariances of HOST callers before expansion
   DevBuf d_kp_out[8];  // device outputs of the from-keypoints entry points for HOST callers
   static constexpr int kMaxChunks = 8;
   static constexpr int kMaxRounds = 64;
@@ -349,6 +350,8 @@ int validate_batch(const pnec_batch *b, int variant, bool need_poses) {
     return fail(PNEC_ERR_INVALID_ARGUMENT, "n_per_problem < 0");
   if (b->memspace != PNEC_MEM_HOST && b->memspace != PNEC_MEM_DEVICE)
     return fail(PNEC_ERR_INVALID_ARGUMENT, "unknown memspace");
+  if (b->cov_layout != PNEC_COV_FULL && b->cov_layout != PNEC_COV_PACKED)
+    return fail(PNEC_ERR_INVALID_ARGUMENT, "unknown cov_layout");
   if (variant < PNEC_VARIANT_NEC || variant > PNEC_VARIANT_SYMMETRIC)
     return fail(PNEC_ERR_INVALID_ARGUMENT, "unknown residual variant");
   // grids are one CTA per frame pair and the kernels index a pair's correspondences with int
@@ -407,6 +410,7 @@ int stage_alloc(pnec_handle *h, const pnec_batch *b, int variant, cudaStream_t s
   }
   const bool need_ct = variant != PNEC_VARIANT_NEC;
   const bool need_ch = variant == PNEC_VARIANT_SYMMETRIC;
+  const bool packed = b->cov_layout == PNEC_COV_PACKED;
   if (b->memspace == PNEC_MEM_HOST) {
     const size_t nel = static_cast<size_t>(total);
     PNEC_CUDA(h->d_f1.ensure(nel * 24));
@@ -414,6 +418,8 @@ int stage_alloc(pnec_handle *h, const pnec_batch *b, int variant, cudaStream_t s
     PNEC_CUDA(h->d_poses.ensure(static_cast<size_t>(B) * 56));
     if (need_ct) PNEC_CUDA(h->d_ct.ensure(nel * 72));
     if (need_ch) PNEC_CUDA(h->d_ch.ensure(nel * 72));
+    if (packed && need_ct) PNEC_CUDA(h->d_pk_ct.ensure(nel * 48));
+    if (packed && need_ch) PNEC_CUDA(h->d_pk_ch.ensure(nel * 48));
     bv.f1 = static_cast<const double *>(h->d_f1.p);
     bv.f2 = static_cast<const double *>(h->d_f2.p);
     bv.ct = need_ct ? static_cast<const double *>(h->d_ct.p) : nullptr;
@@ -425,16 +431,23 @@ int stage_alloc(pnec_handle *h, const pnec_batch *b, int variant, cudaStream_t s
     bv.ct = need_ct ? b->covs_target : nullptr;
     bv.ch = need_ch ? b->covs_host : nullptr;
     bv.poses = b->poses;
+    if (packed) {  // expanded into the handle's buffers by stage_copy
+      const size_t nel = static_cast<size_t>(std::max<long long>(total, 1));
+      if (need_ct) { PNEC_CUDA(h->d_ct.ensure(nel * 72)); bv.ct = static_cast<const double *>(h->d_ct.p); }
+      if (need_ch) { PNEC_CUDA(h->d_ch.ensure(nel * 72)); bv.ch = static_cast<const double *>(h->d_ch.p); }
+    }
   }
   out->bv = bv;
   out->max_n = max_n;
   return PNEC_OK;
 }
 
-// H2D of pairs [p0, p1) of a HOST batch into the buffers of stage_alloc (no-op for DEVICE batches).
+// H2D of pairs [p0, p1) of a HOST batch into the buffers of stage_alloc; PNEC_COV_PACKED covariances
+// (HOST or DEVICE) are expanded to the 3x3 layout the kernels stream.  Otherwise a no-op for DEVICE batches.
 int stage_copy(pnec_handle *h, const pnec_batch *b, int variant, long long p0, long long p1,
                cudaStream_t stream) {
-  if (b->memspace != PNEC_MEM_HOST || p1 <= p0) return PNEC_OK;
+  const bool host = b->memspace == PNEC_MEM_HOST, packed = b->cov_layout == PNEC_COV_PACKED;
+  if ((!host && !packed) || p1 <= p0) return PNEC_OK;
   const long long e0 = b->offsets ? b->offsets[p0] : p0 * b->n_per_problem;
   const long long e1 = b->offsets ? b->offsets[p1] : p1 * b->n_per_problem;
   const size_t nel = static_cast<size_t>(e1 - e0);
@@ -445,13 +458,32 @@ int stage_copy(pnec_handle *h, const pnec_batch *b, int variant, long long p0, l
       return h->stager.h2d(dst, src, bytes, stream);
     return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream);
   };
+  auto covs = [&](const double *src, DevBuf &pk, DevBuf &full) -> int {
+    if (!packed) {
+      PNEC_CUDA(h2d(at(full.p, e0 * 72), src + 9 * e0, nel * 72));
+      return PNEC_OK;
+    }
+    const double *dsrc = src;
+    if (host) {
+      PNEC_CUDA(h2d(at(pk.p, e0 * 48), src + 6 * e0, nel * 48));
+      dsrc = static_cast<const double *>(pk.p);
+    }
+    expand_covs_kernel<<<static_cast<unsigned>((nel + 255) / 256), 256, 0, stream>>>(dsrc, static_cast<double *>(full.p), e0,
+                                                                                  static_cast<long long>(nel));
+    PNEC_CUDA(cudaGetLastError());
+    h->launches++;
+    return PNEC_OK;
+  };
   if (nel) {
-    PNEC_CUDA(h2d(at(h->d_f1.p, e0 * 24), b->bvs_host + 3 * e0, nel * 24));
-    PNEC_CUDA(h2d(at(h->d_f2.p, e0 * 24), b->bvs_target + 3 * e0, nel * 24));
-    if (variant != PNEC_VARIANT_NEC) PNEC_CUDA(h2d(at(h->d_ct.p, e0 * 72), b->covs_target + 9 * e0, nel * 72));
-    if (variant == PNEC_VARIANT_SYMMETRIC) PNEC_CUDA(h2d(at(h->d_ch.p, e0 * 72), b->covs_host + 9 * e0, nel * 72));
+    if (host) {
+      PNEC_CUDA(h2d(at(h->d_f1.p, e0 * 24), b->bvs_host + 3 * e0, nel * 24));
+      PNEC_CUDA(h2d(at(h->d_f2.p, e0 * 24), b->bvs_target + 3 * e0, nel * 24));
+    }
+    int rc;
+    if (variant != PNEC_VARIANT_NEC && (rc = covs(b->covs_target, h->d_pk_ct, h->d_ct)) != PNEC_OK) return rc;
+    if (variant == PNEC_VARIANT_SYMMETRIC && (rc = covs(b->covs_host, h->d_pk_ch, h->d_ch)) != PNEC_OK) return rc;
   }
-  if (b->poses)
+  if (host && b->poses)
     PNEC_CUDA(cudaMemcpyAsync(at(h->d_poses.p, p0 * 56), b->poses + 7 * p0, static_cast<size_t>(p1 - p0) * 56,
                               cudaMemcpyHostToDevice, stream));
   return PNEC_OK;
@@ -1111,6 +1143,8 @@ void pnec_destroy(pnec_handle *h) {
                     &h->d_kp_hp, &h->d_kp_tp, &h->d_kp_hc, &h->d_kp_tc, &h->d_kp_hi, &h->d_kp_ti};
   for (DevBuf *b : bufs) b->release();
   for (DevBuf &b : h->d_kp_out) b.release();
+  h->d_pk_ct.release();
+  h->d_pk_ch.release();
   for (int i = 0; i < pnec_handle::kMaxChunks; ++i) {
     if (h->side[i]) cudaStreamDestroy(h->side[i]);
     if (h->lm_side[i]) cudaStreamDestroy(h->lm_side[i]);
