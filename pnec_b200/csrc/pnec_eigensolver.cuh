@@ -311,7 +311,14 @@ __device__ __forceinline__ double pick3(const double v[3], int k) { return k == 
 __device__ __forceinline__ void put3(double v[3], int k, double x) {
   if (k == 0) v[0] = x; else if (k == 1) v[1] = x; else v[2] = x;
 }
-__device__ __forceinline__ double enorm3(const double v[3]) { return sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
+// The MINPACK logic runs on every lane of a 4-lane group and the groups of a warp sit in different
+// states, so its cost is paid by the whole warp in almost every turn of the loop: divisions and square
+// roots (each a ~40-instruction sequence with a slow-path branch in IEEE form) go through the
+// branch-free reciprocal / reciprocal-square-root forms (<= 2 ulp).  Operands that can be zero are
+// guarded by MINPACK's own tests before they are used as divisors.
+__device__ __forceinline__ double es_div(double a, double b) { return a * fast_rcp(b); }
+__device__ __forceinline__ double es_sqrt(double x) { return fast_sqrt(x); }
+__device__ __forceinline__ double enorm3(const double v[3]) { return es_sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
 
 // qrfac with column pivoting (a[i][j], row i, column j).  On exit: strict upper triangle = R,
 // rdiag = diagonal of R, lower trapezoid = Householder vectors, acnorm = input column norms.
@@ -319,7 +326,7 @@ __device__ __forceinline__ void es_qrfac(double a[3][3], int ipvt[3], double rdi
   double wa[3];
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
-    acnorm[j] = sqrt(a[0][j] * a[0][j] + a[1][j] * a[1][j] + a[2][j] * a[2][j]);
+    acnorm[j] = es_sqrt(a[0][j] * a[0][j] + a[1][j] * a[1][j] + a[2][j] * a[2][j]);
     rdiag[j] = acnorm[j];
     wa[j] = acnorm[j];
     ipvt[j] = j;
@@ -343,29 +350,33 @@ __device__ __forceinline__ void es_qrfac(double a[3][3], int ipvt[3], double rdi
     double ss = 0.0;
 #pragma unroll
     for (int i = j; i < 3; ++i) ss += a[i][j] * a[i][j];
-    double ajnorm = sqrt(ss);
+    double ajnorm = es_sqrt(ss);
     if (ajnorm != 0.0) {
       if (a[j][j] < 0.0) ajnorm = -ajnorm;
 #pragma unroll
-      for (int i = j; i < 3; ++i) a[i][j] /= ajnorm;
+      {
+        const double inv = fast_rcp(ajnorm);
+#pragma unroll
+        for (int i = j; i < 3; ++i) a[i][j] *= inv;
+      }
       a[j][j] += 1.0;
 #pragma unroll
       for (int k = j + 1; k < 3; ++k) {
         double sum = 0.0;
 #pragma unroll
         for (int i = j; i < 3; ++i) sum += a[i][j] * a[i][k];
-        const double temp = sum / a[j][j];
+        const double temp = es_div(sum, a[j][j]);  // a[j][j] in [1, 2]
 #pragma unroll
         for (int i = j; i < 3; ++i) a[i][k] -= temp * a[i][j];
         if (rdiag[k] != 0.0) {
-          const double tq = a[j][k] / rdiag[k];
-          rdiag[k] *= sqrt(fmax(0.0, 1.0 - tq * tq));
-          const double qq = rdiag[k] / wa[k];
+          const double tq = es_div(a[j][k], rdiag[k]);
+          rdiag[k] *= es_sqrt(fmax(0.0, 1.0 - tq * tq));
+          const double qq = es_div(rdiag[k], wa[k]);
           if (0.05 * qq * qq <= DBL_EPSILON) {
             double rs = 0.0;
 #pragma unroll
             for (int i = j + 1; i < 3; ++i) rs += a[i][k] * a[i][k];
-            rdiag[k] = sqrt(rs);
+            rdiag[k] = es_sqrt(rs);
             wa[k] = rdiag[k];
           }
         }
@@ -399,12 +410,12 @@ __device__ __forceinline__ void es_qrsolv(double r[3][3], const double dp[3], co
         if (sdiag[k] != 0.0) {
           double sn, cs;
           if (fabs(r[k][k]) < fabs(sdiag[k])) {
-            const double cotan = r[k][k] / sdiag[k];
-            sn = 0.5 / sqrt(0.25 + 0.25 * cotan * cotan);
+            const double cotan = es_div(r[k][k], sdiag[k]);
+            sn = 0.5 * rsqrt(0.25 + 0.25 * cotan * cotan);
             cs = sn * cotan;
           } else {
-            const double tn = sdiag[k] / r[k][k];
-            cs = 0.5 / sqrt(0.25 + 0.25 * tn * tn);
+            const double tn = es_div(sdiag[k], r[k][k]);
+            cs = 0.5 * rsqrt(0.25 + 0.25 * tn * tn);
             sn = cs * tn;
           }
           r[k][k] = cs * r[k][k] + sn * sdiag[k];
@@ -436,7 +447,7 @@ __device__ __forceinline__ void es_qrsolv(double r[3][3], const double dp[3], co
 #pragma unroll
       for (int i = j + 1; i < 3; ++i)
         if (i < nsing) sum += r[i][j] * wa[i];
-      wa[j] = (wa[j] - sum) / sdiag[j];
+      wa[j] = es_div(wa[j] - sum, sdiag[j]);
     }
   }
 #pragma unroll
@@ -458,7 +469,7 @@ __device__ __forceinline__ void es_lmpar(double r[3][3], const double dp[3], con
 #pragma unroll
   for (int j = 2; j >= 0; --j) {
     if (j < nsing) {
-      wa1[j] /= r[j][j];
+      wa1[j] = es_div(wa1[j], r[j][j]);
       const double temp = wa1[j];
 #pragma unroll
       for (int i = 0; i < j; ++i) wa1[i] -= r[i][j] * temp;
@@ -475,32 +486,36 @@ __device__ __forceinline__ void es_lmpar(double r[3][3], const double dp[3], con
   double parl = 0.0;
   if (nsing >= 3) {
 #pragma unroll
-    for (int j = 0; j < 3; ++j) wa1[j] = dp[j] * (wa2[j] / dxnorm);
+    {
+      const double inv = fast_rcp(dxnorm);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) wa1[j] = dp[j] * (wa2[j] * inv);
+    }
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       double sum = 0.0;
 #pragma unroll
       for (int i = 0; i < j; ++i) sum += r[i][j] * wa1[i];
-      wa1[j] = (wa1[j] - sum) / r[j][j];
+      wa1[j] = es_div(wa1[j] - sum, r[j][j]);
     }
     const double temp = enorm3(wa1);
-    parl = ((fp / delta) / temp) / temp;
+    parl = ((fp / delta) / temp) / temp;  // (once per call: IEEE, temp may vanish)
   }
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
     double sum = 0.0;
 #pragma unroll
     for (int i = 0; i <= j; ++i) sum += r[i][j] * qtb[i];
-    wa1[j] = sum / dp[j];
+    wa1[j] = es_div(sum, dp[j]);
   }
   const double gnorm = enorm3(wa1);
-  double paru = gnorm / delta;
+  double paru = es_div(gnorm, delta);
   if (paru == 0.0) paru = dwarf / fmin(delta, 0.1);
   par = fmin(fmax(par, parl), paru);
-  if (par == 0.0) par = gnorm / dxnorm;
+  if (par == 0.0) par = es_div(gnorm, dxnorm);
   for (int iter = 1;; ++iter) {
     if (par == 0.0) par = fmax(dwarf, 0.001 * paru);
-    double temp = sqrt(par);
+    double temp = es_sqrt(par);
 #pragma unroll
     for (int j = 0; j < 3; ++j) wa1[j] = temp * dp[j];
     es_qrsolv(r, wa1, qtb, xp, sdiag);
@@ -511,16 +526,21 @@ __device__ __forceinline__ void es_lmpar(double r[3][3], const double dp[3], con
     fp = dxnorm - delta;
     if (fabs(fp) <= 0.1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || iter == 10) break;
 #pragma unroll
-    for (int j = 0; j < 3; ++j) wa1[j] = dp[j] * (wa2[j] / dxnorm);
+    {
+      const double inv = fast_rcp(dxnorm);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) wa1[j] = dp[j] * (wa2[j] * inv);
+    }
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      wa1[j] /= sdiag[j];
+      wa1[j] = es_div(wa1[j], sdiag[j]);
       const double t2 = wa1[j];
 #pragma unroll
       for (int i = j + 1; i < 3; ++i) wa1[i] -= r[i][j] * t2;
     }
     temp = enorm3(wa1);
-    const double parc = ((fp / delta) / temp) / temp;
+    const double it = fast_rcp(temp);
+    const double parc = (fp * fast_rcp(delta)) * it * it;
     if (fp > 0.0) parl = fmax(parl, par);
     if (fp < 0.0) paru = fmin(paru, par);
     par = fmax(parl, par + parc);
@@ -560,7 +580,7 @@ struct EsLmParams {
 __device__ __forceinline__ void es_lm_group(const double *mom, int stride, const EsLmParams &args, bool active,
                                             int sub, double x[3], int &info_out, int &nfev_out) {
   const double epsmch = DBL_EPSILON;
-  const double eps = sqrt(epsmch);  // epsfcn = 0
+  const double eps = es_sqrt(epsmch);  // epsfcn = 0
   double fvec[3] = {0, 0, 0}, r[3][3], diag[3] = {1, 1, 1}, dp[3], qtf[3] = {0, 0, 0}, wa1[3], wa2[3], acn[3];
   int ipvt[3] = {0, 1, 2};
   double fnorm = 0.0, par = 0.0, delta = 0.0, xnorm = 0.0, gnorm = 0.0, h = 0.0, pnorm = 0.0;
@@ -594,9 +614,10 @@ __device__ __forceinline__ void es_lm_group(const double *mom, int stride, const
       state = 1;
     } else if (state <= 3) {
       const int j = state - 1;
+      const double inv_h = fast_rcp(h);
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
-        const double v = (fe[i] - fvec[i]) / h;
+        const double v = (fe[i] - fvec[i]) * inv_h;
         if (j == 0) r[i][0] = v; else if (j == 1) r[i][1] = v; else r[i][2] = v;
       }
       if (state < 3) {
@@ -621,7 +642,7 @@ __device__ __forceinline__ void es_lm_group(const double *mom, int stride, const
             double sum = 0.0;
 #pragma unroll
             for (int i = j2; i < 3; ++i) sum += r[i][j2] * w4[i];
-            const double temp = -sum / r[j2][j2];
+            const double temp = -es_div(sum, r[j2][j2]);
 #pragma unroll
             for (int i = j2; i < 3; ++i) w4[i] += r[i][j2] * temp;
           }
@@ -630,14 +651,15 @@ __device__ __forceinline__ void es_lm_group(const double *mom, int stride, const
         }
         gnorm = 0.0;
         if (fnorm != 0.0) {
+          const double inv_fnorm = fast_rcp(fnorm);
 #pragma unroll
           for (int j2 = 0; j2 < 3; ++j2) {
             const double cn = pick3(acn, ipvt[j2]);
             if (cn != 0.0) {
               double sum = 0.0;
 #pragma unroll
-              for (int i = 0; i <= j2; ++i) sum += r[i][j2] * (qtf[i] / fnorm);
-              gnorm = fmax(gnorm, fabs(sum / cn));
+              for (int i = 0; i <= j2; ++i) sum += r[i][j2] * (qtf[i] * inv_fnorm);
+              gnorm = fmax(gnorm, fabs(es_div(sum, cn)));
             }
           }
         }
@@ -657,27 +679,28 @@ __device__ __forceinline__ void es_lm_group(const double *mom, int stride, const
       ++nfev;
       const double fnorm1 = enorm3(fe);
       double actred = -1.0;
-      if (0.1 * fnorm1 < fnorm) actred = 1.0 - (fnorm1 / fnorm) * (fnorm1 / fnorm);
+      const double inv_fnorm = fast_rcp(fnorm);  // fnorm > 0: a zero residual stops at the gradient test
+      if (0.1 * fnorm1 < fnorm) actred = 1.0 - (fnorm1 * inv_fnorm) * (fnorm1 * inv_fnorm);
       // wa3 = R * P^T p  (wa1 holds p in pivoted order)
       double w3[3] = {0, 0, 0};
 #pragma unroll
       for (int j2 = 0; j2 < 3; ++j2)
 #pragma unroll
         for (int i = 0; i <= j2; ++i) w3[i] += r[i][j2] * wa1[j2];
-      const double t1 = enorm3(w3) / fnorm, t2 = sqrt(par) * pnorm / fnorm;
+      const double t1 = enorm3(w3) * inv_fnorm, t2 = es_sqrt(par) * pnorm * inv_fnorm;
       const double temp1 = t1 * t1, temp2 = t2 * t2;
-      const double prered = temp1 + temp2 / 0.5;
+      const double prered = temp1 + temp2 * 2.0;
       const double dirder = -(temp1 + temp2);
       double ratio = 0.0;
-      if (prered != 0.0) ratio = actred / prered;
+      if (prered != 0.0) ratio = es_div(actred, prered);
       if (ratio <= 0.25) {
         double temp = 0.5;
-        if (actred < 0.0) temp = 0.5 * dirder / (dirder + 0.5 * actred);
+        if (actred < 0.0) temp = es_div(0.5 * dirder, dirder + 0.5 * actred);
         if (0.1 * fnorm1 >= fnorm || temp < 0.1) temp = 0.1;
-        delta = temp * fmin(delta, pnorm / 0.1);
-        par /= temp;
+        delta = temp * fmin(delta, pnorm * 10.0);
+        par = es_div(par, temp);
       } else if (!(par != 0.0 && ratio < 0.75)) {
-        delta = pnorm / 0.5;
+        delta = pnorm * 2.0;
         par = 0.5 * par;
       }
       if (ratio >= 1e-4) {
