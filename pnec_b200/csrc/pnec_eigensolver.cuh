@@ -267,7 +267,9 @@ __device__ __forceinline__ double es_smallest_ev(const double *mom, int stride, 
   const double ist = 0.5 * irq * irq * irq;  // 1 / sqrt(t)
   const double ratio = s * ist;         // cos(alpha)
   // y = cos(alpha / 3): the largest root of 4 y^3 - 3 y = cos(alpha), in [1/2, 1] where the cubic is
-  // increasing and convex, so Newton from y = 1 descends to it monotonically (instead of acos + cos)
+  // increasing and convex, so Newton from y = 1 descends to it monotonically (instead of acos + cos).
+  // (A single-precision acos / cos seed was tried: no faster, and it lands on the other side of the
+  // double root at y = 1/2 for near-degenerate pairs.)
   double cb = 1.0;
 #pragma unroll 1
   for (int it = 0; it < 48; ++it) {
@@ -570,8 +572,16 @@ constexpr int kEsLmPairs = kEsLmThreads / 4;  // four lanes per frame pair
 // The Levenberg-Marquardt run of one 4-lane group (opengv's eigensolver_main on the 36 moments at
 // `mom`, consecutive moments `stride` doubles apart).  Must be called by all 32 lanes of a warp;
 // groups without work pass active = false.  The four lanes share the function evaluation (see
-// es_smallest_ev) and run the scalar logic redundantly, so a group never diverges.  States of the
-// evaluation loop: 0 = f(x0), 1..3 = forward-difference column j = state - 1, 4 = trial point.
+// es_smallest_ev) and run the scalar logic redundantly, so a group never diverges.
+//
+// The eight groups of a warp move through lmdif's phases TOGETHER (the phase is warp-uniform):
+// f(x0); then per outer iteration the three forward-difference columns, the QR factorisation /
+// gradient test / first step, and trial points until every group of the warp has either accepted
+// one (ratio >= 1e-4) or terminated -- groups that are through wait for the others.  A turn of the
+// loop therefore executes ONE kind of post-processing for the whole warp (with unsynchronised
+// groups nearly every turn paid for the factorisation, the step computation and the step
+// assessment, each for a fraction of the lanes), and there is a single call site of the evaluation.
+// Each group performs exactly lmdif's sequence of operations; only the interleaving differs.
 struct EsLmParams {
   double ftol, xtol, gtol, factor;
   int maxfev;
@@ -581,48 +591,63 @@ __device__ __forceinline__ void es_lm_group(const double *mom, int stride, const
                                             int sub, double x[3], int &info_out, int &nfev_out) {
   const double epsmch = DBL_EPSILON;
   const double eps = es_sqrt(epsmch);  // epsfcn = 0
-  double fvec[3] = {0, 0, 0}, r[3][3], diag[3] = {1, 1, 1}, dp[3], qtf[3] = {0, 0, 0}, wa1[3], wa2[3], acn[3];
+  double fvec[3] = {0, 0, 0}, r[3][3], diag[3] = {1, 1, 1}, dp[3] = {1, 1, 1}, qtf[3] = {0, 0, 0}, wa1[3] = {0, 0, 0};
+  double wa2[3] = {x[0], x[1], x[2]}, acn[3] = {0, 0, 0};
   int ipvt[3] = {0, 1, 2};
   double fnorm = 0.0, par = 0.0, delta = 0.0, xnorm = 0.0, gnorm = 0.0, h = 0.0, pnorm = 0.0;
-  int info = 0, nfev = 0, iter = 1, state = 0;
-  bool done = !active;
+  int info = 0, nfev = 0, iter = 1;
+  int phase = 0;        // warp-uniform: 0 = f(x0), 1..3 = forward-difference column phase - 1, 4 = trial point
+  bool done = !active;  // this group has terminated
+  bool trying = false;  // this group has a trial point pending (phase 4)
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int j = 0; j < 3; ++j) r[i][j] = 0.0;
+  if (__all_sync(0xffffffffu, done)) {
+    info_out = 0;
+    nfev_out = 0;
+    return;
+  }
 
-  while (!__all_sync(0xffffffffu, done)) {
+  for (;;) {
     // ---- the point to evaluate
     double xe[3] = {x[0], x[1], x[2]};
-    if (state >= 1 && state <= 3) {
-      const double xj = pick3(x, state - 1);
+    if (phase >= 1 && phase <= 3) {
+      const double xj = pick3(x, phase - 1);
       h = eps * fabs(xj);
       if (h == 0.0) h = eps;
-      put3(xe, state - 1, xj + h);
-    } else if (state == 4) {
+      put3(xe, phase - 1, xj + h);
+    } else if (phase == 4 && trying) {
       xe[0] = wa2[0]; xe[1] = wa2[1]; xe[2] = wa2[2];
     }
     double fe[3];
     es_smallest_ev(mom, stride, xe, sub, fe);
-    if (done) continue;
 
     bool need_step = false;
-    if (state == 0) {
-      fvec[0] = fe[0]; fvec[1] = fe[1]; fvec[2] = fe[2];
-      fnorm = enorm3(fvec);
-      nfev = 1;
-      state = 1;
-    } else if (state <= 3) {
-      const int j = state - 1;
-      const double inv_h = fast_rcp(h);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const double v = (fe[i] - fvec[i]) * inv_h;
-        if (j == 0) r[i][0] = v; else if (j == 1) r[i][1] = v; else r[i][2] = v;
+    if (phase == 0) {
+      if (!done) {
+        fvec[0] = fe[0]; fvec[1] = fe[1]; fvec[2] = fe[2];
+        fnorm = enorm3(fvec);
+        nfev = 1;
       }
-      if (state < 3) {
-        state += 1;
-      } else {
+      phase = 1;
+      continue;
+    }
+    if (phase <= 3) {
+      if (!done) {
+        const int j = phase - 1;
+        const double inv_h = fast_rcp(h);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const double v = (fe[i] - fvec[i]) * inv_h;
+          if (j == 0) r[i][0] = v; else if (j == 1) r[i][1] = v; else r[i][2] = v;
+        }
+      }
+      if (phase < 3) {
+        phase += 1;
+        continue;
+      }
+      if (!done) {
         nfev += 4;  // Eigen's NumericalDiff (Forward) evaluates f(x) again: n + 1 calls per Jacobian
         double rdiag[3];
         es_qrfac(r, ipvt, rdiag, acn);
@@ -674,7 +699,7 @@ __device__ __forceinline__ void es_lm_group(const double *mom, int stride, const
           need_step = true;
         }
       }
-    } else {
+    } else if (trying) {
       // ---- trial point evaluated: fe = f(x + p)
       ++nfev;
       const double fnorm1 = enorm3(fe);
@@ -721,12 +746,11 @@ __device__ __forceinline__ void es_lm_group(const double *mom, int stride, const
         if (delta <= epsmch * xnorm) info = 7;
         if (gnorm <= epsmch) info = 8;
       }
+      trying = false;
       if (info != 0) {
         done = true;
       } else if (ratio < 1e-4) {
         need_step = true;  // inner loop of lmdif: same Jacobian, smaller region
-      } else {
-        state = 1;
       }
     }
     if (need_step) {
@@ -743,8 +767,13 @@ __device__ __forceinline__ void es_lm_group(const double *mom, int stride, const
       for (int j2 = 0; j2 < 3; ++j2) put3(wa2, ipvt[j2], pick3(x, ipvt[j2]) + wa1[j2]);
       pnorm = enorm3(dpn);
       if (iter == 1) delta = fmin(delta, pnorm);
-      state = 4;
+      trying = true;
     }
+    // ---- next phase (warp-uniform): more trial points while any group has one pending, else a new
+    // outer iteration for the groups that are not done, else out
+    if (__any_sync(0xffffffffu, trying)) phase = 4;
+    else if (__all_sync(0xffffffffu, done)) break;
+    else phase = 1;
   }
   info_out = info;
   nfev_out = nfev;
