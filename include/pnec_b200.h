@@ -283,6 +283,9 @@ typedef struct pnec_frame_opts {
                                     EigensolverSacProblem::computeModelCoefficients             */
   uint64_t ransac_seed;          /* key of the counter-based random stream (opengv: time-seeded
                                     mt19937 + rand(), not reproducible)                         */
+  int64_t ransac_pair_index_base;/* 0; pair b draws from the stream of pair (base + b): a shard of
+                                    a larger batch passes its first pair's index and reproduces
+                                    what the whole batch would compute                          */
 } pnec_frame_opts;
 
 /* Options() defaults (use_ransac = 1). */
@@ -343,7 +346,7 @@ int pnec_ransac_batch(pnec_handle *h, const pnec_batch *batch, const pnec_frame_
  *      from the pose of step 1; SCF translation started at the previous translation };
  *      == 1: the pose of step 1;  == 0: batch->poses
  *   4. use_ceres: CeresSolver (TARGET residual) from 3
- * batch->covs_target may be NULL when use_nec.  The random stream of pair b is keyed by b. */
+ * batch->covs_target may be NULL when use_nec. */
 int pnec_frame_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_frame_opts *opts,
                            const pnec_frame_out *out, void *cuda_stream);
 

@@ -135,6 +135,7 @@ class FrameOpts(ctypes.Structure):
         ("ransac_probability", ctypes.c_double),
         ("ransac_max_variation", ctypes.c_double),
         ("ransac_seed", ctypes.c_uint64),
+        ("ransac_pair_index_base", ctypes.c_int64),
     ]
 
 

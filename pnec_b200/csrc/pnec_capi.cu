@@ -83,7 +83,6 @@ int env_int(const char *name, int dflt) {
 // created: no getenv on the call path (a single-pair solve is a 0.1 ms affair).
 struct Config {
   int dump_timing = 0;
-  int eval_cfg = 0;
   int frame_chunks = 0;
   int fused_rounds_max_pairs = 512;
   int h2d_chunks = 0;
@@ -92,18 +91,15 @@ struct Config {
   int no_lm_ahead = 0;
   int no_stager = 0;
   int ransac_warps = 0;
-  int ransac_occ = 16;  // PNEC_B200_RANSAC_OCC: warps per SM the RANSAC kernels are compiled for (8, 12, 16)
   int ransac_defer = -1;  // PNEC_B200_RANSAC_DEFER: iterations after which pass 1 hands a pair to pass 2 (0: never)
   int scf_debug = 0;
   int scf_defer = 48;
   int scf_warps = 0;
   int solve_warps = 0;
-  int stream_cfg = 3;
   int stream_min_n = 896;
   int copy_threads = 0;  // PNEC_B200_COPY_THREADS: worker threads of the pageable-input stager (0 = auto)
   void load() {
     dump_timing = env_int("PNEC_B200_DUMP_TIMING", 0);
-    eval_cfg = env_int("PNEC_B200_EVAL_CFG", 0);
     frame_chunks = env_int("PNEC_B200_FRAME_CHUNKS", 0);
     fused_rounds_max_pairs = env_int("PNEC_B200_FUSED_ROUNDS_MAX_PAIRS", 512);
     h2d_chunks = env_int("PNEC_B200_H2D_CHUNKS", 0);
@@ -112,13 +108,11 @@ struct Config {
     no_lm_ahead = env_int("PNEC_B200_NO_LM_AHEAD", 0);
     no_stager = env_int("PNEC_B200_NO_STAGER", 0);
     ransac_warps = env_int("PNEC_B200_RANSAC_WARPS", 0);
-    ransac_occ = env_int("PNEC_B200_RANSAC_OCC", 16);
     ransac_defer = env_int("PNEC_B200_RANSAC_DEFER", -1);
     scf_debug = env_int("PNEC_B200_SCF_DEBUG", 0);
     scf_defer = env_int("PNEC_B200_SCF_DEFER", 48);
     scf_warps = env_int("PNEC_B200_SCF_WARPS", 0);
     solve_warps = env_int("PNEC_B200_SOLVE_WARPS", 0);
-    stream_cfg = env_int("PNEC_B200_STREAM_CFG", 3);
     stream_min_n = env_int("PNEC_B200_STREAM_MIN_N", 896);
     copy_threads = env_int("PNEC_B200_COPY_THREADS", 0);
   }
@@ -570,17 +564,8 @@ int launch_solve_stream_t(pnec_handle *h, const SolveArgs &a, cudaStream_t strea
 
 template <int V>
 int launch_solve_stream_v(pnec_handle *h, const SolveArgs &a, cudaStream_t stream) {
-  switch (h->cfg.stream_cfg) {
-    case 1: return launch_solve_stream_t<V, 6, 4, 2>(h, a, stream);   // 2 CTAs x 6 warps per SM
-    case 2: return launch_solve_stream_t<V, 12, 4, 1>(h, a, stream);  // 1 CTA x 12 warps
-    case 3: return launch_solve_stream_t<V, 4, 4, 3>(h, a, stream);   // 3 CTAs x 4 warps
-    case 4: return launch_solve_stream_t<V, 6, 3, 2>(h, a, stream);
-    case 5: return launch_solve_stream_t<V, 1, 4, 12>(h, a, stream);  // one warp per pair, 12 pairs per SM
-    case 6: return launch_solve_stream_t<V, 2, 4, 6>(h, a, stream);
-    case 7: return launch_solve_stream_t<V, 1, 3, 12>(h, a, stream);
-    case 8: return launch_solve_stream_t<V, 1, 6, 8>(h, a, stream);
-    default: return fail(PNEC_ERR_INVALID_ARGUMENT, "unknown PNEC_B200_STREAM_CFG");
-  }
+  // 3 CTAs x 4 warps per SM, 4-stage rings (measured best of the round-1 sweep over 1 .. 12 warps per CTA)
+  return launch_solve_stream_t<V, 4, 4, 3>(h, a, stream);
 }
 
 int launch_solve(pnec_handle *h, const SolveArgs &a0, int variant, long long max_n,
@@ -662,20 +647,11 @@ int launch_eval_warp_t(pnec_handle *h, const EvalArgs &a, cudaStream_t stream) {
 template <int V>
 int launch_eval_v(pnec_handle *h, const EvalArgs &a, long long max_n, cudaStream_t stream) {
   (void)max_n;
-  int cfg = h->cfg.eval_cfg;
-  if (cfg == 0) cfg = a.use_bulk ? 11 : 2;  // 3 stages of 32 correspondences per warp: measured best
-  switch (cfg) {
-    case 2: return launch_eval_t<V, 4, 4, 3>(h, a, stream);    // CTA per problem, 128-wide tiles
-    case 10: return launch_eval_warp_t<V, 4, 4, 8, 3>(h, a, stream);  // warp-private, 4 stages
-    case 11: return launch_eval_warp_t<V, 4, 3, 8, 3>(h, a, stream);  // warp-private, 3 stages (default)
-    case 12: return launch_eval_warp_t<V, 4, 6, 8, 2>(h, a, stream);
-    case 13: return launch_eval_warp_t<V, 8, 3, 8, 2>(h, a, stream);
-    case 14: return launch_eval_warp_t<V, 4, 2, 8, 3, 64>(h, a, stream);   // 64-wide tiles, 2 stages
-    case 15: return launch_eval_warp_t<V, 4, 3, 8, 3, 64>(h, a, stream);   // 64-wide tiles, 3 stages (smem: 2 CTAs)
-    case 16: return launch_eval_warp_t<V, 4, 2, 8, 3, 128>(h, a, stream);  // 128-wide tiles
-    case 17: return launch_eval_warp_t<V, 4, 2, 8, 3>(h, a, stream);       // 32-wide tiles, 2 stages
-    default: return fail(PNEC_ERR_INVALID_ARGUMENT, "unknown PNEC_B200_EVAL_CFG");
-  }
+  // warp-private rings of 3 stages x 32 correspondences, 4 warps per CTA, 3 CTAs per SM (measured best of
+  // the round-1 sweep: 2 / 4 / 6 stages, 64- and 128-wide tiles, 8 warps); CTA-per-pair cooperative
+  // loads for arrays that are not 16-byte aligned
+  if (a.use_bulk) return launch_eval_warp_t<V, 4, 3, 8, 3>(h, a, stream);
+  return launch_eval_t<V, 4, 4, 3>(h, a, stream);
 }
 
 int launch_eval(pnec_handle *h, const EvalArgs &a0, int variant, long long max_n,
@@ -1014,21 +990,11 @@ int run_ransac(pnec_handle *h, const BatchView &bv, const pnec_frame_opts &o, lo
   a.hyp_count = static_cast<int *>(h->d_rs_hyp.p) + pair0 * kRansacSuper;
   if (defer_after > 0) PNEC_CUDA(cudaMemsetAsync(a.defer, 0, 4 * sizeof(int), stream));
   const unsigned grid = static_cast<unsigned>(bv.num_problems);
-  // registers per thread: 255 (8 warps per SM), 168 (12) or 128 (16); the hypotheses are latency bound
-  const int occ = h->cfg.ransac_occ;
-  if (nw == 1) {
-    if (occ == 8) ransac_kernel<1, 8><<<grid, 32, 0, stream>>>(a);
-    else if (occ == 12) ransac_kernel<1, 12><<<grid, 32, 0, stream>>>(a);
-    else ransac_kernel<1, 16><<<grid, 32, 0, stream>>>(a);
-  } else if (nw == 2) {
-    if (occ == 8) ransac_kernel<2, 4><<<grid, 64, 0, stream>>>(a);
-    else if (occ == 12) ransac_kernel<2, 6><<<grid, 64, 0, stream>>>(a);
-    else ransac_kernel<2, 8><<<grid, 64, 0, stream>>>(a);
-  } else {
-    if (occ == 8) ransac_kernel<4, 2><<<grid, 128, 0, stream>>>(a);
-    else if (occ == 12) ransac_kernel<4, 3><<<grid, 128, 0, stream>>>(a);
-    else ransac_kernel<4, 4><<<grid, 128, 0, stream>>>(a);
-  }
+  // compiled for 16 warps per SM (128 registers): the hypotheses are latency bound (255 / 168 registers,
+  // i.e. 8 / 12 warps per SM, measured 15 % / 3 % slower)
+  if (nw == 1) ransac_kernel<1, 16><<<grid, 32, 0, stream>>>(a);
+  else if (nw == 2) ransac_kernel<2, 8><<<grid, 64, 0, stream>>>(a);
+  else ransac_kernel<4, 4><<<grid, 128, 0, stream>>>(a);
   PNEC_CUDA(cudaGetLastError());
   h->launches++;
   if (defer_after > 0) {
@@ -1036,14 +1002,11 @@ int run_ransac(pnec_handle *h, const BatchView &bv, const pnec_frame_opts &o, lo
     // this many super-rounds cover the worst case; with nothing (left) to do the kernels return at once.
     int rounds = 0;
     for (int it = defer_after; it <= o.max_ransac_iterations; ++rounds) it += ransac_grant(it, o.max_ransac_iterations);
-    const int per_sm = occ == 8 ? 2 : occ == 12 ? 3 : 4;  // CTAs of 4 independent warps per SM
-    const unsigned pgrid = static_cast<unsigned>(std::min<long long>(
-        1LL * per_sm * h->sm_count, (bv.num_problems * (kRansacSuper / kRansacBlock) + 3) / 4));
+    const unsigned pgrid = static_cast<unsigned>(std::min<long long>(  // 4 CTAs of 4 independent warps per SM
+        4LL * h->sm_count, (bv.num_problems * (kRansacSuper / kRansacBlock) + 3) / 4));
     ransac_plan_kernel<<<1, 1024, 0, stream>>>(a, 0);
     for (int r = 0; r < rounds; ++r) {
-      if (per_sm == 2) ransac_hyp_kernel<4, 2><<<pgrid, 128, 0, stream>>>(a);
-      else if (per_sm == 3) ransac_hyp_kernel<4, 3><<<pgrid, 128, 0, stream>>>(a);
-      else ransac_hyp_kernel<4, 4><<<pgrid, 128, 0, stream>>>(a);
+      ransac_hyp_kernel<4, 4><<<pgrid, 128, 0, stream>>>(a);
       ransac_plan_kernel<<<1, 1024, 0, stream>>>(a, 1);
     }
     ransac_final_kernel<<<static_cast<unsigned>(std::min<long long>(2LL * h->sm_count, bv.num_problems)), 128, 0, stream>>>(a);
@@ -1567,6 +1530,7 @@ void pnec_frame_opts_default(pnec_frame_opts *o) {
   o->ransac_probability = 0.99;
   o->ransac_max_variation = 0.1;
   o->ransac_seed = 1;
+  o->ransac_pair_index_base = 0;
 }
 
 int pnec_ransac_batch(pnec_handle *h, const pnec_batch *batch, const pnec_frame_opts *opts, int64_t pair_index_base,
@@ -1738,7 +1702,7 @@ int pnec_frame_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_f
       r.f1 += 3 * e0; r.f2 += 3 * e0;
       if (r.ct) r.ct += 9 * e0;
       if (r.index) r.index += e0;
-      if ((rcc = run_ransac(h, bv, *opts, c0, r, c0, chunk, cs)) != PNEC_OK) return rcc;
+      if ((rcc = run_ransac(h, bv, *opts, opts->ransac_pair_index_base + c0, r, c0, chunk, cs)) != PNEC_OK) return rcc;
       bv.f1 = r.f1; bv.f2 = r.f2;
       if (r.ct) bv.ct = r.ct;
       bv.counts = r.count;

@@ -355,7 +355,6 @@ __device__ __forceinline__ void es_qrfac(double a[3][3], int ipvt[3], double rdi
     double ajnorm = es_sqrt(ss);
     if (ajnorm != 0.0) {
       if (a[j][j] < 0.0) ajnorm = -ajnorm;
-#pragma unroll
       {
         const double inv = fast_rcp(ajnorm);
 #pragma unroll
@@ -487,7 +486,6 @@ __device__ __forceinline__ void es_lmpar(double r[3][3], const double dp[3], con
   }
   double parl = 0.0;
   if (nsing >= 3) {
-#pragma unroll
     {
       const double inv = fast_rcp(dxnorm);
 #pragma unroll
@@ -527,7 +525,6 @@ __device__ __forceinline__ void es_lmpar(double r[3][3], const double dp[3], con
     temp = fp;
     fp = dxnorm - delta;
     if (fabs(fp) <= 0.1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || iter == 10) break;
-#pragma unroll
     {
       const double inv = fast_rcp(dxnorm);
 #pragma unroll

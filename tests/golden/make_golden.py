@@ -205,11 +205,43 @@ def oracle_frame_fixtures():
     np.savez_compressed(os.path.join(HERE, "oracle_frame.npz"), **out)
 
 
+def oracle_ransac_fixtures():
+    """oracle_ransac.npz: PNEC::Solve with the reference's default options (RANSAC over the eigensolver,
+    pnec.cc:239-272) on seeded frame pairs, half of them with 20 % gross outliers, as minted by the
+    oracle's restatement of opengv's Ransac<EigensolverSacProblem> (independent-hypotheses mode, seed 1):
+    inlier masks, iteration counts, winning models, eigensolver and final poses, and the same on inputs
+    moved by one ulp (pairs on which the algorithm is not stable under that are no parity cases)."""
+    import oracle
+    from pnec_b200 import synthetic as syn
+
+    out = {}
+    B, N = 32, 160
+    b = syn.make_batch(B, N, seed=611, noise_level=0.5)
+    rng = np.random.default_rng(612)
+    for k in range(0, B, 2):
+        bad = k * N + rng.choice(N, N // 5, replace=False)
+        v = rng.standard_normal((len(bad), 3))
+        b.bvs_target[bad] = v / np.linalg.norm(v, axis=1, keepdims=True)
+    f1p = b.bvs_host * (1.0 + rng.uniform(-1, 1, b.bvs_host.shape) * 2.0 ** -52)
+    f2p = b.bvs_target * (1.0 + rng.uniform(-1, 1, b.bvs_target.shape) * 2.0 ** -52)
+    out["f1"], out["f2"], out["cov"], out["init"], out["n"] = b.bvs_host, b.bvs_target, b.covs_target, b.init_poses, np.int64(N)
+    for tag, (f1, f2) in {"": (b.bvs_host, b.bvs_target), "_ulp": (f1p, f2p)}.items():
+        poses, es, mask, ni, it = oracle.frame_solve_batch(f1, f2, b.covs_target, b.init_poses,
+                                                           oracle.default_frame_opts(), n_per_problem=N,
+                                                           return_ransac=True)
+        models = np.array([oracle.ransac_compute_model(f1[k * N:(k + 1) * N], f2[k * N:(k + 1) * N], b.init_poses[k],
+                                                       pair_index=k)[0] for k in range(B)])
+        out[f"poses{tag}"], out[f"es_poses{tag}"], out[f"mask{tag}"] = poses, es, mask
+        out[f"num_inliers{tag}"], out[f"iterations{tag}"], out[f"models{tag}"] = ni, it, models
+    np.savez_compressed(os.path.join(HERE, "oracle_ransac.npz"), **out)
+
+
 if __name__ == "__main__":
     reference_fixtures()
     reference_scf_fixtures()
     oracle_fixtures()
     oracle_frame_fixtures()
+    oracle_ransac_fixtures()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

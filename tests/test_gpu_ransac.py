@@ -239,3 +239,33 @@ def test_stage_timing_fields(handle):
                                     api.default_frame_opts(weighted_iterations=1, use_ceres=0), n_per_problem=200,
                                     stage_timing=True)
     assert res0.stage_ms[0] > 0 and res0.stage_ms[1] < 0.05
+
+
+def test_frame_solve_matches_committed_ransac_fixture(handle):
+    """CUDA path vs tests/golden/oracle_ransac.npz (the oracle's default-options PNEC::Solve on 32 pairs,
+    half with 20 % outliers); pairs whose fixture differs from its one-ulp twin are no parity cases."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_ransac.npz"))
+    N, B = int(g["n"]), g["init"].shape[0]
+    res = handle.frame_solve_batch(g["f1"], g["f2"], g["cov"], g["init"], api.default_frame_opts(), n_per_problem=N)
+    models, ni, it, idx = handle.ransac_batch(g["f1"], g["f2"], g["init"], api.default_frame_opts(), n_per_problem=N)
+    checked = 0
+    for k in range(B):
+        sl = slice(k * N, (k + 1) * N)
+        stable = (g["iterations"][k] == g["iterations_ulp"][k] and np.array_equal(g["mask"][sl], g["mask_ulp"][sl]) and
+                  rotation_angle(g["poses"][k], g["poses_ulp"][k]) <= 1e-8 and
+                  direction_angle(g["poses"][k][4:], g["poses_ulp"][k][4:]) <= 1e-8)
+        if not stable:
+            continue
+        checked += 1
+        assert res.ransac_iterations[k] == g["iterations"][k] == it[k]
+        assert res.num_inliers[k] == g["num_inliers"][k] == ni[k]
+        m = np.zeros(N, bool)
+        m[res.inlier_index[sl][:res.num_inliers[k]]] = True
+        np.testing.assert_array_equal(m, g["mask"][sl])
+        assert rotation_angle(models[k], g["models"][k]) <= ROT_TOL
+        assert rotation_angle(res.es_poses[k], g["es_poses"][k]) <= ROT_TOL
+        assert rotation_angle(res.poses[k], g["poses"][k]) <= ROT_TOL
+        assert direction_angle(res.poses[k][4:], g["poses"][k][4:]) <= DIR_TOL
+    assert checked >= 0.75 * B, checked

@@ -78,7 +78,7 @@ def test_frame_options_are_the_reference_defaults():
     assert f.ransac_probability == 0.99
     assert (f.fibonacci_samples, f.scf_steps) == (500, 10)  # literals of pnec.cc:331 and :342
     assert f.ceres.regularization == 1e-13 and f.ceres.max_num_iterations == 50
-    assert ctypes.sizeof(api.FrameOpts) == 6 * 4 + ctypes.sizeof(api.SolverOpts) + 2 * 4 + 4 * 8
+    assert ctypes.sizeof(api.FrameOpts) == 6 * 4 + ctypes.sizeof(api.SolverOpts) + 2 * 4 + 5 * 8
     o = oracle.default_frame_opts()
     for name in ("use_nec", "use_ceres", "weighted_iterations", "fibonacci_samples", "scf_steps", "use_ransac"):
         assert getattr(o, name) == getattr(f, name), name
@@ -96,6 +96,9 @@ def test_frame_entry_points_reject_null_arguments():
     lib = api.load_library()
     assert lib.pnec_frame_solve_batch(None, None, None, None, None) == -1
     assert lib.pnec_ransac_batch(None, None, None, 0, None, None, None, None, None) == -1
+    assert lib.pnec_keypoints_to_batch(None, None, None, None) == -1
+    assert lib.pnec_solve_from_keypoints_batch(None, None, None, None, None) == -1
+    assert lib.pnec_frame_solve_from_keypoints_batch(None, None, None, None, None) == -1
     assert lib.pnec_eigensolver_batch(None, None, None, 0.0, None, None, None, None) == -1
     lib.pnec_frame_opts_default(None)  # must be a no-op
 

@@ -52,11 +52,6 @@ b = syn.make_batch(len(counts), 0, seed=4, camera=syn.PINHOLE, counts=counts)
 run("C4 4540x~2000 ragged, max 20 it", b.bvs_host, b.bvs_target, b.covs_target, b.init_poses,
     api.default_opts(api.TARGET, max_num_iterations=20), offsets=b.offsets)
 # C5: correspondence-count sweep at 4096 problems
-for cfg in ("1", "2", "3", "4"):
-    os.environ["PNEC_B200_STREAM_CFG"] = cfg; h = api.Handle(0)  # switches are read at handle creation
-    run(f"C4 stream cfg {cfg}", b.bvs_host, b.bvs_target, b.covs_target, b.init_poses,
-        api.default_opts(api.TARGET, max_num_iterations=20), offsets=b.offsets)
-os.environ.pop("PNEC_B200_STREAM_CFG"); h = api.Handle(0)  # switches are read at handle creation
 os.environ["PNEC_B200_STREAM_MIN_N"] = "100000000"; h = api.Handle(0)  # switches are read at handle creation
 run("C4 resident/global path", b.bvs_host, b.bvs_target, b.covs_target, b.init_poses,
     api.default_opts(api.TARGET, max_num_iterations=20), offsets=b.offsets)
@@ -101,4 +96,4 @@ row = dict(config="NEC translation (ComposeM + TranslationFromM), 10000x512", po
            points_per_s=10000 / ms * 1e3, GBps=10000 * 512 * 48 / ms / 1e6, algorithmic_bytes_per_point=512 * 48)
 rows.append(row); print(json.dumps(row), flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(rows, open("gpurun_out/configs_r01.json", "w"), indent=1)
+json.dump(rows, open("gpurun_out/configs_r02.json", "w"), indent=1)

@@ -20,10 +20,9 @@ bad = rng.random(B * N) < 0.25
 v = rng.standard_normal((int(bad.sum()), 3)); f2o[bad] = v / np.linalg.norm(v, axis=1, keepdims=True)
 f1, f2, f2od, init = dev(batch.bvs_host), dev(batch.bvs_target), dev(f2o), dev(batch.init_poses)
 for name, tgt in (("clean", f2), ("25% outliers", f2od)):
-    for nw, occ in (("1", "16"), ("1", "12"), ("4", "16")):
+    for nw, occ in (("1", "16"), ("4", "16")):
         for defer, max_it in (("0", 7), ("0", 55), ("-1", 247), ("-1", 5000)):
             os.environ["PNEC_B200_RANSAC_WARPS"] = nw; os.environ["PNEC_B200_RANSAC_DEFER"] = defer
-            os.environ["PNEC_B200_RANSAC_OCC"] = occ
             h = api.Handle(0)
             o = api.default_frame_opts(max_ransac_iterations=max_it)
             ms = timed(lambda: h.ransac_batch(f1, tgt, init, o, n_per_problem=N))
