@@ -29,6 +29,7 @@
 #include "pnec_frame.cuh"
 #include "pnec_ransac.cuh"
 #include "pnec_solve.cuh"
+#include "pnec_solve_slots.cuh"
 #include "pnec_translation.cuh"
 
 // =================================================================== host side
@@ -96,6 +97,7 @@ struct Config {
   int scf_defer = 48;
   int scf_warps = 0;
   int solve_warps = 0;
+  int solve_slots = 1;  // PNEC_B200_SOLVE_SLOTS: 0 never, 1 large batches (default), 2 whenever the pairs fit
   int stream_min_n = 896;
   int copy_threads = 0;  // PNEC_B200_COPY_THREADS: worker threads of the pageable-input stager (0 = auto)
   void load() {
@@ -113,6 +115,7 @@ struct Config {
     scf_defer = env_int("PNEC_B200_SCF_DEFER", 48);
     scf_warps = env_int("PNEC_B200_SCF_WARPS", 0);
     solve_warps = env_int("PNEC_B200_SOLVE_WARPS", 0);
+    solve_slots = env_int("PNEC_B200_SOLVE_SLOTS", 1);
     stream_min_n = env_int("PNEC_B200_STREAM_MIN_N", 896);
     copy_threads = env_int("PNEC_B200_COPY_THREADS", 0);
   }
@@ -257,6 +260,7 @@ struct pnec_handle {
   int device = 0;
   int sm_count = 0;
   size_t smem_optin = 0;
+  size_t smem_per_sm = 0;
   int64_t launches = 0;
   Config cfg;
   // staging for HOST-memspace calls and for the device copy of offsets
@@ -273,6 +277,8 @@ struct pnec_handle {
   DevBuf d_rs_state, d_rs_defer, d_rs_prefix, d_rs_hyp;  // pass 2 of the RANSAC stage (pnec_ransac.cuh)
   DevBuf d_kp_hp, d_kp_tp, d_kp_hc, d_kp_tc, d_kp_hi, d_kp_ti;  // keypoint tables and match indices (HOST callers)
   DevBuf d_pk_ct, d_pk_ch;  // PNEC_COV_PACKED covariances of HOST callers before expansion
+  DevBuf d_slot_ctr;        // work counters of solve_slots_kernel, one {next pair, CTAs gone} per stream seen
+  std::vector<cudaStream_t> slot_ctr_streams;
   DevBuf d_kp_out[8];  // device outputs of the from-keypoints entry points for HOST callers
   static constexpr int kMaxChunks = 8;
   static constexpr int kMaxRounds = 64;
@@ -568,10 +574,108 @@ int launch_solve_stream_v(pnec_handle *h, const SolveArgs &a, cudaStream_t strea
   return launch_solve_stream_t<V, 4, 4, 3>(h, a, stream);
 }
 
+// solve_slots_kernel draws its pairs from a device counter that the kernel itself rewinds when its last
+// CTA leaves.  Launches on one stream run one after the other and can share a counter; every stream the
+// handle sees gets its own (64 of them; beyond that the kernel falls back to a static partition).
+constexpr int kSlotCounters = 64;
+int slot_counter(pnec_handle *h, cudaStream_t stream, unsigned int **out) {
+  *out = nullptr;
+  if (!h->d_slot_ctr.p) {
+    PNEC_CUDA(h->d_slot_ctr.ensure(kSlotCounters * 2 * sizeof(unsigned int)));
+    PNEC_CUDA(cudaMemset(h->d_slot_ctr.p, 0, kSlotCounters * 2 * sizeof(unsigned int)));
+    PNEC_CUDA(cudaDeviceSynchronize());
+  }
+  size_t i = 0;
+  for (; i < h->slot_ctr_streams.size(); ++i)
+    if (h->slot_ctr_streams[i] == stream) break;
+  if (i == h->slot_ctr_streams.size()) {
+    if (i == kSlotCounters) return PNEC_OK;
+    h->slot_ctr_streams.push_back(stream);
+  }
+  *out = static_cast<unsigned int *>(h->d_slot_ctr.p) + 2 * i;
+  return PNEC_OK;
+}
+
+// Two slots per CTA, two CTAs per SM: the capacity of a slot in correspondences (a multiple of 32), 0 if
+// the kernel cannot be resident twice.
+template <int V>
+int slots_capacity(pnec_handle *h, int *static_smem) {
+  cudaFuncAttributes fa{};
+  if (cudaFuncGetAttributes(&fa, solve_slots_kernel<V, 2>) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  *static_smem = static_cast<int>(fa.sharedSizeBytes);
+  const long long per_cta = static_cast<long long>(h->smem_per_sm) / 2 - 1024 - static_cast<long long>(fa.sharedSizeBytes);
+  const long long cap = per_cta / (2LL * SlotLayout<V>::kDoubles * 8);
+  return static_cast<int>(std::max<long long>(0, cap & ~31LL));
+}
+
+template <int V>
+int launch_solve_slots_v(pnec_handle *h, SolveArgs a, long long need, cudaStream_t stream, bool *done) {
+  static int cap_max = -1, static_smem = 0;  // per process: the same kernel image on every device of a box
+  if (cap_max < 0) cap_max = slots_capacity<V>(h, &static_smem);
+  const long long cap = (need + 31) & ~31LL;
+  if (cap > cap_max) return PNEC_OK;
+  auto kern = solve_slots_kernel<V, 2>;
+  const size_t dyn = static_cast<size_t>(2) * SlotLayout<V>::kDoubles * 8 * static_cast<size_t>(cap);
+  PNEC_CUDA(ensure_dyn_smem(h, kern, dyn));
+  int rc = slot_counter(h, stream, &a.work_counter);
+  if (rc != PNEC_OK) return rc;
+  a.cap_elems = static_cast<int>(cap);
+  a.use_bulk = 1;
+  a.dbg = nullptr;
+  const unsigned grid = static_cast<unsigned>(std::min<long long>(2LL * h->sm_count, (a.bv.num_problems + 1) / 2));
+  kern<<<grid, (kSlotEvalWarps + 2) * 32, dyn, stream>>>(a);
+  PNEC_CUDA(cudaGetLastError());
+  h->launches++;
+#ifdef PNEC_SLOT_TIMING
+  if (h->cfg.dump_timing) {
+    cudaDeviceSynchronize();
+    unsigned long long pr[16], zero[16] = {0};
+    cudaMemcpyFromSymbol(pr, g_slot_probe, sizeof(pr));
+    cudaMemcpyToSymbol(g_slot_probe, zero, sizeof(zero));
+    const double B = static_cast<double>(a.bv.num_problems);
+    std::fprintf(stderr, "[slots, cycles per pair] init %.0f load1 %.0f repack %.0f load2 %.0f wait-eval %.0f lm %.0f total %.0f | "
+                 "eval warps (per warp, per pair): busy %.0f poll %.0f | passes %.2f\n",
+                 pr[9] / B, pr[0] / B, pr[1] / B, pr[2] / B, pr[3] / B, pr[4] / B, pr[5] / B,
+                 pr[6] / B / kSlotEvalWarps, pr[7] / B / kSlotEvalWarps, pr[8] / B);
+#ifdef PNEC_PHASE_TIMING
+    unsigned long long probe[8], zero8[8] = {0};
+    cudaMemcpyFromSymbol(probe, g_lm_probe, sizeof(probe));
+    cudaMemcpyToSymbol(g_lm_probe, zero8, sizeof(zero8));
+    std::fprintf(stderr, "[lm_step probes, cycles per pair] judge %.0f bookkeeping %.0f tr-step %.0f candidate %.0f store %.0f\n",
+                 (double)probe[0] / B, (double)probe[1] / B, (double)probe[2] / B, (double)probe[3] / B, (double)probe[4] / B);
+#endif
+  }
+#endif
+  *done = true;
+  return PNEC_OK;
+}
+
 int launch_solve(pnec_handle *h, const SolveArgs &a0, int variant, long long max_n,
                  cudaStream_t stream) {
   SolveArgs a = a0;
   if (a.bv.num_problems == 0) return PNEC_OK;
+  // Batches that oversubscribe the device with pairs small enough for four slots per SM: evaluation
+  // and LM update decoupled (pnec_solve_slots.cuh).  Below that every pair gets its own CTA at once.
+  const int slots_mode = h->cfg.solve_slots;
+  if (slots_mode != 0 && bulk_ok(a.bv) && !h->cfg.no_bulk && max_n > 0 &&
+      (slots_mode == 2 || a.bv.num_problems >= 3LL * h->sm_count)) {
+    // a pair starts at an even correspondence index of its arrays (16-byte alignment of the bulk copies):
+    // one more element when its range starts at an odd one
+    const bool even_starts = !a.bv.offsets && (a.bv.n_uniform % 2 == 0);
+    const long long need = max_n + (even_starts ? 0 : 1);
+    bool done = false;
+    int rc;
+    switch (variant) {
+      case PNEC_VARIANT_NEC: rc = launch_solve_slots_v<PNEC_VARIANT_NEC>(h, a, need, stream, &done); break;
+      case PNEC_VARIANT_TARGET: rc = launch_solve_slots_v<PNEC_VARIANT_TARGET>(h, a, need, stream, &done); break;
+      case PNEC_VARIANT_HOST: rc = launch_solve_slots_v<PNEC_VARIANT_HOST>(h, a, need, stream, &done); break;
+      default: rc = launch_solve_slots_v<PNEC_VARIANT_SYMMETRIC>(h, a, need, stream, &done); break;
+    }
+    if (rc != PNEC_OK || done) return rc;
+  }
   // Large frame pairs: stream every pass (bulk-copy rings) instead of keeping one pair per SM
   // resident.  Needs 16-byte aligned arrays; SYMMETRIC (192 B / correspondence) stays resident-first.
   const long long stream_min_n = h->cfg.stream_min_n;
@@ -1086,6 +1190,7 @@ int pnec_create(int device, pnec_handle **out) {
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
   h->smem_optin = prop.sharedMemPerBlockOptin;
+  h->smem_per_sm = prop.sharedMemPerMultiprocessor;
   h->cfg.load();
   h->stager.copy_threads = h->cfg.copy_threads;
   *out = h;
@@ -1108,6 +1213,7 @@ void pnec_destroy(pnec_handle *h) {
   for (DevBuf &b : h->d_kp_out) b.release();
   h->d_pk_ct.release();
   h->d_pk_ch.release();
+  h->d_slot_ctr.release();
   for (int i = 0; i < pnec_handle::kMaxChunks; ++i) {
     if (h->side[i]) cudaStreamDestroy(h->side[i]);
     if (h->lm_side[i]) cudaStreamDestroy(h->lm_side[i]);

@@ -13,11 +13,11 @@ namespace pnec {
 // problem.  Lives in shared memory between evaluations so that it costs no
 // registers while the CTA streams correspondences.
 //
-// The per-iteration update is the serial part of a solve (one warp, the other
-// warps of the CTA wait), so it is written as straight-line, branch-free code:
-// Newton-refined MUFU reciprocals instead of IEEE division, LDL^T instead of
-// Cholesky (no square roots), small-angle polynomials + angle addition instead of
-// sin/cos calls.  All of it stays within a few ulp of the IEEE forms.
+// The per-iteration update is the serial part of a solve, so it is written as straight-line code
+// shared out over the lanes of one warp (see "warp-cooperative update" below): Newton-refined MUFU
+// reciprocals instead of IEEE division, adjugate block elimination instead of Cholesky (no square
+// roots), small-angle polynomials + angle addition instead of sin/cos calls.  All of it stays within
+// a few ulp of the IEEE forms.
 struct LMState {
   // Points and totals are double-buffered so that accepting a step flips an index
   // instead of copying: pts[xi] is the accepted point x, pts[xi ^ 1] the candidate;
@@ -32,6 +32,7 @@ struct LMState {
   int xi, ti;
   int iteration, num_invalid, reuse_diagonal, step_successful, grad_converged, status, done;
   int pass_mode;     // what the CTA evaluates next: kPassFull or kPassCost
+  double xch[40];    // exchange between the lanes of the warp that runs the update (lm_trust_region_step)
 };
 
 constexpr int kPassFull = 0;  // residual + Jacobian + JtJ/Jtr at the candidate
@@ -163,117 +164,125 @@ __device__ __forceinline__ bool gradient_converged(const double x[6], const doub
   return quaternion_chord_max(x + 2, g + 2) <= tol;
 }
 
-// 5x5 SPD solve A d = b by block elimination over the (theta, phi | rotation) split with
-// closed-form 2x2 / 3x3 adjugate inverses: 2 reciprocals and a ~30-deep dependent chain
-// (LDL^T + substitutions is ~65 deep).  Returns false if A is not positive definite
-// (Sylvester: all leading minors of P and of the Schur complement positive) or the
-// solution is not finite: LINEAR_SOLVER_FAILURE in Ceres terms, an invalid step.
-__device__ __forceinline__ bool spd_solve5(const double A[5][5], const double b[5], double d[5]) {
-  // P = A[0:2,0:2]
-  const double p00 = A[0][0], p01 = A[0][1], p11 = A[1][1];
+// ---------------------------------------------------------------- warp-cooperative update
+//
+// The update between two evaluations is the serial part of a solve and shares its SM sub-partition's
+// fp64 pipe with the evaluation warps of other pairs, where every instruction of a lone lane costs as
+// much as a full-width one.  So the warp works on it together: each stage computes its independent
+// outputs (the five damped diagonal entries, the 2x3 block W and u, the six entries of the Schur
+// complement and its right-hand side, the six cofactors, the three small-angle evaluations, the four
+// quaternion components, the eighteen pose constants) one per lane, and the lanes exchange them through
+// a 40-double scratch in shared memory.  About 150 fp64 instructions per update instead of 650.
+// The arithmetic of every output is what the single-lane form computed.
+
+// scratch layout (LMState::xch)
+constexpr int kXDiag = 0;   // 5: H_aa + lambda_a
+constexpr int kXW0 = 5;     // 4: W0[0..2], u0        (P^-1 Q, P^-1 b1: first rows)
+constexpr int kXW1 = 9;     // 4: W1[0..2], u1
+constexpr int kXS = 13;     // 6: S00 S01 S02 S11 S12 S22 (Schur complement), then
+constexpr int kXC = 19;     // 3: c = b2 - Q^T u
+constexpr int kXAdj = 22;   // 6: c00 c01 c02 c11 c12 c22 (cofactors of S)
+constexpr int kXD = 28;     // 5: d
+constexpr int kXIn = 33;    // 5: lambda_a d_a + g_a
+
+// value `lane` of a table of 4-bit entries
+__device__ __forceinline__ int nib(unsigned long long table, int lane) {
+  return static_cast<int>((table >> (4 * lane)) & 0xFull);
+}
+
+// One trust-region solve attempt at the accepted point, all 32 lanes.  Ceres solves, in Jacobi-scaled
+// coordinates, (S H S + D) y = S g with D = diag / radius and takes delta = -S y.  With d = S y this is
+// (H + S^-1 D S^-1) d = g: the same system without the 45 scaling products, and
+// model_cost_change = (y.Sg + y^T D y) / 2 = sum d_a (g_a + L_a d_a) / 2, L = D / s^2.
+// The 5x5 SPD system is solved by block elimination over the (theta, phi | rotation) split with
+// closed-form 2x2 / 3x3 adjugate inverses (2 reciprocals).  Lane a < 5 owns parameter a: diag_l in/out,
+// d[0..4] out on every lane.  Returns false for an invalid step: LINEAR_SOLVER_FAILURE in Ceres terms
+// (not positive definite by Sylvester's criterion, or a non-finite solution) or model_cost_change <= 0.
+__device__ __forceinline__ bool lm_trust_region_step(const double *Hg, double *xch, int lane, int a5, double haa,
+                                                     double scale_l, double inv_scale2_l, double &diag_l,
+                                                     bool reuse_diagonal, double inv_radius,
+                                                     const pnec_solver_opts &o, double d[5], double &mcc) {
+  if (!reuse_diagonal)  // squared column norm of the scaled Jacobian, clamped
+    diag_l = fmin(fmax(haa * scale_l * scale_l, o.min_lm_diagonal), o.max_lm_diagonal);
+  const double lam_l = diag_l * inv_radius * inv_scale2_l;
+  if (lane < 5) xch[kXDiag + lane] = haa + lam_l;
+  __syncwarp();
+  // P = A[0:2,0:2] and its inverse: every lane
+  const double p00 = xch[kXDiag], p11 = xch[kXDiag + 1], p01 = Hg[1];
   const double detP = fma(p00, p11, -p01 * p01);
   const double iP = fast_rcp(detP);
-  const double i00 = p11 * iP, i01 = -p01 * iP, i11 = p00 * iP;  // P^-1
-  // W = P^-1 Q (2x3), u = P^-1 b1
-  double W0[3], W1[3];
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    W0[j] = fma(i00, A[0][2 + j], i01 * A[1][2 + j]);
-    W1[j] = fma(i01, A[0][2 + j], i11 * A[1][2 + j]);
-  }
-  const double u0 = fma(i00, b[0], i01 * b[1]), u1 = fma(i01, b[0], i11 * b[1]);
-  // Schur complement S = R - Q^T W (symmetric 3x3), c = b2 - Q^T u
-  double S[3][3], c[3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-#pragma unroll
-    for (int j = i; j < 3; ++j) {
-      S[i][j] = A[2 + i][2 + j] - fma(A[0][2 + i], W0[j], A[1][2 + i] * W1[j]);
-      S[j][i] = S[i][j];
+  const double i00 = p11 * iP, i01 = -p01 * iP, i11 = p00 * iP;
+  {  // W = P^-1 Q (lanes 0..2: column j), u = P^-1 b1 (lane 3)
+    const int l = min(lane, 3);
+    const double x = Hg[l < 3 ? 2 + l : 15], y = Hg[l < 3 ? 6 + l : 16];  // A[0][2+j], A[1][2+j] | b0, b1
+    if (lane < 4) {
+      xch[kXW0 + lane] = fma(i00, x, i01 * y);
+      xch[kXW1 + lane] = fma(i01, x, i11 * y);
     }
-    c[i] = b[2 + i] - fma(A[0][2 + i], u0, A[1][2 + i] * u1);
   }
-  // adjugate of S
-  const double c00 = fma(S[1][1], S[2][2], -S[1][2] * S[1][2]);
-  const double c01 = fma(S[0][2], S[1][2], -S[0][1] * S[2][2]);
-  const double c02 = fma(S[0][1], S[1][2], -S[0][2] * S[1][1]);
-  const double c11 = fma(S[0][0], S[2][2], -S[0][2] * S[0][2]);
-  const double c12 = fma(S[0][1], S[0][2], -S[0][0] * S[1][2]);
-  const double c22 = fma(S[0][0], S[1][1], -S[0][1] * S[0][1]);
-  const double detS = fma(S[0][0], c00, fma(S[0][1], c01, S[0][2] * c02));
+  __syncwarp();
+  {  // Schur complement S = R - Q^T W (lanes 0..5: (0,0) (0,1) (0,2) (1,1) (1,2) (2,2)), c = b2 - Q^T u (lanes 6..8)
+    const int l = min(lane, 8);
+    const int i = nib(0x210211000ull, l), k = nib(0x333221210ull, l);
+    const bool diagonal = (l == 0) || (l == 3) || (l == 5);
+    const double base = (l < 6) ? (diagonal ? xch[kXDiag + 2 + i] : Hg[9 + l]) : Hg[17 + i];
+    const double sv = base - fma(Hg[2 + i], xch[kXW0 + k], Hg[6 + i] * xch[kXW1 + k]);
+    if (lane < 9) xch[kXS + lane] = sv;
+  }
+  __syncwarp();
+  const double *S = xch + kXS;
+  {  // cofactors of S: lanes 0..5
+    const int l = min(lane, 5);
+    const double v = fma(S[nib(0x010123ull, l)], S[nib(0x325445ull, l)], -S[nib(0x102214ull, l)] * S[nib(0x142354ull, l)]);
+    if (lane < 6) xch[kXAdj + lane] = v;
+  }
+  __syncwarp();
+  const double *C = xch + kXAdj;
+  const double S00 = S[0], c22 = C[5];
+  const double detS = fma(S00, C[0], fma(S[1], C[1], S[2] * C[2]));
   const double iS = fast_rcp(detS);
-  const double n0 = fma(c00, c[0], fma(c01, c[1], c02 * c[2]));
-  const double n1 = fma(c01, c[0], fma(c11, c[1], c12 * c[2]));
-  const double n2 = fma(c02, c[0], fma(c12, c[1], c22 * c[2]));
-  d[2] = n0 * iS;
-  d[3] = n1 * iS;
-  d[4] = n2 * iS;
-  d[0] = u0 - fma(W0[0], d[2], fma(W0[1], d[3], W0[2] * d[4]));
-  d[1] = u1 - fma(W1[0], d[2], fma(W1[1], d[3], W1[2] * d[4]));
-  bool ok = (p00 > 0.0) && (detP > 0.0) && (S[0][0] > 0.0) && (c22 > 0.0) && (detS > 0.0);
-#pragma unroll
-  for (int i = 0; i < 5; ++i) ok = ok && (fabs(d[i]) < CUDART_INF);
-  return ok;
-}
-
-// One trust-region solve attempt at the accepted point.  Ceres solves, in Jacobi-scaled
-// coordinates, (S H S + D) y = S g with D = diag / radius and takes delta = -S y.  With
-// d = S y this is (H + S^-1 D S^-1) d = g: the same system without the 45 scaling products,
-// and model_cost_change = (y.Sg + y^T D y) / 2 = sum d_a (g_a + L_a d_a) / 2, L = D / s^2.
-// Returns false for an invalid step (LINEAR_SOLVER_FAILURE or model_cost_change <= 0).
-__device__ __forceinline__ bool lm_trust_region_step(const double *Hg, const double scale[5],
-                                                     const double inv_scale2[5], double diag[5],
-                                                     bool reuse_diagonal, double inv_radius,
-                                                     const pnec_solver_opts &o, double delta[5],
-                                                     double &mcc) {
-  double A[5][5], lam[5], d[5];
-#pragma unroll
-  for (int a = 0; a < 5; ++a) {
-#pragma unroll
-    for (int b = a; b < 5; ++b) {
-      A[a][b] = Hg[tri(a, b)];
-      A[b][a] = A[a][b];
-    }
+  {  // rotation part: lanes 0..2, row r of adj(S) . c / det
+    const int r = min(lane, 2);
+    const int e1 = nib(0x431ull, r), e2 = nib(0x542ull, r);  // rows (0 1 2), (1 3 4), (2 4 5) of the packed cofactors
+    const double n = fma(C[r], xch[kXC], fma(C[e1], xch[kXC + 1], C[e2] * xch[kXC + 2]));
+    if (lane < 3) xch[kXD + 2 + lane] = n * iS;
   }
-#pragma unroll
-  for (int a = 0; a < 5; ++a) {
-    if (!reuse_diagonal)  // squared column norm of the scaled Jacobian, clamped
-      diag[a] = fmin(fmax(A[a][a] * scale[a] * scale[a], o.min_lm_diagonal), o.max_lm_diagonal);
-    lam[a] = diag[a] * inv_radius * inv_scale2[a];
-    A[a][a] += lam[a];
+  __syncwarp();
+  {  // translation part: lanes 0..1
+    const int r = min(lane, 1);
+    const double *W = xch + (r ? kXW1 : kXW0);
+    const double v = W[3] - fma(W[0], xch[kXD + 2], fma(W[1], xch[kXD + 3], W[2] * xch[kXD + 4]));
+    if (lane < 2) xch[kXD + lane] = v;
   }
-  bool valid = spd_solve5(A, Hg + 15, d);
+  __syncwarp();
+  if (lane < 5) xch[kXIn + lane] = fma(lam_l, xch[kXD + a5], Hg[15 + a5]);
+  __syncwarp();
+  bool ok = (p00 > 0.0) && (detP > 0.0) && (S00 > 0.0) && (c22 > 0.0) && (detS > 0.0);
   mcc = 0.0;
 #pragma unroll
-  for (int a = 0; a < 5; ++a) mcc = fma(d[a], fma(lam[a], d[a], Hg[15 + a]), mcc);
+  for (int a = 0; a < 5; ++a) {
+    d[a] = xch[kXD + a];
+    ok = ok && (fabs(d[a]) < CUDART_INF);
+    mcc = fma(d[a], xch[kXIn + a], mcc);
+  }
   mcc *= 0.5;
-#pragma unroll
-  for (int a = 0; a < 5; ++a) delta[a] = -d[a];
-  return valid && (mcc > 0.0);
+  return ok && (mcc > 0.0);
 }
 
-// The whole LM update between two evaluations, straight-line:
+// The whole LM update between two evaluations, executed by all 32 lanes of one warp (converged):
 //   (FIRST)  IterationZero bookkeeping,
 //   (!FIRST) FunctionToleranceReached, IsStepSuccessful, StepAccepted / StepRejected,
 //   then FinalizeIterationAndCheckIfMinimizerCanContinue, ComputeTrustRegionStep (invalid
 //   steps retried in place: they need no evaluation), candidate = Plus(x, delta),
 //   ParameterToleranceReached, choice of the next pass, pose constants of the candidate.
-// `st` is the shared-memory state; every lane of the calling warp executes this with
-// identical values, lane 0 stores.  New totals are in st.tot[st.ti ^ 1].
+// `st` is the shared-memory state; the new totals are in st.tot[st.ti ^ 1].  The caller synchronises
+// the warp before reading what this wrote.
 #ifdef PNEC_PHASE_TIMING
 __device__ unsigned long long g_lm_probe[8];
 #define LM_PROBE(k) do { const long long t_now = clock64(); if (lane == 0) atomicAdd(&g_lm_probe[k], (unsigned long long)(t_now - t_prev)); t_prev = t_now; } while (0)
 #else
 #define LM_PROBE(k) do { } while (0)
 #endif
-
-// The LM update runs on lane 0 of the LM warp only (measured 4 % faster than all 32 lanes
-// redundantly, and it keeps the fp64 pipe free for the co-resident CTAs' evaluations).
-// PNEC_LM_FULL_WARP=1 restores the redundant variant.
-#ifndef PNEC_LM_FULL_WARP
-#define PNEC_LM_FULL_WARP 0
-#endif
-constexpr bool kLmFullWarp = PNEC_LM_FULL_WARP != 0;
 
 template <bool FIRST>
 __device__ __forceinline__ void lm_step(LMState &st, const pnec_solver_opts &o, int lane,
@@ -318,19 +327,21 @@ __device__ __forceinline__ void lm_step(LMState &st, const pnec_solver_opts &o, 
   const double *Hg = st.tot[nti];
   const double *x = st.pts[nxi];
   const double *sc = st.scs[nxi];
+  double *cnd = st.pts[nxi ^ 1], *scn = st.scs[nxi ^ 1];  // the candidate's slots
 
-  double scale[5], inv_scale2[5], diag[5];
-#pragma unroll
-  for (int a = 0; a < 5; ++a) {
-    if (FIRST) {
-      const double one_plus = 1.0 + fast_sqrt(Hg[tri(a, a)]);  // scale = 1 / (1 + |J col|)
-      scale[a] = o.jacobi_scaling ? fast_rcp(one_plus) : 1.0;
-      inv_scale2[a] = o.jacobi_scaling ? one_plus * one_plus : 1.0;
-    } else {
-      scale[a] = st.scale[a];
-      inv_scale2[a] = st.inv_scale2[a];
-    }
-    diag[a] = FIRST ? 0.0 : st.diag[a];
+  // lane a < 5 owns parameter a (the others shadow parameter 4)
+  const int a5 = min(lane, 4);
+  const double haa = Hg[a5 * 5 - (a5 * (a5 - 1)) / 2];  // tri(a, a)
+  double scale_l, inv_scale2_l, diag_l;
+  if (FIRST) {
+    const double one_plus = 1.0 + fast_sqrt(haa);  // scale = 1 / (1 + |J col|)
+    scale_l = o.jacobi_scaling ? fast_rcp(one_plus) : 1.0;
+    inv_scale2_l = o.jacobi_scaling ? one_plus * one_plus : 1.0;
+    diag_l = 0.0;
+  } else {
+    scale_l = st.scale[a5];
+    inv_scale2_l = st.inv_scale2[a5];
+    diag_l = st.diag[a5];
   }
   // the gradient test of a newly accepted point (cheap unless |g| is already tiny)
   int grad_conv = st.grad_converged;
@@ -338,13 +349,14 @@ __device__ __forceinline__ void lm_step(LMState &st, const pnec_solver_opts &o, 
   LM_PROBE(1);  // scale, gradient test
   int iteration = st.iteration, num_invalid = st.num_invalid, step_successful = accept ? 1 : 0;
   int status = st.status, done = 0;
-  double delta[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, mcc = 0.0;
+  double d[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, mcc = 0.0;
   for (;;) {  // FinalizeIterationAndCheckIfMinimizerCanContinue
     if (iteration >= o.max_num_iterations) { status = PNEC_STATUS_MAX_ITERATIONS; done = 1; break; }
     if (step_successful && grad_conv) { status = PNEC_STATUS_CONVERGED_GRADIENT; done = 1; break; }
     if (inv_radius * o.min_trust_region_radius >= 1.0) { status = PNEC_STATUS_CONVERGED_RADIUS; done = 1; break; }
     ++iteration;
-    const bool valid = lm_trust_region_step(Hg, scale, inv_scale2, diag, reuse_diagonal != 0, inv_radius, o, delta, mcc);
+    const bool valid = lm_trust_region_step(Hg, st.xch, lane, a5, haa, scale_l, inv_scale2_l, diag_l,
+                                            reuse_diagonal != 0, inv_radius, o, d, mcc);
     reuse_diagonal = 1;
     if (valid) { num_invalid = 0; break; }
     if (++num_invalid >= o.max_num_consecutive_invalid_steps) { status = PNEC_STATUS_FAILURE; done = 1; break; }
@@ -353,38 +365,45 @@ __device__ __forceinline__ void lm_step(LMState &st, const pnec_solver_opts &o, 
   }
 
   LM_PROBE(2);  // trust-region step
-  double cand[6], scc[4];
   int pass_mode = kPassFull;
   if (!done) {
-    cand[0] = x[0] + delta[0];
-    cand[1] = x[1] + delta[1];
+    const double delta[5] = {-d[0], -d[1], -d[2], -d[3], -d[4]};
     const double zt = delta[0] * delta[0], zp = delta[1] * delta[1];
     const double zq = fma(delta[2], delta[2], fma(delta[3], delta[3], delta[4] * delta[4]));
     if (fmax(fmax(zt, zp), zq) <= kSmallAngle2) {
-      // common case, one branch: three independent small-angle evaluations + angle addition
-      double sct, cdt, scp, cdp, sq, cq;
-      small_sinc_cos(zt, sct, cdt);
-      small_sinc_cos(zp, scp, cdp);
-      small_sinc_cos(zq, sq, cq);
-      const double sdt = delta[0] * sct, sdp = delta[1] * scp;
-      scc[0] = fma(sc[0], cdt, sc[1] * sdt);
-      scc[1] = fma(sc[1], cdt, -sc[0] * sdt);
-      scc[2] = fma(sc[2], cdp, sc[3] * sdp);
-      scc[3] = fma(sc[3], cdp, -sc[2] * sdp);
-      const double dx = sq * delta[2], dy = sq * delta[3], dz = sq * delta[4];
-      const double xx = x[2], xy = x[3], xz = x[4], xw = x[5];
-      cand[5] = cq * xw - dx * xx - dy * xy - dz * xz;
-      cand[2] = cq * xx + dx * xw + dy * xz - dz * xy;
-      cand[3] = cq * xy - dx * xz + dy * xw + dz * xx;
-      cand[4] = cq * xz + dx * xy - dy * xx + dz * xw;
-    } else {
+      // common case: the three small-angle evaluations on lanes 0 (theta), 1 (phi), 2.. (rotation)
+      double sinc, cs;
+      small_sinc_cos(lane == 0 ? zt : lane == 1 ? zp : zq, sinc, cs);
+      if (lane < 2) {  // angle addition
+        const double s0 = sc[2 * lane], c0 = sc[2 * lane + 1], sd = delta[lane] * sinc;
+        cnd[lane] = x[lane] + delta[lane];
+        scn[2 * lane] = fma(s0, cs, c0 * sd);
+        scn[2 * lane + 1] = fma(c0, cs, -s0 * sd);
+      } else if (lane < 6) {  // EigenQuaternionManifold::Plus, component k of (x, y, z, w)
+        const int k = lane - 2;
+        const double *q = x + 2;
+        //   x' = cq x + dx w + dy z - dz y     y' = cq y - dx z + dy w + dz x
+        //   z' = cq z + dx y - dy x + dz w     w' = cq w - dx x - dy y - dz z
+        const double dx = sinc * delta[2], dy = sinc * delta[3], dz = sinc * delta[4];
+        const double sx = (k == 1 || k == 3) ? -dx : dx, sy = (k == 2 || k == 3) ? -dy : dy, sz = (k == 0 || k == 3) ? -dz : dz;
+        cnd[2 + k] = fma(sz, q[nib(0x2301ull, k)], fma(sy, q[nib(0x1032ull, k)], fma(sx, q[nib(0x0123ull, k)], cs * q[k])));
+      }
+    } else if (lane == 0) {
+      double cand[6], scc[4];
+      cand[0] = x[0] + delta[0];
+      cand[1] = x[1] + delta[1];
       lm_candidate_large_step(x, sc, delta, cand, scc);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) cnd[i] = cand[i];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) scn[i] = scc[i];
     }
+    __syncwarp();
     // ParameterToleranceReached depends on the step only.  Ceres evaluates the candidate's
     // cost first and then returns without applying the step, so the evaluation cannot change
     // the outcome: decide here and skip it.
-    const double e0 = x[0] - cand[0], e1 = x[1] - cand[1], e2 = x[2] - cand[2];
-    const double e3 = x[3] - cand[3], e4 = x[4] - cand[4], e5 = x[5] - cand[5];
+    const double e0 = x[0] - cnd[0], e1 = x[1] - cnd[1], e2 = x[2] - cnd[2];
+    const double e3 = x[3] - cnd[3], e4 = x[4] - cnd[4], e5 = x[5] - cnd[5];
     const double sn = fma(e0, e0, e1 * e1) + fma(e2, e2, e3 * e3) + fma(e4, e4, e5 * e5);
     // |x| <= |theta| + |phi| + |q| gives a cheap upper bound of the tolerance; the exact
     // norm is only formed when the step is small enough for the test to possibly pass.
@@ -404,32 +423,46 @@ __device__ __forceinline__ void lm_step(LMState &st, const pnec_solver_opts &o, 
     pass_mode = (mcc <= 1.05 * o.function_tolerance * x_cost) ? kPassCost : kPassFull;
   }
   LM_PROBE(3);  // candidate
-  if (kLmFullWarp) __syncwarp();  // every lane has read the state it needs; lane 0 may now overwrite it
+  if (!done && lane < 18) {
+    // pose constants of the candidate, one per lane: R (row-major) on lanes 0..8, t, dt/dtheta, dt/dphi on 9..17
+    const double *q = cnd + 2;
+    double v;
+    if (lane < 9) {
+      //   R0 = 1 - (tyy + tzz)   R1 = txy - twz         R2 = txz + twy          with tab = 2 q_a q_b
+      //   R3 = txy + twz         R4 = 1 - (txx + tzz)   R5 = tyz - twx
+      //   R6 = txz - twy         R7 = tyz + twx         R8 = 1 - (txx + tyy)
+      const double p = (2.0 * q[nib(0x022201211ull, lane)]) * q[nib(0x010100001ull, lane)];
+      const double r = (2.0 * q[nib(0x101022122ull, lane)]) * q[nib(0x133323332ull, lane)];
+      const bool diagonal = (lane == 0) || (lane == 4) || (lane == 8);
+      const bool minus = (lane == 1) || (lane == 5) || (lane == 6);
+      v = diagonal ? 1.0 - (p + r) : (minus ? p - r : p + r);
+    } else {
+      //   t = (st cp, st sp, ct)   dt/dtheta = (ct cp, ct sp, -st)   dt/dphi = (-st sp, st cp, 0)
+      const int m = lane - 9;
+      const double u = scn[nib(0x000011100ull, m)];                      // st or ct
+      const double su = (m == 5 || m == 6) ? -u : u;
+      const int vi = nib(0x032423423ull, m);                             // 2: sp, 3: cp, 4: the constant 1
+      const double w = (vi == 4) ? 1.0 : scn[vi];
+      v = (m == 8) ? 0.0 : su * w;
+    }
+    reinterpret_cast<double *>(&s_pc)[lane] = v;
+  }
+  if (lane < 5) {
+    if (FIRST) {
+      st.scale[lane] = scale_l;
+      st.inv_scale2[lane] = inv_scale2_l;
+    }
+    st.diag[lane] = diag_l;
+  }
+  const double imcc = (mcc > 0.0) ? fast_rcp(mcc) : 0.0;
   if (lane == 0) {
-    if (!done) {
-      PoseConst pcn;
-      make_pose_const_sc(scc, cand + 2, pcn);
-      s_pc = pcn;
-#pragma unroll
-      for (int i = 0; i < 6; ++i) st.pts[nxi ^ 1][i] = cand[i];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) st.scs[nxi ^ 1][i] = scc[i];
-    }
-#pragma unroll
-    for (int a = 0; a < 5; ++a) {
-      if (FIRST) {
-        st.scale[a] = scale[a];
-        st.inv_scale2[a] = inv_scale2[a];
-      }
-      st.diag[a] = diag[a];
-    }
     st.xi = nxi;
     st.ti = nti;
     st.x_cost = x_cost;
     if (FIRST) st.initial_cost = x_cost;
     st.inv_radius = inv_radius;
     st.decrease_factor = decrease_factor;
-    st.inv_model_cost_change = (mcc > 0.0) ? fast_rcp(mcc) : 0.0;  // off the critical path
+    st.inv_model_cost_change = imcc;
     st.iteration = iteration;
     st.num_invalid = num_invalid;
     st.reuse_diagonal = reuse_diagonal;

@@ -21,6 +21,7 @@ struct SolveArgs {
   int cap_elems;  // resident capacity of the dynamic smem, in correspondences (even)
   int use_bulk;   // all base pointers 16-byte aligned
   long long *dbg; // PNEC_PHASE_TIMING builds only: per-CTA cycle counters
+  unsigned int *work_counter;  // solve_slots_kernel: {next pair, CTAs that have left}; nullptr = static partition
 };
 
 // PNECCeres::InitValues(orientation, translation) (pnec_ceres.cc:188-192) + the start state of
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) solve_kernel(const __grid_const
         const long long t1 = clock64();
         t_e += t1 - t0;
 #endif
-        if (warp == lmw && (kLmFullWarp || lane == 0)) {
+        if (warp == lmw) {
           if (first) lm_step<true>(s_lm, o, lane, s_pc);
           else lm_step<false>(s_lm, o, lane, s_pc);
         }
@@ -288,7 +289,7 @@ solve_stream_kernel(const __grid_constant__ SolveArgs args) {
         if (warp == lmw) lm_after_cost_pass(s_lm, cand_cost, o, lane);
       } else {
         block_reduce<NW>(acc, s_part, warp, lane, s_lm.tot[s_lm.ti ^ 1], lmw);
-        if (warp == lmw && (kLmFullWarp || lane == 0)) {
+        if (warp == lmw) {
           if (first) lm_step<true>(s_lm, o, lane, s_pc);
           else lm_step<false>(s_lm, o, lane, s_pc);
         }

@@ -1,0 +1,372 @@
+// pnec_solve_slots.cuh — the LM solve of PNECCeres::Optimize (src/optimization/pnec_ceres.cc:70-168) for
+// large batches of frame pairs that fit shared memory: evaluation and LM update decoupled.
+//
+// solve_kernel gives every frame pair a CTA whose warps evaluate together and then wait at a barrier
+// while one lane runs the serial LM update: half of a pair's life its evaluation warps are parked, and
+// shared memory (not warps) caps the pairs resident per SM.  Here a CTA owns P pair SLOTS in shared
+// memory, one OWNER warp per slot and one group of evaluation warps for all of them:
+//
+//   owner warp of slot s   claims a pair (atomic work counter), bulk-copies it into the slot, repacks the
+//                          3x3 covariances to their symmetric part IN PLACE (96 instead of 120 B per
+//                          correspondence: four slots per SM at N = 512 instead of three), then loops
+//                          { post the candidate's pose constants -> wait for the 4 partial sums -> LM update }
+//                          and writes the result;
+//   evaluation warps       poll the slots, evaluate their quarter of whichever slot has a candidate posted
+//                          (residual + Jacobian row + J^T J / J^T r, or cost only) and hand the partial sums
+//                          to the owner.  They never wait for an LM update: while slot A is in its update
+//                          they evaluate slot B.
+//
+// Hand-over is by mbarriers (candidate posted: 1 arrival; partial sums ready: 4 arrivals), no
+// __syncthreads after start-up.  A pair's correspondences are assigned to lanes, and its partial sums
+// added, exactly as solve_kernel<V, 4, .> does: results are bit-identical to that kernel.
+#pragma once
+
+#include "pnec_solve.cuh"
+
+namespace pnec {
+
+constexpr int kSlotExit = 2;       // SlotCtl::mode besides kPassFull / kPassCost: no more pairs for this slot
+constexpr int kSlotEvalWarps = 4;  // evaluation warps per CTA (== the cross-warp split of solve_kernel<V, 4, .>)
+
+// Slot layout, in doubles, for `cap` correspondences (cap a multiple of 32):
+//   [K packed covariance areas, 6 cap each][f1: 3 cap][f2: 3 cap]
+// A packed covariance area is a sequence of 32-correspondence chunks [32 x (xx, xy, xz)][32 x (yy, yz, zz)]:
+// stride-3 accesses, free of bank conflicts (a plain stride of 6 doubles would be 2-way conflicted).
+template <int V>
+struct SlotLayout {
+  static constexpr int kCov = (VariantTraits<V>::kHasCt ? 1 : 0) + (VariantTraits<V>::kHasCh ? 1 : 0);
+  static constexpr int kDoubles = 6 + 6 * kCov;
+};
+
+#ifdef PNEC_SLOT_TIMING
+// debug build: cycles summed over the batch: 0 load trip 1, 1 repack, 2 load trip 2, 3 owner waits for the
+// evaluation, 4 LM update, 5 pair total, 6 evaluation warps busy, 7 evaluation warps polling, 8 passes, 9 init
+__device__ unsigned long long g_slot_probe[16];
+#define SLOT_PROBE(k) do { const long long t_now = clock64(); if (lane == 0) atomicAdd(&g_slot_probe[k], (unsigned long long)(t_now - t_prev)); t_prev = t_now; } while (0)
+#define SLOT_PROBE_START() long long t_prev = clock64()
+#else
+#define SLOT_PROBE(k) do { } while (0)
+#define SLOT_PROBE_START() do { } while (0)
+#endif
+
+struct SlotCtl {
+  LMState lm;
+  PoseConst pc;
+  double part[kSlotEvalWarps][kAccPad];
+  int head, span, mode, pad;
+};
+
+__device__ __forceinline__ bool mbar_test_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+// L2 prefetch of a byte range (the next pair of a slot, while the current one is being solved)
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
+template <int V>
+__device__ __forceinline__ void slot_load_corr(const double *base, int cap, int j, double a1[3], double a2[3],
+                                               double c1[6], double c2[6]) {
+  constexpr int K = SlotLayout<V>::kCov;
+  const double *f1 = base + 6 * K * cap + 3 * j;
+  const double *f2 = f1 + 3 * cap;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) a1[k] = f1[k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) a2[k] = f2[k];
+  const int off = 6 * (j & ~31) + 3 * (j & 31);
+  if (K >= 1) {
+    const double *p = base + off;
+    c1[0] = p[0]; c1[1] = p[1]; c1[2] = p[2]; c1[3] = p[96]; c1[4] = p[97]; c1[5] = p[98];
+  }
+  if (K == 2) {
+    const double *p = base + 6 * cap + off;
+    c2[0] = p[0]; c2[1] = p[1]; c2[2] = p[2]; c2[3] = p[96]; c2[4] = p[97]; c2[5] = p[98];
+  }
+}
+
+// One array of a slot load: `cb` (even) correspondences of `dpc` doubles each by bulk copy, plus the odd
+// last element of the whole batch by hand (cp.async.bulk moves 16-byte units and must not run past the end).
+__device__ __forceinline__ void slot_copy_array(double *dst, const double *src, int cb, bool tail, int dpc,
+                                                uint64_t *bar) {
+  if (tail) {
+    for (int k = 0; k < dpc; ++k) dst[dpc * cb + k] = src[dpc * cb + k];
+  }
+  if (cb > 0) bulk_g2s(dst, src, static_cast<uint32_t>(cb) * dpc * 8u, bar);
+}
+
+// Trip 1 of a slot load: the raw 3x3 covariances land at the front of the slot (72 B per correspondence
+// over what will be the packed covariances and f1), f2 goes to its final place when that is free.
+// Trip 2 (after the in-place repack): what trip 1 could not place.  Called by ONE lane.
+template <int V>
+__device__ __forceinline__ void slot_issue(const BatchView &bv, long long g0, int span, int cap, double *base,
+                                           uint64_t *bar, int trip) {
+  constexpr int K = SlotLayout<V>::kCov;
+  int cb = span + (span & 1);
+  bool tail = false;
+  if (g0 + cb > bv.total) {
+    cb = span - 1;
+    tail = true;
+  }
+  double *sf1 = base + 6 * K * cap, *sf2 = sf1 + 3 * cap;
+  const bool f1_now = (K == 0) ? (trip == 1) : (trip == 2);
+  const bool f2_now = (K == 1) ? (trip == 1) : f1_now;
+  const bool cov_now = (K > 0) && trip == 1;
+  const uint32_t bytes = static_cast<uint32_t>(cb) * 8u * ((f1_now ? 3 : 0) + (f2_now ? 3 : 0) + (cov_now ? 9 * K : 0));
+  mbar_arrive_expect_tx(bar, bytes);
+  if (cov_now) {
+    slot_copy_array(base, bv.ct + 9 * g0, cb, tail, 9, bar);
+    if (K == 2) slot_copy_array(base + 9 * cap, bv.ch + 9 * g0, cb, tail, 9, bar);
+  }
+  if (f1_now) slot_copy_array(sf1, bv.f1 + 3 * g0, cb, tail, 3, bar);
+  if (f2_now) slot_copy_array(sf2, bv.f2 + 3 * g0, cb, tail, 3, bar);
+}
+
+// In-place repack of one raw covariance area (9 doubles per correspondence from `src`) to the chunked
+// symmetric layout at `dst` <= src, by one warp, two 32-correspondence waves per turn.  Wave k writes
+// [192 k, 192 (k + 1)) and later waves read from 288 (k + 1) on: a wave never overwrites unread input.
+__device__ __forceinline__ void slot_repack(double *dst, const double *src, int span, int lane) {
+  for (int j0 = 0; j0 < span; j0 += 64) {
+    double p[2][6];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (j0 + 32 * u < span) {
+        const double *r = src + 9 * (j0 + 32 * u + lane);
+        double c[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) c[i] = r[i];
+        pack_sym(c, p[u]);
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (j0 + 32 * u < span) {
+        double *d = dst + 6 * (j0 + 32 * u) + 3 * lane;
+        d[0] = p[u][0]; d[1] = p[u][1]; d[2] = p[u][2];
+        d[96] = p[u][3]; d[97] = p[u][4]; d[98] = p[u][5];
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// The owner warp of one slot: claim, load, repack, LM loop, result; until the batch is exhausted.
+template <int V, int P>
+__device__ __forceinline__ void slot_owner_warp(const SolveArgs &args, int slot, SlotCtl &ctl, double *base,
+                                                uint64_t *bar_eval, uint64_t *bar_lm, uint64_t *bar_load,
+                                                int lane) {
+  constexpr int K = SlotLayout<V>::kCov;
+  const int cap = args.cap_elems;
+  const pnec_solver_opts &o = args.o;
+  uint32_t par_lm = 0, par_load = 0;
+  long long b_static = static_cast<long long>(blockIdx.x) * P + slot;
+  const long long stride = static_cast<long long>(gridDim.x) * P;
+  for (;;) {
+    long long b;
+    if (args.work_counter) {
+      unsigned int v = 0;
+      if (lane == 0) v = atomicAdd(args.work_counter, 1u);
+      b = __shfl_sync(0xffffffffu, v, 0);
+    } else {
+      b = b_static;
+      b_static += stride;
+    }
+    if (b >= args.bv.num_problems) break;
+    long long s, e;
+    problem_range(args.bv, b, s, e);
+    const int n = static_cast<int>(e - s);
+    const long long g0 = s & ~1LL;  // even => 16-byte aligned in every array
+    const int head = static_cast<int>(s - g0);
+    const int span = n + head;
+    SLOT_PROBE_START();
+#ifdef PNEC_SLOT_TIMING
+    const long long t_pair = t_prev;
+#endif
+    if (lane == 0) {
+      if (n > 0) {
+        fence_proxy_async();  // the evaluation warps' reads of the previous pair precede these writes
+        slot_issue<V>(args.bv, g0, span, cap, base, bar_load, 1);
+      }
+      solve_init_state(args, b, n, ctl.lm, ctl.pc);  // acos / atan2 / sincos under the copy
+    }
+    __syncwarp();
+    SLOT_PROBE(9);
+    if (n > 0) {
+      if (K > 0) {
+        mbar_wait(bar_load, par_load);
+        par_load ^= 1u;
+        SLOT_PROBE(0);
+        slot_repack(base, base, span, lane);
+        if (K == 2) slot_repack(base + 6 * cap, base + 9 * cap, span, lane);
+        __syncwarp();
+        SLOT_PROBE(1);
+        if (lane == 0) {
+          fence_proxy_async();
+          slot_issue<V>(args.bv, g0, span, cap, base, bar_load, 2);
+        }
+      }
+      mbar_wait(bar_load, par_load);
+      par_load ^= 1u;
+      __syncwarp();
+      SLOT_PROBE(2);
+      if (lane == 0) {
+        ctl.head = head;
+        ctl.span = span;
+        ctl.mode = kPassFull;
+        mbar_arrive(bar_eval);
+      }
+      bool first = true;
+      for (;;) {
+        mbar_wait(bar_lm, par_lm);
+        par_lm ^= 1u;
+        SLOT_PROBE(3);
+        if (ctl.mode == kPassCost) {
+          double t = 0.0;
+#pragma unroll
+          for (int w = 0; w < kSlotEvalWarps; ++w) t += ctl.part[w][kNumAcc - 1];
+          t *= 0.5;
+          lm_after_cost_pass(ctl.lm, t, o, lane);
+        } else {
+          if (lane < kNumAcc) {
+            double mine = 0.0;
+#pragma unroll
+            for (int w = 0; w < kSlotEvalWarps; ++w) mine += ctl.part[w][lane];
+            ctl.lm.tot[ctl.lm.ti ^ 1][lane] = mine * acc_scale(lane);
+          }
+          __syncwarp();
+          if (first) lm_step<true>(ctl.lm, o, lane, ctl.pc);
+          else lm_step<false>(ctl.lm, o, lane, ctl.pc);
+        }
+        __syncwarp();
+        SLOT_PROBE(4);
+        if (ctl.lm.done) break;
+        first = false;
+        if (lane == 0) {
+          ctl.mode = ctl.lm.pass_mode;
+          mbar_arrive(bar_eval);
+        }
+      }
+    }
+    if (lane == 0) solve_write_result(args, b, ctl.lm);
+    __syncwarp();
+#ifdef PNEC_SLOT_TIMING
+    if (lane == 0) atomicAdd(&g_slot_probe[5], (unsigned long long)(clock64() - t_pair));
+#endif
+  }
+  if (lane == 0) {
+    ctl.mode = kSlotExit;
+    mbar_arrive(bar_eval);
+  }
+}
+
+// An evaluation warp: quarter `warp` of whichever slot has a candidate posted.
+template <int V, int P>
+__device__ __forceinline__ void slot_eval_warp(const SolveArgs &args, SlotCtl *ctl, uint64_t *bar_eval,
+                                               uint64_t *bar_lm, int warp, int lane) {
+  constexpr int kD = SlotLayout<V>::kDoubles;
+  const int cap = args.cap_elems;
+  const double reg = args.o.regularization;
+  unsigned par = 0, alive = (1u << P) - 1u;
+  int s = 0;
+  SLOT_PROBE_START();
+  while (alive) {
+    if (!((alive >> s) & 1u) || !mbar_test_wait(&bar_eval[s], (par >> s) & 1u)) {
+      s = (s + 1 == P) ? 0 : s + 1;
+      continue;
+    }
+    par ^= 1u << s;
+    SlotCtl &c = ctl[s];
+    const int mode = c.mode;
+    if (mode == kSlotExit) {
+      alive &= ~(1u << s);
+      continue;
+    }
+    SLOT_PROBE(7);
+    const double *base = dyn_smem + static_cast<size_t>(s) * kD * cap;
+    PoseConst pc;
+    load_pose_const(c.pc, pc);
+    const int hi = c.span;
+    if (mode == kPassCost) {
+      double sum = 0.0;
+      for (int j = c.head + warp * 32 + lane; j < hi; j += kSlotEvalWarps * 32) {
+        double a1[3], a2[3], c1[6], c2[6];
+        slot_load_corr<V>(base, cap, j, a1, a2, c1, c2);
+        const double r = residual_only<V>(pc, reg, a1, a2, c1, c2);
+        sum = fma(r, r, sum);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if (lane == 0) c.part[warp][kNumAcc - 1] = sum;
+    } else {
+      double acc[kNumAcc];
+#pragma unroll
+      for (int i = 0; i < kNumAcc; ++i) acc[i] = 0.0;
+      for (int j = c.head + warp * 32 + lane; j < hi; j += kSlotEvalWarps * 32) {
+        double a1[3], a2[3], c1[6], c2[6], r, row[5];
+        slot_load_corr<V>(base, cap, j, a1, a2, c1, c2);
+        residual_row<V>(pc, reg, a1, a2, c1, c2, r, row);
+        accumulate(acc, r, row);
+      }
+      const double v = warp_transpose_reduce(acc, lane);
+      const int idx = warp_reduce_owner_index(lane);
+      if (idx >= 0 && idx < kNumAcc) c.part[warp][idx] = v;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bar_lm[s]);
+    SLOT_PROBE(6);
+#ifdef PNEC_SLOT_TIMING
+    if (lane == 0 && warp == 0) atomicAdd(&g_slot_probe[8], 1ull);
+#endif
+    s = (s + 1 == P) ? 0 : s + 1;
+  }
+}
+
+template <int V, int P>
+__global__ void __launch_bounds__((kSlotEvalWarps + P) * 32, 2)
+solve_slots_kernel(const __grid_constant__ SolveArgs args) {
+  __shared__ __align__(8) uint64_t s_bar_eval[P], s_bar_lm[P], s_bar_load[P];
+  __shared__ SlotCtl s_ctl[P];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < P; ++s) {
+      mbar_init(&s_bar_eval[s], 1);
+      mbar_init(&s_bar_lm[s], kSlotEvalWarps);
+      mbar_init(&s_bar_load[s], 1);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (warp >= kSlotEvalWarps) {
+    const int slot = warp - kSlotEvalWarps;
+    double *base = dyn_smem + static_cast<size_t>(slot) * SlotLayout<V>::kDoubles * args.cap_elems;
+    slot_owner_warp<V, P>(args, slot, s_ctl[slot], base, &s_bar_eval[slot], &s_bar_lm[slot], &s_bar_load[slot], lane);
+  } else {
+    slot_eval_warp<V, P>(args, s_ctl, s_bar_eval, s_bar_lm, warp, lane);
+  }
+  __syncthreads();
+  // the work counter serves the next launch on this stream: the last CTA to leave rewinds it
+  if (tid == 0 && args.work_counter) {
+    __threadfence();
+    if (atomicAdd(args.work_counter + 1, 1u) == gridDim.x - 1) {
+      args.work_counter[0] = 0u;
+      args.work_counter[1] = 0u;
+      __threadfence();
+    }
+  }
+}
+
+}  // namespace pnec
