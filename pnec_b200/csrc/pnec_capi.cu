@@ -279,6 +279,7 @@ struct pnec_handle {
   DevBuf d_pk_ct, d_pk_ch;  // PNEC_COV_PACKED covariances of HOST callers before expansion
   DevBuf d_slot_ctr;        // work counters of solve_slots_kernel, one {next pair, CTAs gone} per stream seen
   std::vector<cudaStream_t> slot_ctr_streams;
+  std::vector<DevBuf> d_slot_start;  // start points [B][10] of solve_prep_kernel, one buffer per stream seen
   DevBuf d_kp_out[8];  // device outputs of the from-keypoints entry points for HOST callers
   static constexpr int kMaxChunks = 8;
   static constexpr int kMaxRounds = 64;
@@ -578,8 +579,10 @@ int launch_solve_stream_v(pnec_handle *h, const SolveArgs &a, cudaStream_t strea
 // CTA leaves.  Launches on one stream run one after the other and can share a counter; every stream the
 // handle sees gets its own (64 of them; beyond that the kernel falls back to a static partition).
 constexpr int kSlotCounters = 64;
-int slot_counter(pnec_handle *h, cudaStream_t stream, unsigned int **out) {
+int slot_counter(pnec_handle *h, cudaStream_t stream, unsigned int **out, DevBuf **start) {
   *out = nullptr;
+  *start = nullptr;
+  if (h->d_slot_start.empty()) h->d_slot_start.resize(kSlotCounters + 1);
   if (!h->d_slot_ctr.p) {
     PNEC_CUDA(h->d_slot_ctr.ensure(kSlotCounters * 2 * sizeof(unsigned int)));
     PNEC_CUDA(cudaMemset(h->d_slot_ctr.p, 0, kSlotCounters * 2 * sizeof(unsigned int)));
@@ -589,10 +592,11 @@ int slot_counter(pnec_handle *h, cudaStream_t stream, unsigned int **out) {
   for (; i < h->slot_ctr_streams.size(); ++i)
     if (h->slot_ctr_streams[i] == stream) break;
   if (i == h->slot_ctr_streams.size()) {
-    if (i == kSlotCounters) return PNEC_OK;
+    if (i == kSlotCounters) return PNEC_OK;  // (the caller takes the one-CTA-per-pair kernel)
     h->slot_ctr_streams.push_back(stream);
   }
   *out = static_cast<unsigned int *>(h->d_slot_ctr.p) + 2 * i;
+  *start = &h->d_slot_start[i];
   return PNEC_OK;
 }
 
@@ -620,8 +624,15 @@ int launch_solve_slots_v(pnec_handle *h, SolveArgs a, long long need, cudaStream
   auto kern = solve_slots_kernel<V, 2>;
   const size_t dyn = static_cast<size_t>(2) * SlotLayout<V>::kDoubles * 8 * static_cast<size_t>(cap);
   PNEC_CUDA(ensure_dyn_smem(h, kern, dyn));
-  int rc = slot_counter(h, stream, &a.work_counter);
+  DevBuf *start = nullptr;
+  int rc = slot_counter(h, stream, &a.work_counter, &start);
   if (rc != PNEC_OK) return rc;
+  if (!start) return PNEC_OK;
+  PNEC_CUDA(start->ensure(static_cast<size_t>(a.bv.num_problems) * 80));
+  a.start_state = static_cast<double *>(start->p);
+  solve_prep_kernel<<<static_cast<unsigned>((a.bv.num_problems + 127) / 128), 128, 0, stream>>>(a.bv.poses, a.bv.num_problems, a.start_state);
+  PNEC_CUDA(cudaGetLastError());
+  h->launches++;
   a.cap_elems = static_cast<int>(cap);
   a.use_bulk = 1;
   a.dbg = nullptr;
@@ -636,6 +647,8 @@ int launch_solve_slots_v(pnec_handle *h, SolveArgs a, long long need, cudaStream
     cudaMemcpyFromSymbol(pr, g_slot_probe, sizeof(pr));
     cudaMemcpyToSymbol(g_slot_probe, zero, sizeof(zero));
     const double B = static_cast<double>(a.bv.num_problems);
+    std::fprintf(stderr, "[slots init] issue+claim %.0f state %.0f | warp lifetimes, cycles: owner %.0f eval %.0f (grid %u)\n", pr[10] / B, pr[11] / B,
+                 (double)pr[12] / (2.0 * grid), (double)pr[13] / (4.0 * grid), grid);
     std::fprintf(stderr, "[slots, cycles per pair] init %.0f load1 %.0f repack %.0f load2 %.0f wait-eval %.0f lm %.0f total %.0f | "
                  "eval warps (per warp, per pair): busy %.0f poll %.0f | passes %.2f\n",
                  pr[9] / B, pr[0] / B, pr[1] / B, pr[2] / B, pr[3] / B, pr[4] / B, pr[5] / B,
@@ -657,11 +670,13 @@ int launch_solve(pnec_handle *h, const SolveArgs &a0, int variant, long long max
                  cudaStream_t stream) {
   SolveArgs a = a0;
   if (a.bv.num_problems == 0) return PNEC_OK;
-  // Batches that oversubscribe the device with pairs small enough for four slots per SM: evaluation
-  // and LM update decoupled (pnec_solve_slots.cuh).  Below that every pair gets its own CTA at once.
+  // Batches that oversubscribe the device many times over, of pairs for which solve_kernel has room for
+  // three per SM only (4 warps per pair, N > 448) but four slots fit: evaluation and LM update decoupled
+  // (pnec_solve_slots.cuh; measured on B200: 10000 x 512 0.449 vs 0.473 ms).  Smaller pairs are better
+  // off with one warp per pair and seven or more pairs per SM, smaller batches with a CTA per pair.
   const int slots_mode = h->cfg.solve_slots;
   if (slots_mode != 0 && bulk_ok(a.bv) && !h->cfg.no_bulk && max_n > 0 &&
-      (slots_mode == 2 || a.bv.num_problems >= 3LL * h->sm_count)) {
+      (slots_mode == 2 || (max_n > 448 && a.bv.num_problems >= 32LL * h->sm_count))) {
     // a pair starts at an even correspondence index of its arrays (16-byte alignment of the bulk copies):
     // one more element when its range starts at an odd one
     const bool even_starts = !a.bv.offsets && (a.bv.n_uniform % 2 == 0);
@@ -1214,6 +1229,7 @@ void pnec_destroy(pnec_handle *h) {
   h->d_pk_ct.release();
   h->d_pk_ch.release();
   h->d_slot_ctr.release();
+  for (DevBuf &b : h->d_slot_start) b.release();
   for (int i = 0; i < pnec_handle::kMaxChunks; ++i) {
     if (h->side[i]) cudaStreamDestroy(h->side[i]);
     if (h->lm_side[i]) cudaStreamDestroy(h->lm_side[i]);

@@ -124,12 +124,13 @@ __device__ __forceinline__ void make_pose_const_sc(const double sc[4], const dou
   pc.tph[0] = -st * sp; pc.tph[1] = st * cp; pc.tph[2] = 0.0;
   const double qx = q[0], qy = q[1], qz = q[2], qw = q[3];
   const double tx = 2.0 * qx, ty = 2.0 * qy, tz = 2.0 * qz;
-  const double twx = tx * qw, twy = ty * qw, twz = tz * qw;
-  const double txx = tx * qx, txy = ty * qx, txz = tz * qx;
-  const double tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
-  pc.R[0] = 1.0 - (tyy + tzz); pc.R[1] = txy - twz;         pc.R[2] = txz + twy;
-  pc.R[3] = txy + twz;         pc.R[4] = 1.0 - (txx + tzz); pc.R[5] = tyz - twx;
-  pc.R[6] = txz - twy;         pc.R[7] = tyz + twx;         pc.R[8] = 1.0 - (txx + tyy);
+  // explicit roundings (no contraction into fma): pose_const_lanes computes the same bits
+  const double twx = __dmul_rn(tx, qw), twy = __dmul_rn(ty, qw), twz = __dmul_rn(tz, qw);
+  const double txx = __dmul_rn(tx, qx), txy = __dmul_rn(ty, qx), txz = __dmul_rn(tz, qx);
+  const double tyy = __dmul_rn(ty, qy), tyz = __dmul_rn(tz, qy), tzz = __dmul_rn(tz, qz);
+  pc.R[0] = __dsub_rn(1.0, __dadd_rn(tyy, tzz)); pc.R[1] = __dsub_rn(txy, twz); pc.R[2] = __dadd_rn(txz, twy);
+  pc.R[3] = __dadd_rn(txy, twz); pc.R[4] = __dsub_rn(1.0, __dadd_rn(txx, tzz)); pc.R[5] = __dsub_rn(tyz, twx);
+  pc.R[6] = __dsub_rn(txz, twy); pc.R[7] = __dadd_rn(tyz, twx); pc.R[8] = __dsub_rn(1.0, __dadd_rn(txx, tyy));
 }
 
 // Rare path of lm_step (a step above 0.25 rad): exact sin/cos.  Kept out of line so that the
@@ -166,67 +167,110 @@ __device__ __forceinline__ bool gradient_converged(const double x[6], const doub
 
 // ---------------------------------------------------------------- warp-cooperative update
 //
-// The update between two evaluations is the serial part of a solve and shares its SM sub-partition's
-// fp64 pipe with the evaluation warps of other pairs, where every instruction of a lone lane costs as
-// much as a full-width one.  So the warp works on it together: each stage computes its independent
-// outputs (the five damped diagonal entries, the 2x3 block W and u, the six entries of the Schur
-// complement and its right-hand side, the six cofactors, the three small-angle evaluations, the four
-// quaternion components, the eighteen pose constants) one per lane, and the lanes exchange them through
-// a 40-double scratch in shared memory.  About 150 fp64 instructions per update instead of 650.
-// The arithmetic of every output is what the single-lane form computed.
+// The update between two evaluations is the serial part of a solve: one warp runs it while the pair's
+// evaluation waits, so what counts is its dependent chain (measured on B200: DFMA 8 cycles, a
+// shared-memory load 29, a store + __syncwarp + load exchange between lanes 43).  The warp works on it
+// together: each stage computes its independent outputs (the five damped diagonal entries, the 2x3 block
+// W and u, the six entries of the Schur complement and its right-hand side, the six cofactors, the three
+// small-angle evaluations, the four quaternion components, the eighteen pose constants) one per lane, and
+// the lanes exchange them through a 40-double scratch in shared memory.  Everything a lane needs from
+// the state is read in ONE batch of loads right after the accept / reject decision, before the first
+// scratch store (the compiler cannot move a shared-memory load across a store it cannot tell apart),
+// so the chain sees one load latency, seven exchanges and about 55 dependent fp64 operations.
+// The arithmetic of every output is what a single lane would compute.
 
 // scratch layout (LMState::xch)
 constexpr int kXDiag = 0;   // 5: H_aa + lambda_a
-constexpr int kXW0 = 5;     // 4: W0[0..2], u0        (P^-1 Q, P^-1 b1: first rows)
-constexpr int kXW1 = 9;     // 4: W1[0..2], u1
-constexpr int kXS = 13;     // 6: S00 S01 S02 S11 S12 S22 (Schur complement), then
-constexpr int kXC = 19;     // 3: c = b2 - Q^T u
-constexpr int kXAdj = 22;   // 6: c00 c01 c02 c11 c12 c22 (cofactors of S)
-constexpr int kXD = 28;     // 5: d
-constexpr int kXIn = 33;    // 5: lambda_a d_a + g_a
+constexpr int kXLam = 5;    // 5: lambda_a
+constexpr int kXW0 = 10;    // 4: W0[0..2], u0        (P^-1 Q, P^-1 b1: first rows)
+constexpr int kXW1 = 14;    // 4: W1[0..2], u1
+constexpr int kXS = 18;     // 6: S00 S01 S02 S11 S12 S22 (Schur complement), then
+constexpr int kXC = 24;     // 3: c = b2 - Q^T u
+constexpr int kXAdj = 27;   // 6: c00 c01 c02 c11 c12 c22 (cofactors of S)
+constexpr int kXD = 33;     // 5: d
 
 // value `lane` of a table of 4-bit entries
 __device__ __forceinline__ int nib(unsigned long long table, int lane) {
   return static_cast<int>((table >> (4 * lane)) & 0xFull);
 }
 
+// Pose constants from a quaternion q (x, y, z, w) and (sin theta, cos theta, sin phi, cos phi) in shared
+// memory, one per lane: R (row-major) on lanes 0..8, t, dt/dtheta, dt/dphi on lanes 9..17.
+__device__ __forceinline__ void pose_const_lanes(const double *q, const double *scn, PoseConst &s_pc, int lane) {
+  if (lane >= 18) return;
+  double v;
+  if (lane < 9) {
+    //   R0 = 1 - (tyy + tzz)   R1 = txy - twz         R2 = txz + twy          with tab = 2 q_a q_b
+    //   R3 = txy + twz         R4 = 1 - (txx + tzz)   R5 = tyz - twx
+    //   R6 = txz - twy         R7 = tyz + twx         R8 = 1 - (txx + tyy)
+    // (explicit roundings: make_pose_const_sc must give the same bits)
+    const double p = __dmul_rn(2.0 * q[nib(0x022201211ull, lane)], q[nib(0x010100001ull, lane)]);
+    const double r = __dmul_rn(2.0 * q[nib(0x101022122ull, lane)], q[nib(0x133323332ull, lane)]);
+    const bool diagonal = (lane == 0) || (lane == 4) || (lane == 8);
+    const bool minus = (lane == 1) || (lane == 5) || (lane == 6);
+    v = diagonal ? __dsub_rn(1.0, __dadd_rn(p, r)) : __dadd_rn(p, minus ? -r : r);
+  } else {
+    //   t = (st cp, st sp, ct)   dt/dtheta = (ct cp, ct sp, -st)   dt/dphi = (-st sp, st cp, 0)
+    const int m = lane - 9;
+    const double u = scn[nib(0x000011100ull, m)];                      // st or ct
+    const double su = (m == 5 || m == 6) ? -u : u;
+    const int vi = nib(0x032423423ull, m);                             // 2: sp, 3: cp, 4: the constant 1
+    const double w = (vi == 4) ? 1.0 : scn[vi & 3];
+    v = (m == 8) ? 0.0 : su * w;
+  }
+  reinterpret_cast<double *>(&s_pc)[lane] = v;
+}
+
+// What a lane reads of the totals (J^T J upper triangle, J^T r) at the accepted point.
+struct LmLaneTotals {
+  double haa;      // H[a][a], a = min(lane, 4)
+  double h01;      // H[0][1]
+  double wx, wy;   // lanes 0..2: H[0][2+j], H[1][2+j]; lane 3: g0, g1
+  double sp, sq;   // lanes 0..8: H[0][2+i], H[1][2+i] of the lane's Schur entry
+  double sbase;    // off-diagonal H[2+i][2+j] (lanes 1, 2, 4) or g[2+i] (lanes 6..8)
+  double g[5];     // J^T r
+};
+
 // One trust-region solve attempt at the accepted point, all 32 lanes.  Ceres solves, in Jacobi-scaled
 // coordinates, (S H S + D) y = S g with D = diag / radius and takes delta = -S y.  With d = S y this is
 // (H + S^-1 D S^-1) d = g: the same system without the 45 scaling products, and
 // model_cost_change = (y.Sg + y^T D y) / 2 = sum d_a (g_a + L_a d_a) / 2, L = D / s^2.
 // The 5x5 SPD system is solved by block elimination over the (theta, phi | rotation) split with
-// closed-form 2x2 / 3x3 adjugate inverses (2 reciprocals).  Lane a < 5 owns parameter a: diag_l in/out,
+// closed-form 2x2 / 3x3 adjugate inverses (2 reciprocals).  Lane a < 5 owns parameter a: diag_l in/out;
 // d[0..4] out on every lane.  Returns false for an invalid step: LINEAR_SOLVER_FAILURE in Ceres terms
 // (not positive definite by Sylvester's criterion, or a non-finite solution) or model_cost_change <= 0.
-__device__ __forceinline__ bool lm_trust_region_step(const double *Hg, double *xch, int lane, int a5, double haa,
+__device__ __forceinline__ bool lm_trust_region_step(const LmLaneTotals &t, double *xch, int lane,
                                                      double scale_l, double inv_scale2_l, double &diag_l,
                                                      bool reuse_diagonal, double inv_radius,
                                                      const pnec_solver_opts &o, double d[5], double &mcc) {
   if (!reuse_diagonal)  // squared column norm of the scaled Jacobian, clamped
-    diag_l = fmin(fmax(haa * scale_l * scale_l, o.min_lm_diagonal), o.max_lm_diagonal);
+    diag_l = fmin(fmax(t.haa * scale_l * scale_l, o.min_lm_diagonal), o.max_lm_diagonal);
   const double lam_l = diag_l * inv_radius * inv_scale2_l;
-  if (lane < 5) xch[kXDiag + lane] = haa + lam_l;
+  if (lane < 5) {
+    xch[kXDiag + lane] = t.haa + lam_l;
+    xch[kXLam + lane] = lam_l;
+  }
   __syncwarp();
   // P = A[0:2,0:2] and its inverse: every lane
-  const double p00 = xch[kXDiag], p11 = xch[kXDiag + 1], p01 = Hg[1];
-  const double detP = fma(p00, p11, -p01 * p01);
+  const double p00 = xch[kXDiag], p11 = xch[kXDiag + 1];
+  const int ls = min(lane, 8);                                          // Schur stage: entry of this lane
+  const int si = nib(0x210211000ull, ls), sk = nib(0x333221210ull, ls);  // row i; column j (3: right-hand side)
+  const bool sdiag = (ls == 0) || (ls == 3) || (ls == 5);
+  const double sdiag_v = xch[kXDiag + 2 + si];
+  double lam[5];
+#pragma unroll
+  for (int a = 0; a < 5; ++a) lam[a] = xch[kXLam + a];
+  const double detP = fma(p00, p11, -t.h01 * t.h01);
   const double iP = fast_rcp(detP);
-  const double i00 = p11 * iP, i01 = -p01 * iP, i11 = p00 * iP;
-  {  // W = P^-1 Q (lanes 0..2: column j), u = P^-1 b1 (lane 3)
-    const int l = min(lane, 3);
-    const double x = Hg[l < 3 ? 2 + l : 15], y = Hg[l < 3 ? 6 + l : 16];  // A[0][2+j], A[1][2+j] | b0, b1
-    if (lane < 4) {
-      xch[kXW0 + lane] = fma(i00, x, i01 * y);
-      xch[kXW1 + lane] = fma(i01, x, i11 * y);
-    }
+  const double i00 = p11 * iP, i01 = -t.h01 * iP, i11 = p00 * iP;
+  if (lane < 4) {  // W = P^-1 Q (lanes 0..2: column j), u = P^-1 b1 (lane 3)
+    xch[kXW0 + lane] = fma(i00, t.wx, i01 * t.wy);
+    xch[kXW1 + lane] = fma(i01, t.wx, i11 * t.wy);
   }
   __syncwarp();
   {  // Schur complement S = R - Q^T W (lanes 0..5: (0,0) (0,1) (0,2) (1,1) (1,2) (2,2)), c = b2 - Q^T u (lanes 6..8)
-    const int l = min(lane, 8);
-    const int i = nib(0x210211000ull, l), k = nib(0x333221210ull, l);
-    const bool diagonal = (l == 0) || (l == 3) || (l == 5);
-    const double base = (l < 6) ? (diagonal ? xch[kXDiag + 2 + i] : Hg[9 + l]) : Hg[17 + i];
-    const double sv = base - fma(Hg[2 + i], xch[kXW0 + k], Hg[6 + i] * xch[kXW1 + k]);
+    const double base = sdiag ? sdiag_v : t.sbase;
+    const double sv = base - fma(t.sp, xch[kXW0 + sk], t.sq * xch[kXW1 + sk]);
     if (lane < 9) xch[kXS + lane] = sv;
   }
   __syncwarp();
@@ -236,35 +280,38 @@ __device__ __forceinline__ bool lm_trust_region_step(const double *Hg, double *x
     const double v = fma(S[nib(0x010123ull, l)], S[nib(0x325445ull, l)], -S[nib(0x102214ull, l)] * S[nib(0x142354ull, l)]);
     if (lane < 6) xch[kXAdj + lane] = v;
   }
+  const double S00 = S[0], S01 = S[1], S02 = S[2];
+  const double c0 = xch[kXC], c1 = xch[kXC + 1], c2 = xch[kXC + 2];
   __syncwarp();
   const double *C = xch + kXAdj;
-  const double S00 = S[0], c22 = C[5];
-  const double detS = fma(S00, C[0], fma(S[1], C[1], S[2] * C[2]));
+  const double c22 = C[5];
+  const double detS = fma(S00, C[0], fma(S01, C[1], S02 * C[2]));
   const double iS = fast_rcp(detS);
   {  // rotation part: lanes 0..2, row r of adj(S) . c / det
     const int r = min(lane, 2);
     const int e1 = nib(0x431ull, r), e2 = nib(0x542ull, r);  // rows (0 1 2), (1 3 4), (2 4 5) of the packed cofactors
-    const double n = fma(C[r], xch[kXC], fma(C[e1], xch[kXC + 1], C[e2] * xch[kXC + 2]));
+    const double n = fma(C[r], c0, fma(C[e1], c1, C[e2] * c2));
     if (lane < 3) xch[kXD + 2 + lane] = n * iS;
   }
+  const double *W = xch + ((lane & 1) ? kXW1 : kXW0);
+  const double w0 = W[0], w1 = W[1], w2 = W[2], wu = W[3];
   __syncwarp();
   {  // translation part: lanes 0..1
-    const int r = min(lane, 1);
-    const double *W = xch + (r ? kXW1 : kXW0);
-    const double v = W[3] - fma(W[0], xch[kXD + 2], fma(W[1], xch[kXD + 3], W[2] * xch[kXD + 4]));
+    const double v = wu - fma(w0, xch[kXD + 2], fma(w1, xch[kXD + 3], w2 * xch[kXD + 4]));
     if (lane < 2) xch[kXD + lane] = v;
   }
   __syncwarp();
-  if (lane < 5) xch[kXIn + lane] = fma(lam_l, xch[kXD + a5], Hg[15 + a5]);
-  __syncwarp();
   bool ok = (p00 > 0.0) && (detP > 0.0) && (S00 > 0.0) && (c22 > 0.0) && (detS > 0.0);
-  mcc = 0.0;
+  double term[5];
 #pragma unroll
   for (int a = 0; a < 5; ++a) {
     d[a] = xch[kXD + a];
     ok = ok && (fabs(d[a]) < CUDART_INF);
-    mcc = fma(d[a], xch[kXIn + a], mcc);
+    term[a] = fma(lam[a], d[a], t.g[a]);
   }
+  mcc = 0.0;
+#pragma unroll
+  for (int a = 0; a < 5; ++a) mcc = fma(d[a], term[a], mcc);
   mcc *= 0.5;
   return ok && (mcc > 0.0);
 }
@@ -291,17 +338,20 @@ __device__ __forceinline__ void lm_step(LMState &st, const pnec_solver_opts &o, 
   long long t_prev = clock64();
 #endif
   const int xi = st.xi, ti = st.ti;
-  const double *newtot = st.tot[ti ^ 1];
   // The trust-region radius is carried as its inverse: every use is a division by it
   // (D = diag / radius, radius /= factor), so the update chain needs no reciprocal.
   double inv_radius = st.inv_radius, decrease_factor = st.decrease_factor, x_cost = st.x_cost;
   int reuse_diagonal = st.reuse_diagonal;
+  const double inv_mcc_prev = st.inv_model_cost_change;
+  int grad_conv = st.grad_converged;
+  int iteration = st.iteration, num_invalid = st.num_invalid, status = st.status;
   bool accept = true;
-  double cand_cost = newtot[20];
+  const double new_cost = st.tot[ti ^ 1][20];
+  double cand_cost = new_cost;
   if (!(fabs(cand_cost) < CUDART_INF)) cand_cost = DBL_MAX;
   if (FIRST) {
     if (cand_cost >= DBL_MAX) {
-      if (lane == 0) { st.status = PNEC_STATUS_NONFINITE; st.done = 1; st.initial_cost = newtot[20]; st.x_cost = newtot[20]; }
+      if (lane == 0) { st.status = PNEC_STATUS_NONFINITE; st.done = 1; st.initial_cost = new_cost; st.x_cost = new_cost; }
       return;
     }
     x_cost = cand_cost;
@@ -311,7 +361,7 @@ __device__ __forceinline__ void lm_step(LMState &st, const pnec_solver_opts &o, 
       if (lane == 0) { st.status = PNEC_STATUS_CONVERGED_FUNCTION; st.done = 1; }
       return;
     }
-    const double rho = (cand_cost >= DBL_MAX) ? -DBL_MAX : cost_change * st.inv_model_cost_change;
+    const double rho = (cand_cost >= DBL_MAX) ? -DBL_MAX : cost_change * inv_mcc_prev;
     accept = rho > o.min_relative_decrease;
     const double c = 2.0 * rho - 1.0;
     // StepAccepted: radius /= max(1/3, 1 - (2 rho - 1)^3), capped; StepRejected: radius /= factor
@@ -324,39 +374,61 @@ __device__ __forceinline__ void lm_step(LMState &st, const pnec_solver_opts &o, 
   LM_PROBE(0);  // judge
   const int nxi = accept ? (FIRST ? xi : xi ^ 1) : xi;  // index of the accepted point
   const int nti = accept ? ti ^ 1 : ti;                 // index of its totals
-  const double *Hg = st.tot[nti];
-  const double *x = st.pts[nxi];
-  const double *sc = st.scs[nxi];
   double *cnd = st.pts[nxi ^ 1], *scn = st.scs[nxi ^ 1];  // the candidate's slots
 
-  // lane a < 5 owns parameter a (the others shadow parameter 4)
+  // ---- the one batch of state loads (lane a < 5 owns parameter a, the others shadow parameter 4)
   const int a5 = min(lane, 4);
-  const double haa = Hg[a5 * 5 - (a5 * (a5 - 1)) / 2];  // tri(a, a)
+  LmLaneTotals t;
+  double x[6], sc_s, sc_c, q4[4];
   double scale_l, inv_scale2_l, diag_l;
+  {
+    const double *Hg = st.tot[nti];
+    const double *xs = st.pts[nxi];
+    const double *scs = st.scs[nxi];
+    const int lw = min(lane, 3), ls = min(lane, 8);
+    const int si = nib(0x210211000ull, ls);
+    t.haa = Hg[a5 * 5 - (a5 * (a5 - 1)) / 2];  // tri(a, a)
+    t.h01 = Hg[1];
+    t.wx = Hg[lw < 3 ? 2 + lw : 15];
+    t.wy = Hg[lw < 3 ? 6 + lw : 16];
+    t.sp = Hg[2 + si];
+    t.sq = Hg[6 + si];
+    t.sbase = Hg[ls < 6 ? 9 + ls : 17 + si];
+#pragma unroll
+    for (int a = 0; a < 5; ++a) t.g[a] = Hg[15 + a];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) x[i] = xs[i];
+    sc_s = scs[2 * (lane & 1)];
+    sc_c = scs[2 * (lane & 1) + 1];
+    const int k = (lane - 2) & 3;  // quaternion component of lanes 2..5
+    q4[0] = xs[2 + k];
+    q4[1] = xs[2 + nib(0x0123ull, k)];
+    q4[2] = xs[2 + nib(0x1032ull, k)];
+    q4[3] = xs[2 + nib(0x2301ull, k)];
+    if (!FIRST) {
+      scale_l = st.scale[a5];
+      inv_scale2_l = st.inv_scale2[a5];
+      diag_l = st.diag[a5];
+    }
+  }
   if (FIRST) {
-    const double one_plus = 1.0 + fast_sqrt(haa);  // scale = 1 / (1 + |J col|)
+    const double one_plus = 1.0 + fast_sqrt(t.haa);  // scale = 1 / (1 + |J col|)
     scale_l = o.jacobi_scaling ? fast_rcp(one_plus) : 1.0;
     inv_scale2_l = o.jacobi_scaling ? one_plus * one_plus : 1.0;
     diag_l = 0.0;
-  } else {
-    scale_l = st.scale[a5];
-    inv_scale2_l = st.inv_scale2[a5];
-    diag_l = st.diag[a5];
   }
   // the gradient test of a newly accepted point (cheap unless |g| is already tiny)
-  int grad_conv = st.grad_converged;
-  if (accept) grad_conv = gradient_converged(x, Hg + 15, o.gradient_tolerance) ? 1 : 0;
-  LM_PROBE(1);  // scale, gradient test
-  int iteration = st.iteration, num_invalid = st.num_invalid, step_successful = accept ? 1 : 0;
-  int status = st.status, done = 0;
+  if (accept) grad_conv = gradient_converged(x, t.g, o.gradient_tolerance) ? 1 : 0;
+  LM_PROBE(1);  // loads, scale, gradient test
+  int step_successful = accept ? 1 : 0, done = 0;
   double d[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, mcc = 0.0;
   for (;;) {  // FinalizeIterationAndCheckIfMinimizerCanContinue
     if (iteration >= o.max_num_iterations) { status = PNEC_STATUS_MAX_ITERATIONS; done = 1; break; }
     if (step_successful && grad_conv) { status = PNEC_STATUS_CONVERGED_GRADIENT; done = 1; break; }
     if (inv_radius * o.min_trust_region_radius >= 1.0) { status = PNEC_STATUS_CONVERGED_RADIUS; done = 1; break; }
     ++iteration;
-    const bool valid = lm_trust_region_step(Hg, st.xch, lane, a5, haa, scale_l, inv_scale2_l, diag_l,
-                                            reuse_diagonal != 0, inv_radius, o, d, mcc);
+    const bool valid = lm_trust_region_step(t, st.xch, lane, scale_l, inv_scale2_l, diag_l, reuse_diagonal != 0,
+                                            inv_radius, o, d, mcc);
     reuse_diagonal = 1;
     if (valid) { num_invalid = 0; break; }
     if (++num_invalid >= o.max_num_consecutive_invalid_steps) { status = PNEC_STATUS_FAILURE; done = 1; break; }
@@ -375,24 +447,23 @@ __device__ __forceinline__ void lm_step(LMState &st, const pnec_solver_opts &o, 
       double sinc, cs;
       small_sinc_cos(lane == 0 ? zt : lane == 1 ? zp : zq, sinc, cs);
       if (lane < 2) {  // angle addition
-        const double s0 = sc[2 * lane], c0 = sc[2 * lane + 1], sd = delta[lane] * sinc;
-        cnd[lane] = x[lane] + delta[lane];
-        scn[2 * lane] = fma(s0, cs, c0 * sd);
-        scn[2 * lane + 1] = fma(c0, cs, -s0 * sd);
+        const double dl = lane ? delta[1] : delta[0], sd = dl * sinc;
+        cnd[lane] = (lane ? x[1] : x[0]) + dl;
+        scn[2 * lane] = fma(sc_s, cs, sc_c * sd);
+        scn[2 * lane + 1] = fma(sc_c, cs, -sc_s * sd);
       } else if (lane < 6) {  // EigenQuaternionManifold::Plus, component k of (x, y, z, w)
         const int k = lane - 2;
-        const double *q = x + 2;
         //   x' = cq x + dx w + dy z - dz y     y' = cq y - dx z + dy w + dz x
         //   z' = cq z + dx y - dy x + dz w     w' = cq w - dx x - dy y - dz z
         const double dx = sinc * delta[2], dy = sinc * delta[3], dz = sinc * delta[4];
         const double sx = (k == 1 || k == 3) ? -dx : dx, sy = (k == 2 || k == 3) ? -dy : dy, sz = (k == 0 || k == 3) ? -dz : dz;
-        cnd[2 + k] = fma(sz, q[nib(0x2301ull, k)], fma(sy, q[nib(0x1032ull, k)], fma(sx, q[nib(0x0123ull, k)], cs * q[k])));
+        cnd[2 + k] = fma(sz, q4[3], fma(sy, q4[2], fma(sx, q4[1], cs * q4[0])));
       }
     } else if (lane == 0) {
       double cand[6], scc[4];
       cand[0] = x[0] + delta[0];
       cand[1] = x[1] + delta[1];
-      lm_candidate_large_step(x, sc, delta, cand, scc);
+      lm_candidate_large_step(st.pts[nxi], st.scs[nxi], delta, cand, scc);
 #pragma unroll
       for (int i = 0; i < 6; ++i) cnd[i] = cand[i];
 #pragma unroll
@@ -423,30 +494,7 @@ __device__ __forceinline__ void lm_step(LMState &st, const pnec_solver_opts &o, 
     pass_mode = (mcc <= 1.05 * o.function_tolerance * x_cost) ? kPassCost : kPassFull;
   }
   LM_PROBE(3);  // candidate
-  if (!done && lane < 18) {
-    // pose constants of the candidate, one per lane: R (row-major) on lanes 0..8, t, dt/dtheta, dt/dphi on 9..17
-    const double *q = cnd + 2;
-    double v;
-    if (lane < 9) {
-      //   R0 = 1 - (tyy + tzz)   R1 = txy - twz         R2 = txz + twy          with tab = 2 q_a q_b
-      //   R3 = txy + twz         R4 = 1 - (txx + tzz)   R5 = tyz - twx
-      //   R6 = txz - twy         R7 = tyz + twx         R8 = 1 - (txx + tyy)
-      const double p = (2.0 * q[nib(0x022201211ull, lane)]) * q[nib(0x010100001ull, lane)];
-      const double r = (2.0 * q[nib(0x101022122ull, lane)]) * q[nib(0x133323332ull, lane)];
-      const bool diagonal = (lane == 0) || (lane == 4) || (lane == 8);
-      const bool minus = (lane == 1) || (lane == 5) || (lane == 6);
-      v = diagonal ? 1.0 - (p + r) : (minus ? p - r : p + r);
-    } else {
-      //   t = (st cp, st sp, ct)   dt/dtheta = (ct cp, ct sp, -st)   dt/dphi = (-st sp, st cp, 0)
-      const int m = lane - 9;
-      const double u = scn[nib(0x000011100ull, m)];                      // st or ct
-      const double su = (m == 5 || m == 6) ? -u : u;
-      const int vi = nib(0x032423423ull, m);                             // 2: sp, 3: cp, 4: the constant 1
-      const double w = (vi == 4) ? 1.0 : scn[vi];
-      v = (m == 8) ? 0.0 : su * w;
-    }
-    reinterpret_cast<double *>(&s_pc)[lane] = v;
-  }
+  if (!done) pose_const_lanes(cnd + 2, scn, s_pc, lane);
   if (lane < 5) {
     if (FIRST) {
       st.scale[lane] = scale_l;

@@ -22,18 +22,42 @@ struct SolveArgs {
   int use_bulk;   // all base pointers 16-byte aligned
   long long *dbg; // PNEC_PHASE_TIMING builds only: per-CTA cycle counters
   unsigned int *work_counter;  // solve_slots_kernel: {next pair, CTAs that have left}; nullptr = static partition
+  double *start_state;         // solve_slots_kernel: [B][10] (theta, phi, q, sin/cos of theta and phi), solve_prep_kernel
 };
 
-// PNECCeres::InitValues(orientation, translation) (pnec_ceres.cc:188-192) + the start state of
-// the minimiser; called by one thread.
-__device__ __forceinline__ void solve_init_state(const SolveArgs &args, long long b, int n,
-                                                 LMState &st, PoseConst &s_pc) {
-  const double *p = args.bv.poses + 7 * b;
-  double *x = st.pts[0], *sc = st.scs[0];
-  angles_from_vec(p + 4, x[0], x[1]);
-  x[2] = p[0]; x[3] = p[1]; x[4] = p[2]; x[5] = p[3];
+// PNECCeres::InitValues(orientation, translation) (pnec_ceres.cc:188-192): the start point
+// x = (theta, phi, q) of a pair and the sines / cosines of its angles.
+__device__ __forceinline__ void solve_start_point(const double *pose, double x[6], double sc[4]) {
+  angles_from_vec(pose + 4, x[0], x[1]);
+  x[2] = pose[0]; x[3] = pose[1]; x[4] = pose[2]; x[5] = pose[3];
   sincos(x[0], &sc[0], &sc[1]);
   sincos(x[1], &sc[2], &sc[3]);
+}
+
+// The start state of the minimiser apart from the start point; called by one thread.
+__device__ __forceinline__ void solve_reset_state(const SolveArgs &args, int n, LMState &st) {
+  st.inv_radius = 1.0 / args.o.initial_trust_region_radius;
+  st.decrease_factor = 2.0;
+  st.inv_model_cost_change = 0.0;
+  st.x_cost = 0.0;
+  st.initial_cost = 0.0;
+  st.xi = 0;
+  st.ti = 0;
+  st.iteration = 0;
+  st.num_invalid = 0;
+  st.reuse_diagonal = 0;
+  st.step_successful = 1;
+  st.grad_converged = 0;
+  st.status = (n <= 0) ? PNEC_STATUS_EMPTY : PNEC_STATUS_MAX_ITERATIONS;
+  st.done = (n <= 0) ? 1 : 0;
+  st.pass_mode = kPassFull;
+}
+
+// Start point + start state + pose constants; called by one thread.
+__device__ __forceinline__ void solve_init_state(const SolveArgs &args, long long b, int n,
+                                                 LMState &st, PoseConst &s_pc) {
+  double *x = st.pts[0], *sc = st.scs[0];
+  solve_start_point(args.bv.poses + 7 * b, x, sc);
   st.inv_radius = 1.0 / args.o.initial_trust_region_radius;
   st.decrease_factor = 2.0;
   st.inv_model_cost_change = 0.0;

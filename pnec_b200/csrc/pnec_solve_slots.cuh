@@ -16,8 +16,11 @@
 //                          to the owner.  They never wait for an LM update: while slot A is in its update
 //                          they evaluate slot B.
 //
-// Hand-over is by mbarriers (candidate posted: 1 arrival; partial sums ready: 4 arrivals), no
-// __syncthreads after start-up.  A pair's correspondences are assigned to lanes, and its partial sums
+// Hand-over is by mbarriers, no __syncthreads after start-up and no polling: an owner posts a candidate
+// as a ticket in a small ring (one mbarrier per ring entry, tickets numbered by an atomic counter in
+// shared memory), the evaluation warps sleep in try_wait on the next ticket and so all work through the
+// posted candidates in the same order; the owner sleeps on its slot's "partial sums ready" barrier
+// (4 arrivals).  A pair's correspondences are assigned to lanes, and its partial sums
 // added, exactly as solve_kernel<V, 4, .> does: results are bit-identical to that kernel.
 #pragma once
 
@@ -27,6 +30,20 @@ namespace pnec {
 
 constexpr int kSlotExit = 2;       // SlotCtl::mode besides kPassFull / kPassCost: no more pairs for this slot
 constexpr int kSlotEvalWarps = 4;  // evaluation warps per CTA (== the cross-warp split of solve_kernel<V, 4, .>)
+constexpr int kSlotTickets = 4;    // ring entries; a slot has at most one ticket outstanding, so P <= 4 never laps a reader
+
+// The hand-over from the owners to the evaluation warps.
+struct SlotTickets {
+  unsigned long long bar[kSlotTickets];  // mbarriers, 1 arrival: ticket posted
+  int slot[kSlotTickets];
+  unsigned int tail;
+};
+// Called by ONE lane of an owner: everything it wrote before (candidate, mode) is released to the readers.
+__device__ __forceinline__ void slot_post(SlotTickets &tk, int slot) {
+  const unsigned int t = atomicAdd(&tk.tail, 1u);
+  tk.slot[t & (kSlotTickets - 1)] = slot;
+  mbar_arrive(reinterpret_cast<uint64_t *>(&tk.bar[t & (kSlotTickets - 1)]));
+}
 
 // Slot layout, in doubles, for `cap` correspondences (cap a multiple of 32):
 //   [K packed covariance areas, 6 cap each][f1: 3 cap][f2: 3 cap]
@@ -42,11 +59,16 @@ struct SlotLayout {
 // debug build: cycles summed over the batch: 0 load trip 1, 1 repack, 2 load trip 2, 3 owner waits for the
 // evaluation, 4 LM update, 5 pair total, 6 evaluation warps busy, 7 evaluation warps polling, 8 passes, 9 init
 __device__ unsigned long long g_slot_probe[16];
-#define SLOT_PROBE(k) do { const long long t_now = clock64(); if (lane == 0) atomicAdd(&g_slot_probe[k], (unsigned long long)(t_now - t_prev)); t_prev = t_now; } while (0)
-#define SLOT_PROBE_START() long long t_prev = clock64()
+// (accumulated in registers, flushed once per warp: an atomic per probe costs hundreds of cycles)
+#define SLOT_PROBE(k) do { const long long t_now = clock64(); probe_acc[k] += t_now - t_prev; t_prev = t_now; } while (0)
+#define SLOT_PROBE_START() t_prev = clock64()
+#define SLOT_PROBE_DECL() long long probe_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long t_prev = 0; const long long t_birth = clock64()
+#define SLOT_PROBE_FLUSH() do { if (lane == 0) { probe_acc[12 + (warp_role_)] += clock64() - t_birth; for (int k_ = 0; k_ < 16; ++k_) atomicAdd(&g_slot_probe[k_], (unsigned long long)probe_acc[k_]); } } while (0)
 #else
 #define SLOT_PROBE(k) do { } while (0)
 #define SLOT_PROBE_START() do { } while (0)
+#define SLOT_PROBE_DECL() do { } while (0)
+#define SLOT_PROBE_FLUSH() do { } while (0)
 #endif
 
 struct SlotCtl {
@@ -133,6 +155,20 @@ __device__ __forceinline__ void slot_issue(const BatchView &bv, long long g0, in
   if (f2_now) slot_copy_array(sf2, bv.f2 + 3 * g0, cb, tail, 3, bar);
 }
 
+// The next pair of a slot on its way into L2 while the current one is being solved.
+template <int V>
+__device__ __forceinline__ void slot_prefetch(const BatchView &bv, long long b) {
+  long long s, e;
+  problem_range(bv, b, s, e);
+  const long long g0 = s & ~1LL;
+  const long long cnt = (e - g0) & ~1LL;  // whole 16-byte units inside the batch
+  if (cnt <= 0) return;
+  bulk_prefetch_l2(bv.f1 + 3 * g0, static_cast<uint32_t>(cnt) * 24u);
+  bulk_prefetch_l2(bv.f2 + 3 * g0, static_cast<uint32_t>(cnt) * 24u);
+  if (VariantTraits<V>::kHasCt) bulk_prefetch_l2(bv.ct + 9 * g0, static_cast<uint32_t>(cnt) * 72u);
+  if (VariantTraits<V>::kHasCh) bulk_prefetch_l2(bv.ch + 9 * g0, static_cast<uint32_t>(cnt) * 72u);
+}
+
 // In-place repack of one raw covariance area (9 doubles per correspondence from `src`) to the chunked
 // symmetric layout at `dst` <= src, by one warp, two 32-correspondence waves per turn.  Wave k writes
 // [192 k, 192 (k + 1)) and later waves read from 288 (k + 1) on: a wave never overwrites unread input.
@@ -162,27 +198,42 @@ __device__ __forceinline__ void slot_repack(double *dst, const double *src, int 
   }
 }
 
+// Start points of all pairs, one thread each (acos, atan2 and two sincos per pair: a few microseconds for
+// the batch at full SIMT width, instead of 1200 instructions of a lone lane in front of every pair).
+__global__ void __launch_bounds__(128) solve_prep_kernel(const double *__restrict__ poses, long long num_problems,
+                                                         double *__restrict__ start_state) {
+  const long long b = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (b >= num_problems) return;
+  double x[6], sc[4];
+  solve_start_point(poses + 7 * b, x, sc);
+  double *o = start_state + 10 * b;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) o[i] = x[i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) o[6 + i] = sc[i];
+}
+
 // The owner warp of one slot: claim, load, repack, LM loop, result; until the batch is exhausted.
 template <int V, int P>
 __device__ __forceinline__ void slot_owner_warp(const SolveArgs &args, int slot, SlotCtl &ctl, double *base,
-                                                uint64_t *bar_eval, uint64_t *bar_lm, uint64_t *bar_load,
+                                                SlotTickets &tk, uint64_t *bar_lm, uint64_t *bar_load,
                                                 int lane) {
   constexpr int K = SlotLayout<V>::kCov;
   const int cap = args.cap_elems;
   const pnec_solver_opts &o = args.o;
   uint32_t par_lm = 0, par_load = 0;
-  long long b_static = static_cast<long long>(blockIdx.x) * P + slot;
+  // Pairs are claimed one ahead: the atomic's round trip, the load of the next start point and the L2
+  // prefetch of the next pair's correspondences run under the current pair's solve.
   const long long stride = static_cast<long long>(gridDim.x) * P;
+  long long b = static_cast<long long>(blockIdx.x) * P + slot;
+  if (args.work_counter) {
+    unsigned int v = 0;
+    if (lane == 0) v = atomicAdd(args.work_counter, 1u);
+    b = __shfl_sync(0xffffffffu, v, 0);
+  }
+  double start_v = (lane < 10 && b < args.bv.num_problems) ? args.start_state[10 * b + lane] : 0.0;
+  SLOT_PROBE_DECL();
   for (;;) {
-    long long b;
-    if (args.work_counter) {
-      unsigned int v = 0;
-      if (lane == 0) v = atomicAdd(args.work_counter, 1u);
-      b = __shfl_sync(0xffffffffu, v, 0);
-    } else {
-      b = b_static;
-      b_static += stride;
-    }
     if (b >= args.bv.num_problems) break;
     long long s, e;
     problem_range(args.bv, b, s, e);
@@ -194,13 +245,23 @@ __device__ __forceinline__ void slot_owner_warp(const SolveArgs &args, int slot,
 #ifdef PNEC_SLOT_TIMING
     const long long t_pair = t_prev;
 #endif
+    unsigned int claimed = 0;  // lane 0: the next pair; read after the first candidate is posted
     if (lane == 0) {
-      if (n > 0) {
-        fence_proxy_async();  // the evaluation warps' reads of the previous pair precede these writes
-        slot_issue<V>(args.bv, g0, span, cap, base, bar_load, 1);
-      }
-      solve_init_state(args, b, n, ctl.lm, ctl.pc);  // acos / atan2 / sincos under the copy
+      // (write-after-read against the previous pair's evaluation: every read of the slot returned its
+      // value before the reader arrived on bar_lm, so no proxy fence is needed in front of the copies)
+      if (n > 0) slot_issue<V>(args.bv, g0, span, cap, base, bar_load, 1);
+      if (args.work_counter) claimed = atomicAdd(args.work_counter, 1u);
     }
+    SLOT_PROBE(10);
+    {  // start state: the point from solve_prep_kernel, pose constants one per lane
+      if (lane < 6) ctl.lm.pts[0][lane] = start_v;
+      else if (lane < 10) ctl.lm.scs[0][lane - 6] = start_v;
+      if (lane == 0) solve_reset_state(args, n, ctl.lm);
+      __syncwarp();
+      SLOT_PROBE(11);
+      pose_const_lanes(ctl.lm.pts[0] + 2, ctl.lm.scs[0], ctl.pc, lane);
+    }
+    long long b_next = b + stride;
     __syncwarp();
     SLOT_PROBE(9);
     if (n > 0) {
@@ -212,10 +273,7 @@ __device__ __forceinline__ void slot_owner_warp(const SolveArgs &args, int slot,
         if (K == 2) slot_repack(base + 6 * cap, base + 9 * cap, span, lane);
         __syncwarp();
         SLOT_PROBE(1);
-        if (lane == 0) {
-          fence_proxy_async();
-          slot_issue<V>(args.bv, g0, span, cap, base, bar_load, 2);
-        }
+        if (lane == 0) slot_issue<V>(args.bv, g0, span, cap, base, bar_load, 2);
       }
       mbar_wait(bar_load, par_load);
       par_load ^= 1u;
@@ -225,7 +283,12 @@ __device__ __forceinline__ void slot_owner_warp(const SolveArgs &args, int slot,
         ctl.head = head;
         ctl.span = span;
         ctl.mode = kPassFull;
-        mbar_arrive(bar_eval);
+        slot_post(tk, slot);
+      }
+      if (args.work_counter) b_next = __shfl_sync(0xffffffffu, claimed, 0);
+      if (b_next < args.bv.num_problems) {
+        if (lane == 0) slot_prefetch<V>(args.bv, b_next);
+        if (lane < 10) start_v = args.start_state[10 * b_next + lane];
       }
       bool first = true;
       for (;;) {
@@ -255,42 +318,48 @@ __device__ __forceinline__ void slot_owner_warp(const SolveArgs &args, int slot,
         first = false;
         if (lane == 0) {
           ctl.mode = ctl.lm.pass_mode;
-          mbar_arrive(bar_eval);
+          slot_post(tk, slot);
         }
       }
     }
     if (lane == 0) solve_write_result(args, b, ctl.lm);
     __syncwarp();
 #ifdef PNEC_SLOT_TIMING
-    if (lane == 0) atomicAdd(&g_slot_probe[5], (unsigned long long)(clock64() - t_pair));
+    probe_acc[5] += clock64() - t_pair;
 #endif
+    if (n <= 0) {  // (nothing was posted: the claim and the next start point are still to be read)
+      if (args.work_counter) b_next = __shfl_sync(0xffffffffu, claimed, 0);
+      if (lane < 10 && b_next < args.bv.num_problems) start_v = args.start_state[10 * b_next + lane];
+    }
+    b = b_next;
   }
   if (lane == 0) {
     ctl.mode = kSlotExit;
-    mbar_arrive(bar_eval);
+    slot_post(tk, slot);
   }
+#ifdef PNEC_SLOT_TIMING
+  const int warp_role_ = 0;
+#endif
+  SLOT_PROBE_FLUSH();
 }
 
-// An evaluation warp: quarter `warp` of whichever slot has a candidate posted.
+// An evaluation warp: quarter `warp` of every posted candidate, in ticket order.
 template <int V, int P>
-__device__ __forceinline__ void slot_eval_warp(const SolveArgs &args, SlotCtl *ctl, uint64_t *bar_eval,
+__device__ __forceinline__ void slot_eval_warp(const SolveArgs &args, SlotCtl *ctl, SlotTickets &tk,
                                                uint64_t *bar_lm, int warp, int lane) {
   constexpr int kD = SlotLayout<V>::kDoubles;
   const int cap = args.cap_elems;
   const double reg = args.o.regularization;
-  unsigned par = 0, alive = (1u << P) - 1u;
-  int s = 0;
+  int exited = 0;
+  SLOT_PROBE_DECL();
   SLOT_PROBE_START();
-  while (alive) {
-    if (!((alive >> s) & 1u) || !mbar_test_wait(&bar_eval[s], (par >> s) & 1u)) {
-      s = (s + 1 == P) ? 0 : s + 1;
-      continue;
-    }
-    par ^= 1u << s;
+  for (unsigned int h = 0; exited < P; ++h) {
+    mbar_wait(reinterpret_cast<uint64_t *>(&tk.bar[h & (kSlotTickets - 1)]), (h / kSlotTickets) & 1u);
+    const int s = tk.slot[h & (kSlotTickets - 1)];
     SlotCtl &c = ctl[s];
     const int mode = c.mode;
     if (mode == kSlotExit) {
-      alive &= ~(1u << s);
+      ++exited;
       continue;
     }
     SLOT_PROBE(7);
@@ -327,35 +396,42 @@ __device__ __forceinline__ void slot_eval_warp(const SolveArgs &args, SlotCtl *c
     if (lane == 0) mbar_arrive(&bar_lm[s]);
     SLOT_PROBE(6);
 #ifdef PNEC_SLOT_TIMING
-    if (lane == 0 && warp == 0) atomicAdd(&g_slot_probe[8], 1ull);
+    if (warp == 0) probe_acc[8] += 1;
 #endif
-    s = (s + 1 == P) ? 0 : s + 1;
   }
+#ifdef PNEC_SLOT_TIMING
+  const int warp_role_ = 1;
+#endif
+  SLOT_PROBE_FLUSH();
 }
 
 template <int V, int P>
 __global__ void __launch_bounds__((kSlotEvalWarps + P) * 32, 2)
 solve_slots_kernel(const __grid_constant__ SolveArgs args) {
-  __shared__ __align__(8) uint64_t s_bar_eval[P], s_bar_lm[P], s_bar_load[P];
+  static_assert(P <= kSlotTickets, "a reader must never be lapped");
+  __shared__ __align__(8) uint64_t s_bar_lm[P], s_bar_load[P];
+  __shared__ __align__(8) SlotTickets s_tk;
   __shared__ SlotCtl s_ctl[P];
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < P; ++s) {
-      mbar_init(&s_bar_eval[s], 1);
       mbar_init(&s_bar_lm[s], kSlotEvalWarps);
       mbar_init(&s_bar_load[s], 1);
     }
+#pragma unroll
+    for (int r = 0; r < kSlotTickets; ++r) mbar_init(reinterpret_cast<uint64_t *>(&s_tk.bar[r]), 1);
+    s_tk.tail = 0u;
     fence_mbar_init();
   }
   __syncthreads();
   if (warp >= kSlotEvalWarps) {
     const int slot = warp - kSlotEvalWarps;
     double *base = dyn_smem + static_cast<size_t>(slot) * SlotLayout<V>::kDoubles * args.cap_elems;
-    slot_owner_warp<V, P>(args, slot, s_ctl[slot], base, &s_bar_eval[slot], &s_bar_lm[slot], &s_bar_load[slot], lane);
+    slot_owner_warp<V, P>(args, slot, s_ctl[slot], base, s_tk, &s_bar_lm[slot], &s_bar_load[slot], lane);
   } else {
-    slot_eval_warp<V, P>(args, s_ctl, s_bar_eval, s_bar_lm, warp, lane);
+    slot_eval_warp<V, P>(args, s_ctl, s_tk, s_bar_lm, warp, lane);
   }
   __syncthreads();
   // the work counter serves the next launch on this stream: the last CTA to leave rewinds it

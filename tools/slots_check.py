@@ -16,7 +16,7 @@ def handle(**env):
     return h
 
 
-def timed(fn, reps=20):
+def timed(fn, reps=50):
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
@@ -53,8 +53,8 @@ def case(name, b, variant, **kw):
             print("   pair", i, "old", ro.poses[i].tolist(), int(ro.iterations[i]), float(ro.initial_cost[i]))
             print("   pair", i, "new", rn.poses[i].tolist(), int(rn.iterations[i]), float(rn.initial_cost[i]))
     row = dict(case=name, B=int(b.num_problems), bit_identical=bool(same),
-               ms_old4=timed(lambda: old.solve_batch(*args, **kw)), ms_old_default=timed(lambda: dflt.solve_batch(*args, **kw)),
-               ms_slots=timed(lambda: new.solve_batch(*args, **kw)),
+               ms_old4=timed(lambda: old.solve_batch(*args, out=ro, **kw)), ms_old_default=timed(lambda: dflt.solve_batch(*args, out=ro, **kw)),
+               ms_slots=timed(lambda: new.solve_batch(*args, out=rn, **kw)),
                mean_iterations=float(rn.iterations.double().mean()))
     print(json.dumps(row), flush=True)
     return same
