@@ -177,8 +177,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) solve_kernel(const __grid_const
         t_e += t1 - t0;
 #endif
         if (warp == lmw) {
-          if (first) lm_step<true>(s_lm, o, lane, s_pc);
-          else lm_step<false>(s_lm, o, lane, s_pc);
+          lm_step(first, s_lm, o, lane, s_pc);
         }
 #ifdef PNEC_PHASE_TIMING
         const long long t2 = clock64();
@@ -314,8 +313,7 @@ solve_stream_kernel(const __grid_constant__ SolveArgs args) {
       } else {
         block_reduce<NW>(acc, s_part, warp, lane, s_lm.tot[s_lm.ti ^ 1], lmw);
         if (warp == lmw) {
-          if (first) lm_step<true>(s_lm, o, lane, s_pc);
-          else lm_step<false>(s_lm, o, lane, s_pc);
+          lm_step(first, s_lm, o, lane, s_pc);
         }
       }
       __syncthreads();

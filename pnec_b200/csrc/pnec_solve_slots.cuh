@@ -309,8 +309,7 @@ __device__ __forceinline__ void slot_owner_warp(const SolveArgs &args, int slot,
             ctl.lm.tot[ctl.lm.ti ^ 1][lane] = mine * acc_scale(lane);
           }
           __syncwarp();
-          if (first) lm_step<true>(ctl.lm, o, lane, ctl.pc);
-          else lm_step<false>(ctl.lm, o, lane, ctl.pc);
+          lm_step(first, ctl.lm, o, lane, ctl.pc);
         }
         __syncwarp();
         SLOT_PROBE(4);
