@@ -605,7 +605,7 @@ int slot_counter(pnec_handle *h, cudaStream_t stream, unsigned int **out, DevBuf
 template <int V>
 int slots_capacity(pnec_handle *h, int *static_smem) {
   cudaFuncAttributes fa{};
-  if (cudaFuncGetAttributes(&fa, solve_slots_kernel<V, 2>) != cudaSuccess) {
+  if (cudaFuncGetAttributes(&fa, solve_slots_kernel<V, 2, 1>) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
@@ -621,9 +621,11 @@ int launch_solve_slots_v(pnec_handle *h, SolveArgs a, long long need, cudaStream
   if (cap_max < 0) cap_max = slots_capacity<V>(h, &static_smem);
   const long long cap = (need + 31) & ~31LL;
   if (cap > cap_max) return PNEC_OK;
-  auto kern = solve_slots_kernel<V, 2>;
-  const size_t dyn = static_cast<size_t>(2) * SlotLayout<V>::kDoubles * 8 * static_cast<size_t>(cap);
-  PNEC_CUDA(ensure_dyn_smem(h, kern, dyn));
+  // (one CTA per SM with four slots and two evaluation groups serving all of them -- solve_slots_kernel<V, 4, 2>
+  // -- was measured too: the same 0.485 ms on C2, so the queueing for an evaluation group is not what binds)
+  constexpr int P = 2;
+  const size_t dyn = static_cast<size_t>(P) * SlotLayout<V>::kDoubles * 8 * static_cast<size_t>(cap);
+  PNEC_CUDA(ensure_dyn_smem(h, solve_slots_kernel<V, 2, 1>, dyn));
   DevBuf *start = nullptr;
   int rc = slot_counter(h, stream, &a.work_counter, &start);
   if (rc != PNEC_OK) return rc;
@@ -636,8 +638,8 @@ int launch_solve_slots_v(pnec_handle *h, SolveArgs a, long long need, cudaStream
   a.cap_elems = static_cast<int>(cap);
   a.use_bulk = 1;
   a.dbg = nullptr;
-  const unsigned grid = static_cast<unsigned>(std::min<long long>(2LL * h->sm_count, (a.bv.num_problems + 1) / 2));
-  kern<<<grid, (kSlotEvalWarps + 2) * 32, dyn, stream>>>(a);
+  const unsigned grid = static_cast<unsigned>(std::min<long long>(2LL * h->sm_count, (a.bv.num_problems + P - 1) / P));
+  solve_slots_kernel<V, 2, 1><<<grid, (kSlotEvalWarps + 2) * 32, dyn, stream>>>(a);
   PNEC_CUDA(cudaGetLastError());
   h->launches++;
 #ifdef PNEC_SLOT_TIMING
@@ -1075,8 +1077,10 @@ int ensure_ransac_scratch(pnec_handle *h, long long B) {
 }
 
 // `bv`: pairs [pair0, pair0 + bv.num_problems) of the batch the scratch was sized for, chunk `chunk`.
+// `may_sync`: the caller is a small HOST-memspace call (it synchronises anyway): look at the number of pairs
+// pass 1 deferred and skip the ~20 launches of pass 2 when there is none (the usual case for one clean pair).
 int run_ransac(pnec_handle *h, const BatchView &bv, const pnec_frame_opts &o, long long pair_index_base,
-               const RansacOut &out, long long pair0, int chunk, cudaStream_t stream) {
+               const RansacOut &out, long long pair0, int chunk, cudaStream_t stream, bool may_sync = false) {
   RansacArgs a{};
   a.bv = bv;
   a.best_poses = out.best;
@@ -1116,6 +1120,12 @@ int run_ransac(pnec_handle *h, const BatchView &bv, const pnec_frame_opts &o, lo
   else ransac_kernel<4, 4><<<grid, 128, 0, stream>>>(a);
   PNEC_CUDA(cudaGetLastError());
   h->launches++;
+  if (defer_after > 0 && may_sync) {
+    int deferred = -1;
+    PNEC_CUDA(cudaMemcpyAsync(&deferred, a.defer, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    PNEC_CUDA(cudaStreamSynchronize(stream));
+    if (deferred == 0) return PNEC_OK;
+  }
   if (defer_after > 0) {
     // Pass 2: every super-round finishes a deferred pair or consumes its whole grant (ransac_grant), so
     // this many super-rounds cover the worst case; with nothing (left) to do the kernels return at once.
@@ -1695,7 +1705,7 @@ int pnec_ransac_batch(pnec_handle *h, const pnec_batch *batch, const pnec_frame_
   }
   rc = ensure_ransac_scratch(h, B);
   if (rc != PNEC_OK) return rc;
-  rc = run_ransac(h, st.bv, *opts, pair_index_base, ro, 0, 0, stream);
+  rc = run_ransac(h, st.bv, *opts, pair_index_base, ro, 0, 0, stream, host && B <= 64);
   if (rc != PNEC_OK) return rc;
   if (host) {
     PNEC_CUDA(cudaMemcpyAsync(out_models, ro.best, nb * 56, cudaMemcpyDeviceToHost, stream));
@@ -1824,7 +1834,8 @@ int pnec_frame_solve_batch(pnec_handle *h, const pnec_batch *batch, const pnec_f
       r.f1 += 3 * e0; r.f2 += 3 * e0;
       if (r.ct) r.ct += 9 * e0;
       if (r.index) r.index += e0;
-      if ((rcc = run_ransac(h, bv, *opts, opts->ransac_pair_index_base + c0, r, c0, chunk, cs)) != PNEC_OK) return rcc;
+      if ((rcc = run_ransac(h, bv, *opts, opts->ransac_pair_index_base + c0, r, c0, chunk, cs, host && B <= 64)) != PNEC_OK)
+        return rcc;
       bv.f1 = r.f1; bv.f2 = r.f2;
       if (r.ct) bv.ct = r.ct;
       bv.counts = r.count;

@@ -30,13 +30,14 @@ namespace pnec {
 
 constexpr int kSlotExit = 2;       // SlotCtl::mode besides kPassFull / kPassCost: no more pairs for this slot
 constexpr int kSlotEvalWarps = 4;  // evaluation warps per CTA (== the cross-warp split of solve_kernel<V, 4, .>)
-constexpr int kSlotTickets = 4;    // ring entries; a slot has at most one ticket outstanding, so P <= 4 never laps a reader
+constexpr int kSlotTickets = 8;    // ring entries; a slot has at most one ticket outstanding, so P <= 8 never laps a reader
 
 // The hand-over from the owners to the evaluation warps.
 struct SlotTickets {
   unsigned long long bar[kSlotTickets];  // mbarriers, 1 arrival: ticket posted
-  int slot[kSlotTickets];
+  int slot[kSlotTickets];        // -1: no more work (posted once per evaluation group by the last owner to leave)
   unsigned int tail;
+  unsigned int owners_gone;
 };
 // Called by ONE lane of an owner: everything it wrote before (candidate, mode) is released to the readers.
 __device__ __forceinline__ void slot_post(SlotTickets &tk, int slot) {
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(128) solve_prep_kernel(const double *__restric
 }
 
 // The owner warp of one slot: claim, load, repack, LM loop, result; until the batch is exhausted.
-template <int V, int P>
+template <int V, int P, int G>
 __device__ __forceinline__ void slot_owner_warp(const SolveArgs &args, int slot, SlotCtl &ctl, double *base,
                                                 SlotTickets &tk, uint64_t *bar_lm, uint64_t *bar_load,
                                                 int lane) {
@@ -332,9 +333,8 @@ __device__ __forceinline__ void slot_owner_warp(const SolveArgs &args, int slot,
     }
     b = b_next;
   }
-  if (lane == 0) {
-    ctl.mode = kSlotExit;
-    slot_post(tk, slot);
+  if (lane == 0 && atomicAdd(&tk.owners_gone, 1u) == P - 1) {
+    for (int g = 0; g < G; ++g) slot_post(tk, -1);  // consecutive tickets: one for every evaluation group
   }
 #ifdef PNEC_SLOT_TIMING
   const int warp_role_ = 0;
@@ -342,25 +342,22 @@ __device__ __forceinline__ void slot_owner_warp(const SolveArgs &args, int slot,
   SLOT_PROBE_FLUSH();
 }
 
-// An evaluation warp: quarter `warp` of every posted candidate, in ticket order.
-template <int V, int P>
+// An evaluation warp: quarter `warp` of the posted candidates that fall to its group (ticket t goes to group
+// t mod G), in ticket order.
+template <int V, int P, int G>
 __device__ __forceinline__ void slot_eval_warp(const SolveArgs &args, SlotCtl *ctl, SlotTickets &tk,
-                                               uint64_t *bar_lm, int warp, int lane) {
+                                               uint64_t *bar_lm, int group, int warp, int lane) {
   constexpr int kD = SlotLayout<V>::kDoubles;
   const int cap = args.cap_elems;
   const double reg = args.o.regularization;
-  int exited = 0;
   SLOT_PROBE_DECL();
   SLOT_PROBE_START();
-  for (unsigned int h = 0; exited < P; ++h) {
+  for (unsigned int h = group;; h += G) {
     mbar_wait(reinterpret_cast<uint64_t *>(&tk.bar[h & (kSlotTickets - 1)]), (h / kSlotTickets) & 1u);
     const int s = tk.slot[h & (kSlotTickets - 1)];
+    if (s < 0) break;
     SlotCtl &c = ctl[s];
     const int mode = c.mode;
-    if (mode == kSlotExit) {
-      ++exited;
-      continue;
-    }
     SLOT_PROBE(7);
     const double *base = dyn_smem + static_cast<size_t>(s) * kD * cap;
     PoseConst pc;
@@ -404,8 +401,10 @@ __device__ __forceinline__ void slot_eval_warp(const SolveArgs &args, SlotCtl *c
   SLOT_PROBE_FLUSH();
 }
 
-template <int V, int P>
-__global__ void __launch_bounds__((kSlotEvalWarps + P) * 32, 2)
+// P slots (= owner warps) and G groups of four evaluation warps per CTA: <2, 1> twice per SM, or <4, 2> once
+// (the two groups then serve all four slots of the SM).
+template <int V, int P, int G>
+__global__ void __launch_bounds__((kSlotEvalWarps * G + P) * 32, G == 1 ? 2 : 1)
 solve_slots_kernel(const __grid_constant__ SolveArgs args) {
   static_assert(P <= kSlotTickets, "a reader must never be lapped");
   __shared__ __align__(8) uint64_t s_bar_lm[P], s_bar_load[P];
@@ -422,15 +421,16 @@ solve_slots_kernel(const __grid_constant__ SolveArgs args) {
 #pragma unroll
     for (int r = 0; r < kSlotTickets; ++r) mbar_init(reinterpret_cast<uint64_t *>(&s_tk.bar[r]), 1);
     s_tk.tail = 0u;
+    s_tk.owners_gone = 0u;
     fence_mbar_init();
   }
   __syncthreads();
-  if (warp >= kSlotEvalWarps) {
-    const int slot = warp - kSlotEvalWarps;
+  if (warp >= kSlotEvalWarps * G) {
+    const int slot = warp - kSlotEvalWarps * G;
     double *base = dyn_smem + static_cast<size_t>(slot) * SlotLayout<V>::kDoubles * args.cap_elems;
-    slot_owner_warp<V, P>(args, slot, s_ctl[slot], base, s_tk, &s_bar_lm[slot], &s_bar_load[slot], lane);
+    slot_owner_warp<V, P, G>(args, slot, s_ctl[slot], base, s_tk, &s_bar_lm[slot], &s_bar_load[slot], lane);
   } else {
-    slot_eval_warp<V, P>(args, s_ctl, s_tk, s_bar_lm, warp, lane);
+    slot_eval_warp<V, P, G>(args, s_ctl, s_tk, s_bar_lm, warp / kSlotEvalWarps, warp % kSlotEvalWarps, lane);
   }
   __syncthreads();
   // the work counter serves the next launch on this stream: the last CTA to leave rewinds it

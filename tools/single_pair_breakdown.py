@@ -24,3 +24,11 @@ for w in ("1", "2"):
 os.environ["PNEC_B200_RANSAC_DEFER"] = "0"
 h3 = api.Handle(0)
 print("ransac_batch alone, warps=2 no pass 2   %.3f ms" % t(lambda k: h3.ransac_batch(args(k)[0], args(k)[1], args(k)[3], api.default_frame_opts(), n_per_problem=N)))
+# pinned host buffers (what packing small inputs into one pinned staging block would give at best)
+import torch
+os.environ.pop("PNEC_B200_RANSAC_WARPS", None); os.environ.pop("PNEC_B200_RANSAC_DEFER", None)
+hp = api.Handle(0)
+pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+P = [tuple(pin(x) for x in args(k)) for k in range(8)]
+print("pinned inputs: frame default   %.3f ms" % t(lambda k: hp.frame_solve_batch(*P[k], api.default_frame_opts(), n_per_problem=N)))
+print("pinned inputs: frame no ransac %.3f ms" % t(lambda k: hp.frame_solve_batch(*P[k], api.default_frame_opts(use_ransac=0), n_per_problem=N)))
