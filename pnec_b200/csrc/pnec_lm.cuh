@@ -334,8 +334,13 @@ __device__ unsigned long long g_lm_probe[8];
 // (`first` is a run-time flag, not a template parameter: two instantiations doubled the update's code, and the
 // update is bound by instruction fetch -- the L1.5 instruction cache delivers ~4 lines per cycle to the whole
 // GPU, and the solve kernels used 66-73 % of that with the update's code streamed in for every update.)
+// `post(pass_mode)` is called by the whole warp as soon as the candidate's pose constants are stored.
+struct LmNoPost {
+  __device__ __forceinline__ void operator()(int) const {}
+};
+template <class Post = LmNoPost>
 __device__ __forceinline__ void lm_step(const bool FIRST, LMState &st, const pnec_solver_opts &o, int lane,
-                                        PoseConst &s_pc) {
+                                        PoseConst &s_pc, Post post = Post()) {
 #ifdef PNEC_PHASE_TIMING
   long long t_prev = clock64();
 #endif
@@ -472,9 +477,17 @@ __device__ __forceinline__ void lm_step(const bool FIRST, LMState &st, const pne
       for (int i = 0; i < 4; ++i) scn[i] = scc[i];
     }
     __syncwarp();
+    // If the quadratic model already predicts |cost change| <= function_tolerance * cost the
+    // iteration will almost surely terminate there: evaluate the cost alone first.
+    pass_mode = (mcc <= 1.05 * o.function_tolerance * x_cost) ? kPassCost : kPassFull;
+    // The candidate is complete: pose constants, and the caller may hand it to the evaluation already
+    // (solve_slots_kernel does; what follows is off the pair's critical path).
+    pose_const_lanes(cnd + 2, scn, s_pc, lane);
+    post(pass_mode);
+    LM_PROBE(3);  // candidate
     // ParameterToleranceReached depends on the step only.  Ceres evaluates the candidate's
     // cost first and then returns without applying the step, so the evaluation cannot change
-    // the outcome: decide here and skip it.
+    // the outcome: decide here and skip it (a caller that posted the candidate above discards its sums).
     const double e0 = x[0] - cnd[0], e1 = x[1] - cnd[1], e2 = x[2] - cnd[2];
     const double e3 = x[3] - cnd[3], e4 = x[4] - cnd[4], e5 = x[5] - cnd[5];
     const double sn = fma(e0, e0, e1 * e1) + fma(e2, e2, e3 * e3) + fma(e4, e4, e5 * e5);
@@ -491,12 +504,7 @@ __device__ __forceinline__ void lm_step(const bool FIRST, LMState &st, const pne
         done = 1;
       }
     }
-    // If the quadratic model already predicts |cost change| <= function_tolerance * cost the
-    // iteration will almost surely terminate there: evaluate the cost alone first.
-    pass_mode = (mcc <= 1.05 * o.function_tolerance * x_cost) ? kPassCost : kPassFull;
   }
-  LM_PROBE(3);  // candidate
-  if (!done) pose_const_lanes(cnd + 2, scn, s_pc, lane);
   if (lane < 5) {
     if (FIRST) {
       st.scale[lane] = scale_l;

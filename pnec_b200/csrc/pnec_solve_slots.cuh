@@ -296,6 +296,7 @@ __device__ __forceinline__ void slot_owner_warp(const SolveArgs &args, int slot,
         mbar_wait(bar_lm, par_lm);
         par_lm ^= 1u;
         SLOT_PROBE(3);
+        bool posted = false;
         if (ctl.mode == kPassCost) {
           double t = 0.0;
 #pragma unroll
@@ -310,13 +311,27 @@ __device__ __forceinline__ void slot_owner_warp(const SolveArgs &args, int slot,
             ctl.lm.tot[ctl.lm.ti ^ 1][lane] = mine * acc_scale(lane);
           }
           __syncwarp();
-          lm_step(first, ctl.lm, o, lane, ctl.pc);
+          // the candidate is posted from inside the update, before its bookkeeping
+          lm_step(first, ctl.lm, o, lane, ctl.pc, [&](int pass_mode) {
+            __syncwarp();
+            if (lane == 0) {
+              ctl.mode = pass_mode;
+              slot_post(tk, slot);
+            }
+            posted = true;
+          });
         }
         __syncwarp();
         SLOT_PROBE(4);
-        if (ctl.lm.done) break;
+        if (ctl.lm.done) {
+          if (posted) {  // converged by parameter tolerance after the candidate went out: discard its sums
+            mbar_wait(bar_lm, par_lm);
+            par_lm ^= 1u;
+          }
+          break;
+        }
         first = false;
-        if (lane == 0) {
+        if (!posted && lane == 0) {  // after a cost-only pass: the same candidate again, in full
           ctl.mode = ctl.lm.pass_mode;
           slot_post(tk, slot);
         }
