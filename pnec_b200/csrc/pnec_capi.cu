@@ -93,6 +93,7 @@ struct Config {
   int no_stager = 0;
   int ransac_warps = 0;
   int ransac_defer = -1;  // PNEC_B200_RANSAC_DEFER: iterations after which pass 1 hands a pair to pass 2 (0: never)
+  int ransac_split = 1;   // PNEC_B200_RANSAC_SPLIT: pass 1 of large batches as three kernels per round (0: one kernel)
   int scf_debug = 0;
   int scf_defer = 48;
   int scf_warps = 0;
@@ -111,6 +112,7 @@ struct Config {
     no_stager = env_int("PNEC_B200_NO_STAGER", 0);
     ransac_warps = env_int("PNEC_B200_RANSAC_WARPS", 0);
     ransac_defer = env_int("PNEC_B200_RANSAC_DEFER", -1);
+    ransac_split = env_int("PNEC_B200_RANSAC_SPLIT", 1);
     scf_debug = env_int("PNEC_B200_SCF_DEBUG", 0);
     scf_defer = env_int("PNEC_B200_SCF_DEFER", 48);
     scf_warps = env_int("PNEC_B200_SCF_WARPS", 0);
@@ -275,6 +277,7 @@ struct pnec_handle {
   DevBuf d_rs_f1, d_rs_f2, d_rs_ct;  // RANSAC: inliers compacted to the front of every pair's slot
   DevBuf d_rs_best, d_rs_cnt, d_rs_iters, d_rs_idx;  // winning models [B][7], counts, iterations, indices
   DevBuf d_rs_state, d_rs_defer, d_rs_prefix, d_rs_hyp;  // pass 2 of the RANSAC stage (pnec_ransac.cuh)
+  DevBuf d_rs_sp_mom, d_rs_sp_x, d_rs_sp_int;            // pass 1 as three kernels per round
   DevBuf d_kp_hp, d_kp_tp, d_kp_hc, d_kp_tc, d_kp_hi, d_kp_ti;  // keypoint tables and match indices (HOST callers)
   DevBuf d_pk_ct, d_pk_ch;  // PNEC_COV_PACKED covariances of HOST callers before expansion
   DevBuf d_slot_ctr;        // work counters of solve_slots_kernel, one {next pair, CTAs gone} per stream seen
@@ -1073,6 +1076,11 @@ int ensure_ransac_scratch(pnec_handle *h, long long B) {
   PNEC_CUDA(h->d_rs_defer.ensure(sizeof(int) * (4 * pnec_handle::kMaxChunks + nb)));
   PNEC_CUDA(h->d_rs_prefix.ensure(sizeof(int) * (pnec_handle::kMaxChunks + nb)));
   PNEC_CUDA(h->d_rs_hyp.ensure(sizeof(int) * nb * kRansacSuper));
+  if (h->cfg.ransac_split) {
+    PNEC_CUDA(h->d_rs_sp_mom.ensure(nb * 8 * kEsMom * sizeof(double)));
+    PNEC_CUDA(h->d_rs_sp_x.ensure(nb * 8 * 3 * sizeof(double)));
+    PNEC_CUDA(h->d_rs_sp_int.ensure(nb * (8 + 8 + 1) * sizeof(int)));  // i0 [B][8], active [B][8], live [B]
+  }
   return PNEC_OK;
 }
 
@@ -1115,11 +1123,33 @@ int run_ransac(pnec_handle *h, const BatchView &bv, const pnec_frame_opts &o, lo
   const unsigned grid = static_cast<unsigned>(bv.num_problems);
   // compiled for 16 warps per SM (128 registers): the hypotheses are latency bound (255 / 168 registers,
   // i.e. 8 / 12 warps per SM, measured 15 % / 3 % slower)
-  if (nw == 1) ransac_kernel<1, 16><<<grid, 32, 0, stream>>>(a);
-  else if (nw == 2) ransac_kernel<2, 8><<<grid, 64, 0, stream>>>(a);
-  else ransac_kernel<4, 4><<<grid, 128, 0, stream>>>(a);
-  PNEC_CUDA(cudaGetLastError());
-  h->launches++;
+  if (nw == 1 && defer_after > 0 && h->cfg.ransac_split && h->d_rs_sp_mom.p) {
+    // large batches: every round of pass 1 as three kernels over the pairs still in it (pnec_ransac.cuh:
+    // the one-kernel form is bound by instruction fetch)
+    const long long B0 = bv.num_problems;
+    a.sp_mom = static_cast<double *>(h->d_rs_sp_mom.p) + pair0 * 8 * kEsMom;
+    a.sp_x = static_cast<double *>(h->d_rs_sp_x.p) + pair0 * 8 * 3;
+    int *ints = static_cast<int *>(h->d_rs_sp_int.p);
+    const long long nb_all = static_cast<long long>(h->d_rs_sp_int.cap / (17 * sizeof(int)));  // layout by capacity
+    a.sp_i0 = ints + pair0 * 8;
+    a.sp_active = ints + nb_all * 8 + pair0 * 8;
+    a.sp_live = ints + nb_all * 16 + pair0;
+    const int rounds1 = (std::min(defer_after, o.max_ransac_iterations + 1) + 7) / 8;
+    for (int r = 0; r < rounds1; ++r) {
+      a.sp_round = r;
+      ransac_pre_kernel<<<static_cast<unsigned>((B0 + 3) / 4), 128, 0, stream>>>(a);
+      ransac_lm_kernel<<<static_cast<unsigned>((B0 * 8 + kEsLmPairs - 1) / kEsLmPairs), kEsLmThreads, 0, stream>>>(a);
+      ransac_post_kernel<<<grid, 32, 0, stream>>>(a);
+    }
+    PNEC_CUDA(cudaGetLastError());
+    h->launches += 3 * rounds1;
+  } else {
+    if (nw == 1) ransac_kernel<1, 16><<<grid, 32, 0, stream>>>(a);
+    else if (nw == 2) ransac_kernel<2, 8><<<grid, 64, 0, stream>>>(a);
+    else ransac_kernel<4, 4><<<grid, 128, 0, stream>>>(a);
+    PNEC_CUDA(cudaGetLastError());
+    h->launches++;
+  }
   if (defer_after > 0 && may_sync) {
     int deferred = -1;
     PNEC_CUDA(cudaMemcpyAsync(&deferred, a.defer, sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -1233,6 +1263,7 @@ void pnec_destroy(pnec_handle *h) {
                     &h->d_fr_es, &h->d_fr_a, &h->d_fr_cache, &h->d_fr_flags, &h->d_scf_defer, &h->d_fr_defer, &h->d_scf_spill,
                     &h->d_rs_f1, &h->d_rs_f2, &h->d_rs_ct, &h->d_rs_best, &h->d_rs_cnt, &h->d_rs_iters, &h->d_rs_idx,
                     &h->d_rs_state, &h->d_rs_defer, &h->d_rs_prefix, &h->d_rs_hyp,
+                    &h->d_rs_sp_mom, &h->d_rs_sp_x, &h->d_rs_sp_int,
                     &h->d_kp_hp, &h->d_kp_tp, &h->d_kp_hc, &h->d_kp_tc, &h->d_kp_hi, &h->d_kp_ti};
   for (DevBuf *b : bufs) b->release();
   for (DevBuf &b : h->d_kp_out) b.release();

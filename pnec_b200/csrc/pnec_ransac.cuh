@@ -64,6 +64,13 @@ struct RansacArgs {
                              // super-round, [3] cursor of ransac_final_kernel; the list follows at defer + 4 [B]
   int *blk_prefix;           // [B + 1] exclusive prefix of the work items per deferred slot
   int *hyp_count;            // [B][kRansacSuper] inlier counts of the current super-round
+  // pass 1 as three kernels per round (ransac_pre_kernel / ransac_lm_kernel / ransac_post_kernel)
+  double *sp_mom;            // [B][8][36] moment sums of the round's samples
+  double *sp_x;              // [B][8][3]  Cayley start of the round's hypotheses, overwritten by the LM result
+  int *sp_i0;                // [B][8]     first correspondence of the sample (sign of the translation)
+  int *sp_active;            // [B][8]     hypothesis takes part in this round
+  int *sp_live;              // [B]        pair still in pass 1
+  int sp_round;              // round r evaluates hypotheses 8 r .. 8 r + 7
 };
 
 __device__ __forceinline__ unsigned long long rs_mix(unsigned long long z) {  // splitmix64 finaliser
@@ -432,6 +439,236 @@ __global__ void __launch_bounds__(NW * 32, MINB) ransac_kernel(const __grid_cons
     }
   }
   ransac_select<NW>(args, b, s, n, f1, f2, s_best, s_state[1], s_wcnt);
+}
+
+// ------------------------------------------------------------------ pass 1, split
+//
+// ransac_kernel spends 65 % of its stall samples waiting for instructions (ncu: `no_inst`, L1.5 instruction
+// bandwidth 96 % used, ICC hit rate 53 %): sampling, the unrolled Levenberg-Marquardt, the model and the
+// scoring loop are one 126 KB body, and every warp of an SM is somewhere else in it.  es_lm_kernel -- the
+// same LM, alone in its kernel -- does not have the problem (89 % ICC hits, 40 % of the bandwidth).  For
+// large batches a round of pass 1 therefore runs as three kernels over all pairs still in it:
+//   ransac_pre_kernel   sample, 36 moment sums, perturbed start          (one warp per pair, 8 hypotheses)
+//   ransac_lm_kernel    es_lm_group on B x 8 virtual pairs               (as es_lm_kernel)
+//   ransac_post_kernel  model, scores, bookkeeping, inlier extraction    (one warp per pair)
+// with the pair's state (best model, count, k, iterations) in RansacPairState between the kernels.  The
+// same device functions in the same order as ransac_hypothesis / ransac_kernel<1, .>; a pair unfinished
+// after `defer_after` iterations goes to pass 2 exactly as before (its best model travels in the state,
+// so no hypothesis of pass 1 is ever rebuilt by another kernel).
+
+__global__ void __launch_bounds__(128) ransac_pre_kernel(const __grid_constant__ RansacArgs args) {
+  constexpr int NG = 8;
+  __shared__ int s_front[4][kRansacMaxSample * NG], s_bpos[4][kRansacMaxSample * NG], s_bval[4][kRansacMaxSample * NG];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, sub = lane & 3;
+  const long long b = static_cast<long long>(blockIdx.x) * 4 + warp;
+  if (b >= args.bv.num_problems) return;
+  long long s, e;
+  problem_range(args.bv, b, s, e);
+  const int n = static_cast<int>(e - s);
+  const int ns = args.sample_size;
+  const double *f1 = args.bv.f1 + 3 * s, *f2 = args.bv.f2 + 3 * s;
+  const double *pose = args.bv.poses + 7 * b;
+  int live;
+  if (args.sp_round == 0) {
+    live = !(n < ns || ns < 1);
+    if (lane == 0) {
+      RansacPairState &st = args.state[b];
+      st.k = 1.0;
+      st.best_count = -1;
+      st.iters = 0;
+      st.done = 0;
+      st.best_h = -1;
+      st.best_in_state = 1;
+      args.sp_live[b] = live;
+      if (!live) {  // getSamples: "Can not select %zu unique points out of %zu": no model
+        const double qn = 1.0 / sqrt(pose[0] * pose[0] + pose[1] * pose[1] + pose[2] * pose[2] + pose[3] * pose[3]);
+        double *bp = args.best_poses + 7 * b;
+        bp[0] = pose[0] * qn; bp[1] = pose[1] * qn; bp[2] = pose[2] * qn; bp[3] = pose[3] * qn;
+        bp[4] = pose[4]; bp[5] = pose[5]; bp[6] = pose[6];
+        args.num_inliers[b] = 0;
+        args.iterations[b] = 0;
+      }
+    }
+  } else {
+    live = args.sp_live[b];
+  }
+  const int h = args.sp_round * NG + g;  // == opengv's iterations_ for this hypothesis
+  const bool active = live && h <= args.max_iterations;
+  const long long vb = b * NG + g;
+  if (sub == 0) args.sp_active[vb] = active ? 1 : 0;
+  if (!active) return;
+  const unsigned long long pair = static_cast<unsigned long long>(args.pair_index_base + b);
+  int *front = s_front[warp], *bpos = s_bpos[warp], *bval = s_bval[warp];
+  if (sub == 0) {
+    // drawIndexSample from the identity permutation (as in ransac_hypothesis)
+    int nb = 0;
+    for (int i = 0; i < ns; ++i) front[i * NG + g] = i;
+    for (int i = 0; i < ns; ++i) {
+      const int j = i + static_cast<int>(rs_u31(args.seed, pair, h, i) % static_cast<unsigned>(n - i));
+      const int vi = front[i * NG + g];
+      if (j < ns) {
+        front[i * NG + g] = front[j * NG + g];
+        front[j * NG + g] = vi;
+      } else {
+        int k = 0;
+        while (k < nb && bpos[k * NG + g] != j) ++k;
+        if (k == nb) { bpos[k * NG + g] = j; bval[k * NG + g] = j; ++nb; }
+        front[i * NG + g] = bval[k * NG + g];
+        bval[k * NG + g] = vi;
+      }
+    }
+  }
+  __syncwarp(0xfu << (lane & ~3));
+  double acc0[6] = {0, 0, 0, 0, 0, 0}, acc1[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < ns; ++i) {
+    const int idx = front[i * NG + g];
+    const double a[3] = {f1[3 * idx], f1[3 * idx + 1], f1[3 * idx + 2]};
+    const double c[3] = {f2[3 * idx], f2[3 * idx + 1], f2[3 * idx + 2]};
+    const double A[6] = {a[0] * a[0], a[0] * a[1], a[0] * a[2], a[1] * a[1], a[1] * a[2], a[2] * a[2]};
+    const double F[6] = {c[0] * c[0], c[0] * c[1], c[0] * c[2], c[1] * c[1], c[1] * c[2], c[2] * c[2]};
+    const double A0 = sub == 0 ? A[0] : sub == 1 ? A[1] : sub == 2 ? A[2] : A[3];
+    const double A1 = sub == 0 ? A[4] : A[5];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      acc0[q] = fma(A0, F[q], acc0[q]);
+      acc1[q] = fma(A1, F[q], acc1[q]);
+    }
+  }
+  double *mom = args.sp_mom + vb * kEsMom;
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    mom[6 * sub + q] = acc0[q];
+    if (sub < 2) mom[6 * (sub + 4) + q] = acc1[q];
+  }
+  if (sub == 0) {
+    // opengv::math::rot2cayley of the start rotation, then computeModelCoefficients: "randomize the starting point a bit"
+    double x[3] = {pose[0] / pose[3], pose[1] / pose[3], pose[2] / pose[3]};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const double u = static_cast<double>(rs_u31(args.seed, pair, h, ns + d)) / 2147483647.0;
+      x[d] += (u - 0.5) * 2.0 * args.max_variation;
+      args.sp_x[3 * vb + d] = x[d];
+    }
+    args.sp_i0[vb] = front[g];
+  }
+}
+
+// es_lm_kernel on the round's hypotheses: Cayley start in, Cayley result out (sp_x), moments at sp_mom.
+__global__ void __launch_bounds__(kEsLmThreads) ransac_lm_kernel(const __grid_constant__ RansacArgs args) {
+  __shared__ double s_mom[kEsMom * kEsLmPairs];
+  const int tid = threadIdx.x, sub = tid & 3, slot = tid >> 2;
+  const long long nvirt = args.bv.num_problems * 8;
+  const long long first = static_cast<long long>(blockIdx.x) * kEsLmPairs;
+  const long long vb = first + slot;
+  const bool active = vb < nvirt && args.sp_active[vb] != 0;
+  if (!__syncthreads_or(active)) return;
+  {
+    const long long cnt = min(static_cast<long long>(kEsLmPairs), nvirt - first);
+    for (long long i = tid; i < cnt * kEsMom; i += kEsLmThreads) {
+      const int p = static_cast<int>(i / kEsMom), k = static_cast<int>(i % kEsMom);
+      s_mom[k * kEsLmPairs + p] = args.sp_mom[first * kEsMom + i];
+    }
+    __syncthreads();
+  }
+  const long long vv = active ? vb : first;
+  double x[3] = {args.sp_x[3 * vv], args.sp_x[3 * vv + 1], args.sp_x[3 * vv + 2]};
+  int info = 0, nfev = 0;
+  es_lm_group(s_mom + (active ? slot : 0), kEsLmPairs, args.lm, active, sub, x, info, nfev);
+  if (active && sub == 0) {
+    args.sp_x[3 * vb] = x[0];
+    args.sp_x[3 * vb + 1] = x[1];
+    args.sp_x[3 * vb + 2] = x[2];
+  }
+}
+
+__global__ void __launch_bounds__(32, 16) ransac_post_kernel(const __grid_constant__ RansacArgs args) {
+  constexpr int NG = 8;
+  __shared__ double s_model[NG * 16];
+  __shared__ double s_best[16];
+  __shared__ int s_count[NG];
+  __shared__ int s_wcnt[1];
+  __shared__ int s_flag, s_iters;
+  const int lane = threadIdx.x, g = lane >> 2, sub = lane & 3;
+  const long long b = blockIdx.x;
+  if (!args.sp_live[b]) return;
+  long long s, e;
+  problem_range(args.bv, b, s, e);
+  const int n = static_cast<int>(e - s);
+  const int ns = args.sample_size;
+  const double *f1 = args.bv.f1 + 3 * s, *f2 = args.bv.f2 + 3 * s;
+  const long long vb = b * NG + g;
+  const int base = args.sp_round * NG;
+  if (args.sp_active[vb]) {
+    // eigensolver_main's tail (as in ransac_hypothesis): rotation = cayley2rot(x), translation along the eigenvector
+    // of the smallest eigenvalue of M(x), towards the optical flow of the sample's first correspondence
+    const double x[3] = {args.sp_x[3 * vb], args.sp_x[3 * vb + 1], args.sp_x[3 * vb + 2]};
+    double M[6], t[3], lam, q[4], R[9];
+    es_compose_m(args.sp_mom + vb * kEsMom, 1, x, M);
+    sym3_smallest_eigvec(M, t, lam);
+    const double sc = 1.0 / sqrt(1.0 + x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+    q[0] = x[0] * sc; q[1] = x[1] * sc; q[2] = x[2] * sc; q[3] = sc;
+    quat_rotation(q, R);
+    const int i0 = args.sp_i0[vb];
+    const double a[3] = {f1[3 * i0], f1[3 * i0 + 1], f1[3 * i0 + 2]};
+    const double c[3] = {f2[3 * i0], f2[3 * i0 + 1], f2[3 * i0 + 2]};
+    double gg[3];
+    rot(R, c, gg);
+    const double flow = (a[0] - gg[0]) * t[0] + (a[1] - gg[1]) * t[1] + (a[2] - gg[2]) * t[2];
+    if (flow < 0.0) { t[0] = -t[0]; t[1] = -t[1]; t[2] = -t[2]; }
+    if (sub == 0) {
+      double *m = s_model + 16 * g;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) m[k] = R[k];
+      m[9] = t[0]; m[10] = t[1]; m[11] = t[2];
+      m[12] = q[0]; m[13] = q[1]; m[14] = q[2]; m[15] = q[3];
+    }
+  }
+  __syncthreads();
+  const int round = NG;
+  ransac_count<1, NG>(f1, f2, n, s_model, min(round, args.max_iterations - base + 1), args.threshold, s_count, 0);
+  __syncthreads();
+  RansacPairState &st = args.state[b];
+  if (lane == 0) {
+    // computeModel's bookkeeping, in order (as in ransac_kernel)
+    int best = st.best_count, iters = st.iters, done = 0;
+    double k = st.k;
+    for (int j = 0; j < round; ++j) {
+      if (!(static_cast<double>(iters) < k)) { done = 1; break; }
+      const int count = s_count[j];
+      if (count > best) {
+        best = count;
+        st.best_h = base + j;
+#pragma unroll
+        for (int m = 0; m < 16; ++m) st.best[m] = s_model[16 * j + m];
+        k = ransac_k(count, n, ns, args.probability);
+      }
+      ++iters;
+      if (iters > args.max_iterations) { done = 1; break; }
+    }
+    if (!done && !(static_cast<double>(iters) < k)) done = 1;
+    st.best_count = best;
+    st.iters = iters;
+    st.k = k;
+    s_iters = iters;
+    int flag = 0;
+    if (done) {
+      flag = 1;
+    } else if (args.defer_after > 0 && iters >= args.defer_after) {
+      // unfinished: the rest of this pair's hypotheses are spread over the device by pass 2
+      st.done = 0;
+      st.best_in_state = 1;
+      args.defer[4 + atomicAdd(args.defer, 1)] = static_cast<int>(b);
+      flag = 2;
+    }
+    if (flag) args.sp_live[b] = 0;
+    s_flag = flag;
+  }
+  __syncthreads();
+  if (s_flag == 1) {
+    if (lane < 16) s_best[lane] = st.best[lane];
+    __syncthreads();
+    ransac_select<1>(args, b, s, n, f1, f2, s_best, s_iters, s_wcnt);
+  }
 }
 
 // ------------------------------------------------------------------ pass 2

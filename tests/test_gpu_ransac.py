@@ -269,3 +269,36 @@ def test_frame_solve_matches_committed_ransac_fixture(handle):
         assert rotation_angle(res.poses[k], g["poses"][k]) <= ROT_TOL
         assert direction_angle(res.poses[k][4:], g["poses"][k][4:]) <= DIR_TOL
     assert checked >= 0.75 * B, checked
+
+
+def test_pass1_as_three_kernels_per_round_gives_the_bits_of_the_one_kernel_form():
+    """Large batches run every round of pass 1 as sampling / LM / scoring kernels (the fused kernel is bound by
+    instruction fetch); same device functions in the same order: iterations, inlier sets and models bit for bit,
+    with outliers (pairs that go on to pass 2), an iteration cap below the hand-over, and pairs too small to sample."""
+    import os
+
+    def handle_with(**env):
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update({k: str(v) for k, v in env.items()})
+        try:
+            return api.Handle(0)
+        finally:
+            for k, v in old.items():
+                os.environ.pop(k) if v is None else os.environ.__setitem__(k, v)
+
+    one = handle_with(PNEC_B200_RANSAC_SPLIT=0, PNEC_B200_RANSAC_WARPS=1)
+    split = handle_with(PNEC_B200_RANSAC_SPLIT=1, PNEC_B200_RANSAC_WARPS=1)
+    for B, N, frac, kw in ((700, 160, 0.25, {}), (300, 64, 0.3, dict(max_ransac_iterations=20)), (40, 9, 0.0, {})):
+        b = syn.make_batch(B, N, seed=71 + B, noise_level=0.5)
+        rng = np.random.default_rng(B)
+        bad = rng.random(B * N) < frac
+        v = rng.standard_normal((int(bad.sum()), 3))
+        b.bvs_target[bad] = v / np.linalg.norm(v, axis=1, keepdims=True)
+        o = api.default_frame_opts(**kw)
+        r0 = one.ransac_batch(b.bvs_host, b.bvs_target, b.init_poses, o, n_per_problem=N)
+        r1 = split.ransac_batch(b.bvs_host, b.bvs_target, b.init_poses, o, n_per_problem=N)
+        for x0, x1 in zip(r0[:3], r1[:3]):
+            np.testing.assert_array_equal(np.asarray(x0), np.asarray(x1))
+        n_in = np.asarray(r0[1])
+        for k in range(B):
+            np.testing.assert_array_equal(np.asarray(r0[3])[k * N:k * N + n_in[k]], np.asarray(r1[3])[k * N:k * N + n_in[k]])
