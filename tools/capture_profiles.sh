@@ -20,11 +20,17 @@ run_cap() {  # name regex skip script [env assignments...]
   ncu -i /tmp/prof_$name.ncu-rep --page raw --csv > $OUT/${name}_${TAG}_ncu_raw.csv 2>/dev/null
   python tools/ncu_src_summary.py /tmp/prof_$name.ncu-rep 25 > $OUT/${name}_${TAG}_source_summary.txt 2>&1
 }
+if [ -z "$CAPTURE_RANSAC_ONLY" ]; then
 run_cap k1_eval_warp eval_warp_kernel 2 tools/profile_run.py PROF_MODE=eval
 run_cap solve_slots_kernel solve_slots_kernel 2 tools/profile_run.py PROF_MODE=solve
 run_cap solve_kernel 'solve_kernel' 2 tools/profile_run.py PROF_MODE=solve PNEC_B200_SOLVE_SLOTS=0
 run_cap es_lm_kernel es_lm_kernel 1 tools/profile_frame.py
 run_cap scf_kernel 'scf_kernel' 1 tools/profile_frame.py
-run_cap ransac_kernel 'ransac_kernel' 0 tools/ransac_once.py
+fi
+if [ -z "$CAPTURE_RANSAC_ONLY" ]; then
+run_cap ransac_kernel 'ransac_kernel' 0 tools/ransac_once.py PNEC_B200_RANSAC_SPLIT=0
 run_cap ransac_hyp_kernel 'ransac_hyp_kernel' 1 tools/ransac_once.py
+fi
+run_cap ransac_lm_kernel 'ransac_lm_kernel' 0 tools/ransac_once.py OUTLIERS=0
+run_cap ransac_post_kernel 'ransac_post_kernel' 0 tools/ransac_once.py OUTLIERS=0
 ls -la $OUT | tail -30
