@@ -1163,14 +1163,16 @@ int run_ransac(pnec_handle *h, const BatchView &bv, const pnec_frame_opts &o, lo
     for (int it = defer_after; it <= o.max_ransac_iterations; ++rounds) it += ransac_grant(it, o.max_ransac_iterations);
     const unsigned pgrid = static_cast<unsigned>(std::min<long long>(  // 4 CTAs of 4 independent warps per SM
         4LL * h->sm_count, (bv.num_problems * (kRansacSuper / kRansacBlock) + 3) / 4));
-    ransac_plan_kernel<<<1, 1024, 0, stream>>>(a, 0);
+    const unsigned rgrid = static_cast<unsigned>((bv.num_problems + 3) / 4);  // a warp per pair that may have been deferred
+    ransac_plan_kernel<<<1, 1024, 0, stream>>>(a);
     for (int r = 0; r < rounds; ++r) {
       ransac_hyp_kernel<4, 4><<<pgrid, 128, 0, stream>>>(a);
-      ransac_plan_kernel<<<1, 1024, 0, stream>>>(a, 1);
+      ransac_replay_kernel<<<rgrid, 128, 0, stream>>>(a);
+      ransac_plan_kernel<<<1, 1024, 0, stream>>>(a);
     }
     ransac_final_kernel<<<static_cast<unsigned>(std::min<long long>(2LL * h->sm_count, bv.num_problems)), 128, 0, stream>>>(a);
     PNEC_CUDA(cudaGetLastError());
-    h->launches += 2 + 2 * rounds;
+    h->launches += 2 + 3 * rounds;
   }
   return PNEC_OK;
 }
