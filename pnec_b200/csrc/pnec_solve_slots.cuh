@@ -6,15 +6,15 @@
 // shared memory (not warps) caps the pairs resident per SM.  Here a CTA owns P pair SLOTS in shared
 // memory, one OWNER warp per slot and one group of evaluation warps for all of them:
 //
-//   owner warp of slot s   claims a pair (atomic work counter), bulk-copies it into the slot, repacks the
-//                          3x3 covariances to their symmetric part IN PLACE (96 instead of 120 B per
-//                          correspondence: four slots per SM at N = 512 instead of three), then loops
-//                          { post the candidate's pose constants -> wait for the 4 partial sums -> LM update }
-//                          and writes the result;
-//   evaluation warps       poll the slots, evaluate their quarter of whichever slot has a candidate posted
-//                          (residual + Jacobian row + J^T J / J^T r, or cost only) and hand the partial sums
-//                          to the owner.  They never wait for an LM update: while slot A is in its update
-//                          they evaluate slot B.
+//   owner warp of slot s   claims a pair (atomic work counter, one pair ahead), bulk-copies it into the slot,
+//                          repacks the 3x3 covariances to their symmetric part IN PLACE (96 instead of 120 B
+//                          per correspondence: four slots per SM at N = 512 instead of three), then loops
+//                          { wait for the 4 partial sums -> LM update, which posts the next candidate's pose
+//                          constants as soon as they are stored } and writes the result;
+//   evaluation warps       take the posted candidates in order, evaluate their quarter of the slot (residual +
+//                          Jacobian row + J^T J / J^T r, or cost only) and hand the partial sums to the owner.
+//                          They never wait for an LM update: while slot A is in its update they evaluate
+//                          slot B.
 //
 // Hand-over is by mbarriers, no __syncthreads after start-up and no polling: an owner posts a candidate
 // as a ticket in a small ring (one mbarrier per ring entry, tickets numbered by an atomic counter in
@@ -28,7 +28,6 @@
 
 namespace pnec {
 
-constexpr int kSlotExit = 2;       // SlotCtl::mode besides kPassFull / kPassCost: no more pairs for this slot
 constexpr int kSlotEvalWarps = 4;  // evaluation warps per CTA (== the cross-warp split of solve_kernel<V, 4, .>)
 constexpr int kSlotTickets = 8;    // ring entries; a slot has at most one ticket outstanding, so P <= 8 never laps a reader
 
@@ -78,20 +77,6 @@ struct SlotCtl {
   double part[kSlotEvalWarps][kAccPad];
   int head, span, mode, pad;
 };
-
-__device__ __forceinline__ bool mbar_test_wait(uint64_t *bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
 
 // L2 prefetch of a byte range (the next pair of a slot, while the current one is being solved)
 __device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
