@@ -42,6 +42,12 @@ def run(name, b, **kw):
                final_over_1e6_well_posed=int(((gr > 1e-6) | (gt > 1e-6))[ok].sum()),
                final_max_rot_all=float(gr.max()), final_median_rot_all=float(np.median(gr)),
                oracle_self_max_rot=float(sr.max()), oracle_self_max_dir=float(st.max()))
+    # the pair on which the GPU differs most from the oracle, next to the oracle's own instability on it
+    w = int(np.argmax(gr))
+    row["worst_pair"] = dict(index=w, gpu_vs_oracle_rot=float(gr[w]), gpu_vs_oracle_dir=float(gt[w]),
+                             oracle_self_rot=float(sr[w]), oracle_self_dir=float(st[w]),
+                             es_gpu_vs_oracle_rot=float(ger[w]), es_gpu_vs_oracle_dir=float(get[w]),
+                             es_oracle_self_rot=float(er[w]), es_oracle_self_dir=float(et[w]))
     print(json.dumps(row), flush=True)
 
 run("C2 shape 2000x512 omni aniso", syn.make_batch(2000, 512, seed=2025), n_per_problem=512)
