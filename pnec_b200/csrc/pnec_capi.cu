@@ -1146,7 +1146,7 @@ int run_ransac(pnec_handle *h, const BatchView &bv, const pnec_frame_opts &o, lo
   } else {
     if (nw == 1) ransac_kernel<1, 16><<<grid, 32, 0, stream>>>(a);
     else if (nw == 2) ransac_kernel<2, 8><<<grid, 64, 0, stream>>>(a);
-    else ransac_kernel<4, 4><<<grid, 128, 0, stream>>>(a);
+    else ransac_kernel<4, 2><<<grid, 128, 0, stream>>>(a);  // few pairs: all the registers, no spills in the LM
     PNEC_CUDA(cudaGetLastError());
     h->launches++;
   }

@@ -567,9 +567,11 @@ constexpr int kEsLmThreads = 128;
 constexpr int kEsLmPairs = kEsLmThreads / 4;  // four lanes per frame pair
 
 // The Levenberg-Marquardt run of one 4-lane group (opengv's eigensolver_main on the 36 moments at
-// `mom`, consecutive moments `stride` doubles apart).  Must be called by all 32 lanes of a warp;
-// groups without work pass active = false.  The four lanes share the function evaluation (see
-// es_smallest_ev) and run the scalar logic redundantly, so a group never diverges.
+// `mom`, consecutive moments `stride` doubles apart).  Must be called by all 32 lanes of a warp with
+// group = lane / 4, sub = lane % 4; groups without work pass active = false.  The moments of group g'
+// must be readable at mom + (g' - g) * gpitch by every lane of the warp (see the wide turns below).
+// The four lanes share the function evaluation (see es_smallest_ev) and run the scalar logic
+// redundantly, so a group never diverges.
 //
 // The eight groups of a warp move through lmdif's phases TOGETHER (the phase is warp-uniform):
 // f(x0); then per outer iteration the three forward-difference columns, the QR factorisation /
@@ -579,15 +581,33 @@ constexpr int kEsLmPairs = kEsLmThreads / 4;  // four lanes per frame pair
 // groups nearly every turn paid for the factorisation, the step computation and the step
 // assessment, each for a fraction of the lanes), and there is a single call site of the evaluation.
 // Each group performs exactly lmdif's sequence of operations; only the interleaving differs.
+//
+// WIDE TURNS.  A warp's duration is its slowest group's, and a kernel's is that of the few pairs that
+// run into maxfev: most of the time one or two groups of a warp are still at work and 24+ lanes idle.
+// As soon as at most two groups are left, every turn evaluates FOUR points per group at once: the
+// group's own lanes take its base point (the pending trial point, or x when a Jacobian is due) and
+// three finished groups take base + h_k e_k, k = 0..2 -- the forward-difference columns lmdif would
+// ask for next if the trial point is accepted.  It nearly always is, so an outer iteration costs one
+// evaluation turn instead of four; a rejected trial point discards the three columns.  The values
+// are the ones the narrow turns would compute (same points, same arithmetic, nfev counted as lmdif
+// counts it): results are bit-identical, only the latency of the tail changes.  A warp with a single
+// pair (frame_rounds_kernel, one pair per call) runs wide from the first turn.
 struct EsLmParams {
   double ftol, xtol, gtol, factor;
   int maxfev;
 };
 
-__device__ __forceinline__ void es_lm_group(const double *mom, int stride, const EsLmParams &args, bool active,
-                                            int sub, double x[3], int &info_out, int &nfev_out) {
+//
+// WIDE = false compiles the wide turns out: the RANSAC kernels are bound by instruction fetch, their
+// eight hypotheses per warp finish within a few turns of each other, and the extra code costs them
+// more than the shorter tail returns (measured: stage on C2 15.2 -> 16.8 ms with wide turns).
+template <bool WIDE>
+__device__ __forceinline__ void es_lm_group(const double *mom, int stride, int gpitch, const EsLmParams &args,
+                                            bool active, int sub, double x[3], int &info_out, int &nfev_out) {
+  const unsigned kFull = 0xffffffffu;
   const double epsmch = DBL_EPSILON;
   const double eps = es_sqrt(epsmch);  // epsfcn = 0
+  const int lane = static_cast<int>(threadIdx.x) & 31, grp = lane >> 2;
   double fvec[3] = {0, 0, 0}, r[3][3], diag[3] = {1, 1, 1}, dp[3] = {1, 1, 1}, qtf[3] = {0, 0, 0}, wa1[3] = {0, 0, 0};
   double wa2[3] = {x[0], x[1], x[2]}, acn[3] = {0, 0, 0};
   int ipvt[3] = {0, 1, 2};
@@ -600,37 +620,84 @@ __device__ __forceinline__ void es_lm_group(const double *mom, int stride, const
   for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int j = 0; j < 3; ++j) r[i][j] = 0.0;
-  if (__all_sync(0xffffffffu, done)) {
+  if (__all_sync(kFull, done)) {
     info_out = 0;
     nfev_out = 0;
     return;
   }
 
   for (;;) {
+    // ---- wide or narrow turn (warp-uniform; the set of unfinished groups only changes after phases 3 and 4)
+    const unsigned act_lanes = __ballot_sync(kFull, !done);
+    const bool wide = WIDE && __popc(act_lanes) <= 8 && (phase == 0 || phase == 1 || phase == 4);
+    const bool was_trying = trying;
+    // roles of a wide turn: an unfinished group evaluates its own base point (col = -1); the finished
+    // groups, in lane order, serve the unfinished ones three by three (col = 0..2)
+    int col = -1, serve = grp;
+    int src_lane[3] = {lane, lane, lane};  // an unfinished group's helpers (first lane of each)
+    if (wide) {
+      const unsigned a0 = __ffs(act_lanes) - 1;                        // first lane of the first unfinished group
+      const unsigned rest = act_lanes & ~(0xfu << a0);
+      const int a1 = rest ? __ffs(rest) - 1 : -1;                      // ... of the second, if any
+      const unsigned idle = ~act_lanes;
+      if (done) {
+        const int rank = __popc(idle & ((1u << (lane & ~3)) - 1u)) >> 2;  // finished groups below this one
+        const int tgt = rank / 3;
+        col = rank - 3 * tgt;
+        serve = tgt == 0 ? static_cast<int>(a0 >> 2) : (tgt == 1 && a1 >= 0 ? a1 >> 2 : -1);
+        if (serve < 0) { serve = grp; col = -1; }  // nothing to do this turn
+      } else {
+        const int first = (a1 >= 0 && lane >= a1) ? 3 : 0;  // rank of this group's first helper
+#pragma unroll
+        for (int k = 0; k < 3; ++k) src_lane[k] = static_cast<int>(__fns(idle, 0, 4 * (first + k) + 1));
+      }
+    }
     // ---- the point to evaluate
     double xe[3] = {x[0], x[1], x[2]};
-    if (phase >= 1 && phase <= 3) {
+    if (trying) { xe[0] = wa2[0]; xe[1] = wa2[1]; xe[2] = wa2[2]; }
+    const double *mom_e = mom;
+    if (wide) {
+      const int src = 4 * serve;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) xe[j] = __shfl_sync(kFull, xe[j], src);
+      mom_e = mom + (serve - grp) * gpitch;
+      if (col >= 0) {
+        const double xj = pick3(xe, col);
+        double hh = eps * fabs(xj);
+        if (hh == 0.0) hh = eps;
+        put3(xe, col, xj + hh);
+      }
+    } else if (phase >= 1 && phase <= 3) {
       const double xj = pick3(x, phase - 1);
       h = eps * fabs(xj);
       if (h == 0.0) h = eps;
       put3(xe, phase - 1, xj + h);
-    } else if (phase == 4 && trying) {
-      xe[0] = wa2[0]; xe[1] = wa2[1]; xe[2] = wa2[2];
     }
     double fe[3];
-    es_smallest_ev(mom, stride, xe, sub, fe);
+    es_smallest_ev(mom_e, stride, xe, sub, fe);
+    // a wide turn's columns: f(base + h_k e_k) from the helpers
+    double fd[3][3];
+    if (wide) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) fd[k][i] = __shfl_sync(kFull, fe[i], src_lane[k]);
+    }
 
     bool need_step = false;
+    bool new_jac = false;  // r holds fresh forward differences at x
     if (phase == 0) {
       if (!done) {
         fvec[0] = fe[0]; fvec[1] = fe[1]; fvec[2] = fe[2];
         fnorm = enorm3(fvec);
         nfev = 1;
       }
-      phase = 1;
-      continue;
+      if (!wide) {
+        phase = 1;
+        continue;
+      }
     }
-    if (phase <= 3) {
+    if (!wide && phase <= 3) {
       if (!done) {
         const int j = phase - 1;
         const double inv_h = fast_rcp(h);
@@ -644,59 +711,9 @@ __device__ __forceinline__ void es_lm_group(const double *mom, int stride, const
         phase += 1;
         continue;
       }
-      if (!done) {
-        nfev += 4;  // Eigen's NumericalDiff (Forward) evaluates f(x) again: n + 1 calls per Jacobian
-        double rdiag[3];
-        es_qrfac(r, ipvt, rdiag, acn);
-        if (iter == 1) {
-#pragma unroll
-          for (int j2 = 0; j2 < 3; ++j2) diag[j2] = (acn[j2] == 0.0) ? 1.0 : acn[j2];
-          const double dx[3] = {diag[0] * x[0], diag[1] * x[1], diag[2] * x[2]};
-          xnorm = enorm3(dx);
-          delta = args.factor * xnorm;
-          if (delta == 0.0) delta = args.factor;
-        }
-        // qtf = first n components of Q^T fvec; store R's diagonal
-        double w4[3] = {fvec[0], fvec[1], fvec[2]};
-#pragma unroll
-        for (int j2 = 0; j2 < 3; ++j2) {
-          if (r[j2][j2] != 0.0) {
-            double sum = 0.0;
-#pragma unroll
-            for (int i = j2; i < 3; ++i) sum += r[i][j2] * w4[i];
-            const double temp = -es_div(sum, r[j2][j2]);
-#pragma unroll
-            for (int i = j2; i < 3; ++i) w4[i] += r[i][j2] * temp;
-          }
-          r[j2][j2] = rdiag[j2];
-          qtf[j2] = w4[j2];
-        }
-        gnorm = 0.0;
-        if (fnorm != 0.0) {
-          const double inv_fnorm = fast_rcp(fnorm);
-#pragma unroll
-          for (int j2 = 0; j2 < 3; ++j2) {
-            const double cn = pick3(acn, ipvt[j2]);
-            if (cn != 0.0) {
-              double sum = 0.0;
-#pragma unroll
-              for (int i = 0; i <= j2; ++i) sum += r[i][j2] * (qtf[i] * inv_fnorm);
-              gnorm = fmax(gnorm, fabs(es_div(sum, cn)));
-            }
-          }
-        }
-        if (gnorm <= args.gtol) {
-          info = 4;
-          done = true;
-        } else {
-#pragma unroll
-          for (int j2 = 0; j2 < 3; ++j2) diag[j2] = fmax(diag[j2], acn[j2]);
-#pragma unroll
-          for (int j2 = 0; j2 < 3; ++j2) dp[j2] = pick3(diag, ipvt[j2]);
-          need_step = true;
-        }
-      }
-    } else if (trying) {
+      new_jac = !done;
+    }
+    if (phase == 4 && was_trying) {
       // ---- trial point evaluated: fe = f(x + p)
       ++nfev;
       const double fnorm1 = enorm3(fe);
@@ -750,6 +767,70 @@ __device__ __forceinline__ void es_lm_group(const double *mom, int stride, const
         need_step = true;  // inner loop of lmdif: same Jacobian, smaller region
       }
     }
+    if (wide && !done && !need_step) {
+      // the helpers' points were x + h_k e_k (x = the base point: just accepted, or unchanged)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        double hh = eps * fabs(x[k]);
+        if (hh == 0.0) hh = eps;
+        const double inv_h = fast_rcp(hh);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) r[i][k] = (fd[k][i] - fvec[i]) * inv_h;
+      }
+      new_jac = true;
+    }
+    if (new_jac) {
+      nfev += 4;  // Eigen's NumericalDiff (Forward) evaluates f(x) again: n + 1 calls per Jacobian
+      double rdiag[3];
+      es_qrfac(r, ipvt, rdiag, acn);
+      if (iter == 1) {
+#pragma unroll
+        for (int j2 = 0; j2 < 3; ++j2) diag[j2] = (acn[j2] == 0.0) ? 1.0 : acn[j2];
+        const double dx[3] = {diag[0] * x[0], diag[1] * x[1], diag[2] * x[2]};
+        xnorm = enorm3(dx);
+        delta = args.factor * xnorm;
+        if (delta == 0.0) delta = args.factor;
+      }
+      // qtf = first n components of Q^T fvec; store R's diagonal
+      double w4[3] = {fvec[0], fvec[1], fvec[2]};
+#pragma unroll
+      for (int j2 = 0; j2 < 3; ++j2) {
+        if (r[j2][j2] != 0.0) {
+          double sum = 0.0;
+#pragma unroll
+          for (int i = j2; i < 3; ++i) sum += r[i][j2] * w4[i];
+          const double temp = -es_div(sum, r[j2][j2]);
+#pragma unroll
+          for (int i = j2; i < 3; ++i) w4[i] += r[i][j2] * temp;
+        }
+        r[j2][j2] = rdiag[j2];
+        qtf[j2] = w4[j2];
+      }
+      gnorm = 0.0;
+      if (fnorm != 0.0) {
+        const double inv_fnorm = fast_rcp(fnorm);
+#pragma unroll
+        for (int j2 = 0; j2 < 3; ++j2) {
+          const double cn = pick3(acn, ipvt[j2]);
+          if (cn != 0.0) {
+            double sum = 0.0;
+#pragma unroll
+            for (int i = 0; i <= j2; ++i) sum += r[i][j2] * (qtf[i] * inv_fnorm);
+            gnorm = fmax(gnorm, fabs(es_div(sum, cn)));
+          }
+        }
+      }
+      if (gnorm <= args.gtol) {
+        info = 4;
+        done = true;
+      } else {
+#pragma unroll
+        for (int j2 = 0; j2 < 3; ++j2) diag[j2] = fmax(diag[j2], acn[j2]);
+#pragma unroll
+        for (int j2 = 0; j2 < 3; ++j2) dp[j2] = pick3(diag, ipvt[j2]);
+        need_step = true;
+      }
+    }
     if (need_step) {
       // wa1 <- step in pivoted order, wa2 <- x + p
       es_lmpar(r, dp, qtf, delta, par, wa1);
@@ -768,8 +849,8 @@ __device__ __forceinline__ void es_lm_group(const double *mom, int stride, const
     }
     // ---- next phase (warp-uniform): more trial points while any group has one pending, else a new
     // outer iteration for the groups that are not done, else out
-    if (__any_sync(0xffffffffu, trying)) phase = 4;
-    else if (__all_sync(0xffffffffu, done)) break;
+    if (__any_sync(kFull, trying)) phase = 4;
+    else if (__all_sync(kFull, done)) break;
     else phase = 1;
   }
   info_out = info;
@@ -789,20 +870,20 @@ __global__ void __launch_bounds__(kEsLmThreads) es_lm_kernel(const __grid_consta
   {
     const long long first = static_cast<long long>(blockIdx.x) * kEsLmPairs;
     const long long cnt = min(static_cast<long long>(kEsLmPairs), args.num_problems - first);
-    for (long long i = tid; i < cnt * kEsMom; i += kEsLmThreads) {
+    for (long long i = tid; i < kEsLmPairs * kEsMom; i += kEsLmThreads) {
       const int p = static_cast<int>(i / kEsMom), k = static_cast<int>(i % kEsMom);
-      s_mom[k * kEsLmPairs + p] = args.moments[first * kEsMom + i];
+      s_mom[k * kEsLmPairs + p] = i < cnt * kEsMom ? args.moments[first * kEsMom + i] : 0.0;
     }
     __syncthreads();
   }
-  const double *mom = s_mom + (active ? slot : 0);
+  const double *mom = s_mom + slot;  // every lane its own slot: es_lm_group's wide turns address the others from it
   const double *pin = args.poses_in + 7 * bb;
   // opengv::math::rot2cayley: [c]x = (R - I)(R + I)^-1, i.e. q_xyz / q_w
   double x[3] = {pin[0] / pin[3], pin[1] / pin[3], pin[2] / pin[3]};
 
   const EsLmParams params{args.ftol, args.xtol, args.gtol, args.factor, args.maxfev};
   int info = 0, nfev = 0;
-  es_lm_group(mom, kEsLmPairs, params, active, sub, x, info, nfev);
+  es_lm_group<true>(mom, kEsLmPairs, 1, params, active, sub, x, info, nfev);
   if (passthrough && sub == 0) {
     double *po = args.poses_out + 7 * b;
 #pragma unroll

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(NW * 32) frame_rounds_kernel(const __grid_cons
       } else {
         double x[3] = {prev[0] / prev[3], prev[1] / prev[3], prev[2] / prev[3]};  // rot2cayley
         int info, nfev;
-        es_lm_group(s_mom, 1, args.lm, lane < 4, lane & 3, x, info, nfev);
+        es_lm_group<true>(s_mom, 1, 0, args.lm, lane < 4, lane & 3, x, info, nfev);
         if (lane == 0) {
           const double sc = 1.0 / sqrt(1.0 + x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
           const double q[4] = {x[0] * sc, x[1] * sc, x[2] * sc, sc};

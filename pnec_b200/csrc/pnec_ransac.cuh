@@ -155,6 +155,10 @@ __device__ __forceinline__ double ransac_score(const double *m, const double f1[
 // every kernel, so that a hypothesis is the same bits wherever it is evaluated.  Shared-memory
 // scratch of the calling CTA: s_mom [36][NG], s_front / s_bpos / s_bval [kRansacMaxSample][NG];
 // the model goes to model16 = R (9), t (3), q (4) (written by lane 0 of the group).
+// WIDE: es_lm_group's wide turns (same bits either way) -- on where a warp is left with one or two
+// hypotheses and latency counts (one CTA per pair, the rebuild of the winner), off in the
+// device-filling pass 2, which is bound by instruction fetch.
+template <bool WIDE>
 __device__ __noinline__ void ransac_hypothesis(const double *f1, const double *f2, int n, int ns, double c0x, double c0y,
                                                double c0z, unsigned long long seed, unsigned long long pair, int h,
                                                double max_variation, const EsLmParams *lm, bool active, int g,
@@ -216,7 +220,7 @@ __device__ __noinline__ void ransac_hypothesis(const double *f1, const double *f
   __syncwarp();
   {
     int info, nfev;
-    es_lm_group(s_mom + g, NG, *lm, active, sub, x, info, nfev);
+    es_lm_group<WIDE>(s_mom + g, NG, 1, *lm, active, sub, x, info, nfev);
   }
   if (active) {
     // eigensolver_main's tail: rotation = cayley2rot(x), translation along the eigenvector of the
@@ -386,10 +390,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) ransac_kernel(const __grid_cons
 
   for (int base = 0;;) {
     const int round = s_state[3];
-    const int h = base + g;  // == opengv's iterations_ for this hypothesis
-    const bool active = g < round && h <= args.max_iterations;
-    ransac_hypothesis(f1, f2, n, ns, c0[0], c0[1], c0[2], args.seed, pair, h, args.max_variation, &args.lm, active, g,
-                      NG, s_mom, s_front, s_bpos, s_bval, s_model + 16 * g);
+    // hypothesis j of the round goes to warp j % NW: a short round leaves every warp with one or two
+    // hypotheses, which es_lm_group then runs with wide turns (the first round of 8 over 4 warps)
+    const int j = (g & 7) * NW + (g >> 3);
+    const int h = base + j;  // == opengv's iterations_ for this hypothesis
+    const bool active = j < round && h <= args.max_iterations;
+    ransac_hypothesis<true>(f1, f2, n, ns, c0[0], c0[1], c0[2], args.seed, pair, h, args.max_variation, &args.lm, active, g,
+                            NG, s_mom, s_front, s_bpos, s_bval, s_model + 16 * j);
     __syncthreads();
     ransac_count<NW, NG>(f1, f2, n, s_model, min(round, args.max_iterations - base + 1), args.threshold, s_count,
                          tid >> 5);
@@ -415,7 +422,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) ransac_kernel(const __grid_cons
       }
       if (!done && !(static_cast<double>(iters) < k)) done = 1;
       s_state[0] = best; s_state[1] = iters; s_state[2] = done;
-      s_state[3] = min(NG, 2 * round);
+      // the next round: what the stopping rule still asks for (k only falls from here, so more would be
+      // wasted, and a short round runs with wide turns), a full round while k is far away
+      const double rem = k - static_cast<double>(iters);
+      s_state[3] = !(rem < static_cast<double>(NG)) ? NG : max(1, static_cast<int>(ceil(rem)));
       s_k = k;
     }
     __syncthreads();
@@ -564,16 +574,16 @@ __global__ void __launch_bounds__(kEsLmThreads) ransac_lm_kernel(const __grid_co
   if (!__syncthreads_or(active)) return;
   {
     const long long cnt = min(static_cast<long long>(kEsLmPairs), nvirt - first);
-    for (long long i = tid; i < cnt * kEsMom; i += kEsLmThreads) {
+    for (long long i = tid; i < kEsLmPairs * kEsMom; i += kEsLmThreads) {
       const int p = static_cast<int>(i / kEsMom), k = static_cast<int>(i % kEsMom);
-      s_mom[k * kEsLmPairs + p] = args.sp_mom[first * kEsMom + i];
+      s_mom[k * kEsLmPairs + p] = i < cnt * kEsMom ? args.sp_mom[first * kEsMom + i] : 0.0;
     }
     __syncthreads();
   }
   const long long vv = active ? vb : first;
   double x[3] = {args.sp_x[3 * vv], args.sp_x[3 * vv + 1], args.sp_x[3 * vv + 2]};
   int info = 0, nfev = 0;
-  es_lm_group(s_mom + (active ? slot : 0), kEsLmPairs, args.lm, active, sub, x, info, nfev);
+  es_lm_group<false>(s_mom + slot, kEsLmPairs, 1, args.lm, active, sub, x, info, nfev);
   if (active && sub == 0) {
     args.sp_x[3 * vb] = x[0];
     args.sp_x[3 * vb + 1] = x[1];
@@ -838,7 +848,7 @@ __global__ void __launch_bounds__(WPC * 32, MINB) ransac_hyp_kernel(const __grid
     const int first = args.state[b].iters + blk * kRansacBlock;
     const int h = first + g;
     const bool active = h <= args.max_iterations;
-    ransac_hypothesis(f1, f2, n, args.sample_size, pose[0] / pose[3], pose[1] / pose[3], pose[2] / pose[3], args.seed,
+    ransac_hypothesis<false>(f1, f2, n, args.sample_size, pose[0] / pose[3], pose[1] / pose[3], pose[2] / pose[3], args.seed,
                       static_cast<unsigned long long>(args.pair_index_base + b), h, args.max_variation, &args.lm, active,
                       g, NG, s_mom[warp], s_front[warp], s_bpos[warp], s_bval[warp], s_model[warp] + 16 * g);
     __syncwarp();
@@ -879,7 +889,7 @@ __global__ void __launch_bounds__(128) ransac_final_kernel(const __grid_constant
     if (st.best_in_state) {
       if (tid < 16) s_best[tid] = st.best[tid];
     } else if (tid < 32) {  // warp 0, group 0 recomputes hypothesis best_h
-      ransac_hypothesis(f1, f2, n, args.sample_size, pose[0] / pose[3], pose[1] / pose[3], pose[2] / pose[3], args.seed,
+      ransac_hypothesis<true>(f1, f2, n, args.sample_size, pose[0] / pose[3], pose[1] / pose[3], pose[2] / pose[3], args.seed,
                         static_cast<unsigned long long>(args.pair_index_base + b), st.best_h, args.max_variation,
                         &args.lm, g == 0, g, NG, s_mom, s_front, s_bpos, s_bval, s_best);
     }

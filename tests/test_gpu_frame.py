@@ -304,3 +304,22 @@ def test_fused_rounds_kernel_matches_per_round_kernels(handle, monkeypatch):
         rounds = api.Handle(0).frame_solve_batch(*args, api.default_frame_opts(use_ransac=0, **kw), offsets=batch.offsets)
         np.testing.assert_allclose(fused.poses, rounds.poses, rtol=0, atol=1e-13)  # (rotation LM: two instantiations)
         np.testing.assert_array_equal(fused.es_poses, rounds.es_poses)
+
+
+def test_rotation_lm_wide_turns_are_bit_identical(handle):
+    """es_lm_group evaluates a trial point and its three forward-difference columns in ONE turn as soon
+    as at most two of a warp's eight pairs are unfinished (wide turns, pnec_eigensolver.cuh).  The
+    arithmetic per pair is lmdif's either way: a pair solved alone in its call (wide from the first
+    turn), next to one other pair, and inside a batch of 96 (narrow turns until the warp's tail) must
+    give the same bits -- rotation, MINPACK info code and smallest eigenvalue."""
+    n = 160
+    batch = syn.make_batch(96, n, seed=77, noise_level=1.0)
+    full, info, ev = handle.eigensolver_batch(batch.bvs_host, batch.bvs_target, batch.init_poses, n_per_problem=n)
+    assert len(set(info.tolist())) >= 1
+    for group in ([0], [5], [37, 38], [90, 3], list(range(8, 11))):
+        rows = np.concatenate([np.arange(b * n, (b + 1) * n) for b in group])
+        p, i, e = handle.eigensolver_batch(batch.bvs_host[rows], batch.bvs_target[rows], batch.init_poses[group],
+                                           n_per_problem=n)
+        np.testing.assert_array_equal(p, full[group])
+        np.testing.assert_array_equal(i, info[group])
+        np.testing.assert_array_equal(e, ev[group])
