@@ -92,6 +92,7 @@ struct Config {
   int no_lm_ahead = 0;
   int no_stager = 0;
   int ransac_warps = 0;
+  int es_wide_max_pairs = -1;  // rotation LM: two pairs per warp up to this many pairs (-1: by SM count)
   int ransac_defer = -1;  // PNEC_B200_RANSAC_DEFER: iterations after which pass 1 hands a pair to pass 2 (0: never)
   int ransac_split = 1;   // PNEC_B200_RANSAC_SPLIT: pass 1 of large batches as three kernels per round (0: one kernel)
   int scf_debug = 0;
@@ -103,6 +104,7 @@ struct Config {
   int copy_threads = 0;  // PNEC_B200_COPY_THREADS: worker threads of the pageable-input stager (0 = auto)
   void load() {
     dump_timing = env_int("PNEC_B200_DUMP_TIMING", 0);
+    es_wide_max_pairs = env_int("PNEC_B200_ES_WIDE_MAX_PAIRS", -1);
     frame_chunks = env_int("PNEC_B200_FRAME_CHUNKS", 0);
     fused_rounds_max_pairs = env_int("PNEC_B200_FUSED_ROUNDS_MAX_PAIRS", 512);
     h2d_chunks = env_int("PNEC_B200_H2D_CHUNKS", 0);
@@ -1049,8 +1051,15 @@ int run_es_lm(pnec_handle *h, long long B, const double *d_mom, const double *d_
   a.gtol = 0.0;
   a.factor = 100.0;
   a.maxfev = 100;
-  const unsigned grid = static_cast<unsigned>((B + kEsLmPairs - 1) / kEsLmPairs);
-  es_lm_kernel<<<grid, kEsLmThreads, 0, stream>>>(a);
+  // Two pairs per warp (every turn a wide one, es_lm_group) while that fits the machine in one wave
+  // (196 registers: two CTAs of 8 pairs per SM); eight per warp beyond.  Measured on the C2 shape:
+  // 1000 pairs 0.257 -> 0.235 ms, 2500 pairs 0.267 -> 0.251 ms, 5000 pairs 0.293 -> 0.317 ms.
+  const long long wide_max = h->cfg.es_wide_max_pairs >= 0 ? h->cfg.es_wide_max_pairs : 16LL * h->sm_count;
+  if (B <= wide_max) {
+    es_lm_kernel<2><<<static_cast<unsigned>((B + 7) / 8), kEsLmThreads, 0, stream>>>(a);
+  } else {
+    es_lm_kernel<8><<<static_cast<unsigned>((B + kEsLmPairs - 1) / kEsLmPairs), kEsLmThreads, 0, stream>>>(a);
+  }
   PNEC_CUDA(cudaGetLastError());
   h->launches++;
   return PNEC_OK;

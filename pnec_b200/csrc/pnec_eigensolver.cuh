@@ -857,22 +857,36 @@ __device__ __forceinline__ void es_lm_group(const double *mom, int stride, int g
   nfev_out = nfev;
 }
 
-// Four lanes per frame pair (es_lm_group), 32 pairs per CTA, moments staged in shared memory.
+// Four lanes per frame pair (es_lm_group), moments staged in shared memory.  GPW = pairs per warp:
+// 8 fills every 4-lane group (32 pairs per CTA; es_lm_group goes wide for the warp's tail), 2 leaves
+// six groups of each warp free from the start, so that EVERY turn is a wide one (8 pairs per CTA):
+// per pair more instructions but a quarter of the dependent turns -- for batches that do not fill
+// the machine with narrow turns (the launcher decides, run_es_lm).
+template <int GPW>
 __global__ void __launch_bounds__(kEsLmThreads) es_lm_kernel(const __grid_constant__ EsLmArgs args) {
-  __shared__ double s_mom[kEsMom * kEsLmPairs];
-  const int tid = threadIdx.x, sub = tid & 3, slot = tid >> 2;
-  const long long b = static_cast<long long>(blockIdx.x) * kEsLmPairs + slot;
-  const bool in_range = b < args.num_problems;
+  constexpr int kPairs = (kEsLmThreads / 32) * GPW;  // pairs per CTA
+  __shared__ double s_mom[kEsMom * kEsLmPairs];      // [k][slot], slot = 4-lane group of the CTA
+  const int tid = threadIdx.x, sub = tid & 3, slot = tid >> 2, warp = tid >> 5, grp = slot & 7;
+  const long long first = static_cast<long long>(blockIdx.x) * kPairs;
+  const long long b = first + warp * GPW + grp;
+  const bool in_range = grp < GPW && b < args.num_problems;
   const long long bb = in_range ? b : args.num_problems - 1;
   const bool passthrough = in_range && args.fixed && args.fixed[bb];
   const bool active = in_range && !passthrough;
-  // coalesced staging of this CTA's moments, transposed to [k][thread]
+  // coalesced staging of this CTA's moments, transposed to [k][slot]
   {
-    const long long first = static_cast<long long>(blockIdx.x) * kEsLmPairs;
-    const long long cnt = min(static_cast<long long>(kEsLmPairs), args.num_problems - first);
-    for (long long i = tid; i < kEsLmPairs * kEsMom; i += kEsLmThreads) {
+    const long long cnt = min(static_cast<long long>(kPairs), args.num_problems - first);
+    if (GPW < 8)
+      for (int i = tid; i < kEsLmPairs * kEsMom; i += kEsLmThreads) s_mom[i] = 0.0;
+    if (GPW < 8) __syncthreads();
+    for (long long i = tid; i < kPairs * kEsMom; i += kEsLmThreads) {
       const int p = static_cast<int>(i / kEsMom), k = static_cast<int>(i % kEsMom);
-      s_mom[k * kEsLmPairs + p] = i < cnt * kEsMom ? args.moments[first * kEsMom + i] : 0.0;
+      const int sl = (p / GPW) * 8 + (p % GPW);
+      if (GPW < 8) {
+        if (i < cnt * kEsMom) s_mom[k * kEsLmPairs + sl] = args.moments[first * kEsMom + i];
+      } else {
+        s_mom[k * kEsLmPairs + sl] = i < cnt * kEsMom ? args.moments[first * kEsMom + i] : 0.0;
+      }
     }
     __syncthreads();
   }
