@@ -991,7 +991,11 @@ int run_scf(pnec_handle *h, const BatchView &bv, long long max_n, double reg, in
 
 int run_nec_translation(pnec_handle *h, const BatchView &bv, double *out_t, int out_stride, double *out_M,
                         cudaStream_t stream) {
-  nec_translation_kernel<<<static_cast<unsigned>(bv.num_problems), 128, 0, stream>>>(bv, out_t, out_stride, out_M);
+  // large batches: a warp per pair (same bits, pnec_translation.cuh); few pairs: a CTA each for the latency
+  if (bv.num_problems >= 8LL * h->sm_count)
+    nec_translation_warp_kernel<<<static_cast<unsigned>((bv.num_problems + 3) / 4), 128, 0, stream>>>(bv, out_t, out_stride, out_M);
+  else
+    nec_translation_kernel<<<static_cast<unsigned>(bv.num_problems), 128, 0, stream>>>(bv, out_t, out_stride, out_M);
   PNEC_CUDA(cudaGetLastError());
   h->launches++;
   return PNEC_OK;

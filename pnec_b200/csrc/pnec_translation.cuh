@@ -729,4 +729,70 @@ __global__ void __launch_bounds__(128) nec_translation_kernel(BatchView bv, doub
   }
 }
 
+// The same for large batches: a warp per pair, four independent pairs per CTA.  With a CTA per pair
+// 127 threads wait while one solves the 3x3 eigenproblem, and the loads of a pair are one round trip
+// per stride (3.0 TB/s at 10 000 x 512).  Here a lane plays the four threads lane, lane + 32, lane + 64,
+// lane + 96 of the CTA-per-pair kernel -- four accumulator sets, 24 loads in flight -- and the sums are
+// combined exactly as block_sum6<4> combines them (butterfly per set, then sets 0..3 in order), so both
+// kernels give the same bits; no CTA-wide barrier, a warp's serial tail costs 31 lanes, not 127.
+__global__ void __launch_bounds__(128) nec_translation_warp_kernel(BatchView bv, double *out_t, int out_stride,
+                                                                    double *out_M) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long b = static_cast<long long>(blockIdx.x) * 4 + warp;
+  if (b >= bv.num_problems) return;
+  long long s, e;
+  problem_range(bv, b, s, e);
+  double R[9];
+  pose_rotation(bv.poses + 7 * b, R);
+  double M[4][6];
+#pragma unroll
+  for (int w = 0; w < 4; ++w)
+#pragma unroll
+    for (int k = 0; k < 6; ++k) M[w][k] = 0.0;
+  for (long long i0 = s + 1 + lane; i0 < e; i0 += 128) {
+    double f1[4][3], f2[4][3];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const long long i = i0 + 32 * w;
+      if (i < e) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { f1[w][k] = bv.f1[3 * i + k]; f2[w][k] = bv.f2[3 * i + k]; }
+      }
+    }
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      if (i0 + 32 * w < e) {
+        double g[3], n[3];
+        rot(R, f2[w], g);
+        cross3(f1[w], g, n);
+        M[w][0] = fma(n[0], n[0], M[w][0]); M[w][1] = fma(n[0], n[1], M[w][1]); M[w][2] = fma(n[0], n[2], M[w][2]);
+        M[w][3] = fma(n[1], n[1], M[w][3]); M[w][4] = fma(n[1], n[2], M[w][4]); M[w][5] = fma(n[2], n[2], M[w][5]);
+      }
+    }
+  }
+  double T[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      double v = M[w][k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      t += v;
+    }
+    T[k] = t;
+  }
+  if (lane == 0) {
+    double v[3], lam;
+    sym3_smallest_eigvec(T, v, lam);
+    double *ot = out_t + static_cast<long long>(out_stride) * b;
+    ot[0] = v[0]; ot[1] = v[1]; ot[2] = v[2];
+    if (out_M) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) out_M[6 * b + k] = T[k];
+    }
+  }
+}
+
 }  // namespace pnec

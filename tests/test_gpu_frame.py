@@ -323,3 +323,22 @@ def test_rotation_lm_wide_turns_are_bit_identical(handle):
         np.testing.assert_array_equal(p, full[group])
         np.testing.assert_array_equal(i, info[group])
         np.testing.assert_array_equal(e, ev[group])
+
+
+def test_nec_translation_warp_kernel_is_bit_identical(handle):
+    """Large batches run TranslationFromM(ComposeM(...)) with a warp per pair, small ones with a CTA per
+    pair (pnec_translation.cuh); the sums are combined in the same order, so the same pair gives the
+    same bits in a batch of 1 500 (warp kernel: >= 8 pairs per SM) and in a batch of 40."""
+    counts = np.tile(np.array([130, 1, 64, 257, 2, 33, 96, 512, 129, 5], dtype=np.int64), 150)
+    batch = syn.make_batch(len(counts), 0, seed=41, counts=counts)
+    big, big_m = handle.nec_translation_batch(batch.bvs_host, batch.bvs_target, batch.init_poses, offsets=batch.offsets)
+    k = 40
+    n = int(batch.offsets[k])
+    small, small_m = handle.nec_translation_batch(batch.bvs_host[:n], batch.bvs_target[:n], batch.init_poses[:k],
+                                                  offsets=batch.offsets[: k + 1])
+    np.testing.assert_array_equal(big[:k], small)
+    np.testing.assert_array_equal(big_m[:k], small_m)
+    for b in (0, 3, 7, 1203):
+        sl = slice(int(batch.offsets[b]), int(batch.offsets[b + 1]))
+        rt, rm = oracle.nec_translation(batch.bvs_host[sl], batch.bvs_target[sl], batch.init_poses[b])
+        np.testing.assert_allclose(big_m[b], rm, rtol=1e-12, atol=1e-15)
