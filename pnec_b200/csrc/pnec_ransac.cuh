@@ -827,10 +827,24 @@ __global__ void __launch_bounds__(WPC * 32, MINB) ransac_hyp_kernel(const __grid
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2;
   const int total = args.defer[2], count = args.defer[0];
   const int *list = args.defer + 4;
+  // The first item of a warp is its own index, later ones come from the cursor: a super-round with fewer
+  // items than the grid has warps (clean data: a few hundred) occupies the first CTAs only and the others
+  // leave at once, instead of every CTA of the machine holding its registers and shared memory for one
+  // busy warp (stage on C2 15.0 -> 14.4 ms).
+  // (Tried on top: splitting a block of 8 hypotheses over four warps of two, run with es_lm_group's wide
+  // turns, for super-rounds that do not fill the machine -- stage 14.3 -> 13.9 ms, but the default frame
+  // solve 19.2 -> 20.5 ms: a second 100 KB instantiation of the hypothesis competes for the instruction
+  // caches with every other kernel in flight.  What a small super-round costs is the cold pass of each
+  // warp through that code, not the slowest Levenberg-Marquardt run.)
+  const int nwarps = static_cast<int>(gridDim.x) * WPC;
+  bool first_item = true;
   for (;;) {
-    int w = 0;
-    if (lane == 0) w = atomicAdd(args.defer + 1, 1);
-    w = __shfl_sync(0xffffffffu, w, 0);
+    int w = static_cast<int>(blockIdx.x) * WPC + warp;
+    if (!first_item) {
+      if (lane == 0) w = nwarps + atomicAdd(args.defer + 1, 1);
+      w = __shfl_sync(0xffffffffu, w, 0);
+    }
+    first_item = false;
     if (w >= total) return;
     // slot with blk_prefix[slot] <= w < blk_prefix[slot + 1]
     int lo = 0, hi = count;
