@@ -92,6 +92,7 @@ struct Config {
   int no_lm_ahead = 0;
   int no_stager = 0;
   int ransac_warps = 0;
+  int solve_order = 1;         // solve_slots_kernel: start the worst-conditioned pairs first
   int es_wide_max_pairs = -1;  // rotation LM: two pairs per warp up to this many pairs (-1: by SM count)
   int ransac_defer = -1;  // PNEC_B200_RANSAC_DEFER: iterations after which pass 1 hands a pair to pass 2 (0: never)
   int ransac_split = 1;   // PNEC_B200_RANSAC_SPLIT: pass 1 of large batches as three kernels per round (0: one kernel)
@@ -120,6 +121,7 @@ struct Config {
     scf_warps = env_int("PNEC_B200_SCF_WARPS", 0);
     solve_warps = env_int("PNEC_B200_SOLVE_WARPS", 0);
     solve_slots = env_int("PNEC_B200_SOLVE_SLOTS", 1);
+    solve_order = env_int("PNEC_B200_SOLVE_ORDER", 1);
     stream_min_n = env_int("PNEC_B200_STREAM_MIN_N", 896);
     copy_threads = env_int("PNEC_B200_COPY_THREADS", 0);
   }
@@ -635,11 +637,24 @@ int launch_solve_slots_v(pnec_handle *h, SolveArgs a, long long need, cudaStream
   int rc = slot_counter(h, stream, &a.work_counter, &start);
   if (rc != PNEC_OK) return rc;
   if (!start) return PNEC_OK;
-  PNEC_CUDA(start->ensure(static_cast<size_t>(a.bv.num_problems) * 80));
+  // per stream: start points [B][10], then order [B], bins [B], histogram and bin offsets (ints)
+  const size_t nbp = static_cast<size_t>(a.bv.num_problems);
+  PNEC_CUDA(start->ensure(nbp * 80 + nbp * 8 + 2 * kOrderBins * sizeof(int)));
   a.start_state = static_cast<double *>(start->p);
   solve_prep_kernel<<<static_cast<unsigned>((a.bv.num_problems + 127) / 128), 128, 0, stream>>>(a.bv.poses, a.bv.num_problems, a.start_state);
   PNEC_CUDA(cudaGetLastError());
   h->launches++;
+  a.work_order = nullptr;
+  if (a.work_counter && h->cfg.solve_order && a.bv.num_problems < 0x7fffffffLL) {
+    // worst-conditioned pairs first (pnec_solve_slots.cuh): two small launches
+    int *order = reinterpret_cast<int *>(a.start_state + 10 * nbp), *bins = order + nbp, *hist = bins + nbp, *cursor = hist + kOrderBins;
+    PNEC_CUDA(cudaMemsetAsync(hist, 0, 2 * kOrderBins * sizeof(int), stream));
+    solve_score_kernel<V><<<static_cast<unsigned>((a.bv.num_problems + 3) / 4), 128, 0, stream>>>(a.bv, a.o.regularization, a.start_state, bins, hist);
+    solve_order_scatter_kernel<<<static_cast<unsigned>((a.bv.num_problems + 255) / 256), 256, 0, stream>>>(bins, hist, cursor, order, a.bv.num_problems);
+    PNEC_CUDA(cudaGetLastError());
+    h->launches += 2;
+    a.work_order = order;
+  }
   a.cap_elems = static_cast<int>(cap);
   a.use_bulk = 1;
   a.dbg = nullptr;

@@ -23,6 +23,7 @@ struct SolveArgs {
   long long *dbg; // PNEC_PHASE_TIMING builds only: per-CTA cycle counters
   unsigned int *work_counter;  // solve_slots_kernel: {next pair, CTAs that have left}; nullptr = static partition
   double *start_state;         // solve_slots_kernel: [B][10] (theta, phi, q, sin/cos of theta and phi), solve_prep_kernel
+  const int *work_order;       // solve_slots_kernel: ticket k of the work counter is pair work_order[k] (nullptr: pair k)
 };
 
 // PNECCeres::InitValues(orientation, translation) (pnec_ceres.cc:188-192): the start point

@@ -199,6 +199,103 @@ __global__ void __launch_bounds__(128) solve_prep_kernel(const double *__restric
   for (int i = 0; i < 4; ++i) o[6 + i] = sc[i];
 }
 
+// ---- the order the pairs are started in
+//
+// A pair costs ~7 k cycles per LM iteration whatever the machine does around it, so one that runs into
+// max_num_iterations (50: 355 k cycles = 0.18 ms; three of the 10 000 pairs of C2) ends 0.18 ms after
+// it was STARTED, and in index order the last of them starts anywhere in a 0.26 ms kernel.  Which pairs
+// those are shows at the start point: they are the ones whose normal equations are badly conditioned.
+// The ratio of the smallest to the largest diagonal entry of J^T J over the pair's first 32
+// correspondences -- one residual row per lane, 6 % of the data -- puts every pair of C2 with 20 or more
+// iterations among the worst-conditioned 9 % (measured with the oracle, two seeds; cost, gradient norm
+// or Jacobi-scaled measures do not separate them).  The pairs are therefore started in ascending order of that
+// ratio (counting sort over quarter-octave bins): longest expected run first, the three-iteration bulk
+// last.  Per-pair results do not depend on the order.
+constexpr int kOrderBins = 264;  // quarter octaves from 2^-64 (and below) to 1
+
+template <int V>
+__global__ void __launch_bounds__(128) solve_score_kernel(BatchView bv, double reg, const double *__restrict__ start_state,
+                                                          int *__restrict__ bins, int *__restrict__ hist) {
+  const int lane = threadIdx.x & 31;
+  const long long b = static_cast<long long>(blockIdx.x) * 4 + (threadIdx.x >> 5);
+  if (b >= bv.num_problems) return;
+  long long s, e;
+  problem_range(bv, b, s, e);
+  const int n = static_cast<int>(min(e - s, 32LL));
+  double d[5] = {0, 0, 0, 0, 0};
+  if (lane < n) {
+    PoseConst pc;
+    make_pose_const(start_state + 10 * b, pc);
+    const long long i = s + lane;
+    double f1[3], f2[3], c9[9], ct[6] = {0, 0, 0, 0, 0, 0}, ch[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { f1[k] = bv.f1[3 * i + k]; f2[k] = bv.f2[3 * i + k]; }
+    if (VariantTraits<V>::kHasCt) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) c9[k] = bv.ct[9 * i + k];
+      pack_sym(c9, ct);
+    }
+    if (VariantTraits<V>::kHasCh) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) c9[k] = bv.ch[9 * i + k];
+      pack_sym(c9, ch);
+    }
+    double r, row[5];
+    residual_row<V>(pc, reg, f1, f2, ct, ch, r, row);
+    d[0] = row[0] * row[0]; d[1] = row[1] * row[1];
+    d[2] = 4.0 * row[2] * row[2]; d[3] = 4.0 * row[3] * row[3]; d[4] = 4.0 * row[4] * row[4];  // tangent columns are 2 dr/dw
+  }
+#pragma unroll
+  for (int k = 0; k < 5; ++k)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d[k] += __shfl_xor_sync(0xffffffffu, d[k], o);
+  if (lane == 0) {
+    const double lo = fmin(fmin(d[0], d[1]), fmin(d[2], fmin(d[3], d[4])));
+    const double hi = fmax(fmax(d[0], d[1]), fmax(d[2], fmax(d[3], d[4])));
+    int bin = 0;  // empty pairs, zero or non-finite rows: first
+    if (hi > 0.0 && lo > 0.0 && hi < DBL_MAX) {
+      const double ratio = lo / hi;  // in (0, 1]
+      const long long q = (__double_as_longlong(ratio) >> 50) - ((1023LL - 64LL) << 2);  // quarter octaves above 2^-64
+      bin = static_cast<int>(q < 1 ? 1 : (q > kOrderBins - 1 ? kOrderBins - 1 : q));
+    }
+    bins[b] = bin;
+    atomicAdd(hist + bin, 1);
+  }
+}
+
+// Counting sort by bin: every CTA forms the exclusive prefix of the histogram for itself (264 entries) and
+// its threads take their places from per-bin cursors (`cursor` zeroed with the histogram before the call).
+__global__ void __launch_bounds__(256) solve_order_scatter_kernel(const int *__restrict__ bins, const int *__restrict__ hist,
+                                                                  int *__restrict__ cursor, int *__restrict__ order,
+                                                                  long long num_problems) {
+  __shared__ int s_off[kOrderBins];
+  __shared__ int s_wsum[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // exclusive scan of hist[0 .. 263]: 256 threads take one entry each, the last eight entries follow serially
+  const int v = hist[tid];
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += u;
+  }
+  if (lane == 31) s_wsum[warp] = incl;
+  __syncthreads();
+  int base = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) base += w < warp ? s_wsum[w] : 0;
+  s_off[tid] = base + incl - v;
+  if (tid == 255) {
+    int run = base + incl;
+    for (int k = 256; k < kOrderBins; ++k) { s_off[k] = run; run += hist[k]; }
+  }
+  __syncthreads();
+  const long long b = static_cast<long long>(blockIdx.x) * blockDim.x + tid;
+  if (b >= num_problems) return;
+  const int bin = bins[b];
+  order[s_off[bin] + atomicAdd(cursor + bin, 1)] = static_cast<int>(b);
+}
+
 // The owner warp of one slot: claim, load, repack, LM loop, result; until the batch is exhausted.
 template <int V, int P, int G>
 __device__ __forceinline__ void slot_owner_warp(const SolveArgs &args, int slot, SlotCtl &ctl, double *base,
@@ -216,6 +313,7 @@ __device__ __forceinline__ void slot_owner_warp(const SolveArgs &args, int slot,
     unsigned int v = 0;
     if (lane == 0) v = atomicAdd(args.work_counter, 1u);
     b = __shfl_sync(0xffffffffu, v, 0);
+    if (args.work_order && b < args.bv.num_problems) b = args.work_order[b];
   }
   double start_v = (lane < 10 && b < args.bv.num_problems) ? args.start_state[10 * b + lane] : 0.0;
   SLOT_PROBE_DECL();
@@ -271,7 +369,10 @@ __device__ __forceinline__ void slot_owner_warp(const SolveArgs &args, int slot,
         ctl.mode = kPassFull;
         slot_post(tk, slot);
       }
-      if (args.work_counter) b_next = __shfl_sync(0xffffffffu, claimed, 0);
+      if (args.work_counter) {
+        b_next = __shfl_sync(0xffffffffu, claimed, 0);
+        if (args.work_order && b_next < args.bv.num_problems) b_next = args.work_order[b_next];
+      }
       if (b_next < args.bv.num_problems) {
         if (lane == 0) slot_prefetch<V>(args.bv, b_next);
         if (lane < 10) start_v = args.start_state[10 * b_next + lane];
@@ -328,7 +429,10 @@ __device__ __forceinline__ void slot_owner_warp(const SolveArgs &args, int slot,
     probe_acc[5] += clock64() - t_pair;
 #endif
     if (n <= 0) {  // (nothing was posted: the claim and the next start point are still to be read)
-      if (args.work_counter) b_next = __shfl_sync(0xffffffffu, claimed, 0);
+      if (args.work_counter) {
+        b_next = __shfl_sync(0xffffffffu, claimed, 0);
+        if (args.work_order && b_next < args.bv.num_problems) b_next = args.work_order[b_next];
+      }
       if (lane < 10 && b_next < args.bv.num_problems) start_v = args.start_state[10 * b_next + lane];
     }
     b = b_next;

@@ -67,8 +67,10 @@ def assert_same_bits(r0, r1):
 
 
 def test_default_selection_takes_the_slots_kernel_on_c2(per_pair):
-    """The default handle on a C2 batch: 2 launches (start points + slots kernel), the bits of the kernel with
-    a CTA per pair.  (tests/test_gpu_parity.py::test_c2_full_batch_matches_oracle compares this very path
+    """The default handle on a C2 batch: 4 launches (start points, the two kernels that order the pairs
+    by the conditioning of their normal equations, slots kernel), the bits of the kernel with a CTA per
+    pair -- and of the slots kernel taking the pairs in index order (2 launches).
+    (tests/test_gpu_parity.py::test_c2_full_batch_matches_oracle compares this very path
     with the oracle: the default handle takes it for 10 000 x 512.)"""
     import torch
 
@@ -78,8 +80,14 @@ def test_default_selection_takes_the_slots_kernel_on_c2(per_pair):
     n0 = h.launch_count
     res = h.solve_batch(*a, n_per_problem=512)
     torch.cuda.synchronize()
-    assert h.launch_count - n0 == 2
+    assert h.launch_count - n0 == 4
     assert_same_bits(per_pair.solve_batch(*a, n_per_problem=512), res)
+    plain = handle_with(PNEC_B200_SOLVE_ORDER=0)
+    n0 = plain.launch_count
+    res_plain = plain.solve_batch(*a, n_per_problem=512)
+    torch.cuda.synchronize()
+    assert plain.launch_count - n0 == 2
+    assert_same_bits(res_plain, res)
     its = res.iterations.cpu().numpy()
     assert its.max() == 50 and 3.0 < its.mean() < 3.6  # the batch of bench.py: a few pairs run into max_num_iterations
 
