@@ -92,7 +92,8 @@ struct Config {
   int no_lm_ahead = 0;
   int no_stager = 0;
   int ransac_warps = 0;
-  int solve_order = 1;         // solve_slots_kernel: start the worst-conditioned pairs first
+  int solve_order = 1;         // refinement: start the worst-conditioned pairs first
+  int solve_order_min_pairs = -1;  // ... in the kernels with a CTA per pair from this many pairs (-1: 32 per SM)
   int es_wide_max_pairs = -1;  // rotation LM: two pairs per warp up to this many pairs (-1: by SM count)
   int ransac_defer = -1;  // PNEC_B200_RANSAC_DEFER: iterations after which pass 1 hands a pair to pass 2 (0: never)
   int ransac_split = 1;   // PNEC_B200_RANSAC_SPLIT: pass 1 of large batches as three kernels per round (0: one kernel)
@@ -122,6 +123,7 @@ struct Config {
     solve_warps = env_int("PNEC_B200_SOLVE_WARPS", 0);
     solve_slots = env_int("PNEC_B200_SOLVE_SLOTS", 1);
     solve_order = env_int("PNEC_B200_SOLVE_ORDER", 1);
+    solve_order_min_pairs = env_int("PNEC_B200_SOLVE_ORDER_MIN_PAIRS", -1);
     stream_min_n = env_int("PNEC_B200_STREAM_MIN_N", 896);
     copy_threads = env_int("PNEC_B200_COPY_THREADS", 0);
   }
@@ -622,6 +624,30 @@ int slots_capacity(pnec_handle *h, int *static_smem) {
   return static_cast<int>(std::max<long long>(0, cap & ~31LL));
 }
 
+// Start points (solve_prep_kernel) and the order the pairs are started in (worst-conditioned first,
+// pnec_solve_slots.cuh) in the stream's scratch: start points [B][10], then order [B], bins [B],
+// histogram and cursors (ints).  a.work_order stays nullptr when the order is switched off.
+template <int V>
+int prepare_start_and_order(pnec_handle *h, SolveArgs &a, DevBuf *start, cudaStream_t stream) {
+  const size_t nbp = static_cast<size_t>(a.bv.num_problems);
+  PNEC_CUDA(start->ensure(nbp * 80 + nbp * 8 + 2 * kOrderBins * sizeof(int)));
+  a.start_state = static_cast<double *>(start->p);
+  solve_prep_kernel<<<static_cast<unsigned>((a.bv.num_problems + 127) / 128), 128, 0, stream>>>(a.bv.poses, a.bv.num_problems, a.start_state);
+  PNEC_CUDA(cudaGetLastError());
+  h->launches++;
+  a.work_order = nullptr;
+  if (h->cfg.solve_order && a.bv.num_problems < 0x7fffffffLL) {
+    int *order = reinterpret_cast<int *>(a.start_state + 10 * nbp), *bins = order + nbp, *hist = bins + nbp, *cursor = hist + kOrderBins;
+    PNEC_CUDA(cudaMemsetAsync(hist, 0, 2 * kOrderBins * sizeof(int), stream));
+    solve_score_kernel<V><<<static_cast<unsigned>((a.bv.num_problems + 3) / 4), 128, 0, stream>>>(a.bv, a.o.regularization, a.start_state, bins, hist);
+    solve_order_scatter_kernel<<<static_cast<unsigned>((a.bv.num_problems + 255) / 256), 256, 0, stream>>>(bins, hist, cursor, order, a.bv.num_problems);
+    PNEC_CUDA(cudaGetLastError());
+    h->launches += 2;
+    a.work_order = order;
+  }
+  return PNEC_OK;
+}
+
 template <int V>
 int launch_solve_slots_v(pnec_handle *h, SolveArgs a, long long need, cudaStream_t stream, bool *done) {
   static int cap_max = -1, static_smem = 0;  // per process: the same kernel image on every device of a box
@@ -637,24 +663,8 @@ int launch_solve_slots_v(pnec_handle *h, SolveArgs a, long long need, cudaStream
   int rc = slot_counter(h, stream, &a.work_counter, &start);
   if (rc != PNEC_OK) return rc;
   if (!start) return PNEC_OK;
-  // per stream: start points [B][10], then order [B], bins [B], histogram and bin offsets (ints)
-  const size_t nbp = static_cast<size_t>(a.bv.num_problems);
-  PNEC_CUDA(start->ensure(nbp * 80 + nbp * 8 + 2 * kOrderBins * sizeof(int)));
-  a.start_state = static_cast<double *>(start->p);
-  solve_prep_kernel<<<static_cast<unsigned>((a.bv.num_problems + 127) / 128), 128, 0, stream>>>(a.bv.poses, a.bv.num_problems, a.start_state);
-  PNEC_CUDA(cudaGetLastError());
-  h->launches++;
-  a.work_order = nullptr;
-  if (a.work_counter && h->cfg.solve_order && a.bv.num_problems < 0x7fffffffLL) {
-    // worst-conditioned pairs first (pnec_solve_slots.cuh): two small launches
-    int *order = reinterpret_cast<int *>(a.start_state + 10 * nbp), *bins = order + nbp, *hist = bins + nbp, *cursor = hist + kOrderBins;
-    PNEC_CUDA(cudaMemsetAsync(hist, 0, 2 * kOrderBins * sizeof(int), stream));
-    solve_score_kernel<V><<<static_cast<unsigned>((a.bv.num_problems + 3) / 4), 128, 0, stream>>>(a.bv, a.o.regularization, a.start_state, bins, hist);
-    solve_order_scatter_kernel<<<static_cast<unsigned>((a.bv.num_problems + 255) / 256), 256, 0, stream>>>(bins, hist, cursor, order, a.bv.num_problems);
-    PNEC_CUDA(cudaGetLastError());
-    h->launches += 2;
-    a.work_order = order;
-  }
+  rc = prepare_start_and_order<V>(h, a, start, stream);
+  if (rc != PNEC_OK) return rc;
   a.cap_elems = static_cast<int>(cap);
   a.use_bulk = 1;
   a.dbg = nullptr;
@@ -686,6 +696,25 @@ int launch_solve_slots_v(pnec_handle *h, SolveArgs a, long long need, cudaStream
 #endif
   *done = true;
   return PNEC_OK;
+}
+
+// The kernels with a CTA per pair take their pair from the same order (the hardware starts CTAs in
+// blockIdx order) once the batch is several waves deep; below that the three extra launches cost more
+// than a late straggler.
+int order_for_cta_kernels(pnec_handle *h, SolveArgs &a, int variant, cudaStream_t stream) {
+  a.work_order = nullptr;
+  const long long min_pairs = h->cfg.solve_order_min_pairs >= 0 ? h->cfg.solve_order_min_pairs : 32LL * h->sm_count;
+  if (!h->cfg.solve_order || a.bv.num_problems < min_pairs) return PNEC_OK;
+  unsigned int *ctr = nullptr;
+  DevBuf *start = nullptr;
+  int rc = slot_counter(h, stream, &ctr, &start);
+  if (rc != PNEC_OK || !start) return rc;
+  switch (variant) {
+    case PNEC_VARIANT_NEC: return prepare_start_and_order<PNEC_VARIANT_NEC>(h, a, start, stream);
+    case PNEC_VARIANT_TARGET: return prepare_start_and_order<PNEC_VARIANT_TARGET>(h, a, start, stream);
+    case PNEC_VARIANT_HOST: return prepare_start_and_order<PNEC_VARIANT_HOST>(h, a, start, stream);
+    default: return prepare_start_and_order<PNEC_VARIANT_SYMMETRIC>(h, a, start, stream);
+  }
 }
 
 int launch_solve(pnec_handle *h, const SolveArgs &a0, int variant, long long max_n,
@@ -720,6 +749,8 @@ int launch_solve(pnec_handle *h, const SolveArgs &a0, int variant, long long max
     a.use_bulk = 1;
     a.cap_elems = 0;
     a.dbg = nullptr;
+    const int orc = order_for_cta_kernels(h, a, variant, stream);
+    if (orc != PNEC_OK) return orc;
     switch (variant) {
       case PNEC_VARIANT_NEC: return launch_solve_stream_v<PNEC_VARIANT_NEC>(h, a, stream);
       case PNEC_VARIANT_TARGET: return launch_solve_stream_v<PNEC_VARIANT_TARGET>(h, a, stream);
@@ -748,6 +779,8 @@ int launch_solve(pnec_handle *h, const SolveArgs &a0, int variant, long long max
 #endif
   const size_t dyn = static_cast<size_t>(cap_elems) * bpc;
   int rc;
+  rc = order_for_cta_kernels(h, a, variant, stream);
+  if (rc != PNEC_OK) return rc;
   switch (variant) {
     case PNEC_VARIANT_NEC: rc = launch_solve_v<PNEC_VARIANT_NEC>(h, a, nw, dyn, stream); break;
     case PNEC_VARIANT_TARGET: rc = launch_solve_v<PNEC_VARIANT_TARGET>(h, a, nw, dyn, stream); break;

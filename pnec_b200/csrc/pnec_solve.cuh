@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) solve_kernel(const __grid_const
   __shared__ double s_part[NW][kAccPad];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long b = blockIdx.x;
+  const long long b = args.work_order ? args.work_order[blockIdx.x] : blockIdx.x;  // (pnec_solve_slots.cuh: the order)
   long long s, e;
   problem_range(args.bv, b, s, e);
   const int n = static_cast<int>(e - s);
@@ -227,7 +227,7 @@ solve_stream_kernel(const __grid_constant__ SolveArgs args) {
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler
-  const long long b = blockIdx.x;
+  const long long b = args.work_order ? args.work_order[blockIdx.x] : blockIdx.x;  // (pnec_solve_slots.cuh: the order)
   long long s, e;
   problem_range(args.bv, b, s, e);
   const int n = static_cast<int>(e - s);

@@ -21,7 +21,7 @@ def timed(fn, reps=30, warm=5):
     return e0.elapsed_time(e1) / reps
 h0, h1 = handle(0), handle(1)
 o = api.default_opts(api.TARGET)
-for B, N, seed in ((10000, 512, 1), (10000, 512, 2), (10000, 512, 3), (10000, 512, 7), (12500, 256, 1), (40000, 512, 1)):
+for B, N, seed in ((10000, 512, 1), (10000, 512, 2), (10000, 512, 3), (10000, 512, 7), (12500, 256, 1), (12500, 256, 2), (2500, 512, 1), (5000, 200, 1), (4000, 1000, 1), (40000, 512, 1)):
     b = syn.make_batch(B, N, seed=seed)
     a = (dev(b.bvs_host), dev(b.bvs_target), dev(b.covs_target), None, dev(b.init_poses), o)
     r = h1.solve_batch(*a, n_per_problem=N)
