@@ -378,7 +378,8 @@ def run_b200(args):
     achieved = B * N * BYTES_PER_CORR / (k1_ms * 1e-3) / 1e9
     # `roofline` is the kernel BASELINE.json's second metric names (the fused residual + Jacobian +
     # JtJ kernel, K1).  It is launched by this measurement loop, not by the timed solve step, whose
-    # kernel (solve_slots_kernel, after the one-thread-per-pair start-point kernel: 2 launches per step)
+    # kernel (solve_slots_kernel, after the start-point kernel and the two small kernels that order the
+    # pairs by the conditioning of their normal equations: 4 launches per step)
     # is reported next to it as `roofline_step_kernel`.
     roofline = {"bound": "hbm", "kernel": "eval_warp_kernel (fused residual + Jacobian + JtJ/Jtr, K1)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -387,14 +388,15 @@ def run_b200(args):
                 "in_timed_step": False}
     step_gbs = B * N * BYTES_PER_CORR / (ms_per_step * 1e-3) / 1e9
     roofline_step = {"bound": "hbm", "kernel": "solve_slots_kernel (whole LM solve, inputs read from HBM once; "
-                                                "preceded by solve_prep_kernel, a few microseconds)",
+                                                "preceded by solve_prep_kernel, solve_score_kernel and solve_order_scatter_kernel, "
+                                                "~25 microseconds together, inside the timed step)",
                      "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak,
                      "traffic": ncu_traffic_bytes("solve"), "ms_per_launch": ms_per_step,
                      "algorithmic_bytes_per_launch": B * N * BYTES_PER_CORR,
                      "mean_lm_iterations": iters,
                      "note": "latency bound, not HBM bound: ~4.2 evaluations + ~3.3 serial LM updates per pair on "
-                             "one pass of data, four pairs resident per SM, and a tail of pairs that run into "
-                             "max_num_iterations (DESIGN.md section 3)"}
+                             "one pass of data, four pairs resident per SM; the pairs that run into max_num_iterations "
+                             "(0.18 ms each) are started first (DESIGN.md section 3)"}
 
     # ---- end to end through the C-ABI with HOST buffers (pinned), copies inside the timed region
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()

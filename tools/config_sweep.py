@@ -96,4 +96,4 @@ row = dict(config="NEC translation (ComposeM + TranslationFromM), 10000x512", po
            points_per_s=10000 / ms * 1e3, GBps=10000 * 512 * 48 / ms / 1e6, algorithmic_bytes_per_point=512 * 48)
 rows.append(row); print(json.dumps(row), flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(rows, open("gpurun_out/configs_r02.json", "w"), indent=1)
+json.dump(rows, open(os.environ.get("CONFIGS_OUT", "gpurun_out/configs_r02.json"), "w"), indent=1)
