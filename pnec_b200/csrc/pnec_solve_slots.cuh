@@ -224,8 +224,24 @@ __global__ void __launch_bounds__(128) solve_score_kernel(BatchView bv, double r
   const int n = static_cast<int>(min(e - s, 32LL));
   double d[5] = {0, 0, 0, 0, 0};
   if (lane < n) {
+    // pose constants from the start point and the sines / cosines solve_prep_kernel stored with it
+    // (make_pose_const without its two sincos)
+    const double *x = start_state + 10 * b;
+    const double st = x[6], ct_ = x[7], sp = x[8], cp = x[9];
     PoseConst pc;
-    make_pose_const(start_state + 10 * b, pc);
+    pc.t[0] = st * cp;  pc.t[1] = st * sp;  pc.t[2] = ct_;
+    pc.tth[0] = ct_ * cp; pc.tth[1] = ct_ * sp; pc.tth[2] = -st;
+    pc.tph[0] = -st * sp; pc.tph[1] = st * cp; pc.tph[2] = 0.0;
+    {
+      const double qx = x[2], qy = x[3], qz = x[4], qw = x[5];
+      const double tx = 2.0 * qx, ty = 2.0 * qy, tz = 2.0 * qz;
+      const double twx = tx * qw, twy = ty * qw, twz = tz * qw;
+      const double txx = tx * qx, txy = ty * qx, txz = tz * qx;
+      const double tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
+      pc.R[0] = 1.0 - (tyy + tzz); pc.R[1] = txy - twz;         pc.R[2] = txz + twy;
+      pc.R[3] = txy + twz;         pc.R[4] = 1.0 - (txx + tzz); pc.R[5] = tyz - twx;
+      pc.R[6] = txz - twy;         pc.R[7] = tyz + twx;         pc.R[8] = 1.0 - (txx + tyy);
+    }
     const long long i = s + lane;
     double f1[3], f2[3], c9[9], ct[6] = {0, 0, 0, 0, 0, 0}, ch[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
