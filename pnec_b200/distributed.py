@@ -68,6 +68,11 @@ def gather_results(local, bounds: List[Tuple[int, int]], group=None):
     sizes = [b1 - b0 for b0, b1 in bounds]
     assert len(sizes) == world and local.shape[0] == sizes[dist.get_rank(group)]
     m = max(sizes) if sizes else 0
+    if m > 0 and all(s == m for s in sizes):
+        # equal shards (the usual case): one collective straight into the result, no padding, no concatenation
+        out = local.new_empty((world * m,) + tuple(local.shape[1:]))
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
     padded = local.new_zeros((m,) + tuple(local.shape[1:]))
     padded[: local.shape[0]] = local
     parts = [torch.empty_like(padded) for _ in range(world)]

@@ -80,3 +80,33 @@ def test_sharded_frame_solve_matches_single_process(tmp_path):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), True, str(tmp_path), True), nprocs=world, join=True)
     assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
+
+
+def _gather_worker(rank, world, port, out_dir):
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    from pnec_b200 import distributed
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        for B in (8, 7, 2, 1):  # equal shards (one collective into the result) and unequal ones (padded)
+            bounds = distributed.shard_bounds(B, world)
+            b0, b1 = bounds[rank]
+            full_p = torch.arange(B * 7, dtype=torch.float64).reshape(B, 7) * 0.5
+            full_s = torch.arange(B, dtype=torch.int32) * 3
+            got_p = distributed.gather_results(full_p[b0:b1].clone(), bounds)
+            got_s = distributed.gather_results(full_s[b0:b1].clone(), bounds)
+            assert torch.equal(got_p, full_p) and torch.equal(got_s, full_s) and got_s.dtype == torch.int32
+        open(os.path.join(out_dir, f"ok{rank}"), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_results_equal_and_unequal_shards(tmp_path):
+    world = 2
+    mp.spawn(_gather_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
