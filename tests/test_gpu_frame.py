@@ -315,7 +315,6 @@ def test_rotation_lm_wide_turns_are_bit_identical(handle):
     n = 160
     batch = syn.make_batch(96, n, seed=77, noise_level=1.0)
     full, info, ev = handle.eigensolver_batch(batch.bvs_host, batch.bvs_target, batch.init_poses, n_per_problem=n)
-    assert len(set(info.tolist())) >= 1
     for group in ([0], [5], [37, 38], [90, 3], list(range(8, 11))):
         rows = np.concatenate([np.arange(b * n, (b + 1) * n) for b in group])
         p, i, e = handle.eigensolver_batch(batch.bvs_host[rows], batch.bvs_target[rows], batch.init_poses[group],
